@@ -1,0 +1,254 @@
+// common.cuh -- shared types, error plumbing and device helpers of libgranges_b200.
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+#include <stdio.h>
+#include <string.h>
+
+#include "granges_b200.h"
+
+typedef uint8_t u8;
+typedef uint32_t u32;
+typedef uint64_t u64;
+typedef int64_t i64;
+typedef unsigned __int128 u128;
+typedef __int128 i128;
+
+#define GRB_FULL 0xffffffffu
+
+// ---- context -------------------------------------------------------------
+
+struct grb_ctx {
+    int device;
+    int sm_count;
+    cudaStream_t own_stream;
+    cudaStream_t stream;
+    cudaMemPool_t pool;
+    u64 launches;
+    int tile_mode;  // 1 = TMA-staged smem windows (default), 0 = global binary search only (debug)
+    char err[512];
+};
+
+int grb_fail(grb_ctx *ctx, int code, const char *fmt, ...);
+
+#define GRB_CUDA(ctx, expr)                                                                         \
+    do {                                                                                            \
+        cudaError_t _e = (expr);                                                                    \
+        if (_e != cudaSuccess)                                                                      \
+            return grb_fail((ctx), _e == cudaErrorMemoryAllocation ? GRB_ERR_OOM : GRB_ERR_CUDA,    \
+                            "%s:%d: %s: %s", __FILE__, __LINE__, #expr, cudaGetErrorString(_e));    \
+    } while (0)
+
+#define GRB_TRY(expr)          \
+    do {                       \
+        int _rc = (expr);      \
+        if (_rc != GRB_OK) return _rc; \
+    } while (0)
+
+// Count + check one kernel launch.
+#define GRB_LAUNCHED(ctx)                                                                     \
+    do {                                                                                      \
+        (ctx)->launches++;                                                                    \
+        cudaError_t _e = cudaGetLastError();                                                  \
+        if (_e != cudaSuccess)                                                                \
+            return grb_fail((ctx), GRB_ERR_CUDA, "%s:%d: kernel launch: %s", __FILE__, __LINE__, \
+                            cudaGetErrorString(_e));                                          \
+    } while (0)
+
+// Stream-ordered temporary device buffer (pool keeps the memory cached, no sync on free).
+struct TempBuf {
+    grb_ctx *ctx = nullptr;
+    void *p = nullptr;
+    size_t bytes = 0;
+    TempBuf() {}
+    TempBuf(const TempBuf &) = delete;
+    TempBuf &operator=(const TempBuf &) = delete;
+    int alloc(grb_ctx *c, size_t nbytes) {
+        release();
+        ctx = c;
+        bytes = nbytes ? nbytes : 16;
+        cudaError_t e = cudaMallocAsync(&p, bytes, c->stream);
+        if (e != cudaSuccess) {
+            p = nullptr;
+            return grb_fail(c, e == cudaErrorMemoryAllocation ? GRB_ERR_OOM : GRB_ERR_CUDA,
+                            "cudaMallocAsync(%zu bytes): %s", bytes, cudaGetErrorString(e));
+        }
+        return GRB_OK;
+    }
+    void release() {
+        if (p) cudaFreeAsync(p, ctx->stream);
+        p = nullptr;
+    }
+    template <typename T>
+    T *as() const {
+        return (T *)p;
+    }
+    ~TempBuf() { release(); }
+};
+
+// An input that may live on the host or on the device: dev() is always a device pointer.
+struct InBuf {
+    TempBuf tmp;
+    const void *d = nullptr;
+    int stage(grb_ctx *ctx, const void *src, size_t bytes);
+    template <typename T>
+    const T *as() const {
+        return (const T *)d;
+    }
+};
+
+// An output that may live on the host or on the device: kernels write dev(); finish() copies back.
+struct OutBuf {
+    TempBuf tmp;
+    void *d = nullptr;
+    void *host = nullptr;
+    size_t bytes = 0;
+    int stage(grb_ctx *ctx, void *dst, size_t nbytes);
+    int finish(grb_ctx *ctx);  // enqueue D2H if the destination is a host buffer
+    template <typename T>
+    T *as() const {
+        return (T *)d;
+    }
+};
+
+bool grb_is_device_ptr(const void *p);
+
+// ---- index ----------------------------------------------------------------
+
+// How SUM / MEAN are answered for one index.
+enum { GRB_SUM_SWEEP = 0, GRB_SUM_COMPACT = 1, GRB_SUM_WIDE = 2 };
+
+#define GRB_BASE_SHIFT 8  // compact mode: one i128 base per 256 rights, i64 local prefixes inside
+#define GRB_BME_SHIFT 6   // block-max-end granularity: 64 rights
+
+struct grb_index {
+    grb_ctx *ctx;
+    u32 n;
+    // start order: sorted by (start, end, data index)
+    u32 *starts;  // n + pad, padded with 0xffffffff
+    u32 *ends;    // n + pad
+    u32 *didx;    // n
+    u32 *bme;     // ceil(n/64): max end of each block of 64 rights (start order)
+    // end order
+    u32 *ends_sorted;  // n + pad, padded with 0xffffffff
+    u32 *perm_e;       // n: position in start order of the i-th smallest end
+    // scores (set_scores)
+    bool has_scores, has_nulls, has_nan;
+    u64 n_data;
+    double *score_a;  // n, start order; None -> 0.0
+    u32 *vbits_a;     // ceil(n/32) validity bits (start order), only if has_nulls
+    u32 *vcnt_a;      // n+1 prefix count of valid scores (start order), only if has_nulls
+    u32 *vcnt_b;      // n+1 prefix count of valid scores (end order), only if has_nulls
+    int sum_mode;
+    int e0;       // fixed-point unit = 2^e0
+    i64 *loc_a;   // compact: n+1 local prefixes (start order)
+    i64 *loc_b;   // compact: n+1 local prefixes (end order)
+    i128 *base_a; // compact: (n>>8)+1 block bases;  wide: n+1 full prefixes
+    i128 *base_b;
+};
+
+// Per-seqname view handed to the kernels (one entry per seqname of a batch).
+struct SeqDev {
+    const u32 *starts, *ends, *ends_sorted, *didx, *bme;
+    const double *score_a;
+    const u32 *vbits_a, *vcnt_a, *vcnt_b;
+    const i64 *loc_a, *loc_b;
+    const i128 *base_a, *base_b;
+    u64 left_begin, left_end;
+    u32 n;
+    u32 tile_begin;
+    int e0;
+    int sum_mode;
+    int has_nulls;
+    int has_scores;
+};
+
+// ---- device helpers ---------------------------------------------------------
+
+#ifdef __CUDACC__
+
+__device__ __forceinline__ u32 lane_id() { return threadIdx.x & 31; }
+
+__device__ __forceinline__ u32 warp_min(u32 v) {
+#pragma unroll
+    for (int o = 16; o; o >>= 1) v = min(v, __shfl_xor_sync(GRB_FULL, v, o));
+    return v;
+}
+__device__ __forceinline__ u32 warp_max(u32 v) {
+#pragma unroll
+    for (int o = 16; o; o >>= 1) v = max(v, __shfl_xor_sync(GRB_FULL, v, o));
+    return v;
+}
+__device__ __forceinline__ u32 warp_sum(u32 v) {
+#pragma unroll
+    for (int o = 16; o; o >>= 1) v += __shfl_xor_sync(GRB_FULL, v, o);
+    return v;
+}
+__device__ __forceinline__ u64 warp_sum64(u64 v) {
+#pragma unroll
+    for (int o = 16; o; o >>= 1) v += __shfl_xor_sync(GRB_FULL, v, o);
+    return v;
+}
+
+// f64 -> fixed point in units of 2^e0.  Exact by construction of e0 (every score is a multiple
+// of 2^e0); zero, and anything the mode selection excluded, maps to 0.
+__device__ __forceinline__ i128 to_fx(double x, int e0) {
+    u64 b = (u64)__double_as_longlong(x);
+    int ex = (int)((b >> 52) & 0x7ff);
+    if (ex == 0 || ex == 0x7ff) return 0;
+    u64 m = (b & ((1ull << 52) - 1)) | (1ull << 52);
+    int sh = (ex - 1075) - e0;
+    u128 v = sh >= 0 ? ((u128)m << sh) : ((u128)m >> (-sh));
+    return (b >> 63) ? -(i128)v : (i128)v;
+}
+
+// fixed point -> nearest f64 (round half to even): the correctly rounded exact sum.
+__device__ __forceinline__ double fx_to_double(i128 v, int e0) {
+    if (v == 0) return 0.0;
+    bool neg = v < 0;
+    u128 m = neg ? (u128)(-v) : (u128)v;
+    u64 hi = (u64)(m >> 64), lo = (u64)m;
+    int nbits = hi ? 128 - __clzll((long long)hi) : 64 - __clzll((long long)lo);
+    int sh = 0;
+    u64 q;
+    if (nbits <= 53) {
+        q = lo;
+    } else {
+        sh = nbits - 53;
+        q = (u64)(m >> sh);
+        u128 rem = m & (((u128)1 << sh) - 1);
+        u128 half = (u128)1 << (sh - 1);
+        if (rem > half || (rem == half && (q & 1))) q++;
+    }
+    double r = (double)q;  // exact: q <= 2^53
+    // scale by 2^(sh+e0) in two exact steps (each factor is a normal power of two)
+    int e = sh + e0;
+    int e1 = e / 2, e2 = e - e1;
+    r *= __longlong_as_double((long long)(u64)(1023 + e1) << 52);
+    r *= __longlong_as_double((long long)(u64)(1023 + e2) << 52);
+    return neg ? -r : r;
+}
+
+__device__ __forceinline__ u64 ld_relaxed_u64(const u64 *p) {
+    u64 v;
+    asm volatile("ld.relaxed.gpu.global.u64 %0, [%1];" : "=l"(v) : "l"(p) : "memory");
+    return v;
+}
+__device__ __forceinline__ void st_relaxed_u64(u64 *p, u64 v) {
+    asm volatile("st.relaxed.gpu.global.u64 [%0], %1;" ::"l"(p), "l"(v) : "memory");
+}
+
+#endif  // __CUDACC__
+
+// ---- internal entry points between translation units -----------------------
+
+// scan.cu: exclusive scan, out[i] = sum(in[0..i)), i in [0, n]; out has n+1 entries when
+// write_total, else n.  Single-pass decoupled look-back.
+int grb_scan_u32_to_u64(grb_ctx *ctx, const u32 *in, u64 *out, size_t n, bool write_total);
+int grb_scan_u32_to_u32(grb_ctx *ctx, const u32 *in, u32 *out, size_t n, bool write_total);
+
+// sort.cu: stable LSD radix sort of (u64 key, u32 value) pairs; skips digits that do not vary and
+// the whole sort when the keys are already non-decreasing.  On return *keys_out / *vals_out point
+// at whichever of the two buffers holds the result.
+int grb_sort_pairs(grb_ctx *ctx, u64 *keys, u32 *vals, u64 *keys_alt, u32 *vals_alt, size_t n, u64 **keys_out,
+                   u32 **vals_out, bool *was_sorted);

@@ -1,0 +1,126 @@
+// ctx.cu -- context, error reporting, host/device buffer staging.
+#include <stdarg.h>
+#include <stdlib.h>
+
+#include "common.cuh"
+
+int grb_fail(grb_ctx *ctx, int code, const char *fmt, ...) {
+    if (ctx) {
+        va_list ap;
+        va_start(ap, fmt);
+        vsnprintf(ctx->err, sizeof(ctx->err), fmt, ap);
+        va_end(ap);
+    }
+    return code;
+}
+
+bool grb_is_device_ptr(const void *p) {
+    cudaPointerAttributes a;
+    cudaError_t e = cudaPointerGetAttributes(&a, p);
+    if (e != cudaSuccess) {
+        cudaGetLastError();
+        return false;
+    }
+    return a.type == cudaMemoryTypeDevice || a.type == cudaMemoryTypeManaged;
+}
+
+int InBuf::stage(grb_ctx *ctx, const void *src, size_t bytes) {
+    if (bytes == 0 || src == nullptr) {
+        d = src;
+        return GRB_OK;
+    }
+    if (grb_is_device_ptr(src)) {
+        d = src;
+        return GRB_OK;
+    }
+    GRB_TRY(tmp.alloc(ctx, bytes));
+    GRB_CUDA(ctx, cudaMemcpyAsync(tmp.p, src, bytes, cudaMemcpyHostToDevice, ctx->stream));
+    d = tmp.p;
+    return GRB_OK;
+}
+
+int OutBuf::stage(grb_ctx *ctx, void *dst, size_t nbytes) {
+    bytes = nbytes;
+    host = nullptr;
+    if (nbytes == 0 || dst == nullptr) {
+        d = dst;
+        return GRB_OK;
+    }
+    if (grb_is_device_ptr(dst)) {
+        d = dst;
+        return GRB_OK;
+    }
+    GRB_TRY(tmp.alloc(ctx, nbytes));
+    d = tmp.p;
+    host = dst;
+    return GRB_OK;
+}
+
+int OutBuf::finish(grb_ctx *ctx) {
+    if (host && bytes) GRB_CUDA(ctx, cudaMemcpyAsync(host, d, bytes, cudaMemcpyDeviceToHost, ctx->stream));
+    return GRB_OK;
+}
+
+extern "C" {
+
+int grb_abi_version(void) { return GRB_ABI_VERSION; }
+
+int grb_ctx_create(int device, grb_ctx **out) {
+    if (!out) return GRB_ERR_INVALID_ARG;
+    *out = nullptr;
+    grb_ctx *ctx = (grb_ctx *)calloc(1, sizeof(grb_ctx));
+    if (!ctx) return GRB_ERR_OOM;
+    ctx->device = device;
+    ctx->tile_mode = 1;
+    const char *tm = getenv("GRB_TILE_MODE");
+    if (tm) ctx->tile_mode = atoi(tm);
+    int ndev = 0;
+    cudaError_t e = cudaGetDeviceCount(&ndev);
+    if (e != cudaSuccess || device < 0 || device >= ndev) {
+        // No CPU fallback: the caller gets a hard error.
+        fprintf(stderr, "granges_b200: no usable CUDA device %d (%s)\n", device,
+                e != cudaSuccess ? cudaGetErrorString(e) : "out of range");
+        free(ctx);
+        return GRB_ERR_CUDA;
+    }
+    if (cudaSetDevice(device) != cudaSuccess || cudaStreamCreateWithFlags(&ctx->own_stream, cudaStreamNonBlocking) != cudaSuccess) {
+        free(ctx);
+        return GRB_ERR_CUDA;
+    }
+    ctx->stream = ctx->own_stream;
+    cudaDeviceGetAttribute(&ctx->sm_count, cudaDevAttrMultiProcessorCount, device);
+    if (cudaDeviceGetDefaultMemPool(&ctx->pool, device) == cudaSuccess) {
+        uint64_t thr = UINT64_MAX;  // keep freed temporaries cached in the pool
+        cudaMemPoolSetAttribute(ctx->pool, cudaMemPoolAttrReleaseThreshold, &thr);
+    }
+    *out = ctx;
+    return GRB_OK;
+}
+
+int grb_ctx_set_stream(grb_ctx *ctx, void *cuda_stream) {
+    if (!ctx) return GRB_ERR_INVALID_ARG;
+    ctx->stream = cuda_stream ? (cudaStream_t)cuda_stream : ctx->own_stream;
+    return GRB_OK;
+}
+
+int grb_ctx_sync(grb_ctx *ctx) {
+    if (!ctx) return GRB_ERR_INVALID_ARG;
+    GRB_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+    return GRB_OK;
+}
+
+void grb_ctx_destroy(grb_ctx *ctx) {
+    if (!ctx) return;
+    cudaSetDevice(ctx->device);
+    cudaStreamSynchronize(ctx->stream);
+    cudaStreamDestroy(ctx->own_stream);
+    free(ctx);
+}
+
+const char *grb_last_error(const grb_ctx *ctx) { return ctx ? ctx->err : "no context"; }
+
+uint64_t grb_ctx_launch_count(const grb_ctx *ctx) { return ctx ? ctx->launches : 0; }
+
+int grb_ctx_sm_count(const grb_ctx *ctx) { return ctx ? ctx->sm_count : 0; }
+
+}  // extern "C"

@@ -1,0 +1,542 @@
+// index.cu -- the right-hand index that replaces COITrees<M>.
+//
+// Reference: COITrees::from(VecRanges<R>) (src/ranges/coitrees.rs:78-84), reached from
+// GRanges::into_coitrees (src/granges.rs:1365-1402); closed/half-open conversion
+// src/ranges/coitrees.rs:172-198; the map_data score extraction src/commands.rs:514-517.
+//
+// Layout in HBM, per seqname (n rights):
+//   start order  starts[n] ends[n] didx[n]      sorted by (start, end, data index) = sort_ranges order
+//                bme[n/64]                      block-max-end (replaces coitrees' subtree_last)
+//   end order    ends_sorted[n] perm_e[n]       the ends sorted on their own
+//   scores       score_a[n] (+ validity bits and prefix counts when some scores are None)
+//   exact sums   fixed-point prefix sums of the scores in BOTH orders, so that
+//                sum(overlapping) = PA[#{r.start < l.end}] - PB[#{r.end <= l.start}]
+//                compact: i64 prefix local to a block of 256 + one i128 base per block
+//                wide:    one i128 prefix per right
+// count_overlaps is the same identity on the two key arrays:
+//   #{r.start < l.end} - #{r.end <= l.start}   (exact: r.end <= l.start implies r.start < l.end).
+#include <math.h>
+#include <stdlib.h>
+
+#include "common.cuh"
+
+namespace {
+
+constexpr u32 PAD = 16;  // sentinel entries after the last key (bulk copies round up to 16 B)
+
+struct BuildFlags {
+    u32 invalid_range;
+    u32 idx_too_big;
+};
+
+__global__ void k_make_keys(const u32 *__restrict__ starts, const u32 *__restrict__ ends, const u32 *__restrict__ order,
+                            size_t n, u64 *__restrict__ keys, u32 *__restrict__ vals, BuildFlags *flags) {
+    size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    u32 src = order ? order[i] : (u32)i;
+    u32 s = starts[src], e = ends[src];
+    if (e <= s || e > 0x7fffffffu) flags->invalid_range = 1;
+    keys[i] = ((u64)s << 32) | e;
+    vals[i] = src;
+}
+
+__global__ void k_idx_keys(const u64 *__restrict__ data_idx, size_t n, u64 *__restrict__ keys, u32 *__restrict__ vals,
+                           BuildFlags *flags) {
+    size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    u64 d = data_idx[i];
+    if (d >= 0xffffffffull) flags->idx_too_big = 1;
+    keys[i] = d;
+    vals[i] = (u32)i;
+}
+
+__global__ void k_unpack_start_order(const u64 *__restrict__ keys, const u32 *__restrict__ perm,
+                                     const u64 *__restrict__ data_idx, size_t n, u32 *__restrict__ starts,
+                                     u32 *__restrict__ ends, u32 *__restrict__ didx, u64 *__restrict__ keys2,
+                                     u32 *__restrict__ vals2) {
+    size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n + PAD) return;
+    if (i >= n) {
+        starts[i] = 0xffffffffu;
+        ends[i] = 0xffffffffu;
+        return;
+    }
+    u64 k = keys[i];
+    u32 p = perm[i];
+    starts[i] = (u32)(k >> 32);
+    ends[i] = (u32)k;
+    didx[i] = data_idx ? (u32)data_idx[p] : p;
+    keys2[i] = (u64)(u32)k;
+    vals2[i] = (u32)i;
+}
+
+__global__ void k_unpack_end_order(const u64 *__restrict__ keys2, const u32 *__restrict__ vals2, size_t n,
+                                   u32 *__restrict__ ends_sorted, u32 *__restrict__ perm_e) {
+    size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n + PAD) return;
+    if (i >= n) {
+        ends_sorted[i] = 0xffffffffu;
+        return;
+    }
+    ends_sorted[i] = (u32)keys2[i];
+    perm_e[i] = vals2[i];
+}
+
+__global__ void k_block_max_end(const u32 *__restrict__ ends, size_t n, u32 *__restrict__ bme) {
+    // one warp per block of 64 rights
+    size_t b = ((size_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+    size_t nb = (n + 63) >> GRB_BME_SHIFT;
+    if (b >= nb) return;
+    size_t i0 = b << GRB_BME_SHIFT;
+    u32 m = 0;
+    for (int k = 0; k < 2; k++) {
+        size_t i = i0 + k * 32 + lane_id();
+        if (i < n) m = max(m, ends[i]);
+    }
+    m = warp_max(m);
+    if (lane_id() == 0) bme[b] = m;
+}
+
+// ---- scores ------------------------------------------------------------------
+
+struct ScoreStats {
+    int min_lsb_exp;  // min over finite non-zero scores of the exponent of the lowest set bit
+    int max_exp;      // max exponent of the highest set bit
+    u32 n_null;
+    u32 has_nonfinite;
+    u32 has_nan;
+    u32 has_subnormal;
+    u32 idx_out_of_range;
+    u32 n_nonzero;
+};
+
+__global__ void k_gather_scores(const u32 *__restrict__ didx, size_t n, const double *__restrict__ scores,
+                                const u8 *__restrict__ valid, u64 n_data, double *__restrict__ score_a,
+                                u32 *__restrict__ vbits_a, u32 *__restrict__ vflag_a, ScoreStats *st) {
+    size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    bool in = i < n;
+    bool ok = false;
+    double x = 0.0;
+    int lsb = 1 << 30, top = -(1 << 30);
+    u32 nonfinite = 0, nan = 0, sub = 0, oor = 0, nz = 0;
+    if (in) {
+        u32 d = didx[i];
+        if ((u64)d >= n_data) {
+            oor = 1;
+        } else {
+            ok = valid ? valid[d] != 0 : true;
+            if (ok) x = scores[d];
+        }
+        score_a[i] = x;
+        if (ok) {
+            u64 b = (u64)__double_as_longlong(x);
+            int ex = (int)((b >> 52) & 0x7ff);
+            u64 frac = b & ((1ull << 52) - 1);
+            if (ex == 0x7ff) {
+                nonfinite = 1;
+                if (frac) nan = 1;
+            } else if (ex == 0) {
+                if (frac) sub = 1;
+            } else {
+                u64 m = frac | (1ull << 52);
+                int tz = __ffsll((long long)m) - 1;
+                lsb = ex - 1075 + tz;
+                top = ex - 1023;
+                nz = 1;
+            }
+        }
+    }
+    u32 okmask = __ballot_sync(GRB_FULL, ok);
+    if (in) {
+        if (vbits_a && lane_id() == 0) vbits_a[i >> 5] = okmask;
+        if (vflag_a) vflag_a[i] = ok ? 1u : 0u;
+    }
+    // warp reduce stats
+    u32 nnull = __popc(__ballot_sync(GRB_FULL, in && !ok));
+#pragma unroll
+    for (int s = 16; s; s >>= 1) {
+        lsb = min(lsb, __shfl_xor_sync(GRB_FULL, lsb, s));
+        top = max(top, __shfl_xor_sync(GRB_FULL, top, s));
+        nonfinite |= __shfl_xor_sync(GRB_FULL, nonfinite, s);
+        nan |= __shfl_xor_sync(GRB_FULL, nan, s);
+        sub |= __shfl_xor_sync(GRB_FULL, sub, s);
+        oor |= __shfl_xor_sync(GRB_FULL, oor, s);
+        nz |= __shfl_xor_sync(GRB_FULL, nz, s);
+    }
+    if (lane_id() == 0) {
+        if (nz) {
+            atomicMin(&st->min_lsb_exp, lsb);
+            atomicMax(&st->max_exp, top);
+            atomicOr(&st->n_nonzero, 1u);
+        }
+        if (nnull) atomicAdd(&st->n_null, nnull);
+        if (nonfinite) atomicOr(&st->has_nonfinite, 1u);
+        if (nan) atomicOr(&st->has_nan, 1u);
+        if (sub) atomicOr(&st->has_subnormal, 1u);
+        if (oor) atomicOr(&st->idx_out_of_range, 1u);
+    }
+}
+
+__global__ void k_permute_u32(const u32 *__restrict__ src, const u32 *__restrict__ perm, size_t n, u32 *__restrict__ dst) {
+    size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n) dst[i] = src[perm[i]];
+}
+
+// Block-of-256 fixed-point prefix.  Positions p in [b*256, b*256+256) with p <= n; the value at
+// position p is the sum of the block's elements before p.
+//   phase 0: blocksum[b] = sum of the block's elements
+//   phase 1 (compact): loc[p] = local exclusive prefix (i64)
+//   phase 2 (wide):    wide[p] = base[b] + local exclusive prefix (i128)
+template <int PHASE>
+__global__ void __launch_bounds__(256) k_fx_blocks(const double *__restrict__ score_a, const u32 *__restrict__ perm,
+                                                   size_t n, int e0, i128 *__restrict__ blocksum,
+                                                   const i128 *__restrict__ base, i64 *__restrict__ loc,
+                                                   i128 *__restrict__ wide) {
+    __shared__ u64 s_lo[8], s_hi[8];
+    const size_t b = blockIdx.x;
+    const size_t p = (b << GRB_BASE_SHIFT) + threadIdx.x;
+    i128 v = 0;
+    if (p < n) v = to_fx(score_a[perm ? perm[p] : p], e0);
+    // warp inclusive scan of i128 through its two halves
+    i128 incl = v;
+    const u32 lane = lane_id(), warp = threadIdx.x >> 5;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {
+        u64 tlo = __shfl_up_sync(GRB_FULL, (u64)incl, o);
+        u64 thi = __shfl_up_sync(GRB_FULL, (u64)((u128)incl >> 64), o);
+        if (lane >= o) incl += (i128)(((u128)thi << 64) | tlo);
+    }
+    if (lane == 31) {
+        s_lo[warp] = (u64)incl;
+        s_hi[warp] = (u64)((u128)incl >> 64);
+    }
+    __syncthreads();
+    i128 woff = 0, total = 0;
+#pragma unroll
+    for (int w = 0; w < 8; w++) {
+        i128 t = (i128)(((u128)s_hi[w] << 64) | s_lo[w]);
+        if (w < (int)warp) woff += t;
+        total += t;
+    }
+    i128 excl = woff + incl - v;
+    if (PHASE == 0) {
+        if (threadIdx.x == 0) blocksum[b] = total;
+    } else if (PHASE == 1) {
+        if (p <= n) loc[p] = (i64)excl;
+    } else {
+        if (p <= n) wide[p] = base[b] + excl;
+    }
+}
+
+// Exclusive scan of nb i128 block sums by one CTA (nb = n/256 + 1: small).
+__global__ void __launch_bounds__(1024) k_scan_i128_single(const i128 *__restrict__ in, size_t nb, i128 *__restrict__ out) {
+    __shared__ u64 s_lo[1024], s_hi[1024];
+    const size_t per = (nb + 1023) / 1024;
+    const size_t lo = (size_t)threadIdx.x * per;
+    const size_t hi = lo + per < nb ? lo + per : nb;
+    i128 t = 0;
+    for (size_t i = lo; i < hi; i++) t += in[i];
+    s_lo[threadIdx.x] = (u64)t;
+    s_hi[threadIdx.x] = (u64)((u128)t >> 64);
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        i128 run = 0;
+        for (int k = 0; k < 1024; k++) {
+            i128 c = (i128)(((u128)s_hi[k] << 64) | s_lo[k]);
+            s_lo[k] = (u64)run;
+            s_hi[k] = (u64)((u128)run >> 64);
+            run += c;
+        }
+    }
+    __syncthreads();
+    i128 run = (i128)(((u128)s_hi[threadIdx.x] << 64) | s_lo[threadIdx.x]);
+    for (size_t i = lo; i < hi; i++) {
+        i128 c = in[i];
+        out[i] = run;
+        run += c;
+    }
+}
+
+inline unsigned blocks_for(size_t n, int tpb) { return (unsigned)((n + tpb - 1) / tpb); }
+
+int dev_alloc(grb_ctx *ctx, void **p, size_t bytes) {
+    GRB_CUDA(ctx, cudaMalloc(p, bytes ? bytes : 16));
+    return GRB_OK;
+}
+
+void free_scores(grb_index *ix) {
+    cudaFree(ix->score_a);
+    cudaFree(ix->vbits_a);
+    cudaFree(ix->vcnt_a);
+    cudaFree(ix->vcnt_b);
+    cudaFree(ix->loc_a);
+    cudaFree(ix->loc_b);
+    cudaFree(ix->base_a);
+    cudaFree(ix->base_b);
+    ix->score_a = nullptr;
+    ix->vbits_a = ix->vcnt_a = ix->vcnt_b = nullptr;
+    ix->loc_a = ix->loc_b = nullptr;
+    ix->base_a = ix->base_b = nullptr;
+    ix->has_scores = ix->has_nulls = ix->has_nan = false;
+    ix->sum_mode = GRB_SUM_SWEEP;
+}
+
+int build_prefix(grb_ctx *ctx, grb_index *ix, const u32 *perm, i64 **loc_out, i128 **base_out) {
+    const size_t n = ix->n;
+    const size_t nb = (n >> GRB_BASE_SHIFT) + 1;
+    TempBuf bsum;
+    GRB_TRY(bsum.alloc(ctx, nb * sizeof(i128)));
+    k_fx_blocks<0><<<(unsigned)nb, 256, 0, ctx->stream>>>(ix->score_a, perm, n, ix->e0, bsum.as<i128>(), nullptr, nullptr, nullptr);
+    GRB_LAUNCHED(ctx);
+    if (ix->sum_mode == GRB_SUM_COMPACT) {
+        GRB_TRY(dev_alloc(ctx, (void **)base_out, nb * sizeof(i128)));
+        GRB_TRY(dev_alloc(ctx, (void **)loc_out, (n + 1) * sizeof(i64)));
+        k_scan_i128_single<<<1, 1024, 0, ctx->stream>>>(bsum.as<i128>(), nb, *base_out);
+        GRB_LAUNCHED(ctx);
+        k_fx_blocks<1><<<(unsigned)nb, 256, 0, ctx->stream>>>(ix->score_a, perm, n, ix->e0, nullptr, nullptr, *loc_out, nullptr);
+        GRB_LAUNCHED(ctx);
+    } else {
+        TempBuf bbase;
+        GRB_TRY(bbase.alloc(ctx, nb * sizeof(i128)));
+        GRB_TRY(dev_alloc(ctx, (void **)base_out, (n + 1) * sizeof(i128)));
+        k_scan_i128_single<<<1, 1024, 0, ctx->stream>>>(bsum.as<i128>(), nb, bbase.as<i128>());
+        GRB_LAUNCHED(ctx);
+        k_fx_blocks<2><<<(unsigned)nb, 256, 0, ctx->stream>>>(ix->score_a, perm, n, ix->e0, nullptr, bbase.as<i128>(), nullptr, *base_out);
+        GRB_LAUNCHED(ctx);
+    }
+    return GRB_OK;
+}
+
+int ceil_log2(u64 x) {
+    int l = 0;
+    while ((1ull << l) < x) l++;
+    return l;
+}
+
+}  // namespace
+
+extern "C" {
+
+int grb_index_build(grb_ctx *ctx, const uint32_t *starts, const uint32_t *ends, const uint64_t *data_idx, size_t n,
+                    grb_index **out) {
+    if (!ctx || !out) return GRB_ERR_INVALID_ARG;
+    *out = nullptr;
+    if (n && (!starts || !ends)) return grb_fail(ctx, GRB_ERR_INVALID_ARG, "index_build: NULL range buffer");
+    if (n >= 0xfffffff0ull) return grb_fail(ctx, GRB_ERR_UNSUPPORTED, "index_build: more than 2^32-16 ranges on one seqname");
+    GRB_CUDA(ctx, cudaSetDevice(ctx->device));
+    grb_index *ix = (grb_index *)calloc(1, sizeof(grb_index));
+    if (!ix) return grb_fail(ctx, GRB_ERR_OOM, "index_build: host allocation failed");
+    ix->ctx = ctx;
+    ix->n = (u32)n;
+    ix->sum_mode = GRB_SUM_SWEEP;
+    int rc = GRB_OK;
+    do {
+        if ((rc = dev_alloc(ctx, (void **)&ix->starts, (n + PAD) * 4))) break;
+        if ((rc = dev_alloc(ctx, (void **)&ix->ends, (n + PAD) * 4))) break;
+        if ((rc = dev_alloc(ctx, (void **)&ix->ends_sorted, (n + PAD) * 4))) break;
+        if ((rc = dev_alloc(ctx, (void **)&ix->didx, n * 4))) break;
+        if ((rc = dev_alloc(ctx, (void **)&ix->perm_e, n * 4))) break;
+        if ((rc = dev_alloc(ctx, (void **)&ix->bme, ((n + 63) >> GRB_BME_SHIFT) * 4))) break;
+        InBuf d_starts, d_ends, d_idx;
+        if ((rc = d_starts.stage(ctx, starts, n * 4))) break;
+        if ((rc = d_ends.stage(ctx, ends, n * 4))) break;
+        if ((rc = d_idx.stage(ctx, data_idx, data_idx ? n * 8 : 0))) break;
+        TempBuf k0, k1, v0, v1, fl;
+        if ((rc = k0.alloc(ctx, n * 8))) break;
+        if ((rc = k1.alloc(ctx, n * 8))) break;
+        if ((rc = v0.alloc(ctx, n * 4))) break;
+        if ((rc = v1.alloc(ctx, n * 4))) break;
+        if ((rc = fl.alloc(ctx, sizeof(BuildFlags)))) break;
+        cudaMemsetAsync(fl.p, 0, sizeof(BuildFlags), ctx->stream);
+        u64 *ks = k0.as<u64>();
+        u32 *vs = v0.as<u32>();
+        const u32 *order = nullptr;
+        TempBuf order_buf;
+        if (n && data_idx) {
+            // ties on (start, end) must come out in data-index order: pre-order the input by data index
+            k_idx_keys<<<blocks_for(n, 256), 256, 0, ctx->stream>>>(d_idx.as<u64>(), n, k0.as<u64>(), v0.as<u32>(), fl.as<BuildFlags>());
+            ctx->launches++;
+            bool sorted0;
+            if ((rc = grb_sort_pairs(ctx, k0.as<u64>(), v0.as<u32>(), k1.as<u64>(), v1.as<u32>(), n, &ks, &vs, &sorted0))) break;
+            if (!sorted0) {
+                if ((rc = order_buf.alloc(ctx, n * 4))) break;
+                cudaMemcpyAsync(order_buf.p, vs, n * 4, cudaMemcpyDeviceToDevice, ctx->stream);
+                order = order_buf.as<u32>();
+            }
+        }
+        if (n) {
+            k_make_keys<<<blocks_for(n, 256), 256, 0, ctx->stream>>>(d_starts.as<u32>(), d_ends.as<u32>(), order, n, k0.as<u64>(),
+                                                                    v0.as<u32>(), fl.as<BuildFlags>());
+            ctx->launches++;
+        }
+        if ((rc = grb_sort_pairs(ctx, k0.as<u64>(), v0.as<u32>(), k1.as<u64>(), v1.as<u32>(), n, &ks, &vs, nullptr))) break;
+        BuildFlags hf;
+        cudaMemcpyAsync(&hf, fl.p, sizeof(hf), cudaMemcpyDeviceToHost, ctx->stream);
+        if (cudaStreamSynchronize(ctx->stream) != cudaSuccess) {
+            rc = grb_fail(ctx, GRB_ERR_CUDA, "index_build: %s", cudaGetErrorString(cudaGetLastError()));
+            break;
+        }
+        if (hf.invalid_range) {
+            rc = grb_fail(ctx, GRB_ERR_INVALID_RANGE,
+                          "index_build: a range has end <= start or end > 2^31-1 (the reference panics: "
+                          "ranges/mod.rs:109, ranges/coitrees.rs:53-54)");
+            break;
+        }
+        if (hf.idx_too_big) {
+            rc = grb_fail(ctx, GRB_ERR_UNSUPPORTED, "index_build: data index >= 2^32-1");
+            break;
+        }
+        // the other ping-pong pair is free now: reuse it for the end-order sort
+        u64 *k2 = (ks == k0.as<u64>()) ? k1.as<u64>() : k0.as<u64>();
+        u32 *v2 = (vs == v0.as<u32>()) ? v1.as<u32>() : v0.as<u32>();
+        k_unpack_start_order<<<blocks_for(n + PAD, 256), 256, 0, ctx->stream>>>(ks, vs, d_idx.as<u64>(), n, ix->starts, ix->ends,
+                                                                               ix->didx, k2, v2);
+        ctx->launches++;
+        // end order: sort (end, position) -- the start-order buffers double as scratch
+        u64 *ke;
+        u32 *ve;
+        if ((rc = grb_sort_pairs(ctx, k2, v2, ks, vs, n, &ke, &ve, nullptr))) break;
+        k_unpack_end_order<<<blocks_for(n + PAD, 256), 256, 0, ctx->stream>>>(ke, ve, n, ix->ends_sorted, ix->perm_e);
+        ctx->launches++;
+        if (n) {
+            size_t nbw = (n + 63) >> GRB_BME_SHIFT;
+            k_block_max_end<<<blocks_for(nbw * 32, 256), 256, 0, ctx->stream>>>(ix->ends, n, ix->bme);
+            ctx->launches++;
+        }
+        cudaError_t e = cudaStreamSynchronize(ctx->stream);
+        if (e != cudaSuccess) {
+            rc = grb_fail(ctx, GRB_ERR_CUDA, "index_build: %s", cudaGetErrorString(e));
+            break;
+        }
+    } while (0);
+    if (rc != GRB_OK) {
+        grb_index_destroy(ix);
+        return rc;
+    }
+    *out = ix;
+    return GRB_OK;
+}
+
+void grb_index_destroy(grb_index *ix) {
+    if (!ix) return;
+    cudaSetDevice(ix->ctx->device);
+    free_scores(ix);
+    cudaFree(ix->starts);
+    cudaFree(ix->ends);
+    cudaFree(ix->didx);
+    cudaFree(ix->bme);
+    cudaFree(ix->ends_sorted);
+    cudaFree(ix->perm_e);
+    free(ix);
+}
+
+size_t grb_index_len(const grb_index *ix) { return ix ? ix->n : 0; }
+
+int grb_index_exact_sums(const grb_index *ix) { return ix && ix->has_scores && ix->sum_mode != GRB_SUM_SWEEP; }
+
+int grb_index_set_scores(grb_index *ix, const double *by_data_idx, const uint8_t *valid, size_t n_data) {
+    if (!ix) return GRB_ERR_INVALID_ARG;
+    grb_ctx *ctx = ix->ctx;
+    if (n_data && !by_data_idx) return grb_fail(ctx, GRB_ERR_INVALID_ARG, "set_scores: NULL scores");
+    GRB_CUDA(ctx, cudaSetDevice(ctx->device));
+    free_scores(ix);
+    const size_t n = ix->n;
+    ix->n_data = n_data;
+    InBuf d_scores, d_valid;
+    GRB_TRY(d_scores.stage(ctx, by_data_idx, n_data * 8));
+    GRB_TRY(d_valid.stage(ctx, valid, valid ? n_data : 0));
+    GRB_TRY(dev_alloc(ctx, (void **)&ix->score_a, n * 8));
+    TempBuf stb, vflag_a, vflag_b;
+    GRB_TRY(stb.alloc(ctx, sizeof(ScoreStats)));
+    ScoreStats init;
+    memset(&init, 0, sizeof(init));
+    init.min_lsb_exp = 1 << 30;
+    init.max_exp = -(1 << 30);
+    GRB_CUDA(ctx, cudaMemcpyAsync(stb.p, &init, sizeof(init), cudaMemcpyHostToDevice, ctx->stream));
+    if (valid) {
+        GRB_TRY(dev_alloc(ctx, (void **)&ix->vbits_a, ((n + 31) / 32) * 4));
+        GRB_TRY(vflag_a.alloc(ctx, n * 4));
+    }
+    if (n) {
+        k_gather_scores<<<blocks_for(n, 256), 256, 0, ctx->stream>>>(ix->didx, n, d_scores.as<double>(), d_valid.as<u8>(), n_data,
+                                                                    ix->score_a, ix->vbits_a, valid ? vflag_a.as<u32>() : nullptr,
+                                                                    stb.as<ScoreStats>());
+        GRB_LAUNCHED(ctx);
+    }
+    ScoreStats st;
+    GRB_CUDA(ctx, cudaMemcpyAsync(&st, stb.p, sizeof(st), cudaMemcpyDeviceToHost, ctx->stream));
+    GRB_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+    if (st.idx_out_of_range) {
+        free_scores(ix);
+        return grb_fail(ctx, GRB_ERR_INDEX_RANGE, "set_scores: a right range's data index is >= n_data (%zu)", n_data);
+    }
+    ix->has_scores = true;
+    ix->has_nulls = st.n_null != 0;
+    ix->has_nan = st.has_nan != 0;
+    if (ix->has_nulls) {
+        GRB_TRY(dev_alloc(ctx, (void **)&ix->vcnt_a, (n + 1) * 4));
+        GRB_TRY(dev_alloc(ctx, (void **)&ix->vcnt_b, (n + 1) * 4));
+        GRB_TRY(vflag_b.alloc(ctx, n * 4));
+        k_permute_u32<<<blocks_for(n, 256), 256, 0, ctx->stream>>>(vflag_a.as<u32>(), ix->perm_e, n, vflag_b.as<u32>());
+        GRB_LAUNCHED(ctx);
+        GRB_TRY(grb_scan_u32_to_u32(ctx, vflag_a.as<u32>(), ix->vcnt_a, n, true));
+        GRB_TRY(grb_scan_u32_to_u32(ctx, vflag_b.as<u32>(), ix->vcnt_b, n, true));
+    } else if (ix->vbits_a) {
+        cudaFree(ix->vbits_a);
+        ix->vbits_a = nullptr;
+    }
+    // choose how SUM / MEAN are answered
+    ix->sum_mode = GRB_SUM_SWEEP;
+    ix->e0 = 0;
+    const char *force = getenv("GRB_SUM_MODE");  // debug: 0 sweep, 1 compact, 2 wide (only if representable)
+    if (!st.has_nonfinite && !st.has_subnormal) {
+        int W = 1, e0 = 0, emax = 0;
+        if (st.n_nonzero) {
+            e0 = st.min_lsb_exp;
+            emax = st.max_exp;
+            W = emax - e0 + 1;
+        }
+        int L = ceil_log2((u64)n + 1);
+        bool representable = (W + L <= 126) && (emax + L + 1 < 1023) && (e0 >= -1022);
+        if (representable) {
+            ix->e0 = e0;
+            ix->sum_mode = (W + GRB_BASE_SHIFT <= 62) ? GRB_SUM_COMPACT : GRB_SUM_WIDE;
+            if (force) {
+                int f = atoi(force);
+                if (f == GRB_SUM_SWEEP) ix->sum_mode = GRB_SUM_SWEEP;
+                if (f == GRB_SUM_WIDE) ix->sum_mode = GRB_SUM_WIDE;
+            }
+        }
+    }
+    if (ix->sum_mode != GRB_SUM_SWEEP) {
+        GRB_TRY(build_prefix(ctx, ix, nullptr, &ix->loc_a, &ix->base_a));
+        GRB_TRY(build_prefix(ctx, ix, ix->perm_e, &ix->loc_b, &ix->base_b));
+    }
+    GRB_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+    return GRB_OK;
+}
+
+int grb_index_copy_sorted(const grb_index *ix, uint32_t *starts, uint32_t *ends, uint64_t *data_idx) {
+    if (!ix) return GRB_ERR_INVALID_ARG;
+    grb_ctx *ctx = ix->ctx;
+    const size_t n = ix->n;
+    GRB_CUDA(ctx, cudaSetDevice(ctx->device));
+    if (starts) GRB_CUDA(ctx, cudaMemcpyAsync(starts, ix->starts, n * 4, cudaMemcpyDefault, ctx->stream));
+    if (ends) GRB_CUDA(ctx, cudaMemcpyAsync(ends, ix->ends, n * 4, cudaMemcpyDefault, ctx->stream));
+    if (data_idx) {
+        u32 *tmp = (u32 *)malloc(n * 4 + 4);
+        if (!tmp) return grb_fail(ctx, GRB_ERR_OOM, "copy_sorted: host allocation failed");
+        cudaError_t e = cudaMemcpyAsync(tmp, ix->didx, n * 4, cudaMemcpyDeviceToHost, ctx->stream);
+        if (e == cudaSuccess) e = cudaStreamSynchronize(ctx->stream);
+        if (e != cudaSuccess) {
+            free(tmp);
+            return grb_fail(ctx, GRB_ERR_CUDA, "copy_sorted: %s", cudaGetErrorString(e));
+        }
+        for (size_t i = 0; i < n; i++) data_idx[i] = tmp[i];
+        free(tmp);
+    }
+    GRB_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+    return GRB_OK;
+}
+
+}  // extern "C"

@@ -1,0 +1,1001 @@
+// query.cu -- the overlap-join hot path: count / filter / fused map reductions / pair emission.
+//
+// Reference path being replaced (per left range, src/granges.rs:958-969):
+//     COITrees::query(start, end, |node| join.add_right(node))     ranges/coitrees.rs:48-57
+//     JoinDataLeftEmpty::map -> gather right data by index          join.rs:343-361
+//     drop None scores, FloatOperation::run per op                  commands.rs:524-542, operations.rs:53-109
+//
+// Here, per tile of 1024 consecutive lefts (one CTA):
+//   1. four warp-cooperative 32-ary searches bound the slices of `starts` and `ends_sorted`
+//      the tile can touch;
+//   2. the two slices are staged into shared memory with TMA bulk copies (cp.async.bulk +
+//      mbarrier) and every left resolves
+//          ub = #{r.start < l.end}      lb = #{r.end <= l.start}
+//      by a branch-free binary search in shared memory;  count = ub - lb  (exact);
+//   3. SUM / MEAN come from exact fixed-point prefix sums PA[ub] - PB[lb] (index.cu), rounded
+//      once to f64 -- no pair is visited;
+//   4. MIN / MAX / MEDIAN / overlap bp need the members: a warp per left sweeps backward from
+//      ub over `ends` (skipping 64-blocks whose block-max-end cannot overlap) until it has seen
+//      `count` hits, reducing with ballots / shuffles; pair emission is the same sweep writing
+//      positions behind a count -> scan -> emit CSR.
+#include <stdlib.h>
+
+#include <vector>
+
+#include "common.cuh"
+
+namespace {
+
+constexpr int TILE_TPB = 256;
+constexpr int TILE_LPT = 4;
+constexpr int TILE = TILE_TPB * TILE_LPT;
+constexpr u32 WIN_CAP = 3072;  // keys per staged window (2 x 12 KB of shared memory)
+
+enum { M_COUNTS = 1, M_KEEP = 2, M_UBLB = 4, M_MAP = 8 };
+
+struct TileOut {
+    u32 *counts;
+    u8 *keep;
+    unsigned long long *n_kept;
+    int anti;
+    u32 *ub, *lb;
+    double *out;
+    u8 *out_valid;
+    int k;
+    int need_sum;
+    int ops[GRB_MAX_OPS];
+};
+
+// ---- PTX: mbarrier + TMA 1-D bulk copy ---------------------------------------
+
+__device__ __forceinline__ u32 smem_addr(const void *p) { return (u32)__cvta_generic_to_shared(p); }
+
+__device__ __forceinline__ void mbar_init(u64 *bar, u32 count) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_addr(bar)), "r"(count) : "memory");
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+}
+__device__ __forceinline__ void mbar_arrive_expect_tx(u64 *bar, u32 bytes) {
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_addr(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void tma_load_1d(void *dst, const void *src, u32 bytes, u64 *bar) {
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(smem_addr(dst)),
+                 "l"(src), "r"(bytes), "r"(smem_addr(bar))
+                 : "memory");
+}
+__device__ __forceinline__ void mbar_wait(u64 *bar, u32 parity) {
+    asm volatile(
+        "{\n"
+        ".reg .pred P1;\n"
+        "LAB_WAIT:\n"
+        "mbarrier.try_wait.parity.shared::cta.b64 P1, [%0], %1;\n"
+        "@P1 bra DONE;\n"
+        "bra LAB_WAIT;\n"
+        "DONE:\n"
+        "}\n" ::"r"(smem_addr(bar)),
+        "r"(parity)
+        : "memory");
+}
+
+// ---- searches -------------------------------------------------------------------
+
+// #keys < x over a sorted global array, by a whole warp: 32 probes per round.
+__device__ __forceinline__ u32 warp_lower_bound(const u32 *__restrict__ keys, u32 n, u32 x) {
+    const u32 lane = lane_id();
+    u32 lo = 0, hi = n;
+    while (hi - lo > 32) {
+        u32 len = hi - lo;
+        u32 p = lo + (u32)(((u64)(lane + 1) * len) / 33);
+        bool less = keys[p] < x;
+        u32 c = __popc(__ballot_sync(GRB_FULL, less));
+        u32 plo = __shfl_sync(GRB_FULL, p, c ? c - 1 : 0);
+        u32 phi = __shfl_sync(GRB_FULL, p, c < 32 ? c : 31);
+        if (c) lo = plo + 1;
+        if (c < 32) hi = phi;
+    }
+    u32 p = lo + lane;
+    bool less = p < hi && keys[p] < x;
+    return lo + __popc(__ballot_sync(GRB_FULL, less));
+}
+
+// #keys < x in s[0..len): branch-free, the trip count depends on len only.
+__device__ __forceinline__ u32 smem_lower_bound(const u32 *s, u32 len, u32 x) {
+    if (len == 0) return 0;
+    u32 base = 0, n = len;
+    while (n > 1) {
+        u32 half = n >> 1;
+        base = (s[base + half - 1] < x) ? base + half : base;
+        n -= half;
+    }
+    return base + (s[base] < x ? 1u : 0u);
+}
+
+// #keys < x restricted to the answer interval [lo, hi] of a global array.
+__device__ __forceinline__ u32 global_lower_bound(const u32 *__restrict__ keys, u32 lo, u32 hi, u32 x) {
+    while (lo < hi) {
+        u32 mid = lo + ((hi - lo) >> 1);
+        if (keys[mid] < x)
+            lo = mid + 1;
+        else
+            hi = mid;
+    }
+    return lo;
+}
+
+__device__ __forceinline__ int find_seq_by_tile(const u32 *__restrict__ tile_begin, int nseq, u32 t) {
+    int lo = 0, hi = nseq;
+    while (hi - lo > 1) {
+        int mid = (lo + hi) >> 1;
+        if (tile_begin[mid] <= t)
+            lo = mid;
+        else
+            hi = mid;
+    }
+    return lo;
+}
+
+__device__ __forceinline__ int find_seq_by_left(const SeqDev *__restrict__ seqs, int nseq, u64 g) {
+    int lo = 0, hi = nseq;
+    while (hi - lo > 1) {
+        int mid = (lo + hi) >> 1;
+        if (seqs[mid].left_begin <= g)
+            lo = mid;
+        else
+            hi = mid;
+    }
+    return lo;
+}
+
+// ---- the tile kernel --------------------------------------------------------------
+
+template <int MODE>
+__global__ void __launch_bounds__(TILE_TPB) k_tile(const SeqDev *__restrict__ seqs, const u32 *__restrict__ tile_begin, int nseq,
+                                                   const u32 *__restrict__ ls, const u32 *__restrict__ le, const TileOut o,
+                                                   int use_tma) {
+    __shared__ __align__(16) u32 sA[WIN_CAP + 8];
+    __shared__ __align__(16) u32 sB[WIN_CAP + 8];
+    __shared__ __align__(8) u64 mbar;
+    __shared__ u32 s_red[4][TILE_TPB / 32];
+    __shared__ u32 s_win[4];
+
+    const u32 tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    if (tid == 0) mbar_init(&mbar, 1);
+
+    const u32 t = blockIdx.x;
+    const int s = find_seq_by_tile(tile_begin, nseq, t);
+    const SeqDev *sd = &seqs[s];
+    const u64 base = sd->left_begin + (u64)(t - sd->tile_begin) * TILE;
+    const u64 remain = sd->left_end - base;
+    const u32 cnt = remain < (u64)TILE ? (u32)remain : (u32)TILE;
+    const u32 n = sd->n;
+    const u32 *__restrict__ starts = sd->starts;
+    const u32 *__restrict__ ends_sorted = sd->ends_sorted;
+
+    u32 a[TILE_LPT], b[TILE_LPT];
+    u32 mn_s = 0xffffffffu, mx_s = 0, mn_e = 0xffffffffu, mx_e = 0;
+#pragma unroll
+    for (int k = 0; k < TILE_LPT; k++) {
+        u32 i = tid + k * TILE_TPB;
+        bool ok = i < cnt;
+        a[k] = ok ? ls[base + i] : 0u;
+        b[k] = ok ? le[base + i] : 0u;
+        if (ok) {
+            mn_s = min(mn_s, a[k]);
+            mx_s = max(mx_s, a[k]);
+            mn_e = min(mn_e, b[k]);
+            mx_e = max(mx_e, b[k]);
+        }
+    }
+    mn_e = warp_min(mn_e);
+    mx_e = warp_max(mx_e);
+    mn_s = warp_min(mn_s);
+    mx_s = warp_max(mx_s);
+    if (lane == 0) {
+        s_red[0][warp] = mn_e;
+        s_red[1][warp] = mx_e;
+        s_red[2][warp] = mn_s;
+        s_red[3][warp] = mx_s;
+    }
+    __syncthreads();
+    if (warp < 4) {
+        u32 v = s_red[warp][lane & 7];
+        // warps 0,2 reduce with min, warps 1,3 with max
+        v = (warp & 1) ? warp_max(v) : warp_min(v);
+        // ub candidates: #{start < l.end};  lb candidates: #{end <= l.start} = #{end < l.start + 1}
+        u32 r = (warp < 2) ? warp_lower_bound(starts, n, v) : warp_lower_bound(ends_sorted, n, v + 1);
+        if (lane == 0) s_win[warp] = r;
+    }
+    __syncthreads();
+    const u32 A_lo = s_win[0], A_hi = s_win[1], B_lo = s_win[2], B_hi = s_win[3];
+    const u32 a0 = A_lo & ~3u, b0 = B_lo & ~3u;
+    const u32 alen = A_hi - a0, blen = B_hi - b0;
+    const bool staged = use_tma && alen <= WIN_CAP && blen <= WIN_CAP;
+
+    u32 ub[TILE_LPT], lb[TILE_LPT];
+    if (staged) {
+        const u32 bytes_a = (alen * 4 + 15) & ~15u, bytes_b = (blen * 4 + 15) & ~15u;
+        if (bytes_a + bytes_b) {
+            if (tid == 0) {
+                mbar_arrive_expect_tx(&mbar, bytes_a + bytes_b);
+                if (bytes_a) tma_load_1d(sA, starts + a0, bytes_a, &mbar);
+                if (bytes_b) tma_load_1d(sB, ends_sorted + b0, bytes_b, &mbar);
+            }
+            mbar_wait(&mbar, 0);
+        }
+#pragma unroll
+        for (int k = 0; k < TILE_LPT; k++) {
+            ub[k] = a0 + smem_lower_bound(sA, alen, b[k]);
+            lb[k] = b0 + smem_lower_bound(sB, blen, a[k] + 1);
+        }
+    } else {
+#pragma unroll
+        for (int k = 0; k < TILE_LPT; k++) {
+            ub[k] = global_lower_bound(starts, A_lo, A_hi, b[k]);
+            lb[k] = global_lower_bound(ends_sorted, B_lo, B_hi, a[k] + 1);
+        }
+    }
+
+    u32 kept = 0;
+#pragma unroll
+    for (int k = 0; k < TILE_LPT; k++) {
+        u32 i = tid + k * TILE_TPB;
+        if (i >= cnt) continue;
+        const u64 g = base + i;
+        const u32 c_all = ub[k] - lb[k];
+        if (MODE & M_COUNTS) o.counts[g] = c_all;
+        if (MODE & M_KEEP) {
+            u8 kp = (u8)((c_all != 0) != (o.anti != 0));
+            o.keep[g] = kp;
+            kept += kp;
+        }
+        if (MODE & M_UBLB) {
+            o.ub[g] = ub[k];
+            o.lb[g] = lb[k];
+        }
+        if (MODE & M_MAP) {
+            const int mode = sd->sum_mode;
+            u32 nvalid = c_all;
+            if (sd->has_nulls) nvalid = sd->vcnt_a[ub[k]] - sd->vcnt_b[lb[k]];
+            if (!sd->has_scores) nvalid = 0;
+            double sum = 0.0;
+            if (o.need_sum) {
+                if (mode == GRB_SUM_COMPACT) {
+                    i128 pa = sd->base_a[ub[k] >> GRB_BASE_SHIFT] + (i128)sd->loc_a[ub[k]];
+                    i128 pb = sd->base_b[lb[k] >> GRB_BASE_SHIFT] + (i128)sd->loc_b[lb[k]];
+                    sum = fx_to_double(pa - pb, sd->e0);
+                } else if (mode == GRB_SUM_WIDE) {
+                    sum = fx_to_double(sd->base_a[ub[k]] - sd->base_b[lb[k]], sd->e0);
+                }
+            }
+            for (int c = 0; c < o.k; c++) {
+                const int op = o.ops[c];
+                double r = 0.0;
+                u8 ok = 0;
+                bool mine = true;
+                switch (op) {
+                    case GRB_OP_COUNT:
+                        r = (double)c_all;
+                        ok = 1;
+                        break;
+                    case GRB_OP_SUM:
+                        mine = mode != GRB_SUM_SWEEP;
+                        r = sum;
+                        ok = 1;
+                        break;
+                    case GRB_OP_SUM_NOT_EMPTY:
+                        mine = mode != GRB_SUM_SWEEP;
+                        ok = nvalid != 0;
+                        r = ok ? sum : 0.0;
+                        break;
+                    case GRB_OP_MEAN:
+                        mine = mode != GRB_SUM_SWEEP;
+                        ok = nvalid != 0;
+                        r = ok ? sum / (double)nvalid : 0.0;
+                        break;
+                    default:
+                        mine = false;
+                        break;
+                }
+                if (mine) {
+                    o.out[g * (u64)o.k + c] = r;
+                    o.out_valid[g * (u64)o.k + c] = ok;
+                }
+            }
+        }
+    }
+    if (MODE & M_KEEP) {
+        if (o.n_kept) {
+            kept = warp_sum(kept);
+            if (lane == 0 && kept) atomicAdd(o.n_kept, (unsigned long long)kept);
+        }
+    }
+}
+
+// ---- the sweep kernels ----------------------------------------------------------------
+
+constexpr int SW_TPB = 256;
+constexpr int SW_WARPS = SW_TPB / 32;
+constexpr u32 MED_CAP = 256;  // scores a warp keeps in shared memory for the median
+
+struct SweepOut {
+    double *out;
+    u8 *out_valid;
+    int k;
+    int ops[GRB_MAX_OPS];
+    int want_median, want_bp;
+    u32 *heavy_list;
+    u32 *heavy_count;
+};
+
+__device__ __forceinline__ u64 f64_key(double x) {
+    u64 b = (u64)__double_as_longlong(x);
+    return (b >> 63) ? ~b : (b | (1ull << 63));
+}
+__device__ __forceinline__ double key_f64(u64 k) {
+    u64 b = (k >> 63) ? (k & ~(1ull << 63)) : ~k;
+    return __longlong_as_double((long long)b);
+}
+
+__device__ __forceinline__ bool score_valid(const SeqDev *sd, u32 j) {
+    if (!sd->has_scores) return false;
+    if (!sd->has_nulls) return true;
+    return (sd->vbits_a[j >> 5] >> (j & 31)) & 1u;
+}
+
+// One warp per left: sweep backward from ub until `count` overlapping rights were seen.
+__global__ void __launch_bounds__(SW_TPB) k_sweep(const SeqDev *__restrict__ seqs, int nseq, u64 total,
+                                                  const u32 *__restrict__ ls, const u32 *__restrict__ le,
+                                                  const u32 *__restrict__ ubv, const u32 *__restrict__ lbv, const SweepOut o) {
+    __shared__ double s_buf[SW_WARPS][MED_CAP];
+    __shared__ double s_med[SW_WARPS][2];
+    const u32 lane = lane_id(), warp = threadIdx.x >> 5;
+    const u64 g = (u64)blockIdx.x * SW_WARPS + warp;
+    if (g >= total) return;
+    const SeqDev *sd = &seqs[find_seq_by_left(seqs, nseq, g)];
+    const u32 u = ubv[g], count = u - lbv[g];
+    const u32 lstart = ls[g], lend = le[g];
+    const u32 *__restrict__ ends = sd->ends;
+    const u32 lt = (1u << lane) - 1;
+
+    u32 found = 0, nvalid = 0, nfinite = 0;
+    double sum = 0.0, mn = 0.0, mx = 0.0;
+    bool have = false;
+    u64 bp = 0;
+    long long cb = u ? (long long)((u - 1) & ~31u) : -1;
+    while (found < count && cb >= 0) {
+        if (sd->bme[cb >> GRB_BME_SHIFT] > lstart) {
+            u32 j = (u32)cb + lane;
+            bool in = j < u;
+            u32 e = in ? ends[j] : 0u;
+            bool hit = in && e > lstart;
+            u32 hm = __ballot_sync(GRB_FULL, hit);
+            bool v = hit && score_valid(sd, j);
+            u32 vm = __ballot_sync(GRB_FULL, v);
+            if (hit && o.want_bp) bp += (u64)(min(lend, e) - max(lstart, sd->starts[j]));
+            if (v) {
+                double x = sd->score_a[j];
+                sum += x;
+                if (isfinite(x)) {
+                    if (!have) {
+                        mn = mx = x;
+                        have = true;
+                    } else {
+                        mn = fmin(mn, x);
+                        mx = fmax(mx, x);
+                    }
+                }
+                if (o.want_median) {
+                    u32 slot = nvalid + __popc(vm & lt);
+                    if (slot < MED_CAP) s_buf[warp][slot] = x;
+                }
+            }
+            found += __popc(hm);
+            nvalid += __popc(vm);
+        }
+        cb -= 32;
+    }
+    // warp reductions (fixed shuffle order: deterministic)
+#pragma unroll
+    for (int s = 16; s; s >>= 1) {
+        sum += __shfl_xor_sync(GRB_FULL, sum, s);
+        double omn = __shfl_xor_sync(GRB_FULL, mn, s), omx = __shfl_xor_sync(GRB_FULL, mx, s);
+        bool ohave = __shfl_xor_sync(GRB_FULL, (int)have, s);
+        if (ohave) {
+            if (have) {
+                mn = fmin(mn, omn);
+                mx = fmax(mx, omx);
+            } else {
+                mn = omn;
+                mx = omx;
+                have = true;
+            }
+        }
+        bp += __shfl_xor_sync(GRB_FULL, bp, s);
+    }
+    (void)nfinite;
+    // median of up to MED_CAP values by rank counting
+    bool heavy = false;
+    if (o.want_median && nvalid) {
+        if (nvalid > MED_CAP) {
+            heavy = true;
+        } else {
+            __syncwarp();
+            const u32 m = nvalid, k1 = (m - 1) >> 1, k2 = m >> 1;
+            for (u32 e = lane; e < m; e += 32) {
+                double x = s_buf[warp][e];
+                u32 r = 0;
+                for (u32 q = 0; q < m; q++) {
+                    double y = s_buf[warp][q];
+                    r += (y < x || (y == x && q < e)) ? 1u : 0u;
+                }
+                if (r == k1) s_med[warp][0] = x;
+                if (r == k2) s_med[warp][1] = x;
+            }
+            __syncwarp();
+        }
+    }
+    if (lane == 0) {
+        const bool sweep_sums = sd->sum_mode == GRB_SUM_SWEEP;
+        for (int c = 0; c < o.k; c++) {
+            double r = 0.0;
+            u8 ok = 0;
+            bool mine = true;
+            switch (o.ops[c]) {
+                case GRB_OP_SUM:
+                    mine = sweep_sums;
+                    r = sum;
+                    ok = 1;
+                    break;
+                case GRB_OP_SUM_NOT_EMPTY:
+                    mine = sweep_sums;
+                    ok = nvalid != 0;
+                    r = ok ? sum : 0.0;
+                    break;
+                case GRB_OP_MEAN:
+                    mine = sweep_sums;
+                    ok = nvalid != 0;
+                    r = ok ? sum / (double)nvalid : 0.0;
+                    break;
+                case GRB_OP_MIN:
+                    ok = have;
+                    r = have ? mn : 0.0;
+                    break;
+                case GRB_OP_MAX:
+                    ok = have;
+                    r = have ? mx : 0.0;
+                    break;
+                case GRB_OP_MEDIAN:
+                    if (heavy) {
+                        mine = false;
+                    } else if (nvalid) {
+                        ok = 1;
+                        r = (nvalid & 1) ? s_med[warp][1] : (s_med[warp][0] + s_med[warp][1]) / 2.0;
+                    }
+                    break;
+                case GRB_OP_OVERLAP_BP:
+                    ok = 1;
+                    r = (double)bp;
+                    break;
+                default:
+                    mine = false;
+                    break;
+            }
+            if (mine) {
+                o.out[g * (u64)o.k + c] = r;
+                o.out_valid[g * (u64)o.k + c] = ok;
+            }
+        }
+        if (heavy) {
+            u32 slot = atomicAdd(o.heavy_count, 1u);
+            o.heavy_list[slot] = (u32)g;  // the host checks total < 2^32 when a median is requested
+        }
+    }
+}
+
+// Median of groups with more than MED_CAP valid scores: one CTA per such left, MSB-first radix
+// select (8 bits per pass) over the order-preserving integer image of the scores, re-sweeping the
+// candidates instead of materialising them.
+__global__ void __launch_bounds__(SW_TPB) k_median_heavy(const SeqDev *__restrict__ seqs, int nseq, const u32 *__restrict__ ls,
+                                                         const u32 *__restrict__ ubv, const u32 *__restrict__ lbv,
+                                                         const u32 *__restrict__ heavy_list, const u32 *__restrict__ heavy_count,
+                                                         const SweepOut o) {
+    __shared__ u32 hist[256];
+    __shared__ u64 s_prefix;
+    __shared__ u32 s_kk;
+    const u32 nheavy = *heavy_count;
+    for (u32 h = blockIdx.x; h < nheavy; h += gridDim.x) {
+        const u64 g = heavy_list[h];
+        const SeqDev *sd = &seqs[find_seq_by_left(seqs, nseq, g)];
+        const u32 u = ubv[g], count = u - lbv[g], lstart = ls[g];
+        const u32 *__restrict__ ends = sd->ends;
+        // 1. how far back do the members reach, and how many carry a score?
+        u32 found = 0, m = 0, j_top = u;
+        while (found < count && j_top > 0) {
+            long long j = (long long)j_top - 1 - threadIdx.x;
+            bool hit = j >= 0 && ends[j] > lstart;
+            bool v = hit && score_valid(sd, (u32)j);
+            found += __syncthreads_count(hit);
+            m += __syncthreads_count(v);
+            j_top = j_top > SW_TPB ? j_top - SW_TPB : 0;
+        }
+        const u32 j_lo = j_top;
+        double res[2] = {0.0, 0.0};
+        const u32 targets[2] = {(m - 1) >> 1, m >> 1};
+        for (int which = 0; which < 2; which++) {
+            if (which == 1 && targets[1] == targets[0]) {
+                res[1] = res[0];
+                break;
+            }
+            if (threadIdx.x == 0) {
+                s_prefix = 0;
+                s_kk = targets[which];
+            }
+            for (int pass = 7; pass >= 0; pass--) {
+                hist[threadIdx.x] = 0;
+                __syncthreads();
+                const u64 prefix = s_prefix;
+                for (u32 j = j_lo + threadIdx.x; j < u; j += SW_TPB) {
+                    if (ends[j] > lstart && score_valid(sd, j)) {
+                        u64 key = f64_key(sd->score_a[j]);
+                        bool match = pass == 7 ? true : ((key ^ prefix) >> (8 * (pass + 1))) == 0;
+                        if (match) atomicAdd(&hist[(key >> (8 * pass)) & 0xff], 1u);
+                    }
+                }
+                __syncthreads();
+                if (threadIdx.x == 0) {
+                    u32 kk = s_kk, cum = 0;
+                    int d = 0;
+                    for (; d < 255; d++) {
+                        if (cum + hist[d] > kk) break;
+                        cum += hist[d];
+                    }
+                    s_kk = kk - cum;
+                    s_prefix = prefix | ((u64)d << (8 * pass));
+                }
+                __syncthreads();
+            }
+            res[which] = key_f64(s_prefix);
+            __syncthreads();
+        }
+        if (threadIdx.x == 0) {
+            for (int c = 0; c < o.k; c++) {
+                if (o.ops[c] != GRB_OP_MEDIAN) continue;
+                o.out[g * (u64)o.k + c] = (m & 1) ? res[1] : (res[0] + res[1]) / 2.0;
+                o.out_valid[g * (u64)o.k + c] = 1;
+            }
+        }
+        __syncthreads();
+    }
+}
+
+// Emit pass of left_overlaps: positions (start order) of the members of every group, ascending,
+// which IS sort_ranges order (join.rs:121-128) because the index is sorted by (start, end, index).
+__global__ void __launch_bounds__(SW_TPB) k_emit(const SeqDev *__restrict__ seqs, int nseq, u64 total,
+                                                 const u32 *__restrict__ ls, const u32 *__restrict__ ubv,
+                                                 const u32 *__restrict__ lbv, const u64 *__restrict__ offsets,
+                                                 u32 *__restrict__ pos) {
+    const u32 lane = lane_id(), warp = threadIdx.x >> 5;
+    const u64 g = (u64)blockIdx.x * SW_WARPS + warp;
+    if (g >= total) return;
+    const SeqDev *sd = &seqs[find_seq_by_left(seqs, nseq, g)];
+    const u32 u = ubv[g], count = u - lbv[g];
+    const u32 lstart = ls[g];
+    const u32 *__restrict__ ends = sd->ends;
+    const u64 off = offsets[g];
+    u32 found = 0;
+    long long cb = u ? (long long)((u - 1) & ~31u) : -1;
+    while (found < count && cb >= 0) {
+        if (sd->bme[cb >> GRB_BME_SHIFT] > lstart) {
+            u32 j = (u32)cb + lane;
+            bool hit = j < u && ends[j] > lstart;
+            u32 hm = __ballot_sync(GRB_FULL, hit);
+            if (hit) {
+                u32 above = lane == 31 ? 0u : __popc(hm >> (lane + 1));
+                pos[off + (u64)(count - 1 - (found + above))] = j;
+            }
+            found += __popc(hm);
+        }
+        cb -= 32;
+    }
+}
+
+__global__ void k_pairs_gather(const u32 *__restrict__ pos, u64 np, const u32 *__restrict__ starts, const u32 *__restrict__ ends,
+                               const u32 *__restrict__ didx, u64 *__restrict__ out_idx, u32 *__restrict__ out_s,
+                               u32 *__restrict__ out_e) {
+    u64 i = (u64)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= np) return;
+    u32 j = pos[i];
+    if (out_idx) out_idx[i] = didx[j];
+    if (out_s) out_s[i] = starts[j];
+    if (out_e) out_e[i] = ends[j];
+}
+
+// overlap_width (traits.rs:73-80) of every pair: one warp per left walks its group.
+__global__ void k_pairs_widths(const u32 *__restrict__ pos, const u64 *__restrict__ offsets, u64 nl, const u32 *__restrict__ ls,
+                               const u32 *__restrict__ le, const u32 *__restrict__ starts, const u32 *__restrict__ ends,
+                               u32 *__restrict__ widths) {
+    const u64 g = ((u64)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+    if (g >= nl) return;
+    const u32 a = ls[g], b = le[g];
+    for (u64 i = offsets[g] + lane_id(); i < offsets[g + 1]; i += 32) {
+        u32 j = pos[i];
+        u32 s = max(a, starts[j]), e = min(b, ends[j]);
+        widths[i] = e > s ? e - s : 0u;
+    }
+}
+
+// ---- host orchestration -------------------------------------------------------------------
+
+struct Batch {
+    TempBuf seqs_dev, tiles_dev;
+    const SeqDev *seqs = nullptr;
+    const u32 *tile_begin = nullptr;
+    u32 ntiles = 0;
+    u64 total = 0;
+    int nseq = 0;
+};
+
+int make_batch(grb_ctx *ctx, const grb_index *const *idx, const u64 *left_offsets, int nseq, Batch *b) {
+    if (nseq <= 0) return grb_fail(ctx, GRB_ERR_INVALID_ARG, "batch: nseq must be >= 1");
+    std::vector<SeqDev> h((size_t)nseq);
+    std::vector<u32> tb((size_t)nseq + 1);
+    u64 tiles = 0;
+    for (int s = 0; s < nseq; s++) {
+        if (left_offsets[s + 1] < left_offsets[s]) return grb_fail(ctx, GRB_ERR_INVALID_ARG, "batch: left_offsets must be non-decreasing");
+        SeqDev d;
+        memset(&d, 0, sizeof(d));
+        const grb_index *ix = idx ? idx[s] : nullptr;
+        if (ix && ix->ctx != ctx) return grb_fail(ctx, GRB_ERR_INVALID_ARG, "batch: index belongs to another context");
+        if (ix && ix->n) {
+            d.starts = ix->starts;
+            d.ends = ix->ends;
+            d.ends_sorted = ix->ends_sorted;
+            d.didx = ix->didx;
+            d.bme = ix->bme;
+            d.score_a = ix->score_a;
+            d.vbits_a = ix->vbits_a;
+            d.vcnt_a = ix->vcnt_a;
+            d.vcnt_b = ix->vcnt_b;
+            d.loc_a = ix->loc_a;
+            d.loc_b = ix->loc_b;
+            d.base_a = ix->base_a;
+            d.base_b = ix->base_b;
+            d.n = ix->n;
+            d.e0 = ix->e0;
+            d.sum_mode = ix->has_scores ? ix->sum_mode : 3;
+            d.has_nulls = ix->has_nulls;
+            d.has_scores = ix->has_scores;
+        } else {
+            d.sum_mode = 3;  // nothing to sum: every group is empty
+        }
+        d.left_begin = left_offsets[s];
+        d.left_end = left_offsets[s + 1];
+        d.tile_begin = (u32)tiles;
+        tb[s] = (u32)tiles;
+        tiles += (d.left_end - d.left_begin + TILE - 1) / TILE;
+        if (tiles >= 0x7fffffffull) return grb_fail(ctx, GRB_ERR_UNSUPPORTED, "batch: too many left ranges for one call");
+        h[s] = d;
+    }
+    tb[nseq] = (u32)tiles;
+    b->ntiles = (u32)tiles;
+    b->total = left_offsets[nseq];
+    b->nseq = nseq;
+    GRB_TRY(b->seqs_dev.alloc(ctx, sizeof(SeqDev) * nseq));
+    GRB_TRY(b->tiles_dev.alloc(ctx, sizeof(u32) * (nseq + 1)));
+    GRB_CUDA(ctx, cudaMemcpyAsync(b->seqs_dev.p, h.data(), sizeof(SeqDev) * nseq, cudaMemcpyHostToDevice, ctx->stream));
+    GRB_CUDA(ctx, cudaMemcpyAsync(b->tiles_dev.p, tb.data(), sizeof(u32) * (nseq + 1), cudaMemcpyHostToDevice, ctx->stream));
+    b->seqs = b->seqs_dev.as<SeqDev>();
+    b->tile_begin = b->tiles_dev.as<u32>();
+    return GRB_OK;
+}
+
+template <int MODE>
+int launch_tile(grb_ctx *ctx, const Batch &b, const u32 *ls, const u32 *le, const TileOut &o) {
+    if (b.ntiles == 0) return GRB_OK;
+    k_tile<MODE><<<b.ntiles, TILE_TPB, 0, ctx->stream>>>(b.seqs, b.tile_begin, b.nseq, ls, le, o, ctx->tile_mode);
+    GRB_LAUNCHED(ctx);
+    return GRB_OK;
+}
+
+int enter(grb_ctx *ctx) {
+    if (!ctx) return GRB_ERR_INVALID_ARG;
+    GRB_CUDA(ctx, cudaSetDevice(ctx->device));
+    return GRB_OK;
+}
+
+}  // namespace
+
+struct grb_pairs {
+    grb_ctx *ctx;
+    const grb_index *idx;
+    u64 nl, np;
+    u32 *ls, *le;   // device copies of the lefts
+    u64 *offsets;   // device, nl + 1
+    u32 *pos;       // device, np positions in the index's start order
+};
+
+extern "C" {
+
+int grb_count_overlaps_batch(grb_ctx *ctx, const grb_index *const *idx, const uint64_t *left_offsets, int nseq,
+                             const uint32_t *ls, const uint32_t *le, uint32_t *counts) {
+    GRB_TRY(enter(ctx));
+    if (!left_offsets) return grb_fail(ctx, GRB_ERR_INVALID_ARG, "count_overlaps: NULL left_offsets");
+    Batch b;
+    GRB_TRY(make_batch(ctx, idx, left_offsets, nseq, &b));
+    if (b.total == 0) return GRB_OK;
+    if (!ls || !le || !counts) return grb_fail(ctx, GRB_ERR_INVALID_ARG, "count_overlaps: NULL buffer");
+    InBuf dls, dle;
+    OutBuf dc;
+    GRB_TRY(dls.stage(ctx, ls, b.total * 4));
+    GRB_TRY(dle.stage(ctx, le, b.total * 4));
+    GRB_TRY(dc.stage(ctx, counts, b.total * 4));
+    TileOut o;
+    memset(&o, 0, sizeof(o));
+    o.counts = dc.as<u32>();
+    GRB_TRY(launch_tile<M_COUNTS>(ctx, b, dls.as<u32>(), dle.as<u32>(), o));
+    GRB_TRY(dc.finish(ctx));
+    if (dc.host) GRB_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+    return GRB_OK;
+}
+
+int grb_count_overlaps(grb_ctx *ctx, const grb_index *idx, const uint32_t *ls, const uint32_t *le, size_t nl,
+                       uint32_t *counts) {
+    uint64_t off[2] = {0, nl};
+    return grb_count_overlaps_batch(ctx, &idx, off, 1, ls, le, counts);
+}
+
+int grb_filter_overlaps_batch(grb_ctx *ctx, const grb_index *const *idx, const uint64_t *left_offsets, int nseq,
+                              const uint32_t *ls, const uint32_t *le, int anti, uint8_t *keep, uint64_t *n_kept) {
+    GRB_TRY(enter(ctx));
+    if (!left_offsets) return grb_fail(ctx, GRB_ERR_INVALID_ARG, "filter_overlaps: NULL left_offsets");
+    Batch b;
+    GRB_TRY(make_batch(ctx, idx, left_offsets, nseq, &b));
+    if (n_kept) *n_kept = 0;
+    if (b.total == 0) return GRB_OK;
+    if (!ls || !le || !keep) return grb_fail(ctx, GRB_ERR_INVALID_ARG, "filter_overlaps: NULL buffer");
+    InBuf dls, dle;
+    OutBuf dk;
+    TempBuf nk;
+    GRB_TRY(dls.stage(ctx, ls, b.total * 4));
+    GRB_TRY(dle.stage(ctx, le, b.total * 4));
+    GRB_TRY(dk.stage(ctx, keep, b.total));
+    TileOut o;
+    memset(&o, 0, sizeof(o));
+    o.keep = dk.as<u8>();
+    o.anti = anti;
+    if (n_kept) {
+        GRB_TRY(nk.alloc(ctx, 8));
+        GRB_CUDA(ctx, cudaMemsetAsync(nk.p, 0, 8, ctx->stream));
+        o.n_kept = nk.as<unsigned long long>();
+    }
+    GRB_TRY(launch_tile<M_KEEP>(ctx, b, dls.as<u32>(), dle.as<u32>(), o));
+    GRB_TRY(dk.finish(ctx));
+    if (n_kept) GRB_CUDA(ctx, cudaMemcpyAsync(n_kept, nk.p, 8, cudaMemcpyDeviceToHost, ctx->stream));
+    if (dk.host || n_kept) GRB_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+    return GRB_OK;
+}
+
+int grb_filter_overlaps(grb_ctx *ctx, const grb_index *idx, const uint32_t *ls, const uint32_t *le, size_t nl, int anti,
+                        uint8_t *keep, uint64_t *n_kept) {
+    uint64_t off[2] = {0, nl};
+    return grb_filter_overlaps_batch(ctx, &idx, off, 1, ls, le, anti, keep, n_kept);
+}
+
+int grb_map_joins_f64_batch(grb_ctx *ctx, const grb_index *const *idx, const uint64_t *left_offsets, int nseq,
+                            const uint32_t *ls, const uint32_t *le, const int *ops, int k, double *out,
+                            uint8_t *out_valid) {
+    GRB_TRY(enter(ctx));
+    if (!left_offsets || !ops) return grb_fail(ctx, GRB_ERR_INVALID_ARG, "map_joins: NULL left_offsets / ops");
+    if (k < 1 || k > GRB_MAX_OPS) return grb_fail(ctx, GRB_ERR_INVALID_ARG, "map_joins: k must be in [1, %d]", GRB_MAX_OPS);
+    bool need_scores = false, need_sum = false, need_members = false, want_median = false, want_bp = false;
+    for (int c = 0; c < k; c++) {
+        switch (ops[c]) {
+            case GRB_OP_SUM:
+            case GRB_OP_SUM_NOT_EMPTY:
+            case GRB_OP_MEAN:
+                need_scores = need_sum = true;
+                break;
+            case GRB_OP_MIN:
+            case GRB_OP_MAX:
+                need_scores = need_members = true;
+                break;
+            case GRB_OP_MEDIAN:
+                need_scores = need_members = want_median = true;
+                break;
+            case GRB_OP_COUNT:
+                break;
+            case GRB_OP_OVERLAP_BP:
+                need_members = want_bp = true;
+                break;
+            default:
+                return grb_fail(ctx, GRB_ERR_INVALID_ARG, "map_joins: unknown operation code %d", ops[c]);
+        }
+    }
+    for (int s = 0; s < nseq; s++) {
+        const grb_index *ix = idx ? idx[s] : nullptr;
+        if (!ix) continue;
+        if (need_scores && !ix->has_scores)
+            return grb_fail(ctx, GRB_ERR_NO_DATA, "map_joins: the right index of seqname %d has no data container (scores)", s);
+        if (want_median && ix->has_nan)
+            return grb_fail(ctx, GRB_ERR_NAN_SCORE, "map_joins: median over NaN scores (the reference panics in partial_cmp().unwrap())");
+        if (need_sum && ix->n && ix->sum_mode == GRB_SUM_SWEEP) need_members = true;
+    }
+    Batch b;
+    GRB_TRY(make_batch(ctx, idx, left_offsets, nseq, &b));
+    if (b.total == 0) return GRB_OK;
+    if (!ls || !le || !out || !out_valid) return grb_fail(ctx, GRB_ERR_INVALID_ARG, "map_joins: NULL buffer");
+    InBuf dls, dle;
+    OutBuf dout, dval;
+    GRB_TRY(dls.stage(ctx, ls, b.total * 4));
+    GRB_TRY(dle.stage(ctx, le, b.total * 4));
+    GRB_TRY(dout.stage(ctx, out, b.total * (u64)k * 8));
+    GRB_TRY(dval.stage(ctx, out_valid, b.total * (u64)k));
+    TileOut o;
+    memset(&o, 0, sizeof(o));
+    o.out = dout.as<double>();
+    o.out_valid = dval.as<u8>();
+    o.k = k;
+    o.need_sum = need_sum;
+    for (int c = 0; c < k; c++) o.ops[c] = ops[c];
+    if (!need_members) {
+        GRB_TRY(launch_tile<M_MAP>(ctx, b, dls.as<u32>(), dle.as<u32>(), o));
+    } else {
+        TempBuf ub, lb, heavy;
+        GRB_TRY(ub.alloc(ctx, b.total * 4));
+        GRB_TRY(lb.alloc(ctx, b.total * 4));
+        o.ub = ub.as<u32>();
+        o.lb = lb.as<u32>();
+        GRB_TRY(launch_tile<M_MAP | M_UBLB>(ctx, b, dls.as<u32>(), dle.as<u32>(), o));
+        SweepOut so;
+        memset(&so, 0, sizeof(so));
+        so.out = o.out;
+        so.out_valid = o.out_valid;
+        so.k = k;
+        for (int c = 0; c < k; c++) so.ops[c] = ops[c];
+        so.want_median = want_median;
+        so.want_bp = want_bp;
+        if (want_median) {
+            if (b.total >= 0xffffffffull) return grb_fail(ctx, GRB_ERR_UNSUPPORTED, "map_joins: median over more than 2^32-1 lefts per call");
+            GRB_TRY(heavy.alloc(ctx, (b.total + 1) * 4));
+            GRB_CUDA(ctx, cudaMemsetAsync(heavy.p, 0, 4, ctx->stream));
+            so.heavy_count = heavy.as<u32>();
+            so.heavy_list = heavy.as<u32>() + 1;
+        }
+        u64 blocks = (b.total + SW_WARPS - 1) / SW_WARPS;
+        if (blocks >= 0x7fffffffull) return grb_fail(ctx, GRB_ERR_UNSUPPORTED, "map_joins: too many left ranges for one call");
+        k_sweep<<<(unsigned)blocks, SW_TPB, 0, ctx->stream>>>(b.seqs, b.nseq, b.total, dls.as<u32>(), dle.as<u32>(), o.ub, o.lb, so);
+        GRB_LAUNCHED(ctx);
+        if (want_median) {
+            k_median_heavy<<<ctx->sm_count * 4, SW_TPB, 0, ctx->stream>>>(b.seqs, b.nseq, dls.as<u32>(), o.ub, o.lb, so.heavy_list,
+                                                                          so.heavy_count, so);
+            GRB_LAUNCHED(ctx);
+        }
+    }
+    GRB_TRY(dout.finish(ctx));
+    GRB_TRY(dval.finish(ctx));
+    if (dout.host || dval.host) GRB_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+    return GRB_OK;
+}
+
+int grb_map_joins_f64(grb_ctx *ctx, const grb_index *idx, const uint32_t *ls, const uint32_t *le, size_t nl,
+                      const int *ops, int k, double *out, uint8_t *out_valid) {
+    uint64_t off[2] = {0, nl};
+    return grb_map_joins_f64_batch(ctx, &idx, off, 1, ls, le, ops, k, out, out_valid);
+}
+
+int grb_left_overlaps(grb_ctx *ctx, const grb_index *idx, const uint32_t *ls, const uint32_t *le, size_t nl,
+                      uint64_t *offsets, grb_pairs **out) {
+    GRB_TRY(enter(ctx));
+    if (!out || !offsets) return grb_fail(ctx, GRB_ERR_INVALID_ARG, "left_overlaps: NULL output");
+    *out = nullptr;
+    if (nl && (!ls || !le)) return grb_fail(ctx, GRB_ERR_INVALID_ARG, "left_overlaps: NULL buffer");
+    grb_pairs *p = (grb_pairs *)calloc(1, sizeof(grb_pairs));
+    if (!p) return grb_fail(ctx, GRB_ERR_OOM, "left_overlaps: host allocation failed");
+    p->ctx = ctx;
+    p->idx = idx;
+    p->nl = nl;
+    int rc = GRB_OK;
+    do {
+        if (cudaMalloc(&p->ls, nl * 4 + 16) != cudaSuccess || cudaMalloc(&p->le, nl * 4 + 16) != cudaSuccess ||
+            cudaMalloc(&p->offsets, (nl + 1) * 8) != cudaSuccess) {
+            rc = grb_fail(ctx, GRB_ERR_OOM, "left_overlaps: device allocation failed");
+            break;
+        }
+        if (nl) {
+            cudaMemcpyAsync(p->ls, ls, nl * 4, cudaMemcpyDefault, ctx->stream);
+            cudaMemcpyAsync(p->le, le, nl * 4, cudaMemcpyDefault, ctx->stream);
+        }
+        uint64_t off[2] = {0, nl};
+        Batch b;
+        if ((rc = make_batch(ctx, &idx, off, 1, &b))) break;
+        TempBuf counts, ub, lb;
+        if ((rc = counts.alloc(ctx, nl * 4))) break;
+        if ((rc = ub.alloc(ctx, nl * 4))) break;
+        if ((rc = lb.alloc(ctx, nl * 4))) break;
+        TileOut o;
+        memset(&o, 0, sizeof(o));
+        o.counts = counts.as<u32>();
+        o.ub = ub.as<u32>();
+        o.lb = lb.as<u32>();
+        if ((rc = launch_tile<M_COUNTS | M_UBLB>(ctx, b, p->ls, p->le, o))) break;
+        if ((rc = grb_scan_u32_to_u64(ctx, counts.as<u32>(), p->offsets, nl, true))) break;
+        u64 np = 0;
+        cudaMemcpyAsync(&np, p->offsets + nl, 8, cudaMemcpyDeviceToHost, ctx->stream);
+        cudaError_t e = cudaStreamSynchronize(ctx->stream);
+        if (e != cudaSuccess) {
+            rc = grb_fail(ctx, GRB_ERR_CUDA, "left_overlaps: %s", cudaGetErrorString(e));
+            break;
+        }
+        p->np = np;
+        if (cudaMalloc(&p->pos, np * 4 + 16) != cudaSuccess) {
+            rc = grb_fail(ctx, GRB_ERR_OOM, "left_overlaps: cannot allocate %llu pairs on the device", (unsigned long long)np);
+            break;
+        }
+        if (np) {
+            u64 blocks = (nl + SW_WARPS - 1) / SW_WARPS;
+            k_emit<<<(unsigned)blocks, SW_TPB, 0, ctx->stream>>>(b.seqs, 1, nl, p->ls, o.ub, o.lb, p->offsets, p->pos);
+            ctx->launches++;
+        }
+        e = cudaMemcpyAsync(offsets, p->offsets, (nl + 1) * 8, cudaMemcpyDefault, ctx->stream);
+        if (e == cudaSuccess) e = cudaStreamSynchronize(ctx->stream);
+        if (e != cudaSuccess) {
+            rc = grb_fail(ctx, GRB_ERR_CUDA, "left_overlaps: %s", cudaGetErrorString(e));
+            break;
+        }
+    } while (0);
+    if (rc != GRB_OK) {
+        grb_pairs_destroy(p);
+        return rc;
+    }
+    *out = p;
+    return GRB_OK;
+}
+
+size_t grb_pairs_len(const grb_pairs *p) { return p ? (size_t)p->np : 0; }
+
+int grb_pairs_copy(const grb_pairs *p, uint64_t *right_data_idx, uint32_t *r_start, uint32_t *r_end) {
+    if (!p) return GRB_ERR_INVALID_ARG;
+    grb_ctx *ctx = p->ctx;
+    GRB_TRY(enter(ctx));
+    if (p->np == 0) return GRB_OK;
+    OutBuf di, ds, de;
+    GRB_TRY(di.stage(ctx, right_data_idx, p->np * 8));
+    GRB_TRY(ds.stage(ctx, r_start, p->np * 4));
+    GRB_TRY(de.stage(ctx, r_end, p->np * 4));
+    u64 blocks = (p->np + 255) / 256;
+    k_pairs_gather<<<(unsigned)blocks, 256, 0, ctx->stream>>>(p->pos, p->np, p->idx->starts, p->idx->ends, p->idx->didx, di.as<u64>(),
+                                                             ds.as<u32>(), de.as<u32>());
+    GRB_LAUNCHED(ctx);
+    GRB_TRY(di.finish(ctx));
+    GRB_TRY(ds.finish(ctx));
+    GRB_TRY(de.finish(ctx));
+    GRB_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+    return GRB_OK;
+}
+
+int grb_pairs_overlap_widths(const grb_pairs *p, uint32_t *widths) {
+    if (!p || !widths) return GRB_ERR_INVALID_ARG;
+    grb_ctx *ctx = p->ctx;
+    GRB_TRY(enter(ctx));
+    if (p->np == 0) return GRB_OK;
+    OutBuf dw;
+    GRB_TRY(dw.stage(ctx, widths, p->np * 4));
+    u64 blocks = (p->nl * 32 + 255) / 256;
+    k_pairs_widths<<<(unsigned)blocks, 256, 0, ctx->stream>>>(p->pos, p->offsets, p->nl, p->ls, p->le, p->idx->starts, p->idx->ends,
+                                                             dw.as<u32>());
+    GRB_LAUNCHED(ctx);
+    GRB_TRY(dw.finish(ctx));
+    GRB_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+    return GRB_OK;
+}
+
+void grb_pairs_destroy(grb_pairs *p) {
+    if (!p) return;
+    cudaSetDevice(p->ctx->device);
+    cudaFree(p->ls);
+    cudaFree(p->le);
+    cudaFree(p->offsets);
+    cudaFree(p->pos);
+    free(p);
+}
+
+}  // extern "C"

@@ -1,0 +1,175 @@
+// sort.cu -- stable LSD radix sort of (u64 key, u32 value) pairs, hand-written.
+//
+// Index build only (replaces the sort inside coitrees' BasicCOITree::new, reached from
+// src/ranges/coitrees.rs:78-84).  8-bit digits; one pre-pass finds which digits vary at all
+// (coordinates < 2^28 leave most of the 8 digits constant) and whether the keys are already
+// sorted (BED files usually are), so typical inputs pay for 0-4 scatter passes.
+//
+// Per pass: tile histograms (digit-major) -> decoupled look-back scan -> stable scatter.  In
+// the scatter a warp ranks its keys with match_any (all lanes holding the same digit elect a
+// leader that bumps the warp's shared-memory counter once), which keeps equal digits in input
+// order without atomics.
+#include "common.cuh"
+
+namespace {
+
+constexpr int SORT_TPB = 256;
+constexpr int SORT_ITEMS = 8;
+constexpr int SORT_TILE = SORT_TPB * SORT_ITEMS;
+constexpr int SORT_WARPS = SORT_TPB / 32;
+
+struct KeyStats {
+    u64 or_all;
+    u64 and_all;
+    u32 unsorted;
+    u32 pad;
+};
+
+__global__ void k_key_stats(const u64 *__restrict__ keys, size_t n, KeyStats *st) {
+    u64 o = 0, a = ~0ull;
+    u32 bad = 0;
+    for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (size_t)gridDim.x * blockDim.x) {
+        u64 k = keys[i];
+        o |= k;
+        a &= k;
+        if (i + 1 < n && keys[i + 1] < k) bad = 1;
+    }
+#pragma unroll
+    for (int s = 16; s; s >>= 1) {
+        o |= __shfl_xor_sync(GRB_FULL, o, s);
+        a &= __shfl_xor_sync(GRB_FULL, a, s);
+        bad |= __shfl_xor_sync(GRB_FULL, bad, s);
+    }
+    if (lane_id() == 0) {
+        atomicOr((unsigned long long *)&st->or_all, (unsigned long long)o);
+        atomicAnd((unsigned long long *)&st->and_all, (unsigned long long)a);
+        if (bad) atomicOr(&st->unsorted, 1u);
+    }
+}
+
+__global__ void __launch_bounds__(SORT_TPB) k_tile_hist(const u64 *__restrict__ keys, size_t n, int shift, u32 ntiles,
+                                                        u32 *__restrict__ hist /* [256][ntiles] */) {
+    __shared__ u32 h[256];
+    h[threadIdx.x] = 0;
+    __syncthreads();
+    const size_t base = (size_t)blockIdx.x * SORT_TILE;
+#pragma unroll
+    for (int i = 0; i < SORT_ITEMS; i++) {
+        size_t g = base + (size_t)i * SORT_TPB + threadIdx.x;
+        if (g < n) atomicAdd(&h[(keys[g] >> shift) & 0xff], 1u);
+    }
+    __syncthreads();
+    hist[(size_t)threadIdx.x * ntiles + blockIdx.x] = h[threadIdx.x];
+}
+
+__global__ void __launch_bounds__(SORT_TPB) k_scatter(const u64 *__restrict__ keys, const u32 *__restrict__ vals, size_t n,
+                                                      int shift, u32 ntiles, const u32 *__restrict__ offs /* [256][ntiles] */,
+                                                      u64 *__restrict__ keys_out, u32 *__restrict__ vals_out) {
+    __shared__ u32 wcnt[SORT_WARPS][256];
+    for (int i = threadIdx.x; i < SORT_WARPS * 256; i += SORT_TPB) (&wcnt[0][0])[i] = 0;
+    __syncthreads();
+    const u32 lane = lane_id(), warp = threadIdx.x >> 5;
+    const u32 lt = (1u << lane) - 1;
+    // warp w owns keys [base + w*256, base + (w+1)*256); item i of lane l is element i*32 + l of that chunk
+    const size_t wbase = (size_t)blockIdx.x * SORT_TILE + (size_t)warp * (32 * SORT_ITEMS);
+    u64 k[SORT_ITEMS];
+    u32 v[SORT_ITEMS], rank[SORT_ITEMS];
+#pragma unroll
+    for (int i = 0; i < SORT_ITEMS; i++) {
+        size_t g = wbase + (size_t)i * 32 + lane;
+        bool ok = g < n;
+        k[i] = ok ? keys[g] : 0;
+        v[i] = ok ? vals[g] : 0;
+    }
+#pragma unroll
+    for (int i = 0; i < SORT_ITEMS; i++) {
+        size_t g = wbase + (size_t)i * 32 + lane;
+        bool ok = g < n;
+        u32 d = (u32)(k[i] >> shift) & 0xff;
+        u32 okmask = __ballot_sync(GRB_FULL, ok);
+        u32 peers = __match_any_sync(GRB_FULL, d) & okmask;
+        int leader = ok ? __ffs(peers) - 1 : 0;
+        u32 old = 0;
+        if (ok && (int)lane == leader) {
+            old = wcnt[warp][d];
+            wcnt[warp][d] = old + __popc(peers);
+        }
+        old = __shfl_sync(GRB_FULL, old, leader);
+        rank[i] = old + __popc(peers & lt);
+        __syncwarp();
+    }
+    __syncthreads();
+    {
+        // thread d turns the per-warp counts of digit d into global bases
+        u32 d = threadIdx.x;
+        u32 run = offs[(size_t)d * ntiles + blockIdx.x];
+#pragma unroll
+        for (int w = 0; w < SORT_WARPS; w++) {
+            u32 c = wcnt[w][d];
+            wcnt[w][d] = run;
+            run += c;
+        }
+    }
+    __syncthreads();
+#pragma unroll
+    for (int i = 0; i < SORT_ITEMS; i++) {
+        size_t g = wbase + (size_t)i * 32 + lane;
+        if (g < n) {
+            u32 d = (u32)(k[i] >> shift) & 0xff;
+            u32 pos = wcnt[warp][d] + rank[i];
+            keys_out[pos] = k[i];
+            vals_out[pos] = v[i];
+        }
+    }
+}
+
+}  // namespace
+
+int grb_sort_pairs(grb_ctx *ctx, u64 *keys, u32 *vals, u64 *keys_alt, u32 *vals_alt, size_t n, u64 **keys_out,
+                   u32 **vals_out, bool *was_sorted) {
+    *keys_out = keys;
+    *vals_out = vals;
+    if (was_sorted) *was_sorted = true;
+    if (n <= 1) return GRB_OK;
+    if (n >= 0xfffffff0ull) return grb_fail(ctx, GRB_ERR_UNSUPPORTED, "sort: more than 2^32-16 ranges on one seqname");
+
+    TempBuf stb;
+    GRB_TRY(stb.alloc(ctx, sizeof(KeyStats)));
+    KeyStats init = {0ull, ~0ull, 0u, 0u};
+    GRB_CUDA(ctx, cudaMemcpyAsync(stb.p, &init, sizeof(init), cudaMemcpyHostToDevice, ctx->stream));
+    int grid = (int)((n + 255) / 256);
+    if (grid > ctx->sm_count * 16) grid = ctx->sm_count * 16;
+    k_key_stats<<<grid, 256, 0, ctx->stream>>>(keys, n, stb.as<KeyStats>());
+    GRB_LAUNCHED(ctx);
+    KeyStats st;
+    GRB_CUDA(ctx, cudaMemcpyAsync(&st, stb.p, sizeof(st), cudaMemcpyDeviceToHost, ctx->stream));
+    GRB_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+    if (!st.unsorted) return GRB_OK;
+    if (was_sorted) *was_sorted = false;
+
+    const u32 ntiles = (u32)((n + SORT_TILE - 1) / SORT_TILE);
+    TempBuf hist, offs;
+    GRB_TRY(hist.alloc(ctx, (size_t)256 * ntiles * sizeof(u32)));
+    GRB_TRY(offs.alloc(ctx, (size_t)256 * ntiles * sizeof(u32)));
+    const u64 varying = st.or_all ^ st.and_all;
+    u64 *kin = keys, *kout = keys_alt;
+    u32 *vin = vals, *vout = vals_alt;
+    for (int pass = 0; pass < 8; pass++) {
+        int shift = pass * 8;
+        if (((varying >> shift) & 0xff) == 0) continue;  // every key has the same digit here
+        k_tile_hist<<<ntiles, SORT_TPB, 0, ctx->stream>>>(kin, n, shift, ntiles, hist.as<u32>());
+        GRB_LAUNCHED(ctx);
+        GRB_TRY(grb_scan_u32_to_u32(ctx, hist.as<u32>(), offs.as<u32>(), (size_t)256 * ntiles, false));
+        k_scatter<<<ntiles, SORT_TPB, 0, ctx->stream>>>(kin, vin, n, shift, ntiles, offs.as<u32>(), kout, vout);
+        GRB_LAUNCHED(ctx);
+        u64 *tk = kin;
+        kin = kout;
+        kout = tk;
+        u32 *tv = vin;
+        vin = vout;
+        vout = tv;
+    }
+    *keys_out = kin;
+    *vals_out = vin;
+    return GRB_OK;
+}

@@ -1,0 +1,329 @@
+"""Parity of the CUDA path (through the C ABI) against the CPU oracle: the reference's golden
+vectors, seeded random cases at sizes the oracle finishes in seconds, edge cases, and
+size-independent properties at larger sizes.  Bit-exact for pairs, counts, min, max, median;
+sum / mean within 1e-12 of sum|x| over the group (f64)."""
+import numpy as np
+import pytest
+
+from tests import golden_checks as gc
+from tests.randcases import ALL_OPS, random_case
+
+pytestmark = pytest.mark.gpu
+
+SUM_TOL = 1e-12
+
+
+@pytest.fixture(scope="module")
+def eng():
+    from tests.engines import CudaEngine
+
+    return CudaEngine()
+
+
+@pytest.fixture(scope="module")
+def orc():
+    from oracle import oracle
+
+    return oracle
+
+
+@pytest.mark.parametrize("check", gc.ALL_ENGINE_CHECKS, ids=lambda f: f.__name__)
+def test_golden(eng, goldens, check):
+    check(eng, goldens)
+
+
+def assert_map_equal(out, ov, want, wv, ops, abs_sums):
+    assert (np.asarray(ov) == wv).all(), "validity (NoValue) mismatch"
+    for c, op in enumerate(ops):
+        m = wv[:, c] == 1
+        if op in ("sum", "sum-not-empty", "mean"):
+            tol = SUM_TOL * np.maximum(abs_sums[m], 0) + 0.0
+            if op == "mean":
+                pass  # |mean error| <= |sum error| / n <= tol
+            err = np.abs(out[m, c] - want[m, c])
+            bad = err > tol
+            assert not bad.any(), (op, out[m, c][bad][:5], want[m, c][bad][:5])
+        else:
+            assert (out[m, c] == want[m, c]).all(), op
+
+
+def run_case(eng, orc, c, ops=ALL_OPS, idx=None):
+    t = orc.Tree(c["rs"], c["re"], idx)
+    ix = eng.build(c["rs"], c["re"], idx, c["scores"], c["valid"])
+    # counts + filter
+    want_counts = np.array([t.count_overlaps(int(a), int(b)) for a, b in zip(c["ls"], c["le"])], dtype=np.uint32) \
+        if len(c["ls"]) <= 5000 else orc.map_joins(t, None, None, c["ls"], c["le"], ["count"])[0][:, 0].astype(np.uint32)
+    got_counts = eng.count(ix, c["ls"], c["le"])
+    assert (got_counts == want_counts).all()
+    assert (eng.filter(ix, c["ls"], c["le"]) == (want_counts > 0)).all()
+    assert (eng.filter(ix, c["ls"], c["le"], anti=True) == (want_counts == 0)).all()
+    # reductions
+    want, wv = orc.map_joins(t, c["scores"], c["valid"], c["ls"], c["le"], ops)
+    abs_sums = orc.map_joins(t, np.abs(c["scores"]), c["valid"], c["ls"], c["le"], ["sum"])[0][:, 0]
+    out, ov = eng.map_joins(ix, c["ls"], c["le"], ops)
+    assert_map_equal(out, ov, want, wv, ops, abs_sums)
+    return ix, t
+
+
+SIZES = [(1, 1), (7, 0), (0, 5), (40, 31), (40, 33), (64, 65), (300, 1000), (1500, 2500), (5000, 300), (1025, 4097)]
+KINDS = {
+    "plain": dict(),
+    "nulls-int": dict(null_frac=0.3, score_kind="int"),
+    "long-mixed": dict(long_frac=0.05, score_kind="mixed"),
+    "dense-ties": dict(maxlen=3, span=50),
+    "wide": dict(score_kind="wide"),
+    "nonfinite": dict(score_kind="nonfinite"),
+    "sorted-left": dict(sorted_left=True, span=20000),
+    "nulls-sorted": dict(null_frac=0.5, sorted_left=True, span=5000),
+}
+
+
+@pytest.mark.parametrize("nl,nr", SIZES)
+@pytest.mark.parametrize("kind", list(KINDS))
+def test_random_vs_oracle(eng, orc, nl, nr, kind):
+    c = random_case(2000 + nl * 7 + nr, nl, nr, **KINDS[kind])
+    run_case(eng, orc, c)
+
+
+def test_sum_paths_agree(eng, orc, monkeypatch):
+    """SUM / MEAN served by compact prefixes, wide prefixes and the sweep must all meet the bound;
+    compact and wide are both exactly-rounded sums, so they agree bit for bit."""
+    c = random_case(77, 3000, 4000, span=30000, sorted_left=True)
+    res = {}
+    for mode in ("1", "2", "0"):
+        monkeypatch.setenv("GRB_SUM_MODE", mode)
+        ix = eng.build(c["rs"], c["re"], None, c["scores"], None)
+        assert ix.exact_sums == (mode != "0")
+        res[mode] = eng.map_joins(ix, c["ls"], c["le"], ["sum", "mean", "sum-not-empty"])
+    assert (res["1"][0] == res["2"][0]).all() and (res["1"][1] == res["2"][1]).all()
+    t = orc.Tree(c["rs"], c["re"])
+    want, wv = orc.map_joins(t, c["scores"], None, c["ls"], c["le"], ["sum", "mean", "sum-not-empty"])
+    for mode in res:
+        assert (res[mode][1] == wv).all()
+        assert np.allclose(res[mode][0], want, rtol=1e-12, atol=0)
+
+
+def test_exact_sum_is_correctly_rounded(eng):
+    """The prefix path returns the correctly rounded value of the exact sum (math.fsum)."""
+    import math
+
+    c = random_case(5, 400, 600, span=3000, score_kind="mixed")
+    ix = eng.build(c["rs"], c["re"], None, c["scores"], None)
+    assert ix.exact_sums
+    out, ov = eng.map_joins(ix, c["ls"], c["le"], ["sum"])
+    for i in range(len(c["ls"])):
+        m = (c["rs"] < c["le"][i]) & (c["re"] > c["ls"][i])
+        assert out[i, 0] == math.fsum(c["scores"][m])
+
+
+def test_tile_modes_agree(orc, monkeypatch):
+    """TMA-staged shared-memory windows vs plain global binary search: identical results."""
+    import granges_b200 as gb
+
+    c = random_case(11, 20000, 30000, span=400000, sorted_left=True, null_frac=0.1)
+    outs = []
+    for mode in ("1", "0"):
+        monkeypatch.setenv("GRB_TILE_MODE", mode)
+        ctx = gb.Context(0)
+        ix = ctx.index_build(c["rs"], c["re"]).set_scores(c["scores"], c["valid"])
+        outs.append((ctx.count_overlaps(ix, c["ls"], c["le"]), ctx.map_joins(ix, c["ls"], c["le"], ["mean", "min", "median"])))
+    assert (outs[0][0] == outs[1][0]).all()
+    assert (outs[0][1][0] == outs[1][1][0]).all() and (outs[0][1][1] == outs[1][1][1]).all()
+    t = orc.Tree(c["rs"], c["re"])
+    want = orc.map_joins(t, None, None, c["ls"], c["le"], ["count"])[0][:, 0]
+    assert (outs[0][0] == want).all()
+
+
+def test_custom_data_index(eng, orc):
+    c = random_case(9, 500, 800, maxlen=5, span=300)
+    idx = np.random.default_rng(1).permutation(800).astype(np.uint64)
+    t = orc.Tree(c["rs"], c["re"], idx)
+    ix = eng.build(c["rs"], c["re"], idx, c["scores"], None)
+    off, gi, gs, ge = eng.left_overlaps(ix, c["ls"], c["le"])
+    woff, wi, ws, we = orc.left_overlaps(t, c["ls"], c["le"])
+    assert (off == woff).all() and (gi == wi).all() and (gs == ws).all() and (ge == we).all()
+    out, ov = eng.map_joins(ix, c["ls"], c["le"], ["mean", "max"])
+    want, wv = orc.map_joins(t, c["scores"], None, c["ls"], c["le"], ["mean", "max"])
+    assert (ov == wv).all() and np.allclose(out, want, rtol=1e-12, atol=0)
+    s, e, d = ix.sorted_ranges()
+    o = np.lexsort((idx, c["re"], c["rs"]))
+    assert (s == c["rs"][o]).all() and (e == c["re"][o]).all() and (d == idx[o]).all()
+
+
+@pytest.mark.parametrize("kw", [dict(), dict(long_frac=0.02), dict(maxlen=4, span=200)], ids=["plain", "long", "ties"])
+def test_pairs_vs_oracle(eng, orc, kw):
+    c = random_case(31, 3000, 5000, **kw)
+    t = orc.Tree(c["rs"], c["re"])
+    ix = eng.build(c["rs"], c["re"])
+    res = eng.ctx.left_overlaps(ix, c["ls"], c["le"], widths=True)
+    off, gi, gs, ge, w = res
+    woff, wi, ws, we = orc.left_overlaps(t, c["ls"], c["le"])
+    assert (off == woff).all() and (gi == wi).all() and (gs == ws).all() and (ge == we).all()
+    lid = np.repeat(np.arange(len(c["ls"])), np.diff(off.astype(np.int64)))
+    ww = np.minimum(c["le"][lid], ge).astype(np.int64) - np.maximum(c["ls"][lid], gs).astype(np.int64)
+    assert (w == ww).all() and (ww > 0).all()
+
+
+def test_median_heavy_groups(eng, orc):
+    """Groups with more members than the in-warp buffer (256) take the radix-select path."""
+    rng = np.random.default_rng(4)
+    nr = 6000
+    rs = rng.integers(0, 2000, nr).astype(np.uint32)
+    re = (rs + rng.integers(1, 800, nr)).astype(np.uint32)
+    sc = np.round(rng.standard_normal(nr) * 50) / 8  # many ties, both signs, +-0
+    sc[:7] = 0.0
+    sc[7:14] = -0.0
+    valid = (rng.random(nr) > 0.2).astype(np.uint8)
+    ls = rng.integers(0, 2500, 300).astype(np.uint32)
+    le = (ls + rng.integers(1, 1500, 300)).astype(np.uint32)
+    c = dict(ls=ls, le=le, rs=rs, re=re, scores=sc, valid=valid)
+    ix, t = run_case(eng, orc, c, ops=["median", "min", "max", "count", "mean"])
+    cnt = eng.count(ix, ls, le)
+    assert cnt.max() > 1000
+
+
+def test_hg38_like_100k(eng, orc):
+    """BASELINE.json configs[0]: 100k x 100k random ranges, lengths U{1..999} (chr1-sized seqname)."""
+    rng = np.random.default_rng(13)
+    n, span = 100_000, 5_000_000
+    ln = rng.integers(1, 1000, n)
+    rs = (rng.random(n) * (span - ln)).astype(np.uint32)
+    re = (rs + ln).astype(np.uint32)
+    ln = rng.integers(1, 1000, n)
+    ls = np.sort((rng.random(n) * (span - ln)).astype(np.uint32))
+    le = (ls + ln).astype(np.uint32)
+    c = dict(ls=ls, le=le, rs=rs, re=re, scores=rng.random(n), valid=None)
+    run_case(eng, orc, c, ops=["mean", "sum", "min", "max", "median", "count"])
+
+
+def test_batch_multi_seqname(eng, orc):
+    """Whole-GRanges call: 5 seqnames (one absent in the right, one without lefts) in one launch."""
+    import granges_b200 as gb
+
+    ctx = eng.ctx
+    cases = [random_case(100 + s, nl, nr, span=50000, sorted_left=True) for s, (nl, nr) in
+             enumerate([(3000, 2000), (0, 500), (1500, 0), (2048, 4000), (1, 1)])]
+    idxs, trees = [], []
+    for s, c in enumerate(cases):
+        if s == 2:
+            idxs.append(None)  # seqname absent in the right
+            trees.append(None)
+        else:
+            idxs.append(ctx.index_build(c["rs"], c["re"]).set_scores(c["scores"]))
+            trees.append(orc.Tree(c["rs"], c["re"]))
+    off = np.concatenate([[0], np.cumsum([len(c["ls"]) for c in cases])]).astype(np.uint64)
+    ls = np.concatenate([c["ls"] for c in cases])
+    le = np.concatenate([c["le"] for c in cases])
+    ops = ["mean", "count", "max", "median", "sum"]
+    out, ov = ctx.map_joins_batch(idxs, off, ls, le, ops)
+    cnt = ctx.count_overlaps_batch(idxs, off, ls, le)
+    keep, nk = ctx.filter_overlaps_batch(idxs, off, ls, le)
+    akeep, ank = ctx.filter_overlaps_batch(idxs, off, ls, le, anti=True)
+    for s, c in enumerate(cases):
+        sl = slice(int(off[s]), int(off[s + 1]))
+        want, wv = orc.map_joins(trees[s], c["scores"] if trees[s] is not None else None, None, c["ls"], c["le"], ops)
+        assert (ov[sl] == wv).all()
+        m = wv == 1
+        assert np.allclose(out[sl][m], want[m], rtol=1e-12, atol=0)
+        assert (out[sl][:, 2][wv[:, 2] == 1] == want[:, 2][wv[:, 2] == 1]).all()
+        assert (cnt[sl] == want[:, 1]).all()
+        assert (keep[sl] == (want[:, 1] > 0)).all() and (akeep[sl] == (want[:, 1] == 0)).all()
+    assert nk == int(keep.sum()) and ank == int(akeep.sum()) and nk + ank == len(ls)
+
+
+def test_device_resident_buffers(eng, orc):
+    """torch CUDA tensors in, torch CUDA tensors out (no host staging)."""
+    import torch
+
+    c = random_case(55, 5000, 5000, span=60000, sorted_left=True)
+    ix = eng.build(c["rs"], c["re"], None, c["scores"], None)
+    dls = torch.from_numpy(c["ls"].astype(np.int32)).cuda()
+    dle = torch.from_numpy(c["le"].astype(np.int32)).cuda()
+    out, ov = eng.ctx.map_joins(ix, dls, dle, ["mean", "count"])
+    eng.ctx.sync()
+    assert out.is_cuda
+    h, hv = eng.ctx.map_joins(ix, c["ls"], c["le"], ["mean", "count"])
+    assert (out.cpu().numpy() == h).all() and (ov.cpu().numpy() == hv).all()
+
+
+def test_windows_large_property(eng, orc):
+    """hg38-sized window generation: device closed form == the reference's loop (oracle)."""
+    lens = [248_956_422 // 50, 1_000_003, 999, 1000, 1001, 1]
+    for width, step, chop in [(1000, 500, False), (1000, 500, True), (1000, None, False), (131123, 10001, True), (7, 3, False)]:
+        got = eng.windows(lens, width, step, chop)
+        want = orc.windows(lens, width, step, chop)
+        for g, w in zip(got, want):
+            assert len(g) == len(w) and (g == w).all()
+
+
+def test_windows_then_map(eng, orc):
+    """windows -> left_overlaps -> map_joins without leaving the device (granges windows | granges map)."""
+    rng = np.random.default_rng(8)
+    L, nr = 2_000_000, 50_000
+    ln = rng.integers(1, 1000, nr)
+    rs = (rng.random(nr) * (L - ln)).astype(np.uint32)
+    re = (rs + ln).astype(np.uint32)
+    sc = rng.random(nr)
+    ix = eng.build(rs, re, None, sc, None)
+    w = eng.ctx.windows_dev([L], 1000, 500, False)
+    import ctypes as C
+
+    import granges_b200._capi as capi
+
+    ps, pe = w.dev_ptrs()
+    n = len(w)
+    out = np.empty((n, 1))
+    ov = np.empty((n, 1), np.uint8)
+    ops = (C.c_int * 1)(4)
+    rc = capi.lib().grb_map_joins_f64(eng.ctx.h, ix.h, ps, pe, n, ops, 1, out.ctypes.data, ov.ctypes.data)
+    assert rc == 0
+    q, s, e = w.copy()
+    want, wv = orc.map_joins(orc.Tree(rs, re), sc, None, s, e, ["mean"])
+    assert (ov == wv).all() and np.allclose(out[wv == 1], want[wv == 1], rtol=1e-12, atol=0)
+
+
+def test_errors(eng):
+    import granges_b200 as gb
+
+    ctx = eng.ctx
+    with pytest.raises(gb.GRangesError) as ei:
+        ctx.index_build([5], [5])
+    assert ei.value.code == -2  # end <= start: the reference asserts (ranges/mod.rs:109)
+    with pytest.raises(gb.GRangesError) as ei:
+        ctx.index_build([0], [2**31 + 5])
+    assert ei.value.code == -2  # does not fit i32 (ranges/coitrees.rs:53-54)
+    ix = ctx.index_build([0, 10], [5, 20])
+    with pytest.raises(gb.GRangesError) as ei:
+        ctx.map_joins(ix, [0], [10], ["mean"])
+    assert ei.value.code == -3  # NoDataContainer
+    out, ov = ctx.map_joins(ix, [0], [10], ["count"])
+    assert out[0, 0] == 1
+    with pytest.raises(gb.GRangesError) as ei:
+        ix.set_scores([1.0])  # data index 1 out of range
+    assert ei.value.code == -7
+    ix.set_scores([1.0, float("nan")])
+    with pytest.raises(gb.GRangesError) as ei:
+        ctx.map_joins(ix, [0], [30], ["median"])
+    assert ei.value.code == -6  # the reference panics on NaN in median
+    out, ov = ctx.map_joins(ix, [0], [30], ["sum", "min"])
+    assert np.isnan(out[0, 0]) and out[0, 1] == 1.0
+    with pytest.raises(gb.GRangesError):
+        ctx.map_joins(ix, [0], [30], [99])
+
+
+def test_unsorted_index_large_sort(eng, orc):
+    """Index build from shuffled input exercises every radix pass (coordinates up to 2^31-1)."""
+    rng = np.random.default_rng(21)
+    n = 200_000
+    rs = rng.integers(0, 2**31 - 2000, n).astype(np.uint32)
+    re = (rs + rng.integers(1, 1000, n)).astype(np.uint32)
+    ix = eng.build(rs, re)
+    s, e, d = ix.sorted_ranges()
+    o = np.lexsort((np.arange(n), re, rs))
+    assert (s == rs[o]).all() and (e == re[o]).all() and (d == o).all()
+    ls = np.sort(rng.integers(0, 2**31 - 5000, 50_000).astype(np.uint32))
+    le = ls + 4000
+    got = eng.count(ix, ls, le)
+    es = np.sort(re)
+    want = np.searchsorted(np.sort(rs), le, side="left") - np.searchsorted(es, ls, side="right")
+    assert (got == want).all()
