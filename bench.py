@@ -1,0 +1,454 @@
+#!/usr/bin/env python
+"""bench.py -- `granges map --func mean` hot path (left_overlaps + map_joins(mean)) on synthetic hg38.
+
+Workload (BASELINE.json north_star / metric): 100M left x 100M right ranges over the 22 hg38
+autosomes, generated like the reference's random_granges (src/test_utilities.rs:60-164: lengths
+U{1..999}, starts uniform, scores U[0,1), equal share per seqname), both sides sorted.
+
+  value      left ranges/s of one map pass (left_overlaps + map_joins(mean), index already built,
+             everything resident in HBM), CUDA events on the launching stream, max over ranks
+  e2e        the same metric through the C ABI with HOST (pinned) buffers: H2D of rights + lefts,
+             index build, map pass, D2H of the results, all inside the timed region
+  roofline   the dominant kernel (k_tile<MAP>) against the measured HBM peak
+  cpu_baseline / --impl reference
+             the CPU oracle (coitrees-restated, oracle/granges_oracle.c) on a bounded sample
+             (one whole seqname) -- the reference is Rust and cannot be built in this image
+N > 1: strong scaling -- the same 100M x 100M job split into independent units by seqname /
+coordinate (grb_shard_plan), no data-path collective.
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import subprocess
+import sys
+import tempfile
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+if ROOT not in sys.path:
+    sys.path.insert(0, ROOT)
+
+import numpy as np  # noqa: E402
+import torch  # noqa: E402
+
+HG38 = [248956422, 242193529, 198295559, 190214555, 181538259, 170805979, 159345973, 145138636, 138394717, 133797422,
+        135086622, 133275309, 114364328, 107043718, 101991189, 90338345, 83257441, 80373285, 58617616, 64444167, 46709983,
+        50818468]  # chr1..chr22, tests_data/hg38_seqlens.tsv
+
+M63 = (1 << 63) - 1
+
+
+def _lsr(z, k):
+    return (z >> k) & ((1 << (64 - k)) - 1)
+
+
+def _mix(x):
+    """splitmix64 finaliser on int64 tensors (wrapping arithmetic): identical on CPU and CUDA."""
+    z = x + (-7046029254386353131)
+    z = (z ^ _lsr(z, 30)) * (-4658895280553007687)
+    z = (z ^ _lsr(z, 27)) * (-7723592293110705685)
+    return z ^ _lsr(z, 31)
+
+
+def gen_ranges(seq, n, seed, device, with_scores):
+    """n sorted ranges on seqname `seq`: (starts int32, ends int32[, scores f64 by sorted position])."""
+    L = HG38[seq]
+    i = torch.arange(n, dtype=torch.int64, device=device)
+    base = i * 4 + (seed * 1000003 + seq * 7919) * 1_000_000_007
+    ln = 1 + (_mix(base) & M63) % 999
+    st = (_mix(base + 1) & M63) % (L - ln + 1)
+    key, _ = torch.sort(st * 4294967296 + (st + ln))
+    starts = (key >> 32).to(torch.int32)
+    ends = (key & 0xFFFFFFFF).to(torch.int32)
+    if not with_scores:
+        return starts, ends
+    sc = _lsr(_mix(base + 2), 11).to(torch.float64) * (2.0 ** -53)
+    return starts, ends, sc
+
+
+def split_counts(total, nseq):
+    q, r = divmod(total, nseq)
+    return [q + (1 if s < r else 0) for s in range(nseq)]
+
+
+class ClockSampler:
+    """SM clock and throttle reasons sampled DURING the timed region (NVML, every ~5 ms, own thread)."""
+    REASONS = {0x8: "hw_slowdown", 0x40: "hw_thermal_slowdown", 0x20: "sw_thermal_slowdown", 0x4: "sw_power_cap"}
+
+    def __init__(self, gpu_index):
+        import threading
+
+        self.sm, self.reason_bits, self.max_mhz, self.err = [], 0, None, None
+        self._stop = threading.Event()
+        self._ready = threading.Event()
+        self._idx = gpu_index
+        self._t = threading.Thread(target=self._run, daemon=True)
+        self._t.start()
+        self._ready.wait(timeout=10)
+
+    def _run(self):
+        try:
+            import pynvml as nv
+
+            nv.nvmlInit()
+            uuid = torch.cuda.get_device_properties(self._idx).uuid
+            try:
+                h = nv.nvmlDeviceGetHandleByUUID(("GPU-" + str(uuid)).encode())
+            except Exception:
+                h = nv.nvmlDeviceGetHandleByIndex(self._idx)
+            self.max_mhz = float(nv.nvmlDeviceGetMaxClockInfo(h, nv.NVML_CLOCK_SM))
+            self._ready.set()
+            while not self._stop.is_set():
+                self.sm.append(float(nv.nvmlDeviceGetClockInfo(h, nv.NVML_CLOCK_SM)))
+                self.reason_bits |= int(nv.nvmlDeviceGetCurrentClocksEventReasons(h))
+                time.sleep(0.003)
+            # one more sample after the region so that a very short region still has >= 2
+            self.sm.append(float(nv.nvmlDeviceGetClockInfo(h, nv.NVML_CLOCK_SM)))
+            self.reason_bits |= int(nv.nvmlDeviceGetCurrentClocksEventReasons(h))
+        except Exception as e:  # noqa: BLE001
+            self.err = repr(e)
+            self._ready.set()
+
+    def stop(self):
+        self._stop.set()
+        self._t.join(timeout=5)
+        out = {"sm_mhz": None, "sm_max_mhz": self.max_mhz, "reasons": [], "samples": len(self.sm)}
+        if self.sm:
+            out["sm_mhz"] = float(np.median(self.sm))
+            out["reasons"] = sorted(n for b, n in self.REASONS.items() if self.reason_bits & b)
+        if self.err:
+            out["error"] = self.err
+        return out
+
+
+def pick_sample_seqs(nl_per, nr_per, nsample=5):
+    """The seqnames whose expected pairs/left are closest to the genome-wide mean (cpu sample)."""
+    dens = np.array([nr_per[s] * 1000.0 / HG38[s] for s in range(22)])
+    mean = float((dens * np.array(nl_per)).sum() / sum(nl_per))
+    order = np.argsort(np.abs(dens - mean), kind="stable")
+    return [int(s) for s in order[:nsample]], mean
+
+
+def cpu_sample_data(seqs, nl_per, nr_per):
+    data = []
+    for seq in seqs:
+        rs, re, sc = (t.numpy() for t in gen_ranges(seq, nr_per[seq], 14, "cpu", True))
+        ls, le = (t.numpy() for t in gen_ranges(seq, nl_per[seq], 13, "cpu", False))
+        data.append(tuple(a.astype(np.uint32) for a in (rs, re, ls, le)) + (sc,))
+    return data
+
+
+def cpu_reference_run(data, threads, ops=("mean",)):
+    """Oracle (coitrees-restated) on whole seqnames: tree build + left_overlaps + map_joins, the
+    in-memory work of `granges map` (into_coitrees + left_overlaps + map_joins).  threads == 1 is
+    the reference's own execution model (single thread, seqnames one after another); threads > 1
+    runs the seqnames concurrently and splits each seqname's lefts over the remaining threads."""
+    from concurrent.futures import ThreadPoolExecutor
+
+    from oracle import oracle as orc
+
+    per_seq = max(1, threads // len(data))
+
+    def one(d):
+        rs, re, ls, le, sc = d
+        t0 = time.perf_counter()
+        tree = orc.Tree(rs, re)
+        t1 = time.perf_counter()
+        res = orc.map_joins(tree, sc, None, ls, le, list(ops), nthreads=per_seq)
+        return t1 - t0, time.perf_counter() - t1, res
+
+    t0 = time.perf_counter()
+    if threads == 1:
+        parts = [one(d) for d in data]
+    else:
+        with ThreadPoolExecutor(max_workers=min(threads, len(data))) as ex:
+            parts = list(ex.map(one, data))
+    total = time.perf_counter() - t0
+    return dict(build_s=sum(p[0] for p in parts), map_s=sum(p[1] for p in parts), total_s=total, first=parts[0][2])
+
+
+def reference_arm(args):
+    """--impl reference: the reference's CPU algorithm (oracle port) on the host cores."""
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    from oracle import oracle as orc
+
+    orc.build()
+    nl_per, nr_per = split_counts(args.lefts, 22), split_counts(args.rights, 22)
+    seqs, mean_ppl = pick_sample_seqs(nl_per, nr_per)
+    data = cpu_sample_data(seqs, nl_per, nr_per)
+    n_sample = sum(nl_per[s] for s in seqs)
+    threads = orc.max_threads()
+    times = []
+    for it in range(args.warmup + args.steps):
+        r = cpu_reference_run(data, threads, tuple(args.ops.split(",")))
+        if it >= args.warmup:
+            times.append(r["total_s"])
+        last = r
+    t = float(np.mean(times))
+    value = n_sample / t
+    line = {
+        "impl": "reference", "metric": "map_mean left ranges/s", "value": value, "unit": "left ranges/s", "n_gpus": args.gpus,
+        "steps": args.steps, "warmup": args.warmup, "ms_per_step": t * 1e3, "higher_is_better": True, "scaling": "strong",
+        "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+        "config": workload_config(args),
+        "cpu_baseline": {"value": value, "unit": "left ranges/s", "cores": threads, "kind": "port",
+                         "sample": f"{len(seqs)} whole seqnames ({','.join('chr%d' % (q + 1) for q in seqs)}; {n_sample} lefts x "
+                                   f"{sum(nr_per[q] for q in seqs)} rights, ~{mean_ppl:.1f} pairs/left) per step: tree build + "
+                                   f"left_overlaps + map_joins, seqnames concurrent, {threads} threads in all "
+                                   f"(summed thread time: build {last['build_s']:.2f} s, join+reduce {last['map_s']:.2f} s)"},
+        "e2e": {"value": value, "unit": "left ranges/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+    }
+    print(json.dumps(line))
+
+
+def workload_config(args):
+    return {"workload": f"granges map --func mean: {args.lefts} left x {args.rights} right synthetic hg38 ranges (22 autosomes, "
+                        "len U{1..999}, sorted BED3 x BED5)",
+            "lefts": args.lefts, "rights": args.rights, "ops": ["mean"], "l2": "inputs_larger_than_l2",
+            "sharding": "seqname/coordinate units, no collective"}
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=10)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--lefts", type=int, default=100_000_000)
+    ap.add_argument("--rights", type=int, default=100_000_000)
+    ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
+    ap.add_argument("--no-e2e", action="store_true")
+    ap.add_argument("--ops", default="mean")
+    args = ap.parse_args()
+    if args.impl == "reference":
+        reference_arm(args)
+        return
+
+    rank = int(os.environ.get("RANK", "0"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py needs a CUDA device: granges_b200 has no CPU fallback")
+    torch.cuda.set_device(local_rank)
+    dev = torch.device("cuda", local_rank)
+    dist = None
+    if world > 1:
+        import torch.distributed as dist
+
+        dist.init_process_group("nccl", device_id=dev)
+
+    import granges_b200 as gb
+
+    ops = args.ops.split(",")
+    k = len(ops)
+    nl_per, nr_per = split_counts(args.lefts, 22), split_counts(args.rights, 22)
+    left_off = np.concatenate([[0], np.cumsum(nl_per)]).astype(np.uint64)
+
+    # ---- shard plan (identical on every rank; bounds come from the data below)
+    plan = gb.shard_plan(left_off, nr_per, None, None, world)
+    mine = [p for p in plan if p["rank"] == rank]
+
+    # a non-default stream: stream-ordered allocation on the legacy default stream is several times slower
+    stream = torch.cuda.Stream(device=dev)
+    torch.cuda.set_stream(stream)
+    ctx = gb.Context(local_rank, stream=stream)
+    # ---- synthetic data, generated on the device, only what this rank's units touch
+    idxs, offs, ls_parts, le_parts, host_parts = [], [0], [], [], []
+    n_right_mine = 0
+    t_build = 0.0
+    for p in mine:
+        s = p["seq"]
+        a, b = p["left_begin"] - int(left_off[s]), p["left_end"] - int(left_off[s])
+        ls_s, le_s = gen_ranges(s, nl_per[s], 13, dev, False)
+        ls_s, le_s = ls_s[a:b].contiguous(), le_s[a:b].contiguous()
+        rs, re, sc = gen_ranges(s, nr_per[s], 14, dev, True)
+        if (a, b) != (0, nl_per[s]):
+            # a coordinate slice of the seqname: keep the rights that can overlap this run of lefts
+            lo, hi = int(ls_s.min()), int(le_s.max())
+            m = (rs < hi) & (re > lo)
+            rs, re, sc = rs[m].contiguous(), re[m].contiguous(), sc[m].contiguous()
+        torch.cuda.synchronize()
+        t0 = time.perf_counter()
+        ix = ctx.index_build(rs, re).set_scores(sc)
+        ctx.sync()
+        t_build += time.perf_counter() - t0
+        idxs.append(ix)
+        n_right_mine += len(rs)
+        offs.append(offs[-1] + (b - a))
+        ls_parts.append(ls_s)
+        le_parts.append(le_s)
+        if rank == 0 and world == 1 and not args.no_e2e:
+            host_parts.append((rs.cpu(), re.cpu(), sc.cpu()))
+        del rs, re, sc
+    ls = torch.cat(ls_parts) if ls_parts else torch.zeros(0, dtype=torch.int32, device=dev)
+    le = torch.cat(le_parts) if le_parts else torch.zeros(0, dtype=torch.int32, device=dev)
+    del ls_parts, le_parts
+    nl_mine = int(offs[-1])
+    offs = np.array(offs, dtype=np.uint64)
+    out = torch.empty((nl_mine, k), dtype=torch.float64, device=dev)
+    ov = torch.empty((nl_mine, k), dtype=torch.uint8, device=dev)
+
+    def step():
+        if nl_mine:
+            ctx.map_joins_batch(idxs, offs, ls, le, ops, out=out, out_valid=ov)
+
+    def barrier():
+        if dist is not None:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    for _ in range(args.warmup):
+        step()
+    barrier()
+    sampler = ClockSampler(local_rank) if rank == 0 else None
+    launches0 = ctx.launch_count
+    evs = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(args.steps)]
+    t_all0, t_all1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    barrier()
+    t_all0.record()
+    for e0, e1 in evs:
+        e0.record()
+        step()
+        e1.record()
+    t_all1.record()
+    barrier()
+    launches = ctx.launch_count - launches0
+    clocks = sampler.stop() if sampler else None
+    total_ms = t_all0.elapsed_time(t_all1)
+    per_step = [a.elapsed_time(b) for a, b in evs]
+    tmax = torch.tensor([total_ms], dtype=torch.float64, device=dev)
+    if dist is not None:
+        dist.all_reduce(tmax, op=dist.ReduceOp.MAX)
+    total_ms_max = float(tmax.item())
+    ms_per_step = total_ms_max / args.steps
+
+    # ---- results: pairs (for pairs/s) and a checksum
+    pairs_mine = 0
+    if nl_mine:
+        cnt = ctx.count_overlaps_batch(idxs, offs, ls, le)
+        ctx.sync()
+        pairs_mine = int(cnt.to(torch.int64).sum().item())
+        del cnt
+    agg = torch.tensor([pairs_mine, nl_mine, n_right_mine], dtype=torch.int64, device=dev)
+    if dist is not None:
+        dist.all_reduce(agg)
+    pairs_total, nl_total = int(agg[0].item()), int(agg[1].item())
+
+    if rank != 0:
+        if dist is not None:
+            dist.barrier()
+            dist.destroy_process_group()
+        return
+
+    # keep one seqname's device-timed results for the parity check against the oracle below
+    chk_seq = pick_sample_seqs(nl_per, nr_per)[0][0]
+    chk_slice = None
+    if world == 1:
+        a, b = int(left_off[chk_seq]), int(left_off[chk_seq + 1])
+        chk_slice = (out[a:b].cpu().numpy(), ov[a:b].cpu().numpy())
+
+    value = args.lefts / (ms_per_step * 1e-3)
+    line = {
+        "metric": "map_mean left ranges/s", "value": value, "unit": "left ranges/s", "n_gpus": world, "steps": args.steps,
+        "warmup": args.warmup, "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "strong", "vs_baseline": None,
+        "dtype": "f64", "data": "synthetic", "config": workload_config(args),
+        "pairs_per_s": pairs_total / (ms_per_step * 1e-3), "overlap_pairs": pairs_total, "lefts_processed": nl_total,
+        "index_build_ms_rank0": t_build * 1e3, "gpu_launches": int(launches), "clocks": clocks,
+        "step_ms_rank0": {"min": min(per_step), "median": float(np.median(per_step)), "max": max(per_step)},
+        "units_rank0": len(mine),
+    }
+    if ops != ["mean"]:
+        line["metric"] = "map_%s left ranges/s" % "_".join(ops)
+        line["config"]["ops"] = ops
+
+    # ---- roofline of the dominant kernel (k_tile<MAP>: the only kernel of a map_mean step)
+    peaks_path = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(peaks_path):
+        peak, peak_src = float(json.load(open(peaks_path))["hbm_gbs"]), "measured (MEASURED_PEAKS.json hbm_gbs)"
+    else:
+        peak, peak_src = 6650.0, "fallback (B200_PROFILING.md)"
+    nr_tot = int(agg[2].item())
+    alg_bytes = nl_total * 8 + nr_tot * 16 + nl_total * k * 8 + nl_total * k / 8  # B_map
+    kernel_ms = float(np.mean(per_step))  # rank 0's launch duration (one k_tile launch per step when ops = mean)
+    alg_rank0 = nl_mine * 8 + n_right_mine * 16 + nl_mine * k * 8 + nl_mine * k / 8
+    achieved = alg_rank0 / (kernel_ms * 1e-3) / 1e9
+    line["roofline"] = {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
+                        "traffic": None, "peak_source": peak_src, "kernel": "k_tile<M_MAP>", "kernel_ms": kernel_ms,
+                        "algorithmic_bytes_per_launch": alg_rank0, "algorithmic_bytes_whole_job": alg_bytes}
+    prof = os.path.join(ROOT, "profiles", "traffic.json")
+    if os.path.exists(prof):
+        try:
+            tj = json.load(open(prof))
+            if tj.get("lefts") == nl_mine:
+                line["roofline"]["traffic"] = tj.get("dram_bytes_per_launch")
+        except Exception:
+            pass
+
+    # ---- e2e: host (pinned) buffers through the C ABI, copies inside the timed region
+    if world == 1 and not args.no_e2e:
+        h_ls, h_le = ls.cpu().pin_memory(), le.cpu().pin_memory()
+        h_rights = [(a.pin_memory(), b.pin_memory(), c.pin_memory()) for a, b, c in host_parts]
+        h_out = torch.empty((nl_mine, k), dtype=torch.float64).pin_memory()
+        h_ov = torch.empty((nl_mine, k), dtype=torch.uint8).pin_memory()
+        for ix in idxs:
+            ix.close()
+        idxs.clear()
+        del out, ov
+        torch.cuda.empty_cache()
+
+        def e2e_step():
+            hs = [ctx.index_build(a.numpy().view(np.uint32), b.numpy().view(np.uint32)).set_scores(c.numpy()) for a, b, c in h_rights]
+            ctx.map_joins_batch(hs, offs, h_ls.numpy().view(np.uint32), h_le.numpy().view(np.uint32), ops, out=h_out.numpy(),
+                                out_valid=h_ov.numpy())
+            chk = float(h_out[0, 0])  # the result is on the host
+            for h in hs:
+                h.close()
+            return chk
+
+        e2e_steps = max(2, min(args.steps, 3))
+        e2e_step()
+        torch.cuda.synchronize()
+        t0 = time.perf_counter()
+        for _ in range(e2e_steps):
+            e2e_step()
+        torch.cuda.synchronize()
+        e2e_s = (time.perf_counter() - t0) / e2e_steps
+        h2d = nr_tot * 16 + nl_total * 8
+        d2h = nl_total * k * 9
+        line["e2e"] = {"value": args.lefts / e2e_s, "unit": "left ranges/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
+                       "ms_per_step": e2e_s * 1e3, "steps": e2e_steps,
+                       "includes": "H2D rights+scores+lefts (pinned), index build (22 seqnames), map pass, D2H results"}
+        del h_rights, h_ls, h_le
+    else:
+        line["e2e"] = None
+
+    # ---- cpu baseline: the oracle on a bounded sample (one seqname), 1 thread like the reference
+    if world == 1 and not args.no_cpu:
+        seqs, mean_ppl = pick_sample_seqs(nl_per, nr_per)
+        data = cpu_sample_data(seqs, nl_per, nr_per)
+        n_sample = sum(nl_per[q] for q in seqs)
+        r = cpu_reference_run(data, 1, tuple(ops))
+        want, wv = r["first"]
+        got, gv = chk_slice
+        okv = bool((gv == wv).all())
+        m = wv == 1
+        rel = float(np.max(np.abs(got[m] - want[m]) / np.maximum(np.abs(want[m]), 1e-300))) if m.any() else 0.0
+        line["parity_check"] = {"seqname": f"chr{chk_seq + 1}", "lefts": int(len(want)), "validity_equal": okv, "max_rel_err": rel,
+                                "tolerance": 1e-12, "ok": bool(okv and rel <= 1e-12)}
+        line["cpu_baseline"] = {"value": n_sample / r["total_s"], "unit": "left ranges/s", "cores": 1, "kind": "port",
+                                "sample": f"{len(seqs)} whole seqnames ({','.join('chr%d' % (q + 1) for q in seqs)}; {n_sample} lefts x "
+                                          f"{sum(nr_per[q] for q in seqs)} rights, ~{mean_ppl:.1f} pairs/left): tree build "
+                                          f"{r['build_s']:.2f} s + left_overlaps + map_joins {r['map_s']:.2f} s, single thread "
+                                          f"like the reference (host has {os.cpu_count()} cores)"}
+    print(json.dumps(line))
+    if dist is not None:
+        dist.barrier()
+        dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    main()

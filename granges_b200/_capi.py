@@ -29,6 +29,7 @@ SIGNATURES = {
     "grb_abi_version": (C.c_int, []),
     "grb_ctx_create": (C.c_int, [C.c_int, C.POINTER(vp)]),
     "grb_ctx_set_stream": (C.c_int, [vp, vp]),
+    "grb_ctx_use_own_stream": (C.c_int, [vp]),
     "grb_ctx_sync": (C.c_int, [vp]),
     "grb_ctx_destroy": (None, [vp]),
     "grb_last_error": (C.c_char_p, [vp]),

@@ -165,8 +165,12 @@ class Context:
             raise GRangesError(rc, _capi.lib().grb_last_error(self.h).decode())
 
     def set_stream(self, stream):
-        ptr = getattr(stream, "cuda_stream", stream)
-        self._check(_capi.lib().grb_ctx_set_stream(self.h, ptr))
+        """Run on `stream` (a torch.cuda.Stream or a raw cudaStream_t; 0 is the default stream); None = own stream."""
+        if stream is None:
+            self._check(_capi.lib().grb_ctx_use_own_stream(self.h))
+            return
+        ptr = int(getattr(stream, "cuda_stream", stream))
+        self._check(_capi.lib().grb_ctx_set_stream(self.h, C.c_void_p(ptr)))
 
     def sync(self):
         self._check(_capi.lib().grb_ctx_sync(self.h))

@@ -25,6 +25,8 @@ struct grb_ctx {
     cudaStream_t stream;
     cudaMemPool_t pool;
     u64 launches;
+    void *zeros;    // 1 KB of zeros (tables) + 1 KB of 0xff (sentinel keys): what an absent seqname / empty index reads
+    int pipe_mode;  // 1 = persistent warp-specialised pipeline for single-reduction maps (default), 0 = k_tile only (debug)
     int tile_mode;  // 1 = TMA-staged smem windows (default), 0 = global binary search only (debug)
     char err[512];
 };
@@ -39,9 +41,9 @@ int grb_fail(grb_ctx *ctx, int code, const char *fmt, ...);
                             "%s:%d: %s: %s", __FILE__, __LINE__, #expr, cudaGetErrorString(_e));    \
     } while (0)
 
-#define GRB_TRY(expr)          \
+#define GRB_TRY(...)           \
     do {                       \
-        int _rc = (expr);      \
+        int _rc = (__VA_ARGS__); \
         if (_rc != GRB_OK) return _rc; \
     } while (0)
 
@@ -118,7 +120,7 @@ bool grb_is_device_ptr(const void *p);
 // How SUM / MEAN are answered for one index.
 enum { GRB_SUM_SWEEP = 0, GRB_SUM_COMPACT = 1, GRB_SUM_WIDE = 2 };
 
-#define GRB_BASE_SHIFT 8  // compact mode: one i128 base per 256 rights, i64 local prefixes inside
+#define GRB_BASE_SHIFT 8  // compact mode: one exact i128 base per 256 rights beside the 64-bit wrapped prefixes
 #define GRB_BME_SHIFT 6   // block-max-end granularity: 64 rights
 
 struct grb_index {
@@ -141,10 +143,16 @@ struct grb_index {
     u32 *vcnt_b;      // n+1 prefix count of valid scores (end order), only if has_nulls
     int sum_mode;
     int e0;       // fixed-point unit = 2^e0
-    i64 *loc_a;   // compact: n+1 local prefixes (start order)
-    i64 *loc_b;   // compact: n+1 local prefixes (end order)
-    i128 *base_a; // compact: (n>>8)+1 block bases;  wide: n+1 full prefixes
+    int width;    // bits of the largest |score| in fixed point (W)
+    u64 *pfx_a;   // compact: n+1 prefixes mod 2^64 (start order)
+    u64 *pfx_b;   // compact: n+1 prefixes mod 2^64 (end order)
+    i128 *base_a; // compact: (n>>8)+1 exact block bases;  wide: n+1 exact prefixes
     i128 *base_b;
+    // coordinate-bin lookup tables: lut[b] = #keys < (b << lut_shift), b in [0, lut_bmax + 1]
+    int lut_shift;
+    u32 lut_bmax;
+    u32 *lut_a;   // over starts
+    u32 *lut_b;   // over ends_sorted
 };
 
 // Per-seqname view handed to the kernels (one entry per seqname of a batch).
@@ -152,11 +160,16 @@ struct SeqDev {
     const u32 *starts, *ends, *ends_sorted, *didx, *bme;
     const double *score_a;
     const u32 *vbits_a, *vcnt_a, *vcnt_b;
-    const i64 *loc_a, *loc_b;
+    const u64 *pfx_a, *pfx_b;
     const i128 *base_a, *base_b;
+    const u32 *lut_a, *lut_b;
     u64 left_begin, left_end;
+    double scale;    // 2^e0
     u32 n;
     u32 tile_begin;
+    u32 lut_bmax;
+    u32 fast_cmax;   // groups smaller than this have sums that fit 63 bits: wrapped 64-bit prefixes suffice
+    int lut_shift;
     int e0;
     int sum_mode;
     int has_nulls;
@@ -169,16 +182,9 @@ struct SeqDev {
 
 __device__ __forceinline__ u32 lane_id() { return threadIdx.x & 31; }
 
-__device__ __forceinline__ u32 warp_min(u32 v) {
-#pragma unroll
-    for (int o = 16; o; o >>= 1) v = min(v, __shfl_xor_sync(GRB_FULL, v, o));
-    return v;
-}
-__device__ __forceinline__ u32 warp_max(u32 v) {
-#pragma unroll
-    for (int o = 16; o; o >>= 1) v = max(v, __shfl_xor_sync(GRB_FULL, v, o));
-    return v;
-}
+// REDUX: one instruction per warp-wide integer min / max on sm_80+
+__device__ __forceinline__ u32 warp_min(u32 v) { return __reduce_min_sync(GRB_FULL, v); }
+__device__ __forceinline__ u32 warp_max(u32 v) { return __reduce_max_sync(GRB_FULL, v); }
 __device__ __forceinline__ u32 warp_sum(u32 v) {
 #pragma unroll
     for (int o = 16; o; o >>= 1) v += __shfl_xor_sync(GRB_FULL, v, o);

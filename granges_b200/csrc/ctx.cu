@@ -74,6 +74,9 @@ int grb_ctx_create(int device, grb_ctx **out) {
     ctx->tile_mode = 1;
     const char *tm = getenv("GRB_TILE_MODE");
     if (tm) ctx->tile_mode = atoi(tm);
+    ctx->pipe_mode = 1;
+    const char *pm = getenv("GRB_PIPE_MODE");
+    if (pm) ctx->pipe_mode = atoi(pm);
     int ndev = 0;
     cudaError_t e = cudaGetDeviceCount(&ndev);
     if (e != cudaSuccess || device < 0 || device >= ndev) {
@@ -93,13 +96,25 @@ int grb_ctx_create(int device, grb_ctx **out) {
         uint64_t thr = UINT64_MAX;  // keep freed temporaries cached in the pool
         cudaMemPoolSetAttribute(ctx->pool, cudaMemPoolAttrReleaseThreshold, &thr);
     }
+    if (cudaMalloc(&ctx->zeros, 2048) != cudaSuccess || cudaMemset(ctx->zeros, 0, 1024) != cudaSuccess ||
+        cudaMemset((char *)ctx->zeros + 1024, 0xff, 1024) != cudaSuccess) {
+        cudaStreamDestroy(ctx->own_stream);
+        free(ctx);
+        return GRB_ERR_OOM;
+    }
     *out = ctx;
     return GRB_OK;
 }
 
 int grb_ctx_set_stream(grb_ctx *ctx, void *cuda_stream) {
     if (!ctx) return GRB_ERR_INVALID_ARG;
-    ctx->stream = cuda_stream ? (cudaStream_t)cuda_stream : ctx->own_stream;
+    ctx->stream = (cudaStream_t)cuda_stream;  // a null handle is CUDA's default stream, as everywhere in CUDA
+    return GRB_OK;
+}
+
+int grb_ctx_use_own_stream(grb_ctx *ctx) {
+    if (!ctx) return GRB_ERR_INVALID_ARG;
+    ctx->stream = ctx->own_stream;
     return GRB_OK;
 }
 
@@ -114,6 +129,7 @@ void grb_ctx_destroy(grb_ctx *ctx) {
     cudaSetDevice(ctx->device);
     cudaStreamSynchronize(ctx->stream);
     cudaStreamDestroy(ctx->own_stream);
+    cudaFree(ctx->zeros);
     free(ctx);
 }
 

@@ -97,6 +97,26 @@ __global__ void k_block_max_end(const u32 *__restrict__ ends, size_t n, u32 *__r
     if (lane_id() == 0) bme[b] = m;
 }
 
+// lut[b] = #keys < (b << shift) for b in [0, bmax]; entries bmax+1 .. bmax+PAD = n.
+__global__ void k_build_lut(const u32 *__restrict__ keys, u32 n, int shift, u32 bmax, u32 *__restrict__ lut) {
+    u32 b = blockIdx.x * blockDim.x + threadIdx.x;
+    if (b > bmax + PAD) return;
+    if (b > bmax) {
+        lut[b] = n;
+        return;
+    }
+    u64 x = (u64)b << shift;
+    u32 lo = 0, hi = n;
+    while (lo < hi) {
+        u32 mid = lo + ((hi - lo) >> 1);
+        if ((u64)keys[mid] < x)
+            lo = mid + 1;
+        else
+            hi = mid;
+    }
+    lut[b] = lo;
+}
+
 // ---- scores ------------------------------------------------------------------
 
 struct ScoreStats {
@@ -164,16 +184,18 @@ __global__ void k_gather_scores(const u32 *__restrict__ didx, size_t n, const do
         nz |= __shfl_xor_sync(GRB_FULL, nz, s);
     }
     if (lane_id() == 0) {
+        // plain reads first: after the first few warps almost nobody needs the atomic any more
+        volatile ScoreStats *vs = st;
         if (nz) {
-            atomicMin(&st->min_lsb_exp, lsb);
-            atomicMax(&st->max_exp, top);
-            atomicOr(&st->n_nonzero, 1u);
+            if (lsb < vs->min_lsb_exp) atomicMin(&st->min_lsb_exp, lsb);
+            if (top > vs->max_exp) atomicMax(&st->max_exp, top);
+            if (!vs->n_nonzero) atomicOr(&st->n_nonzero, 1u);
         }
         if (nnull) atomicAdd(&st->n_null, nnull);
-        if (nonfinite) atomicOr(&st->has_nonfinite, 1u);
-        if (nan) atomicOr(&st->has_nan, 1u);
-        if (sub) atomicOr(&st->has_subnormal, 1u);
-        if (oor) atomicOr(&st->idx_out_of_range, 1u);
+        if (nonfinite && !vs->has_nonfinite) atomicOr(&st->has_nonfinite, 1u);
+        if (nan && !vs->has_nan) atomicOr(&st->has_nan, 1u);
+        if (sub && !vs->has_subnormal) atomicOr(&st->has_subnormal, 1u);
+        if (oor && !vs->idx_out_of_range) atomicOr(&st->idx_out_of_range, 1u);
     }
 }
 
@@ -185,12 +207,12 @@ __global__ void k_permute_u32(const u32 *__restrict__ src, const u32 *__restrict
 // Block-of-256 fixed-point prefix.  Positions p in [b*256, b*256+256) with p <= n; the value at
 // position p is the sum of the block's elements before p.
 //   phase 0: blocksum[b] = sum of the block's elements
-//   phase 1 (compact): loc[p] = local exclusive prefix (i64)
+//   phase 1 (compact): pfx[p] = low 64 bits of base[b] + local exclusive prefix
 //   phase 2 (wide):    wide[p] = base[b] + local exclusive prefix (i128)
 template <int PHASE>
 __global__ void __launch_bounds__(256) k_fx_blocks(const double *__restrict__ score_a, const u32 *__restrict__ perm,
                                                    size_t n, int e0, i128 *__restrict__ blocksum,
-                                                   const i128 *__restrict__ base, i64 *__restrict__ loc,
+                                                   const i128 *__restrict__ base, u64 *__restrict__ pfx,
                                                    i128 *__restrict__ wide) {
     __shared__ u64 s_lo[8], s_hi[8];
     const size_t b = blockIdx.x;
@@ -222,7 +244,7 @@ __global__ void __launch_bounds__(256) k_fx_blocks(const double *__restrict__ sc
     if (PHASE == 0) {
         if (threadIdx.x == 0) blocksum[b] = total;
     } else if (PHASE == 1) {
-        if (p <= n) loc[p] = (i64)excl;
+        if (p <= n) pfx[p] = (u64)(u128)(base[b] + excl);
     } else {
         if (p <= n) wide[p] = base[b] + excl;
     }
@@ -269,19 +291,19 @@ void free_scores(grb_index *ix) {
     cudaFree(ix->vbits_a);
     cudaFree(ix->vcnt_a);
     cudaFree(ix->vcnt_b);
-    cudaFree(ix->loc_a);
-    cudaFree(ix->loc_b);
+    cudaFree(ix->pfx_a);
+    cudaFree(ix->pfx_b);
     cudaFree(ix->base_a);
     cudaFree(ix->base_b);
     ix->score_a = nullptr;
     ix->vbits_a = ix->vcnt_a = ix->vcnt_b = nullptr;
-    ix->loc_a = ix->loc_b = nullptr;
+    ix->pfx_a = ix->pfx_b = nullptr;
     ix->base_a = ix->base_b = nullptr;
     ix->has_scores = ix->has_nulls = ix->has_nan = false;
     ix->sum_mode = GRB_SUM_SWEEP;
 }
 
-int build_prefix(grb_ctx *ctx, grb_index *ix, const u32 *perm, i64 **loc_out, i128 **base_out) {
+int build_prefix(grb_ctx *ctx, grb_index *ix, const u32 *perm, u64 **pfx_out, i128 **base_out) {
     const size_t n = ix->n;
     const size_t nb = (n >> GRB_BASE_SHIFT) + 1;
     TempBuf bsum;
@@ -290,10 +312,10 @@ int build_prefix(grb_ctx *ctx, grb_index *ix, const u32 *perm, i64 **loc_out, i1
     GRB_LAUNCHED(ctx);
     if (ix->sum_mode == GRB_SUM_COMPACT) {
         GRB_TRY(dev_alloc(ctx, (void **)base_out, nb * sizeof(i128)));
-        GRB_TRY(dev_alloc(ctx, (void **)loc_out, (n + 1) * sizeof(i64)));
+        GRB_TRY(dev_alloc(ctx, (void **)pfx_out, (n + 1 + PAD) * sizeof(u64)));  // padded: bulk copies round up to 16 B
         k_scan_i128_single<<<1, 1024, 0, ctx->stream>>>(bsum.as<i128>(), nb, *base_out);
         GRB_LAUNCHED(ctx);
-        k_fx_blocks<1><<<(unsigned)nb, 256, 0, ctx->stream>>>(ix->score_a, perm, n, ix->e0, nullptr, nullptr, *loc_out, nullptr);
+        k_fx_blocks<1><<<(unsigned)nb, 256, 0, ctx->stream>>>(ix->score_a, perm, n, ix->e0, nullptr, *base_out, *pfx_out, nullptr);
         GRB_LAUNCHED(ctx);
     } else {
         TempBuf bbase;
@@ -398,6 +420,23 @@ int grb_index_build(grb_ctx *ctx, const uint32_t *starts, const uint32_t *ends, 
         if ((rc = grb_sort_pairs(ctx, k2, v2, ks, vs, n, &ke, &ve, nullptr))) break;
         k_unpack_end_order<<<blocks_for(n + PAD, 256), 256, 0, ctx->stream>>>(ke, ve, n, ix->ends_sorted, ix->perm_e);
         ctx->launches++;
+        {
+            // coordinate bins of ~4-8 rights each; the largest end bounds every key
+            u32 maxend = 0;
+            if (n) cudaMemcpyAsync(&maxend, ke + (n - 1), 4, cudaMemcpyDeviceToHost, ctx->stream);  // low half of the last u64 key
+            cudaStreamSynchronize(ctx->stream);
+            int shift = 0;
+            while (shift < 31 && ((u64)maxend >> shift) > (u64)n / 4 + 1) shift++;
+            ix->lut_shift = shift;
+            ix->lut_bmax = (maxend >> shift) + 1;
+            size_t entries = (size_t)ix->lut_bmax + 1 + PAD;
+            if ((rc = dev_alloc(ctx, (void **)&ix->lut_a, entries * 4))) break;
+            if ((rc = dev_alloc(ctx, (void **)&ix->lut_b, entries * 4))) break;
+            k_build_lut<<<blocks_for(entries, 256), 256, 0, ctx->stream>>>(ix->starts, (u32)n, shift, ix->lut_bmax, ix->lut_a);
+            ctx->launches++;
+            k_build_lut<<<blocks_for(entries, 256), 256, 0, ctx->stream>>>(ix->ends_sorted, (u32)n, shift, ix->lut_bmax, ix->lut_b);
+            ctx->launches++;
+        }
         if (n) {
             size_t nbw = (n + 63) >> GRB_BME_SHIFT;
             k_block_max_end<<<blocks_for(nbw * 32, 256), 256, 0, ctx->stream>>>(ix->ends, n, ix->bme);
@@ -427,6 +466,8 @@ void grb_index_destroy(grb_index *ix) {
     cudaFree(ix->bme);
     cudaFree(ix->ends_sorted);
     cudaFree(ix->perm_e);
+    cudaFree(ix->lut_a);
+    cudaFree(ix->lut_b);
     free(ix);
 }
 
@@ -500,6 +541,7 @@ int grb_index_set_scores(grb_index *ix, const double *by_data_idx, const uint8_t
         bool representable = (W + L <= 126) && (emax + L + 1 < 1023) && (e0 >= -1022);
         if (representable) {
             ix->e0 = e0;
+            ix->width = W;
             ix->sum_mode = (W + GRB_BASE_SHIFT <= 62) ? GRB_SUM_COMPACT : GRB_SUM_WIDE;
             if (force) {
                 int f = atoi(force);
@@ -509,8 +551,8 @@ int grb_index_set_scores(grb_index *ix, const double *by_data_idx, const uint8_t
         }
     }
     if (ix->sum_mode != GRB_SUM_SWEEP) {
-        GRB_TRY(build_prefix(ctx, ix, nullptr, &ix->loc_a, &ix->base_a));
-        GRB_TRY(build_prefix(ctx, ix, ix->perm_e, &ix->loc_b, &ix->base_b));
+        GRB_TRY(build_prefix(ctx, ix, nullptr, &ix->pfx_a, &ix->base_a));
+        GRB_TRY(build_prefix(ctx, ix, ix->perm_e, &ix->pfx_b, &ix->base_b));
     }
     GRB_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
     return GRB_OK;

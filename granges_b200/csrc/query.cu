@@ -18,6 +18,7 @@
 //      ub over `ends` (skipping 64-blocks whose block-max-end cannot overlap) until it has seen
 //      `count` hits, reducing with ballots / shuffles; pair emission is the same sweep writing
 //      positions behind a count -> scan -> emit CSR.
+#include <math.h>
 #include <stdlib.h>
 
 #include <vector>
@@ -29,7 +30,10 @@ namespace {
 constexpr int TILE_TPB = 256;
 constexpr int TILE_LPT = 4;
 constexpr int TILE = TILE_TPB * TILE_LPT;
-constexpr u32 WIN_CAP = 3072;  // keys per staged window (2 x 12 KB of shared memory)
+constexpr int TILE_SHIFT = 10;
+static_assert(TILE == 1 << TILE_SHIFT, "tile size");
+constexpr u32 WIN_CAP = 2048;  // keys per staged window (2 x 8 KB of shared memory)
+constexpr u32 LUT_CAP = 1024;  // bin-table entries per staged slice (2 x 4 KB)
 
 enum { M_COUNTS = 1, M_KEEP = 2, M_UBLB = 4, M_MAP = 8 };
 
@@ -78,47 +82,31 @@ __device__ __forceinline__ void mbar_wait(u64 *bar, u32 parity) {
 
 // ---- searches -------------------------------------------------------------------
 
-// #keys < x over a sorted global array, by a whole warp: 32 probes per round.
-__device__ __forceinline__ u32 warp_lower_bound(const u32 *__restrict__ keys, u32 n, u32 x) {
-    const u32 lane = lane_id();
-    u32 lo = 0, hi = n;
-    while (hi - lo > 32) {
-        u32 len = hi - lo;
-        u32 p = lo + (u32)(((u64)(lane + 1) * len) / 33);
-        bool less = keys[p] < x;
-        u32 c = __popc(__ballot_sync(GRB_FULL, less));
-        u32 plo = __shfl_sync(GRB_FULL, p, c ? c - 1 : 0);
-        u32 phi = __shfl_sync(GRB_FULL, p, c < 32 ? c : 31);
-        if (c) lo = plo + 1;
-        if (c < 32) hi = phi;
-    }
-    u32 p = lo + lane;
-    bool less = p < hi && keys[p] < x;
-    return lo + __popc(__ballot_sync(GRB_FULL, less));
-}
-
-// #keys < x in s[0..len): branch-free, the trip count depends on len only.
-__device__ __forceinline__ u32 smem_lower_bound(const u32 *s, u32 len, u32 x) {
-    if (len == 0) return 0;
-    u32 base = 0, n = len;
-    while (n > 1) {
-        u32 half = n >> 1;
-        base = (s[base + half - 1] < x) ? base + half : base;
-        n -= half;
-    }
-    return base + (s[base] < x ? 1u : 0u);
-}
-
-// #keys < x restricted to the answer interval [lo, hi] of a global array.
-__device__ __forceinline__ u32 global_lower_bound(const u32 *__restrict__ keys, u32 lo, u32 hi, u32 x) {
+// #keys < x in the answer interval [lo, hi] of a sorted array (shared or global).
+__device__ __forceinline__ u32 bounded_lower_bound(const u32 *__restrict__ keys, u32 lo, u32 hi, u32 x) {
     while (lo < hi) {
-        u32 mid = lo + ((hi - lo) >> 1);
+        u32 mid = (lo + hi) >> 1;
         if (keys[mid] < x)
             lo = mid + 1;
         else
             hi = mid;
     }
     return lo;
+}
+
+
+// #keys < x, scanning forward from a bin's first position `lo` (<= answer) four keys at a time.
+// No upper bound is needed: `keys` is sorted and every key at or after the end of the searched
+// slice is >= x (real keys of later bins, then the 0xffffffff sentinels that pad every key
+// array), so the predicates are a run of trues followed by falses and the scan always stops.
+// Bins hold ~4-8 keys; the four loads of a round are independent.
+__device__ __forceinline__ u32 scan_lower_bound(const u32 *__restrict__ keys, u32 lo, u32 x) {
+    while (true) {
+        const u32 c = (keys[lo] < x ? 1u : 0u) + (keys[lo + 1] < x ? 1u : 0u) + (keys[lo + 2] < x ? 1u : 0u) +
+                      (keys[lo + 3] < x ? 1u : 0u);
+        if (c < 4) return lo + c;
+        lo += 4;
+    }
 }
 
 __device__ __forceinline__ int find_seq_by_tile(const u32 *__restrict__ tile_begin, int nseq, u32 t) {
@@ -145,40 +133,88 @@ __device__ __forceinline__ int find_seq_by_left(const SeqDev *__restrict__ seqs,
     return lo;
 }
 
-// ---- the tile kernel --------------------------------------------------------------
+// Exact sum of the group [lb, ub) from the compact prefixes.  Small groups (the usual case): the
+// sum fits 63 bits, so the difference of the prefixes mod 2^64 IS the sum; otherwise rebuild the
+// two exact 128-bit prefixes from the per-256 bases.  Either way one rounding to f64.
+__device__ __forceinline__ double compact_group_sum(const u64 *__restrict__ pfx_a, const u64 *__restrict__ pfx_b,
+                                                    const i128 *__restrict__ base_a, const i128 *__restrict__ base_b, u32 ub,
+                                                    u32 lb, u32 fast_cmax, double scale, int e0) {
+    const u64 pa = pfx_a[ub], pb = pfx_b[lb];
+    if (ub - lb < fast_cmax) return (double)(i64)(pa - pb) * scale;
+    const i128 ba = base_a[ub >> GRB_BASE_SHIFT], bb = base_b[lb >> GRB_BASE_SHIFT];
+    const i128 PA = ba + (i128)(i64)(pa - (u64)(u128)ba);
+    const i128 PB = bb + (i128)(i64)(pb - (u64)(u128)bb);
+    return fx_to_double(PA - PB, e0);
+}
 
-template <int MODE>
+// ---- the tile kernel --------------------------------------------------------------
+//
+// One CTA = up to 1024 consecutive lefts of one seqname (tiles are aligned to multiples of 1024 in
+// the concatenated left arrays, so full tiles read / write with 128-bit accesses); thread t owns
+// lefts 4t..4t+3 of the tile.
+//   a. load the lefts, block-reduce min/max of l.start and l.end;
+//   b. warp 0 turns those into coordinate bins, reads the four bounding entries of the two
+//      bin tables and issues TMA bulk copies of (starts slice, ends_sorted slice, both table
+//      slices) into shared memory behind one mbarrier;
+//   c. every left: bin -> [lo, hi] from the staged table -> short binary search in the staged keys;
+//   d. outputs (counts / keep flags / ub,lb / fused reductions).
+// FAST >= 0: the batch is uniform (every seqname has scores, no None, compact prefixes) and there
+// is exactly one reduction, FAST = its grb_op code; the general path handles everything else.
+
+template <int MODE, int FAST>
 __global__ void __launch_bounds__(TILE_TPB) k_tile(const SeqDev *__restrict__ seqs, const u32 *__restrict__ tile_begin, int nseq,
-                                                   const u32 *__restrict__ ls, const u32 *__restrict__ le, const TileOut o,
-                                                   int use_tma) {
-    __shared__ __align__(16) u32 sA[WIN_CAP + 8];
-    __shared__ __align__(16) u32 sB[WIN_CAP + 8];
+                                                   const u32 *__restrict__ ls, const u32 *__restrict__ le, const u64 total,
+                                                   const TileOut o, int use_tma) {
+    __shared__ __align__(16) u32 sKA[WIN_CAP + 8];
+    __shared__ __align__(16) u32 sKB[WIN_CAP + 8];
+    __shared__ __align__(16) u32 sLA[LUT_CAP + 8];
+    __shared__ __align__(16) u32 sLB[LUT_CAP + 8];
     __shared__ __align__(8) u64 mbar;
     __shared__ u32 s_red[4][TILE_TPB / 32];
-    __shared__ u32 s_win[4];
+    __shared__ u32 s_win[8];
 
     const u32 tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     if (tid == 0) mbar_init(&mbar, 1);
 
     const u32 t = blockIdx.x;
     const int s = find_seq_by_tile(tile_begin, nseq, t);
-    const SeqDev *sd = &seqs[s];
-    const u64 base = sd->left_begin + (u64)(t - sd->tile_begin) * TILE;
-    const u64 remain = sd->left_end - base;
-    const u32 cnt = remain < (u64)TILE ? (u32)remain : (u32)TILE;
+    const SeqDev *__restrict__ sd = &seqs[s];
+    const u64 seq_lo = sd->left_begin, seq_hi = sd->left_end;
+    const u64 gblock = (seq_lo >> TILE_SHIFT) + (t - sd->tile_begin);
+    const u64 g0 = (gblock << TILE_SHIFT) + (u64)tid * TILE_LPT;  // first left of this thread (global index)
     const u32 n = sd->n;
     const u32 *__restrict__ starts = sd->starts;
     const u32 *__restrict__ ends_sorted = sd->ends_sorted;
+    const u32 *__restrict__ lut_a = sd->lut_a;
+    const u32 *__restrict__ lut_b = sd->lut_b;
+    const int sh = sd->lut_shift;
+    const u32 bmax = sd->lut_bmax;
 
+    // ---- a. lefts
     u32 a[TILE_LPT], b[TILE_LPT];
+    bool okv[TILE_LPT];
+    const bool full = g0 >= seq_lo && g0 + TILE_LPT <= seq_hi;
+    const bool vec_ok = ((((uintptr_t)ls) | ((uintptr_t)le)) & 15) == 0;
+    if (full && vec_ok) {
+        const uint4 va = *reinterpret_cast<const uint4 *>(ls + g0);
+        const uint4 vb = *reinterpret_cast<const uint4 *>(le + g0);
+        a[0] = va.x, a[1] = va.y, a[2] = va.z, a[3] = va.w;
+        b[0] = vb.x, b[1] = vb.y, b[2] = vb.z, b[3] = vb.w;
+#pragma unroll
+        for (int k = 0; k < TILE_LPT; k++) okv[k] = true;
+    } else {
+#pragma unroll
+        for (int k = 0; k < TILE_LPT; k++) {
+            const u64 g = g0 + k;
+            okv[k] = g >= seq_lo && g < seq_hi;
+            a[k] = okv[k] ? ls[g] : 0u;
+            b[k] = okv[k] ? le[g] : 0u;
+        }
+    }
     u32 mn_s = 0xffffffffu, mx_s = 0, mn_e = 0xffffffffu, mx_e = 0;
 #pragma unroll
     for (int k = 0; k < TILE_LPT; k++) {
-        u32 i = tid + k * TILE_TPB;
-        bool ok = i < cnt;
-        a[k] = ok ? ls[base + i] : 0u;
-        b[k] = ok ? le[base + i] : 0u;
-        if (ok) {
+        if (okv[k]) {
             mn_s = min(mn_s, a[k]);
             mx_s = max(mx_s, a[k]);
             mn_e = min(mn_e, b[k]);
@@ -196,50 +232,140 @@ __global__ void __launch_bounds__(TILE_TPB) k_tile(const SeqDev *__restrict__ se
         s_red[3][warp] = mx_s;
     }
     __syncthreads();
-    if (warp < 4) {
-        u32 v = s_red[warp][lane & 7];
-        // warps 0,2 reduce with min, warps 1,3 with max
-        v = (warp & 1) ? warp_max(v) : warp_min(v);
-        // ub candidates: #{start < l.end};  lb candidates: #{end <= l.start} = #{end < l.start + 1}
-        u32 r = (warp < 2) ? warp_lower_bound(starts, n, v) : warp_lower_bound(ends_sorted, n, v + 1);
-        if (lane == 0) s_win[warp] = r;
+
+    // ---- b. windows (warp 0)
+    if (warp == 0) {
+        // lane q in 0..3 finishes reduction q (min for even q, max for odd q) and fetches one table entry
+        const u32 q = lane & 3;
+        u32 v = (q & 1) ? 0u : 0xffffffffu;
+#pragma unroll
+        for (int w = 0; w < TILE_TPB / 32; w++) {
+            u32 p = s_red[q][w];
+            v = (q & 1) ? max(v, p) : min(v, p);
+        }
+        // x = l.end for the starts table (q = 0,1); x = l.start + 1 for the ends table (q = 2,3)
+        const u32 x = v + (q >> 1);
+        const u32 bin = min(x >> sh, bmax);
+        const u32 *tab = (q < 2) ? lut_a : lut_b;
+        const u32 bound = tab[bin + (q & 1)];  // lower bins give the window start, upper bin + 1 its end
+        const u32 binA0 = __shfl_sync(GRB_FULL, bin, 0), binA1 = __shfl_sync(GRB_FULL, bin, 1);
+        const u32 binB0 = __shfl_sync(GRB_FULL, bin, 2), binB1 = __shfl_sync(GRB_FULL, bin, 3);
+        const u32 A_lo = __shfl_sync(GRB_FULL, bound, 0), A_hi = __shfl_sync(GRB_FULL, bound, 1);
+        const u32 B_lo = __shfl_sync(GRB_FULL, bound, 2), B_hi = __shfl_sync(GRB_FULL, bound, 3);
+        if (lane == 0) {
+            const u32 a0 = A_lo & ~3u, b0 = B_lo & ~3u, la0 = binA0 & ~3u, lb0 = binB0 & ~3u;
+            // + 4: the forward scan may read up to 3 keys past the last one it can return
+            const u32 alen = A_hi - a0 + 4, blen = B_hi - b0 + 4;
+            const u32 lalen = binA1 + 1 - la0, lblen = binB1 + 1 - lb0;
+            const bool staged = use_tma && alen <= WIN_CAP && blen <= WIN_CAP && lalen <= LUT_CAP && lblen <= LUT_CAP;
+            s_win[0] = a0;
+            s_win[1] = b0;
+            s_win[2] = la0;
+            s_win[3] = lb0;
+            s_win[4] = staged ? 1u : 0u;
+            if (staged) {
+                const u32 by_a = (alen * 4 + 15) & ~15u, by_b = (blen * 4 + 15) & ~15u;
+                const u32 by_la = (lalen * 4 + 15) & ~15u, by_lb = (lblen * 4 + 15) & ~15u;
+                mbar_arrive_expect_tx(&mbar, by_a + by_b + by_la + by_lb);
+                tma_load_1d(sLA, lut_a + la0, by_la, &mbar);
+                tma_load_1d(sLB, lut_b + lb0, by_lb, &mbar);
+                tma_load_1d(sKA, starts + a0, by_a, &mbar);
+                tma_load_1d(sKB, ends_sorted + b0, by_b, &mbar);
+            }
+        }
     }
     __syncthreads();
-    const u32 A_lo = s_win[0], A_hi = s_win[1], B_lo = s_win[2], B_hi = s_win[3];
-    const u32 a0 = A_lo & ~3u, b0 = B_lo & ~3u;
-    const u32 alen = A_hi - a0, blen = B_hi - b0;
-    const bool staged = use_tma && alen <= WIN_CAP && blen <= WIN_CAP;
+    const u32 a0 = s_win[0], b0 = s_win[1], la0 = s_win[2], lb0 = s_win[3];
+    const bool staged = s_win[4] != 0;
 
+    // ---- c. per-left searches
     u32 ub[TILE_LPT], lb[TILE_LPT];
     if (staged) {
-        const u32 bytes_a = (alen * 4 + 15) & ~15u, bytes_b = (blen * 4 + 15) & ~15u;
-        if (bytes_a + bytes_b) {
-            if (tid == 0) {
-                mbar_arrive_expect_tx(&mbar, bytes_a + bytes_b);
-                if (bytes_a) tma_load_1d(sA, starts + a0, bytes_a, &mbar);
-                if (bytes_b) tma_load_1d(sB, ends_sorted + b0, bytes_b, &mbar);
-            }
-            mbar_wait(&mbar, 0);
-        }
+        mbar_wait(&mbar, 0);
 #pragma unroll
         for (int k = 0; k < TILE_LPT; k++) {
-            ub[k] = a0 + smem_lower_bound(sA, alen, b[k]);
-            lb[k] = b0 + smem_lower_bound(sB, blen, a[k] + 1);
+            ub[k] = lb[k] = 0;
+            if (!okv[k]) continue;
+            const u32 xa = b[k], xb = a[k] + 1;
+            const u32 ba = min(xa >> sh, bmax) - la0;
+            const u32 bb = min(xb >> sh, bmax) - lb0;
+            ub[k] = a0 + scan_lower_bound(sKA, sLA[ba] - a0, xa);
+            lb[k] = b0 + scan_lower_bound(sKB, sLB[bb] - b0, xb);
         }
     } else {
 #pragma unroll
         for (int k = 0; k < TILE_LPT; k++) {
-            ub[k] = global_lower_bound(starts, A_lo, A_hi, b[k]);
-            lb[k] = global_lower_bound(ends_sorted, B_lo, B_hi, a[k] + 1);
+            const u32 xa = b[k], xb = a[k] + 1;
+            const u32 ba = min(xa >> sh, bmax), bb = min(xb >> sh, bmax);
+            ub[k] = okv[k] ? scan_lower_bound(starts, lut_a[ba], xa) : 0u;
+            lb[k] = okv[k] ? scan_lower_bound(ends_sorted, lut_b[bb], xb) : 0u;
         }
     }
 
+    // ---- d. outputs
+    if (FAST >= 0) {
+        // uniform batch, one reduction, k == 1
+        const u64 *__restrict__ pfx_a = sd->pfx_a;
+        const u64 *__restrict__ pfx_b = sd->pfx_b;
+        const u32 fast_cmax = sd->fast_cmax;
+        const double scale = sd->scale;
+        double r[TILE_LPT];
+        u8 v[TILE_LPT];
+#pragma unroll
+        for (int k = 0; k < TILE_LPT; k++) {
+            const u32 c = ub[k] - lb[k];
+            if (FAST == GRB_OP_COUNT) {
+                r[k] = (double)c;
+                v[k] = 1;
+            } else {
+                double sum = 0.0;
+                if (okv[k]) sum = compact_group_sum(pfx_a, pfx_b, sd->base_a, sd->base_b, ub[k], lb[k], fast_cmax, scale, sd->e0);
+                if (FAST == GRB_OP_SUM) {
+                    r[k] = sum;
+                    v[k] = 1;
+                } else if (FAST == GRB_OP_SUM_NOT_EMPTY) {
+                    v[k] = c != 0;
+                    r[k] = sum;
+                } else {
+                    v[k] = c != 0;
+                    r[k] = c ? sum / (double)c : 0.0;
+                }
+            }
+        }
+        const bool ovec = ((((uintptr_t)o.out) & 15) | (((uintptr_t)o.out_valid) & 3)) == 0;
+        if (full && ovec) {
+            double2 *po = reinterpret_cast<double2 *>(o.out + g0);
+            po[0] = make_double2(r[0], r[1]);
+            po[1] = make_double2(r[2], r[3]);
+            *reinterpret_cast<uchar4 *>(o.out_valid + g0) = make_uchar4(v[0], v[1], v[2], v[3]);
+        } else {
+#pragma unroll
+            for (int k = 0; k < TILE_LPT; k++) {
+                if (okv[k]) {
+                    o.out[g0 + k] = r[k];
+                    o.out_valid[g0 + k] = v[k];
+                }
+            }
+        }
+        if (MODE & M_UBLB) {
+#pragma unroll
+            for (int k = 0; k < TILE_LPT; k++) {
+                if (okv[k]) {
+                    o.ub[g0 + k] = ub[k];
+                    o.lb[g0 + k] = lb[k];
+                }
+            }
+        }
+        return;
+    }
+
+    const int mode = sd->sum_mode;
+    const int has_nulls = sd->has_nulls, has_scores = sd->has_scores;
     u32 kept = 0;
 #pragma unroll
     for (int k = 0; k < TILE_LPT; k++) {
-        u32 i = tid + k * TILE_TPB;
-        if (i >= cnt) continue;
-        const u64 g = base + i;
+        if (!okv[k]) continue;
+        const u64 g = g0 + k;
         const u32 c_all = ub[k] - lb[k];
         if (MODE & M_COUNTS) o.counts[g] = c_all;
         if (MODE & M_KEEP) {
@@ -252,19 +378,15 @@ __global__ void __launch_bounds__(TILE_TPB) k_tile(const SeqDev *__restrict__ se
             o.lb[g] = lb[k];
         }
         if (MODE & M_MAP) {
-            const int mode = sd->sum_mode;
             u32 nvalid = c_all;
-            if (sd->has_nulls) nvalid = sd->vcnt_a[ub[k]] - sd->vcnt_b[lb[k]];
-            if (!sd->has_scores) nvalid = 0;
+            if (has_nulls) nvalid = sd->vcnt_a[ub[k]] - sd->vcnt_b[lb[k]];
+            if (!has_scores) nvalid = 0;
             double sum = 0.0;
             if (o.need_sum) {
-                if (mode == GRB_SUM_COMPACT) {
-                    i128 pa = sd->base_a[ub[k] >> GRB_BASE_SHIFT] + (i128)sd->loc_a[ub[k]];
-                    i128 pb = sd->base_b[lb[k] >> GRB_BASE_SHIFT] + (i128)sd->loc_b[lb[k]];
-                    sum = fx_to_double(pa - pb, sd->e0);
-                } else if (mode == GRB_SUM_WIDE) {
+                if (mode == GRB_SUM_COMPACT)
+                    sum = compact_group_sum(sd->pfx_a, sd->pfx_b, sd->base_a, sd->base_b, ub[k], lb[k], sd->fast_cmax, sd->scale, sd->e0);
+                else if (mode == GRB_SUM_WIDE)
                     sum = fx_to_double(sd->base_a[ub[k]] - sd->base_b[lb[k]], sd->e0);
-                }
             }
             for (int c = 0; c < o.k; c++) {
                 const int op = o.ops[c];
@@ -306,6 +428,345 @@ __global__ void __launch_bounds__(TILE_TPB) k_tile(const SeqDev *__restrict__ se
         if (o.n_kept) {
             kept = warp_sum(kept);
             if (lane == 0 && kept) atomicAdd(o.n_kept, (unsigned long long)kept);
+        }
+    }
+}
+
+// ---- the pipelined map kernel (headline path) ------------------------------------------
+//
+// Same arithmetic as k_tile<M_MAP, FAST>, organised as a persistent, warp-specialised TMA pipeline
+// so that no warp ever waits on a dependent chain of global loads:
+//   warp 0 (producer), software-pipelined over the CTA's tiles:
+//     A  tile j    : TMA the 1024 lefts (ls, le) into the lefts ring
+//     B  tile j-2  : min/max of those lefts out of shared memory -> coordinate bins -> four
+//                    bin-table entries fetched with plain loads (used one iteration later)
+//     C  tile j-3  : TMA the slices of starts, ends_sorted, both bin tables and both prefix-sum
+//                    arrays the tile can touch into the window ring, behind one mbarrier
+//   warps 1..8 (consumers): wait for the window stage, resolve ub / lb per left out of shared
+//     memory, take the exact sums from the staged prefixes, write the results, release the stage.
+// Rings: PIPE_LSTAGES x 8 KB of lefts, PIPE_WSTAGES x ~43 KB of windows (one CTA per SM).
+// Tiles whose windows do not fit (sparse lefts over dense rights) fall back to per-left global
+// searches inside the consumers; results are identical.
+
+constexpr int PIPE_NC = 8;  // consumer warps; each thread owns 4 consecutive lefts of a tile
+constexpr int PIPE_THREADS = (PIPE_NC + 1) * 32;
+constexpr int PIPE_LSTAGES = 6;
+constexpr int PIPE_WSTAGES = 3;
+constexpr u32 PIPE_WIN = 1536;  // keys (and prefixes) per staged window
+constexpr u32 PIPE_LUT = 768;   // bin-table entries per staged slice
+
+struct PipeDesc {
+    u64 g_first;   // global index of the tile's slot 0
+    double scale;
+    u32 vlo, vhi;  // valid slots of the tile: [vlo, vhi)
+    u32 a0, b0, la0, lb0;
+    u32 staged;
+    u32 bmax, fast_cmax;
+    int sh;
+    int seq;
+    u32 pad;
+};
+
+struct PipeSmem {
+    alignas(16) u32 ls[PIPE_LSTAGES][TILE];
+    alignas(16) u32 le[PIPE_LSTAGES][TILE];
+    alignas(16) u64 pa[PIPE_WSTAGES][PIPE_WIN + 8];
+    alignas(16) u64 pb[PIPE_WSTAGES][PIPE_WIN + 8];
+    alignas(16) u32 ka[PIPE_WSTAGES][PIPE_WIN + 8];
+    alignas(16) u32 kb[PIPE_WSTAGES][PIPE_WIN + 8];
+    alignas(16) u32 la[PIPE_WSTAGES][PIPE_LUT + 8];
+    alignas(16) u32 lb[PIPE_WSTAGES][PIPE_LUT + 8];
+    PipeDesc desc[PIPE_WSTAGES];
+    alignas(8) u64 fullL[PIPE_LSTAGES];
+    alignas(8) u64 emptyL[PIPE_LSTAGES];
+    alignas(8) u64 fullW[PIPE_WSTAGES];
+    alignas(8) u64 emptyW[PIPE_WSTAGES];
+};
+
+__device__ __forceinline__ void mbar_arrive(u64 *bar) {
+    asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_addr(bar)) : "memory");
+}
+
+// What phase B learns about a tile and phase C needs one iteration later (held in registers).
+struct PipeTileInfo {
+    u64 g_first;
+    u32 vlo, vhi;
+    int seq;
+    u32 bin, bound;  // lane q (mod 4): bin / table entry of reduction q
+};
+
+template <int FAST>
+__global__ void __launch_bounds__(PIPE_THREADS, 1) k_map_pipe(const SeqDev *__restrict__ seqs, const u32 *__restrict__ tile_begin,
+                                                              int nseq, u32 ntiles, const u32 *__restrict__ ls,
+                                                              const u32 *__restrict__ le, const u64 total,
+                                                              double *__restrict__ out, u8 *__restrict__ out_valid, int use_tma) {
+    extern __shared__ __align__(128) unsigned char smem_raw[];
+    PipeSmem &S = *reinterpret_cast<PipeSmem *>(smem_raw);
+    const u32 tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    if (tid == 0) {
+        for (int i = 0; i < PIPE_LSTAGES; i++) {
+            mbar_init(&S.fullL[i], 1);
+            mbar_init(&S.emptyL[i], PIPE_NC);
+        }
+        for (int i = 0; i < PIPE_WSTAGES; i++) {
+            mbar_init(&S.fullW[i], 1);
+            mbar_init(&S.emptyW[i], PIPE_NC);
+        }
+    }
+    __syncthreads();
+    // tiles of this CTA: blockIdx.x, blockIdx.x + gridDim.x, ...
+    const u32 nmine = blockIdx.x < ntiles ? (ntiles - blockIdx.x + gridDim.x - 1) / gridDim.x : 0;
+    const bool vec_in = ((((uintptr_t)ls) | ((uintptr_t)le)) & 15) == 0;
+
+    if (warp == 0) {
+        // ================= producer =================
+        PipeTileInfo cur;  // filled by phase B, consumed by phase C of the NEXT iteration (the loads get a whole iteration)
+        cur.g_first = 0;
+        cur.vlo = cur.vhi = 0;
+        cur.seq = 0;
+        cur.bin = cur.bound = 0;
+        for (u32 it = 0; it < nmine + 3; it++) {
+            // ---- C: windows of tile it-3 (uses what phase B loaded one iteration ago)
+            if (it >= 3) {
+                const u32 j = it - 3, sw = j % PIPE_WSTAGES;
+                mbar_wait(&S.emptyW[sw], ((j / PIPE_WSTAGES) & 1) ^ 1);
+                const SeqDev *__restrict__ sd = &seqs[cur.seq];
+                const u32 binA0 = __shfl_sync(GRB_FULL, cur.bin, 0), binA1 = __shfl_sync(GRB_FULL, cur.bin, 1);
+                const u32 binB0 = __shfl_sync(GRB_FULL, cur.bin, 2), binB1 = __shfl_sync(GRB_FULL, cur.bin, 3);
+                const u32 A_lo = __shfl_sync(GRB_FULL, cur.bound, 0), A_hi = __shfl_sync(GRB_FULL, cur.bound, 1);
+                const u32 B_lo = __shfl_sync(GRB_FULL, cur.bound, 2), B_hi = __shfl_sync(GRB_FULL, cur.bound, 3);
+                if (lane == 0) {
+                    const u32 a0 = A_lo & ~3u, b0 = B_lo & ~3u, la0 = binA0 & ~3u, lb0 = binB0 & ~3u;
+                    // + 4: the forward scan may read up to 3 keys past the last one it can return
+                    const u32 alen = A_hi - a0 + 4, blen = B_hi - b0 + 4;
+                    const u32 lalen = binA1 + 1 - la0, lblen = binB1 + 1 - lb0;
+                    const bool staged = use_tma && alen <= PIPE_WIN && blen <= PIPE_WIN && lalen <= PIPE_LUT && lblen <= PIPE_LUT;
+                    PipeDesc &d = S.desc[sw];
+                    d.g_first = cur.g_first;
+                    d.vlo = cur.vlo;
+                    d.vhi = cur.vhi;
+                    d.seq = cur.seq;
+                    d.a0 = a0;
+                    d.b0 = b0;
+                    d.la0 = la0;
+                    d.lb0 = lb0;
+                    d.staged = staged ? 1u : 0u;
+                    d.sh = sd->lut_shift;
+                    d.bmax = sd->lut_bmax;
+                    d.fast_cmax = sd->fast_cmax;
+                    d.scale = sd->scale;
+                    if (staged) {
+                        const u32 by_a = (alen * 4 + 15) & ~15u, by_b = (blen * 4 + 15) & ~15u;
+                        const u32 by_la = (lalen * 4 + 15) & ~15u, by_lb = (lblen * 4 + 15) & ~15u;
+                        const u32 by_pa = (alen * 8 + 15) & ~15u, by_pb = (blen * 8 + 15) & ~15u;
+                        const bool want_pfx = FAST != GRB_OP_COUNT;
+                        mbar_arrive_expect_tx(&S.fullW[sw], by_a + by_b + by_la + by_lb + (want_pfx ? by_pa + by_pb : 0u));
+                        tma_load_1d(S.la[sw], sd->lut_a + la0, by_la, &S.fullW[sw]);
+                        tma_load_1d(S.lb[sw], sd->lut_b + lb0, by_lb, &S.fullW[sw]);
+                        tma_load_1d(S.ka[sw], sd->starts + a0, by_a, &S.fullW[sw]);
+                        tma_load_1d(S.kb[sw], sd->ends_sorted + b0, by_b, &S.fullW[sw]);
+                        if (want_pfx) {
+                            tma_load_1d(S.pa[sw], sd->pfx_a + a0, by_pa, &S.fullW[sw]);
+                            tma_load_1d(S.pb[sw], sd->pfx_b + b0, by_pb, &S.fullW[sw]);
+                        }
+                    } else {
+                        mbar_arrive(&S.fullW[sw]);
+                    }
+                }
+                __syncwarp();
+            }
+            // ---- A: lefts of tile `it`
+            if (it < nmine) {
+                const u32 j = it, sl = j % PIPE_LSTAGES;
+                const u32 t = blockIdx.x + j * gridDim.x;
+                mbar_wait(&S.emptyL[sl], ((j / PIPE_LSTAGES) & 1) ^ 1);
+                const int sq = find_seq_by_tile(tile_begin, nseq, t);
+                const SeqDev *__restrict__ sd = &seqs[sq];
+                const u64 g_first = ((sd->left_begin >> TILE_SHIFT) + (t - sd->tile_begin)) << TILE_SHIFT;
+                const bool whole = vec_in && g_first >= sd->left_begin && g_first + TILE <= sd->left_end;
+                if (whole && use_tma) {
+                    if (lane == 0) {
+                        mbar_arrive_expect_tx(&S.fullL[sl], 2 * TILE * 4);
+                        tma_load_1d(S.ls[sl], ls + g_first, TILE * 4, &S.fullL[sl]);
+                        tma_load_1d(S.le[sl], le + g_first, TILE * 4, &S.fullL[sl]);
+                    }
+                } else {
+                    // ragged tile (seqname boundary, end of the arrays, unaligned pointers): plain copies
+                    for (u32 i = lane; i < TILE; i += 32) {
+                        const u64 g = g_first + i;
+                        const bool ok = g >= sd->left_begin && g < sd->left_end;
+                        S.ls[sl][i] = ok ? ls[g] : 0u;
+                        S.le[sl][i] = ok ? le[g] : 0u;
+                    }
+                    __syncwarp();
+                    if (lane == 0) mbar_arrive(&S.fullL[sl]);
+                }
+                __syncwarp();
+            }
+            // ---- B: statistics of tile it-2 and its bin-table entries
+            if (it >= 2 && it - 2 < nmine) {
+                const u32 j = it - 2, sl = j % PIPE_LSTAGES;
+                const u32 t = blockIdx.x + j * gridDim.x;
+                const int sq = find_seq_by_tile(tile_begin, nseq, t);
+                const SeqDev *__restrict__ sd = &seqs[sq];
+                const u64 g_first = ((sd->left_begin >> TILE_SHIFT) + (t - sd->tile_begin)) << TILE_SHIFT;
+                const u64 lo_g = sd->left_begin > g_first ? sd->left_begin : g_first;
+                const u64 hi_g = sd->left_end < g_first + TILE ? sd->left_end : g_first + TILE;
+                const u32 vlo = (u32)(lo_g - g_first), vhi = (u32)(hi_g - g_first);
+                mbar_wait(&S.fullL[sl], (j / PIPE_LSTAGES) & 1);
+                u32 mn_s = 0xffffffffu, mx_s = 0, mn_e = 0xffffffffu, mx_e = 0;
+                const uint4 *vs = reinterpret_cast<const uint4 *>(S.ls[sl]);
+                const uint4 *ve = reinterpret_cast<const uint4 *>(S.le[sl]);
+                if (vlo == 0 && vhi == TILE) {
+#pragma unroll
+                    for (int r = 0; r < TILE / 128; r++) {
+                        const uint4 x = vs[r * 32 + lane], y = ve[r * 32 + lane];
+                        mn_s = min(mn_s, min(min(x.x, x.y), min(x.z, x.w)));
+                        mx_s = max(mx_s, max(max(x.x, x.y), max(x.z, x.w)));
+                        mn_e = min(mn_e, min(min(y.x, y.y), min(y.z, y.w)));
+                        mx_e = max(mx_e, max(max(y.x, y.y), max(y.z, y.w)));
+                    }
+                } else {
+                    for (u32 i = vlo + lane; i < vhi; i += 32) {
+                        const u32 x = S.ls[sl][i], y = S.le[sl][i];
+                        mn_s = min(mn_s, x);
+                        mx_s = max(mx_s, x);
+                        mn_e = min(mn_e, y);
+                        mx_e = max(mx_e, y);
+                    }
+                }
+                mn_e = warp_min(mn_e);
+                mx_e = warp_max(mx_e);
+                mn_s = warp_min(mn_s);
+                mx_s = warp_max(mx_s);
+                const u32 q = lane & 3;
+                const u32 v = q == 0 ? mn_e : q == 1 ? mx_e : q == 2 ? mn_s : mx_s;
+                const u32 x = v + (q >> 1);
+                cur.bin = min(x >> sd->lut_shift, sd->lut_bmax);
+                cur.bound = ((q < 2) ? sd->lut_a : sd->lut_b)[cur.bin + (q & 1)];
+                cur.g_first = g_first;
+                cur.vlo = vlo;
+                cur.vhi = vhi;
+                cur.seq = sq;
+            }
+        }
+        return;
+    }
+
+    // ================= consumers =================
+    const u32 cw = warp - 1;
+    const u32 i0 = (cw * 32 + lane) * TILE_LPT;  // first slot of this thread inside a tile
+    const bool ovec = ((((uintptr_t)out) & 15) | (((uintptr_t)out_valid) & 3)) == 0;
+    for (u32 j = 0; j < nmine; j++) {
+        const u32 sw = j % PIPE_WSTAGES, sl = j % PIPE_LSTAGES;
+        mbar_wait(&S.fullW[sw], (j / PIPE_WSTAGES) & 1);
+        const PipeDesc &d = S.desc[sw];
+        const u32 vlo = d.vlo, vhi = d.vhi;
+        const int sh = d.sh;
+        const u32 bmax = d.bmax;
+        const uint4 va = *reinterpret_cast<const uint4 *>(&S.ls[sl][i0]);
+        const uint4 vb = *reinterpret_cast<const uint4 *>(&S.le[sl][i0]);
+        const u32 a[TILE_LPT] = {va.x, va.y, va.z, va.w};
+        const u32 b[TILE_LPT] = {vb.x, vb.y, vb.z, vb.w};
+        bool okv[TILE_LPT];
+#pragma unroll
+        for (int k = 0; k < TILE_LPT; k++) okv[k] = i0 + k >= vlo && i0 + k < vhi;
+        double r[TILE_LPT];
+        u8 v[TILE_LPT];
+        if (d.staged) {
+            const u32 a0 = d.a0, b0 = d.b0, la0 = d.la0, lb0 = d.lb0;
+            const u32 *__restrict__ sKA = S.ka[sw];
+            const u32 *__restrict__ sKB = S.kb[sw];
+            const u32 *__restrict__ sLA = S.la[sw];
+            const u32 *__restrict__ sLB = S.lb[sw];
+#pragma unroll
+            for (int k = 0; k < TILE_LPT; k++) {
+                r[k] = 0.0;
+                v[k] = 0;
+                if (!okv[k]) continue;
+                const u32 xa = b[k], xb = a[k] + 1;
+                const u32 ba = min(xa >> sh, bmax) - la0;
+                const u32 bb = min(xb >> sh, bmax) - lb0;
+                const u32 ua = scan_lower_bound(sKA, sLA[ba] - a0, xa);   // relative to a0
+                const u32 lbk = scan_lower_bound(sKB, sLB[bb] - b0, xb);  // relative to b0
+                const u32 c = (a0 + ua) - (b0 + lbk);
+                if (FAST == GRB_OP_COUNT) {
+                    r[k] = (double)c;
+                    v[k] = 1;
+                    continue;
+                }
+                double sum;
+                const u64 pa = S.pa[sw][ua], pb = S.pb[sw][lbk];
+                if (c < d.fast_cmax) {
+                    sum = (double)(i64)(pa - pb) * d.scale;
+                } else {
+                    const SeqDev *__restrict__ sd = &seqs[d.seq];
+                    const i128 ba128 = sd->base_a[(a0 + ua) >> GRB_BASE_SHIFT], bb128 = sd->base_b[(b0 + lbk) >> GRB_BASE_SHIFT];
+                    const i128 PA = ba128 + (i128)(i64)(pa - (u64)(u128)ba128);
+                    const i128 PB = bb128 + (i128)(i64)(pb - (u64)(u128)bb128);
+                    sum = fx_to_double(PA - PB, sd->e0);
+                }
+                if (FAST == GRB_OP_SUM) {
+                    r[k] = sum;
+                    v[k] = 1;
+                } else if (FAST == GRB_OP_SUM_NOT_EMPTY) {
+                    r[k] = sum;
+                    v[k] = c != 0;
+                } else {
+                    v[k] = c != 0;
+                    r[k] = c ? sum / (double)c : 0.0;
+                }
+            }
+        } else {
+            const SeqDev *__restrict__ sd = &seqs[d.seq];
+#pragma unroll
+            for (int k = 0; k < TILE_LPT; k++) {
+                r[k] = 0.0;
+                v[k] = 0;
+                if (!okv[k]) continue;
+                const u32 xa = b[k], xb = a[k] + 1;
+                const u32 ba = min(xa >> sh, bmax), bb = min(xb >> sh, bmax);
+                const u32 ub = scan_lower_bound(sd->starts, sd->lut_a[ba], xa);
+                const u32 lbk = scan_lower_bound(sd->ends_sorted, sd->lut_b[bb], xb);
+                const u32 c = ub - lbk;
+                if (FAST == GRB_OP_COUNT) {
+                    r[k] = (double)c;
+                    v[k] = 1;
+                    continue;
+                }
+                const double sum = compact_group_sum(sd->pfx_a, sd->pfx_b, sd->base_a, sd->base_b, ub, lbk, d.fast_cmax, d.scale, sd->e0);
+                if (FAST == GRB_OP_SUM) {
+                    r[k] = sum;
+                    v[k] = 1;
+                } else if (FAST == GRB_OP_SUM_NOT_EMPTY) {
+                    r[k] = sum;
+                    v[k] = c != 0;
+                } else {
+                    v[k] = c != 0;
+                    r[k] = c ? sum / (double)c : 0.0;
+                }
+            }
+        }
+        const u64 g0 = d.g_first + i0;
+        if (ovec && okv[0] && okv[TILE_LPT - 1]) {
+            double2 *po = reinterpret_cast<double2 *>(out + g0);
+            po[0] = make_double2(r[0], r[1]);
+            po[1] = make_double2(r[2], r[3]);
+            *reinterpret_cast<uchar4 *>(out_valid + g0) = make_uchar4(v[0], v[1], v[2], v[3]);
+        } else {
+#pragma unroll
+            for (int k = 0; k < TILE_LPT; k++) {
+                if (okv[k]) {
+                    out[g0 + k] = r[k];
+                    out_valid[g0 + k] = v[k];
+                }
+            }
+        }
+        // done with this stage: one arrival per consumer warp
+        __syncwarp();
+        if (lane == 0) {
+            mbar_arrive(&S.emptyW[sw]);
+            mbar_arrive(&S.emptyL[sl]);
         }
     }
 }
@@ -632,6 +1093,7 @@ struct Batch {
     u32 ntiles = 0;
     u64 total = 0;
     int nseq = 0;
+    bool uniform = true;  // every present seqname: scores, no None, compact prefixes
 };
 
 int make_batch(grb_ctx *ctx, const grb_index *const *idx, const u64 *left_offsets, int nseq, Batch *b) {
@@ -639,6 +1101,8 @@ int make_batch(grb_ctx *ctx, const grb_index *const *idx, const u64 *left_offset
     std::vector<SeqDev> h((size_t)nseq);
     std::vector<u32> tb((size_t)nseq + 1);
     u64 tiles = 0;
+    b->uniform = true;
+    const u32 *zeros = (const u32 *)ctx->zeros;
     for (int s = 0; s < nseq; s++) {
         if (left_offsets[s + 1] < left_offsets[s]) return grb_fail(ctx, GRB_ERR_INVALID_ARG, "batch: left_offsets must be non-decreasing");
         SeqDev d;
@@ -655,23 +1119,44 @@ int make_batch(grb_ctx *ctx, const grb_index *const *idx, const u64 *left_offset
             d.vbits_a = ix->vbits_a;
             d.vcnt_a = ix->vcnt_a;
             d.vcnt_b = ix->vcnt_b;
-            d.loc_a = ix->loc_a;
-            d.loc_b = ix->loc_b;
+            d.pfx_a = ix->pfx_a;
+            d.pfx_b = ix->pfx_b;
+            d.lut_a = ix->lut_a;
+            d.lut_b = ix->lut_b;
+            d.lut_shift = ix->lut_shift;
+            d.lut_bmax = ix->lut_bmax;
             d.base_a = ix->base_a;
             d.base_b = ix->base_b;
             d.n = ix->n;
             d.e0 = ix->e0;
+            d.scale = ldexp(1.0, ix->e0);
             d.sum_mode = ix->has_scores ? ix->sum_mode : 3;
             d.has_nulls = ix->has_nulls;
             d.has_scores = ix->has_scores;
+            d.fast_cmax = 0;
+            if (d.sum_mode == GRB_SUM_COMPACT) {
+                int room = 63 - ix->width;  // a group of fewer than 2^room members sums to < 2^63
+                d.fast_cmax = room >= 31 ? 0x7fffffffu : (1u << room);
+            }
+            if (!(ix->has_scores && !ix->has_nulls && ix->sum_mode == GRB_SUM_COMPACT)) b->uniform = false;
         } else {
-            d.sum_mode = 3;  // nothing to sum: every group is empty
+            // absent seqname / empty index: every group is empty; all tables read as zeros
+            d.lut_a = d.lut_b = zeros;
+            d.starts = d.ends = d.ends_sorted = zeros + 256;  // sentinel keys: every forward scan stops at once
+            d.pfx_a = d.pfx_b = (const u64 *)zeros;
+            d.base_a = d.base_b = (const i128 *)zeros;
+            d.lut_shift = 31;
+            d.lut_bmax = 0;
+            d.scale = 1.0;
+            d.fast_cmax = 0x7fffffffu;
+            d.sum_mode = 3;  // nothing to sum
         }
         d.left_begin = left_offsets[s];
         d.left_end = left_offsets[s + 1];
         d.tile_begin = (u32)tiles;
         tb[s] = (u32)tiles;
-        tiles += (d.left_end - d.left_begin + TILE - 1) / TILE;
+        // tiles are aligned to multiples of TILE in the concatenated left index space
+        if (d.left_end > d.left_begin) tiles += ((d.left_end + TILE - 1) >> TILE_SHIFT) - (d.left_begin >> TILE_SHIFT);
         if (tiles >= 0x7fffffffull) return grb_fail(ctx, GRB_ERR_UNSUPPORTED, "batch: too many left ranges for one call");
         h[s] = d;
     }
@@ -688,12 +1173,62 @@ int make_batch(grb_ctx *ctx, const grb_index *const *idx, const u64 *left_offset
     return GRB_OK;
 }
 
-template <int MODE>
+template <int MODE, int FAST>
 int launch_tile(grb_ctx *ctx, const Batch &b, const u32 *ls, const u32 *le, const TileOut &o) {
     if (b.ntiles == 0) return GRB_OK;
-    k_tile<MODE><<<b.ntiles, TILE_TPB, 0, ctx->stream>>>(b.seqs, b.tile_begin, b.nseq, ls, le, o, ctx->tile_mode);
+    k_tile<MODE, FAST><<<b.ntiles, TILE_TPB, 0, ctx->stream>>>(b.seqs, b.tile_begin, b.nseq, ls, le, b.total, o, ctx->tile_mode);
     GRB_LAUNCHED(ctx);
     return GRB_OK;
+}
+
+template <int FAST>
+int launch_pipe(grb_ctx *ctx, const Batch &b, const u32 *ls, const u32 *le, const TileOut &o) {
+    if (b.ntiles == 0) return GRB_OK;
+    static bool configured = false;
+    if (!configured) {
+        GRB_CUDA(ctx, cudaFuncSetAttribute(k_map_pipe<FAST>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(PipeSmem)));
+        configured = true;
+    }
+    u32 grid = (u32)ctx->sm_count;
+    if (grid > b.ntiles) grid = b.ntiles;
+    k_map_pipe<FAST><<<grid, PIPE_THREADS, sizeof(PipeSmem), ctx->stream>>>(b.seqs, b.tile_begin, b.nseq, b.ntiles, ls, le, b.total, o.out,
+                                                                          o.out_valid, ctx->tile_mode);
+    GRB_LAUNCHED(ctx);
+    return GRB_OK;
+}
+
+// MAP launch: the single-reduction fast kernels when the batch is uniform, else the general one.
+template <int MODE>
+int launch_map(grb_ctx *ctx, const Batch &b, const u32 *ls, const u32 *le, const TileOut &o) {
+    if (MODE == M_MAP && b.uniform && o.k == 1 && ctx->pipe_mode) {
+        switch (o.ops[0]) {
+            case GRB_OP_MEAN:
+                return launch_pipe<GRB_OP_MEAN>(ctx, b, ls, le, o);
+            case GRB_OP_SUM:
+                return launch_pipe<GRB_OP_SUM>(ctx, b, ls, le, o);
+            case GRB_OP_SUM_NOT_EMPTY:
+                return launch_pipe<GRB_OP_SUM_NOT_EMPTY>(ctx, b, ls, le, o);
+            case GRB_OP_COUNT:
+                return launch_pipe<GRB_OP_COUNT>(ctx, b, ls, le, o);
+            default:
+                break;
+        }
+    }
+    if (b.uniform && o.k == 1) {
+        switch (o.ops[0]) {
+            case GRB_OP_MEAN:
+                return launch_tile<MODE, GRB_OP_MEAN>(ctx, b, ls, le, o);
+            case GRB_OP_SUM:
+                return launch_tile<MODE, GRB_OP_SUM>(ctx, b, ls, le, o);
+            case GRB_OP_SUM_NOT_EMPTY:
+                return launch_tile<MODE, GRB_OP_SUM_NOT_EMPTY>(ctx, b, ls, le, o);
+            case GRB_OP_COUNT:
+                return launch_tile<MODE, GRB_OP_COUNT>(ctx, b, ls, le, o);
+            default:
+                break;
+        }
+    }
+    return launch_tile<MODE, -1>(ctx, b, ls, le, o);
 }
 
 int enter(grb_ctx *ctx) {
@@ -731,7 +1266,7 @@ int grb_count_overlaps_batch(grb_ctx *ctx, const grb_index *const *idx, const ui
     TileOut o;
     memset(&o, 0, sizeof(o));
     o.counts = dc.as<u32>();
-    GRB_TRY(launch_tile<M_COUNTS>(ctx, b, dls.as<u32>(), dle.as<u32>(), o));
+    GRB_TRY(launch_tile<M_COUNTS, -1>(ctx, b, dls.as<u32>(), dle.as<u32>(), o));
     GRB_TRY(dc.finish(ctx));
     if (dc.host) GRB_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
     return GRB_OK;
@@ -767,7 +1302,7 @@ int grb_filter_overlaps_batch(grb_ctx *ctx, const grb_index *const *idx, const u
         GRB_CUDA(ctx, cudaMemsetAsync(nk.p, 0, 8, ctx->stream));
         o.n_kept = nk.as<unsigned long long>();
     }
-    GRB_TRY(launch_tile<M_KEEP>(ctx, b, dls.as<u32>(), dle.as<u32>(), o));
+    GRB_TRY(launch_tile<M_KEEP, -1>(ctx, b, dls.as<u32>(), dle.as<u32>(), o));
     GRB_TRY(dk.finish(ctx));
     if (n_kept) GRB_CUDA(ctx, cudaMemcpyAsync(n_kept, nk.p, 8, cudaMemcpyDeviceToHost, ctx->stream));
     if (dk.host || n_kept) GRB_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
@@ -837,14 +1372,14 @@ int grb_map_joins_f64_batch(grb_ctx *ctx, const grb_index *const *idx, const uin
     o.need_sum = need_sum;
     for (int c = 0; c < k; c++) o.ops[c] = ops[c];
     if (!need_members) {
-        GRB_TRY(launch_tile<M_MAP>(ctx, b, dls.as<u32>(), dle.as<u32>(), o));
+        GRB_TRY(launch_map<M_MAP>(ctx, b, dls.as<u32>(), dle.as<u32>(), o));
     } else {
         TempBuf ub, lb, heavy;
         GRB_TRY(ub.alloc(ctx, b.total * 4));
         GRB_TRY(lb.alloc(ctx, b.total * 4));
         o.ub = ub.as<u32>();
         o.lb = lb.as<u32>();
-        GRB_TRY(launch_tile<M_MAP | M_UBLB>(ctx, b, dls.as<u32>(), dle.as<u32>(), o));
+        GRB_TRY(launch_map<M_MAP | M_UBLB>(ctx, b, dls.as<u32>(), dle.as<u32>(), o));
         SweepOut so;
         memset(&so, 0, sizeof(so));
         so.out = o.out;
@@ -916,7 +1451,7 @@ int grb_left_overlaps(grb_ctx *ctx, const grb_index *idx, const uint32_t *ls, co
         o.counts = counts.as<u32>();
         o.ub = ub.as<u32>();
         o.lb = lb.as<u32>();
-        if ((rc = launch_tile<M_COUNTS | M_UBLB>(ctx, b, p->ls, p->le, o))) break;
+        if ((rc = launch_tile<M_COUNTS | M_UBLB, -1>(ctx, b, p->ls, p->le, o))) break;
         if ((rc = grb_scan_u32_to_u64(ctx, counts.as<u32>(), p->offsets, nl, true))) break;
         u64 np = 0;
         cudaMemcpyAsync(&np, p->offsets + nl, 8, cudaMemcpyDeviceToHost, ctx->stream);

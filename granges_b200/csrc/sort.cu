@@ -47,7 +47,7 @@ __global__ void k_key_stats(const u64 *__restrict__ keys, size_t n, KeyStats *st
     }
 }
 
-__global__ void __launch_bounds__(SORT_TPB) k_tile_hist(const u64 *__restrict__ keys, size_t n, int shift, u32 ntiles,
+__global__ void __launch_bounds__(SORT_TPB) k_sort_hist(const u64 *__restrict__ keys, size_t n, int shift, u32 ntiles,
                                                         u32 *__restrict__ hist /* [256][ntiles] */) {
     __shared__ u32 h[256];
     h[threadIdx.x] = 0;
@@ -157,7 +157,7 @@ int grb_sort_pairs(grb_ctx *ctx, u64 *keys, u32 *vals, u64 *keys_alt, u32 *vals_
     for (int pass = 0; pass < 8; pass++) {
         int shift = pass * 8;
         if (((varying >> shift) & 0xff) == 0) continue;  // every key has the same digit here
-        k_tile_hist<<<ntiles, SORT_TPB, 0, ctx->stream>>>(kin, n, shift, ntiles, hist.as<u32>());
+        k_sort_hist<<<ntiles, SORT_TPB, 0, ctx->stream>>>(kin, n, shift, ntiles, hist.as<u32>());
         GRB_LAUNCHED(ctx);
         GRB_TRY(grb_scan_u32_to_u32(ctx, hist.as<u32>(), offs.as<u32>(), (size_t)256 * ntiles, false));
         k_scatter<<<ntiles, SORT_TPB, 0, ctx->stream>>>(kin, vin, n, shift, ntiles, offs.as<u32>(), kout, vout);

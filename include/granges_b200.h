@@ -85,8 +85,10 @@ typedef struct grb_ranges grb_ranges;
 int grb_abi_version(void);
 /* Bind a context to CUDA device `device` (creates its own non-blocking stream). */
 int grb_ctx_create(int device, grb_ctx **out);
-/* Run on a caller-provided cudaStream_t instead (NULL = back to the context's own stream). */
+/* Run on a caller-provided cudaStream_t instead (a null handle is CUDA's default stream). */
 int grb_ctx_set_stream(grb_ctx *ctx, void *cuda_stream);
+/* Back to the stream the context created for itself. */
+int grb_ctx_use_own_stream(grb_ctx *ctx);
 /* Block until everything enqueued on the context's stream has finished. */
 int grb_ctx_sync(grb_ctx *ctx);
 void grb_ctx_destroy(grb_ctx *ctx);

@@ -327,3 +327,35 @@ def test_unsorted_index_large_sort(eng, orc):
     es = np.sort(re)
     want = np.searchsorted(np.sort(rs), le, side="left") - np.searchsorted(es, ls, side="right")
     assert (got == want).all()
+
+
+@pytest.mark.parametrize("op", ["mean", "sum", "sum-not-empty", "count"])
+def test_pipeline_kernel_vs_tile_kernel(orc, monkeypatch, op):
+    """Single-reduction maps run through the persistent TMA pipeline (k_map_pipe); it must agree bit
+    for bit with the one-tile-per-CTA kernel and with the oracle -- ragged tiles at seqname
+    boundaries, an absent seqname, tiles whose windows do not fit (sparse lefts over dense rights),
+    unsorted lefts, and enough tiles that every ring slot is reused many times."""
+    import granges_b200 as gb
+
+    rng = np.random.default_rng(17)
+    specs = [(40_000, 30_000, 900_000, True), (1, 5, 100, True), (2_500, 0, 1000, True), (5_000, 200_000, 3_000_000, True),
+             (3_000, 3_000, 60_000, False), (1023, 2000, 30_000, True), (1025, 2000, 30_000, True)]
+    cases = [random_case(300 + i, nl, nr, span=span, maxlen=999, sorted_left=srt) for i, (nl, nr, span, srt) in enumerate(specs)]
+    off = np.concatenate([[0], np.cumsum([len(c["ls"]) for c in cases])]).astype(np.uint64)
+    ls = np.concatenate([c["ls"] for c in cases])
+    le = np.concatenate([c["le"] for c in cases])
+    res = {}
+    for mode in ("1", "0"):
+        monkeypatch.setenv("GRB_PIPE_MODE", mode)
+        ctx = gb.Context(0)
+        idxs = [None if i == 2 else ctx.index_build(c["rs"], c["re"]).set_scores(c["scores"]) for i, c in enumerate(cases)]
+        res[mode] = ctx.map_joins_batch(idxs, off, ls, le, [op])
+    assert (res["1"][1] == res["0"][1]).all()
+    assert (res["1"][0] == res["0"][0]).all()
+    for i, c in enumerate(cases):
+        sl = slice(int(off[i]), int(off[i + 1]))
+        t = None if i == 2 else orc.Tree(c["rs"], c["re"])
+        want, wv = orc.map_joins(t, None if t is None else c["scores"], None, c["ls"], c["le"], [op])
+        assert (res["1"][1][sl] == wv).all()
+        m = wv[:, 0] == 1
+        assert np.allclose(res["1"][0][sl][m], want[m], rtol=1e-12, atol=0)
