@@ -421,12 +421,13 @@ int grb_index_build(grb_ctx *ctx, const uint32_t *starts, const uint32_t *ends, 
         k_unpack_end_order<<<blocks_for(n + PAD, 256), 256, 0, ctx->stream>>>(ke, ve, n, ix->ends_sorted, ix->perm_e);
         ctx->launches++;
         {
-            // coordinate bins of ~4-8 rights each; the largest end bounds every key
+            // coordinate bins of ~2-4 rights each (so one round of four compares usually ends a search);
+            // the largest end bounds every key
             u32 maxend = 0;
             if (n) cudaMemcpyAsync(&maxend, ke + (n - 1), 4, cudaMemcpyDeviceToHost, ctx->stream);  // low half of the last u64 key
             cudaStreamSynchronize(ctx->stream);
             int shift = 0;
-            while (shift < 31 && ((u64)maxend >> shift) > (u64)n / 4 + 1) shift++;
+            while (shift < 31 && ((u64)maxend >> shift) > (u64)n / 2 + 1) shift++;
             ix->lut_shift = shift;
             ix->lut_bmax = (maxend >> shift) + 1;
             size_t entries = (size_t)ix->lut_bmax + 1 + PAD;

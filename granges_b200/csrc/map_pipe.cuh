@@ -1,0 +1,408 @@
+// map_pipe.cuh -- the pipelined single-reduction map kernel (headline path: `granges map --func mean`).
+// Included by query.cu after the PTX / search helpers.
+//
+// Same arithmetic as k_tile<M_MAP, FAST>, organised as a persistent, warp-specialised TMA pipeline
+// so that no warp ever waits on a dependent chain of global loads.  One CTA per SM, tiles
+// blockIdx.x, blockIdx.x + gridDim.x, ...; per tile (1024 consecutive lefts of one seqname):
+//
+//   warp 0  "loader"    A: TMA the lefts (ls, le) of tile j into the lefts ring           -> fullL
+//                       C: (3 tiles later) read the tile's bins / table entries, TMA the slices of
+//                          starts, ends_sorted, both bin tables and both prefix arrays that the
+//                          tile can touch into the window ring                             -> fullW
+//   warp 1  "surveyor"  B: min / max of the tile's lefts out of shared memory -> coordinate bins
+//                          -> four bin-table entries by plain loads, published one iteration
+//                          later so the loads have a whole iteration to land                -> statsL
+//   warps 2..9 "consumers": wait fullW, resolve ub / lb of 4 lefts per thread out of shared memory,
+//                          exact sums from the staged prefixes, write results, release       -> emptyW, emptyL
+//
+// Tiles whose windows do not fit the ring slots (sparse lefts over dense rights) are resolved by
+// per-left global searches inside the consumers; results are identical.
+
+constexpr int PIPE_NC = 16;  // consumer warps
+constexpr int PIPE_LPT = TILE / (PIPE_NC * 32);  // consecutive lefts per consumer thread
+constexpr int PIPE_THREADS = (PIPE_NC + 2) * 32;
+constexpr int PIPE_LSTAGES = 8;
+constexpr int PIPE_WSTAGES = 3;
+constexpr int PIPE_LEAD = 3;    // phase C runs this many tiles behind phase A
+constexpr u32 PIPE_WIN = 1536;  // keys (and prefixes) per staged window
+constexpr u32 PIPE_LUT = 768;   // bin-table entries per staged slice
+constexpr int PIPE_MAXSEQ = 32; // seqnames per launch (their descriptors live in shared memory)
+
+struct PipeSeq {
+    const u32 *starts, *ends_sorted, *lut_a, *lut_b;
+    const u64 *pfx_a, *pfx_b;
+    u64 left_begin, left_end;
+    double scale;
+    u32 tile_begin, bmax, fast_cmax;
+    int sh;
+};
+
+struct PipeTile {      // one per lefts-ring slot
+    u64 g_first;       // global index of the tile's slot 0                (loader)
+    u32 vlo, vhi;      // valid slots of the tile: [vlo, vhi)              (loader)
+    int seq;           //                                                  (loader)
+    u32 bin[4];        // bins of min l.end, max l.end, min l.start+1, max l.start+1   (surveyor)
+    u32 bound[4];      // lut_a[bin0], lut_a[bin1 + 1], lut_b[bin2], lut_b[bin3 + 1]     (surveyor)
+};
+
+struct PipeDesc {      // one per window-ring slot (loader -> consumers)
+    u64 g_first;
+    u32 vlo, vhi;
+    u32 a0, b0, la0, lb0;
+    u32 staged;
+    int seq;
+};
+
+struct PipeSmem {
+    alignas(16) u32 ls[PIPE_LSTAGES][TILE];
+    alignas(16) u32 le[PIPE_LSTAGES][TILE];
+    alignas(16) u64 pa[PIPE_WSTAGES][PIPE_WIN + 8];
+    alignas(16) u64 pb[PIPE_WSTAGES][PIPE_WIN + 8];
+    alignas(16) u32 ka[PIPE_WSTAGES][PIPE_WIN + 8];
+    alignas(16) u32 kb[PIPE_WSTAGES][PIPE_WIN + 8];
+    alignas(16) u32 la[PIPE_WSTAGES][PIPE_LUT + 8];
+    alignas(16) u32 lb[PIPE_WSTAGES][PIPE_LUT + 8];
+    PipeSeq seq[PIPE_MAXSEQ];
+    PipeTile tile[PIPE_LSTAGES];
+    PipeDesc desc[PIPE_WSTAGES];
+    alignas(8) u64 fullL[PIPE_LSTAGES];
+    alignas(8) u64 emptyL[PIPE_LSTAGES];
+    alignas(8) u64 statsL[PIPE_LSTAGES];
+    alignas(8) u64 fullW[PIPE_WSTAGES];
+    alignas(8) u64 emptyW[PIPE_WSTAGES];
+};
+
+__device__ __forceinline__ void mbar_arrive(u64 *bar) {
+    asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_addr(bar)) : "memory");
+}
+
+// flags: bit 0 = stage with TMA; bit 1 = debug, consumers skip the arithmetic (pipeline-only timing)
+template <int FAST>
+__global__ void __launch_bounds__(PIPE_THREADS, 1) k_map_pipe(const SeqDev *__restrict__ seqs, int nseq, u32 ntiles,
+                                                              const u32 *__restrict__ ls, const u32 *__restrict__ le,
+                                                              double *__restrict__ out, u8 *__restrict__ out_valid, int flags) {
+    extern __shared__ __align__(128) unsigned char smem_raw[];
+    PipeSmem &S = *reinterpret_cast<PipeSmem *>(smem_raw);
+    const u32 tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const bool use_tma = flags & 1;
+    if (tid == 0) {
+        for (int i = 0; i < PIPE_LSTAGES; i++) {
+            mbar_init(&S.fullL[i], 1);
+            mbar_init(&S.emptyL[i], PIPE_NC);
+            mbar_init(&S.statsL[i], 1);
+        }
+        for (int i = 0; i < PIPE_WSTAGES; i++) {
+            mbar_init(&S.fullW[i], 1);
+            mbar_init(&S.emptyW[i], PIPE_NC);
+        }
+    }
+    if ((int)tid < nseq) {
+        const SeqDev *sd = &seqs[tid];
+        PipeSeq &q = S.seq[tid];
+        q.starts = sd->starts;
+        q.ends_sorted = sd->ends_sorted;
+        q.lut_a = sd->lut_a;
+        q.lut_b = sd->lut_b;
+        q.pfx_a = sd->pfx_a;
+        q.pfx_b = sd->pfx_b;
+        q.left_begin = sd->left_begin;
+        q.left_end = sd->left_end;
+        q.scale = sd->scale;
+        q.tile_begin = sd->tile_begin;
+        q.bmax = sd->lut_bmax;
+        q.fast_cmax = sd->fast_cmax;
+        q.sh = sd->lut_shift;
+    }
+    __syncthreads();
+    const u32 nmine = blockIdx.x < ntiles ? (ntiles - blockIdx.x + gridDim.x - 1) / gridDim.x : 0;
+
+    if (warp == 0) {
+        // ================= loader =================
+        const bool vec_in = ((((uintptr_t)ls) | ((uintptr_t)le)) & 15) == 0;
+        int sq = 0;  // seqname of the tile phase A is at; tiles only move forward
+        for (u32 it = 0; it < nmine + PIPE_LEAD; it++) {
+            // ---- C: windows of tile it - PIPE_LEAD
+            if (it >= PIPE_LEAD) {
+                const u32 j = it - PIPE_LEAD, sw = j % PIPE_WSTAGES, sl = j % PIPE_LSTAGES;
+                mbar_wait(&S.statsL[sl], (j / PIPE_LSTAGES) & 1);
+                mbar_wait(&S.emptyW[sw], ((j / PIPE_WSTAGES) & 1) ^ 1);
+                if (lane == 0) {
+                    const PipeTile &ti = S.tile[sl];
+                    const PipeSeq &q = S.seq[ti.seq];
+                    const u32 a0 = ti.bound[0] & ~3u, b0 = ti.bound[2] & ~3u, la0 = ti.bin[0] & ~3u, lb0 = ti.bin[2] & ~3u;
+                    // + 4: the forward scan may read up to 3 keys past the last one it can return
+                    const u32 alen = ti.bound[1] - a0 + 4, blen = ti.bound[3] - b0 + 4;
+                    const u32 lalen = ti.bin[1] + 1 - la0, lblen = ti.bin[3] + 1 - lb0;
+                    const bool staged = use_tma && alen <= PIPE_WIN && blen <= PIPE_WIN && lalen <= PIPE_LUT && lblen <= PIPE_LUT;
+                    PipeDesc &d = S.desc[sw];
+                    d.g_first = ti.g_first;
+                    d.vlo = ti.vlo;
+                    d.vhi = ti.vhi;
+                    d.seq = ti.seq;
+                    d.a0 = a0;
+                    d.b0 = b0;
+                    d.la0 = la0;
+                    d.lb0 = lb0;
+                    d.staged = staged ? 1u : 0u;
+                    if (staged) {
+                        const u32 by_a = (alen * 4 + 15) & ~15u, by_b = (blen * 4 + 15) & ~15u;
+                        const u32 by_la = (lalen * 4 + 15) & ~15u, by_lb = (lblen * 4 + 15) & ~15u;
+                        const u32 by_pa = (alen * 8 + 15) & ~15u, by_pb = (blen * 8 + 15) & ~15u;
+                        const bool want_pfx = FAST != GRB_OP_COUNT;
+                        mbar_arrive_expect_tx(&S.fullW[sw], by_a + by_b + by_la + by_lb + (want_pfx ? by_pa + by_pb : 0u));
+                        tma_load_1d(S.la[sw], q.lut_a + la0, by_la, &S.fullW[sw]);
+                        tma_load_1d(S.lb[sw], q.lut_b + lb0, by_lb, &S.fullW[sw]);
+                        tma_load_1d(S.ka[sw], q.starts + a0, by_a, &S.fullW[sw]);
+                        tma_load_1d(S.kb[sw], q.ends_sorted + b0, by_b, &S.fullW[sw]);
+                        if (want_pfx) {
+                            tma_load_1d(S.pa[sw], q.pfx_a + a0, by_pa, &S.fullW[sw]);
+                            tma_load_1d(S.pb[sw], q.pfx_b + b0, by_pb, &S.fullW[sw]);
+                        }
+                    } else {
+                        mbar_arrive(&S.fullW[sw]);
+                    }
+                }
+                __syncwarp();
+            }
+            // ---- A: lefts of tile `it`
+            if (it < nmine) {
+                const u32 j = it, sl = j % PIPE_LSTAGES;
+                const u32 t = blockIdx.x + j * gridDim.x;
+                while (sq + 1 < nseq && S.seq[sq + 1].tile_begin <= t) sq++;
+                const PipeSeq &q = S.seq[sq];
+                const u64 g_first = ((q.left_begin >> TILE_SHIFT) + (t - q.tile_begin)) << TILE_SHIFT;
+                const u64 lo_g = q.left_begin > g_first ? q.left_begin : g_first;
+                const u64 hi_g = q.left_end < g_first + TILE ? q.left_end : g_first + TILE;
+                const bool whole = vec_in && lo_g == g_first && hi_g == g_first + TILE;
+                mbar_wait(&S.emptyL[sl], ((j / PIPE_LSTAGES) & 1) ^ 1);
+                if (lane == 0) {
+                    PipeTile &ti = S.tile[sl];
+                    ti.g_first = g_first;
+                    ti.vlo = (u32)(lo_g - g_first);
+                    ti.vhi = (u32)(hi_g - g_first);
+                    ti.seq = sq;
+                }
+                if (whole && use_tma) {
+                    if (lane == 0) {
+                        mbar_arrive_expect_tx(&S.fullL[sl], 2 * TILE * 4);
+                        tma_load_1d(S.ls[sl], ls + g_first, TILE * 4, &S.fullL[sl]);
+                        tma_load_1d(S.le[sl], le + g_first, TILE * 4, &S.fullL[sl]);
+                    }
+                } else {
+                    // ragged tile (seqname boundary, end of the arrays, unaligned pointers): plain copies
+                    for (u32 i = lane; i < TILE; i += 32) {
+                        const u64 g = g_first + i;
+                        const bool ok = g >= lo_g && g < hi_g;
+                        S.ls[sl][i] = ok ? ls[g] : 0u;
+                        S.le[sl][i] = ok ? le[g] : 0u;
+                    }
+                    __syncwarp();
+                    if (lane == 0) mbar_arrive(&S.fullL[sl]);
+                }
+                __syncwarp();
+            }
+        }
+        return;
+    }
+
+    if (warp == 1) {
+        // ================= surveyor =================
+        u32 bin_prev = 0, bound_prev = 0;
+        for (u32 j = 0; j <= nmine; j++) {
+            u32 bin_new = 0, bound_new = 0;
+            if (j < nmine) {
+                const u32 sl = j % PIPE_LSTAGES;
+                mbar_wait(&S.fullL[sl], (j / PIPE_LSTAGES) & 1);
+                const PipeTile &ti = S.tile[sl];
+                const u32 vlo = ti.vlo, vhi = ti.vhi;
+                const PipeSeq &q = S.seq[ti.seq];
+                u32 mn_s = 0xffffffffu, mx_s = 0, mn_e = 0xffffffffu, mx_e = 0;
+                if (vlo == 0 && vhi == TILE) {
+                    const uint4 *vs = reinterpret_cast<const uint4 *>(S.ls[sl]);
+                    const uint4 *ve = reinterpret_cast<const uint4 *>(S.le[sl]);
+#pragma unroll
+                    for (int r = 0; r < TILE / 128; r++) {
+                        const uint4 x = vs[r * 32 + lane], y = ve[r * 32 + lane];
+                        mn_s = min(mn_s, min(min(x.x, x.y), min(x.z, x.w)));
+                        mx_s = max(mx_s, max(max(x.x, x.y), max(x.z, x.w)));
+                        mn_e = min(mn_e, min(min(y.x, y.y), min(y.z, y.w)));
+                        mx_e = max(mx_e, max(max(y.x, y.y), max(y.z, y.w)));
+                    }
+                } else {
+                    for (u32 i = vlo + lane; i < vhi; i += 32) {
+                        const u32 x = S.ls[sl][i], y = S.le[sl][i];
+                        mn_s = min(mn_s, x);
+                        mx_s = max(mx_s, x);
+                        mn_e = min(mn_e, y);
+                        mx_e = max(mx_e, y);
+                    }
+                }
+                mn_e = warp_min(mn_e);
+                mx_e = warp_max(mx_e);
+                mn_s = warp_min(mn_s);
+                mx_s = warp_max(mx_s);
+                const u32 qq = lane & 3;
+                const u32 v = qq == 0 ? mn_e : qq == 1 ? mx_e : qq == 2 ? mn_s : mx_s;
+                const u32 x = v + (qq >> 1);  // l.end for the starts table, l.start + 1 for the ends table
+                bin_new = min(x >> q.sh, q.bmax);
+                bound_new = ((qq < 2) ? q.lut_a : q.lut_b)[bin_new + (qq & 1)];
+            }
+            if (j >= 1) {
+                // publish the previous tile: its table entries were requested one iteration ago
+                const u32 sl = (j - 1) % PIPE_LSTAGES;
+                if (lane < 4) {
+                    S.tile[sl].bin[lane] = bin_prev;
+                    S.tile[sl].bound[lane] = bound_prev;
+                }
+                __syncwarp();
+                if (lane == 0) mbar_arrive(&S.statsL[sl]);
+            }
+            bin_prev = bin_new;
+            bound_prev = bound_new;
+        }
+        return;
+    }
+
+    // ================= consumers =================
+    const u32 cw = warp - 2;
+    const u32 i0 = (cw * 32 + lane) * PIPE_LPT;  // first slot of this thread inside a tile
+    const bool ovec = ((((uintptr_t)out) & 15) | (((uintptr_t)out_valid) & 3)) == 0;
+    const bool skip = flags & 2;
+    for (u32 j = 0; j < nmine; j++) {
+        const u32 sw = j % PIPE_WSTAGES, sl = j % PIPE_LSTAGES;
+        mbar_wait(&S.fullW[sw], (j / PIPE_WSTAGES) & 1);
+        if (!skip) {
+            const PipeDesc &d = S.desc[sw];
+            const PipeSeq &q = S.seq[d.seq];
+            const u32 vlo = d.vlo, vhi = d.vhi;
+            const int sh = q.sh;
+            const u32 bmax = q.bmax, fast_cmax = q.fast_cmax;
+            const double scale = q.scale;
+            u32 a[PIPE_LPT], b[PIPE_LPT];
+            if (PIPE_LPT == 4) {
+                const uint4 va = *reinterpret_cast<const uint4 *>(&S.ls[sl][i0]);
+                const uint4 vb = *reinterpret_cast<const uint4 *>(&S.le[sl][i0]);
+                a[0] = va.x, a[1 % PIPE_LPT] = va.y, a[2 % PIPE_LPT] = va.z, a[3 % PIPE_LPT] = va.w;
+                b[0] = vb.x, b[1 % PIPE_LPT] = vb.y, b[2 % PIPE_LPT] = vb.z, b[3 % PIPE_LPT] = vb.w;
+            } else if (PIPE_LPT == 2) {
+                const uint2 va = *reinterpret_cast<const uint2 *>(&S.ls[sl][i0]);
+                const uint2 vb = *reinterpret_cast<const uint2 *>(&S.le[sl][i0]);
+                a[0] = va.x, a[1 % PIPE_LPT] = va.y;
+                b[0] = vb.x, b[1 % PIPE_LPT] = vb.y;
+            } else {
+#pragma unroll
+                for (int k = 0; k < PIPE_LPT; k++) a[k] = S.ls[sl][i0 + k], b[k] = S.le[sl][i0 + k];
+            }
+            bool okv[PIPE_LPT];
+#pragma unroll
+            for (int k = 0; k < PIPE_LPT; k++) okv[k] = i0 + k >= vlo && i0 + k < vhi;
+            const u32 a0 = d.a0, b0 = d.b0, la0 = d.la0, lb0 = d.lb0;
+            const SeqDev *__restrict__ sd = &seqs[d.seq];  // only dereferenced on the rare paths
+            u32 ub[PIPE_LPT], lbk[PIPE_LPT];  // absolute positions
+            u64 pa[PIPE_LPT], pb[PIPE_LPT];
+            if (d.staged) {
+                const u32 *__restrict__ KA = S.ka[sw];
+                const u32 *__restrict__ KB = S.kb[sw];
+                u32 pA[PIPE_LPT], pB[PIPE_LPT], cA[PIPE_LPT], cB[PIPE_LPT];
+                // bin -> first position of the bin (relative to the staged slice); invalid slots scan with x = 0
+#pragma unroll
+                for (int k = 0; k < PIPE_LPT; k++) {
+                    const u32 ba = min(b[k] >> sh, bmax), bb = min((a[k] + 1) >> sh, bmax);
+                    pA[k] = okv[k] ? S.la[sw][ba - la0] - a0 : 0u;
+                    pB[k] = okv[k] ? S.lb[sw][bb - lb0] - b0 : 0u;
+                }
+                // one unconditional round of four compares per search: bins hold ~2-3 keys, so this almost always ends it
+#pragma unroll
+                for (int k = 0; k < PIPE_LPT; k++) {
+                    const u32 xa = okv[k] ? b[k] : 0u, xb = okv[k] ? a[k] + 1 : 0u;
+                    cA[k] = (KA[pA[k]] < xa ? 1u : 0u) + (KA[pA[k] + 1] < xa ? 1u : 0u) + (KA[pA[k] + 2] < xa ? 1u : 0u) +
+                            (KA[pA[k] + 3] < xa ? 1u : 0u);
+                    cB[k] = (KB[pB[k]] < xb ? 1u : 0u) + (KB[pB[k] + 1] < xb ? 1u : 0u) + (KB[pB[k] + 2] < xb ? 1u : 0u) +
+                            (KB[pB[k] + 3] < xb ? 1u : 0u);
+                }
+#pragma unroll
+                for (int k = 0; k < PIPE_LPT; k++) {
+                    pA[k] += cA[k];
+                    pB[k] += cB[k];
+                    if (cA[k] == 4) pA[k] = scan_lower_bound(KA, pA[k], b[k]);      // rare: a crowded bin
+                    if (cB[k] == 4) pB[k] = scan_lower_bound(KB, pB[k], a[k] + 1);
+                    pa[k] = FAST != GRB_OP_COUNT ? S.pa[sw][pA[k]] : 0ull;
+                    pb[k] = FAST != GRB_OP_COUNT ? S.pb[sw][pB[k]] : 0ull;
+                    ub[k] = a0 + pA[k];
+                    lbk[k] = b0 + pB[k];
+                }
+            } else {
+                // the tile's windows do not fit the ring slot: per-left searches in global memory
+#pragma unroll
+                for (int k = 0; k < PIPE_LPT; k++) {
+                    ub[k] = lbk[k] = 0;
+                    pa[k] = pb[k] = 0;
+                    if (!okv[k]) continue;
+                    const u32 xa = b[k], xb = a[k] + 1;
+                    ub[k] = scan_lower_bound(q.starts, q.lut_a[min(xa >> sh, bmax)], xa);
+                    lbk[k] = scan_lower_bound(q.ends_sorted, q.lut_b[min(xb >> sh, bmax)], xb);
+                    if (FAST != GRB_OP_COUNT) {
+                        pa[k] = q.pfx_a[ub[k]];
+                        pb[k] = q.pfx_b[lbk[k]];
+                    }
+                }
+            }
+            // ---- reductions
+            double r[PIPE_LPT];
+            u8 v[PIPE_LPT];
+#pragma unroll
+            for (int k = 0; k < PIPE_LPT; k++) {
+                const u32 c = ub[k] - lbk[k];
+                if (FAST == GRB_OP_COUNT) {
+                    r[k] = (double)c;
+                    v[k] = 1;
+                    continue;
+                }
+                double sum;
+                if (c < fast_cmax) {
+                    sum = (double)(i64)(pa[k] - pb[k]) * scale;
+                } else {
+                    const i128 ba128 = sd->base_a[ub[k] >> GRB_BASE_SHIFT], bb128 = sd->base_b[lbk[k] >> GRB_BASE_SHIFT];
+                    const i128 PA = ba128 + (i128)(i64)(pa[k] - (u64)(u128)ba128);
+                    const i128 PB = bb128 + (i128)(i64)(pb[k] - (u64)(u128)bb128);
+                    sum = fx_to_double(PA - PB, sd->e0);
+                }
+                if (FAST == GRB_OP_SUM) {
+                    r[k] = sum;
+                    v[k] = 1;
+                } else if (FAST == GRB_OP_SUM_NOT_EMPTY) {
+                    r[k] = sum;
+                    v[k] = c != 0;
+                } else {
+                    v[k] = c != 0;
+                    r[k] = c ? sum / (double)c : 0.0;
+                }
+            }
+            const u64 g0 = d.g_first + i0;
+            if (ovec && okv[0] && okv[PIPE_LPT - 1] && (PIPE_LPT == 4 || PIPE_LPT == 2)) {
+                double2 *po = reinterpret_cast<double2 *>(out + g0);
+                po[0] = make_double2(r[0], r[1 % PIPE_LPT]);
+                if (PIPE_LPT == 4) {
+                    po[1] = make_double2(r[2 % PIPE_LPT], r[3 % PIPE_LPT]);
+                    *reinterpret_cast<uchar4 *>(out_valid + g0) = make_uchar4(v[0], v[1 % PIPE_LPT], v[2 % PIPE_LPT], v[3 % PIPE_LPT]);
+                } else {
+                    *reinterpret_cast<uchar2 *>(out_valid + g0) = make_uchar2(v[0], v[1 % PIPE_LPT]);
+                }
+            } else {
+#pragma unroll
+                for (int k = 0; k < PIPE_LPT; k++) {
+                    if (okv[k]) {
+                        out[g0 + k] = r[k];
+                        out_valid[g0 + k] = v[k];
+                    }
+                }
+            }
+        }
+        // done with this stage: one arrival per consumer warp
+        __syncwarp();
+        if (lane == 0) {
+            mbar_arrive(&S.emptyW[sw]);
+            mbar_arrive(&S.emptyL[sl]);
+        }
+    }
+}

@@ -432,344 +432,7 @@ __global__ void __launch_bounds__(TILE_TPB) k_tile(const SeqDev *__restrict__ se
     }
 }
 
-// ---- the pipelined map kernel (headline path) ------------------------------------------
-//
-// Same arithmetic as k_tile<M_MAP, FAST>, organised as a persistent, warp-specialised TMA pipeline
-// so that no warp ever waits on a dependent chain of global loads:
-//   warp 0 (producer), software-pipelined over the CTA's tiles:
-//     A  tile j    : TMA the 1024 lefts (ls, le) into the lefts ring
-//     B  tile j-2  : min/max of those lefts out of shared memory -> coordinate bins -> four
-//                    bin-table entries fetched with plain loads (used one iteration later)
-//     C  tile j-3  : TMA the slices of starts, ends_sorted, both bin tables and both prefix-sum
-//                    arrays the tile can touch into the window ring, behind one mbarrier
-//   warps 1..8 (consumers): wait for the window stage, resolve ub / lb per left out of shared
-//     memory, take the exact sums from the staged prefixes, write the results, release the stage.
-// Rings: PIPE_LSTAGES x 8 KB of lefts, PIPE_WSTAGES x ~43 KB of windows (one CTA per SM).
-// Tiles whose windows do not fit (sparse lefts over dense rights) fall back to per-left global
-// searches inside the consumers; results are identical.
-
-constexpr int PIPE_NC = 8;  // consumer warps; each thread owns 4 consecutive lefts of a tile
-constexpr int PIPE_THREADS = (PIPE_NC + 1) * 32;
-constexpr int PIPE_LSTAGES = 6;
-constexpr int PIPE_WSTAGES = 3;
-constexpr u32 PIPE_WIN = 1536;  // keys (and prefixes) per staged window
-constexpr u32 PIPE_LUT = 768;   // bin-table entries per staged slice
-
-struct PipeDesc {
-    u64 g_first;   // global index of the tile's slot 0
-    double scale;
-    u32 vlo, vhi;  // valid slots of the tile: [vlo, vhi)
-    u32 a0, b0, la0, lb0;
-    u32 staged;
-    u32 bmax, fast_cmax;
-    int sh;
-    int seq;
-    u32 pad;
-};
-
-struct PipeSmem {
-    alignas(16) u32 ls[PIPE_LSTAGES][TILE];
-    alignas(16) u32 le[PIPE_LSTAGES][TILE];
-    alignas(16) u64 pa[PIPE_WSTAGES][PIPE_WIN + 8];
-    alignas(16) u64 pb[PIPE_WSTAGES][PIPE_WIN + 8];
-    alignas(16) u32 ka[PIPE_WSTAGES][PIPE_WIN + 8];
-    alignas(16) u32 kb[PIPE_WSTAGES][PIPE_WIN + 8];
-    alignas(16) u32 la[PIPE_WSTAGES][PIPE_LUT + 8];
-    alignas(16) u32 lb[PIPE_WSTAGES][PIPE_LUT + 8];
-    PipeDesc desc[PIPE_WSTAGES];
-    alignas(8) u64 fullL[PIPE_LSTAGES];
-    alignas(8) u64 emptyL[PIPE_LSTAGES];
-    alignas(8) u64 fullW[PIPE_WSTAGES];
-    alignas(8) u64 emptyW[PIPE_WSTAGES];
-};
-
-__device__ __forceinline__ void mbar_arrive(u64 *bar) {
-    asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_addr(bar)) : "memory");
-}
-
-// What phase B learns about a tile and phase C needs one iteration later (held in registers).
-struct PipeTileInfo {
-    u64 g_first;
-    u32 vlo, vhi;
-    int seq;
-    u32 bin, bound;  // lane q (mod 4): bin / table entry of reduction q
-};
-
-template <int FAST>
-__global__ void __launch_bounds__(PIPE_THREADS, 1) k_map_pipe(const SeqDev *__restrict__ seqs, const u32 *__restrict__ tile_begin,
-                                                              int nseq, u32 ntiles, const u32 *__restrict__ ls,
-                                                              const u32 *__restrict__ le, const u64 total,
-                                                              double *__restrict__ out, u8 *__restrict__ out_valid, int use_tma) {
-    extern __shared__ __align__(128) unsigned char smem_raw[];
-    PipeSmem &S = *reinterpret_cast<PipeSmem *>(smem_raw);
-    const u32 tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-    if (tid == 0) {
-        for (int i = 0; i < PIPE_LSTAGES; i++) {
-            mbar_init(&S.fullL[i], 1);
-            mbar_init(&S.emptyL[i], PIPE_NC);
-        }
-        for (int i = 0; i < PIPE_WSTAGES; i++) {
-            mbar_init(&S.fullW[i], 1);
-            mbar_init(&S.emptyW[i], PIPE_NC);
-        }
-    }
-    __syncthreads();
-    // tiles of this CTA: blockIdx.x, blockIdx.x + gridDim.x, ...
-    const u32 nmine = blockIdx.x < ntiles ? (ntiles - blockIdx.x + gridDim.x - 1) / gridDim.x : 0;
-    const bool vec_in = ((((uintptr_t)ls) | ((uintptr_t)le)) & 15) == 0;
-
-    if (warp == 0) {
-        // ================= producer =================
-        PipeTileInfo cur;  // filled by phase B, consumed by phase C of the NEXT iteration (the loads get a whole iteration)
-        cur.g_first = 0;
-        cur.vlo = cur.vhi = 0;
-        cur.seq = 0;
-        cur.bin = cur.bound = 0;
-        for (u32 it = 0; it < nmine + 3; it++) {
-            // ---- C: windows of tile it-3 (uses what phase B loaded one iteration ago)
-            if (it >= 3) {
-                const u32 j = it - 3, sw = j % PIPE_WSTAGES;
-                mbar_wait(&S.emptyW[sw], ((j / PIPE_WSTAGES) & 1) ^ 1);
-                const SeqDev *__restrict__ sd = &seqs[cur.seq];
-                const u32 binA0 = __shfl_sync(GRB_FULL, cur.bin, 0), binA1 = __shfl_sync(GRB_FULL, cur.bin, 1);
-                const u32 binB0 = __shfl_sync(GRB_FULL, cur.bin, 2), binB1 = __shfl_sync(GRB_FULL, cur.bin, 3);
-                const u32 A_lo = __shfl_sync(GRB_FULL, cur.bound, 0), A_hi = __shfl_sync(GRB_FULL, cur.bound, 1);
-                const u32 B_lo = __shfl_sync(GRB_FULL, cur.bound, 2), B_hi = __shfl_sync(GRB_FULL, cur.bound, 3);
-                if (lane == 0) {
-                    const u32 a0 = A_lo & ~3u, b0 = B_lo & ~3u, la0 = binA0 & ~3u, lb0 = binB0 & ~3u;
-                    // + 4: the forward scan may read up to 3 keys past the last one it can return
-                    const u32 alen = A_hi - a0 + 4, blen = B_hi - b0 + 4;
-                    const u32 lalen = binA1 + 1 - la0, lblen = binB1 + 1 - lb0;
-                    const bool staged = use_tma && alen <= PIPE_WIN && blen <= PIPE_WIN && lalen <= PIPE_LUT && lblen <= PIPE_LUT;
-                    PipeDesc &d = S.desc[sw];
-                    d.g_first = cur.g_first;
-                    d.vlo = cur.vlo;
-                    d.vhi = cur.vhi;
-                    d.seq = cur.seq;
-                    d.a0 = a0;
-                    d.b0 = b0;
-                    d.la0 = la0;
-                    d.lb0 = lb0;
-                    d.staged = staged ? 1u : 0u;
-                    d.sh = sd->lut_shift;
-                    d.bmax = sd->lut_bmax;
-                    d.fast_cmax = sd->fast_cmax;
-                    d.scale = sd->scale;
-                    if (staged) {
-                        const u32 by_a = (alen * 4 + 15) & ~15u, by_b = (blen * 4 + 15) & ~15u;
-                        const u32 by_la = (lalen * 4 + 15) & ~15u, by_lb = (lblen * 4 + 15) & ~15u;
-                        const u32 by_pa = (alen * 8 + 15) & ~15u, by_pb = (blen * 8 + 15) & ~15u;
-                        const bool want_pfx = FAST != GRB_OP_COUNT;
-                        mbar_arrive_expect_tx(&S.fullW[sw], by_a + by_b + by_la + by_lb + (want_pfx ? by_pa + by_pb : 0u));
-                        tma_load_1d(S.la[sw], sd->lut_a + la0, by_la, &S.fullW[sw]);
-                        tma_load_1d(S.lb[sw], sd->lut_b + lb0, by_lb, &S.fullW[sw]);
-                        tma_load_1d(S.ka[sw], sd->starts + a0, by_a, &S.fullW[sw]);
-                        tma_load_1d(S.kb[sw], sd->ends_sorted + b0, by_b, &S.fullW[sw]);
-                        if (want_pfx) {
-                            tma_load_1d(S.pa[sw], sd->pfx_a + a0, by_pa, &S.fullW[sw]);
-                            tma_load_1d(S.pb[sw], sd->pfx_b + b0, by_pb, &S.fullW[sw]);
-                        }
-                    } else {
-                        mbar_arrive(&S.fullW[sw]);
-                    }
-                }
-                __syncwarp();
-            }
-            // ---- A: lefts of tile `it`
-            if (it < nmine) {
-                const u32 j = it, sl = j % PIPE_LSTAGES;
-                const u32 t = blockIdx.x + j * gridDim.x;
-                mbar_wait(&S.emptyL[sl], ((j / PIPE_LSTAGES) & 1) ^ 1);
-                const int sq = find_seq_by_tile(tile_begin, nseq, t);
-                const SeqDev *__restrict__ sd = &seqs[sq];
-                const u64 g_first = ((sd->left_begin >> TILE_SHIFT) + (t - sd->tile_begin)) << TILE_SHIFT;
-                const bool whole = vec_in && g_first >= sd->left_begin && g_first + TILE <= sd->left_end;
-                if (whole && use_tma) {
-                    if (lane == 0) {
-                        mbar_arrive_expect_tx(&S.fullL[sl], 2 * TILE * 4);
-                        tma_load_1d(S.ls[sl], ls + g_first, TILE * 4, &S.fullL[sl]);
-                        tma_load_1d(S.le[sl], le + g_first, TILE * 4, &S.fullL[sl]);
-                    }
-                } else {
-                    // ragged tile (seqname boundary, end of the arrays, unaligned pointers): plain copies
-                    for (u32 i = lane; i < TILE; i += 32) {
-                        const u64 g = g_first + i;
-                        const bool ok = g >= sd->left_begin && g < sd->left_end;
-                        S.ls[sl][i] = ok ? ls[g] : 0u;
-                        S.le[sl][i] = ok ? le[g] : 0u;
-                    }
-                    __syncwarp();
-                    if (lane == 0) mbar_arrive(&S.fullL[sl]);
-                }
-                __syncwarp();
-            }
-            // ---- B: statistics of tile it-2 and its bin-table entries
-            if (it >= 2 && it - 2 < nmine) {
-                const u32 j = it - 2, sl = j % PIPE_LSTAGES;
-                const u32 t = blockIdx.x + j * gridDim.x;
-                const int sq = find_seq_by_tile(tile_begin, nseq, t);
-                const SeqDev *__restrict__ sd = &seqs[sq];
-                const u64 g_first = ((sd->left_begin >> TILE_SHIFT) + (t - sd->tile_begin)) << TILE_SHIFT;
-                const u64 lo_g = sd->left_begin > g_first ? sd->left_begin : g_first;
-                const u64 hi_g = sd->left_end < g_first + TILE ? sd->left_end : g_first + TILE;
-                const u32 vlo = (u32)(lo_g - g_first), vhi = (u32)(hi_g - g_first);
-                mbar_wait(&S.fullL[sl], (j / PIPE_LSTAGES) & 1);
-                u32 mn_s = 0xffffffffu, mx_s = 0, mn_e = 0xffffffffu, mx_e = 0;
-                const uint4 *vs = reinterpret_cast<const uint4 *>(S.ls[sl]);
-                const uint4 *ve = reinterpret_cast<const uint4 *>(S.le[sl]);
-                if (vlo == 0 && vhi == TILE) {
-#pragma unroll
-                    for (int r = 0; r < TILE / 128; r++) {
-                        const uint4 x = vs[r * 32 + lane], y = ve[r * 32 + lane];
-                        mn_s = min(mn_s, min(min(x.x, x.y), min(x.z, x.w)));
-                        mx_s = max(mx_s, max(max(x.x, x.y), max(x.z, x.w)));
-                        mn_e = min(mn_e, min(min(y.x, y.y), min(y.z, y.w)));
-                        mx_e = max(mx_e, max(max(y.x, y.y), max(y.z, y.w)));
-                    }
-                } else {
-                    for (u32 i = vlo + lane; i < vhi; i += 32) {
-                        const u32 x = S.ls[sl][i], y = S.le[sl][i];
-                        mn_s = min(mn_s, x);
-                        mx_s = max(mx_s, x);
-                        mn_e = min(mn_e, y);
-                        mx_e = max(mx_e, y);
-                    }
-                }
-                mn_e = warp_min(mn_e);
-                mx_e = warp_max(mx_e);
-                mn_s = warp_min(mn_s);
-                mx_s = warp_max(mx_s);
-                const u32 q = lane & 3;
-                const u32 v = q == 0 ? mn_e : q == 1 ? mx_e : q == 2 ? mn_s : mx_s;
-                const u32 x = v + (q >> 1);
-                cur.bin = min(x >> sd->lut_shift, sd->lut_bmax);
-                cur.bound = ((q < 2) ? sd->lut_a : sd->lut_b)[cur.bin + (q & 1)];
-                cur.g_first = g_first;
-                cur.vlo = vlo;
-                cur.vhi = vhi;
-                cur.seq = sq;
-            }
-        }
-        return;
-    }
-
-    // ================= consumers =================
-    const u32 cw = warp - 1;
-    const u32 i0 = (cw * 32 + lane) * TILE_LPT;  // first slot of this thread inside a tile
-    const bool ovec = ((((uintptr_t)out) & 15) | (((uintptr_t)out_valid) & 3)) == 0;
-    for (u32 j = 0; j < nmine; j++) {
-        const u32 sw = j % PIPE_WSTAGES, sl = j % PIPE_LSTAGES;
-        mbar_wait(&S.fullW[sw], (j / PIPE_WSTAGES) & 1);
-        const PipeDesc &d = S.desc[sw];
-        const u32 vlo = d.vlo, vhi = d.vhi;
-        const int sh = d.sh;
-        const u32 bmax = d.bmax;
-        const uint4 va = *reinterpret_cast<const uint4 *>(&S.ls[sl][i0]);
-        const uint4 vb = *reinterpret_cast<const uint4 *>(&S.le[sl][i0]);
-        const u32 a[TILE_LPT] = {va.x, va.y, va.z, va.w};
-        const u32 b[TILE_LPT] = {vb.x, vb.y, vb.z, vb.w};
-        bool okv[TILE_LPT];
-#pragma unroll
-        for (int k = 0; k < TILE_LPT; k++) okv[k] = i0 + k >= vlo && i0 + k < vhi;
-        double r[TILE_LPT];
-        u8 v[TILE_LPT];
-        if (d.staged) {
-            const u32 a0 = d.a0, b0 = d.b0, la0 = d.la0, lb0 = d.lb0;
-            const u32 *__restrict__ sKA = S.ka[sw];
-            const u32 *__restrict__ sKB = S.kb[sw];
-            const u32 *__restrict__ sLA = S.la[sw];
-            const u32 *__restrict__ sLB = S.lb[sw];
-#pragma unroll
-            for (int k = 0; k < TILE_LPT; k++) {
-                r[k] = 0.0;
-                v[k] = 0;
-                if (!okv[k]) continue;
-                const u32 xa = b[k], xb = a[k] + 1;
-                const u32 ba = min(xa >> sh, bmax) - la0;
-                const u32 bb = min(xb >> sh, bmax) - lb0;
-                const u32 ua = scan_lower_bound(sKA, sLA[ba] - a0, xa);   // relative to a0
-                const u32 lbk = scan_lower_bound(sKB, sLB[bb] - b0, xb);  // relative to b0
-                const u32 c = (a0 + ua) - (b0 + lbk);
-                if (FAST == GRB_OP_COUNT) {
-                    r[k] = (double)c;
-                    v[k] = 1;
-                    continue;
-                }
-                double sum;
-                const u64 pa = S.pa[sw][ua], pb = S.pb[sw][lbk];
-                if (c < d.fast_cmax) {
-                    sum = (double)(i64)(pa - pb) * d.scale;
-                } else {
-                    const SeqDev *__restrict__ sd = &seqs[d.seq];
-                    const i128 ba128 = sd->base_a[(a0 + ua) >> GRB_BASE_SHIFT], bb128 = sd->base_b[(b0 + lbk) >> GRB_BASE_SHIFT];
-                    const i128 PA = ba128 + (i128)(i64)(pa - (u64)(u128)ba128);
-                    const i128 PB = bb128 + (i128)(i64)(pb - (u64)(u128)bb128);
-                    sum = fx_to_double(PA - PB, sd->e0);
-                }
-                if (FAST == GRB_OP_SUM) {
-                    r[k] = sum;
-                    v[k] = 1;
-                } else if (FAST == GRB_OP_SUM_NOT_EMPTY) {
-                    r[k] = sum;
-                    v[k] = c != 0;
-                } else {
-                    v[k] = c != 0;
-                    r[k] = c ? sum / (double)c : 0.0;
-                }
-            }
-        } else {
-            const SeqDev *__restrict__ sd = &seqs[d.seq];
-#pragma unroll
-            for (int k = 0; k < TILE_LPT; k++) {
-                r[k] = 0.0;
-                v[k] = 0;
-                if (!okv[k]) continue;
-                const u32 xa = b[k], xb = a[k] + 1;
-                const u32 ba = min(xa >> sh, bmax), bb = min(xb >> sh, bmax);
-                const u32 ub = scan_lower_bound(sd->starts, sd->lut_a[ba], xa);
-                const u32 lbk = scan_lower_bound(sd->ends_sorted, sd->lut_b[bb], xb);
-                const u32 c = ub - lbk;
-                if (FAST == GRB_OP_COUNT) {
-                    r[k] = (double)c;
-                    v[k] = 1;
-                    continue;
-                }
-                const double sum = compact_group_sum(sd->pfx_a, sd->pfx_b, sd->base_a, sd->base_b, ub, lbk, d.fast_cmax, d.scale, sd->e0);
-                if (FAST == GRB_OP_SUM) {
-                    r[k] = sum;
-                    v[k] = 1;
-                } else if (FAST == GRB_OP_SUM_NOT_EMPTY) {
-                    r[k] = sum;
-                    v[k] = c != 0;
-                } else {
-                    v[k] = c != 0;
-                    r[k] = c ? sum / (double)c : 0.0;
-                }
-            }
-        }
-        const u64 g0 = d.g_first + i0;
-        if (ovec && okv[0] && okv[TILE_LPT - 1]) {
-            double2 *po = reinterpret_cast<double2 *>(out + g0);
-            po[0] = make_double2(r[0], r[1]);
-            po[1] = make_double2(r[2], r[3]);
-            *reinterpret_cast<uchar4 *>(out_valid + g0) = make_uchar4(v[0], v[1], v[2], v[3]);
-        } else {
-#pragma unroll
-            for (int k = 0; k < TILE_LPT; k++) {
-                if (okv[k]) {
-                    out[g0 + k] = r[k];
-                    out_valid[g0 + k] = v[k];
-                }
-            }
-        }
-        // done with this stage: one arrival per consumer warp
-        __syncwarp();
-        if (lane == 0) {
-            mbar_arrive(&S.emptyW[sw]);
-            mbar_arrive(&S.emptyL[sl]);
-        }
-    }
-}
+#include "map_pipe.cuh"
 
 // ---- the sweep kernels ----------------------------------------------------------------
 
@@ -1191,8 +854,8 @@ int launch_pipe(grb_ctx *ctx, const Batch &b, const u32 *ls, const u32 *le, cons
     }
     u32 grid = (u32)ctx->sm_count;
     if (grid > b.ntiles) grid = b.ntiles;
-    k_map_pipe<FAST><<<grid, PIPE_THREADS, sizeof(PipeSmem), ctx->stream>>>(b.seqs, b.tile_begin, b.nseq, b.ntiles, ls, le, b.total, o.out,
-                                                                          o.out_valid, ctx->tile_mode);
+    const int flags = (ctx->tile_mode ? 1 : 0) | (ctx->pipe_mode == 2 ? 2 : 0);
+    k_map_pipe<FAST><<<grid, PIPE_THREADS, sizeof(PipeSmem), ctx->stream>>>(b.seqs, b.nseq, b.ntiles, ls, le, o.out, o.out_valid, flags);
     GRB_LAUNCHED(ctx);
     return GRB_OK;
 }
@@ -1200,7 +863,7 @@ int launch_pipe(grb_ctx *ctx, const Batch &b, const u32 *ls, const u32 *le, cons
 // MAP launch: the single-reduction fast kernels when the batch is uniform, else the general one.
 template <int MODE>
 int launch_map(grb_ctx *ctx, const Batch &b, const u32 *ls, const u32 *le, const TileOut &o) {
-    if (MODE == M_MAP && b.uniform && o.k == 1 && ctx->pipe_mode) {
+    if (MODE == M_MAP && b.uniform && o.k == 1 && ctx->pipe_mode && b.nseq <= PIPE_MAXSEQ) {
         switch (o.ops[0]) {
             case GRB_OP_MEAN:
                 return launch_pipe<GRB_OP_MEAN>(ctx, b, ls, le, o);
