@@ -427,7 +427,9 @@ int grb_index_build(grb_ctx *ctx, const uint32_t *starts, const uint32_t *ends, 
             if (n) cudaMemcpyAsync(&maxend, ke + (n - 1), 4, cudaMemcpyDeviceToHost, ctx->stream);  // low half of the last u64 key
             cudaStreamSynchronize(ctx->stream);
             int shift = 0;
-            while (shift < 31 && ((u64)maxend >> shift) > (u64)n / 2 + 1) shift++;
+            const char *ld = getenv("GRB_LUT_DIV");  // tuning knob: average rights per bin (default 2)
+            const u64 lut_div = ld && atoi(ld) > 0 ? (u64)atoi(ld) : 2;
+            while (shift < 31 && ((u64)maxend >> shift) > (u64)n / lut_div + 1) shift++;
             ix->lut_shift = shift;
             ix->lut_bmax = (maxend >> shift) + 1;
             size_t entries = (size_t)ix->lut_bmax + 1 + PAD;

@@ -5,27 +5,28 @@
 // so that no warp ever waits on a dependent chain of global loads.  One CTA per SM, tiles
 // blockIdx.x, blockIdx.x + gridDim.x, ...; per tile (1024 consecutive lefts of one seqname):
 //
-//   warp 0  "loader"    A: TMA the lefts (ls, le) of tile j into the lefts ring           -> fullL
-//                       C: (3 tiles later) read the tile's bins / table entries, TMA the slices of
-//                          starts, ends_sorted, both bin tables and both prefix arrays that the
-//                          tile can touch into the window ring                             -> fullW
-//   warp 1  "surveyor"  B: min / max of the tile's lefts out of shared memory -> coordinate bins
-//                          -> four bin-table entries by plain loads, published one iteration
-//                          later so the loads have a whole iteration to land                -> statsL
-//   warps 2..9 "consumers": wait fullW, resolve ub / lb of 4 lefts per thread out of shared memory,
-//                          exact sums from the staged prefixes, write results, release       -> emptyW, emptyL
+//   warp 0  lefts loader   A: TMA the lefts (ls, le) of tile j into the lefts ring, as far ahead as
+//                             the ring allows                                                 -> fullL
+//   warp 1  surveyor       B: min / max of the tile's lefts out of shared memory -> coordinate bins
+//                             -> four bin-table entries by plain loads, published one iteration
+//                             later so the loads have a whole iteration to land               -> statsL
+//   warp 2  window loader  C: TMA the slices of starts, ends_sorted, both bin tables and both
+//                             prefix arrays that the tile can touch into the window ring (six
+//                             bulk copies issued by six lanes at once, one mbarrier)          -> fullW
+//   warps 3.. consumers:      wait fullW, resolve ub / lb of 2 lefts per thread out of shared
+//                             memory, exact sums from the staged prefixes, write results,
+//                             release the slots                                               -> emptyW, emptyL
 //
 // Tiles whose windows do not fit the ring slots (sparse lefts over dense rights) are resolved by
 // per-left global searches inside the consumers; results are identical.
 
 constexpr int PIPE_NC = 16;  // consumer warps
 constexpr int PIPE_LPT = TILE / (PIPE_NC * 32);  // consecutive lefts per consumer thread
-constexpr int PIPE_THREADS = (PIPE_NC + 2) * 32;
+constexpr int PIPE_THREADS = (PIPE_NC + 3) * 32;
 constexpr int PIPE_LSTAGES = 8;
-constexpr int PIPE_WSTAGES = 3;
-constexpr int PIPE_LEAD = 3;    // phase C runs this many tiles behind phase A
-constexpr u32 PIPE_WIN = 1536;  // keys (and prefixes) per staged window
-constexpr u32 PIPE_LUT = 768;   // bin-table entries per staged slice
+constexpr int PIPE_WSTAGES = 4;
+constexpr u32 PIPE_WIN = 1280;  // keys (and prefixes) per staged window
+constexpr u32 PIPE_LUT = 640;   // bin-table entries per staged slice
 constexpr int PIPE_MAXSEQ = 32; // seqnames per launch (their descriptors live in shared memory)
 
 struct PipeSeq {
@@ -117,90 +118,94 @@ __global__ void __launch_bounds__(PIPE_THREADS, 1) k_map_pipe(const SeqDev *__re
     const u32 nmine = blockIdx.x < ntiles ? (ntiles - blockIdx.x + gridDim.x - 1) / gridDim.x : 0;
 
     if (warp == 0) {
-        // ================= loader =================
+        // ================= lefts loader (A) =================
         const bool vec_in = ((((uintptr_t)ls) | ((uintptr_t)le)) & 15) == 0;
-        int sq = 0;  // seqname of the tile phase A is at; tiles only move forward
-        for (u32 it = 0; it < nmine + PIPE_LEAD; it++) {
-            // ---- C: windows of tile it - PIPE_LEAD
-            if (it >= PIPE_LEAD) {
-                const u32 j = it - PIPE_LEAD, sw = j % PIPE_WSTAGES, sl = j % PIPE_LSTAGES;
-                mbar_wait(&S.statsL[sl], (j / PIPE_LSTAGES) & 1);
-                mbar_wait(&S.emptyW[sw], ((j / PIPE_WSTAGES) & 1) ^ 1);
-                if (lane == 0) {
-                    const PipeTile &ti = S.tile[sl];
-                    const PipeSeq &q = S.seq[ti.seq];
-                    const u32 a0 = ti.bound[0] & ~3u, b0 = ti.bound[2] & ~3u, la0 = ti.bin[0] & ~3u, lb0 = ti.bin[2] & ~3u;
-                    // + 4: the forward scan may read up to 3 keys past the last one it can return
-                    const u32 alen = ti.bound[1] - a0 + 4, blen = ti.bound[3] - b0 + 4;
-                    const u32 lalen = ti.bin[1] + 1 - la0, lblen = ti.bin[3] + 1 - lb0;
-                    const bool staged = use_tma && alen <= PIPE_WIN && blen <= PIPE_WIN && lalen <= PIPE_LUT && lblen <= PIPE_LUT;
-                    PipeDesc &d = S.desc[sw];
-                    d.g_first = ti.g_first;
-                    d.vlo = ti.vlo;
-                    d.vhi = ti.vhi;
-                    d.seq = ti.seq;
-                    d.a0 = a0;
-                    d.b0 = b0;
-                    d.la0 = la0;
-                    d.lb0 = lb0;
-                    d.staged = staged ? 1u : 0u;
-                    if (staged) {
-                        const u32 by_a = (alen * 4 + 15) & ~15u, by_b = (blen * 4 + 15) & ~15u;
-                        const u32 by_la = (lalen * 4 + 15) & ~15u, by_lb = (lblen * 4 + 15) & ~15u;
-                        const u32 by_pa = (alen * 8 + 15) & ~15u, by_pb = (blen * 8 + 15) & ~15u;
-                        const bool want_pfx = FAST != GRB_OP_COUNT;
-                        mbar_arrive_expect_tx(&S.fullW[sw], by_a + by_b + by_la + by_lb + (want_pfx ? by_pa + by_pb : 0u));
-                        tma_load_1d(S.la[sw], q.lut_a + la0, by_la, &S.fullW[sw]);
-                        tma_load_1d(S.lb[sw], q.lut_b + lb0, by_lb, &S.fullW[sw]);
-                        tma_load_1d(S.ka[sw], q.starts + a0, by_a, &S.fullW[sw]);
-                        tma_load_1d(S.kb[sw], q.ends_sorted + b0, by_b, &S.fullW[sw]);
-                        if (want_pfx) {
-                            tma_load_1d(S.pa[sw], q.pfx_a + a0, by_pa, &S.fullW[sw]);
-                            tma_load_1d(S.pb[sw], q.pfx_b + b0, by_pb, &S.fullW[sw]);
-                        }
-                    } else {
-                        mbar_arrive(&S.fullW[sw]);
-                    }
+        int sq = 0;  // tiles only move forward, so does the seqname
+        for (u32 j = 0; j < nmine; j++) {
+            const u32 sl = j % PIPE_LSTAGES;
+            const u32 t = blockIdx.x + j * gridDim.x;
+            while (sq + 1 < nseq && S.seq[sq + 1].tile_begin <= t) sq++;
+            const PipeSeq &q = S.seq[sq];
+            const u64 g_first = ((q.left_begin >> TILE_SHIFT) + (t - q.tile_begin)) << TILE_SHIFT;
+            const u64 lo_g = q.left_begin > g_first ? q.left_begin : g_first;
+            const u64 hi_g = q.left_end < g_first + TILE ? q.left_end : g_first + TILE;
+            const bool whole = vec_in && lo_g == g_first && hi_g == g_first + TILE;
+            mbar_wait(&S.emptyL[sl], ((j / PIPE_LSTAGES) & 1) ^ 1);
+            if (lane == 0) {
+                PipeTile &ti = S.tile[sl];
+                ti.g_first = g_first;
+                ti.vlo = (u32)(lo_g - g_first);
+                ti.vhi = (u32)(hi_g - g_first);
+                ti.seq = sq;
+            }
+            if (whole && use_tma) {
+                if (lane == 0) mbar_arrive_expect_tx(&S.fullL[sl], 2 * TILE * 4);
+                __syncwarp();
+                if (lane < 2) tma_load_1d(lane ? S.le[sl] : S.ls[sl], (lane ? le : ls) + g_first, TILE * 4, &S.fullL[sl]);
+            } else {
+                // ragged tile (seqname boundary, end of the arrays, unaligned pointers): plain copies
+                for (u32 i = lane; i < TILE; i += 32) {
+                    const u64 g = g_first + i;
+                    const bool ok = g >= lo_g && g < hi_g;
+                    S.ls[sl][i] = ok ? ls[g] : 0u;
+                    S.le[sl][i] = ok ? le[g] : 0u;
                 }
                 __syncwarp();
+                if (lane == 0) mbar_arrive(&S.fullL[sl]);
             }
-            // ---- A: lefts of tile `it`
-            if (it < nmine) {
-                const u32 j = it, sl = j % PIPE_LSTAGES;
-                const u32 t = blockIdx.x + j * gridDim.x;
-                while (sq + 1 < nseq && S.seq[sq + 1].tile_begin <= t) sq++;
-                const PipeSeq &q = S.seq[sq];
-                const u64 g_first = ((q.left_begin >> TILE_SHIFT) + (t - q.tile_begin)) << TILE_SHIFT;
-                const u64 lo_g = q.left_begin > g_first ? q.left_begin : g_first;
-                const u64 hi_g = q.left_end < g_first + TILE ? q.left_end : g_first + TILE;
-                const bool whole = vec_in && lo_g == g_first && hi_g == g_first + TILE;
-                mbar_wait(&S.emptyL[sl], ((j / PIPE_LSTAGES) & 1) ^ 1);
-                if (lane == 0) {
-                    PipeTile &ti = S.tile[sl];
-                    ti.g_first = g_first;
-                    ti.vlo = (u32)(lo_g - g_first);
-                    ti.vhi = (u32)(hi_g - g_first);
-                    ti.seq = sq;
-                }
-                if (whole && use_tma) {
-                    if (lane == 0) {
-                        mbar_arrive_expect_tx(&S.fullL[sl], 2 * TILE * 4);
-                        tma_load_1d(S.ls[sl], ls + g_first, TILE * 4, &S.fullL[sl]);
-                        tma_load_1d(S.le[sl], le + g_first, TILE * 4, &S.fullL[sl]);
-                    }
-                } else {
-                    // ragged tile (seqname boundary, end of the arrays, unaligned pointers): plain copies
-                    for (u32 i = lane; i < TILE; i += 32) {
-                        const u64 g = g_first + i;
-                        const bool ok = g >= lo_g && g < hi_g;
-                        S.ls[sl][i] = ok ? ls[g] : 0u;
-                        S.le[sl][i] = ok ? le[g] : 0u;
-                    }
-                    __syncwarp();
-                    if (lane == 0) mbar_arrive(&S.fullL[sl]);
-                }
-                __syncwarp();
+            __syncwarp();
+        }
+        return;
+    }
+
+    if (warp == 2) {
+        // ================= window loader (C) =================
+        for (u32 j = 0; j < nmine; j++) {
+            const u32 sw = j % PIPE_WSTAGES, sl = j % PIPE_LSTAGES;
+            mbar_wait(&S.statsL[sl], (j / PIPE_LSTAGES) & 1);
+            mbar_wait(&S.emptyW[sw], ((j / PIPE_WSTAGES) & 1) ^ 1);
+            const PipeTile &ti = S.tile[sl];
+            const PipeSeq &q = S.seq[ti.seq];
+            const u32 a0 = ti.bound[0] & ~3u, b0 = ti.bound[2] & ~3u, la0 = ti.bin[0] & ~3u, lb0 = ti.bin[2] & ~3u;
+            // + 4: the forward scan may read up to 3 keys past the last one it can return
+            const u32 alen = ti.bound[1] - a0 + 4, blen = ti.bound[3] - b0 + 4;
+            const u32 lalen = ti.bin[1] + 1 - la0, lblen = ti.bin[3] + 1 - lb0;
+            const bool staged = use_tma && alen <= PIPE_WIN && blen <= PIPE_WIN && lalen <= PIPE_LUT && lblen <= PIPE_LUT;
+            const bool want_pfx = FAST != GRB_OP_COUNT;
+            // lane l issues copy l: 0 lut_a, 1 lut_b, 2 starts, 3 ends_sorted, 4 pfx_a, 5 pfx_b
+            const void *src = nullptr;
+            void *dst = nullptr;
+            u32 bytes = 0;
+            switch (lane) {
+                case 0: src = q.lut_a + la0; dst = S.la[sw]; bytes = lalen * 4; break;
+                case 1: src = q.lut_b + lb0; dst = S.lb[sw]; bytes = lblen * 4; break;
+                case 2: src = q.starts + a0; dst = S.ka[sw]; bytes = alen * 4; break;
+                case 3: src = q.ends_sorted + b0; dst = S.kb[sw]; bytes = blen * 4; break;
+                case 4: src = q.pfx_a + a0; dst = S.pa[sw]; bytes = want_pfx ? alen * 8 : 0; break;
+                case 5: src = q.pfx_b + b0; dst = S.pb[sw]; bytes = want_pfx ? blen * 8 : 0; break;
+                default: break;
             }
+            bytes = (bytes + 15) & ~15u;
+            const u32 total_bytes = warp_sum(bytes);
+            if (lane == 0) {
+                PipeDesc &d = S.desc[sw];
+                d.g_first = ti.g_first;
+                d.vlo = ti.vlo;
+                d.vhi = ti.vhi;
+                d.seq = ti.seq;
+                d.a0 = a0;
+                d.b0 = b0;
+                d.la0 = la0;
+                d.lb0 = lb0;
+                d.staged = staged ? 1u : 0u;
+                if (staged)
+                    mbar_arrive_expect_tx(&S.fullW[sw], total_bytes);
+                else
+                    mbar_arrive(&S.fullW[sw]);
+            }
+            __syncwarp();
+            if (staged && bytes) tma_load_1d(dst, src, bytes, &S.fullW[sw]);
+            __syncwarp();
         }
         return;
     }
@@ -264,7 +269,7 @@ __global__ void __launch_bounds__(PIPE_THREADS, 1) k_map_pipe(const SeqDev *__re
     }
 
     // ================= consumers =================
-    const u32 cw = warp - 2;
+    const u32 cw = warp - 3;
     const u32 i0 = (cw * 32 + lane) * PIPE_LPT;  // first slot of this thread inside a tile
     const bool ovec = ((((uintptr_t)out) & 15) | (((uintptr_t)out_valid) & 3)) == 0;
     const bool skip = flags & 2;
