@@ -167,8 +167,8 @@ __global__ void __launch_bounds__(PIPE_THREADS, 1) k_map_pipe(const SeqDev *__re
             const PipeTile &ti = S.tile[sl];
             const PipeSeq &q = S.seq[ti.seq];
             const u32 a0 = ti.bound[0] & ~3u, b0 = ti.bound[2] & ~3u, la0 = ti.bin[0] & ~3u, lb0 = ti.bin[2] & ~3u;
-            // + 4: the forward scan may read up to 3 keys past the last one it can return
-            const u32 alen = ti.bound[1] - a0 + 4, blen = ti.bound[3] - b0 + 4;
+            // + 8: a search reads the two aligned quads around its answer, i.e. up to 7 keys past it
+            const u32 alen = ti.bound[1] - a0 + 8, blen = ti.bound[3] - b0 + 8;
             const u32 lalen = ti.bin[1] + 1 - la0, lblen = ti.bin[3] + 1 - lb0;
             const bool staged = use_tma && alen <= PIPE_WIN && blen <= PIPE_WIN && lalen <= PIPE_LUT && lblen <= PIPE_LUT;
             const bool want_pfx = FAST != GRB_OP_COUNT;
@@ -316,21 +316,26 @@ __global__ void __launch_bounds__(PIPE_THREADS, 1) k_map_pipe(const SeqDev *__re
                     pA[k] = okv[k] ? S.la[sw][ba - la0] - a0 : 0u;
                     pB[k] = okv[k] ? S.lb[sw][bb - lb0] - b0 : 0u;
                 }
-                // one unconditional round of four compares per search: bins hold ~2-3 keys, so this almost always ends it
+                // one unconditional round per search: the 8 keys of the two aligned quads around the bin's first
+                // position, two 128-bit loads.  Keys before that position are < x by construction, so the answer
+                // is (quad base) + #(keys < x) unless all 8 are smaller (a crowded bin: finish with the scan).
 #pragma unroll
                 for (int k = 0; k < PIPE_LPT; k++) {
                     const u32 xa = okv[k] ? b[k] : 0u, xb = okv[k] ? a[k] + 1 : 0u;
-                    cA[k] = (KA[pA[k]] < xa ? 1u : 0u) + (KA[pA[k] + 1] < xa ? 1u : 0u) + (KA[pA[k] + 2] < xa ? 1u : 0u) +
-                            (KA[pA[k] + 3] < xa ? 1u : 0u);
-                    cB[k] = (KB[pB[k]] < xb ? 1u : 0u) + (KB[pB[k] + 1] < xb ? 1u : 0u) + (KB[pB[k] + 2] < xb ? 1u : 0u) +
-                            (KB[pB[k] + 3] < xb ? 1u : 0u);
+                    const u32 qa = pA[k] & ~3u, qb = pB[k] & ~3u;
+                    const uint4 a0v = *reinterpret_cast<const uint4 *>(KA + qa), a1v = *reinterpret_cast<const uint4 *>(KA + qa + 4);
+                    const uint4 b0v = *reinterpret_cast<const uint4 *>(KB + qb), b1v = *reinterpret_cast<const uint4 *>(KB + qb + 4);
+                    cA[k] = (a0v.x < xa) + (a0v.y < xa) + (a0v.z < xa) + (a0v.w < xa) + (a1v.x < xa) + (a1v.y < xa) + (a1v.z < xa) +
+                            (a1v.w < xa);
+                    cB[k] = (b0v.x < xb) + (b0v.y < xb) + (b0v.z < xb) + (b0v.w < xb) + (b1v.x < xb) + (b1v.y < xb) + (b1v.z < xb) +
+                            (b1v.w < xb);
+                    pA[k] = okv[k] ? qa + cA[k] : 0u;
+                    pB[k] = okv[k] ? qb + cB[k] : 0u;
                 }
 #pragma unroll
                 for (int k = 0; k < PIPE_LPT; k++) {
-                    pA[k] += cA[k];
-                    pB[k] += cB[k];
-                    if (cA[k] == 4) pA[k] = scan_lower_bound(KA, pA[k], b[k]);      // rare: a crowded bin
-                    if (cB[k] == 4) pB[k] = scan_lower_bound(KB, pB[k], a[k] + 1);
+                    if (cA[k] == 8) pA[k] = scan_lower_bound(KA, pA[k], b[k]);      // rare: a crowded bin
+                    if (cB[k] == 8) pB[k] = scan_lower_bound(KB, pB[k], a[k] + 1);
                     pa[k] = FAST != GRB_OP_COUNT ? S.pa[sw][pA[k]] : 0ull;
                     pb[k] = FAST != GRB_OP_COUNT ? S.pb[sw][pB[k]] : 0ull;
                     ub[k] = a0 + pA[k];

@@ -71,12 +71,12 @@ __device__ __forceinline__ void mbar_wait(u64 *bar, u32 parity) {
         "{\n"
         ".reg .pred P1;\n"
         "LAB_WAIT:\n"
-        "mbarrier.try_wait.parity.shared::cta.b64 P1, [%0], %1;\n"
+        "mbarrier.try_wait.parity.shared::cta.b64 P1, [%0], %1, %2;\n"
         "@P1 bra DONE;\n"
         "bra LAB_WAIT;\n"
         "DONE:\n"
         "}\n" ::"r"(smem_addr(bar)),
-        "r"(parity)
+        "r"(parity), "r"(0x989680u)  // suspend-time hint: sleep in hardware instead of spinning through issue slots
         : "memory");
 }
 
