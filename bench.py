@@ -377,7 +377,7 @@ def main():
     alg_rank0 = nl_mine * 8 + n_right_mine * 16 + nl_mine * k * 8 + nl_mine * k / 8
     achieved = alg_rank0 / (kernel_ms * 1e-3) / 1e9
     line["roofline"] = {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
-                        "traffic": None, "peak_source": peak_src, "kernel": "k_tile<M_MAP>", "kernel_ms": kernel_ms,
+                        "traffic": None, "peak_source": peak_src, "kernel": "k_map_pipe<MEAN>" if ops == ["mean"] else "k_tile/k_sweep", "kernel_ms": kernel_ms,
                         "algorithmic_bytes_per_launch": alg_rank0, "algorithmic_bytes_whole_job": alg_bytes}
     prof = os.path.join(ROOT, "profiles", "traffic.json")
     if os.path.exists(prof):

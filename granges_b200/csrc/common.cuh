@@ -25,6 +25,10 @@ struct grb_ctx {
     cudaStream_t stream;
     cudaMemPool_t pool;
     u64 launches;
+    // device copy of the last batch's per-seqname descriptors (reused when the next call has the same batch)
+    void *batch_dev;
+    void *batch_host;
+    size_t batch_bytes, batch_cap;
     void *zeros;    // 1 KB of zeros (tables) + 1 KB of 0xff (sentinel keys): what an absent seqname / empty index reads
     int pipe_mode;  // 1 = persistent warp-specialised pipeline for single-reduction maps (default), 0 = k_tile only (debug)
     int tile_mode;  // 1 = TMA-staged smem windows (default), 0 = global binary search only (debug)
@@ -114,6 +118,13 @@ struct OutBuf {
 };
 
 bool grb_is_device_ptr(const void *p);
+
+// Long-lived device arrays (indexes, pairs, windows) also come from the stream-ordered pool: plain
+// cudaMalloc / cudaFree cost milliseconds each once a process holds many GB, the pool costs microseconds.
+inline cudaError_t grb_dev_malloc(grb_ctx *ctx, void **p, size_t bytes) { return cudaMallocAsync(p, bytes ? bytes : 16, ctx->stream); }
+inline void grb_dev_free(grb_ctx *ctx, void *p) {
+    if (p) cudaFreeAsync(p, ctx->stream);
+}
 
 // ---- index ----------------------------------------------------------------
 

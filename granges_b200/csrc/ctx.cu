@@ -130,6 +130,8 @@ void grb_ctx_destroy(grb_ctx *ctx) {
     cudaStreamSynchronize(ctx->stream);
     cudaStreamDestroy(ctx->own_stream);
     cudaFree(ctx->zeros);
+    cudaFree(ctx->batch_dev);
+    free(ctx->batch_host);
     free(ctx);
 }
 

@@ -282,19 +282,19 @@ __global__ void __launch_bounds__(1024) k_scan_i128_single(const i128 *__restric
 inline unsigned blocks_for(size_t n, int tpb) { return (unsigned)((n + tpb - 1) / tpb); }
 
 int dev_alloc(grb_ctx *ctx, void **p, size_t bytes) {
-    GRB_CUDA(ctx, cudaMalloc(p, bytes ? bytes : 16));
+    GRB_CUDA(ctx, grb_dev_malloc(ctx, p, bytes));
     return GRB_OK;
 }
 
 void free_scores(grb_index *ix) {
-    cudaFree(ix->score_a);
-    cudaFree(ix->vbits_a);
-    cudaFree(ix->vcnt_a);
-    cudaFree(ix->vcnt_b);
-    cudaFree(ix->pfx_a);
-    cudaFree(ix->pfx_b);
-    cudaFree(ix->base_a);
-    cudaFree(ix->base_b);
+    grb_dev_free(ix->ctx, ix->score_a);
+    grb_dev_free(ix->ctx, ix->vbits_a);
+    grb_dev_free(ix->ctx, ix->vcnt_a);
+    grb_dev_free(ix->ctx, ix->vcnt_b);
+    grb_dev_free(ix->ctx, ix->pfx_a);
+    grb_dev_free(ix->ctx, ix->pfx_b);
+    grb_dev_free(ix->ctx, ix->base_a);
+    grb_dev_free(ix->ctx, ix->base_b);
     ix->score_a = nullptr;
     ix->vbits_a = ix->vcnt_a = ix->vcnt_b = nullptr;
     ix->pfx_a = ix->pfx_b = nullptr;
@@ -463,14 +463,14 @@ void grb_index_destroy(grb_index *ix) {
     if (!ix) return;
     cudaSetDevice(ix->ctx->device);
     free_scores(ix);
-    cudaFree(ix->starts);
-    cudaFree(ix->ends);
-    cudaFree(ix->didx);
-    cudaFree(ix->bme);
-    cudaFree(ix->ends_sorted);
-    cudaFree(ix->perm_e);
-    cudaFree(ix->lut_a);
-    cudaFree(ix->lut_b);
+    grb_dev_free(ix->ctx, ix->starts);
+    grb_dev_free(ix->ctx, ix->ends);
+    grb_dev_free(ix->ctx, ix->didx);
+    grb_dev_free(ix->ctx, ix->bme);
+    grb_dev_free(ix->ctx, ix->ends_sorted);
+    grb_dev_free(ix->ctx, ix->perm_e);
+    grb_dev_free(ix->ctx, ix->lut_a);
+    grb_dev_free(ix->ctx, ix->lut_b);
     free(ix);
 }
 
@@ -526,7 +526,7 @@ int grb_index_set_scores(grb_index *ix, const double *by_data_idx, const uint8_t
         GRB_TRY(grb_scan_u32_to_u32(ctx, vflag_a.as<u32>(), ix->vcnt_a, n, true));
         GRB_TRY(grb_scan_u32_to_u32(ctx, vflag_b.as<u32>(), ix->vcnt_b, n, true));
     } else if (ix->vbits_a) {
-        cudaFree(ix->vbits_a);
+        grb_dev_free(ix->ctx, ix->vbits_a);
         ix->vbits_a = nullptr;
     }
     // choose how SUM / MEAN are answered

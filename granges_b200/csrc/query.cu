@@ -750,7 +750,6 @@ __global__ void k_pairs_widths(const u32 *__restrict__ pos, const u64 *__restric
 // ---- host orchestration -------------------------------------------------------------------
 
 struct Batch {
-    TempBuf seqs_dev, tiles_dev;
     const SeqDev *seqs = nullptr;
     const u32 *tile_begin = nullptr;
     u32 ntiles = 0;
@@ -827,12 +826,33 @@ int make_batch(grb_ctx *ctx, const grb_index *const *idx, const u64 *left_offset
     b->ntiles = (u32)tiles;
     b->total = left_offsets[nseq];
     b->nseq = nseq;
-    GRB_TRY(b->seqs_dev.alloc(ctx, sizeof(SeqDev) * nseq));
-    GRB_TRY(b->tiles_dev.alloc(ctx, sizeof(u32) * (nseq + 1)));
-    GRB_CUDA(ctx, cudaMemcpyAsync(b->seqs_dev.p, h.data(), sizeof(SeqDev) * nseq, cudaMemcpyHostToDevice, ctx->stream));
-    GRB_CUDA(ctx, cudaMemcpyAsync(b->tiles_dev.p, tb.data(), sizeof(u32) * (nseq + 1), cudaMemcpyHostToDevice, ctx->stream));
-    b->seqs = b->seqs_dev.as<SeqDev>();
-    b->tile_begin = b->tiles_dev.as<u32>();
+    // descriptors: [SeqDev x nseq][u32 x (nseq + 1)] in one device buffer owned by the context; a call with the
+    // same batch as the previous one (the usual case when a query is repeated) reuses it without any copy
+    const size_t seq_bytes = sizeof(SeqDev) * nseq, bytes = seq_bytes + sizeof(u32) * (nseq + 1);
+    std::vector<unsigned char> blob(bytes);
+    memcpy(blob.data(), h.data(), seq_bytes);
+    memcpy(blob.data() + seq_bytes, tb.data(), sizeof(u32) * (nseq + 1));
+    if (!(ctx->batch_dev && ctx->batch_bytes == bytes && memcmp(ctx->batch_host, blob.data(), bytes) == 0)) {
+        if (bytes > ctx->batch_cap) {
+            GRB_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+            cudaFree(ctx->batch_dev);
+            free(ctx->batch_host);
+            ctx->batch_dev = nullptr;
+            ctx->batch_cap = 0;
+            ctx->batch_bytes = 0;
+            ctx->batch_host = malloc(bytes * 2);
+            if (!ctx->batch_host) return grb_fail(ctx, GRB_ERR_OOM, "batch: host allocation failed");
+            GRB_CUDA(ctx, cudaMalloc(&ctx->batch_dev, bytes * 2));
+            ctx->batch_cap = bytes * 2;
+        }
+        // The copy below is ordered on the stream after every kernel that still reads the previous batch, and
+        // batch_host is pageable, so cudaMemcpyAsync has staged it by the time it returns: no synchronisation.
+        memcpy(ctx->batch_host, blob.data(), bytes);
+        ctx->batch_bytes = bytes;
+        GRB_CUDA(ctx, cudaMemcpyAsync(ctx->batch_dev, ctx->batch_host, bytes, cudaMemcpyHostToDevice, ctx->stream));
+    }
+    b->seqs = (const SeqDev *)ctx->batch_dev;
+    b->tile_begin = (const u32 *)((const unsigned char *)ctx->batch_dev + seq_bytes);
     return GRB_OK;
 }
 
@@ -1093,8 +1113,8 @@ int grb_left_overlaps(grb_ctx *ctx, const grb_index *idx, const uint32_t *ls, co
     p->nl = nl;
     int rc = GRB_OK;
     do {
-        if (cudaMalloc(&p->ls, nl * 4 + 16) != cudaSuccess || cudaMalloc(&p->le, nl * 4 + 16) != cudaSuccess ||
-            cudaMalloc(&p->offsets, (nl + 1) * 8) != cudaSuccess) {
+        if (grb_dev_malloc(ctx, (void **)&p->ls, nl * 4 + 16) != cudaSuccess || grb_dev_malloc(ctx, (void **)&p->le, nl * 4 + 16) != cudaSuccess ||
+            grb_dev_malloc(ctx, (void **)&p->offsets, (nl + 1) * 8) != cudaSuccess) {
             rc = grb_fail(ctx, GRB_ERR_OOM, "left_overlaps: device allocation failed");
             break;
         }
@@ -1124,7 +1144,7 @@ int grb_left_overlaps(grb_ctx *ctx, const grb_index *idx, const uint32_t *ls, co
             break;
         }
         p->np = np;
-        if (cudaMalloc(&p->pos, np * 4 + 16) != cudaSuccess) {
+        if (grb_dev_malloc(ctx, (void **)&p->pos, np * 4 + 16) != cudaSuccess) {
             rc = grb_fail(ctx, GRB_ERR_OOM, "left_overlaps: cannot allocate %llu pairs on the device", (unsigned long long)np);
             break;
         }
@@ -1189,10 +1209,10 @@ int grb_pairs_overlap_widths(const grb_pairs *p, uint32_t *widths) {
 void grb_pairs_destroy(grb_pairs *p) {
     if (!p) return;
     cudaSetDevice(p->ctx->device);
-    cudaFree(p->ls);
-    cudaFree(p->le);
-    cudaFree(p->offsets);
-    cudaFree(p->pos);
+    grb_dev_free(p->ctx, p->ls);
+    grb_dev_free(p->ctx, p->le);
+    grb_dev_free(p->ctx, p->offsets);
+    grb_dev_free(p->ctx, p->pos);
     free(p);
 }
 

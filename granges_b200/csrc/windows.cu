@@ -85,8 +85,8 @@ int grb_windows(grb_ctx *ctx, const uint32_t *seqlens, int nseq, uint32_t width,
     r->n = total;
     int rc = GRB_OK;
     do {
-        if (cudaMalloc(&r->seq_id, total * 4 + 16) != cudaSuccess || cudaMalloc(&r->starts, total * 4 + 16) != cudaSuccess ||
-            cudaMalloc(&r->ends, total * 4 + 16) != cudaSuccess) {
+        if (grb_dev_malloc(ctx, (void **)&r->seq_id, total * 4 + 16) != cudaSuccess || grb_dev_malloc(ctx, (void **)&r->starts, total * 4 + 16) != cudaSuccess ||
+            grb_dev_malloc(ctx, (void **)&r->ends, total * 4 + 16) != cudaSuccess) {
             rc = grb_fail(ctx, GRB_ERR_OOM, "windows: cannot allocate %llu windows on the device", (unsigned long long)total);
             break;
         }
@@ -135,9 +135,9 @@ const uint32_t *grb_ranges_dev_ends(const grb_ranges *r) { return r ? r->ends : 
 void grb_ranges_destroy(grb_ranges *r) {
     if (!r) return;
     cudaSetDevice(r->ctx->device);
-    cudaFree(r->seq_id);
-    cudaFree(r->starts);
-    cudaFree(r->ends);
+    grb_dev_free(r->ctx, r->seq_id);
+    grb_dev_free(r->ctx, r->starts);
+    grb_dev_free(r->ctx, r->ends);
     free(r->seq_offsets);
     free(r);
 }

@@ -5,6 +5,7 @@ import numpy as np, torch
 import bench, granges_b200 as gb
 
 use_default = len(sys.argv) > 1 and sys.argv[1] == "default"
+use_torch_stream = len(sys.argv) > 1 and sys.argv[1] == "torchstream"
 n = 4_545_455
 rs, re, sc = bench.gen_ranges(0, n, 14, "cuda", True)
 ls, le = bench.gen_ranges(0, n, 13, "cuda", False)
@@ -13,7 +14,9 @@ hrs, hre, hls, hle = (h[i].numpy().view(np.uint32) for i in (0, 1, 3, 4))
 hsc = h[2].numpy()
 out = torch.empty((n, 1), dtype=torch.float64).pin_memory().numpy()
 ov = torch.empty((n, 1), dtype=torch.uint8).pin_memory().numpy()
-ctx = gb.Context(0, stream=torch.cuda.current_stream() if use_default else None)
+if use_torch_stream:
+    st = torch.cuda.Stream(); torch.cuda.set_stream(st)
+ctx = gb.Context(0, stream=torch.cuda.current_stream() if (use_default or use_torch_stream) else None)
 def T(f, name, reps=3):
     best = 1e9
     for _ in range(reps):
