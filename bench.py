@@ -249,8 +249,10 @@ def main():
     left_off = np.concatenate([[0], np.cumsum(nl_per)]).astype(np.uint64)
 
     # ---- shard plan (identical on every rank; bounds come from the data below)
-    plan = gb.shard_plan(left_off, nr_per, None, None, world)
-    mine = [p for p in plan if p["rank"] == rank]
+    from granges_b200 import sharding
+
+    plan = sharding.plan(left_off, nr_per, world)
+    mine = sharding.units_of(plan, rank)
 
     # a non-default stream: stream-ordered allocation on the legacy default stream is several times slower
     stream = torch.cuda.Stream(device=dev)
@@ -268,8 +270,8 @@ def main():
         rs, re, sc = gen_ranges(s, nr_per[s], 14, dev, True)
         if (a, b) != (0, nl_per[s]):
             # a coordinate slice of the seqname: keep the rights that can overlap this run of lefts
-            lo, hi = int(ls_s.min()), int(le_s.max())
-            m = (rs < hi) & (re > lo)
+            lo, hi = sharding.unit_bounds(ls_s, le_s)
+            m = sharding.unit_right_mask(rs, re, lo, hi)
             rs, re, sc = rs[m].contiguous(), re[m].contiguous(), sc[m].contiguous()
         torch.cuda.synchronize()
         t0 = time.perf_counter()

@@ -1,0 +1,47 @@
+"""Host-side helpers for running one overlap join on N GPUs (one process per GPU).
+
+The path shards without any exchange step: overlaps never cross seqnames
+(src/granges.rs:958-962 of the reference) and a run of lefts only needs the rights with
+r.start < max(l.end) and r.end > min(l.start).  `plan` wraps the C planner (grb_shard_plan);
+`unit_right_mask` is the coordinate filter a rank applies to a seqname's rights before building
+its index; `concat_in_order` reassembles per-unit results in the reference's output order
+(seqname order, then left insertion order -- src/iterators.rs:43-76).
+Works on numpy arrays and on torch tensors (CPU or CUDA) alike.
+"""
+from __future__ import annotations
+
+import numpy as np
+
+from .api import shard_plan
+
+
+def plan(left_offsets, right_counts, world, ls=None, le=None):
+    """Units (dicts: seq, rank, left_begin, left_end, right_lo, right_hi), ordered by (seq, left_begin)."""
+    return shard_plan(left_offsets, right_counts, ls, le, world)
+
+
+def units_of(units, rank):
+    return [u for u in units if u["rank"] == rank]
+
+
+def unit_bounds(ls_unit, le_unit):
+    """(right_lo, right_hi) of a run of lefts: every overlapping right has start < hi and end > lo."""
+    return int(ls_unit.min()), int(le_unit.max())
+
+
+def unit_right_mask(rs, re, lo, hi):
+    """Rights a unit can touch.  Exact sums make the unit's results independent of this filter."""
+    return (rs < hi) & (re > lo)
+
+
+def concat_in_order(units, parts):
+    """parts[i] = result rows of units[i] (any rank); returns them in the reference's row order."""
+    order = sorted(range(len(units)), key=lambda i: (units[i]["seq"], units[i]["left_begin"]))
+    xs = [parts[i] for i in order]
+    if not xs:
+        return np.zeros((0,))
+    if type(xs[0]).__module__.startswith("torch"):
+        import torch
+
+        return torch.cat(xs)
+    return np.concatenate(xs)

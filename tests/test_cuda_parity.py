@@ -359,3 +359,30 @@ def test_pipeline_kernel_vs_tile_kernel(orc, monkeypatch, op):
         assert (res["1"][1][sl] == wv).all()
         m = wv[:, 0] == 1
         assert np.allclose(res["1"][0][sl][m], want[m], rtol=1e-12, atol=0)
+
+
+def test_sharded_units_bit_identical(eng, orc):
+    """Multi-GPU units (a run of lefts + the rights its coordinate bounds admit) give exactly the bits of
+    the unsharded call: sums are exact, everything else is order-free."""
+    from granges_b200 import sharding
+
+    c = random_case(71, 20_000, 30_000, span=2_000_000, maxlen=999, sorted_left=True)
+    ops = ["mean", "sum", "min", "max", "median", "count"]
+    ix = eng.build(c["rs"], c["re"], None, c["scores"], None)
+    whole, wv = eng.map_joins(ix, c["ls"], c["le"], ops)
+    off = np.array([0, len(c["ls"])], np.uint64)
+    units = sharding.plan(off, [len(c["rs"])], 3, c["ls"], c["le"])
+    assert len(units) == 3
+    parts, vparts = [], []
+    for u in units:
+        a, b = u["left_begin"], u["left_end"]
+        m = sharding.unit_right_mask(c["rs"], c["re"], u["right_lo"], u["right_hi"])
+        assert m.sum() < len(m)
+        sub = eng.build(c["rs"][m], c["re"][m], None, c["scores"][m], None)
+        o, v = eng.map_joins(sub, c["ls"][a:b], c["le"][a:b], ops)
+        parts.append(o)
+        vparts.append(v)
+    got = sharding.concat_in_order(units, parts)
+    gv = sharding.concat_in_order(units, vparts)
+    assert (gv == wv).all()
+    assert (got[wv == 1] == whole[wv == 1]).all()
