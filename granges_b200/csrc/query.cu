@@ -42,7 +42,7 @@ struct TileOut {
     u8 *keep;
     unsigned long long *n_kept;
     int anti;
-    u32 *ub, *lb;
+    u32 *ub, *lb, *pp;  // M_UBLB: #{start < l.end}, #{end <= l.start}, #{start < l.start}
     double *out;
     u8 *out_valid;
     int k;
@@ -237,10 +237,12 @@ __global__ void __launch_bounds__(TILE_TPB) k_tile(const SeqDev *__restrict__ se
     if (warp == 0) {
         // lane q in 0..3 finishes reduction q (min for even q, max for odd q) and fetches one table entry
         const u32 q = lane & 3;
+        // with M_UBLB the starts window must also cover the searches for l.start: its low end comes from min l.start
+        const u32 row = ((MODE & M_UBLB) && q == 0) ? 2u : q;
         u32 v = (q & 1) ? 0u : 0xffffffffu;
 #pragma unroll
         for (int w = 0; w < TILE_TPB / 32; w++) {
-            u32 p = s_red[q][w];
+            u32 p = s_red[row][w];
             v = (q & 1) ? max(v, p) : min(v, p);
         }
         // x = l.end for the starts table (q = 0,1); x = l.start + 1 for the ends table (q = 2,3)
@@ -279,18 +281,19 @@ __global__ void __launch_bounds__(TILE_TPB) k_tile(const SeqDev *__restrict__ se
     const bool staged = s_win[4] != 0;
 
     // ---- c. per-left searches
-    u32 ub[TILE_LPT], lb[TILE_LPT];
+    u32 ub[TILE_LPT], lb[TILE_LPT], pp[TILE_LPT];
     if (staged) {
         mbar_wait(&mbar, 0);
 #pragma unroll
         for (int k = 0; k < TILE_LPT; k++) {
-            ub[k] = lb[k] = 0;
+            ub[k] = lb[k] = pp[k] = 0;
             if (!okv[k]) continue;
             const u32 xa = b[k], xb = a[k] + 1;
             const u32 ba = min(xa >> sh, bmax) - la0;
             const u32 bb = min(xb >> sh, bmax) - lb0;
             ub[k] = a0 + scan_lower_bound(sKA, sLA[ba] - a0, xa);
             lb[k] = b0 + scan_lower_bound(sKB, sLB[bb] - b0, xb);
+            if (MODE & M_UBLB) pp[k] = a0 + scan_lower_bound(sKA, sLA[min(a[k] >> sh, bmax) - la0] - a0, a[k]);
         }
     } else {
 #pragma unroll
@@ -299,6 +302,8 @@ __global__ void __launch_bounds__(TILE_TPB) k_tile(const SeqDev *__restrict__ se
             const u32 ba = min(xa >> sh, bmax), bb = min(xb >> sh, bmax);
             ub[k] = okv[k] ? scan_lower_bound(starts, lut_a[ba], xa) : 0u;
             lb[k] = okv[k] ? scan_lower_bound(ends_sorted, lut_b[bb], xb) : 0u;
+            pp[k] = 0;
+            if ((MODE & M_UBLB) && okv[k]) pp[k] = scan_lower_bound(starts, lut_a[min(a[k] >> sh, bmax)], a[k]);
         }
     }
 
@@ -353,6 +358,7 @@ __global__ void __launch_bounds__(TILE_TPB) k_tile(const SeqDev *__restrict__ se
                 if (okv[k]) {
                     o.ub[g0 + k] = ub[k];
                     o.lb[g0 + k] = lb[k];
+                    o.pp[g0 + k] = pp[k];
                 }
             }
         }
@@ -376,6 +382,7 @@ __global__ void __launch_bounds__(TILE_TPB) k_tile(const SeqDev *__restrict__ se
         if (MODE & M_UBLB) {
             o.ub[g] = ub[k];
             o.lb[g] = lb[k];
+            o.pp[g] = pp[k];
         }
         if (MODE & M_MAP) {
             u32 nvalid = c_all;
@@ -747,6 +754,8 @@ __global__ void k_pairs_widths(const u32 *__restrict__ pos, const u64 *__restric
     }
 }
 
+#include "sweep.cuh"
+
 // ---- host orchestration -------------------------------------------------------------------
 
 struct Batch {
@@ -897,7 +906,7 @@ int launch_map(grb_ctx *ctx, const Batch &b, const u32 *ls, const u32 *le, const
                 break;
         }
     }
-    if (b.uniform && o.k == 1) {
+    if (MODE == M_MAP && b.uniform && o.k == 1) {
         switch (o.ops[0]) {
             case GRB_OP_MEAN:
                 return launch_tile<MODE, GRB_OP_MEAN>(ctx, b, ls, le, o);
@@ -1057,11 +1066,13 @@ int grb_map_joins_f64_batch(grb_ctx *ctx, const grb_index *const *idx, const uin
     if (!need_members) {
         GRB_TRY(launch_map<M_MAP>(ctx, b, dls.as<u32>(), dle.as<u32>(), o));
     } else {
-        TempBuf ub, lb, heavy;
+        TempBuf ub, lb, pp, heavy;
         GRB_TRY(ub.alloc(ctx, b.total * 4));
         GRB_TRY(lb.alloc(ctx, b.total * 4));
+        GRB_TRY(pp.alloc(ctx, b.total * 4));
         o.ub = ub.as<u32>();
         o.lb = lb.as<u32>();
+        o.pp = pp.as<u32>();
         GRB_TRY(launch_map<M_MAP | M_UBLB>(ctx, b, dls.as<u32>(), dle.as<u32>(), o));
         SweepOut so;
         memset(&so, 0, sizeof(so));
@@ -1078,9 +1089,7 @@ int grb_map_joins_f64_batch(grb_ctx *ctx, const grb_index *const *idx, const uin
             so.heavy_count = heavy.as<u32>();
             so.heavy_list = heavy.as<u32>() + 1;
         }
-        u64 blocks = (b.total + SW_WARPS - 1) / SW_WARPS;
-        if (blocks >= 0x7fffffffull) return grb_fail(ctx, GRB_ERR_UNSUPPORTED, "map_joins: too many left ranges for one call");
-        k_sweep<<<(unsigned)blocks, SW_TPB, 0, ctx->stream>>>(b.seqs, b.nseq, b.total, dls.as<u32>(), dle.as<u32>(), o.ub, o.lb, so);
+        k_sweep2<<<b.ntiles, SW2_TPB, 0, ctx->stream>>>(b.seqs, b.tile_begin, b.nseq, dls.as<u32>(), dle.as<u32>(), o.ub, o.pp, o.lb, so);
         GRB_LAUNCHED(ctx);
         if (want_median) {
             k_median_heavy<<<ctx->sm_count * 4, SW_TPB, 0, ctx->stream>>>(b.seqs, b.nseq, dls.as<u32>(), o.ub, o.lb, so.heavy_list,
@@ -1125,15 +1134,17 @@ int grb_left_overlaps(grb_ctx *ctx, const grb_index *idx, const uint32_t *ls, co
         uint64_t off[2] = {0, nl};
         Batch b;
         if ((rc = make_batch(ctx, &idx, off, 1, &b))) break;
-        TempBuf counts, ub, lb;
+        TempBuf counts, ub, lb, pp;
         if ((rc = counts.alloc(ctx, nl * 4))) break;
         if ((rc = ub.alloc(ctx, nl * 4))) break;
         if ((rc = lb.alloc(ctx, nl * 4))) break;
+        if ((rc = pp.alloc(ctx, nl * 4))) break;
         TileOut o;
         memset(&o, 0, sizeof(o));
         o.counts = counts.as<u32>();
         o.ub = ub.as<u32>();
         o.lb = lb.as<u32>();
+        o.pp = pp.as<u32>();
         if ((rc = launch_tile<M_COUNTS | M_UBLB, -1>(ctx, b, p->ls, p->le, o))) break;
         if ((rc = grb_scan_u32_to_u64(ctx, counts.as<u32>(), p->offsets, nl, true))) break;
         u64 np = 0;
@@ -1149,8 +1160,7 @@ int grb_left_overlaps(grb_ctx *ctx, const grb_index *idx, const uint32_t *ls, co
             break;
         }
         if (np) {
-            u64 blocks = (nl + SW_WARPS - 1) / SW_WARPS;
-            k_emit<<<(unsigned)blocks, SW_TPB, 0, ctx->stream>>>(b.seqs, 1, nl, p->ls, o.ub, o.lb, p->offsets, p->pos);
+            k_emit2<<<b.ntiles, SW2_TPB, 0, ctx->stream>>>(b.seqs, b.tile_begin, 1, p->ls, o.ub, o.pp, o.lb, p->offsets, p->pos);
             ctx->launches++;
         }
         e = cudaMemcpyAsync(offsets, p->offsets, (nl + 1) * 8, cudaMemcpyDefault, ctx->stream);

@@ -1,0 +1,284 @@
+// sweep.cuh -- member sweeps: MIN / MAX / MEDIAN / overlap bp (+ SUM / MEAN when the exact prefix
+// path is unavailable) and the emit pass of left_overlaps.  Included by query.cu.
+//
+// k_tile<M_UBLB> has already resolved, per left,
+//     ub = #{r.start < l.end}   pp = #{r.start < l.start}   lb = #{r.end <= l.start}
+// so in start order the group is:  every right in [pp, ub)  (it starts inside the left, so it
+// overlaps -- no need to look at its end)  plus  pp - lb "straddlers" somewhere below pp with
+// end > l.start, found by walking backward over `ends`, skipping 64-blocks whose block-max-end
+// (the replacement of coitrees' subtree_last) cannot overlap, until pp - lb of them were seen.
+//
+// Work assignment: a group of G lanes per left (G = 8 for the usual tens of members, 32 when a
+// tile averages more than 48 members per left), one CTA per tile of 1024 lefts, so a warp keeps
+// 32 / G lefts in flight.
+
+constexpr int SW2_TPB = 256;
+constexpr u32 MED2_CAP = 128;  // scores a group keeps in shared memory for the median (G = 8)
+constexpr u32 MED32_CAP = 512; // ... (G = 32)
+
+template <int G>
+__device__ __forceinline__ u32 group_mask() {
+    return G == 32 ? 0xffffffffu : (((1u << G) - 1u) << ((threadIdx.x & 31) & ~(G - 1)));
+}
+
+template <int G>
+__device__ __forceinline__ void sweep_tile(const SeqDev *__restrict__ sd, u64 g_lo, u64 g_hi, const u32 *__restrict__ ls,
+                                           const u32 *__restrict__ le, const u32 *__restrict__ ubv, const u32 *__restrict__ ppv,
+                                           const u32 *__restrict__ lbv, const SweepOut &o, double *s_buf /* [groups][CAP] */,
+                                           double *s_med /* [groups][2] */) {
+    constexpr u32 CAP = G == 32 ? MED32_CAP : MED2_CAP;
+    constexpr int NGROUPS = SW2_TPB / G;
+    const u32 glane = threadIdx.x & (G - 1), gidx = threadIdx.x / G;
+    const u32 gmask = group_mask<G>();
+    const u32 gshift = (threadIdx.x & 31) & ~(G - 1);
+    const u32 lt = (1u << glane) - 1;
+    const u32 *__restrict__ ends = sd->ends;
+    const u32 *__restrict__ starts = sd->starts;
+    const double *__restrict__ score = sd->score_a;
+    const u32 *__restrict__ vbits = sd->vbits_a;
+    const u32 *__restrict__ bme = sd->bme;
+    const bool has_scores = sd->has_scores != 0, has_nulls = sd->has_nulls != 0;
+    const bool sweep_sums = sd->sum_mode == GRB_SUM_SWEEP;
+    double *buf = s_buf + (size_t)gidx * CAP;
+    double *med = s_med + (size_t)gidx * 2;
+
+    for (u64 g = g_lo + gidx; g < g_hi; g += NGROUPS) {
+        const u32 u = ubv[g], p = ppv[g], l = lbv[g];
+        const u32 lstart = ls[g], lend = le[g];
+        u32 nvalid = 0;
+        double sum = 0.0, mn = 0.0, mx = 0.0;
+        bool have = false;
+        u64 bp = 0;
+        // ---- members that start inside the left: [p, u), ascending
+        for (u32 j0 = p; j0 < u; j0 += G) {
+            const u32 j = j0 + glane;
+            const bool in = j < u;
+            bool v = in && has_scores;
+            if (v && has_nulls) v = (vbits[j >> 5] >> (j & 31)) & 1u;
+            const u32 vm = (__ballot_sync(gmask, v) >> gshift) & (G == 32 ? 0xffffffffu : ((1u << G) - 1u));
+            if (in && o.want_bp) bp += (u64)(min(lend, ends[j]) - starts[j]);
+            if (v) {
+                const double x = score[j];
+                sum += x;
+                if (isfinite(x)) {
+                    mn = have ? fmin(mn, x) : x;
+                    mx = have ? fmax(mx, x) : x;
+                    have = true;
+                }
+                if (o.want_median) {
+                    const u32 slot = nvalid + __popc(vm & lt);
+                    if (slot < CAP) buf[slot] = x;
+                }
+            }
+            nvalid += __popc(vm);
+        }
+        // ---- straddlers: below p, end > l.start; exactly p - l of them
+        const u32 need = p - l;
+        u32 found = 0;
+        long long cb = p ? (long long)((p - 1) & ~(u32)(G - 1)) : -1;
+        while (found < need && cb >= 0) {
+            if (bme[cb >> GRB_BME_SHIFT] > lstart) {
+                const u32 j = (u32)cb + glane;
+                const bool in = j < p;
+                const u32 e = in ? ends[j] : 0u;
+                const bool hit = in && e > lstart;
+                const u32 hm = (__ballot_sync(gmask, hit) >> gshift) & (G == 32 ? 0xffffffffu : ((1u << G) - 1u));
+                bool v = hit && has_scores;
+                if (v && has_nulls) v = (vbits[j >> 5] >> (j & 31)) & 1u;
+                const u32 vm = (__ballot_sync(gmask, v) >> gshift) & (G == 32 ? 0xffffffffu : ((1u << G) - 1u));
+                if (hit && o.want_bp) bp += (u64)(min(lend, e) - lstart);
+                if (v) {
+                    const double x = score[j];
+                    sum += x;
+                    if (isfinite(x)) {
+                        mn = have ? fmin(mn, x) : x;
+                        mx = have ? fmax(mx, x) : x;
+                        have = true;
+                    }
+                    if (o.want_median) {
+                        const u32 slot = nvalid + __popc(vm & lt);
+                        if (slot < CAP) buf[slot] = x;
+                    }
+                }
+                found += __popc(hm);
+                nvalid += __popc(vm);
+                cb -= G;
+            } else {
+                cb = ((cb >> GRB_BME_SHIFT) << GRB_BME_SHIFT) - G;  // skip the rest of this 64-block
+            }
+        }
+        // ---- group reductions (fixed shuffle order: deterministic)
+#pragma unroll
+        for (int s = G / 2; s; s >>= 1) {
+            sum += __shfl_xor_sync(gmask, sum, s);
+            const double omn = __shfl_xor_sync(gmask, mn, s), omx = __shfl_xor_sync(gmask, mx, s);
+            const bool ohave = __shfl_xor_sync(gmask, (int)have, s);
+            if (ohave) {
+                mn = have ? fmin(mn, omn) : omn;
+                mx = have ? fmax(mx, omx) : omx;
+                have = true;
+            }
+            bp += __shfl_xor_sync(gmask, bp, s);
+        }
+        // ---- median of up to CAP values by rank counting inside the group
+        bool heavy = false;
+        if (o.want_median && nvalid) {
+            if (nvalid > CAP) {
+                heavy = true;
+            } else {
+                __syncwarp(gmask);
+                const u32 m = nvalid, k1 = (m - 1) >> 1, k2 = m >> 1;
+                for (u32 e = glane; e < m; e += G) {
+                    const double x = buf[e];
+                    u32 r = 0;
+                    for (u32 q = 0; q < m; q++) {
+                        const double y = buf[q];
+                        r += (y < x || (y == x && q < e)) ? 1u : 0u;
+                    }
+                    if (r == k1) med[0] = x;
+                    if (r == k2) med[1] = x;
+                }
+                __syncwarp(gmask);
+            }
+        }
+        if (glane == 0) {
+            for (int c = 0; c < o.k; c++) {
+                double r = 0.0;
+                u8 ok = 0;
+                bool mine = true;
+                switch (o.ops[c]) {
+                    case GRB_OP_SUM:
+                        mine = sweep_sums;
+                        r = sum;
+                        ok = 1;
+                        break;
+                    case GRB_OP_SUM_NOT_EMPTY:
+                        mine = sweep_sums;
+                        ok = nvalid != 0;
+                        r = ok ? sum : 0.0;
+                        break;
+                    case GRB_OP_MEAN:
+                        mine = sweep_sums;
+                        ok = nvalid != 0;
+                        r = ok ? sum / (double)nvalid : 0.0;
+                        break;
+                    case GRB_OP_MIN:
+                        ok = have;
+                        r = have ? mn : 0.0;
+                        break;
+                    case GRB_OP_MAX:
+                        ok = have;
+                        r = have ? mx : 0.0;
+                        break;
+                    case GRB_OP_MEDIAN:
+                        if (heavy) {
+                            mine = false;
+                        } else if (nvalid) {
+                            ok = 1;
+                            r = (nvalid & 1) ? med[1] : (med[0] + med[1]) / 2.0;
+                        }
+                        break;
+                    case GRB_OP_OVERLAP_BP:
+                        ok = 1;
+                        r = (double)bp;
+                        break;
+                    default:
+                        mine = false;
+                        break;
+                }
+                if (mine) {
+                    o.out[g * (u64)o.k + c] = r;
+                    o.out_valid[g * (u64)o.k + c] = ok;
+                }
+            }
+            if (heavy) {
+                const u32 slot = atomicAdd(o.heavy_count, 1u);
+                o.heavy_list[slot] = (u32)g;  // the host checks total < 2^32 when a median is requested
+            }
+        }
+        __syncwarp(gmask);  // the next left reuses buf / med
+    }
+}
+
+// One CTA per tile of 1024 lefts (the tiling of k_tile).
+__global__ void __launch_bounds__(SW2_TPB) k_sweep2(const SeqDev *__restrict__ seqs, const u32 *__restrict__ tile_begin, int nseq,
+                                                    const u32 *__restrict__ ls, const u32 *__restrict__ le,
+                                                    const u32 *__restrict__ ubv, const u32 *__restrict__ ppv,
+                                                    const u32 *__restrict__ lbv, const SweepOut o) {
+    __shared__ double s_buf[(SW2_TPB / 8) * MED2_CAP];  // 32 KB; viewed as [8][512] when G = 32
+    __shared__ double s_med[(SW2_TPB / 8) * 2];
+    __shared__ u32 s_cnt[SW2_TPB / 32];
+    const u32 t = blockIdx.x;
+    const SeqDev *__restrict__ sd = &seqs[find_seq_by_tile(tile_begin, nseq, t)];
+    const u64 g_first = ((sd->left_begin >> TILE_SHIFT) + (t - sd->tile_begin)) << TILE_SHIFT;
+    const u64 g_lo = sd->left_begin > g_first ? sd->left_begin : g_first;
+    const u64 g_hi = sd->left_end < g_first + TILE ? sd->left_end : g_first + TILE;
+    // members per left in this tile decide the group width (uniform for the CTA)
+    u32 c = 0;
+    for (u64 g = g_lo + threadIdx.x; g < g_hi; g += SW2_TPB) c += ubv[g] - lbv[g];
+    c = warp_sum(c);
+    if ((threadIdx.x & 31) == 0) s_cnt[threadIdx.x >> 5] = c;
+    __syncthreads();
+    u64 total = 0;
+#pragma unroll
+    for (int w = 0; w < SW2_TPB / 32; w++) total += s_cnt[w];
+    if (total > 48ull * (g_hi - g_lo))
+        sweep_tile<32>(sd, g_lo, g_hi, ls, le, ubv, ppv, lbv, o, s_buf, s_med);
+    else
+        sweep_tile<8>(sd, g_lo, g_hi, ls, le, ubv, ppv, lbv, o, s_buf, s_med);
+}
+
+// Emit pass of left_overlaps: positions (start order) of the members of every group, ascending,
+// which IS sort_ranges order (join.rs:121-128) because the index is sorted by (start, end, index).
+// [pp, ub) is written as an iota without reading anything; the straddlers are found as above.
+template <int G>
+__device__ __forceinline__ void emit_tile(const SeqDev *__restrict__ sd, u64 g_lo, u64 g_hi, const u32 *__restrict__ ls,
+                                          const u32 *__restrict__ ubv, const u32 *__restrict__ ppv, const u32 *__restrict__ lbv,
+                                          const u64 *__restrict__ offsets, u32 *__restrict__ pos) {
+    constexpr int NGROUPS = SW2_TPB / G;
+    const u32 glane = threadIdx.x & (G - 1), gidx = threadIdx.x / G;
+    const u32 gmask = group_mask<G>();
+    const u32 gshift = (threadIdx.x & 31) & ~(G - 1);
+    const u32 *__restrict__ ends = sd->ends;
+    const u32 *__restrict__ bme = sd->bme;
+    for (u64 g = g_lo + gidx; g < g_hi; g += NGROUPS) {
+        const u32 u = ubv[g], p = ppv[g], l = lbv[g];
+        const u32 lstart = ls[g];
+        const u32 need = p - l;
+        u32 *__restrict__ dst = pos + offsets[g];
+        for (u32 j = p + glane; j < u; j += G) dst[need + (j - p)] = j;
+        u32 found = 0;
+        long long cb = p ? (long long)((p - 1) & ~(u32)(G - 1)) : -1;
+        while (found < need && cb >= 0) {
+            if (bme[cb >> GRB_BME_SHIFT] > lstart) {
+                const u32 j = (u32)cb + glane;
+                const bool hit = j < p && ends[j] > lstart;
+                const u32 hm = (__ballot_sync(gmask, hit) >> gshift) & (G == 32 ? 0xffffffffu : ((1u << G) - 1u));
+                if (hit) {
+                    const u32 above = glane == G - 1 ? 0u : __popc(hm >> (glane + 1));
+                    dst[need - 1 - (found + above)] = j;
+                }
+                found += __popc(hm);
+                cb -= G;
+            } else {
+                cb = ((cb >> GRB_BME_SHIFT) << GRB_BME_SHIFT) - G;
+            }
+        }
+    }
+}
+
+__global__ void __launch_bounds__(SW2_TPB) k_emit2(const SeqDev *__restrict__ seqs, const u32 *__restrict__ tile_begin, int nseq,
+                                                   const u32 *__restrict__ ls, const u32 *__restrict__ ubv,
+                                                   const u32 *__restrict__ ppv, const u32 *__restrict__ lbv,
+                                                   const u64 *__restrict__ offsets, u32 *__restrict__ pos) {
+    const u32 t = blockIdx.x;
+    const SeqDev *__restrict__ sd = &seqs[find_seq_by_tile(tile_begin, nseq, t)];
+    const u64 g_first = ((sd->left_begin >> TILE_SHIFT) + (t - sd->tile_begin)) << TILE_SHIFT;
+    const u64 g_lo = sd->left_begin > g_first ? sd->left_begin : g_first;
+    const u64 g_hi = sd->left_end < g_first + TILE ? sd->left_end : g_first + TILE;
+    const u64 pairs = offsets[g_hi] - offsets[g_lo];
+    if (pairs > 64ull * (g_hi - g_lo))
+        emit_tile<32>(sd, g_lo, g_hi, ls, ubv, ppv, lbv, offsets, pos);
+    else
+        emit_tile<8>(sd, g_lo, g_hi, ls, ubv, ppv, lbv, offsets, pos);
+}
