@@ -4,8 +4,8 @@ The product is the C-ABI shared library `libgranges_b200.so` (include/granges_b2
 is its Python face.  Importing it requires the built library -- there is no CPU fallback.
 """
 from . import _capi
-from .api import OPS, Context, GRangesError, Index, Windows, shard_plan
+from .api import OPS, Context, GRangesError, Index, PreparedMap, Windows, shard_plan
 
 _capi.lib()  # fail loudly at import time if the CUDA library is missing
 
-__all__ = ["Context", "Index", "Windows", "GRangesError", "OPS", "shard_plan"]
+__all__ = ["Context", "Index", "Windows", "PreparedMap", "GRangesError", "OPS", "shard_plan"]

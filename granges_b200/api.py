@@ -315,6 +315,11 @@ class Context:
                                                         pl, pe, ops_p, k, po, pv))
         return out, out_valid
 
+    def prepare_map(self, indexes, left_offsets, ls, le, ops, out, out_valid):
+        """Bind every argument of grb_map_joins_f64_batch once; calling the returned object repeats the
+        query with no per-call Python work beyond the foreign call (for tight loops over a fixed batch)."""
+        return PreparedMap(self, indexes, left_offsets, ls, le, ops, out, out_valid)
+
     # -- windows
     def windows_dev(self, seqlens, width, step=None, chop=False):
         sl = np.ascontiguousarray(seqlens, dtype=np.uint32)
@@ -329,6 +334,29 @@ class Context:
             return w.copy()
         finally:
             w.close()
+
+
+class PreparedMap:
+    """A grb_map_joins_f64_batch call with all arguments already marshalled."""
+
+    def __init__(self, ctx, indexes, left_offsets, ls, le, ops, out, out_valid):
+        self.ctx = ctx
+        self._keep = (indexes, ls, le, out, out_valid)  # keep the buffers alive
+        self._handles = Context._handles(indexes)
+        self._off = np.ascontiguousarray(left_offsets, dtype=np.uint64)
+        self._ops, ops_p = Context._ops(ops)
+        k = len(self._ops)
+        pl, _, _ = _arg(ls, np.uint32)
+        pe, _, _ = _arg(le, np.uint32)
+        po = _arg(out, np.float64)[0]
+        pv = _arg(out_valid, np.uint8)[0]
+        self._fn = _capi.lib().grb_map_joins_f64_batch
+        self._args = (ctx.h, self._handles, self._off.ctypes.data_as(_capi.u64p), len(indexes), pl, pe, ops_p, k, po, pv)
+
+    def __call__(self):
+        rc = self._fn(*self._args)
+        if rc != 0:
+            self.ctx._check(rc)
 
 
 def shard_plan(left_offsets, right_counts, ls, le, nranks, max_shards=None):
