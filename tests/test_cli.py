@@ -1,0 +1,152 @@
+"""The `granges` CLI mirror (map / filter / windows) against text rendered from the oracle's results:
+byte-for-byte TSV, the reference's row order (genome-file order, then input order), "." for NoValue,
+Rust-style floats.  Flags as in the reference's clap definitions (src/main/mod.rs:96-214)."""
+import os
+import subprocess
+
+import numpy as np
+import pytest
+
+from tests.test_host_format import rust_display
+
+pytestmark = pytest.mark.gpu
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+CLI = os.path.join(ROOT, "granges_b200", "granges")
+
+
+@pytest.fixture(scope="module")
+def orc():
+    from oracle import oracle
+
+    return oracle
+
+
+def run(*args, check=True):
+    r = subprocess.run([CLI, *map(str, args)], capture_output=True, text=True, timeout=120)
+    if check:
+        assert r.returncode == 0, r.stderr
+    return r
+
+
+def make_files(tmp_path, seed=5, missing_scores=True, extra_left_cols=False):
+    rng = np.random.default_rng(seed)
+    genome = {"chr1": 300_000, "chr2": 150_000, "chrX": 90_000, "chrEmpty": 5000}
+    (tmp_path / "genome.tsv").write_text("".join(f"{k}\t{v}\n" for k, v in genome.items()))
+    left, right = {}, {}
+    llines, rlines = ["# a comment line"], []
+    for name, L in genome.items():
+        if name == "chrEmpty":
+            continue
+        nl, nr = int(rng.integers(200, 400)), int(rng.integers(300, 600))
+        if name == "chrX":
+            nr = 0  # the right file never mentions chrX
+        ls = rng.integers(0, L - 1000, nl)
+        le = ls + rng.integers(1, 1000, nl)
+        rs = rng.integers(0, L - 1000, nr)
+        re = rs + rng.integers(1, 1000, nr)
+        sc = np.round(rng.random(nr) * 100, int(rng.integers(0, 4)))
+        valid = np.ones(nr, bool) if not missing_scores else rng.random(nr) > 0.15
+        left[name] = (ls.astype(np.uint32), le.astype(np.uint32))
+        right[name] = (rs.astype(np.uint32), re.astype(np.uint32), sc, valid)
+    # interleave seqnames in the files: output order must still be genome order, then input order
+    order = [(n, i) for n in left for i in range(len(left[n][0]))]
+    rng.shuffle(order)
+    lrest = {}
+    for n, i in order:
+        rest = f"\tfeat{i}\t+" if extra_left_cols else ""
+        lrest[(n, i)] = rest
+        llines.append(f"{n}\t{left[n][0][i]}\t{left[n][1][i]}{rest}")
+    # per-seqname insertion order = order of appearance in the file
+    lorder = {n: [i for (m, i) in order if m == n] for n in left}
+    rorder = {}
+    ro = [(n, i) for n in right for i in range(len(right[n][0]))]
+    rng.shuffle(ro)
+    for n, i in ro:
+        rs, re, sc, valid = right[n]
+        s = repr(float(sc[i])) if valid[i] else "."
+        rlines.append(f"{n}\t{rs[i]}\t{re[i]}\tr{i}\t{s}")
+    rorder = {n: [i for (m, i) in ro if m == n] for n in right}
+    (tmp_path / "left.bed").write_text("\n".join(llines) + "\n")
+    (tmp_path / "right.bed").write_text("\n".join(rlines) + "\n")
+    return genome, left, right, lorder, rorder, lrest
+
+
+def test_map_matches_oracle_text(tmp_path, orc):
+    genome, left, right, lorder, rorder, _ = make_files(tmp_path)
+    ops = ["min", "max", "mean", "sum", "sum-not-empty", "median"]
+    out = tmp_path / "out.tsv"
+    run("map", "--genome", tmp_path / "genome.tsv", "--left", tmp_path / "left.bed", "--right", tmp_path / "right.bed", "--func",
+        ",".join(ops), "--output", out)
+    want = []
+    for name in genome:
+        if name not in left:
+            continue
+        ls, le = (a[lorder[name]] for a in left[name])
+        rs, re, sc, valid = (a[rorder[name]] for a in right[name])
+        t = orc.Tree(rs, re) if len(rs) else None
+        o, ov = orc.map_joins(t, sc if t is not None else None, valid.astype(np.uint8) if t is not None else None, ls, le, ops)
+        for i in range(len(ls)):
+            vals = [rust_display(float(o[i, c])) if ov[i, c] else "." for c in range(len(ops))]
+            want.append("\t".join([name, str(ls[i]), str(le[i])] + vals))
+    got = out.read_text().splitlines()
+    assert len(got) == len(want)
+    # sums / means: exactly-rounded on the GPU vs sequential on the CPU may differ in the last digit
+    for g, w in zip(got, want):
+        if g != w:
+            gf, wf = g.split("\t"), w.split("\t")
+            assert gf[:3] == wf[:3] and len(gf) == len(wf)
+            for c, (a, b) in enumerate(zip(gf[3:], wf[3:])):
+                if a != b:
+                    assert ops[c] in ("mean", "sum", "sum-not-empty") and abs(float(a) - float(b)) <= 1e-12 * abs(float(b)), (g, w)
+
+
+def test_map_bedtools_doc_example(tmp_path, goldens):
+    g = goldens["bedtools_map_example"]
+    (tmp_path / "g.tsv").write_text("chr1\t1000\n")
+    (tmp_path / "a.bed").write_text("".join(f"chr1\t{s}\t{e}\n" for s, e, *_ in g["left"]["chr1"]))
+    (tmp_path / "b.bed").write_text("".join(f"chr1\t{s}\t{e}\tb{i}\t{sc}\n" for i, (s, e, sc) in enumerate(g["right"]["chr1"])))
+    r = run("map", "-g", tmp_path / "g.tsv", "-l", tmp_path / "a.bed", "-r", tmp_path / "b.bed", "-f", "mean")
+    rows = [line.split("\t") for line in r.stdout.splitlines()]
+    assert [row[3] for row in rows] == ["." if m is None else rust_display(m) for m in g["mean"]]
+
+
+def test_filter_matches_oracle(tmp_path, orc):
+    genome, left, right, lorder, rorder, lrest = make_files(tmp_path, seed=9, extra_left_cols=True)
+    r = run("filter", "-g", tmp_path / "genome.tsv", "-l", tmp_path / "left.bed", "-r", tmp_path / "right.bed")
+    want = []
+    for name in genome:
+        if name not in left or len(right[name][0]) == 0:
+            continue  # no right container for this seqname: the semi-join drops its lefts
+        ls, le = (a[lorder[name]] for a in left[name])
+        t = orc.Tree(right[name][0], right[name][1])
+        keep = orc.filter_overlaps(t, ls, le)
+        for j, i in enumerate(lorder[name]):
+            if keep[j]:
+                want.append(f"{name}\t{ls[j]}\t{le[j]}{lrest[(name, i)]}")
+    assert r.stdout.splitlines() == want
+
+
+def test_windows_matches_oracle(tmp_path, orc):
+    lens = {"chr1": 100_003, "chr2": 999, "chr3": 1000, "chr4": 1}
+    (tmp_path / "g.tsv").write_text("".join(f"{k}\t{v}\n" for k, v in lens.items()))
+    names = list(lens)
+    for width, step, chop in [(1000, 500, False), (1000, 500, True), (1000, None, False), (333, 100, True)]:
+        args = ["windows", "-g", tmp_path / "g.tsv", "-w", width] + (["-s", step] if step else []) + (["--chop"] if chop else [])
+        got = run(*args).stdout.splitlines()
+        seq, s, e = orc.windows(list(lens.values()), width, step, chop)
+        assert got == [f"{names[q]}\t{a}\t{b}" for q, a, b in zip(seq, s, e)]
+
+
+def test_cli_errors(tmp_path):
+    (tmp_path / "g.tsv").write_text("chr1\t1000\n")
+    (tmp_path / "a.bed").write_text("chr1\t1\t5\nchr9\t1\t5\n")
+    (tmp_path / "b.bed").write_text("chr1\t2\t6\tx\t1.5\n")
+    r = run("map", "-g", tmp_path / "g.tsv", "-l", tmp_path / "a.bed", "-r", tmp_path / "b.bed", "-f", "sum", check=False)
+    assert r.returncode == 1 and r.stderr.startswith("Error: The sequence name 'chr9' is not found")
+    r = run("map", "-g", tmp_path / "g.tsv", "-l", tmp_path / "a.bed", "-r", tmp_path / "b.bed", "-f", "sum", "--skip-missing")
+    assert r.stdout == "chr1\t1\t5\t1.5\n"
+    r = run("map", "-g", tmp_path / "g.tsv", "-l", tmp_path / "a.bed", "-r", tmp_path / "b.bed", "-s", check=False)
+    assert r.returncode == 1 and "No operation was specified" in r.stderr
+    (tmp_path / "e.bed").write_text("")
+    r = run("map", "-g", tmp_path / "g.tsv", "-l", tmp_path / "e.bed", "-r", tmp_path / "b.bed", "-f", "sum", check=False)
+    assert r.returncode == 1 and "The input file had no rows." in r.stderr
