@@ -20,8 +20,10 @@
 // Tiles whose windows do not fit the ring slots (sparse lefts over dense rights) are resolved by
 // per-left global searches inside the consumers; results are identical.
 
-constexpr int PIPE_NC = 16;  // consumer warps
-constexpr int PIPE_LPT = TILE / (PIPE_NC * 32);  // consecutive lefts per consumer thread
+constexpr int PIPE_GROUPS = 1;  // consumer groups; group g takes tiles g, g + GROUPS, ... so one group computes while another waits
+constexpr int PIPE_NCG = 16;    // warps per consumer group
+constexpr int PIPE_NC = PIPE_GROUPS * PIPE_NCG;  // consumer warps
+constexpr int PIPE_LPT = TILE / (PIPE_NCG * 32);  // consecutive lefts per consumer thread
 constexpr int PIPE_THREADS = (PIPE_NC + 3) * 32;
 constexpr int PIPE_LSTAGES = 8;
 constexpr int PIPE_WSTAGES = 4;
@@ -89,12 +91,12 @@ __global__ void __launch_bounds__(PIPE_THREADS, 1) k_map_pipe(const SeqDev *__re
     if (tid == 0) {
         for (int i = 0; i < PIPE_LSTAGES; i++) {
             mbar_init(&S.fullL[i], 1);
-            mbar_init(&S.emptyL[i], PIPE_NC);
+            mbar_init(&S.emptyL[i], PIPE_NCG);
             mbar_init(&S.statsL[i], 1);
         }
         for (int i = 0; i < PIPE_WSTAGES; i++) {
             mbar_init(&S.fullW[i], 1);
-            mbar_init(&S.emptyW[i], PIPE_NC);
+            mbar_init(&S.emptyW[i], PIPE_NCG);
         }
     }
     if ((int)tid < nseq) {
@@ -269,11 +271,12 @@ __global__ void __launch_bounds__(PIPE_THREADS, 1) k_map_pipe(const SeqDev *__re
     }
 
     // ================= consumers =================
-    const u32 cw = warp - 3;
+    const u32 cgroup = (warp - 3) / PIPE_NCG, cw = (warp - 3) % PIPE_NCG;
     const u32 i0 = (cw * 32 + lane) * PIPE_LPT;  // first slot of this thread inside a tile
     const bool ovec = ((((uintptr_t)out) & 15) | (((uintptr_t)out_valid) & 3)) == 0;
     const bool skip = flags & 2;
-    for (u32 j = 0; j < nmine; j++) {
+    const bool nostore = flags & 4;  // debug: do the arithmetic, keep the stores out (timing experiments)
+    for (u32 j = cgroup; j < nmine; j += PIPE_GROUPS) {
         const u32 sw = j % PIPE_WSTAGES, sl = j % PIPE_LSTAGES;
         mbar_wait(&S.fullW[sw], (j / PIPE_WSTAGES) & 1);
         if (!skip) {
@@ -357,6 +360,14 @@ __global__ void __launch_bounds__(PIPE_THREADS, 1) k_map_pipe(const SeqDev *__re
                     }
                 }
             }
+            // ---- everything this warp needs from the two ring slots is in registers now: hand them back
+            // before the arithmetic and the stores, so the loaders can refill them meanwhile
+            const u64 g0 = d.g_first + i0;
+            __syncwarp();
+            if (lane == 0) {
+                mbar_arrive(&S.emptyW[sw]);
+                mbar_arrive(&S.emptyL[sl]);
+            }
             // ---- reductions
             double r[PIPE_LPT];
             u8 v[PIPE_LPT];
@@ -388,8 +399,9 @@ __global__ void __launch_bounds__(PIPE_THREADS, 1) k_map_pipe(const SeqDev *__re
                     r[k] = c ? sum / (double)c : 0.0;
                 }
             }
-            const u64 g0 = d.g_first + i0;
-            if (ovec && okv[0] && okv[PIPE_LPT - 1] && (PIPE_LPT == 4 || PIPE_LPT == 2)) {
+            if (nostore && r[0] != 1.2345e300) {
+                // nothing
+            } else if (ovec && okv[0] && okv[PIPE_LPT - 1] && (PIPE_LPT == 4 || PIPE_LPT == 2)) {
                 double2 *po = reinterpret_cast<double2 *>(out + g0);
                 po[0] = make_double2(r[0], r[1 % PIPE_LPT]);
                 if (PIPE_LPT == 4) {
@@ -407,12 +419,12 @@ __global__ void __launch_bounds__(PIPE_THREADS, 1) k_map_pipe(const SeqDev *__re
                     }
                 }
             }
-        }
-        // done with this stage: one arrival per consumer warp
-        __syncwarp();
-        if (lane == 0) {
-            mbar_arrive(&S.emptyW[sw]);
-            mbar_arrive(&S.emptyL[sl]);
+        } else {
+            __syncwarp();
+            if (lane == 0) {
+                mbar_arrive(&S.emptyW[sw]);
+                mbar_arrive(&S.emptyL[sl]);
+            }
         }
     }
 }

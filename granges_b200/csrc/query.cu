@@ -66,18 +66,23 @@ __device__ __forceinline__ void tma_load_1d(void *dst, const void *src, u32 byte
                  "l"(src), "r"(bytes), "r"(smem_addr(bar))
                  : "memory");
 }
-__device__ __forceinline__ void mbar_wait(u64 *bar, u32 parity) {
+__device__ __forceinline__ bool mbar_try_wait(u64 *bar, u32 parity) {
+    u32 ok;
     asm volatile(
         "{\n"
         ".reg .pred P1;\n"
-        "LAB_WAIT:\n"
-        "mbarrier.try_wait.parity.shared::cta.b64 P1, [%0], %1, %2;\n"
-        "@P1 bra DONE;\n"
-        "bra LAB_WAIT;\n"
-        "DONE:\n"
-        "}\n" ::"r"(smem_addr(bar)),
-        "r"(parity), "r"(0x989680u)  // suspend-time hint: sleep in hardware instead of spinning through issue slots
+        "mbarrier.try_wait.parity.shared::cta.b64 P1, [%1], %2;\n"
+        "selp.u32 %0, 1, 0, P1;\n"
+        "}\n"
+        : "=r"(ok)
+        : "r"(smem_addr(bar)), "r"(parity)
         : "memory");
+    return ok != 0;
+}
+// Poll, and sleep between polls: a waiting warp should not eat the issue slots the working warps need.
+__device__ __forceinline__ void mbar_wait(u64 *bar, u32 parity) {
+    if (mbar_try_wait(bar, parity)) return;
+    while (!mbar_try_wait(bar, parity)) __nanosleep(64);
 }
 
 // ---- searches -------------------------------------------------------------------
@@ -883,7 +888,7 @@ int launch_pipe(grb_ctx *ctx, const Batch &b, const u32 *ls, const u32 *le, cons
     }
     u32 grid = (u32)ctx->sm_count;
     if (grid > b.ntiles) grid = b.ntiles;
-    const int flags = (ctx->tile_mode ? 1 : 0) | (ctx->pipe_mode == 2 ? 2 : 0);
+    const int flags = (ctx->tile_mode ? 1 : 0) | (ctx->pipe_mode == 2 ? 2 : 0) | (ctx->pipe_mode == 3 ? 4 : 0);
     k_map_pipe<FAST><<<grid, PIPE_THREADS, sizeof(PipeSmem), ctx->stream>>>(b.seqs, b.nseq, b.ntiles, ls, le, o.out, o.out_valid, flags);
     GRB_LAUNCHED(ctx);
     return GRB_OK;
