@@ -39,8 +39,7 @@ __device__ __forceinline__ void sweep_tile(const SeqDev *__restrict__ sd, u64 g_
     const u32 *__restrict__ bme = sd->bme;
     const bool has_scores = sd->has_scores != 0, has_nulls = sd->has_nulls != 0;
     const bool sweep_sums = sd->sum_mode == GRB_SUM_SWEEP;
-    double *buf = s_buf + (size_t)gidx * CAP;
-    double *med = s_med + (size_t)gidx * 2;
+    u64 *kbuf = reinterpret_cast<u64 *>(s_buf) + (size_t)gidx * CAP;  // order-preserving integer images of the scores
 
     for (u64 g = g_lo + gidx; g < g_hi; g += NGROUPS) {
         const u32 u = ubv[g], p = ppv[g], l = lbv[g];
@@ -67,7 +66,7 @@ __device__ __forceinline__ void sweep_tile(const SeqDev *__restrict__ sd, u64 g_
                 }
                 if (o.want_median) {
                     const u32 slot = nvalid + __popc(vm & lt);
-                    if (slot < CAP) buf[slot] = x;
+                    if (slot < CAP) kbuf[slot] = f64_key(x);
                 }
             }
             nvalid += __popc(vm);
@@ -97,7 +96,7 @@ __device__ __forceinline__ void sweep_tile(const SeqDev *__restrict__ sd, u64 g_
                     }
                     if (o.want_median) {
                         const u32 slot = nvalid + __popc(vm & lt);
-                        if (slot < CAP) buf[slot] = x;
+                        if (slot < CAP) kbuf[slot] = f64_key(x);
                     }
                 }
                 found += __popc(hm);
@@ -120,25 +119,84 @@ __device__ __forceinline__ void sweep_tile(const SeqDev *__restrict__ sd, u64 g_
             }
             bp += __shfl_xor_sync(gmask, bp, s);
         }
-        // ---- median of up to CAP values by rank counting inside the group
+        // ---- median of up to CAP values: quickselect inside the group.  Elements are ordered by (key, slot); a
+        // round counts the elements below the pivot (one pass, each lane over its strided share) and, in the same
+        // pass, remembers the first still-active element on either side as the next pivot.
         bool heavy = false;
+        double med_lo = 0.0, med_hi = 0.0;
         if (o.want_median && nvalid) {
             if (nvalid > CAP) {
                 heavy = true;
             } else {
                 __syncwarp(gmask);
-                const u32 m = nvalid, k1 = (m - 1) >> 1, k2 = m >> 1;
-                for (u32 e = glane; e < m; e += G) {
-                    const double x = buf[e];
-                    u32 r = 0;
-                    for (u32 q = 0; q < m; q++) {
-                        const double y = buf[q];
-                        r += (y < x || (y == x && q < e)) ? 1u : 0u;
+                const u32 m = nvalid, k1 = (m - 1) >> 1;
+                // active range: (lo_k, lo_i) < element < (hi_k, hi_i), exclusive; starts unbounded
+                u64 lo_k = 0, hi_k = ~0ull;
+                u32 lo_i = 0, hi_i = 0xffffffffu;
+                bool has_lo = false;
+                u32 piv = 0;  // slot of the pivot
+                u64 res_k = 0;
+                u32 res_i = 0;
+                while (true) {
+                    const u64 pk = kbuf[piv];
+                    u32 cnt = 0, next_below = 0xffffffffu, next_above = 0xffffffffu;
+                    for (u32 e = glane; e < m; e += G) {
+                        const u64 y = kbuf[e];
+                        const bool below = y < pk || (y == pk && e < piv);
+                        const bool above = y > pk || (y == pk && e > piv);
+                        cnt += below ? 1u : 0u;
+                        const bool gt_lo = !has_lo || y > lo_k || (y == lo_k && e > lo_i);
+                        const bool lt_hi = y < hi_k || (y == hi_k && e < hi_i);
+                        if (below && gt_lo) next_below = min(next_below, e);
+                        if (above && lt_hi) next_above = min(next_above, e);
                     }
-                    if (r == k1) med[0] = x;
-                    if (r == k2) med[1] = x;
+#pragma unroll
+                    for (int s2 = G / 2; s2; s2 >>= 1) {
+                        cnt += __shfl_xor_sync(gmask, cnt, s2);
+                        next_below = min(next_below, __shfl_xor_sync(gmask, next_below, s2));
+                        next_above = min(next_above, __shfl_xor_sync(gmask, next_above, s2));
+                    }
+                    if (cnt == k1) {
+                        res_k = pk;
+                        res_i = piv;
+                        break;
+                    }
+                    if (cnt < k1) {
+                        lo_k = pk;
+                        lo_i = piv;
+                        has_lo = true;
+                        piv = next_above;
+                    } else {
+                        hi_k = pk;
+                        hi_i = piv;
+                        piv = next_below;
+                    }
                 }
-                __syncwarp(gmask);
+                med_lo = key_f64(res_k);
+                med_hi = med_lo;
+                if (!(m & 1)) {
+                    // even count: the upper middle is the smallest element above (res_k, res_i)
+                    u64 bk = ~0ull;
+                    u32 bi = 0xffffffffu;
+                    for (u32 e = glane; e < m; e += G) {
+                        const u64 y = kbuf[e];
+                        const bool above = y > res_k || (y == res_k && e > res_i);
+                        if (above && (y < bk || (y == bk && e < bi))) {
+                            bk = y;
+                            bi = e;
+                        }
+                    }
+#pragma unroll
+                    for (int s2 = G / 2; s2; s2 >>= 1) {
+                        const u64 ok2 = __shfl_xor_sync(gmask, bk, s2);
+                        const u32 oi2 = __shfl_xor_sync(gmask, bi, s2);
+                        if (ok2 < bk || (ok2 == bk && oi2 < bi)) {
+                            bk = ok2;
+                            bi = oi2;
+                        }
+                    }
+                    med_hi = key_f64(bk);
+                }
             }
         }
         if (glane == 0) {
@@ -175,7 +233,7 @@ __device__ __forceinline__ void sweep_tile(const SeqDev *__restrict__ sd, u64 g_
                             mine = false;
                         } else if (nvalid) {
                             ok = 1;
-                            r = (nvalid & 1) ? med[1] : (med[0] + med[1]) / 2.0;
+                            r = (nvalid & 1) ? med_lo : (med_lo + med_hi) / 2.0;
                         }
                         break;
                     case GRB_OP_OVERLAP_BP:
@@ -196,7 +254,7 @@ __device__ __forceinline__ void sweep_tile(const SeqDev *__restrict__ sd, u64 g_
                 o.heavy_list[slot] = (u32)g;  // the host checks total < 2^32 when a median is requested
             }
         }
-        __syncwarp(gmask);  // the next left reuses buf / med
+        __syncwarp(gmask);  // the next left reuses kbuf
     }
 }
 
