@@ -29,6 +29,7 @@ struct grb_ctx {
     void *batch_dev;
     void *batch_host;
     size_t batch_bytes, batch_cap;
+    u32 *dev_flags; // device word: bit 0 = a left range with end <= start or end > 2^31-1 was seen by a kernel
     void *zeros;    // 1 KB of zeros (tables) + 1 KB of 0xff (sentinel keys): what an absent seqname / empty index reads
     int pipe_mode;  // 1 = persistent warp-specialised pipeline for single-reduction maps (default), 0 = k_tile only (debug)
     int tile_mode;  // 1 = TMA-staged smem windows (default), 0 = global binary search only (debug)
@@ -118,6 +119,9 @@ struct OutBuf {
 };
 
 bool grb_is_device_ptr(const void *p);
+// Read-and-clear the device flag word after a synchronisation; turns a flagged invalid left range into
+// GRB_ERR_INVALID_RANGE (the reference cannot even construct such a range: src/ranges/mod.rs:30, coitrees.rs:53-54).
+int grb_check_flags(grb_ctx *ctx);
 
 // Long-lived device arrays (indexes, pairs, windows) also come from the stream-ordered pool: plain
 // cudaMalloc / cudaFree cost milliseconds each once a process holds many GB, the pool costs microseconds.

@@ -61,6 +61,20 @@ int OutBuf::finish(grb_ctx *ctx) {
     return GRB_OK;
 }
 
+int grb_check_flags(grb_ctx *ctx) {
+    u32 f = 0;
+    GRB_CUDA(ctx, cudaMemcpyAsync(&f, ctx->dev_flags, 4, cudaMemcpyDeviceToHost, ctx->stream));
+    GRB_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+    if (f) {
+        GRB_CUDA(ctx, cudaMemsetAsync(ctx->dev_flags, 0, 4, ctx->stream));
+        if (f & 1)
+            return grb_fail(ctx, GRB_ERR_INVALID_RANGE,
+                            "a left range has end <= start or end > 2^31-1 (the reference panics: ranges/mod.rs:30, "
+                            "ranges/coitrees.rs:53-54); its result rows are those of an empty group");
+    }
+    return GRB_OK;
+}
+
 extern "C" {
 
 int grb_abi_version(void) { return GRB_ABI_VERSION; }
@@ -102,6 +116,11 @@ int grb_ctx_create(int device, grb_ctx **out) {
         free(ctx);
         return GRB_ERR_OOM;
     }
+    if (cudaMalloc((void **)&ctx->dev_flags, 16) != cudaSuccess || cudaMemset(ctx->dev_flags, 0, 16) != cudaSuccess) {
+        cudaStreamDestroy(ctx->own_stream);
+        free(ctx);
+        return GRB_ERR_OOM;
+    }
     *out = ctx;
     return GRB_OK;
 }
@@ -121,7 +140,7 @@ int grb_ctx_use_own_stream(grb_ctx *ctx) {
 int grb_ctx_sync(grb_ctx *ctx) {
     if (!ctx) return GRB_ERR_INVALID_ARG;
     GRB_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
-    return GRB_OK;
+    return grb_check_flags(ctx);
 }
 
 void grb_ctx_destroy(grb_ctx *ctx) {
@@ -130,6 +149,7 @@ void grb_ctx_destroy(grb_ctx *ctx) {
     cudaStreamSynchronize(ctx->stream);
     cudaStreamDestroy(ctx->own_stream);
     cudaFree(ctx->zeros);
+    cudaFree(ctx->dev_flags);
     cudaFree(ctx->batch_dev);
     free(ctx->batch_host);
     free(ctx);

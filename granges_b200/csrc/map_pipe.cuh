@@ -24,11 +24,12 @@ constexpr int PIPE_GROUPS = 1;  // consumer groups; group g takes tiles g, g + G
 constexpr int PIPE_NCG = 16;    // warps per consumer group
 constexpr int PIPE_NC = PIPE_GROUPS * PIPE_NCG;  // consumer warps
 constexpr int PIPE_LPT = TILE / (PIPE_NCG * 32);  // consecutive lefts per consumer thread
-constexpr int PIPE_THREADS = (PIPE_NC + 3) * 32;
-constexpr int PIPE_LSTAGES = 8;
-constexpr int PIPE_WSTAGES = 4;
+constexpr int PIPE_NSURV = 4;  // surveyor warps (tile j goes to surveyor j % PIPE_NSURV)
+constexpr int PIPE_THREADS = (PIPE_NC + 2 + PIPE_NSURV) * 32;
+constexpr int PIPE_LSTAGES = 6;
+constexpr int PIPE_WSTAGES = 5;
 constexpr u32 PIPE_WIN = 1280;  // keys (and prefixes) per staged window
-constexpr u32 PIPE_LUT = 640;   // bin-table entries per staged slice
+constexpr u32 PIPE_LUT = 512;   // bin-table entries per staged slice
 constexpr int PIPE_MAXSEQ = 32; // seqnames per launch (their descriptors live in shared memory)
 
 struct PipeSeq {
@@ -83,7 +84,8 @@ __device__ __forceinline__ void mbar_arrive(u64 *bar) {
 template <int FAST>
 __global__ void __launch_bounds__(PIPE_THREADS, 1) k_map_pipe(const SeqDev *__restrict__ seqs, int nseq, u32 ntiles,
                                                               const u32 *__restrict__ ls, const u32 *__restrict__ le,
-                                                              double *__restrict__ out, u8 *__restrict__ out_valid, int flags) {
+                                                              double *__restrict__ out, u8 *__restrict__ out_valid, int flags,
+                                                              u32 *__restrict__ ctx_flags) {
     extern __shared__ __align__(128) unsigned char smem_raw[];
     PipeSmem &S = *reinterpret_cast<PipeSmem *>(smem_raw);
     const u32 tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
@@ -212,10 +214,10 @@ __global__ void __launch_bounds__(PIPE_THREADS, 1) k_map_pipe(const SeqDev *__re
         return;
     }
 
-    if (warp == 1) {
-        // ================= surveyor =================
-        u32 bin_prev = 0, bound_prev = 0;
-        for (u32 j = 0; j <= nmine; j++) {
+    if (warp == 1 || (warp >= 3 && warp < 2 + PIPE_NSURV)) {
+        // ================= surveyors =================
+        const u32 sid = warp == 1 ? 0u : warp - 2;
+        for (u32 j = sid; j < nmine; j += PIPE_NSURV) {
             u32 bin_new = 0, bound_new = 0;
             if (j < nmine) {
                 const u32 sl = j % PIPE_LSTAGES;
@@ -224,12 +226,15 @@ __global__ void __launch_bounds__(PIPE_THREADS, 1) k_map_pipe(const SeqDev *__re
                 const u32 vlo = ti.vlo, vhi = ti.vhi;
                 const PipeSeq &q = S.seq[ti.seq];
                 u32 mn_s = 0xffffffffu, mx_s = 0, mn_e = 0xffffffffu, mx_e = 0;
+                // widest (end - start - 1) mod 2^32: it reaches 2^31-1 iff some left has end <= start (ends <= 2^31-1)
+                u32 mx_w = 0;
                 if (vlo == 0 && vhi == TILE) {
                     const uint4 *vs = reinterpret_cast<const uint4 *>(S.ls[sl]);
                     const uint4 *ve = reinterpret_cast<const uint4 *>(S.le[sl]);
 #pragma unroll
                     for (int r = 0; r < TILE / 128; r++) {
                         const uint4 x = vs[r * 32 + lane], y = ve[r * 32 + lane];
+                        mx_w = max(mx_w, max(max(y.x - x.x - 1, y.y - x.y - 1), max(y.z - x.z - 1, y.w - x.w - 1)));
                         mn_s = min(mn_s, min(min(x.x, x.y), min(x.z, x.w)));
                         mx_s = max(mx_s, max(max(x.x, x.y), max(x.z, x.w)));
                         mn_e = min(mn_e, min(min(y.x, y.y), min(y.z, y.w)));
@@ -238,6 +243,7 @@ __global__ void __launch_bounds__(PIPE_THREADS, 1) k_map_pipe(const SeqDev *__re
                 } else {
                     for (u32 i = vlo + lane; i < vhi; i += 32) {
                         const u32 x = S.ls[sl][i], y = S.le[sl][i];
+                        mx_w = max(mx_w, y - x - 1);
                         mn_s = min(mn_s, x);
                         mx_s = max(mx_s, x);
                         mn_e = min(mn_e, y);
@@ -248,30 +254,28 @@ __global__ void __launch_bounds__(PIPE_THREADS, 1) k_map_pipe(const SeqDev *__re
                 mx_e = warp_max(mx_e);
                 mn_s = warp_min(mn_s);
                 mx_s = warp_max(mx_s);
+                // invalid lefts cannot exist in the reference (it panics: ranges/mod.rs:30, coitrees.rs:53-54): make the call fail
+                mx_w = warp_max(mx_w);
+                if ((mx_w >= 0x7fffffffu || mx_e > 0x7fffffffu) && lane == 0) atomicOr(ctx_flags, 1u);
                 const u32 qq = lane & 3;
                 const u32 v = qq == 0 ? mn_e : qq == 1 ? mx_e : qq == 2 ? mn_s : mx_s;
                 const u32 x = v + (qq >> 1);  // l.end for the starts table, l.start + 1 for the ends table
                 bin_new = min(x >> q.sh, q.bmax);
                 bound_new = ((qq < 2) ? q.lut_a : q.lut_b)[bin_new + (qq & 1)];
-            }
-            if (j >= 1) {
-                // publish the previous tile: its table entries were requested one iteration ago
-                const u32 sl = (j - 1) % PIPE_LSTAGES;
+                // publish at once: this warp now waits for its four table entries, the other surveyors carry on
                 if (lane < 4) {
-                    S.tile[sl].bin[lane] = bin_prev;
-                    S.tile[sl].bound[lane] = bound_prev;
+                    S.tile[sl].bin[lane] = bin_new;
+                    S.tile[sl].bound[lane] = bound_new;
                 }
                 __syncwarp();
                 if (lane == 0) mbar_arrive(&S.statsL[sl]);
             }
-            bin_prev = bin_new;
-            bound_prev = bound_new;
         }
         return;
     }
 
     // ================= consumers =================
-    const u32 cgroup = (warp - 3) / PIPE_NCG, cw = (warp - 3) % PIPE_NCG;
+    const u32 cgroup = (warp - 2 - PIPE_NSURV) / PIPE_NCG, cw = (warp - 2 - PIPE_NSURV) % PIPE_NCG;
     const u32 i0 = (cw * 32 + lane) * PIPE_LPT;  // first slot of this thread inside a tile
     const bool ovec = ((((uintptr_t)out) & 15) | (((uintptr_t)out_valid) & 3)) == 0;
     const bool skip = flags & 2;
@@ -303,7 +307,12 @@ __global__ void __launch_bounds__(PIPE_THREADS, 1) k_map_pipe(const SeqDev *__re
             }
             bool okv[PIPE_LPT];
 #pragma unroll
-            for (int k = 0; k < PIPE_LPT; k++) okv[k] = i0 + k >= vlo && i0 + k < vhi;
+            for (int k = 0; k < PIPE_LPT; k++) {
+                okv[k] = i0 + k >= vlo && i0 + k < vhi;
+            }
+            // (A left with end <= start or end > 2^31-1 -- impossible in the reference, which panics -- was flagged by
+            // the surveyor and makes the call fail; here it needs no special care: its bins lie inside the staged
+            // slices like any other left's, so every access stays in range and only its own row is meaningless.)
             const u32 a0 = d.a0, b0 = d.b0, la0 = d.la0, lb0 = d.lb0;
             const SeqDev *__restrict__ sd = &seqs[d.seq];  // only dereferenced on the rare paths
             u32 ub[PIPE_LPT], lbk[PIPE_LPT];  // absolute positions

@@ -48,6 +48,7 @@ struct TileOut {
     int k;
     int need_sum;
     int ops[GRB_MAX_OPS];
+    u32 *flags;  // context flag word (bit 0: invalid left range seen)
 };
 
 // ---- PTX: mbarrier + TMA 1-D bulk copy ---------------------------------------
@@ -217,6 +218,17 @@ __global__ void __launch_bounds__(TILE_TPB) k_tile(const SeqDev *__restrict__ se
         }
     }
     u32 mn_s = 0xffffffffu, mx_s = 0, mn_e = 0xffffffffu, mx_e = 0;
+    // a left with end <= start or end > 2^31-1 cannot exist in the reference (it panics); flag it and answer it
+    // as (0, 0), which overlaps nothing, so every later index stays in range
+    bool bad = false;
+#pragma unroll
+    for (int k = 0; k < TILE_LPT; k++) {
+        if (okv[k] && (b[k] <= a[k] || b[k] > 0x7fffffffu)) {
+            bad = true;
+            a[k] = b[k] = 0;
+        }
+    }
+    if (__any_sync(GRB_FULL, bad) && lane == 0) atomicOr(o.flags, 1u);
 #pragma unroll
     for (int k = 0; k < TILE_LPT; k++) {
         if (okv[k]) {
@@ -889,7 +901,7 @@ int launch_pipe(grb_ctx *ctx, const Batch &b, const u32 *ls, const u32 *le, cons
     u32 grid = (u32)ctx->sm_count;
     if (grid > b.ntiles) grid = b.ntiles;
     const int flags = (ctx->tile_mode ? 1 : 0) | (ctx->pipe_mode == 2 ? 2 : 0) | (ctx->pipe_mode == 3 ? 4 : 0);
-    k_map_pipe<FAST><<<grid, PIPE_THREADS, sizeof(PipeSmem), ctx->stream>>>(b.seqs, b.nseq, b.ntiles, ls, le, o.out, o.out_valid, flags);
+    k_map_pipe<FAST><<<grid, PIPE_THREADS, sizeof(PipeSmem), ctx->stream>>>(b.seqs, b.nseq, b.ntiles, ls, le, o.out, o.out_valid, flags, o.flags);
     GRB_LAUNCHED(ctx);
     return GRB_OK;
 }
@@ -962,10 +974,11 @@ int grb_count_overlaps_batch(grb_ctx *ctx, const grb_index *const *idx, const ui
     GRB_TRY(dc.stage(ctx, counts, b.total * 4));
     TileOut o;
     memset(&o, 0, sizeof(o));
+    o.flags = ctx->dev_flags;
     o.counts = dc.as<u32>();
     GRB_TRY(launch_tile<M_COUNTS, -1>(ctx, b, dls.as<u32>(), dle.as<u32>(), o));
     GRB_TRY(dc.finish(ctx));
-    if (dc.host) GRB_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+    if (dc.host) return grb_check_flags(ctx);
     return GRB_OK;
 }
 
@@ -992,6 +1005,7 @@ int grb_filter_overlaps_batch(grb_ctx *ctx, const grb_index *const *idx, const u
     GRB_TRY(dk.stage(ctx, keep, b.total));
     TileOut o;
     memset(&o, 0, sizeof(o));
+    o.flags = ctx->dev_flags;
     o.keep = dk.as<u8>();
     o.anti = anti;
     if (n_kept) {
@@ -1002,7 +1016,7 @@ int grb_filter_overlaps_batch(grb_ctx *ctx, const grb_index *const *idx, const u
     GRB_TRY(launch_tile<M_KEEP, -1>(ctx, b, dls.as<u32>(), dle.as<u32>(), o));
     GRB_TRY(dk.finish(ctx));
     if (n_kept) GRB_CUDA(ctx, cudaMemcpyAsync(n_kept, nk.p, 8, cudaMemcpyDeviceToHost, ctx->stream));
-    if (dk.host || n_kept) GRB_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+    if (dk.host || n_kept) return grb_check_flags(ctx);
     return GRB_OK;
 }
 
@@ -1063,6 +1077,7 @@ int grb_map_joins_f64_batch(grb_ctx *ctx, const grb_index *const *idx, const uin
     GRB_TRY(dval.stage(ctx, out_valid, b.total * (u64)k));
     TileOut o;
     memset(&o, 0, sizeof(o));
+    o.flags = ctx->dev_flags;
     o.out = dout.as<double>();
     o.out_valid = dval.as<u8>();
     o.k = k;
@@ -1104,7 +1119,7 @@ int grb_map_joins_f64_batch(grb_ctx *ctx, const grb_index *const *idx, const uin
     }
     GRB_TRY(dout.finish(ctx));
     GRB_TRY(dval.finish(ctx));
-    if (dout.host || dval.host) GRB_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+    if (dout.host || dval.host) return grb_check_flags(ctx);
     return GRB_OK;
 }
 
@@ -1146,6 +1161,8 @@ int grb_left_overlaps(grb_ctx *ctx, const grb_index *idx, const uint32_t *ls, co
         if ((rc = pp.alloc(ctx, nl * 4))) break;
         TileOut o;
         memset(&o, 0, sizeof(o));
+        o.flags = ctx->dev_flags;
+    o.flags = ctx->dev_flags;
         o.counts = counts.as<u32>();
         o.ub = ub.as<u32>();
         o.lb = lb.as<u32>();
@@ -1159,6 +1176,7 @@ int grb_left_overlaps(grb_ctx *ctx, const grb_index *idx, const uint32_t *ls, co
             rc = grb_fail(ctx, GRB_ERR_CUDA, "left_overlaps: %s", cudaGetErrorString(e));
             break;
         }
+        if ((rc = grb_check_flags(ctx))) break;  // an invalid left range: report before materialising anything
         p->np = np;
         if (grb_dev_malloc(ctx, (void **)&p->pos, np * 4 + 16) != cudaSuccess) {
             rc = grb_fail(ctx, GRB_ERR_OOM, "left_overlaps: cannot allocate %llu pairs on the device", (unsigned long long)np);

@@ -386,3 +386,29 @@ def test_sharded_units_bit_identical(eng, orc):
     gv = sharding.concat_in_order(units, vparts)
     assert (gv == wv).all()
     assert (got[wv == 1] == whole[wv == 1]).all()
+
+
+def test_invalid_left_ranges_are_reported(eng):
+    """The reference cannot construct a range with end <= start (RangeEmpty::new asserts, ranges/mod.rs:30) and
+    panics on coordinates beyond i32 (ranges/coitrees.rs:53-54): the kernels flag such lefts, answer them as empty
+    groups (no out-of-range access) and the call reports GRB_ERR_INVALID_RANGE."""
+    import granges_b200 as gb
+
+    ctx = eng.ctx
+    c = random_case(123, 3000, 4000, span=50_000, sorted_left=True)
+    ix = ctx.index_build(c["rs"], c["re"]).set_scores(c["scores"])
+    good, gv = ctx.map_joins(ix, c["ls"], c["le"], ["mean"])
+    for bad_end in (lambda s: s, lambda s: np.uint32(2**31 + 7)):
+        ls, le = c["ls"].copy(), c["le"].copy()
+        le[1500] = bad_end(ls[1500])
+        for ops in (["mean"], ["min", "median", "sum"]):  # pipelined kernel / tile + sweep kernels
+            with pytest.raises(gb.GRangesError) as ei:
+                ctx.map_joins(ix, ls, le, ops)
+            assert ei.value.code == -2
+        with pytest.raises(gb.GRangesError):
+            ctx.count_overlaps(ix, ls, le)
+        with pytest.raises(gb.GRangesError):
+            ctx.left_overlaps(ix, ls, le)
+    # the flag is cleared by the failing call: the next valid call succeeds and is unchanged
+    again, av = ctx.map_joins(ix, c["ls"], c["le"], ["mean"])
+    assert (av == gv).all() and (again[gv == 1] == good[gv == 1]).all()
