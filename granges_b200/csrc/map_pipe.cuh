@@ -26,10 +26,10 @@ constexpr int PIPE_NC = PIPE_GROUPS * PIPE_NCG;  // consumer warps
 constexpr int PIPE_LPT = TILE / (PIPE_NCG * 32);  // consecutive lefts per consumer thread
 constexpr int PIPE_NSURV = 4;  // surveyor warps (tile j goes to surveyor j % PIPE_NSURV)
 constexpr int PIPE_THREADS = (PIPE_NC + 2 + PIPE_NSURV) * 32;
-constexpr int PIPE_LSTAGES = 6;
-constexpr int PIPE_WSTAGES = 5;
+constexpr int PIPE_LSTAGES = 8;
+constexpr int PIPE_WSTAGES = 4;
 constexpr u32 PIPE_WIN = 1280;  // keys (and prefixes) per staged window
-constexpr u32 PIPE_LUT = 512;   // bin-table entries per staged slice
+constexpr u32 PIPE_LUT = 640;   // bin-table entries per staged slice
 constexpr int PIPE_MAXSEQ = 32; // seqnames per launch (their descriptors live in shared memory)
 
 struct PipeSeq {
