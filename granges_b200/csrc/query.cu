@@ -461,8 +461,6 @@ __global__ void __launch_bounds__(TILE_TPB) k_tile(const SeqDev *__restrict__ se
 // ---- the sweep kernels ----------------------------------------------------------------
 
 constexpr int SW_TPB = 256;
-constexpr int SW_WARPS = SW_TPB / 32;
-constexpr u32 MED_CAP = 256;  // scores a warp keeps in shared memory for the median
 
 struct SweepOut {
     double *out;
@@ -489,157 +487,7 @@ __device__ __forceinline__ bool score_valid(const SeqDev *sd, u32 j) {
     return (sd->vbits_a[j >> 5] >> (j & 31)) & 1u;
 }
 
-// One warp per left: sweep backward from ub until `count` overlapping rights were seen.
-__global__ void __launch_bounds__(SW_TPB) k_sweep(const SeqDev *__restrict__ seqs, int nseq, u64 total,
-                                                  const u32 *__restrict__ ls, const u32 *__restrict__ le,
-                                                  const u32 *__restrict__ ubv, const u32 *__restrict__ lbv, const SweepOut o) {
-    __shared__ double s_buf[SW_WARPS][MED_CAP];
-    __shared__ double s_med[SW_WARPS][2];
-    const u32 lane = lane_id(), warp = threadIdx.x >> 5;
-    const u64 g = (u64)blockIdx.x * SW_WARPS + warp;
-    if (g >= total) return;
-    const SeqDev *sd = &seqs[find_seq_by_left(seqs, nseq, g)];
-    const u32 u = ubv[g], count = u - lbv[g];
-    const u32 lstart = ls[g], lend = le[g];
-    const u32 *__restrict__ ends = sd->ends;
-    const u32 lt = (1u << lane) - 1;
-
-    u32 found = 0, nvalid = 0, nfinite = 0;
-    double sum = 0.0, mn = 0.0, mx = 0.0;
-    bool have = false;
-    u64 bp = 0;
-    long long cb = u ? (long long)((u - 1) & ~31u) : -1;
-    while (found < count && cb >= 0) {
-        if (sd->bme[cb >> GRB_BME_SHIFT] > lstart) {
-            u32 j = (u32)cb + lane;
-            bool in = j < u;
-            u32 e = in ? ends[j] : 0u;
-            bool hit = in && e > lstart;
-            u32 hm = __ballot_sync(GRB_FULL, hit);
-            bool v = hit && score_valid(sd, j);
-            u32 vm = __ballot_sync(GRB_FULL, v);
-            if (hit && o.want_bp) bp += (u64)(min(lend, e) - max(lstart, sd->starts[j]));
-            if (v) {
-                double x = sd->score_a[j];
-                sum += x;
-                if (isfinite(x)) {
-                    if (!have) {
-                        mn = mx = x;
-                        have = true;
-                    } else {
-                        mn = fmin(mn, x);
-                        mx = fmax(mx, x);
-                    }
-                }
-                if (o.want_median) {
-                    u32 slot = nvalid + __popc(vm & lt);
-                    if (slot < MED_CAP) s_buf[warp][slot] = x;
-                }
-            }
-            found += __popc(hm);
-            nvalid += __popc(vm);
-        }
-        cb -= 32;
-    }
-    // warp reductions (fixed shuffle order: deterministic)
-#pragma unroll
-    for (int s = 16; s; s >>= 1) {
-        sum += __shfl_xor_sync(GRB_FULL, sum, s);
-        double omn = __shfl_xor_sync(GRB_FULL, mn, s), omx = __shfl_xor_sync(GRB_FULL, mx, s);
-        bool ohave = __shfl_xor_sync(GRB_FULL, (int)have, s);
-        if (ohave) {
-            if (have) {
-                mn = fmin(mn, omn);
-                mx = fmax(mx, omx);
-            } else {
-                mn = omn;
-                mx = omx;
-                have = true;
-            }
-        }
-        bp += __shfl_xor_sync(GRB_FULL, bp, s);
-    }
-    (void)nfinite;
-    // median of up to MED_CAP values by rank counting
-    bool heavy = false;
-    if (o.want_median && nvalid) {
-        if (nvalid > MED_CAP) {
-            heavy = true;
-        } else {
-            __syncwarp();
-            const u32 m = nvalid, k1 = (m - 1) >> 1, k2 = m >> 1;
-            for (u32 e = lane; e < m; e += 32) {
-                double x = s_buf[warp][e];
-                u32 r = 0;
-                for (u32 q = 0; q < m; q++) {
-                    double y = s_buf[warp][q];
-                    r += (y < x || (y == x && q < e)) ? 1u : 0u;
-                }
-                if (r == k1) s_med[warp][0] = x;
-                if (r == k2) s_med[warp][1] = x;
-            }
-            __syncwarp();
-        }
-    }
-    if (lane == 0) {
-        const bool sweep_sums = sd->sum_mode == GRB_SUM_SWEEP;
-        for (int c = 0; c < o.k; c++) {
-            double r = 0.0;
-            u8 ok = 0;
-            bool mine = true;
-            switch (o.ops[c]) {
-                case GRB_OP_SUM:
-                    mine = sweep_sums;
-                    r = sum;
-                    ok = 1;
-                    break;
-                case GRB_OP_SUM_NOT_EMPTY:
-                    mine = sweep_sums;
-                    ok = nvalid != 0;
-                    r = ok ? sum : 0.0;
-                    break;
-                case GRB_OP_MEAN:
-                    mine = sweep_sums;
-                    ok = nvalid != 0;
-                    r = ok ? sum / (double)nvalid : 0.0;
-                    break;
-                case GRB_OP_MIN:
-                    ok = have;
-                    r = have ? mn : 0.0;
-                    break;
-                case GRB_OP_MAX:
-                    ok = have;
-                    r = have ? mx : 0.0;
-                    break;
-                case GRB_OP_MEDIAN:
-                    if (heavy) {
-                        mine = false;
-                    } else if (nvalid) {
-                        ok = 1;
-                        r = (nvalid & 1) ? s_med[warp][1] : (s_med[warp][0] + s_med[warp][1]) / 2.0;
-                    }
-                    break;
-                case GRB_OP_OVERLAP_BP:
-                    ok = 1;
-                    r = (double)bp;
-                    break;
-                default:
-                    mine = false;
-                    break;
-            }
-            if (mine) {
-                o.out[g * (u64)o.k + c] = r;
-                o.out_valid[g * (u64)o.k + c] = ok;
-            }
-        }
-        if (heavy) {
-            u32 slot = atomicAdd(o.heavy_count, 1u);
-            o.heavy_list[slot] = (u32)g;  // the host checks total < 2^32 when a median is requested
-        }
-    }
-}
-
-// Median of groups with more than MED_CAP valid scores: one CTA per such left, MSB-first radix
+// Median of groups too large for the in-group quickselect of k_sweep2: one CTA per such left, MSB-first radix
 // select (8 bits per pass) over the order-preserving integer image of the scores, re-sweeping the
 // candidates instead of materialising them.
 __global__ void __launch_bounds__(SW_TPB) k_median_heavy(const SeqDev *__restrict__ seqs, int nseq, const u32 *__restrict__ ls,
@@ -712,37 +560,6 @@ __global__ void __launch_bounds__(SW_TPB) k_median_heavy(const SeqDev *__restric
             }
         }
         __syncthreads();
-    }
-}
-
-// Emit pass of left_overlaps: positions (start order) of the members of every group, ascending,
-// which IS sort_ranges order (join.rs:121-128) because the index is sorted by (start, end, index).
-__global__ void __launch_bounds__(SW_TPB) k_emit(const SeqDev *__restrict__ seqs, int nseq, u64 total,
-                                                 const u32 *__restrict__ ls, const u32 *__restrict__ ubv,
-                                                 const u32 *__restrict__ lbv, const u64 *__restrict__ offsets,
-                                                 u32 *__restrict__ pos) {
-    const u32 lane = lane_id(), warp = threadIdx.x >> 5;
-    const u64 g = (u64)blockIdx.x * SW_WARPS + warp;
-    if (g >= total) return;
-    const SeqDev *sd = &seqs[find_seq_by_left(seqs, nseq, g)];
-    const u32 u = ubv[g], count = u - lbv[g];
-    const u32 lstart = ls[g];
-    const u32 *__restrict__ ends = sd->ends;
-    const u64 off = offsets[g];
-    u32 found = 0;
-    long long cb = u ? (long long)((u - 1) & ~31u) : -1;
-    while (found < count && cb >= 0) {
-        if (sd->bme[cb >> GRB_BME_SHIFT] > lstart) {
-            u32 j = (u32)cb + lane;
-            bool hit = j < u && ends[j] > lstart;
-            u32 hm = __ballot_sync(GRB_FULL, hit);
-            if (hit) {
-                u32 above = lane == 31 ? 0u : __popc(hm >> (lane + 1));
-                pos[off + (u64)(count - 1 - (found + above))] = j;
-            }
-            found += __popc(hm);
-        }
-        cb -= 32;
     }
 }
 
