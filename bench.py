@@ -417,7 +417,7 @@ def main():
         torch.cuda.empty_cache()
 
         def e2e_step():
-            hs = [ctx.index_build(a.numpy().view(np.uint32), b.numpy().view(np.uint32)).set_scores(c.numpy()) for a, b, c in h_rights]
+            hs = ctx.index_build_batch([(a.numpy().view(np.uint32), b.numpy().view(np.uint32), c.numpy()) for a, b, c in h_rights])
             ctx.map_joins_batch(hs, offs, h_ls.numpy().view(np.uint32), h_le.numpy().view(np.uint32), ops, out=h_out.numpy(),
                                 out_valid=h_ov.numpy())
             chk = float(h_out[0, 0])  # the result is on the host

@@ -36,6 +36,8 @@ SIGNATURES = {
     "grb_ctx_launch_count": (C.c_uint64, [vp]),
     "grb_ctx_sm_count": (C.c_int, [vp]),
     "grb_index_build": (C.c_int, [vp, vp, vp, vp, C.c_size_t, C.POINTER(vp)]),
+    "grb_index_build_batch": (C.c_int, [vp, C.c_int, C.POINTER(vp), C.POINTER(vp), C.POINTER(C.c_size_t), C.POINTER(vp), C.POINTER(vp),
+                                         C.POINTER(vp)]),
     "grb_index_destroy": (None, [vp]),
     "grb_index_len": (C.c_size_t, [vp]),
     "grb_index_set_scores": (C.c_int, [vp, vp, vp, C.c_size_t]),

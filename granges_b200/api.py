@@ -200,6 +200,30 @@ class Context:
         self._check(_capi.lib().grb_index_build(self.h, ps, pe, pi, n, C.byref(h)))
         return Index(self, h)
 
+    def index_build_batch(self, rights):
+        """Indexes of a whole right-hand GRanges: `rights` = [(starts, ends[, scores[, valid]]) per seqname].
+        Host-to-device copies of one seqname overlap the indexing of the previous one."""
+        nseq = len(rights)
+        keep, ps, pe, psc, pva, ns = [], [], [], [], [], []
+        any_scores = any(len(r) > 2 and r[2] is not None for r in rights)
+        any_valid = any(len(r) > 3 and r[3] is not None for r in rights)
+        for r in rights:
+            a, ka, _ = _arg(r[0], np.uint32)
+            b, kb, _ = _arg(r[1], np.uint32)
+            c, kc, _ = _arg(r[2] if len(r) > 2 else None, np.float64)
+            d, kd, _ = _arg(r[3] if len(r) > 3 else None, np.uint8)
+            keep += [ka, kb, kc, kd]
+            ps.append(a)
+            pe.append(b)
+            psc.append(c)
+            pva.append(d)
+            ns.append(len(ka))
+        VP = C.c_void_p * nseq
+        out = VP()
+        self._check(_capi.lib().grb_index_build_batch(self.h, nseq, VP(*ps), VP(*pe), (C.c_size_t * nseq)(*ns),
+                                                      VP(*psc) if any_scores else None, VP(*pva) if any_valid else None, out))
+        return [Index(self, C.c_void_p(h)) for h in out]
+
     # -- helpers
     @staticmethod
     def _ops(ops):

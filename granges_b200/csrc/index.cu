@@ -18,6 +18,8 @@
 #include <math.h>
 #include <stdlib.h>
 
+#include <vector>
+
 #include "common.cuh"
 
 namespace {
@@ -559,6 +561,96 @@ int grb_index_set_scores(grb_index *ix, const double *by_data_idx, const uint8_t
     }
     GRB_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
     return GRB_OK;
+}
+
+// Build the indexes of a whole right-hand GRanges (one per seqname) with the host-to-device copies of
+// seqname s+1 running on a second stream while seqname s is sorted and indexed.
+int grb_index_build_batch(grb_ctx *ctx, int nseq, const uint32_t *const *starts, const uint32_t *const *ends,
+                          const size_t *n, const double *const *scores, const uint8_t *const *valid, grb_index **out) {
+    if (!ctx || nseq < 0 || (nseq && (!starts || !ends || !n || !out))) return GRB_ERR_INVALID_ARG;
+    GRB_CUDA(ctx, cudaSetDevice(ctx->device));
+    for (int s = 0; s < nseq; s++) out[s] = nullptr;
+    cudaStream_t copy_stream;
+    GRB_CUDA(ctx, cudaStreamCreateWithFlags(&copy_stream, cudaStreamNonBlocking));
+    struct Stage {
+        u32 *st = nullptr, *en = nullptr;
+        double *sc = nullptr;
+        u8 *va = nullptr;
+        cudaEvent_t ready = nullptr;
+    };
+    std::vector<Stage> stg((size_t)nseq);
+    int rc = GRB_OK;
+    // everything already enqueued on the context's stream (e.g. frees of earlier buffers) precedes the copies
+    cudaEvent_t start_ev;
+    cudaEventCreateWithFlags(&start_ev, cudaEventDisableTiming);
+    cudaEventRecord(start_ev, ctx->stream);
+    cudaStreamWaitEvent(copy_stream, start_ev, 0);
+    auto enqueue_copy = [&](int s) -> int {
+        Stage &g = stg[s];
+        const size_t m = n[s];
+        cudaEventCreateWithFlags(&g.ready, cudaEventDisableTiming);
+        if (m == 0) {
+            cudaEventRecord(g.ready, copy_stream);
+            return GRB_OK;
+        }
+        const bool dev_in = grb_is_device_ptr(starts[s]);
+        if (!dev_in) {
+            if (cudaMallocAsync((void **)&g.st, m * 4, copy_stream) != cudaSuccess || cudaMallocAsync((void **)&g.en, m * 4, copy_stream) != cudaSuccess)
+                return grb_fail(ctx, GRB_ERR_OOM, "index_build_batch: staging allocation failed");
+            cudaMemcpyAsync(g.st, starts[s], m * 4, cudaMemcpyHostToDevice, copy_stream);
+            cudaMemcpyAsync(g.en, ends[s], m * 4, cudaMemcpyHostToDevice, copy_stream);
+            if (scores && scores[s]) {
+                if (cudaMallocAsync((void **)&g.sc, m * 8, copy_stream) != cudaSuccess)
+                    return grb_fail(ctx, GRB_ERR_OOM, "index_build_batch: staging allocation failed");
+                cudaMemcpyAsync(g.sc, scores[s], m * 8, cudaMemcpyHostToDevice, copy_stream);
+                if (valid && valid[s]) {
+                    if (cudaMallocAsync((void **)&g.va, m, copy_stream) != cudaSuccess)
+                        return grb_fail(ctx, GRB_ERR_OOM, "index_build_batch: staging allocation failed");
+                    cudaMemcpyAsync(g.va, valid[s], m, cudaMemcpyHostToDevice, copy_stream);
+                }
+            }
+        }
+        cudaEventRecord(g.ready, copy_stream);
+        return GRB_OK;
+    };
+    if (nseq) rc = enqueue_copy(0);
+    for (int s = 0; s < nseq && rc == GRB_OK; s++) {
+        if (s + 1 < nseq) rc = enqueue_copy(s + 1);
+        if (rc != GRB_OK) break;
+        Stage &g = stg[s];
+        cudaStreamWaitEvent(ctx->stream, g.ready, 0);
+        const uint32_t *ps = g.st ? g.st : starts[s], *pe = g.en ? g.en : ends[s];
+        rc = grb_index_build(ctx, ps, pe, nullptr, n[s], &out[s]);
+        if (rc == GRB_OK && scores && scores[s]) {
+            const double *psc = g.sc ? g.sc : scores[s];
+            const uint8_t *pva = (valid && valid[s]) ? (g.va ? g.va : valid[s]) : nullptr;
+            rc = grb_index_set_scores(out[s], psc, pva, n[s]);
+        }
+        grb_dev_free(ctx, g.st);
+        grb_dev_free(ctx, g.en);
+        grb_dev_free(ctx, g.sc);
+        grb_dev_free(ctx, g.va);
+        g.st = g.en = nullptr;
+        g.sc = nullptr;
+        g.va = nullptr;
+    }
+    cudaStreamSynchronize(copy_stream);
+    for (auto &g : stg) {
+        grb_dev_free(ctx, g.st);
+        grb_dev_free(ctx, g.en);
+        grb_dev_free(ctx, g.sc);
+        grb_dev_free(ctx, g.va);
+        if (g.ready) cudaEventDestroy(g.ready);
+    }
+    cudaEventDestroy(start_ev);
+    cudaStreamDestroy(copy_stream);
+    if (rc != GRB_OK) {
+        for (int s = 0; s < nseq; s++) {
+            grb_index_destroy(out[s]);
+            out[s] = nullptr;
+        }
+    }
+    return rc;
 }
 
 int grb_index_copy_sorted(const grb_index *ix, uint32_t *starts, uint32_t *ends, uint64_t *data_idx) {

@@ -116,6 +116,12 @@ size_t grb_index_len(const grb_index *idx);
  * valid[i] == 0 marks None (BED "." scores, src/io/parsers/bed/mod.rs:37-73).  Also builds the
  * exact fixed-point prefix sums SUM / MEAN are answered from. */
 int grb_index_set_scores(grb_index *idx, const double *by_data_idx, const uint8_t *valid, size_t n_data);
+/* GRanges::into_coitrees for the whole right-hand GRanges (src/granges.rs:1365-1402 loops over the
+ * seqnames) plus the score extraction: builds nseq indexes (data index = position within the seqname's
+ * arrays), copying seqname s+1 to the device while seqname s is being indexed.  scores / valid may be NULL
+ * (no data container), as may individual entries.  n[s] may be 0.  out receives nseq handles. */
+int grb_index_build_batch(grb_ctx *ctx, int nseq, const uint32_t *const *starts, const uint32_t *const *ends,
+                          const size_t *n, const double *const *scores, const uint8_t *const *valid, grb_index **out);
 /* Sorted iteration, COITrees::iter_ranges (src/ranges/coitrees.rs:154-170): copies the index
  * order out (any pointer may be NULL). */
 int grb_index_copy_sorted(const grb_index *idx, uint32_t *starts, uint32_t *ends, uint64_t *data_idx);

@@ -412,3 +412,21 @@ def test_invalid_left_ranges_are_reported(eng):
     # the flag is cleared by the failing call: the next valid call succeeds and is unchanged
     again, av = ctx.map_joins(ix, c["ls"], c["le"], ["mean"])
     assert (av == gv).all() and (again[gv == 1] == good[gv == 1]).all()
+
+
+def test_index_build_batch(eng, orc):
+    """grb_index_build_batch (copies of one seqname overlap the indexing of the previous) == per-seqname builds."""
+    ctx = eng.ctx
+    cases = [random_case(400 + s, 2000, nr, span=80_000, null_frac=nf) for s, (nr, nf) in enumerate([(5000, 0.0), (0, 0.0), (3000, 0.2), (1, 0.0)])]
+    rights = [(c["rs"], c["re"], c["scores"], c["valid"]) for c in cases]
+    idxs = ctx.index_build_batch(rights)
+    assert [len(ix) for ix in idxs] == [len(c["rs"]) for c in cases]
+    ops = ["mean", "median", "count", "sum"]
+    for c, ix in zip(cases, idxs):
+        single = eng.build(c["rs"], c["re"], None, c["scores"], c["valid"])
+        a = ctx.map_joins(ix, c["ls"], c["le"], ops)
+        b = ctx.map_joins(single, c["ls"], c["le"], ops)
+        assert (a[1] == b[1]).all() and (a[0][a[1] == 1] == b[0][b[1] == 1]).all()
+    # no data container at all
+    bare = ctx.index_build_batch([(c["rs"], c["re"]) for c in cases])
+    assert (ctx.count_overlaps(bare[0], cases[0]["ls"], cases[0]["le"]) == ctx.count_overlaps(idxs[0], cases[0]["ls"], cases[0]["le"])).all()
