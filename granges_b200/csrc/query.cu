@@ -843,9 +843,80 @@ int grb_filter_overlaps(grb_ctx *ctx, const grb_index *idx, const uint32_t *ls, 
     return grb_filter_overlaps_batch(ctx, &idx, off, 1, ls, le, anti, keep, n_kept);
 }
 
+static int map_joins_impl(grb_ctx *ctx, const grb_index *const *idx, const uint64_t *left_offsets, int nseq, const uint32_t *ls,
+                          const uint32_t *le, const int *ops, int k, double *out, uint8_t *out_valid, bool allow_chunks);
+
+// Host buffers, many seqnames: run the seqnames in chunks so that the upload of the next chunk's lefts, the kernels
+// of the current one and the download of the previous chunk's results overlap (PCIe is full duplex).
+static int map_joins_host_chunked(grb_ctx *ctx, const grb_index *const *idx, const uint64_t *left_offsets, int nseq,
+                                  const uint32_t *ls, const uint32_t *le, const int *ops, int k, double *out, uint8_t *out_valid) {
+    const u64 total = left_offsets[nseq];
+    TempBuf d_ls, d_le, d_out, d_val;
+    GRB_TRY(d_ls.alloc(ctx, total * 4));
+    GRB_TRY(d_le.alloc(ctx, total * 4));
+    GRB_TRY(d_out.alloc(ctx, total * (u64)k * 8));
+    GRB_TRY(d_val.alloc(ctx, total * (u64)k));
+    // chunks of whole seqnames, about an eighth of the lefts each
+    std::vector<int> cuts{0};
+    const u64 target = total / 8 + 1;
+    for (int s = 1; s < nseq; s++)
+        if (left_offsets[s] - left_offsets[cuts.back()] >= target) cuts.push_back(s);
+    cuts.push_back(nseq);
+    const int nchunks = (int)cuts.size() - 1;
+    cudaStream_t h2d, d2h;
+    GRB_CUDA(ctx, cudaStreamCreateWithFlags(&h2d, cudaStreamNonBlocking));
+    GRB_CUDA(ctx, cudaStreamCreateWithFlags(&d2h, cudaStreamNonBlocking));
+    std::vector<cudaEvent_t> up((size_t)nchunks), done((size_t)nchunks);
+    cudaEvent_t ready;
+    cudaEventCreateWithFlags(&ready, cudaEventDisableTiming);
+    cudaEventRecord(ready, ctx->stream);  // the staging buffers exist from here on
+    cudaStreamWaitEvent(h2d, ready, 0);
+    for (int c = 0; c < nchunks; c++) {
+        cudaEventCreateWithFlags(&up[c], cudaEventDisableTiming);
+        cudaEventCreateWithFlags(&done[c], cudaEventDisableTiming);
+        const u64 a = left_offsets[cuts[c]], b = left_offsets[cuts[c + 1]];
+        if (b > a) {
+            cudaMemcpyAsync(d_ls.as<u32>() + a, ls + a, (b - a) * 4, cudaMemcpyHostToDevice, h2d);
+            cudaMemcpyAsync(d_le.as<u32>() + a, le + a, (b - a) * 4, cudaMemcpyHostToDevice, h2d);
+        }
+        cudaEventRecord(up[c], h2d);
+    }
+    int rc = GRB_OK;
+    for (int c = 0; c < nchunks && rc == GRB_OK; c++) {
+        const u64 a = left_offsets[cuts[c]], b = left_offsets[cuts[c + 1]];
+        cudaStreamWaitEvent(ctx->stream, up[c], 0);
+        // absolute offsets + whole-array pointers: tiles stay aligned to multiples of 1024 lefts
+        rc = map_joins_impl(ctx, idx ? idx + cuts[c] : nullptr, left_offsets + cuts[c], cuts[c + 1] - cuts[c], d_ls.as<u32>(),
+                            d_le.as<u32>(), ops, k, d_out.as<double>(), d_val.as<u8>(), false);
+        cudaEventRecord(done[c], ctx->stream);
+        cudaStreamWaitEvent(d2h, done[c], 0);
+        if (b > a && rc == GRB_OK) {
+            cudaMemcpyAsync(out + a * (u64)k, d_out.as<double>() + a * (u64)k, (b - a) * (u64)k * 8, cudaMemcpyDeviceToHost, d2h);
+            cudaMemcpyAsync(out_valid + a * (u64)k, d_val.as<u8>() + a * (u64)k, (b - a) * (u64)k, cudaMemcpyDeviceToHost, d2h);
+        }
+    }
+    cudaError_t e1 = cudaStreamSynchronize(h2d), e2 = cudaStreamSynchronize(d2h), e3 = cudaStreamSynchronize(ctx->stream);
+    for (int c = 0; c < nchunks; c++) {
+        cudaEventDestroy(up[c]);
+        cudaEventDestroy(done[c]);
+    }
+    cudaEventDestroy(ready);
+    cudaStreamDestroy(h2d);
+    cudaStreamDestroy(d2h);
+    if (rc != GRB_OK) return rc;
+    if (e1 != cudaSuccess || e2 != cudaSuccess || e3 != cudaSuccess)
+        return grb_fail(ctx, GRB_ERR_CUDA, "map_joins: %s", cudaGetErrorString(e1 != cudaSuccess ? e1 : e2 != cudaSuccess ? e2 : e3));
+    return grb_check_flags(ctx);
+}
+
 int grb_map_joins_f64_batch(grb_ctx *ctx, const grb_index *const *idx, const uint64_t *left_offsets, int nseq,
                             const uint32_t *ls, const uint32_t *le, const int *ops, int k, double *out,
                             uint8_t *out_valid) {
+    return map_joins_impl(ctx, idx, left_offsets, nseq, ls, le, ops, k, out, out_valid, true);
+}
+
+static int map_joins_impl(grb_ctx *ctx, const grb_index *const *idx, const uint64_t *left_offsets, int nseq, const uint32_t *ls,
+                          const uint32_t *le, const int *ops, int k, double *out, uint8_t *out_valid, bool allow_chunks) {
     GRB_TRY(enter(ctx));
     if (!left_offsets || !ops) return grb_fail(ctx, GRB_ERR_INVALID_ARG, "map_joins: NULL left_offsets / ops");
     if (k < 1 || k > GRB_MAX_OPS) return grb_fail(ctx, GRB_ERR_INVALID_ARG, "map_joins: k must be in [1, %d]", GRB_MAX_OPS);
@@ -886,6 +957,9 @@ int grb_map_joins_f64_batch(grb_ctx *ctx, const grb_index *const *idx, const uin
     GRB_TRY(make_batch(ctx, idx, left_offsets, nseq, &b));
     if (b.total == 0) return GRB_OK;
     if (!ls || !le || !out || !out_valid) return grb_fail(ctx, GRB_ERR_INVALID_ARG, "map_joins: NULL buffer");
+    if (allow_chunks && nseq >= 2 && b.total >= (1u << 22) && !grb_is_device_ptr(ls) && !grb_is_device_ptr(le) &&
+        !grb_is_device_ptr(out) && !grb_is_device_ptr(out_valid))
+        return map_joins_host_chunked(ctx, idx, left_offsets, nseq, ls, le, ops, k, out, out_valid);
     InBuf dls, dle;
     OutBuf dout, dval;
     GRB_TRY(dls.stage(ctx, ls, b.total * 4));

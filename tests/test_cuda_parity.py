@@ -430,3 +430,33 @@ def test_index_build_batch(eng, orc):
     # no data container at all
     bare = ctx.index_build_batch([(c["rs"], c["re"]) for c in cases])
     assert (ctx.count_overlaps(bare[0], cases[0]["ls"], cases[0]["le"]) == ctx.count_overlaps(idxs[0], cases[0]["ls"], cases[0]["le"])).all()
+
+
+def test_host_buffers_chunked_pipeline(eng):
+    """Large host-buffer calls run seqname chunks through an upload / compute / download pipeline; the result must be
+    identical to the device-buffer call (single launch sequence), also with several reductions and ragged seqnames."""
+    import torch
+
+    ctx = eng.ctx
+    rng = np.random.default_rng(5)
+    nls = [900_001, 1_200_003, 0, 1_500_000, 700_002, 999_999]
+    idxs, lss, les = [], [], []
+    for s, nl in enumerate(nls):
+        nr = 400_000 + 1000 * s
+        rs = np.sort(rng.integers(0, 50_000_000, nr)).astype(np.uint32)
+        re = (rs + rng.integers(1, 1000, nr)).astype(np.uint32)
+        idxs.append(None if s == 4 else ctx.index_build(rs, re).set_scores(rng.random(nr)))
+        ls = np.sort(rng.integers(0, 50_000_000, nl)).astype(np.uint32)
+        lss.append(ls)
+        les.append((ls + rng.integers(1, 1000, nl)).astype(np.uint32))
+    off = np.concatenate([[0], np.cumsum(nls)]).astype(np.uint64)
+    ls, le = np.concatenate(lss), np.concatenate(les)
+    assert len(ls) >= 1 << 22
+    dls, dle = torch.from_numpy(ls.view(np.int32)).cuda(), torch.from_numpy(le.view(np.int32)).cuda()
+    for ops in (["mean"], ["max", "mean", "count"]):
+        host_out, host_v = ctx.map_joins_batch(idxs, off, ls, le, ops)            # chunked host path
+        dev_out, dev_v = ctx.map_joins_batch(idxs, off, dls, dle, ops)            # device path
+        ctx.sync()
+        assert (host_v == dev_v.cpu().numpy()).all()
+        m = host_v == 1
+        assert (host_out[m] == dev_out.cpu().numpy()[m]).all()
