@@ -18,6 +18,7 @@
 #include <math.h>
 #include <stdlib.h>
 
+#include <thread>
 #include <vector>
 
 #include "common.cuh"
@@ -563,87 +564,64 @@ int grb_index_set_scores(grb_index *ix, const double *by_data_idx, const uint8_t
     return GRB_OK;
 }
 
-// Build the indexes of a whole right-hand GRanges (one per seqname) with the host-to-device copies of
-// seqname s+1 running on a second stream while seqname s is sorted and indexed.
+// Build the indexes of a whole right-hand GRanges (one per seqname).  A build is a chain of small kernels with a
+// few host round trips (sortedness, digit masks, score statistics), so one seqname cannot fill the GPU or the
+// PCIe link on its own: up to four host threads, each with its own stream (a private clone of the context),
+// take the seqnames round-robin, and the uploads and kernels of different seqnames overlap.  The finished
+// indexes are handed to the caller's context.
 int grb_index_build_batch(grb_ctx *ctx, int nseq, const uint32_t *const *starts, const uint32_t *const *ends,
                           const size_t *n, const double *const *scores, const uint8_t *const *valid, grb_index **out) {
     if (!ctx || nseq < 0 || (nseq && (!starts || !ends || !n || !out))) return GRB_ERR_INVALID_ARG;
     GRB_CUDA(ctx, cudaSetDevice(ctx->device));
     for (int s = 0; s < nseq; s++) out[s] = nullptr;
-    cudaStream_t copy_stream;
-    GRB_CUDA(ctx, cudaStreamCreateWithFlags(&copy_stream, cudaStreamNonBlocking));
-    struct Stage {
-        u32 *st = nullptr, *en = nullptr;
-        double *sc = nullptr;
-        u8 *va = nullptr;
-        cudaEvent_t ready = nullptr;
-    };
-    std::vector<Stage> stg((size_t)nseq);
-    int rc = GRB_OK;
-    // everything already enqueued on the context's stream (e.g. frees of earlier buffers) precedes the copies
-    cudaEvent_t start_ev;
-    cudaEventCreateWithFlags(&start_ev, cudaEventDisableTiming);
-    cudaEventRecord(start_ev, ctx->stream);
-    cudaStreamWaitEvent(copy_stream, start_ev, 0);
-    auto enqueue_copy = [&](int s) -> int {
-        Stage &g = stg[s];
-        const size_t m = n[s];
-        cudaEventCreateWithFlags(&g.ready, cudaEventDisableTiming);
-        if (m == 0) {
-            cudaEventRecord(g.ready, copy_stream);
-            return GRB_OK;
+    if (nseq == 0) return GRB_OK;
+    GRB_CUDA(ctx, cudaStreamSynchronize(ctx->stream));  // earlier work on the caller's stream precedes the workers'
+    const int nworkers = nseq < 4 ? nseq : 4;
+    std::vector<grb_ctx> clones((size_t)nworkers);
+    std::vector<int> rcs((size_t)nworkers, GRB_OK);
+    for (int w = 0; w < nworkers; w++) {
+        clones[w] = *ctx;  // shares the device, the pool and the zero / flag words
+        clones[w].batch_dev = nullptr;
+        clones[w].batch_host = nullptr;
+        clones[w].batch_bytes = clones[w].batch_cap = 0;
+        clones[w].launches = 0;
+        clones[w].err[0] = 0;
+        if (cudaStreamCreateWithFlags(&clones[w].own_stream, cudaStreamNonBlocking) != cudaSuccess) {
+            for (int v = 0; v < w; v++) cudaStreamDestroy(clones[v].own_stream);
+            return grb_fail(ctx, GRB_ERR_CUDA, "index_build_batch: cannot create a stream");
         }
-        const bool dev_in = grb_is_device_ptr(starts[s]);
-        if (!dev_in) {
-            if (cudaMallocAsync((void **)&g.st, m * 4, copy_stream) != cudaSuccess || cudaMallocAsync((void **)&g.en, m * 4, copy_stream) != cudaSuccess)
-                return grb_fail(ctx, GRB_ERR_OOM, "index_build_batch: staging allocation failed");
-            cudaMemcpyAsync(g.st, starts[s], m * 4, cudaMemcpyHostToDevice, copy_stream);
-            cudaMemcpyAsync(g.en, ends[s], m * 4, cudaMemcpyHostToDevice, copy_stream);
-            if (scores && scores[s]) {
-                if (cudaMallocAsync((void **)&g.sc, m * 8, copy_stream) != cudaSuccess)
-                    return grb_fail(ctx, GRB_ERR_OOM, "index_build_batch: staging allocation failed");
-                cudaMemcpyAsync(g.sc, scores[s], m * 8, cudaMemcpyHostToDevice, copy_stream);
-                if (valid && valid[s]) {
-                    if (cudaMallocAsync((void **)&g.va, m, copy_stream) != cudaSuccess)
-                        return grb_fail(ctx, GRB_ERR_OOM, "index_build_batch: staging allocation failed");
-                    cudaMemcpyAsync(g.va, valid[s], m, cudaMemcpyHostToDevice, copy_stream);
-                }
+        clones[w].stream = clones[w].own_stream;
+    }
+    auto work = [&](int w) {
+        grb_ctx *c = &clones[w];
+        cudaSetDevice(c->device);
+        for (int s = w; s < nseq; s += nworkers) {
+            int rc = grb_index_build(c, starts[s], ends[s], nullptr, n[s], &out[s]);
+            if (rc == GRB_OK && scores && scores[s]) rc = grb_index_set_scores(out[s], scores[s], (valid && valid[s]) ? valid[s] : nullptr, n[s]);
+            if (rc != GRB_OK) {
+                rcs[w] = rc;
+                return;
             }
         }
-        cudaEventRecord(g.ready, copy_stream);
-        return GRB_OK;
     };
-    if (nseq) rc = enqueue_copy(0);
-    for (int s = 0; s < nseq && rc == GRB_OK; s++) {
-        if (s + 1 < nseq) rc = enqueue_copy(s + 1);
-        if (rc != GRB_OK) break;
-        Stage &g = stg[s];
-        cudaStreamWaitEvent(ctx->stream, g.ready, 0);
-        const uint32_t *ps = g.st ? g.st : starts[s], *pe = g.en ? g.en : ends[s];
-        rc = grb_index_build(ctx, ps, pe, nullptr, n[s], &out[s]);
-        if (rc == GRB_OK && scores && scores[s]) {
-            const double *psc = g.sc ? g.sc : scores[s];
-            const uint8_t *pva = (valid && valid[s]) ? (g.va ? g.va : valid[s]) : nullptr;
-            rc = grb_index_set_scores(out[s], psc, pva, n[s]);
+    {
+        std::vector<std::thread> threads;
+        for (int w = 1; w < nworkers; w++) threads.emplace_back(work, w);
+        work(0);
+        for (auto &t : threads) t.join();
+    }
+    int rc = GRB_OK;
+    for (int w = 0; w < nworkers; w++) {
+        cudaStreamSynchronize(clones[w].own_stream);
+        cudaStreamDestroy(clones[w].own_stream);
+        ctx->launches += clones[w].launches;
+        if (rcs[w] != GRB_OK && rc == GRB_OK) {
+            rc = rcs[w];
+            memcpy(ctx->err, clones[w].err, sizeof(ctx->err));
         }
-        grb_dev_free(ctx, g.st);
-        grb_dev_free(ctx, g.en);
-        grb_dev_free(ctx, g.sc);
-        grb_dev_free(ctx, g.va);
-        g.st = g.en = nullptr;
-        g.sc = nullptr;
-        g.va = nullptr;
     }
-    cudaStreamSynchronize(copy_stream);
-    for (auto &g : stg) {
-        grb_dev_free(ctx, g.st);
-        grb_dev_free(ctx, g.en);
-        grb_dev_free(ctx, g.sc);
-        grb_dev_free(ctx, g.va);
-        if (g.ready) cudaEventDestroy(g.ready);
-    }
-    cudaEventDestroy(start_ev);
-    cudaStreamDestroy(copy_stream);
+    for (int s = 0; s < nseq; s++)
+        if (out[s]) out[s]->ctx = ctx;  // the clones go away; the indexes belong to the caller's context
     if (rc != GRB_OK) {
         for (int s = 0; s < nseq; s++) {
             grb_index_destroy(out[s]);
