@@ -53,6 +53,7 @@ SIGNATURES = {
     "grb_map_joins_f64": (C.c_int, [vp, vp, vp, vp, C.c_size_t, i32p, C.c_int, vp, vp]),
     "grb_count_overlaps_batch": (C.c_int, [vp, C.POINTER(vp), u64p, C.c_int, vp, vp, vp]),
     "grb_filter_overlaps_batch": (C.c_int, [vp, C.POINTER(vp), u64p, C.c_int, vp, vp, C.c_int, vp, u64p]),
+    "grb_filter_overlaps_select": (C.c_int, [vp, C.POINTER(vp), u64p, C.c_int, vp, vp, C.c_int, vp, u64p]),
     "grb_map_joins_f64_batch": (C.c_int, [vp, C.POINTER(vp), u64p, C.c_int, vp, vp, i32p, C.c_int, vp, vp]),
     "grb_windows": (C.c_int, [vp, vp, C.c_int, C.c_uint32, C.c_uint32, C.c_int, C.POINTER(vp)]),
     "grb_ranges_len": (C.c_size_t, [vp]),

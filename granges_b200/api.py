@@ -323,6 +323,17 @@ class Context:
                                                           pl, pe, int(bool(anti)), po, C.byref(nk)))
         return out, nk.value
 
+    def filter_overlaps_select(self, indexes, left_offsets, ls, le, anti=False):
+        """Ascending indices of the lefts the semi- (anti-) join keeps: the rows of the filtered GRanges."""
+        pl, kl, dev = _arg(ls, np.uint32)
+        pe, ke, _ = _arg(le, np.uint32)
+        off = np.ascontiguousarray(left_offsets, dtype=np.uint64)
+        po, out = self._out(dev, (len(kl),), np.uint64, kl)
+        nk = C.c_uint64(0)
+        self._check(_capi.lib().grb_filter_overlaps_select(self.h, self._handles(indexes), off.ctypes.data_as(_capi.u64p), len(indexes),
+                                                           pl, pe, int(bool(anti)), po, C.byref(nk)))
+        return out[: nk.value]
+
     def map_joins_batch(self, indexes, left_offsets, ls, le, ops, out=None, out_valid=None):
         pl, kl, dev = _arg(ls, np.uint32)
         pe, ke, _ = _arg(le, np.uint32)

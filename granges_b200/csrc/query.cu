@@ -590,6 +590,17 @@ __global__ void k_pairs_widths(const u32 *__restrict__ pos, const u64 *__restric
 
 #include "sweep.cuh"
 
+// filter_overlaps as a stream compaction: keep flags -> exclusive scan -> scatter of the kept left indices
+// (ascending, i.e. the reference's order-preserving filter, src/granges.rs:1485-1508).
+__global__ void k_keep_to_u32(const u8 *__restrict__ keep, u64 n, u32 *__restrict__ flags) {
+    u64 i = (u64)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n) flags[i] = keep[i] ? 1u : 0u;
+}
+__global__ void k_scatter_kept(const u8 *__restrict__ keep, const u64 *__restrict__ pos, u64 n, u64 *__restrict__ kept_index) {
+    u64 i = (u64)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n && keep[i]) kept_index[pos[i]] = i;
+}
+
 // ---- host orchestration -------------------------------------------------------------------
 
 struct Batch {
@@ -835,6 +846,40 @@ int grb_filter_overlaps_batch(grb_ctx *ctx, const grb_index *const *idx, const u
     if (n_kept) GRB_CUDA(ctx, cudaMemcpyAsync(n_kept, nk.p, 8, cudaMemcpyDeviceToHost, ctx->stream));
     if (dk.host || n_kept) return grb_check_flags(ctx);
     return GRB_OK;
+}
+
+int grb_filter_overlaps_select(grb_ctx *ctx, const grb_index *const *idx, const uint64_t *left_offsets, int nseq,
+                               const uint32_t *ls, const uint32_t *le, int anti, uint64_t *kept_index, uint64_t *n_kept) {
+    GRB_TRY(enter(ctx));
+    if (!left_offsets || !n_kept) return grb_fail(ctx, GRB_ERR_INVALID_ARG, "filter_overlaps_select: NULL left_offsets / n_kept");
+    const u64 total = left_offsets[nseq > 0 ? nseq : 0];
+    *n_kept = 0;
+    if (total == 0) return GRB_OK;
+    if (!ls || !le || !kept_index) return grb_fail(ctx, GRB_ERR_INVALID_ARG, "filter_overlaps_select: NULL buffer");
+    InBuf dls, dle;
+    GRB_TRY(dls.stage(ctx, ls, total * 4));
+    GRB_TRY(dle.stage(ctx, le, total * 4));
+    TempBuf keep, flags, pos;
+    GRB_TRY(keep.alloc(ctx, total));
+    GRB_TRY(flags.alloc(ctx, total * 4));
+    GRB_TRY(pos.alloc(ctx, (total + 1) * 8));
+    GRB_TRY(grb_filter_overlaps_batch(ctx, idx, left_offsets, nseq, dls.as<u32>(), dle.as<u32>(), anti, keep.as<u8>(), nullptr));
+    const unsigned blocks = (unsigned)((total + 255) / 256);
+    k_keep_to_u32<<<blocks, 256, 0, ctx->stream>>>(keep.as<u8>(), total, flags.as<u32>());
+    GRB_LAUNCHED(ctx);
+    GRB_TRY(grb_scan_u32_to_u64(ctx, flags.as<u32>(), pos.as<u64>(), total, true));
+    u64 nk = 0;
+    GRB_CUDA(ctx, cudaMemcpyAsync(&nk, pos.as<u64>() + total, 8, cudaMemcpyDeviceToHost, ctx->stream));
+    GRB_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+    OutBuf dk;
+    GRB_TRY(dk.stage(ctx, kept_index, nk * 8));
+    if (nk) {
+        k_scatter_kept<<<blocks, 256, 0, ctx->stream>>>(keep.as<u8>(), pos.as<u64>(), total, dk.as<u64>());
+        GRB_LAUNCHED(ctx);
+    }
+    GRB_TRY(dk.finish(ctx));
+    *n_kept = nk;
+    return grb_check_flags(ctx);
 }
 
 int grb_filter_overlaps(grb_ctx *ctx, const grb_index *idx, const uint32_t *ls, const uint32_t *le, size_t nl, int anti,

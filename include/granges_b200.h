@@ -170,6 +170,12 @@ int grb_count_overlaps_batch(grb_ctx *ctx, const grb_index *const *idx, const ui
                              const uint32_t *ls, const uint32_t *le, uint32_t *counts);
 int grb_filter_overlaps_batch(grb_ctx *ctx, const grb_index *const *idx, const uint64_t *left_offsets, int nseq,
                               const uint32_t *ls, const uint32_t *le, int anti, uint8_t *keep, uint64_t *n_kept);
+/* The same semi- / anti-join as an order-preserving stream compaction (keep flags -> scan -> scatter on the
+ * device): kept_index receives the ascending global indices (into ls / le) of the lefts that are kept --
+ * the rows of the filtered GRanges, data included, are the input rows at those indices
+ * (src/granges.rs:1485-1508, 1547-1609).  kept_index must hold up to left_offsets[nseq] entries. */
+int grb_filter_overlaps_select(grb_ctx *ctx, const grb_index *const *idx, const uint64_t *left_offsets, int nseq,
+                               const uint32_t *ls, const uint32_t *le, int anti, uint64_t *kept_index, uint64_t *n_kept);
 int grb_map_joins_f64_batch(grb_ctx *ctx, const grb_index *const *idx, const uint64_t *left_offsets, int nseq,
                             const uint32_t *ls, const uint32_t *le, const int *ops, int k, double *out,
                             uint8_t *out_valid);

@@ -460,3 +460,19 @@ def test_host_buffers_chunked_pipeline(eng):
         assert (host_v == dev_v.cpu().numpy()).all()
         m = host_v == 1
         assert (host_out[m] == dev_out.cpu().numpy()[m]).all()
+
+
+def test_filter_select_compaction(eng, orc):
+    """filter_overlaps as an order-preserving compaction: kept indices ascending, equal to the flagged rows."""
+    ctx = eng.ctx
+    cases = [random_case(600 + s, nl, nr, span=30_000) for s, (nl, nr) in enumerate([(5000, 300), (0, 10), (3000, 0), (4097, 2000)])]
+    idxs = [None if len(c["rs"]) == 0 else ctx.index_build(c["rs"], c["re"]) for c in cases]
+    off = np.concatenate([[0], np.cumsum([len(c["ls"]) for c in cases])]).astype(np.uint64)
+    ls = np.concatenate([c["ls"] for c in cases])
+    le = np.concatenate([c["le"] for c in cases])
+    for anti in (False, True):
+        keep, nk = ctx.filter_overlaps_batch(idxs, off, ls, le, anti=anti)
+        sel = ctx.filter_overlaps_select(idxs, off, ls, le, anti=anti)
+        assert len(sel) == nk and (sel == np.flatnonzero(keep)).all()
+    want = np.concatenate([orc.filter_overlaps(None if ix is None else orc.Tree(c["rs"], c["re"]), c["ls"], c["le"]) for c, ix in zip(cases, idxs)])
+    assert (ctx.filter_overlaps_select(idxs, off, ls, le) == np.flatnonzero(want)).all()
