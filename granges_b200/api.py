@@ -24,6 +24,7 @@ OPS = {
     "median": 5,
     "count": 6,
     "overlap-bp": 7,
+    "weighted-mean": 8,
 }
 
 STATUS = {

@@ -467,7 +467,7 @@ struct SweepOut {
     u8 *out_valid;
     int k;
     int ops[GRB_MAX_OPS];
-    int want_median, want_bp;
+    int want_median, want_bp, want_wm;  // want_wm implies want_bp (the overlap widths are needed)
     u32 *heavy_list;
     u32 *heavy_count;
 };
@@ -965,7 +965,7 @@ static int map_joins_impl(grb_ctx *ctx, const grb_index *const *idx, const uint6
     GRB_TRY(enter(ctx));
     if (!left_offsets || !ops) return grb_fail(ctx, GRB_ERR_INVALID_ARG, "map_joins: NULL left_offsets / ops");
     if (k < 1 || k > GRB_MAX_OPS) return grb_fail(ctx, GRB_ERR_INVALID_ARG, "map_joins: k must be in [1, %d]", GRB_MAX_OPS);
-    bool need_scores = false, need_sum = false, need_members = false, want_median = false, want_bp = false;
+    bool need_scores = false, need_sum = false, need_members = false, want_median = false, want_bp = false, want_wm = false;
     for (int c = 0; c < k; c++) {
         switch (ops[c]) {
             case GRB_OP_SUM:
@@ -984,6 +984,9 @@ static int map_joins_impl(grb_ctx *ctx, const grb_index *const *idx, const uint6
                 break;
             case GRB_OP_OVERLAP_BP:
                 need_members = want_bp = true;
+                break;
+            case GRB_OP_WEIGHTED_MEAN:
+                need_scores = need_members = want_bp = want_wm = true;
                 break;
             default:
                 return grb_fail(ctx, GRB_ERR_INVALID_ARG, "map_joins: unknown operation code %d", ops[c]);
@@ -1038,6 +1041,7 @@ static int map_joins_impl(grb_ctx *ctx, const grb_index *const *idx, const uint6
         for (int c = 0; c < k; c++) so.ops[c] = ops[c];
         so.want_median = want_median;
         so.want_bp = want_bp;
+        so.want_wm = want_wm;
         if (want_median) {
             if (b.total >= 0xffffffffull) return grb_fail(ctx, GRB_ERR_UNSUPPORTED, "map_joins: median over more than 2^32-1 lefts per call");
             GRB_TRY(heavy.alloc(ctx, (b.total + 1) * 4));

@@ -47,7 +47,8 @@ __device__ __forceinline__ void sweep_tile(const SeqDev *__restrict__ sd, u64 g_
         u32 nvalid = 0;
         double sum = 0.0, mn = 0.0, mx = 0.0;
         bool have = false;
-        u64 bp = 0;
+        u64 bp = 0, wtot = 0;  // overlap bp of all members / of the members with a score
+        double wsum = 0.0;     // sum of score * overlap bp
         // ---- members that start inside the left: [p, u), ascending
         for (u32 j0 = p; j0 < u; j0 += G) {
             const u32 j = j0 + glane;
@@ -55,10 +56,18 @@ __device__ __forceinline__ void sweep_tile(const SeqDev *__restrict__ sd, u64 g_
             bool v = in && has_scores;
             if (v && has_nulls) v = (vbits[j >> 5] >> (j & 31)) & 1u;
             const u32 vm = (__ballot_sync(gmask, v) >> gshift) & (G == 32 ? 0xffffffffu : ((1u << G) - 1u));
-            if (in && o.want_bp) bp += (u64)(min(lend, ends[j]) - starts[j]);
+            u32 wid = 0;
+            if (in && o.want_bp) {
+                wid = min(lend, ends[j]) - starts[j];
+                bp += wid;
+            }
             if (v) {
                 const double x = score[j];
                 sum += x;
+                if (o.want_wm) {
+                    wsum += x * (double)wid;
+                    wtot += wid;
+                }
                 if (isfinite(x)) {
                     mn = have ? fmin(mn, x) : x;
                     mx = have ? fmax(mx, x) : x;
@@ -85,10 +94,18 @@ __device__ __forceinline__ void sweep_tile(const SeqDev *__restrict__ sd, u64 g_
                 bool v = hit && has_scores;
                 if (v && has_nulls) v = (vbits[j >> 5] >> (j & 31)) & 1u;
                 const u32 vm = (__ballot_sync(gmask, v) >> gshift) & (G == 32 ? 0xffffffffu : ((1u << G) - 1u));
-                if (hit && o.want_bp) bp += (u64)(min(lend, e) - lstart);
+                u32 wid = 0;
+                if (hit && o.want_bp) {
+                    wid = min(lend, e) - lstart;
+                    bp += wid;
+                }
                 if (v) {
                     const double x = score[j];
                     sum += x;
+                    if (o.want_wm) {
+                        wsum += x * (double)wid;
+                        wtot += wid;
+                    }
                     if (isfinite(x)) {
                         mn = have ? fmin(mn, x) : x;
                         mx = have ? fmax(mx, x) : x;
@@ -118,6 +135,10 @@ __device__ __forceinline__ void sweep_tile(const SeqDev *__restrict__ sd, u64 g_
                 have = true;
             }
             bp += __shfl_xor_sync(gmask, bp, s);
+            if (o.want_wm) {
+                wsum += __shfl_xor_sync(gmask, wsum, s);
+                wtot += __shfl_xor_sync(gmask, wtot, s);
+            }
         }
         // ---- median of up to CAP values: quickselect inside the group.  Elements are ordered by (key, slot); a
         // round counts the elements below the pivot (one pass, each lane over its strided share) and, in the same
@@ -239,6 +260,10 @@ __device__ __forceinline__ void sweep_tile(const SeqDev *__restrict__ sd, u64 g_
                     case GRB_OP_OVERLAP_BP:
                         ok = 1;
                         r = (double)bp;
+                        break;
+                    case GRB_OP_WEIGHTED_MEAN:
+                        ok = 1;
+                        r = wtot ? wsum / (double)wtot : 0.0;
                         break;
                     default:
                         mine = false;

@@ -70,7 +70,9 @@ typedef enum grb_op {
     GRB_OP_MEDIAN = 5,        /* empty -> NoValue        operations.rs:17-32,96-98 */
     GRB_OP_COUNT = 6,         /* LeftGroupedJoin::num_overlaps, join.rs:153 (counts None-score rights too) */
     GRB_OP_OVERLAP_BP = 7,    /* sum of overlap_widths, join.rs:158-163, commands.rs:839-843 */
-    GRB_OP__COUNT = 8
+    GRB_OP_WEIGHTED_MEAN = 8, /* sum(score * overlap_width) / sum(overlap_width) over the non-missing scores, 0.0 if none:
+                                 the closure of examples/weighted_mean.rs:4-31 (join.rs:158-163 overlap_widths) */
+    GRB_OP__COUNT = 9
 } grb_op;
 
 #define GRB_MAX_OPS 16

@@ -88,6 +88,15 @@ def map_joins(ls, le, rs, re, scores, valid, ops, idx=None):
         for o, op in enumerate(ops):
             if op == "count":
                 out[i, o], ov[i, o] = len(g), 1
+            elif op == "weighted-mean":
+                num = den = 0.0
+                for d in g:
+                    if valid is None or valid[d]:
+                        j = pos_of[int(d)]
+                        w = float(max(0, min(le[i], re[j]) - max(ls[i], rs[j])))
+                        num += scores[d] * w
+                        den += w
+                out[i, o], ov[i, o] = (num / den if den > 0 else 0.0), 1
             elif op == "overlap-bp":
                 bp = 0
                 for d in g:

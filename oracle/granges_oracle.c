@@ -59,6 +59,7 @@ enum {
     ORC_OP_MEDIAN = 5,
     ORC_OP_COUNT = 6,      /* LeftGroupedJoin::num_overlaps, join.rs:153 */
     ORC_OP_OVERLAP_BP = 7, /* sum of overlap_widths, join.rs:158-163, commands.rs:839-843 */
+    ORC_OP_WEIGHTED_MEAN = 8, /* examples/weighted_mean.rs:4-31: sum(score*width)/sum(width) over Some scores, else 0.0 */
 };
 
 /* One node = coitrees::IntervalNode<usize, usize> restated: closed interval
@@ -453,10 +454,16 @@ static void *map_worker(void *arg) {
             }
             size_t nv = 0;
             uint64_t bp = 0;
+            double score_sum = 0.0, total_width = 0.0;
             for (size_t j = 0; j < g.len; j++) {
                 uint64_t di = g.v[j].index;
-                bp += orc_overlap_width(g.v[j].start, g.v[j].end, jb->ls[i], jb->le[i]);
-                if (jb->scores && (!jb->valid || jb->valid[di])) vals[nv++] = jb->scores[di];
+                uint32_t w = orc_overlap_width(g.v[j].start, g.v[j].end, jb->ls[i], jb->le[i]);
+                bp += w;
+                if (jb->scores && (!jb->valid || jb->valid[di])) {
+                    vals[nv++] = jb->scores[di];
+                    score_sum += jb->scores[di] * (double)w; /* examples/weighted_mean.rs:17-21 */
+                    total_width += (double)w;
+                }
             }
             for (int o = 0; o < jb->k; o++) {
                 double r = 0.0;
@@ -466,6 +473,9 @@ static void *map_worker(void *arg) {
                     ok = 1;
                 } else if (jb->ops[o] == ORC_OP_OVERLAP_BP) {
                     r = (double)bp;
+                    ok = 1;
+                } else if (jb->ops[o] == ORC_OP_WEIGHTED_MEAN) {
+                    r = total_width > 0.0 ? score_sum / total_width : 0.0; /* examples/weighted_mean.rs:26-30 */
                     ok = 1;
                 } else {
                     ok = orc_float_op(jb->ops[o], vals, nv, &r);

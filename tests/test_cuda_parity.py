@@ -36,7 +36,7 @@ def assert_map_equal(out, ov, want, wv, ops, abs_sums):
     assert (np.asarray(ov) == wv).all(), "validity (NoValue) mismatch"
     for c, op in enumerate(ops):
         m = wv[:, c] == 1
-        if op in ("sum", "sum-not-empty", "mean"):
+        if op in ("sum", "sum-not-empty", "mean", "weighted-mean"):
             tol = SUM_TOL * np.maximum(abs_sums[m], 0) + 0.0
             if op == "mean":
                 pass  # |mean error| <= |sum error| / n <= tol

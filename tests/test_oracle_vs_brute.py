@@ -36,7 +36,7 @@ def test_tree_vs_brute(nl, nr, kw):
     assert (ov == bov).all()
     for o, op in enumerate(ALL_OPS):
         m = bov[:, o] == 1
-        if op in ("sum", "sum-not-empty", "mean"):
+        if op in ("sum", "sum-not-empty", "mean", "weighted-mean"):
             # visit order differs between tree and brute force: tolerance relative to sum |x|
             assert np.allclose(out[m, o], bout[m, o], rtol=1e-12, atol=1e-9 * (np.abs(c["scores"]).max() if nr else 1))
         else:
