@@ -7,8 +7,9 @@ U{1..999}, starts uniform, scores U[0,1), equal share per seqname), both sides s
 
   value      left ranges/s of one map pass (left_overlaps + map_joins(mean), index already built,
              everything resident in HBM), CUDA events on the launching stream, max over ranks
-  e2e        the same metric through the C ABI with HOST (pinned) buffers: H2D of rights + lefts,
-             index build, map pass, D2H of the results, all inside the timed region
+  e2e        the same metric through the C ABI with HOST (pinned) buffers: grb_index_build_batch (H2D of
+             the rights and scores + 22 index builds) then grb_map_joins_f64_batch (H2D of the lefts,
+             map pass, D2H of the results), all inside the timed region
   roofline   the dominant kernel (k_tile<MAP>) against the measured HBM peak
   cpu_baseline / --impl reference
              the CPU oracle (coitrees-restated, oracle/granges_oracle.c) on a bounded sample
@@ -437,7 +438,7 @@ def main():
         d2h = nl_total * k * 9
         line["e2e"] = {"value": args.lefts / e2e_s, "unit": "left ranges/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
                        "ms_per_step": e2e_s * 1e3, "steps": e2e_steps,
-                       "includes": "H2D rights+scores+lefts (pinned), index build (22 seqnames), map pass, D2H results"}
+                       "includes": "grb_index_build_batch (H2D rights+scores, 22 index builds) + grb_map_joins_f64_batch (H2D lefts, map pass, D2H results), pinned host buffers"}
         del h_rights, h_ls, h_le
     else:
         line["e2e"] = None
