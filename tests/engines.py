@@ -42,6 +42,9 @@ class CudaEngine:
     name = "cuda"
 
     def __init__(self):
+        import __graft_entry__ as g
+
+        g.build()  # no-op when the in-tree library is up to date
         import granges_b200 as gb
 
         self.gb = gb

@@ -14,6 +14,14 @@ ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 CLI = os.path.join(ROOT, "granges_b200", "granges")
 
 
+@pytest.fixture(scope="module", autouse=True)
+def _built():
+    if not os.path.exists(CLI):
+        import __graft_entry__ as g
+
+        g.build()
+
+
 @pytest.fixture(scope="module")
 def orc():
     from oracle import oracle
