@@ -123,6 +123,7 @@ __global__ void __launch_bounds__(PIPE_THREADS, 1) k_map_pipe(const SeqDev *__re
 
     if (warp == 0) {
         // ================= lefts loader (A) =================
+        const u64 pol = l2_evict_first_policy();
         const bool vec_in = ((((uintptr_t)ls) | ((uintptr_t)le)) & 15) == 0;
         int sq = 0;  // tiles only move forward, so does the seqname
         for (u32 j = 0; j < nmine; j++) {
@@ -145,7 +146,7 @@ __global__ void __launch_bounds__(PIPE_THREADS, 1) k_map_pipe(const SeqDev *__re
             if (whole && use_tma) {
                 if (lane == 0) mbar_arrive_expect_tx(&S.fullL[sl], 2 * TILE * 4);
                 __syncwarp();
-                if (lane < 2) tma_load_1d(lane ? S.le[sl] : S.ls[sl], (lane ? le : ls) + g_first, TILE * 4, &S.fullL[sl]);
+                if (lane < 2) tma_load_1d_hint(lane ? S.le[sl] : S.ls[sl], (lane ? le : ls) + g_first, TILE * 4, &S.fullL[sl], pol);
             } else {
                 // ragged tile (seqname boundary, end of the arrays, unaligned pointers): plain copies
                 for (u32 i = lane; i < TILE; i += 32) {
@@ -164,6 +165,7 @@ __global__ void __launch_bounds__(PIPE_THREADS, 1) k_map_pipe(const SeqDev *__re
 
     if (warp == 2) {
         // ================= window loader (C) =================
+        const u64 pol = l2_evict_first_policy();
         for (u32 j = 0; j < nmine; j++) {
             const u32 sw = j % PIPE_WSTAGES, sl = j % PIPE_LSTAGES;
             mbar_wait(&S.statsL[sl], (j / PIPE_LSTAGES) & 1);
@@ -208,7 +210,7 @@ __global__ void __launch_bounds__(PIPE_THREADS, 1) k_map_pipe(const SeqDev *__re
                     mbar_arrive(&S.fullW[sw]);
             }
             __syncwarp();
-            if (staged && bytes) tma_load_1d(dst, src, bytes, &S.fullW[sw]);
+            if (staged && bytes) tma_load_1d_hint(dst, src, bytes, &S.fullW[sw], pol);
             __syncwarp();
         }
         return;
@@ -412,12 +414,12 @@ __global__ void __launch_bounds__(PIPE_THREADS, 1) k_map_pipe(const SeqDev *__re
                 // nothing
             } else if (ovec && okv[0] && okv[PIPE_LPT - 1] && (PIPE_LPT == 4 || PIPE_LPT == 2)) {
                 double2 *po = reinterpret_cast<double2 *>(out + g0);
-                po[0] = make_double2(r[0], r[1 % PIPE_LPT]);
+                __stcs(po, make_double2(r[0], r[1 % PIPE_LPT]));  // streaming stores: results are not read back here
                 if (PIPE_LPT == 4) {
-                    po[1] = make_double2(r[2 % PIPE_LPT], r[3 % PIPE_LPT]);
-                    *reinterpret_cast<uchar4 *>(out_valid + g0) = make_uchar4(v[0], v[1 % PIPE_LPT], v[2 % PIPE_LPT], v[3 % PIPE_LPT]);
+                    __stcs(po + 1, make_double2(r[2 % PIPE_LPT], r[3 % PIPE_LPT]));
+                    __stcs(reinterpret_cast<uchar4 *>(out_valid + g0), make_uchar4(v[0], v[1 % PIPE_LPT], v[2 % PIPE_LPT], v[3 % PIPE_LPT]));
                 } else {
-                    *reinterpret_cast<uchar2 *>(out_valid + g0) = make_uchar2(v[0], v[1 % PIPE_LPT]);
+                    __stcs(reinterpret_cast<uchar2 *>(out_valid + g0), make_uchar2(v[0], v[1 % PIPE_LPT]));
                 }
             } else {
 #pragma unroll

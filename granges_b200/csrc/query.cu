@@ -67,6 +67,19 @@ __device__ __forceinline__ void tma_load_1d(void *dst, const void *src, u32 byte
                  "l"(src), "r"(bytes), "r"(smem_addr(bar))
                  : "memory");
 }
+// Same copy with an L2 evict-first policy: for data that is read once per pass (it should not push the
+// prefix bases / descriptors / other CTAs' overlapping slices out of L2).
+__device__ __forceinline__ u64 l2_evict_first_policy() {
+    u64 pol;
+    asm volatile("createpolicy.fractional.L2::evict_first.b64 %0, 1.0;" : "=l"(pol));
+    return pol;
+}
+__device__ __forceinline__ void tma_load_1d_hint(void *dst, const void *src, u32 bytes, u64 *bar, u64 policy) {
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes.L2::cache_hint [%0], [%1], %2, [%3], %4;" ::"r"(
+                     smem_addr(dst)),
+                 "l"(src), "r"(bytes), "r"(smem_addr(bar)), "l"(policy)
+                 : "memory");
+}
 __device__ __forceinline__ bool mbar_try_wait(u64 *bar, u32 parity) {
     u32 ok;
     asm volatile(
