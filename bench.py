@@ -294,7 +294,7 @@ def main():
         offs.append(offs[-1] + (b - a))
         ls_parts.append(ls_s)
         le_parts.append(le_s)
-        if rank == 0 and world == 1 and not args.no_e2e:
+        if not args.no_e2e:
             host_parts.append((rs.cpu(), re.cpu(), sc.cpu()))
         del rs, re, sc
     ls = torch.cat(ls_parts) if ls_parts else torch.zeros(0, dtype=torch.int32, device=dev)
@@ -355,18 +355,62 @@ def main():
         dist.all_reduce(agg)
     pairs_total, nl_total = int(agg[0].item()), int(agg[1].item())
 
+    # keep one seqname's device-timed results for the parity check against the oracle below
+    chk_seq = pick_sample_seqs(nl_per, nr_per)[0][0]
+    chk_slice = None
+    if world == 1 and rank == 0:
+        a, b = int(left_off[chk_seq]), int(left_off[chk_seq + 1])
+        chk_slice = (out[a:b].cpu().numpy(), ov[a:b].cpu().numpy())
+
+    # ---- e2e: host (pinned) buffers through the C ABI, copies inside the timed region; every rank does its own
+    # units from its own host buffers, wall clock between barriers, max over ranks
+    e2e = None
+    if not args.no_e2e:
+        h_ls, h_le = ls.cpu().pin_memory(), le.cpu().pin_memory()
+        h_rights = [(a.pin_memory(), b.pin_memory(), c.pin_memory()) for a, b, c in host_parts]
+        h_out = torch.empty((nl_mine, k), dtype=torch.float64).pin_memory()
+        h_ov = torch.empty((nl_mine, k), dtype=torch.uint8).pin_memory()
+        call = None
+        for ix in idxs:
+            ix.close()
+        idxs.clear()
+        del out, ov
+        torch.cuda.empty_cache()
+
+        def e2e_step():
+            if not nl_mine:
+                return 0.0
+            hs = ctx.index_build_batch([(a.numpy().view(np.uint32), b.numpy().view(np.uint32), c.numpy()) for a, b, c in h_rights])
+            ctx.map_joins_batch(hs, offs, h_ls.numpy().view(np.uint32), h_le.numpy().view(np.uint32), ops, out=h_out.numpy(),
+                                out_valid=h_ov.numpy())
+            chk = float(h_out[0, 0])  # the result is on the host
+            for h in hs:
+                h.close()
+            return chk
+
+        e2e_steps = max(2, min(args.steps, 3))
+        e2e_step()
+        barrier()
+        t0 = time.perf_counter()
+        for _ in range(e2e_steps):
+            e2e_step()
+        torch.cuda.synchronize()
+        te = torch.tensor([time.perf_counter() - t0], dtype=torch.float64, device=dev)
+        if dist is not None:
+            dist.all_reduce(te, op=dist.ReduceOp.MAX)
+        e2e_s = float(te.item()) / e2e_steps
+        nr_all = int(agg[2].item())
+        e2e = {"value": args.lefts / e2e_s, "unit": "left ranges/s", "h2d_bytes_per_step": nr_all * 16 + nl_total * 8,
+               "d2h_bytes_per_step": nl_total * k * 9, "ms_per_step": e2e_s * 1e3, "steps": e2e_steps,
+               "includes": "grb_index_build_batch (H2D rights+scores, index builds) + grb_map_joins_f64_batch (H2D lefts, map pass, D2H "
+                           "results), pinned host buffers, per rank for its own units; wall clock, max over ranks"}
+        del h_rights, h_ls, h_le
+
     if rank != 0:
         if dist is not None:
             dist.barrier()
             dist.destroy_process_group()
         return
-
-    # keep one seqname's device-timed results for the parity check against the oracle below
-    chk_seq = pick_sample_seqs(nl_per, nr_per)[0][0]
-    chk_slice = None
-    if world == 1:
-        a, b = int(left_off[chk_seq]), int(left_off[chk_seq + 1])
-        chk_slice = (out[a:b].cpu().numpy(), ov[a:b].cpu().numpy())
 
     value = args.lefts / (ms_per_step * 1e-3)
     line = {
@@ -405,43 +449,7 @@ def main():
         except Exception:
             pass
 
-    # ---- e2e: host (pinned) buffers through the C ABI, copies inside the timed region
-    if world == 1 and not args.no_e2e:
-        h_ls, h_le = ls.cpu().pin_memory(), le.cpu().pin_memory()
-        h_rights = [(a.pin_memory(), b.pin_memory(), c.pin_memory()) for a, b, c in host_parts]
-        h_out = torch.empty((nl_mine, k), dtype=torch.float64).pin_memory()
-        h_ov = torch.empty((nl_mine, k), dtype=torch.uint8).pin_memory()
-        for ix in idxs:
-            ix.close()
-        idxs.clear()
-        del out, ov
-        torch.cuda.empty_cache()
-
-        def e2e_step():
-            hs = ctx.index_build_batch([(a.numpy().view(np.uint32), b.numpy().view(np.uint32), c.numpy()) for a, b, c in h_rights])
-            ctx.map_joins_batch(hs, offs, h_ls.numpy().view(np.uint32), h_le.numpy().view(np.uint32), ops, out=h_out.numpy(),
-                                out_valid=h_ov.numpy())
-            chk = float(h_out[0, 0])  # the result is on the host
-            for h in hs:
-                h.close()
-            return chk
-
-        e2e_steps = max(2, min(args.steps, 3))
-        e2e_step()
-        torch.cuda.synchronize()
-        t0 = time.perf_counter()
-        for _ in range(e2e_steps):
-            e2e_step()
-        torch.cuda.synchronize()
-        e2e_s = (time.perf_counter() - t0) / e2e_steps
-        h2d = nr_tot * 16 + nl_total * 8
-        d2h = nl_total * k * 9
-        line["e2e"] = {"value": args.lefts / e2e_s, "unit": "left ranges/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
-                       "ms_per_step": e2e_s * 1e3, "steps": e2e_steps,
-                       "includes": "grb_index_build_batch (H2D rights+scores, 22 index builds) + grb_map_joins_f64_batch (H2D lefts, map pass, D2H results), pinned host buffers"}
-        del h_rights, h_ls, h_le
-    else:
-        line["e2e"] = None
+    line["e2e"] = e2e
 
     # ---- cpu baseline: the oracle on a bounded sample (one seqname), 1 thread like the reference
     if world == 1 and not args.no_cpu:
