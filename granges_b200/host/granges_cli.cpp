@@ -11,12 +11,17 @@
 #include <sys/stat.h>
 #include <unistd.h>
 
+#include <time.h>
+
 #include <cerrno>
 #include <cstdio>
 #include <cstdlib>
 #include <cstring>
+#include <algorithm>
+#include <functional>
 #include <string>
 #include <string_view>
+#include <thread>
 #include <unordered_map>
 #include <vector>
 
@@ -24,6 +29,20 @@
 #include "granges_b200.h"
 
 namespace {
+
+// GRANGES_TIMING=1 prints the wall time of every phase on stderr
+struct Phase {
+    const char *name;
+    timespec t0;
+    explicit Phase(const char *n) : name(n) { clock_gettime(CLOCK_MONOTONIC, &t0); }
+    ~Phase() {
+        static const bool on = getenv("GRANGES_TIMING") != nullptr;
+        if (!on) return;
+        timespec t1;
+        clock_gettime(CLOCK_MONOTONIC, &t1);
+        fprintf(stderr, "[timing] %-28s %8.1f ms\n", name, (t1.tv_sec - t0.tv_sec) * 1e3 + (t1.tv_nsec - t0.tv_nsec) * 1e-6);
+    }
+};
 
 [[noreturn]] void die(const std::string &msg) {
     fprintf(stderr, "Error: %s\n", msg.c_str());
@@ -91,77 +110,128 @@ struct SeqRanges {
 
 enum class Cols { Bed3, Bed5, Bedlike };
 
+int n_threads() {
+    const char *e = getenv("GRANGES_THREADS");
+    int t = (e && *e) ? atoi(e) : (int)std::thread::hardware_concurrency();
+    return t < 1 ? 1 : (t > 64 ? 64 : t);
+}
+
+// run f(0..n-1) on up to n_threads() host threads
+void parallel_for(int n, const std::function<void(int)> &f) {
+    const int t = std::min(n, n_threads());
+    if (t <= 1) {
+        for (int i = 0; i < n; i++) f(i);
+        return;
+    }
+    std::vector<std::thread> th;
+    for (int w = 0; w < t; w++)
+        th.emplace_back([&, w] {
+            for (int i = w; i < n; i += t) f(i);
+        });
+    for (auto &x : th) x.join();
+}
+
 // BED parsing as the reference's typed iterators do it (src/io/parsers/tsv.rs:27-121): tab-separated,
 // '#' lines skipped; BED5 = name + score with "." -> None (src/io/parsers/bed/mod.rs:37-73).
-size_t parse_bed(const Mapped &f, const Genome &g, Cols cols, bool skip_missing, std::vector<SeqRanges> &out,
-                 bool *any_rest = nullptr) {
+// The text is cut into chunks at line boundaries, the chunks are parsed on all host threads and
+// stitched back in file order, so the per-seqname insertion order is the file's.
+struct ParseError {
+    bool set = false;
+    std::string msg;
+};
+
+size_t parse_chunk(const char *p, const char *end, const Genome &g, Cols cols, bool skip_missing, std::vector<SeqRanges> &out, bool *any_rest,
+                   ParseError &err) {
     out.assign(g.names.size(), SeqRanges());
-    const char *p = f.p, *end = f.p + f.n;
-    size_t rows = 0, line_no = 0;
+    size_t rows = 0;
     int last_id = -1;
     std::string_view last_name;
+    auto fail = [&](const char *line, const std::string &m) {
+        if (!err.set) {
+            err.set = true;
+            err.msg = m + " (at byte offset of line start " + std::to_string((size_t)(line - p)) + " of its chunk)";
+        }
+    };
     while (p < end) {
+        const char *line = p;
         const char *nl = (const char *)memchr(p, '\n', end - p);
         const char *le = nl ? nl : end;
         const char *next = le + 1;
         if (le > p && le[-1] == '\r') le--;
-        line_no++;
-        if (le == p || *p == '#') {
-            p = next;
-            continue;
+        p = next;
+        if (le == line || *line == '#') continue;
+        const char *t1 = (const char *)memchr(line, '\t', le - line);
+        const char *t2 = t1 ? (const char *)memchr(t1 + 1, '\t', le - t1 - 1) : nullptr;
+        if (!t1 || !t2) {
+            fail(line, "expected at least 3 tab-separated columns");
+            return rows;
         }
-        const char *t1 = (const char *)memchr(p, '\t', le - p);
-        if (!t1) die("line " + std::to_string(line_no) + ": expected at least 3 tab-separated columns");
-        const char *t2 = (const char *)memchr(t1 + 1, '\t', le - t1 - 1);
-        if (!t2) die("line " + std::to_string(line_no) + ": expected at least 3 tab-separated columns");
         const char *t3 = (const char *)memchr(t2 + 1, '\t', le - t2 - 1);
         const char *e3 = t3 ? t3 : le;
-        std::string_view name(p, t1 - p);
+        std::string_view name(line, t1 - line);
         int id;
         if (last_id >= 0 && name == last_name) {
             id = last_id;
         } else {
             auto it = g.id.find(name);
             if (it == g.id.end()) {
-                if (skip_missing) {
-                    p = next;
-                    continue;
-                }
-                die("The sequence name '" + std::string(name) +
-                    "' is not found within the provided ranges container. Check the sequence names for typos or missing entries.");
+                if (skip_missing) continue;
+                fail(line, "The sequence name '" + std::string(name) +
+                               "' is not found within the provided ranges container. Check the sequence names for typos or missing entries.");
+                return rows;
             }
             id = it->second;
             last_id = id;
             last_name = name;
         }
         uint64_t s = 0, e = 0;
+        bool bad = t2 == t1 + 1 || e3 == t2 + 1;
         for (const char *q = t1 + 1; q < t2; q++) {
-            if (*q < '0' || *q > '9') die("line " + std::to_string(line_no) + ": invalid start coordinate");
+            bad |= *q < '0' || *q > '9';
             s = s * 10 + (uint64_t)(*q - '0');
         }
         for (const char *q = t2 + 1; q < e3; q++) {
-            if (*q < '0' || *q > '9') die("line " + std::to_string(line_no) + ": invalid end coordinate");
+            bad |= *q < '0' || *q > '9';
             e = e * 10 + (uint64_t)(*q - '0');
         }
-        if (e <= s || e > 0x7fffffffull)
-            die("line " + std::to_string(line_no) + ": invalid range (the reference panics: end must be > start and fit i32)");
+        if (bad) {
+            fail(line, "invalid start / end coordinate");
+            return rows;
+        }
+        if (e <= s || e > 0x7fffffffull) {
+            fail(line, "invalid range (the reference panics: end must be > start and fit i32)");
+            return rows;
+        }
         SeqRanges &sr = out[id];
         sr.starts.push_back((uint32_t)s);
         sr.ends.push_back((uint32_t)e);
         if (cols == Cols::Bed5) {
-            if (!t3) die("line " + std::to_string(line_no) + ": BED5 needs a name and a score column");
-            const char *t4 = (const char *)memchr(t3 + 1, '\t', le - t3 - 1);
-            if (!t4) die("line " + std::to_string(line_no) + ": BED5 needs a name and a score column");
+            const char *t4 = t3 ? (const char *)memchr(t3 + 1, '\t', le - t3 - 1) : nullptr;
+            if (!t4) {
+                fail(line, "BED5 needs a name and a score column");
+                return rows;
+            }
             const char *t5 = (const char *)memchr(t4 + 1, '\t', le - t4 - 1);
             const char *e5 = t5 ? t5 : le;
             if (e5 - (t4 + 1) == 1 && t4[1] == '.') {
                 sr.score.push_back(0.0);
                 sr.valid.push_back(0);
             } else {
-                std::string tmp(t4 + 1, e5);
-                char *ep;
-                double v = strtod(tmp.c_str(), &ep);
-                if (ep == tmp.c_str() || *ep) die("line " + std::to_string(line_no) + ": parsing error: invalid float literal");
+                char tmp[64];
+                size_t len = (size_t)(e5 - (t4 + 1));
+                double v = 0.0;
+                bool okf = len > 0 && len < sizeof(tmp);
+                if (okf) {
+                    memcpy(tmp, t4 + 1, len);
+                    tmp[len] = 0;
+                    char *ep;
+                    v = strtod(tmp, &ep);
+                    okf = ep != tmp && *ep == 0;
+                }
+                if (!okf) {
+                    fail(line, "parsing error: invalid float literal");
+                    return rows;
+                }
                 sr.score.push_back(v);
                 sr.valid.push_back(1);
             }
@@ -170,32 +240,93 @@ size_t parse_bed(const Mapped &f, const Genome &g, Cols cols, bool skip_missing,
             if (t3 && any_rest) *any_rest = true;
         }
         rows++;
-        p = next;
     }
     return rows;
 }
 
-struct Out {
-    FILE *f;
-    std::vector<char> buf;
-    size_t n = 0;
-    explicit Out(const char *path) : buf(1 << 22) {
-        f = path ? fopen(path, "wb") : stdout;
-        if (!f) die(std::string(path) + ": " + strerror(errno));
+size_t parse_bed(const Mapped &f, const Genome &g, Cols cols, bool skip_missing, std::vector<SeqRanges> &out,
+                 bool *any_rest = nullptr) {
+    const int nchunks = f.n < (1u << 20) ? 1 : n_threads() * 4;
+    std::vector<const char *> cut((size_t)nchunks + 1);
+    cut[0] = f.p;
+    cut[nchunks] = f.p + f.n;
+    for (int c = 1; c < nchunks; c++) {
+        const char *q = f.p + f.n / nchunks * c;
+        const char *nl = (const char *)memchr(q, '\n', f.p + f.n - q);
+        cut[c] = nl ? nl + 1 : f.p + f.n;
+        if (cut[c] < cut[c - 1]) cut[c] = cut[c - 1];
     }
-    char *room(size_t need) {
-        if (n + need > buf.size()) flush();
-        return buf.data() + n;
+    std::vector<std::vector<SeqRanges>> part((size_t)nchunks);
+    std::vector<size_t> rows((size_t)nchunks, 0);
+    std::vector<ParseError> errs((size_t)nchunks);
+    std::vector<char> rest_flag((size_t)nchunks, 0);
+    parallel_for(nchunks, [&](int c) {
+        bool ar = false;
+        rows[c] = parse_chunk(cut[c], cut[c + 1], g, cols, skip_missing, part[c], &ar, errs[c]);
+        rest_flag[c] = ar;
+    });
+    for (int c = 0; c < nchunks; c++)
+        if (errs[c].set) die(errs[c].msg);
+    size_t total = 0;
+    for (int c = 0; c < nchunks; c++) {
+        total += rows[c];
+        if (rest_flag[c] && any_rest) *any_rest = true;
     }
-    void flush() {
-        if (n) fwrite(buf.data(), 1, n, f);
-        n = 0;
+    // stitch: per seqname, the chunks in file order
+    const int nseq = (int)g.names.size();
+    out.assign(nseq, SeqRanges());
+    parallel_for(nseq, [&](int s) {
+        size_t n = 0;
+        for (int c = 0; c < nchunks; c++) n += part[c][s].starts.size();
+        SeqRanges &o = out[s];
+        o.starts.reserve(n);
+        o.ends.reserve(n);
+        if (cols == Cols::Bed5) {
+            o.score.reserve(n);
+            o.valid.reserve(n);
+        }
+        if (cols == Cols::Bedlike) o.rest.reserve(n);
+        for (int c = 0; c < nchunks; c++) {
+            SeqRanges &q = part[c][s];
+            o.starts.insert(o.starts.end(), q.starts.begin(), q.starts.end());
+            o.ends.insert(o.ends.end(), q.ends.begin(), q.ends.end());
+            o.score.insert(o.score.end(), q.score.begin(), q.score.end());
+            o.valid.insert(o.valid.end(), q.valid.begin(), q.valid.end());
+            o.rest.insert(o.rest.end(), q.rest.begin(), q.rest.end());
+            q = SeqRanges();
+        }
+    });
+    return total;
+}
+
+// Rows [0, n) rendered by `row(i, p)` (returns the end of what it wrote at p; at most `max_row` bytes) on all host
+// threads into per-block buffers, then written in order.
+void write_rows(const char *path, size_t n, size_t max_row, const std::function<char *(size_t, char *)> &row) {
+    FILE *f = path ? fopen(path, "wb") : stdout;
+    if (!f) die(std::string(path) + ": " + strerror(errno));
+    const size_t block = 1 << 15;
+    const size_t nblocks = (n + block - 1) / block;
+    const size_t wave = (size_t)n_threads() * 2;
+    std::vector<std::vector<char>> bufs(wave);
+    for (size_t b0 = 0; b0 < nblocks; b0 += wave) {
+        const int nb = (int)std::min(wave, nblocks - b0);
+        parallel_for(nb, [&](int w) {
+            const size_t lo = (b0 + w) * block, hi = std::min(n, lo + block);
+            std::vector<char> &buf = bufs[w];
+            buf.clear();
+            std::vector<char> tmp(max_row);
+            for (size_t i = lo; i < hi; i++) {
+                char *e = row(i, tmp.data());
+                buf.insert(buf.end(), tmp.data(), e);
+            }
+        });
+        for (int w = 0; w < nb; w++) fwrite(bufs[w].data(), 1, bufs[w].size(), f);
     }
-    ~Out() {
-        flush();
-        if (f != stdout) fclose(f);
-    }
-};
+    if (f != stdout)
+        fclose(f);
+    else
+        fflush(stdout);
+}
 
 void check(grb_ctx *ctx, int rc) {
     if (rc != GRB_OK) die(ctx ? grb_last_error(ctx) : "cannot create a CUDA context (granges_b200 has no CPU fallback)");
@@ -226,11 +357,27 @@ int cmd_map(const Args &a) {
     Genome g = read_genome(a.genome);
     Mapped lf(a.left), rf(a.right);
     std::vector<SeqRanges> L, R;
-    size_t nl = parse_bed(lf, g, Cols::Bed3, a.skip_missing, L);
-    size_t nr = parse_bed(rf, g, Cols::Bed5, a.skip_missing, R);
-    if (nl == 0 || nr == 0) die("The input file had no rows.");
+    size_t nl, nr;
     grb_ctx *ctx = nullptr;
-    check(nullptr, grb_ctx_create(0, &ctx));
+    {
+        // CUDA start-up (driver + context, a second or more on a big box) runs beside the parsing
+        int ctx_rc = GRB_OK;
+        std::thread init([&] {
+            Phase ph("cuda context");
+            ctx_rc = grb_ctx_create(0, &ctx);
+        });
+        {
+            Phase ph("parse left");
+            nl = parse_bed(lf, g, Cols::Bed3, a.skip_missing, L);
+        }
+        {
+            Phase ph("parse right");
+            nr = parse_bed(rf, g, Cols::Bed5, a.skip_missing, R);
+        }
+        init.join();
+        if (nl == 0 || nr == 0) die("The input file had no rows.");
+        check(nullptr, ctx_rc);
+    }
     const int nseq = (int)g.names.size();
     std::vector<grb_index *> idx(nseq, nullptr);
     std::vector<uint64_t> off(nseq + 1, 0);
@@ -241,39 +388,59 @@ int cmd_map(const Args &a) {
         off[s] = ls.size();
         ls.insert(ls.end(), L[s].starts.begin(), L[s].starts.end());
         le.insert(le.end(), L[s].ends.begin(), L[s].ends.end());
-        if (!R[s].starts.empty()) {
-            check(ctx, grb_index_build(ctx, R[s].starts.data(), R[s].ends.data(), nullptr, R[s].starts.size(), &idx[s]));
-            check(ctx, grb_index_set_scores(idx[s], R[s].score.data(), R[s].valid.data(), R[s].score.size()));
-        }
     }
     off[nseq] = ls.size();
+    {
+        Phase ph("index build (batch)");
+        // the whole right-hand side at once: uploads and builds of different seqnames overlap
+        std::vector<const uint32_t *> ps(nseq), pe(nseq);
+        std::vector<const double *> psc(nseq);
+        std::vector<const uint8_t *> pva(nseq);
+        std::vector<size_t> pn(nseq);
+        for (int s = 0; s < nseq; s++) {
+            ps[s] = R[s].starts.data();
+            pe[s] = R[s].ends.data();
+            psc[s] = R[s].score.data();
+            pva[s] = R[s].valid.data();
+            pn[s] = R[s].starts.size();
+        }
+        check(ctx, grb_index_build_batch(ctx, nseq, ps.data(), pe.data(), pn.data(), psc.data(), pva.data(), idx.data()));
+        // a seqname the right file never mentions has no container (its groups are empty either way)
+        for (int s = 0; s < nseq; s++)
+            if (pn[s] == 0) {
+                grb_index_destroy(idx[s]);
+                idx[s] = nullptr;
+            }
+    }
     const int k = (int)a.ops.size();
     std::vector<double> out(nl * (size_t)k);
     std::vector<uint8_t> ov(nl * (size_t)k);
-    check(ctx, grb_map_joins_f64_batch(ctx, idx.data(), off.data(), nseq, ls.data(), le.data(), a.ops.data(), k, out.data(), ov.data()));
-    Out w(a.has_output ? a.output.c_str() : nullptr);
-    for (int s = 0; s < nseq; s++) {
-        const std::string &name = g.names[s];
-        for (uint64_t i = off[s]; i < off[s + 1]; i++) {
-            char *p = w.room(name.size() + 64 + (size_t)k * 420);
-            char *q = p;
-            memcpy(q, name.data(), name.size());
-            q += name.size();
-            *q++ = '\t';
-            q = grh::format_u32(q, ls[i]);
-            *q++ = '\t';
-            q = grh::format_u32(q, le[i]);
-            for (int c = 0; c < k; c++) {
-                *q++ = '\t';
-                if (ov[i * k + c])
-                    q = grh::format_f64(q, out[i * k + c]);
-                else
-                    *q++ = '.';
-            }
-            *q++ = '\n';
-            w.n += q - p;
-        }
+    {
+        Phase ph("map_joins");
+        check(ctx, grb_map_joins_f64_batch(ctx, idx.data(), off.data(), nseq, ls.data(), le.data(), a.ops.data(), k, out.data(), ov.data()));
     }
+    Phase phw("write");
+    size_t max_name = 0;
+    for (auto &nm : g.names) max_name = std::max(max_name, nm.size());
+    write_rows(a.has_output ? a.output.c_str() : nullptr, nl, max_name + 64 + (size_t)k * 420, [&](size_t i, char *q) {
+        const int sq = (int)(std::upper_bound(off.begin(), off.end(), (uint64_t)i) - off.begin()) - 1;
+        const std::string &name = g.names[sq];
+        memcpy(q, name.data(), name.size());
+        q += name.size();
+        *q++ = '\t';
+        q = grh::format_u32(q, ls[i]);
+        *q++ = '\t';
+        q = grh::format_u32(q, le[i]);
+        for (int c = 0; c < k; c++) {
+            *q++ = '\t';
+            if (ov[i * k + c])
+                q = grh::format_f64(q, out[i * k + c]);
+            else
+                *q++ = '.';
+        }
+        *q++ = '\n';
+        return q;
+    });
     for (auto ix : idx) grb_index_destroy(ix);
     grb_ctx_destroy(ctx);
     return 0;
@@ -302,32 +469,33 @@ int cmd_filter(const Args &a) {
         if (!R[s].starts.empty()) check(ctx, grb_index_build(ctx, R[s].starts.data(), R[s].ends.data(), nullptr, R[s].starts.size(), &idx[s]));
     }
     off[nseq] = ls.size();
-    std::vector<uint8_t> keep(nl);
+    // the kept rows, in order, straight from the device-side compaction
+    std::vector<uint64_t> kept(nl);
     uint64_t nk = 0;
-    check(ctx, grb_filter_overlaps_batch(ctx, idx.data(), off.data(), nseq, ls.data(), le.data(), 0, keep.data(), &nk));
-    Out w(a.has_output ? a.output.c_str() : nullptr);
-    for (int s = 0; s < nseq; s++) {
-        const std::string &name = g.names[s];
-        for (uint64_t i = off[s]; i < off[s + 1]; i++) {
-            if (!keep[i]) continue;
-            std::string_view rest = L[s].rest[i - off[s]];
-            char *p = w.room(name.size() + 64 + rest.size());
-            char *q = p;
-            memcpy(q, name.data(), name.size());
-            q += name.size();
+    if (nl) check(ctx, grb_filter_overlaps_select(ctx, idx.data(), off.data(), nseq, ls.data(), le.data(), 0, kept.data(), &nk));
+    size_t max_name = 0, max_rest = 0;
+    for (auto &nm : g.names) max_name = std::max(max_name, nm.size());
+    for (auto &sr : L)
+        for (auto &r : sr.rest) max_rest = std::max(max_rest, r.size());
+    write_rows(a.has_output ? a.output.c_str() : nullptr, nk, max_name + 64 + max_rest, [&](size_t r, char *q) {
+        const uint64_t i = kept[r];
+        const int sq = (int)(std::upper_bound(off.begin(), off.end(), i) - off.begin()) - 1;
+        const std::string &name = g.names[sq];
+        std::string_view rest = L[sq].rest[i - off[sq]];
+        memcpy(q, name.data(), name.size());
+        q += name.size();
+        *q++ = '\t';
+        q = grh::format_u32(q, ls[i]);
+        *q++ = '\t';
+        q = grh::format_u32(q, le[i]);
+        if (!rest.empty()) {
             *q++ = '\t';
-            q = grh::format_u32(q, ls[i]);
-            *q++ = '\t';
-            q = grh::format_u32(q, le[i]);
-            if (!rest.empty()) {
-                *q++ = '\t';
-                memcpy(q, rest.data(), rest.size());
-                q += rest.size();
-            }
-            *q++ = '\n';
-            w.n += q - p;
+            memcpy(q, rest.data(), rest.size());
+            q += rest.size();
         }
-    }
+        *q++ = '\n';
+        return q;
+    });
     for (auto ix : idx) grb_index_destroy(ix);
     grb_ctx_destroy(ctx);
     return 0;
@@ -343,11 +511,10 @@ int cmd_windows(const Args &a) {
     const size_t n = grb_ranges_len(r);
     std::vector<uint32_t> seq(n), st(n), en(n);
     check(ctx, grb_ranges_copy(r, seq.data(), st.data(), en.data()));
-    Out w(a.has_output ? a.output.c_str() : nullptr);
-    for (size_t i = 0; i < n; i++) {
+    size_t max_name = 0;
+    for (auto &nm : g.names) max_name = std::max(max_name, nm.size());
+    write_rows(a.has_output ? a.output.c_str() : nullptr, n, max_name + 40, [&](size_t i, char *q) {
         const std::string &name = g.names[seq[i]];
-        char *p = w.room(name.size() + 40);
-        char *q = p;
         memcpy(q, name.data(), name.size());
         q += name.size();
         *q++ = '\t';
@@ -355,10 +522,75 @@ int cmd_windows(const Args &a) {
         *q++ = '\t';
         q = grh::format_u32(q, en[i]);
         *q++ = '\n';
-        w.n += q - p;
-    }
+        return q;
+    });
     grb_ranges_destroy(r);
     grb_ctx_destroy(ctx);
+    return 0;
+}
+
+// `granges random-bed` (dev command of the reference, src/commands.rs:563-588 + src/test_utilities.rs:60-164): seqname
+// uniform over the genome file's names, length U{1..999}, start uniform, optional BED5 name + score U[0,1).  The
+// generator is a counter-based splitmix64 (the reference's StdRng stream is not reproducible without the crate).
+uint64_t splitmix(uint64_t x) {
+    x += 0x9E3779B97F4A7C15ull;
+    x = (x ^ (x >> 30)) * 0xBF58476D1CE4E5B9ull;
+    x = (x ^ (x >> 27)) * 0x94D049BB133111EBull;
+    return x ^ (x >> 31);
+}
+
+int cmd_random_bed(const Args &a, size_t num, bool sort, bool scores, uint64_t seed) {
+    Genome g = read_genome(a.genome);
+    const size_t nseq = g.names.size();
+    if (nseq == 0) die("The input file had no rows.");
+    struct Row {
+        uint32_t seq, start, end;
+        uint64_t id;
+    };
+    std::vector<Row> rows(num);
+    parallel_for(64, [&](int c) {
+        for (size_t i = (size_t)c * num / 64; i < (size_t)(c + 1) * num / 64; i++) {
+            const uint64_t b = seed * 0x100000001B3ull + i * 4;
+            const uint32_t sq = (uint32_t)(splitmix(b) % nseq);
+            const uint32_t L = g.lens[sq];
+            uint32_t len = 1 + (uint32_t)(splitmix(b + 1) % 999);
+            if (len > L) len = L ? L : 1;
+            const uint32_t st = (uint32_t)(splitmix(b + 2) % ((uint64_t)L - len + 1));
+            rows[i] = Row{sq, st, st + len, i};
+        }
+    });
+    if (sort)
+        std::sort(rows.begin(), rows.end(), [](const Row &x, const Row &y) {
+            if (x.seq != y.seq) return x.seq < y.seq;
+            if (x.start != y.start) return x.start < y.start;
+            if (x.end != y.end) return x.end < y.end;
+            return x.id < y.id;
+        });
+    size_t max_name = 0;
+    for (auto &nm : g.names) max_name = std::max(max_name, nm.size());
+    write_rows(a.has_output ? a.output.c_str() : nullptr, num, max_name + 96, [&](size_t i, char *q) {
+        const Row &r = rows[i];
+        const std::string &name = g.names[r.seq];
+        memcpy(q, name.data(), name.size());
+        q += name.size();
+        *q++ = '\t';
+        q = grh::format_u32(q, r.start);
+        *q++ = '\t';
+        q = grh::format_u32(q, r.end);
+        if (scores) {
+            uint64_t h = splitmix(seed * 0x100000001B3ull + r.id * 4 + 3);
+            *q++ = '\t';
+            for (int c = 0; c < 8; c++) {
+                *q++ = (char)('a' + (h % 26));
+                h /= 26;
+            }
+            *q++ = '\t';
+            const double sc = (double)(splitmix(h + r.id) >> 11) * (1.0 / 9007199254740992.0);
+            q = grh::format_f64(q, sc);
+        }
+        *q++ = '\n';
+        return q;
+    });
     return 0;
 }
 
@@ -368,6 +600,7 @@ void usage() {
             "  granges map     -g <genome> -l <left.bed> -r <right.bed5> -f <op[,op..]> [-o <out>] [-s]\n"
             "  granges filter  -g <genome> -l <left.bed> -r <right.bed> [-o <out>] [-s]\n"
             "  granges windows -g <genome> -w <width> [-s <step>] [-c] [-o <out>]\n"
+            "  granges random-bed <genome> -n <num> [-o <out>] [-s] [-c] [--seed <n>]\n"
             "ops: sum, sum-not-empty, min, max, mean, median\n");
 }
 
@@ -381,6 +614,31 @@ int main(int argc, char **argv) {
     const std::string cmd = argv[1];
     const bool windows = cmd == "windows";
     Args a;
+    if (cmd == "random-bed") {
+        size_t num = 0;
+        bool sort = false, scores = false;
+        uint64_t seed = 13;  // TEST_SEED default of the reference (src/test_utilities.rs:34-40)
+        for (int i = 2; i < argc; i++) {
+            std::string f = argv[i];
+            if ((f == "-n" || f == "--num") && i + 1 < argc)
+                num = strtoull(argv[++i], nullptr, 10);
+            else if ((f == "-o" || f == "--output") && i + 1 < argc) {
+                a.output = argv[++i];
+                a.has_output = true;
+            } else if (f == "--seed" && i + 1 < argc)
+                seed = strtoull(argv[++i], nullptr, 10);
+            else if (f == "-s" || f == "--sort")
+                sort = true;
+            else if (f == "-c" || f == "--scores")
+                scores = true;
+            else if (f[0] != '-' && a.genome.empty())
+                a.genome = f;
+            else
+                die("unexpected argument '" + f + "' found");
+        }
+        if (a.genome.empty()) die("the following required arguments were not provided: <GENOME>");
+        return cmd_random_bed(a, num, sort, scores, seed);
+    }
     for (int i = 2; i < argc; i++) {
         std::string f = argv[i], val;
         bool has_val = false;
