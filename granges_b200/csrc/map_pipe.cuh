@@ -82,7 +82,7 @@ __device__ __forceinline__ void mbar_arrive(u64 *bar) {
 
 // flags: bit 0 = stage with TMA; bit 1 = debug, consumers skip the arithmetic (pipeline-only timing)
 template <int FAST>
-__global__ void __launch_bounds__(PIPE_THREADS, 1) k_map_pipe(const SeqDev *__restrict__ seqs, int nseq, u32 ntiles,
+__global__ void __launch_bounds__(PIPE_THREADS, 1) k_map_pipe(const SeqDev *__restrict__ seqs, int nseq, u32 tile_base, u32 ntiles,
                                                               const u32 *__restrict__ ls, const u32 *__restrict__ le,
                                                               double *__restrict__ out, u8 *__restrict__ out_valid, int flags,
                                                               u32 *__restrict__ ctx_flags) {
@@ -128,7 +128,7 @@ __global__ void __launch_bounds__(PIPE_THREADS, 1) k_map_pipe(const SeqDev *__re
         int sq = 0;  // tiles only move forward, so does the seqname
         for (u32 j = 0; j < nmine; j++) {
             const u32 sl = j % PIPE_LSTAGES;
-            const u32 t = blockIdx.x + j * gridDim.x;
+            const u32 t = tile_base + blockIdx.x + j * gridDim.x;
             while (sq + 1 < nseq && S.seq[sq + 1].tile_begin <= t) sq++;
             const PipeSeq &q = S.seq[sq];
             const u64 g_first = ((q.left_begin >> TILE_SHIFT) + (t - q.tile_begin)) << TILE_SHIFT;

@@ -623,6 +623,7 @@ struct Batch {
     u64 total = 0;
     int nseq = 0;
     bool uniform = true;  // every present seqname: scores, no None, compact prefixes
+    std::vector<u32> host_tile_begin;  // nseq + 1
 };
 
 int make_batch(grb_ctx *ctx, const grb_index *const *idx, const u64 *left_offsets, int nseq, Batch *b) {
@@ -690,6 +691,7 @@ int make_batch(grb_ctx *ctx, const grb_index *const *idx, const u64 *left_offset
         h[s] = d;
     }
     tb[nseq] = (u32)tiles;
+    b->host_tile_begin = tb;
     b->ntiles = (u32)tiles;
     b->total = left_offsets[nseq];
     b->nseq = nseq;
@@ -739,18 +741,25 @@ int launch_pipe(grb_ctx *ctx, const Batch &b, const u32 *ls, const u32 *le, cons
         GRB_CUDA(ctx, cudaFuncSetAttribute(k_map_pipe<FAST>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(PipeSmem)));
         configured = true;
     }
-    u32 grid = (u32)ctx->sm_count;
-    if (grid > b.ntiles) grid = b.ntiles;
     const int flags = (ctx->tile_mode ? 1 : 0) | (ctx->pipe_mode == 2 ? 2 : 0) | (ctx->pipe_mode == 3 ? 4 : 0);
-    k_map_pipe<FAST><<<grid, PIPE_THREADS, sizeof(PipeSmem), ctx->stream>>>(b.seqs, b.nseq, b.ntiles, ls, le, o.out, o.out_valid, flags, o.flags);
-    GRB_LAUNCHED(ctx);
+    // the kernel keeps its seqnames' descriptors in shared memory: at most PIPE_MAXSEQ per launch
+    for (int s0 = 0; s0 < b.nseq; s0 += PIPE_MAXSEQ) {
+        const int s1 = s0 + PIPE_MAXSEQ < b.nseq ? s0 + PIPE_MAXSEQ : b.nseq;
+        const u32 t0 = b.host_tile_begin[s0], t1 = b.host_tile_begin[s1];
+        if (t1 == t0) continue;
+        u32 grid = (u32)ctx->sm_count;
+        if (grid > t1 - t0) grid = t1 - t0;
+        k_map_pipe<FAST><<<grid, PIPE_THREADS, sizeof(PipeSmem), ctx->stream>>>(b.seqs + s0, s1 - s0, t0, t1 - t0, ls, le, o.out, o.out_valid,
+                                                                              flags, o.flags);
+        GRB_LAUNCHED(ctx);
+    }
     return GRB_OK;
 }
 
 // MAP launch: the single-reduction fast kernels when the batch is uniform, else the general one.
 template <int MODE>
 int launch_map(grb_ctx *ctx, const Batch &b, const u32 *ls, const u32 *le, const TileOut &o) {
-    if (MODE == M_MAP && b.uniform && o.k == 1 && ctx->pipe_mode && b.nseq <= PIPE_MAXSEQ) {
+    if (MODE == M_MAP && b.uniform && o.k == 1 && ctx->pipe_mode) {
         switch (o.ops[0]) {
             case GRB_OP_MEAN:
                 return launch_pipe<GRB_OP_MEAN>(ctx, b, ls, le, o);

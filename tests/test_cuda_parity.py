@@ -476,3 +476,23 @@ def test_filter_select_compaction(eng, orc):
         assert len(sel) == nk and (sel == np.flatnonzero(keep)).all()
     want = np.concatenate([orc.filter_overlaps(None if ix is None else orc.Tree(c["rs"], c["re"]), c["ls"], c["le"]) for c, ix in zip(cases, idxs)])
     assert (ctx.filter_overlaps_select(idxs, off, ls, le) == np.flatnonzero(want)).all()
+
+
+def test_many_seqnames(eng, orc):
+    """More seqnames than the pipelined kernel keeps descriptors for (32): several launches, same answers."""
+    ctx = eng.ctx
+    rng = np.random.default_rng(77)
+    nseq = 75
+    cases = [random_case(900 + s, int(rng.integers(0, 3000)), int(rng.integers(0, 2000)), span=40_000, sorted_left=True) for s in range(nseq)]
+    idxs = [None if len(c["rs"]) == 0 else ctx.index_build(c["rs"], c["re"]).set_scores(c["scores"]) for c in cases]
+    off = np.concatenate([[0], np.cumsum([len(c["ls"]) for c in cases])]).astype(np.uint64)
+    ls = np.concatenate([c["ls"] for c in cases])
+    le = np.concatenate([c["le"] for c in cases])
+    out, ov = ctx.map_joins_batch(idxs, off, ls, le, ["mean"])
+    for s, c in enumerate(cases):
+        sl = slice(int(off[s]), int(off[s + 1]))
+        t = None if idxs[s] is None else orc.Tree(c["rs"], c["re"])
+        want, wv = orc.map_joins(t, None if t is None else c["scores"], None, c["ls"], c["le"], ["mean"])
+        assert (ov[sl] == wv).all()
+        m = wv[:, 0] == 1
+        assert np.allclose(out[sl][m], want[m], rtol=1e-12, atol=0)
