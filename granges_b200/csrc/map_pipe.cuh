@@ -53,7 +53,7 @@ struct PipeDesc {      // one per window-ring slot (loader -> consumers)
     u64 g_first;
     u32 vlo, vhi;
     u32 a0, b0, la0, lb0;
-    u32 staged;
+    u32 staged;        // 1: windows staged in the slot; 0: search in global memory (windows too large, or invalid lefts)
     int seq;
 };
 
@@ -176,7 +176,9 @@ __global__ void __launch_bounds__(PIPE_THREADS, 1) k_map_pipe(const SeqDev *__re
             // + 8: a search reads the two aligned quads around its answer, i.e. up to 7 keys past it
             const u32 alen = ti.bound[1] - a0 + 8, blen = ti.bound[3] - b0 + 8;
             const u32 lalen = ti.bin[1] + 1 - la0, lblen = ti.bin[3] + 1 - lb0;
-            const bool staged = use_tma && alen <= PIPE_WIN && blen <= PIPE_WIN && lalen <= PIPE_LUT && lblen <= PIPE_LUT;
+            // bound[1] == 0xffffffff: the surveyor found invalid lefts in this tile (no index is that long)
+            const bool staged = use_tma && ti.bound[1] != 0xffffffffu && alen <= PIPE_WIN && blen <= PIPE_WIN && lalen <= PIPE_LUT &&
+                                lblen <= PIPE_LUT;
             const bool want_pfx = FAST != GRB_OP_COUNT;
             // lane l issues copy l: 0 lut_a, 1 lut_b, 2 starts, 3 ends_sorted, 4 pfx_a, 5 pfx_b
             const void *src = nullptr;
@@ -258,13 +260,17 @@ __global__ void __launch_bounds__(PIPE_THREADS, 1) k_map_pipe(const SeqDev *__re
                 mx_s = warp_max(mx_s);
                 // invalid lefts cannot exist in the reference (it panics: ranges/mod.rs:30, coitrees.rs:53-54): make the call fail
                 mx_w = warp_max(mx_w);
-                if ((mx_w >= 0x7fffffffu || mx_e > 0x7fffffffu) && lane == 0) atomicOr(ctx_flags, 1u);
+                const bool tile_bad = mx_w >= 0x7fffffffu || mx_e > 0x7fffffffu;
+                if (tile_bad && lane == 0) atomicOr(ctx_flags, 1u);
                 const u32 qq = lane & 3;
                 const u32 v = qq == 0 ? mn_e : qq == 1 ? mx_e : qq == 2 ? mn_s : mx_s;
                 const u32 x = v + (qq >> 1);  // l.end for the starts table, l.start + 1 for the ends table
                 bin_new = min(x >> q.sh, q.bmax);
                 bound_new = ((qq < 2) ? q.lut_a : q.lut_b)[bin_new + (qq & 1)];
                 // publish at once: this warp now waits for its four table entries, the other surveyors carry on
+                // a tile with invalid lefts must not be staged (their bins may fall outside the slices): an impossible
+                // upper bound tells the window loader, and the consumers' global path skips those lefts
+                if (tile_bad && qq == 1) bound_new = 0xffffffffu;
                 if (lane < 4) {
                     S.tile[sl].bin[lane] = bin_new;
                     S.tile[sl].bound[lane] = bound_new;
@@ -313,8 +319,7 @@ __global__ void __launch_bounds__(PIPE_THREADS, 1) k_map_pipe(const SeqDev *__re
                 okv[k] = i0 + k >= vlo && i0 + k < vhi;
             }
             // (A left with end <= start or end > 2^31-1 -- impossible in the reference, which panics -- was flagged by
-            // the surveyor and makes the call fail; here it needs no special care: its bins lie inside the staged
-            // slices like any other left's, so every access stays in range and only its own row is meaningless.)
+            // the surveyor, which also keeps its tile off the staged path.)
             const u32 a0 = d.a0, b0 = d.b0, la0 = d.la0, lb0 = d.lb0;
             const SeqDev *__restrict__ sd = &seqs[d.seq];  // only dereferenced on the rare paths
             u32 ub[PIPE_LPT], lbk[PIPE_LPT];  // absolute positions
@@ -362,6 +367,7 @@ __global__ void __launch_bounds__(PIPE_THREADS, 1) k_map_pipe(const SeqDev *__re
                     ub[k] = lbk[k] = 0;
                     pa[k] = pb[k] = 0;
                     if (!okv[k]) continue;
+                    if (b[k] <= a[k] || b[k] > 0x7fffffffu) continue;  // invalid left (flagged by the surveyor): an empty group
                     const u32 xa = b[k], xb = a[k] + 1;
                     ub[k] = scan_lower_bound(q.starts, q.lut_a[min(xa >> sh, bmax)], xa);
                     lbk[k] = scan_lower_bound(q.ends_sorted, q.lut_b[min(xb >> sh, bmax)], xb);

@@ -398,9 +398,15 @@ def test_invalid_left_ranges_are_reported(eng):
     c = random_case(123, 3000, 4000, span=50_000, sorted_left=True)
     ix = ctx.index_build(c["rs"], c["re"]).set_scores(c["scores"])
     good, gv = ctx.map_joins(ix, c["ls"], c["le"], ["mean"])
-    for bad_end in (lambda s: s, lambda s: np.uint32(2**31 + 7)):
+    for kind in ("empty", "beyond-i32", "wrap"):
         ls, le = c["ls"].copy(), c["le"].copy()
-        le[1500] = bad_end(ls[1500])
+        if kind == "empty":
+            le[1500] = ls[1500]
+        elif kind == "beyond-i32":
+            le[1500] = np.uint32(2**31 + 7)
+        else:  # coordinates that wrap when 1 is added: must not index outside any staged slice
+            ls[1500] = np.uint32(2**32 - 1)
+            le[1500] = np.uint32(2**32 - 1)
         for ops in (["mean"], ["min", "median", "sum"]):  # pipelined kernel / tile + sweep kernels
             with pytest.raises(gb.GRangesError) as ei:
                 ctx.map_joins(ix, ls, le, ops)
