@@ -21,7 +21,7 @@ __device__ __forceinline__ u32 group_mask() {
     return G == 32 ? 0xffffffffu : (((1u << G) - 1u) << ((threadIdx.x & 31) & ~(G - 1)));
 }
 
-template <int G>
+template <int G, bool WIDTHS>  // WIDTHS: overlap bp / weighted mean are wanted (they need the members' starts)
 __device__ __forceinline__ void sweep_tile(const SeqDev *__restrict__ sd, u64 g_lo, u64 g_hi, const u32 *__restrict__ ls,
                                            const u32 *__restrict__ le, const u32 *__restrict__ ubv, const u32 *__restrict__ ppv,
                                            const u32 *__restrict__ lbv, const SweepOut &o, double *s_buf /* [groups][CAP] */,
@@ -57,14 +57,14 @@ __device__ __forceinline__ void sweep_tile(const SeqDev *__restrict__ sd, u64 g_
             if (v && has_nulls) v = (vbits[j >> 5] >> (j & 31)) & 1u;
             const u32 vm = (__ballot_sync(gmask, v) >> gshift) & (G == 32 ? 0xffffffffu : ((1u << G) - 1u));
             u32 wid = 0;
-            if (in && o.want_bp) {
+            if (WIDTHS && in) {
                 wid = min(lend, ends[j]) - starts[j];
                 bp += wid;
             }
             if (v) {
                 const double x = score[j];
                 sum += x;
-                if (o.want_wm) {
+                if (WIDTHS) {
                     wsum += x * (double)wid;
                     wtot += wid;
                 }
@@ -95,14 +95,14 @@ __device__ __forceinline__ void sweep_tile(const SeqDev *__restrict__ sd, u64 g_
                 if (v && has_nulls) v = (vbits[j >> 5] >> (j & 31)) & 1u;
                 const u32 vm = (__ballot_sync(gmask, v) >> gshift) & (G == 32 ? 0xffffffffu : ((1u << G) - 1u));
                 u32 wid = 0;
-                if (hit && o.want_bp) {
+                if (WIDTHS && hit) {
                     wid = min(lend, e) - lstart;
                     bp += wid;
                 }
                 if (v) {
                     const double x = score[j];
                     sum += x;
-                    if (o.want_wm) {
+                    if (WIDTHS) {
                         wsum += x * (double)wid;
                         wtot += wid;
                     }
@@ -134,8 +134,8 @@ __device__ __forceinline__ void sweep_tile(const SeqDev *__restrict__ sd, u64 g_
                 mx = have ? fmax(mx, omx) : omx;
                 have = true;
             }
-            bp += __shfl_xor_sync(gmask, bp, s);
-            if (o.want_wm) {
+            if (WIDTHS) {
+                bp += __shfl_xor_sync(gmask, bp, s);
                 wsum += __shfl_xor_sync(gmask, wsum, s);
                 wtot += __shfl_xor_sync(gmask, wtot, s);
             }
@@ -305,10 +305,18 @@ __global__ void __launch_bounds__(SW2_TPB) k_sweep2(const SeqDev *__restrict__ s
     u64 total = 0;
 #pragma unroll
     for (int w = 0; w < SW2_TPB / 32; w++) total += s_cnt[w];
-    if (total > 48ull * (g_hi - g_lo))
-        sweep_tile<32>(sd, g_lo, g_hi, ls, le, ubv, ppv, lbv, o, s_buf, s_med);
-    else
-        sweep_tile<8>(sd, g_lo, g_hi, ls, le, ubv, ppv, lbv, o, s_buf, s_med);
+    const bool wide_groups = total > 48ull * (g_hi - g_lo);
+    if (o.want_bp) {
+        if (wide_groups)
+            sweep_tile<32, true>(sd, g_lo, g_hi, ls, le, ubv, ppv, lbv, o, s_buf, s_med);
+        else
+            sweep_tile<8, true>(sd, g_lo, g_hi, ls, le, ubv, ppv, lbv, o, s_buf, s_med);
+    } else {
+        if (wide_groups)
+            sweep_tile<32, false>(sd, g_lo, g_hi, ls, le, ubv, ppv, lbv, o, s_buf, s_med);
+        else
+            sweep_tile<8, false>(sd, g_lo, g_hi, ls, le, ubv, ppv, lbv, o, s_buf, s_med);
+    }
 }
 
 // Emit pass of left_overlaps: positions (start order) of the members of every group, ascending,

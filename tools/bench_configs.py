@@ -183,17 +183,20 @@ def c5(scale):
         from granges_b200 import _capi
 
         off = torch.empty(nl_per[s] + 1, dtype=torch.int64, device=dev)
-        ph = C.c_void_p()
-        torch.cuda.synchronize()
-        t0 = time.perf_counter()
-        rc = _capi.lib().grb_left_overlaps(ctx.h, ix.h, ls.data_ptr(), le.data_ptr(), nl_per[s], off.data_ptr(), C.byref(ph))
-        assert rc == 0, ctx._check(rc)
-        ctx.sync()
-        tot_ms += (time.perf_counter() - t0) * 1e3
-        tot_pairs += _capi.lib().grb_pairs_len(ph)
-        _capi.lib().grb_pairs_destroy(ph)
+        for rep in range(2):  # the second run reuses the pool's memory: steady state
+            ph = C.c_void_p()
+            torch.cuda.synchronize()
+            t0 = time.perf_counter()
+            rc = _capi.lib().grb_left_overlaps(ctx.h, ix.h, ls.data_ptr(), le.data_ptr(), nl_per[s], off.data_ptr(), C.byref(ph))
+            assert rc == 0, ctx._check(rc)
+            ctx.sync()
+            dt = (time.perf_counter() - t0) * 1e3
+            npairs = _capi.lib().grb_pairs_len(ph)
+            _capi.lib().grb_pairs_destroy(ph)
+        tot_ms += dt
+        tot_pairs += npairs
         ix.close()
-    report("C5 left_overlaps pairs %d x %d (per seqname, wall clock incl. the P read-back)" % (nl, nr), ms=tot_ms, pairs=tot_pairs,
+    report("C5 left_overlaps pairs %d x %d (per seqname, wall clock of the second run incl. allocation from the pool and the P read-back)" % (nl, nr), ms=tot_ms, pairs=tot_pairs,
            pairs_per_s=tot_pairs / tot_ms * 1e3, lefts_per_s=nl / tot_ms * 1e3, index_build_ms=tb * 1e3)
 
 
