@@ -502,3 +502,36 @@ def test_many_seqnames(eng, orc):
         assert (ov[sl] == wv).all()
         m = wv[:, 0] == 1
         assert np.allclose(out[sl][m], want[m], rtol=1e-12, atol=0)
+
+
+@pytest.mark.parametrize("kind", ["compact", "wide"])
+@pytest.mark.parametrize("op", ["mean", "sum"])
+def test_large_groups_exact_128bit_path(eng, orc, op, kind):
+    """Groups of more than 2^(63-W) members (1024 for 53-bit scores) leave the 64-bit wrapped-prefix fast path and
+    rebuild the exact 128-bit prefixes from the per-256 bases -- in the pipelined kernel (k = 1) and the tile kernel."""
+    import math
+
+    rng = np.random.default_rng(41)
+    nr = 20_000
+    rs = np.sort(rng.integers(0, 3000, nr)).astype(np.uint32)
+    re = (rs + rng.integers(1, 900, nr)).astype(np.uint32)
+    # compact: multiples of 2^-53 below 1 (W = 53, the pipelined kernel's prefixes); wide: 53-bit mantissas at many
+    # exponents and both signs (128-bit prefixes per right, tile kernel)
+    sc = rng.random(nr) if kind == "compact" else rng.random(nr) * 1000.0 - 300.0
+    ls = np.sort(rng.integers(0, 3500, 4000)).astype(np.uint32)
+    le = (ls + rng.integers(1, 2000, 4000)).astype(np.uint32)
+    ix = eng.build(rs, re, None, sc, None)
+    assert ix.exact_sums
+    cnt = eng.count(ix, ls, le)
+    assert cnt.max() > 5000 and (cnt > 1024).mean() > 0.5
+    out, ov = eng.map_joins(ix, ls, le, [op])                 # pipelined kernel
+    out2, ov2 = eng.map_joins(ix, ls, le, [op, "count"])      # tile kernel (two reductions)
+    assert (ov == ov2[:, :1]).all() and (out[ov == 1] == out2[:, :1][ov == 1]).all()
+    for i in range(0, len(ls), 37):
+        m = (rs < le[i]) & (re > ls[i])
+        exact = math.fsum(sc[m])
+        want = exact if op == "sum" else (exact / int(m.sum()) if m.any() else None)
+        if want is None:
+            assert ov[i, 0] == 0
+        else:
+            assert ov[i, 0] == 1 and out[i, 0] == want, (i, out[i, 0], want)
