@@ -80,12 +80,19 @@ __device__ __forceinline__ void mbar_arrive(u64 *bar) {
     asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_addr(bar)) : "memory");
 }
 
+constexpr int PIPE_MULTI = 100;  // FAST value: several prefix-sum reductions (sum / sum-not-empty / mean / count) per left
+
+struct PipeOps {
+    int k;
+    int ops[GRB_MAX_OPS];
+};
+
 // flags: bit 0 = stage with TMA; bit 1 = debug, consumers skip the arithmetic (pipeline-only timing)
 template <int FAST>
 __global__ void __launch_bounds__(PIPE_THREADS, 1) k_map_pipe(const SeqDev *__restrict__ seqs, int nseq, u32 tile_base, u32 ntiles,
                                                               const u32 *__restrict__ ls, const u32 *__restrict__ le,
                                                               double *__restrict__ out, u8 *__restrict__ out_valid, int flags,
-                                                              u32 *__restrict__ ctx_flags) {
+                                                              u32 *__restrict__ ctx_flags, const PipeOps mops) {
     extern __shared__ __align__(128) unsigned char smem_raw[];
     PipeSmem &S = *reinterpret_cast<PipeSmem *>(smem_raw);
     const u32 tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
@@ -386,6 +393,34 @@ __global__ void __launch_bounds__(PIPE_THREADS, 1) k_map_pipe(const SeqDev *__re
                 mbar_arrive(&S.emptyL[sl]);
             }
             // ---- reductions
+            if (FAST == PIPE_MULTI) {
+                // several reductions from the same (count, exact sum): row-major out[left][column]
+#pragma unroll
+                for (int k = 0; k < PIPE_LPT; k++) {
+                    if (!okv[k]) continue;
+                    const u32 c = ub[k] - lbk[k];
+                    double sum;
+                    if (c < fast_cmax) {
+                        sum = (double)(i64)(pa[k] - pb[k]) * scale;
+                    } else {
+                        const i128 ba128 = sd->base_a[ub[k] >> GRB_BASE_SHIFT], bb128 = sd->base_b[lbk[k] >> GRB_BASE_SHIFT];
+                        const i128 PA = ba128 + (i128)(i64)(pa[k] - (u64)(u128)ba128);
+                        const i128 PB = bb128 + (i128)(i64)(pb[k] - (u64)(u128)bb128);
+                        sum = fx_to_double(PA - PB, sd->e0);
+                    }
+                    const double mean = c ? sum / (double)c : 0.0;
+                    double *po = out + (g0 + k) * (u64)mops.k;
+                    u8 *pv = out_valid + (g0 + k) * (u64)mops.k;
+                    for (int col = 0; col < mops.k; col++) {
+                        const int op = mops.ops[col];
+                        const double rr = op == GRB_OP_COUNT ? (double)c : op == GRB_OP_MEAN ? mean : sum;
+                        const u8 vv = (op == GRB_OP_SUM || op == GRB_OP_COUNT) ? (u8)1 : (u8)(c != 0);
+                        __stcs(po + col, rr);
+                        pv[col] = vv;
+                    }
+                }
+                continue;
+            }
             double r[PIPE_LPT];
             u8 v[PIPE_LPT];
 #pragma unroll

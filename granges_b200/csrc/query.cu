@@ -749,8 +749,11 @@ int launch_pipe(grb_ctx *ctx, const Batch &b, const u32 *ls, const u32 *le, cons
         if (t1 == t0) continue;
         u32 grid = (u32)ctx->sm_count;
         if (grid > t1 - t0) grid = t1 - t0;
+        PipeOps mops;
+        mops.k = o.k;
+        for (int c = 0; c < GRB_MAX_OPS; c++) mops.ops[c] = c < o.k ? o.ops[c] : 0;
         k_map_pipe<FAST><<<grid, PIPE_THREADS, sizeof(PipeSmem), ctx->stream>>>(b.seqs + s0, s1 - s0, t0, t1 - t0, ls, le, o.out, o.out_valid,
-                                                                              flags, o.flags);
+                                                                              flags, o.flags, mops);
         GRB_LAUNCHED(ctx);
     }
     return GRB_OK;
@@ -759,6 +762,13 @@ int launch_pipe(grb_ctx *ctx, const Batch &b, const u32 *ls, const u32 *le, cons
 // MAP launch: the single-reduction fast kernels when the batch is uniform, else the general one.
 template <int MODE>
 int launch_map(grb_ctx *ctx, const Batch &b, const u32 *ls, const u32 *le, const TileOut &o) {
+    if (MODE == M_MAP && b.uniform && o.k > 1 && ctx->pipe_mode) {
+        // several reductions, all answered by the prefix sums: still one pass of the pipelined kernel
+        bool algebraic = true;
+        for (int c = 0; c < o.k; c++)
+            algebraic &= o.ops[c] == GRB_OP_SUM || o.ops[c] == GRB_OP_SUM_NOT_EMPTY || o.ops[c] == GRB_OP_MEAN || o.ops[c] == GRB_OP_COUNT;
+        if (algebraic) return launch_pipe<PIPE_MULTI>(ctx, b, ls, le, o);
+    }
     if (MODE == M_MAP && b.uniform && o.k == 1 && ctx->pipe_mode) {
         switch (o.ops[0]) {
             case GRB_OP_MEAN:

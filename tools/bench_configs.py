@@ -91,6 +91,17 @@ def c3(scale):
            pairs_per_s=pairs / ms * 1e3, index_build_ms=tb * 1e3)
 
 
+def c3ops(scale):
+    """C3's member sweep by reduction subset: where the time goes."""
+    n = int(100_000_000 * scale)
+    idxs, off, ls, le, tb = uniform_sets(n, n)
+    for ops in (["min"], ["min", "max"], ["median"], ["min", "max", "median"], ["min", "max", "mean", "sum", "median"], ["overlap-bp"], ["weighted-mean"]):
+        out = torch.empty((n, len(ops)), dtype=torch.float64, device=dev)
+        ov = torch.empty((n, len(ops)), dtype=torch.uint8, device=dev)
+        ms, _ = timed(lambda: ctx.map_joins_batch(idxs, off, ls, le, ops, out=out, out_valid=ov), reps=2)
+        report("C3 subset " + ",".join(ops) + " %d x %d" % (n, n), ms=ms, lefts_per_s=n / ms * 1e3)
+
+
 def clustered_rights(seq, n, seed):
     """80 % of the ranges in 5 % of the 1 Mb bins (log-normal bin weights, sigma 1.5), the rest uniform."""
     L = HG38[seq]
@@ -211,4 +222,4 @@ if __name__ == "__main__":
     which = args or ["c1", "c2", "c3", "c4", "c5"]
     for w in which:
         torch.cuda.empty_cache()
-        {"c1": c1, "c2": lambda: c2(scale), "c3": lambda: c3(scale), "c4": lambda: c4(scale), "c5": lambda: c5(scale)}[w]()
+        {"c1": c1, "c2": lambda: c2(scale), "c3": lambda: c3(scale), "c4": lambda: c4(scale), "c5": lambda: c5(scale), "c3ops": lambda: c3ops(scale)}[w]()
