@@ -33,6 +33,7 @@ struct grb_ctx {
     void *zeros;    // 1 KB of zeros (tables) + 1 KB of 0xff (sentinel keys): what an absent seqname / empty index reads
     int pipe_mode;  // 1 = persistent warp-specialised pipeline for single-reduction maps (default), 0 = k_tile only (debug)
     int tile_mode;  // 1 = TMA-staged smem windows (default), 0 = global binary search only (debug)
+    int sweep_mode; // 1 = staged rank sweep k_sweep3 for MIN / MAX / MEDIAN (default), 2 = k_sweep3 without staging, 0 = k_sweep2 only (debug)
     char err[512];
 };
 
@@ -168,7 +169,18 @@ struct grb_index {
     u32 lut_bmax;
     u32 *lut_a;   // over starts
     u32 *lut_b;   // over ends_sorted
+    // member-sweep tables (MIN / MAX / MEDIAN), built on first use by grb_index_prepare_members
+    bool has_nonfinite;
+    bool members_ready;
+    u32 n_valid;          // rights that carry a score
+    u32 *rank_a;          // n + pad, start order: rank of the right's score among the valid scores, ordered by
+                          // (score, position) -- all different; GRB_RANK_NONE when the score is None
+    double *score_sorted; // n_valid: the scores in rank order
+    u32 *fb;              // ceil(n/64): fb[b] <= position of the earliest right that straddles any coordinate
+                          // >= starts[64 b]  (how far back a window over the rights must reach)
 };
+
+#define GRB_RANK_NONE 0xffffffffu
 
 // Per-seqname view handed to the kernels (one entry per seqname of a batch).
 struct SeqDev {
@@ -178,6 +190,8 @@ struct SeqDev {
     const u64 *pfx_a, *pfx_b;
     const i128 *base_a, *base_b;
     const u32 *lut_a, *lut_b;
+    const u32 *rank_a, *fb;
+    const double *score_sorted;
     u64 left_begin, left_end;
     double scale;    // 2^e0
     u32 n;
@@ -250,6 +264,16 @@ __device__ __forceinline__ double fx_to_double(i128 v, int e0) {
     return neg ? -r : r;
 }
 
+// order-preserving integer image of an f64 (and back): -inf < ... < -0.0 < +0.0 < ... < +inf
+__device__ __forceinline__ u64 f64_key(double x) {
+    u64 b = (u64)__double_as_longlong(x);
+    return (b >> 63) ? ~b : (b | (1ull << 63));
+}
+__device__ __forceinline__ double key_f64(u64 k) {
+    u64 b = (k >> 63) ? (k & ~(1ull << 63)) : ~k;
+    return __longlong_as_double((long long)b);
+}
+
 __device__ __forceinline__ u64 ld_relaxed_u64(const u64 *p) {
     u64 v;
     asm volatile("ld.relaxed.gpu.global.u64 %0, [%1];" : "=l"(v) : "l"(p) : "memory");
@@ -267,6 +291,9 @@ __device__ __forceinline__ void st_relaxed_u64(u64 *p, u64 v) {
 // write_total, else n.  Single-pass decoupled look-back.
 int grb_scan_u32_to_u64(grb_ctx *ctx, const u32 *in, u64 *out, size_t n, bool write_total);
 int grb_scan_u32_to_u32(grb_ctx *ctx, const u32 *in, u32 *out, size_t n, bool write_total);
+
+// index.cu: build the member-sweep tables of an index (rank_a, score_sorted, fb) if they are not there yet.
+int grb_index_prepare_members(grb_ctx *ctx, grb_index *ix);
 
 // sort.cu: stable LSD radix sort of (u64 key, u32 value) pairs; skips digits that do not vary and
 // the whole sort when the keys are already non-decreasing.  On return *keys_out / *vals_out point

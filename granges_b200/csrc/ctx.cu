@@ -91,6 +91,9 @@ int grb_ctx_create(int device, grb_ctx **out) {
     ctx->pipe_mode = 1;
     const char *pm = getenv("GRB_PIPE_MODE");
     if (pm) ctx->pipe_mode = atoi(pm);
+    ctx->sweep_mode = 1;
+    const char *sm = getenv("GRB_SWEEP_MODE");
+    if (sm) ctx->sweep_mode = atoi(sm);
     int ndev = 0;
     cudaError_t e = cudaGetDeviceCount(&ndev);
     if (e != cudaSuccess || device < 0 || device >= ndev) {

@@ -282,6 +282,88 @@ __global__ void __launch_bounds__(1024) k_scan_i128_single(const i128 *__restric
     }
 }
 
+// ---- member-sweep tables ---------------------------------------------------------
+
+// (order-preserving score image, position) pairs; None sorts last
+__global__ void k_rank_keys(const double *__restrict__ score_a, const u32 *__restrict__ vbits_a, size_t n, u64 *__restrict__ keys,
+                            u32 *__restrict__ vals) {
+    size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    bool ok = vbits_a ? ((vbits_a[i >> 5] >> (i & 31)) & 1u) : true;
+    keys[i] = ok ? f64_key(score_a[i]) : ~0ull;
+    vals[i] = (u32)i;
+}
+
+__global__ void k_rank_scatter(const u64 *__restrict__ keys, const u32 *__restrict__ vals, size_t n, u32 n_valid,
+                               u32 *__restrict__ rank_a, double *__restrict__ score_sorted) {
+    size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n + PAD) return;
+    if (i >= n) {
+        rank_a[i] = GRB_RANK_NONE;
+        return;
+    }
+    if (i < n_valid) {
+        rank_a[vals[i]] = (u32)i;
+        score_sorted[i] = key_f64(keys[i]);
+    } else {
+        rank_a[vals[i]] = GRB_RANK_NONE;
+    }
+}
+
+// inclusive prefix maximum of nb values by one CTA
+__global__ void __launch_bounds__(1024) k_prefix_max_single(const u32 *__restrict__ in, size_t nb, u32 *__restrict__ out) {
+    __shared__ u32 s_m[1024];
+    const size_t per = (nb + 1023) / 1024;
+    const size_t lo = (size_t)threadIdx.x * per;
+    const size_t hi = lo + per < nb ? lo + per : nb;
+    u32 m = 0;
+    for (size_t i = lo; i < hi; i++) m = max(m, in[i]);
+    s_m[threadIdx.x] = m;
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        u32 run = 0;
+        for (int k = 0; k < 1024; k++) {
+            u32 c = s_m[k];
+            s_m[k] = run;
+            run = max(run, c);
+        }
+    }
+    __syncthreads();
+    u32 run = s_m[threadIdx.x];
+    for (size_t i = lo; i < hi; i++) {
+        run = max(run, in[i]);
+        out[i] = run;
+    }
+}
+
+// fb[b] = first position j < 64 b with ends[j] > starts[64 b], else 64 b.  Every right that straddles a
+// coordinate x >= starts[64 b] (start < x < end) sits at or after fb[b]: a straddler of x that starts before
+// starts[64 b] ends after it, and one that starts later is positioned later.
+__global__ void k_first_back(const u32 *__restrict__ starts, const u32 *__restrict__ ends, const u32 *__restrict__ pmax, size_t nb,
+                             u32 *__restrict__ fb) {
+    size_t b = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (b >= nb) return;
+    const u32 x = starts[b << GRB_BME_SHIFT];
+    size_t lo = 0, hi = b;  // first block b' in [0, b) with pmax[b'] > x
+    while (lo < hi) {
+        size_t mid = lo + ((hi - lo) >> 1);
+        if (pmax[mid] > x)
+            hi = mid;
+        else
+            lo = mid + 1;
+    }
+    u32 r = (u32)(b << GRB_BME_SHIFT);
+    if (lo < b) {
+        const size_t j0 = lo << GRB_BME_SHIFT;
+        for (int k = 0; k < 64; k++)
+            if (ends[j0 + k] > x) {
+                r = (u32)(j0 + k);
+                break;
+            }
+    }
+    fb[b] = r;
+}
+
 inline unsigned blocks_for(size_t n, int tpb) { return (unsigned)((n + tpb - 1) / tpb); }
 
 int dev_alloc(grb_ctx *ctx, void **p, size_t bytes) {
@@ -298,6 +380,13 @@ void free_scores(grb_index *ix) {
     grb_dev_free(ix->ctx, ix->pfx_b);
     grb_dev_free(ix->ctx, ix->base_a);
     grb_dev_free(ix->ctx, ix->base_b);
+    grb_dev_free(ix->ctx, ix->rank_a);
+    grb_dev_free(ix->ctx, ix->score_sorted);
+    ix->rank_a = nullptr;
+    ix->score_sorted = nullptr;
+    ix->members_ready = false;
+    ix->has_nonfinite = false;
+    ix->n_valid = 0;
     ix->score_a = nullptr;
     ix->vbits_a = ix->vcnt_a = ix->vcnt_b = nullptr;
     ix->pfx_a = ix->pfx_b = nullptr;
@@ -361,7 +450,7 @@ int grb_index_build(grb_ctx *ctx, const uint32_t *starts, const uint32_t *ends, 
         if ((rc = dev_alloc(ctx, (void **)&ix->ends_sorted, (n + PAD) * 4))) break;
         if ((rc = dev_alloc(ctx, (void **)&ix->didx, n * 4))) break;
         if ((rc = dev_alloc(ctx, (void **)&ix->perm_e, n * 4))) break;
-        if ((rc = dev_alloc(ctx, (void **)&ix->bme, ((n + 63) >> GRB_BME_SHIFT) * 4))) break;
+        if ((rc = dev_alloc(ctx, (void **)&ix->bme, (((n + 63) >> GRB_BME_SHIFT) + PAD) * 4))) break;
         InBuf d_starts, d_ends, d_idx;
         if ((rc = d_starts.stage(ctx, starts, n * 4))) break;
         if ((rc = d_ends.stage(ctx, ends, n * 4))) break;
@@ -474,6 +563,7 @@ void grb_index_destroy(grb_index *ix) {
     grb_dev_free(ix->ctx, ix->perm_e);
     grb_dev_free(ix->ctx, ix->lut_a);
     grb_dev_free(ix->ctx, ix->lut_b);
+    grb_dev_free(ix->ctx, ix->fb);
     free(ix);
 }
 
@@ -520,6 +610,8 @@ int grb_index_set_scores(grb_index *ix, const double *by_data_idx, const uint8_t
     ix->has_scores = true;
     ix->has_nulls = st.n_null != 0;
     ix->has_nan = st.has_nan != 0;
+    ix->has_nonfinite = st.has_nonfinite != 0;
+    ix->n_valid = (u32)(n - st.n_null);
     if (ix->has_nulls) {
         GRB_TRY(dev_alloc(ctx, (void **)&ix->vcnt_a, (n + 1) * 4));
         GRB_TRY(dev_alloc(ctx, (void **)&ix->vcnt_b, (n + 1) * 4));
@@ -630,6 +722,46 @@ int grb_index_build_batch(grb_ctx *ctx, int nseq, const uint32_t *const *starts,
     }
     return rc;
 }
+
+}  // extern "C"
+
+// Tables of the staged member sweep (k_sweep3), built the first time MIN / MAX / MEDIAN are asked of an index:
+// the rank of every score (one more radix sort), the scores in rank order, and the reach-back table.
+int grb_index_prepare_members(grb_ctx *ctx, grb_index *ix) {
+    if (!ix || ix->members_ready || !ix->n || !ix->has_scores) return GRB_OK;
+    const size_t n = ix->n;
+    GRB_TRY(dev_alloc(ctx, (void **)&ix->rank_a, (n + PAD) * 4));
+    GRB_TRY(dev_alloc(ctx, (void **)&ix->score_sorted, ((size_t)ix->n_valid + 1) * 8));
+    {
+        TempBuf k0, k1, v0, v1;
+        GRB_TRY(k0.alloc(ctx, n * 8));
+        GRB_TRY(k1.alloc(ctx, n * 8));
+        GRB_TRY(v0.alloc(ctx, n * 4));
+        GRB_TRY(v1.alloc(ctx, n * 4));
+        k_rank_keys<<<blocks_for(n, 256), 256, 0, ctx->stream>>>(ix->score_a, ix->has_nulls ? ix->vbits_a : nullptr, n, k0.as<u64>(),
+                                                                v0.as<u32>());
+        GRB_LAUNCHED(ctx);
+        u64 *ks;
+        u32 *vs;
+        GRB_TRY(grb_sort_pairs(ctx, k0.as<u64>(), v0.as<u32>(), k1.as<u64>(), v1.as<u32>(), n, &ks, &vs, nullptr));
+        k_rank_scatter<<<blocks_for(n + PAD, 256), 256, 0, ctx->stream>>>(ks, vs, n, ix->n_valid, ix->rank_a, ix->score_sorted);
+        GRB_LAUNCHED(ctx);
+    }
+    if (!ix->fb) {
+        const size_t nb = (n + 63) >> GRB_BME_SHIFT;
+        TempBuf pm;
+        GRB_TRY(pm.alloc(ctx, nb * 4));
+        GRB_TRY(dev_alloc(ctx, (void **)&ix->fb, nb * 4));
+        k_prefix_max_single<<<1, 1024, 0, ctx->stream>>>(ix->bme, nb, pm.as<u32>());
+        GRB_LAUNCHED(ctx);
+        k_first_back<<<blocks_for(nb, 128), 128, 0, ctx->stream>>>(ix->starts, ix->ends, pm.as<u32>(), nb, ix->fb);
+        GRB_LAUNCHED(ctx);
+    }
+    ix->members_ready = true;
+    return GRB_OK;
+}
+
+extern "C" {
 
 int grb_index_copy_sorted(const grb_index *ix, uint32_t *starts, uint32_t *ends, uint64_t *data_idx) {
     if (!ix) return GRB_ERR_INVALID_ARG;

@@ -485,15 +485,6 @@ struct SweepOut {
     u32 *heavy_count;
 };
 
-__device__ __forceinline__ u64 f64_key(double x) {
-    u64 b = (u64)__double_as_longlong(x);
-    return (b >> 63) ? ~b : (b | (1ull << 63));
-}
-__device__ __forceinline__ double key_f64(u64 k) {
-    u64 b = (k >> 63) ? (k & ~(1ull << 63)) : ~k;
-    return __longlong_as_double((long long)b);
-}
-
 __device__ __forceinline__ bool score_valid(const SeqDev *sd, u32 j) {
     if (!sd->has_scores) return false;
     if (!sd->has_nulls) return true;
@@ -602,6 +593,7 @@ __global__ void k_pairs_widths(const u32 *__restrict__ pos, const u64 *__restric
 }
 
 #include "sweep.cuh"
+#include "sweep3.cuh"
 
 // filter_overlaps as a stream compaction: keep flags -> exclusive scan -> scatter of the kept left indices
 // (ascending, i.e. the reference's order-preserving filter, src/granges.rs:1485-1508).
@@ -653,6 +645,9 @@ int make_batch(grb_ctx *ctx, const grb_index *const *idx, const u64 *left_offset
             d.pfx_b = ix->pfx_b;
             d.lut_a = ix->lut_a;
             d.lut_b = ix->lut_b;
+            d.rank_a = ix->rank_a;
+            d.score_sorted = ix->score_sorted;
+            d.fb = ix->fb;
             d.lut_shift = ix->lut_shift;
             d.lut_bmax = ix->lut_bmax;
             d.base_a = ix->base_a;
@@ -1033,6 +1028,18 @@ static int map_joins_impl(grb_ctx *ctx, const grb_index *const *idx, const uint6
             return grb_fail(ctx, GRB_ERR_NAN_SCORE, "map_joins: median over NaN scores (the reference panics in partial_cmp().unwrap())");
         if (need_sum && ix->n && ix->sum_mode == GRB_SUM_SWEEP) need_members = true;
     }
+    // MIN / MAX / MEDIAN alone (beside reductions the prefix sums answer) take the staged rank sweep; its tables
+    // are built the first time an index is asked for them
+    bool rank_sweep = ctx->sweep_mode != 0 && need_members && !want_bp && k <= 8;
+    for (int s = 0; s < nseq && rank_sweep; s++) {
+        const grb_index *ix = idx ? idx[s] : nullptr;
+        if (!ix || !ix->n) continue;
+        if (ix->has_nonfinite || ix->n >= 0x7fffffffu || (need_sum && ix->sum_mode == GRB_SUM_SWEEP)) rank_sweep = false;
+    }
+    for (int s = 0; s < nseq && rank_sweep; s++) {
+        const grb_index *ix = idx ? idx[s] : nullptr;
+        if (ix && ix->n && !ix->members_ready) GRB_TRY(grb_index_prepare_members(ctx, const_cast<grb_index *>(ix)));
+    }
     Batch b;
     GRB_TRY(make_batch(ctx, idx, left_offsets, nseq, &b));
     if (b.total == 0) return GRB_OK;
@@ -1081,7 +1088,17 @@ static int map_joins_impl(grb_ctx *ctx, const grb_index *const *idx, const uint6
             so.heavy_count = heavy.as<u32>();
             so.heavy_list = heavy.as<u32>() + 1;
         }
-        k_sweep2<<<b.ntiles, SW2_TPB, 0, ctx->stream>>>(b.seqs, b.tile_begin, b.nseq, dls.as<u32>(), dle.as<u32>(), o.ub, o.pp, o.lb, so);
+        if (rank_sweep) {
+            static bool configured = false;
+            if (!configured) {
+                GRB_CUDA(ctx, cudaFuncSetAttribute(k_sweep3, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(Sweep3Smem)));
+                configured = true;
+            }
+            k_sweep3<<<b.ntiles, SW3_TPB, sizeof(Sweep3Smem), ctx->stream>>>(b.seqs, b.tile_begin, b.nseq, dls.as<u32>(), o.ub, o.pp, o.lb, so,
+                                                                            ctx->sweep_mode == 1 ? 1 : 0);
+        } else {
+            k_sweep2<<<b.ntiles, SW2_TPB, 0, ctx->stream>>>(b.seqs, b.tile_begin, b.nseq, dls.as<u32>(), dle.as<u32>(), o.ub, o.pp, o.lb, so);
+        }
         GRB_LAUNCHED(ctx);
         if (want_median) {
             k_median_heavy<<<ctx->sm_count * 4, SW_TPB, 0, ctx->stream>>>(b.seqs, b.nseq, dls.as<u32>(), o.ub, o.lb, so.heavy_list,

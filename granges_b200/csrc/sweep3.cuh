@@ -1,0 +1,414 @@
+// sweep3.cuh -- staged member sweep: MIN / MAX / MEDIAN over score *ranks*.  Included by query.cu.
+//
+// Same group structure as sweep.cuh (k_tile<M_UBLB> has resolved ub, pp, lb per left; the members are
+// [pp, ub) plus pp - lb straddlers below pp), but
+//   * a CTA stages the slice of `ends`, `rank_a` and `bme` its lefts can touch into shared memory with
+//     bulk copies: consecutive (sorted) lefts share almost all of it, and no lane ever waits on a chain of
+//     dependent global loads.  The slice starts at fb[..] (index.cu: k_first_back), the precomputed bound on
+//     how far back a straddler can sit, and ends at the largest ub.  A run of lefts whose slice does not
+//     fit is halved until it does; below 32 lefts the groups walk global memory instead (same code);
+//   * the members' scores are replaced by their ranks (32-bit, all different): MIN / MAX are integer
+//     min / max, the median is a quickselect over 32-bit keys, and only the answers are translated back
+//     through score_sorted[] -- by loads that are issued one left ahead of the stores that need them.
+// Used when every index of the batch has its member tables, there are at most 8 reductions and no non-finite score (MIN / MAX skip
+// those: src/data/operations.rs:71-86); k_sweep2 keeps the overlap-width reductions and the rest.
+
+constexpr int SW3_TPB = 256;
+constexpr u32 SW3_WCAP = 4096;      // rights per staged slice
+constexpr u32 SW3_KBUF = 4096;      // rank slots per CTA for the medians: 32 groups x 128 or 8 groups x 512
+constexpr u32 SW3_MIN_RUN = 32;     // runs shorter than this are not halved any further
+
+struct Sweep3Smem {
+    alignas(16) u32 ends[SW3_WCAP];
+    alignas(16) u32 rank[SW3_WCAP];
+    alignas(16) u32 bme[SW3_WCAP / 64 + 8];
+    u32 kbuf[SW3_KBUF];
+    alignas(8) u64 bar;
+    u32 red[3][SW3_TPB / 32];
+    u32 bcast[4];
+};
+
+// Median of m <= G * R different 32-bit keys held in kbuf[0, m) by a group of G lanes: a bitonic sorting network
+// over R registers per lane (element position = lane * R + register: small partner distances stay inside a
+// lane, the large ones are one shuffle per register), padded with low / high sentinels so that the middle pair
+// lands on positions N/2 - 1 and N/2; the last merge stops after its first step, where the lower half of the
+// lanes holds the N/2 smallest keys.  No data-dependent branch: the four groups of a warp stay in lockstep.
+// Keys are shifted by one so that 0 and 0xffffffff are free for the sentinels.  Returns key + 1 of the lower
+// and the upper middle (equal ranks are impossible; for odd m only `lo` is meaningful).
+template <int G, int R>
+__device__ __forceinline__ void bitonic_median(const u32 *kbuf, u32 m, u32 glane, u32 &lo, u32 &hi) {
+    constexpr u32 gmask = 0xffffffffu;  // the whole warp executes this together; the xor distances stay inside a group
+    constexpr int N = G * R;
+    const u32 L = (m & 1) ? (u32)(N / 2 - 1) - ((m - 1) >> 1) : (u32)(N / 2) - (m >> 1);  // low sentinels
+    u32 v[R];
+#pragma unroll
+    for (int r = 0; r < R; r++) {
+        const u32 i = (u32)r * G + glane;  // any assignment of the elements to the slots will do: coalesced reads
+        v[r] = i < m ? kbuf[i] + 1u : (i < m + L ? 0u : 0xffffffffu);
+    }
+    // sort inside the lane (ascending): bitonic network over the registers
+#pragma unroll
+    for (int k = 2; k <= R; k <<= 1) {
+#pragma unroll
+        for (int r = 0; r < R; r++) {  // flip step: r <-> r ^ (k - 1)
+            const int q = r ^ (k - 1);
+            if (q > r) {
+                const u32 a = v[r], b = v[q];
+                v[r] = min(a, b);
+                v[q] = max(a, b);
+            }
+        }
+#pragma unroll
+        for (int j = k >> 2; j >= 1; j >>= 1) {
+#pragma unroll
+            for (int r = 0; r < R; r++) {
+                const int q = r ^ j;
+                if (q > r) {
+                    const u32 a = v[r], b = v[q];
+                    v[r] = min(a, b);
+                    v[q] = max(a, b);
+                }
+            }
+        }
+    }
+    // merges across lanes: blocks of k = 2R, 4R, ... elements
+#pragma unroll
+    for (int k = 2 * R; k <= N; k <<= 1) {
+        {
+            // flip step: position e <-> e ^ (k - 1): lane ^ (k / R - 1), register R - 1 - r
+            const int lm = k / R - 1;
+            const bool lower = (glane & (u32)(k / (2 * R))) == 0;
+#pragma unroll
+            for (int r = 0; r < R / 2; r++) {
+                const u32 a = __shfl_xor_sync(gmask, v[R - 1 - r], lm);
+                const u32 b = __shfl_xor_sync(gmask, v[r], lm);
+                v[r] = lower ? min(v[r], a) : max(v[r], a);
+                v[R - 1 - r] = lower ? min(v[R - 1 - r], b) : max(v[R - 1 - r], b);
+            }
+        }
+        if (k == N) break;  // the halves are separated: no need to finish the merge
+#pragma unroll
+        for (int j = k >> 2; j >= R; j >>= 1) {
+            const int lm = j / R;
+            const bool lower = (glane & (u32)lm) == 0;
+#pragma unroll
+            for (int r = 0; r < R; r++) {
+                const u32 w = __shfl_xor_sync(gmask, v[r], lm);
+                v[r] = lower ? min(v[r], w) : max(v[r], w);
+            }
+        }
+#pragma unroll
+        for (int j = (R >> 1); j >= 1; j >>= 1) {
+#pragma unroll
+            for (int r = 0; r < R; r++) {
+                const int q = r ^ j;
+                if (q > r) {
+                    const u32 a = v[r], b = v[q];
+                    v[r] = min(a, b);
+                    v[q] = max(a, b);
+                }
+            }
+        }
+    }
+    const bool lower = glane < G / 2;
+    u32 x = v[0];
+#pragma unroll
+    for (int r = 1; r < R; r++) x = lower ? max(x, v[r]) : min(x, v[r]);
+#pragma unroll
+    for (int sft = G / 4; sft >= 1; sft >>= 1) {
+        const u32 y = __shfl_xor_sync(gmask, x, sft);
+        x = lower ? max(x, y) : min(x, y);
+    }
+    const u32 y = __shfl_xor_sync(gmask, x, G / 2);
+    lo = lower ? x : y;
+    hi = lower ? y : x;
+}
+
+template <int G, bool STAGED>
+__device__ __forceinline__ void sweep3_run(const SeqDev *__restrict__ sd, u64 c_lo, u64 c_hi, const u32 *__restrict__ ls,
+                                           const u32 *__restrict__ ubv, const u32 *__restrict__ ppv, const u32 *__restrict__ lbv,
+                                           const SweepOut &o, u64 ops_packed, const u32 *ends, const u32 *rank, const u32 *bme,
+                                           u32 *kbuf_all) {
+    // Warp-synchronous: the 32 / G groups of a warp take every step together (a group with nothing left to do
+    // is masked by its predicates), so every vote / shuffle is ONE full-warp instruction.  Per-group masks
+    // would make the hardware run each group's copy of the instruction in turn.
+    constexpr u32 FULL = 0xffffffffu;
+    constexpr u32 CAP = SW3_KBUF / (SW3_TPB / G);
+    constexpr int NGROUPS = SW3_TPB / G;
+    constexpr u32 GM = G == 32 ? 0xffffffffu : ((1u << G) - 1u);
+    const u32 glane = threadIdx.x & (G - 1), gidx = threadIdx.x / G;
+    const u32 gshift = (threadIdx.x & 31) & ~(G - 1);
+    const u32 lt = (1u << glane) - 1;
+    const bool has_nulls = sd->has_nulls != 0;
+    const double *__restrict__ sorted = sd->score_sorted;
+    u32 *kbuf = kbuf_all + (size_t)gidx * CAP;
+    const bool want_median = o.want_median != 0;
+    const int k = o.k;
+    // this lane's output column, if any (k <= 8 <= G)
+    const int my_op = (int)glane < k ? (int)((ops_packed >> (4 * glane)) & 15u) : -1;
+    // answers of the previous left: the loads are in flight while the next left is processed
+    u64 pend_g = ~0ull;
+    double pend_v1 = 0.0, pend_v2 = 0.0;
+    bool pend_ok = false, pend_two = false;
+
+    u64 g = c_lo + gidx;
+    u32 u = 0, p = 0, l = 0, lstart = 0;
+    if (g < c_hi) {
+        u = ubv[g];
+        p = ppv[g];
+        l = lbv[g];
+        lstart = ls[g];
+    }
+    const u64 g_warp = c_lo + (threadIdx.x >> 5) * (32 / G);
+    const u32 rounds = g_warp < c_hi ? (u32)((c_hi - g_warp + NGROUPS - 1) / NGROUPS) : 0u;
+    for (u32 round = 0; round < rounds; round++) {
+        const bool live = g < c_hi;
+        // parameters of the next left of this group
+        const u64 gn = g + NGROUPS;
+        u32 nu = 0, np = 0, nl = 0, nls = 0;
+        if (gn < c_hi) {
+            nu = ubv[gn];
+            np = ppv[gn];
+            nl = lbv[gn];
+            nls = ls[gn];
+        }
+        u32 nvalid = 0;
+        u32 rmin = GRB_RANK_NONE;  // unsigned min ignores NONE
+        int rmax = -1;             // signed max ignores NONE (ranks are below 2^31)
+        // ---- members that start inside the left: [p, u), ascending
+        const u32 fw = u > p ? u - p : 0u;
+        const u32 fw_steps = __reduce_max_sync(FULL, (fw + G - 1) / G);
+        for (u32 it = 0; it < fw_steps; it++) {
+            const u32 j = p + it * G + glane;
+            const u32 r = j < u ? rank[j] : GRB_RANK_NONE;
+            rmin = min(rmin, r);
+            rmax = max(rmax, (int)r);
+            if (has_nulls) {
+                const bool v = r != GRB_RANK_NONE;
+                const u32 vm = (__ballot_sync(FULL, v) >> gshift) & GM;
+                if (want_median && v) {
+                    const u32 slot = nvalid + __popc(vm & lt);
+                    if (slot < CAP) kbuf[slot] = r;
+                }
+                nvalid += __popc(vm);
+            } else if (want_median) {
+                const u32 slot = j - p;
+                if (j < u && slot < CAP) kbuf[slot] = r;
+            }
+        }
+        if (!has_nulls) nvalid = fw;
+        // ---- straddlers: below p, end > l.start; exactly p - l of them
+        const u32 need = p - l;
+        u32 found = 0;
+        int cb = p ? (int)((p - 1) & ~(u32)(G - 1)) : -1;
+        while (true) {
+            const bool act = found < need && cb >= 0;
+            if (!__any_sync(FULL, act)) break;
+            // a group either looks at G rights or skips the rest of a 64-block whose largest end cannot overlap
+            const bool look = act && bme[cb >> GRB_BME_SHIFT] > lstart;
+            const u32 j = (u32)cb + glane;
+            const bool hit = look && j < p && ends[j] > lstart;
+            const u32 hm = (__ballot_sync(FULL, hit) >> gshift) & GM;
+            const u32 r = hit ? rank[j] : GRB_RANK_NONE;
+            rmin = min(rmin, r);
+            rmax = max(rmax, (int)r);
+            u32 vm = hm;
+            bool v = hit;
+            if (has_nulls) {
+                v = r != GRB_RANK_NONE;
+                vm = (__ballot_sync(FULL, v) >> gshift) & GM;
+            }
+            if (want_median && v) {
+                const u32 slot = nvalid + __popc(vm & lt);
+                if (slot < CAP) kbuf[slot] = r;
+            }
+            found += __popc(hm);
+            nvalid += __popc(vm);
+            if (act) cb = look ? cb - G : ((cb >> GRB_BME_SHIFT) << GRB_BME_SHIFT) - G;
+        }
+#pragma unroll
+        for (int s = G / 2; s; s >>= 1) {
+            rmin = min(rmin, __shfl_xor_sync(FULL, rmin, s));
+            rmax = max(rmax, __shfl_xor_sync(FULL, rmax, s));
+        }
+        // ---- median: sorting network over the (all different) ranks; its size is the warp's largest group
+        bool heavy = false;
+        u32 med_lo = 0, med_hi = 0;
+        if (want_median) {
+            heavy = nvalid > CAP;
+            const u32 m = heavy ? 0u : nvalid;
+            const u32 mx = __reduce_max_sync(FULL, m);
+            __syncwarp();
+            if (mx) {
+                u32 a = 1, b = 1;
+                if (mx <= 2 * G)
+                    bitonic_median<G, 2>(kbuf, m, glane, a, b);
+                else if (mx <= 4 * G)
+                    bitonic_median<G, 4>(kbuf, m, glane, a, b);
+                else if (mx <= 8 * G)
+                    bitonic_median<G, 8>(kbuf, m, glane, a, b);
+                else
+                    bitonic_median<G, 16>(kbuf, m, glane, a, b);
+                med_lo = a - 1u;
+                med_hi = (m & 1) ? med_lo : b - 1u;
+            }
+        }
+        // ---- the previous left's answers have arrived by now: store them
+        if (pend_g != ~0ull) {
+            o.out[pend_g * (u64)k + glane] = pend_ok ? (pend_two ? (pend_v1 + pend_v2) / 2.0 : pend_v1) : 0.0;
+            o.out_valid[pend_g * (u64)k + glane] = pend_ok ? 1 : 0;
+            pend_g = ~0ull;
+        }
+        // ---- this left's answers: issue the translations rank -> score
+        {
+            u32 r1 = 0, r2 = 0;
+            bool ok = false, mine = false;
+            if (my_op == GRB_OP_MIN) {
+                mine = true;
+                ok = rmin != GRB_RANK_NONE;
+                r1 = r2 = rmin;
+            } else if (my_op == GRB_OP_MAX) {
+                mine = true;
+                ok = rmax >= 0;
+                r1 = r2 = (u32)rmax;
+            } else if (my_op == GRB_OP_MEDIAN) {
+                mine = !heavy;
+                ok = nvalid != 0;
+                r1 = med_lo;
+                r2 = med_hi;
+            }
+            if (mine && live) {
+                pend_g = g;
+                pend_ok = ok;
+                pend_two = r1 != r2;
+                if (ok) {
+                    pend_v1 = sorted[r1];
+                    pend_v2 = sorted[r2];
+                }
+            }
+        }
+        if (heavy && live && glane == 0) {
+            const u32 slot = atomicAdd(o.heavy_count, 1u);
+            o.heavy_list[slot] = (u32)g;  // the host checks total < 2^32 when a median is requested
+        }
+        __syncwarp();  // the next left reuses kbuf
+        g = gn;
+        u = nu;
+        p = np;
+        l = nl;
+        lstart = nls;
+    }
+    if (pend_g != ~0ull) {
+        o.out[pend_g * (u64)k + glane] = pend_ok ? (pend_two ? (pend_v1 + pend_v2) / 2.0 : pend_v1) : 0.0;
+        o.out_valid[pend_g * (u64)k + glane] = pend_ok ? 1 : 0;
+    }
+}
+
+// One CTA per tile of 1024 lefts (the tiling of k_tile).
+__global__ void __launch_bounds__(SW3_TPB, 3) k_sweep3(const SeqDev *__restrict__ seqs, const u32 *__restrict__ tile_begin, int nseq,
+                                                    const u32 *__restrict__ ls, const u32 *__restrict__ ubv,
+                                                    const u32 *__restrict__ ppv, const u32 *__restrict__ lbv, const SweepOut o,
+                                                    int stage_mode) {
+    extern __shared__ __align__(128) unsigned char sw3_raw[];
+    Sweep3Smem &S = *reinterpret_cast<Sweep3Smem *>(sw3_raw);
+    const u32 t = blockIdx.x, tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const SeqDev *__restrict__ sd = &seqs[find_seq_by_tile(tile_begin, nseq, t)];
+    const u64 g_first = ((sd->left_begin >> TILE_SHIFT) + (t - sd->tile_begin)) << TILE_SHIFT;
+    const u64 g_lo = sd->left_begin > g_first ? sd->left_begin : g_first;
+    const u64 g_hi = sd->left_end < g_first + TILE ? sd->left_end : g_first + TILE;
+    u64 ops_packed = 0;  // 4 bits per reduction (k <= 8): no dynamic indexing of the parameter block
+#pragma unroll
+    for (int c = 0; c < 8; c++)
+        if (c < o.k) ops_packed |= (u64)(o.ops[c] & 15) << (4 * c);
+    if (sd->n == 0 || !sd->has_scores) {
+        // absent seqname / no rights: every group is empty
+        for (u64 g = g_lo + tid; g < g_hi; g += SW3_TPB)
+            for (int c = 0; c < o.k; c++) {
+                const int op = (int)((ops_packed >> (4 * c)) & 15u);
+                if (op == GRB_OP_MIN || op == GRB_OP_MAX || op == GRB_OP_MEDIAN) {
+                    o.out[g * (u64)o.k + c] = 0.0;
+                    o.out_valid[g * (u64)o.k + c] = 0;
+                }
+            }
+        return;
+    }
+    if (tid == 0) {
+        mbar_init(&S.bar, 1);
+    }
+    __syncthreads();
+    u32 phase = 0;
+    u64 c_lo = g_lo;
+    u64 run = g_hi - g_lo;
+    while (c_lo < g_hi) {
+        const u64 c_hi = c_lo + run < g_hi ? c_lo + run : g_hi;
+        // the slice of rights this run of lefts can touch, and its members per left
+        u32 pmin = 0xffffffffu, umax = 0, mem = 0;
+        for (u64 g = c_lo + tid; g < c_hi; g += SW3_TPB) {
+            const u32 u = ubv[g], p = ppv[g];
+            pmin = min(pmin, p);
+            umax = max(umax, max(u, p));  // p > u only for an invalid left (flagged by k_tile); stay inside the slice
+            mem += u - lbv[g];
+        }
+        pmin = warp_min(pmin);
+        umax = warp_max(umax);
+        mem = warp_sum(mem);
+        if (lane == 0) {
+            S.red[0][warp] = pmin;
+            S.red[1][warp] = umax;
+            S.red[2][warp] = mem;
+        }
+        __syncthreads();
+        if (warp == 0) {
+            u32 a = lane < SW3_TPB / 32 ? S.red[0][lane] : 0xffffffffu;
+            u32 b = lane < SW3_TPB / 32 ? S.red[1][lane] : 0u;
+            u32 c = lane < SW3_TPB / 32 ? S.red[2][lane] : 0u;
+            a = warp_min(a);
+            b = warp_max(b);
+            c = warp_sum(c);
+            if (lane == 0) {
+                u32 wlo = a ? sd->fb[(a - 1) >> GRB_BME_SHIFT] : 0u;
+                wlo &= ~255u;  // bulk copies need 16-byte aligned sources, also for the block-max-end slice
+                S.bcast[0] = wlo;
+                S.bcast[1] = b;
+                S.bcast[2] = c;
+            }
+        }
+        __syncthreads();
+        const u32 wlo = S.bcast[0], whi = S.bcast[1];
+        const bool wide_groups = (u64)S.bcast[2] > 48ull * (c_hi - c_lo);
+        const u32 W = whi > wlo ? whi - wlo : 0u;
+        const bool fits = stage_mode && W <= SW3_WCAP;
+        if (!fits && stage_mode && c_hi - c_lo > SW3_MIN_RUN) {
+            run = (c_hi - c_lo + 1) >> 1;
+            __syncthreads();  // S.bcast is rewritten by the next attempt
+            continue;
+        }
+        if (fits) {
+            if (tid == 0 && W) {
+                const u32 bytes = ((W + 3) & ~3u) * 4;
+                const u32 nb = ((whi + 63) >> GRB_BME_SHIFT) - (wlo >> GRB_BME_SHIFT);
+                const u32 bbytes = ((nb + 3) & ~3u) * 4;
+                mbar_arrive_expect_tx(&S.bar, 2 * bytes + bbytes);
+                tma_load_1d(S.ends, sd->ends + wlo, bytes, &S.bar);
+                tma_load_1d(S.rank, sd->rank_a + wlo, bytes, &S.bar);
+                tma_load_1d(S.bme, sd->bme + (wlo >> GRB_BME_SHIFT), bbytes, &S.bar);
+            }
+            if (W) {
+                mbar_wait(&S.bar, phase);
+                phase ^= 1;
+            }
+            const u32 *e_p = S.ends - wlo, *r_p = S.rank - wlo, *b_p = S.bme - (wlo >> GRB_BME_SHIFT);
+            if (wide_groups)
+                sweep3_run<32, true>(sd, c_lo, c_hi, ls, ubv, ppv, lbv, o, ops_packed, e_p, r_p, b_p, S.kbuf);
+            else
+                sweep3_run<8, true>(sd, c_lo, c_hi, ls, ubv, ppv, lbv, o, ops_packed, e_p, r_p, b_p, S.kbuf);
+        } else {
+            if (wide_groups)
+                sweep3_run<32, false>(sd, c_lo, c_hi, ls, ubv, ppv, lbv, o, ops_packed, sd->ends, sd->rank_a, sd->bme, S.kbuf);
+            else
+                sweep3_run<8, false>(sd, c_lo, c_hi, ls, ubv, ppv, lbv, o, ops_packed, sd->ends, sd->rank_a, sd->bme, S.kbuf);
+        }
+        __syncthreads();  // the slice and S.bcast are rewritten by the next run
+        c_lo = c_hi;
+    }
+}

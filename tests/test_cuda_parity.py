@@ -535,3 +535,72 @@ def test_large_groups_exact_128bit_path(eng, orc, op, kind):
             assert ov[i, 0] == 0
         else:
             assert ov[i, 0] == 1 and out[i, 0] == want, (i, out[i, 0], want)
+
+
+RANK_SWEEP_CASES = {
+    "sorted": dict(nl=6000, nr=9000, span=120000, maxlen=999, sorted_left=True),
+    "unsorted": dict(nl=3000, nr=5000, span=60000, maxlen=999),
+    "nulls-ties": dict(nl=5000, nr=7000, span=90000, maxlen=500, sorted_left=True, null_frac=0.4, score_kind="int"),
+    "long-rights": dict(nl=4000, nr=20000, span=300000, maxlen=300, long_frac=0.01, sorted_left=True),
+    "dense": dict(nl=2500, nr=40000, span=20000, maxlen=400, sorted_left=True),
+    "very-dense": dict(nl=1200, nr=60000, span=6000, maxlen=900, sorted_left=True, null_frac=0.1),
+    "mixed-sign": dict(nl=3000, nr=3000, span=30000, maxlen=700, sorted_left=True, score_kind="mixed"),
+}
+
+
+@pytest.mark.parametrize("name", list(RANK_SWEEP_CASES))
+def test_rank_sweep_modes(orc, monkeypatch, name):
+    """MIN / MAX / MEDIAN through the staged rank sweep (k_sweep3: slices of ends / ranks in shared memory,
+    halved runs, global fallback), the same kernel without staging, and the older score sweep (k_sweep2):
+    bit-identical to each other and to the oracle -- slices that do not fit, groups beyond the in-group
+    buffers (radix-select path), None scores, ties, unsorted lefts."""
+    import granges_b200 as gb
+
+    kw = dict(RANK_SWEEP_CASES[name])
+    nl, nr = kw.pop("nl"), kw.pop("nr")
+    c = random_case(4242 + nl, nl, nr, **kw)
+    ops = ["min", "count", "median", "mean", "max"]
+    res = {}
+    for mode in ("1", "2", "0"):
+        monkeypatch.setenv("GRB_SWEEP_MODE", mode)
+        ctx = gb.Context(0)
+        ix = ctx.index_build(c["rs"], c["re"]).set_scores(c["scores"], c["valid"])
+        res[mode] = ctx.map_joins(ix, c["ls"], c["le"], ops)
+        # a second call reuses the member tables
+        again = ctx.map_joins(ix, c["ls"], c["le"], ["median"])
+        assert (again[1][:, 0] == res[mode][1][:, 2]).all()
+        m = again[1][:, 0] == 1
+        assert (again[0][m, 0] == res[mode][0][m, 2]).all()
+    t = orc.Tree(c["rs"], c["re"])
+    want, wv = orc.map_joins(t, c["scores"], c["valid"], c["ls"], c["le"], ops)
+    for mode in res:
+        out, ov = res[mode]
+        assert (ov == wv).all(), mode
+        for col, op in enumerate(ops):
+            m = wv[:, col] == 1
+            if op == "mean":
+                assert np.allclose(out[m, col], want[m, col], rtol=1e-12, atol=0), (mode, op)
+            else:
+                assert (out[m, col] == want[m, col]).all(), (mode, op)
+
+
+def test_rank_sweep_batch_with_absent_seqnames(eng, orc):
+    """Whole-GRanges MIN / MAX / MEDIAN call: an absent seqname, an empty index and one without lefts."""
+    cases = [random_case(900 + i, nl, nr, span=50000, maxlen=800, sorted_left=True, null_frac=nf)
+             for i, (nl, nr, nf) in enumerate([(3000, 4000, 0.0), (1500, 0, 0.0), (0, 500, 0.0), (2100, 2600, 0.3), (700, 900, 0.0)])]
+    ops = ["median", "max", "min"]
+    idxs = [None if i == 1 else eng.build(c["rs"], c["re"], None, c["scores"], c["valid"]) for i, c in enumerate(cases)]
+    off = np.concatenate([[0], np.cumsum([len(c["ls"]) for c in cases])]).astype(np.uint64)
+    ls = np.concatenate([c["ls"] for c in cases])
+    le = np.concatenate([c["le"] for c in cases])
+    out, ov = eng.ctx.map_joins_batch(idxs, off, ls, le, ops)
+    for i, c in enumerate(cases):
+        sl = slice(int(off[i]), int(off[i + 1]))
+        if i == 1:
+            assert (ov[sl] == 0).all()
+            continue
+        t = orc.Tree(c["rs"], c["re"])
+        want, wv = orc.map_joins(t, c["scores"], c["valid"], c["ls"], c["le"], ops)
+        assert (ov[sl] == wv).all()
+        m = wv == 1
+        assert (out[sl][m] == want[m]).all()
