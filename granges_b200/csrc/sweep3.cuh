@@ -15,7 +15,7 @@
 
 constexpr int SW3_TPB = 256;
 constexpr u32 SW3_WCAP = 4096;      // rights per staged slice
-constexpr u32 SW3_KBUF = 4096;      // rank slots per CTA for the medians: 32 groups x 128 or 8 groups x 512
+constexpr u32 SW3_KBUF = 4096;      // rank slots per CTA for the medians: 32 groups x 128, 16 x 256 or 8 x 512
 constexpr u32 SW3_MIN_RUN = 32;     // runs shorter than this are not halved any further
 
 struct Sweep3Smem {
@@ -375,7 +375,10 @@ __global__ void __launch_bounds__(SW3_TPB, 3) k_sweep3(const SeqDev *__restrict_
         }
         __syncthreads();
         const u32 wlo = S.bcast[0], whi = S.bcast[1];
-        const bool wide_groups = (u64)S.bcast[2] > 48ull * (c_hi - c_lo);
+        // lanes per left: 8 up to ~64 members per left on average, 16 up to ~150, else a whole warp (the in-group
+        // median buffers hold 16 ranks per lane, and a left's members range from half to twice the average)
+        const u64 avg_den = c_hi - c_lo;
+        const int gsel = (u64)S.bcast[2] > 150ull * avg_den ? 32 : (u64)S.bcast[2] > 64ull * avg_den ? 16 : 8;
         const u32 W = whi > wlo ? whi - wlo : 0u;
         const bool fits = stage_mode && W <= SW3_WCAP;
         if (!fits && stage_mode && c_hi - c_lo > SW3_MIN_RUN) {
@@ -398,13 +401,17 @@ __global__ void __launch_bounds__(SW3_TPB, 3) k_sweep3(const SeqDev *__restrict_
                 phase ^= 1;
             }
             const u32 *e_p = S.ends - wlo, *r_p = S.rank - wlo, *b_p = S.bme - (wlo >> GRB_BME_SHIFT);
-            if (wide_groups)
+            if (gsel == 32)
                 sweep3_run<32, true>(sd, c_lo, c_hi, ls, ubv, ppv, lbv, o, ops_packed, e_p, r_p, b_p, S.kbuf);
+            else if (gsel == 16)
+                sweep3_run<16, true>(sd, c_lo, c_hi, ls, ubv, ppv, lbv, o, ops_packed, e_p, r_p, b_p, S.kbuf);
             else
                 sweep3_run<8, true>(sd, c_lo, c_hi, ls, ubv, ppv, lbv, o, ops_packed, e_p, r_p, b_p, S.kbuf);
         } else {
-            if (wide_groups)
+            if (gsel == 32)
                 sweep3_run<32, false>(sd, c_lo, c_hi, ls, ubv, ppv, lbv, o, ops_packed, sd->ends, sd->rank_a, sd->bme, S.kbuf);
+            else if (gsel == 16)
+                sweep3_run<16, false>(sd, c_lo, c_hi, ls, ubv, ppv, lbv, o, ops_packed, sd->ends, sd->rank_a, sd->bme, S.kbuf);
             else
                 sweep3_run<8, false>(sd, c_lo, c_hi, ls, ubv, ppv, lbv, o, ops_packed, sd->ends, sd->rank_a, sd->bme, S.kbuf);
         }

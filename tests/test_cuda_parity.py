@@ -542,6 +542,7 @@ RANK_SWEEP_CASES = {
     "unsorted": dict(nl=3000, nr=5000, span=60000, maxlen=999),
     "nulls-ties": dict(nl=5000, nr=7000, span=90000, maxlen=500, sorted_left=True, null_frac=0.4, score_kind="int"),
     "long-rights": dict(nl=4000, nr=20000, span=300000, maxlen=300, long_frac=0.01, sorted_left=True),
+    "mid-dense": dict(nl=4000, nr=12000, span=60000, maxlen=500, sorted_left=True),
     "dense": dict(nl=2500, nr=40000, span=20000, maxlen=400, sorted_left=True),
     "very-dense": dict(nl=1200, nr=60000, span=6000, maxlen=900, sorted_left=True, null_frac=0.1),
     "mixed-sign": dict(nl=3000, nr=3000, span=30000, maxlen=700, sorted_left=True, score_kind="mixed"),
