@@ -176,6 +176,9 @@ struct grb_index {
     u32 *rank_a;          // n + pad, start order: rank of the right's score among the valid scores, ordered by
                           // (score, position) -- all different; GRB_RANK_NONE when the score is None
     double *score_sorted; // n_valid: the scores in rank order
+    // overlap-bp tables, built on first use by grb_index_prepare_bp
+    u64 *sum_starts;      // n + 1: sum of the i smallest starts
+    u64 *sum_ends;        // n + 1: sum of the i smallest ends
     u32 *fb;              // ceil(n/64): fb[b] <= position of the earliest right that straddles any coordinate
                           // >= starts[64 b]  (how far back a window over the rights must reach)
 };
@@ -192,6 +195,7 @@ struct SeqDev {
     const u32 *lut_a, *lut_b;
     const u32 *rank_a, *fb;
     const double *score_sorted;
+    const u64 *sum_starts, *sum_ends;
     u64 left_begin, left_end;
     double scale;    // 2^e0
     u32 n;
@@ -294,6 +298,8 @@ int grb_scan_u32_to_u32(grb_ctx *ctx, const u32 *in, u32 *out, size_t n, bool wr
 
 // index.cu: build the member-sweep tables of an index (rank_a, score_sorted, fb) if they are not there yet.
 int grb_index_prepare_members(grb_ctx *ctx, grb_index *ix);
+// index.cu: prefix sums of the sorted starts / ends (the closed form of OVERLAP_BP), built on first use.
+int grb_index_prepare_bp(grb_ctx *ctx, grb_index *ix);
 
 // sort.cu: stable LSD radix sort of (u64 key, u32 value) pairs; skips digits that do not vary and
 // the whole sort when the keys are already non-decreasing.  On return *keys_out / *vals_out point

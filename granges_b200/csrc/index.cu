@@ -564,6 +564,8 @@ void grb_index_destroy(grb_index *ix) {
     grb_dev_free(ix->ctx, ix->lut_a);
     grb_dev_free(ix->ctx, ix->lut_b);
     grb_dev_free(ix->ctx, ix->fb);
+    grb_dev_free(ix->ctx, ix->sum_starts);
+    grb_dev_free(ix->ctx, ix->sum_ends);
     free(ix);
 }
 
@@ -758,6 +760,19 @@ int grb_index_prepare_members(grb_ctx *ctx, grb_index *ix) {
         GRB_LAUNCHED(ctx);
     }
     ix->members_ready = true;
+    return GRB_OK;
+}
+
+// sum_starts[i] / sum_ends[i] = sum of the i smallest starts / ends (exact: below 2^63).  With them the overlap
+// bp of a left with ALL rights is F(l.end) - F(l.start), F(x) = sum_r |[r.start, r.end) & [0, x)|
+//   = sum_ends[#{end <= x}] - sum_starts[#{start < x}] + x * (#{start < x} - #{end <= x}):  no member is visited.
+int grb_index_prepare_bp(grb_ctx *ctx, grb_index *ix) {
+    if (!ix || ix->sum_starts || !ix->n) return GRB_OK;
+    const size_t n = ix->n;
+    GRB_TRY(dev_alloc(ctx, (void **)&ix->sum_starts, (n + 1) * 8));
+    GRB_TRY(dev_alloc(ctx, (void **)&ix->sum_ends, (n + 1) * 8));
+    GRB_TRY(grb_scan_u32_to_u64(ctx, ix->starts, ix->sum_starts, n, true));
+    GRB_TRY(grb_scan_u32_to_u64(ctx, ix->ends_sorted, ix->sum_ends, n, true));
     return GRB_OK;
 }
 

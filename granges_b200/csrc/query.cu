@@ -595,6 +595,41 @@ __global__ void k_pairs_widths(const u32 *__restrict__ pos, const u64 *__restric
 #include "sweep.cuh"
 #include "sweep3.cuh"
 
+// OVERLAP_BP (sum of LeftGroupedJoin::overlap_widths, join.rs:158-163) in closed form from ub / pp / lb and the
+// prefix sums of the sorted starts / ends (index.cu: grb_index_prepare_bp): one more bounded search per left.
+__global__ void __launch_bounds__(256) k_overlap_bp(const SeqDev *__restrict__ seqs, int nseq, u64 total, const u32 *__restrict__ ls,
+                                                    const u32 *__restrict__ le, const u32 *__restrict__ ubv,
+                                                    const u32 *__restrict__ ppv, const u32 *__restrict__ lbv,
+                                                    double *__restrict__ out, u8 *__restrict__ out_valid, int k, u32 col_mask) {
+    const u64 g = (u64)blockIdx.x * blockDim.x + threadIdx.x;
+    if (g >= total) return;
+    const SeqDev *__restrict__ sd = &seqs[find_seq_by_left(seqs, nseq, g)];
+    u64 bp = 0;
+    if (sd->n) {
+        const u32 u = ubv[g], p = ppv[g], l = lbv[g], a = ls[g], b = le[g];
+        // #{end <= l.end} lies in [lb, ub]: an end <= l.start is <= l.end, and end <= l.end implies start < l.end
+        u32 lo = l, hi = u;
+        if (hi < lo) hi = lo;  // invalid left (flagged elsewhere)
+        const u32 *__restrict__ es = sd->ends_sorted;
+        while (lo < hi) {
+            const u32 mid = lo + ((hi - lo) >> 1);
+            if (es[mid] <= b)
+                lo = mid + 1;
+            else
+                hi = mid;
+        }
+        const u32 a2 = lo;
+        const u64 f_end = sd->sum_ends[a2] - sd->sum_starts[u] + (u64)b * (u64)(u - a2);
+        const u64 f_start = sd->sum_ends[l] - sd->sum_starts[p] + (u64)a * (u64)(p - l);
+        bp = f_end - f_start;
+    }
+    for (int c = 0; c < k; c++)
+        if ((col_mask >> c) & 1u) {
+            out[g * (u64)k + c] = (double)bp;
+            out_valid[g * (u64)k + c] = 1;
+        }
+}
+
 // filter_overlaps as a stream compaction: keep flags -> exclusive scan -> scatter of the kept left indices
 // (ascending, i.e. the reference's order-preserving filter, src/granges.rs:1485-1508).
 __global__ void k_keep_to_u32(const u8 *__restrict__ keep, u64 n, u32 *__restrict__ flags) {
@@ -648,6 +683,8 @@ int make_batch(grb_ctx *ctx, const grb_index *const *idx, const u64 *left_offset
             d.rank_a = ix->rank_a;
             d.score_sorted = ix->score_sorted;
             d.fb = ix->fb;
+            d.sum_starts = ix->sum_starts;
+            d.sum_ends = ix->sum_ends;
             d.lut_shift = ix->lut_shift;
             d.lut_bmax = ix->lut_bmax;
             d.base_a = ix->base_a;
@@ -1028,6 +1065,26 @@ static int map_joins_impl(grb_ctx *ctx, const grb_index *const *idx, const uint6
             return grb_fail(ctx, GRB_ERR_NAN_SCORE, "map_joins: median over NaN scores (the reference panics in partial_cmp().unwrap())");
         if (need_sum && ix->n && ix->sum_mode == GRB_SUM_SWEEP) need_members = true;
     }
+    // OVERLAP_BP has a closed form (k_overlap_bp) unless the weighted mean needs the members' widths anyway
+    const bool bp_closed = want_bp && !want_wm && ctx->sweep_mode != 0;
+    u32 bp_cols = 0;
+    if (bp_closed) {
+        bool others = false;
+        for (int c = 0; c < k; c++) {
+            if (ops[c] == GRB_OP_OVERLAP_BP)
+                bp_cols |= 1u << c;
+            else if (ops[c] == GRB_OP_MIN || ops[c] == GRB_OP_MAX || ops[c] == GRB_OP_MEDIAN)
+                others = true;
+        }
+        want_bp = false;
+        need_members = others;
+        for (int s = 0; s < nseq; s++) {
+            const grb_index *ix = idx ? idx[s] : nullptr;
+            if (!ix || !ix->n) continue;
+            if (need_sum && ix->sum_mode == GRB_SUM_SWEEP) need_members = true;
+            GRB_TRY(grb_index_prepare_bp(ctx, const_cast<grb_index *>(ix)));
+        }
+    }
     // MIN / MAX / MEDIAN alone (beside reductions the prefix sums answer) take the staged rank sweep; its tables
     // are built the first time an index is asked for them
     bool rank_sweep = ctx->sweep_mode != 0 && need_members && !want_bp && k <= 8;
@@ -1061,7 +1118,7 @@ static int map_joins_impl(grb_ctx *ctx, const grb_index *const *idx, const uint6
     o.k = k;
     o.need_sum = need_sum;
     for (int c = 0; c < k; c++) o.ops[c] = ops[c];
-    if (!need_members) {
+    if (!need_members && !bp_cols) {
         GRB_TRY(launch_map<M_MAP>(ctx, b, dls.as<u32>(), dle.as<u32>(), o));
     } else {
         TempBuf ub, lb, pp, heavy;
@@ -1072,38 +1129,45 @@ static int map_joins_impl(grb_ctx *ctx, const grb_index *const *idx, const uint6
         o.lb = lb.as<u32>();
         o.pp = pp.as<u32>();
         GRB_TRY(launch_map<M_MAP | M_UBLB>(ctx, b, dls.as<u32>(), dle.as<u32>(), o));
-        SweepOut so;
-        memset(&so, 0, sizeof(so));
-        so.out = o.out;
-        so.out_valid = o.out_valid;
-        so.k = k;
-        for (int c = 0; c < k; c++) so.ops[c] = ops[c];
-        so.want_median = want_median;
-        so.want_bp = want_bp;
-        so.want_wm = want_wm;
-        if (want_median) {
-            if (b.total >= 0xffffffffull) return grb_fail(ctx, GRB_ERR_UNSUPPORTED, "map_joins: median over more than 2^32-1 lefts per call");
-            GRB_TRY(heavy.alloc(ctx, (b.total + 1) * 4));
-            GRB_CUDA(ctx, cudaMemsetAsync(heavy.p, 0, 4, ctx->stream));
-            so.heavy_count = heavy.as<u32>();
-            so.heavy_list = heavy.as<u32>() + 1;
-        }
-        if (rank_sweep) {
-            static bool configured = false;
-            if (!configured) {
-                GRB_CUDA(ctx, cudaFuncSetAttribute(k_sweep3, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(Sweep3Smem)));
-                configured = true;
-            }
-            k_sweep3<<<b.ntiles, SW3_TPB, sizeof(Sweep3Smem), ctx->stream>>>(b.seqs, b.tile_begin, b.nseq, dls.as<u32>(), o.ub, o.pp, o.lb, so,
-                                                                            ctx->sweep_mode == 1 ? 1 : 0);
-        } else {
-            k_sweep2<<<b.ntiles, SW2_TPB, 0, ctx->stream>>>(b.seqs, b.tile_begin, b.nseq, dls.as<u32>(), dle.as<u32>(), o.ub, o.pp, o.lb, so);
-        }
-        GRB_LAUNCHED(ctx);
-        if (want_median) {
-            k_median_heavy<<<ctx->sm_count * 4, SW_TPB, 0, ctx->stream>>>(b.seqs, b.nseq, dls.as<u32>(), o.ub, o.lb, so.heavy_list,
-                                                                          so.heavy_count, so);
+        if (bp_cols) {
+            k_overlap_bp<<<(unsigned)((b.total + 255) / 256), 256, 0, ctx->stream>>>(b.seqs, b.nseq, b.total, dls.as<u32>(), dle.as<u32>(), o.ub,
+                                                                                   o.pp, o.lb, o.out, o.out_valid, k, bp_cols);
             GRB_LAUNCHED(ctx);
+        }
+        if (need_members) {
+            SweepOut so;
+            memset(&so, 0, sizeof(so));
+            so.out = o.out;
+            so.out_valid = o.out_valid;
+            so.k = k;
+            for (int c = 0; c < k; c++) so.ops[c] = ops[c];
+            so.want_median = want_median;
+            so.want_bp = want_bp;
+            so.want_wm = want_wm;
+            if (want_median) {
+                if (b.total >= 0xffffffffull) return grb_fail(ctx, GRB_ERR_UNSUPPORTED, "map_joins: median over more than 2^32-1 lefts per call");
+                GRB_TRY(heavy.alloc(ctx, (b.total + 1) * 4));
+                GRB_CUDA(ctx, cudaMemsetAsync(heavy.p, 0, 4, ctx->stream));
+                so.heavy_count = heavy.as<u32>();
+                so.heavy_list = heavy.as<u32>() + 1;
+            }
+            if (rank_sweep) {
+                static bool configured = false;
+                if (!configured) {
+                    GRB_CUDA(ctx, cudaFuncSetAttribute(k_sweep3, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(Sweep3Smem)));
+                    configured = true;
+                }
+                k_sweep3<<<b.ntiles, SW3_TPB, sizeof(Sweep3Smem), ctx->stream>>>(b.seqs, b.tile_begin, b.nseq, dls.as<u32>(), o.ub, o.pp, o.lb, so,
+                                                                                ctx->sweep_mode == 1 ? 1 : 0);
+            } else {
+                k_sweep2<<<b.ntiles, SW2_TPB, 0, ctx->stream>>>(b.seqs, b.tile_begin, b.nseq, dls.as<u32>(), dle.as<u32>(), o.ub, o.pp, o.lb, so);
+            }
+            GRB_LAUNCHED(ctx);
+            if (want_median) {
+                k_median_heavy<<<ctx->sm_count * 4, SW_TPB, 0, ctx->stream>>>(b.seqs, b.nseq, dls.as<u32>(), o.ub, o.lb, so.heavy_list,
+                                                                              so.heavy_count, so);
+                GRB_LAUNCHED(ctx);
+            }
         }
     }
     GRB_TRY(dout.finish(ctx));

@@ -258,6 +258,7 @@ __device__ __forceinline__ void sweep_tile(const SeqDev *__restrict__ sd, u64 g_
                         }
                         break;
                     case GRB_OP_OVERLAP_BP:
+                        mine = WIDTHS;  // otherwise k_overlap_bp answers it in closed form
                         ok = 1;
                         r = (double)bp;
                         break;

@@ -605,3 +605,30 @@ def test_rank_sweep_batch_with_absent_seqnames(eng, orc):
         assert (ov[sl] == wv).all()
         m = wv == 1
         assert (out[sl][m] == want[m]).all()
+
+
+@pytest.mark.parametrize("name", ["sorted", "unsorted", "long-rights", "mid-dense", "nulls-ties"])
+@pytest.mark.parametrize("ops", [["overlap-bp"], ["min", "overlap-bp", "mean", "median"], ["overlap-bp", "weighted-mean"]],
+                         ids=["bp", "bp+members", "bp+wm"])
+def test_overlap_bp_closed_form(eng, orc, name, ops):
+    """OVERLAP_BP from the prefix sums of the sorted starts / ends (k_overlap_bp, no member visited) is exact;
+    beside a weighted mean it still comes from the member sweep -- same numbers."""
+    kw = dict(RANK_SWEEP_CASES[name])
+    nl, nr = kw.pop("nl"), kw.pop("nr")
+    c = random_case(777 + nr, nl, nr, **kw)
+    ix = eng.build(c["rs"], c["re"], None, c["scores"], c["valid"])
+    out, ov = eng.map_joins(ix, c["ls"], c["le"], ops)
+    t = orc.Tree(c["rs"], c["re"])
+    want, wv = orc.map_joins(t, c["scores"], c["valid"], c["ls"], c["le"], ops)
+    assert (ov == wv).all()
+    for col, op in enumerate(ops):
+        m = wv[:, col] == 1
+        if op in ("mean", "weighted-mean"):
+            assert np.allclose(out[m, col], want[m, col], rtol=1e-12, atol=0), op
+        else:
+            assert (out[m, col] == want[m, col]).all(), op
+    # brute force for the bp column
+    col = ops.index("overlap-bp")
+    for i in range(0, nl, max(1, nl // 200)):
+        w = np.minimum(c["re"], c["le"][i]).astype(np.int64) - np.maximum(c["rs"], c["ls"][i]).astype(np.int64)
+        assert out[i, col] == w[w > 0].sum()
