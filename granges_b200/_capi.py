@@ -62,6 +62,13 @@ SIGNATURES = {
     "grb_ranges_dev_starts": (vp, [vp]),
     "grb_ranges_dev_ends": (vp, [vp]),
     "grb_ranges_destroy": (None, [vp]),
+    "grb_merge_ranges": (C.c_int, [vp, vp, vp, u64p, C.c_int, C.c_int64, C.POINTER(vp)]),
+    "grb_merged_len": (C.c_size_t, [vp]),
+    "grb_merged_copy": (C.c_int, [vp, vp, vp, vp, u64p]),
+    "grb_merged_dev_starts": (vp, [vp]),
+    "grb_merged_dev_ends": (vp, [vp]),
+    "grb_merged_map_f64": (C.c_int, [vp, vp, vp, vp, i32p, C.c_int, vp, vp]),
+    "grb_merged_destroy": (None, [vp]),
     "grb_shard_plan": (C.c_int, [u64p, u64p, C.c_int, vp, vp, C.c_int, C.POINTER(Shard), C.c_int]),
 }
 

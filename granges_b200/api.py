@@ -372,6 +372,37 @@ class Context:
             w.close()
 
 
+    # -- merging iterators (src/merging_iterators.rs, `granges merge`)
+    def merge(self, starts, ends, run_offsets=None, distance=0, scores=None, valid=None, ops=None):
+        """Merge the records of a file (runs = consecutive records of one seqname; default: one run).
+        -> (run_offsets_merged[nruns+1], m_starts, m_ends, first[m+1][, out[m,k], out_valid[m,k]])."""
+        L = _capi.lib()
+        ps, ks, _ = _arg(starts, np.uint32)
+        pe, ke, _ = _arg(ends, np.uint32)
+        n = len(ks)
+        ro = np.ascontiguousarray([0, n] if run_offsets is None else run_offsets, dtype=np.uint64)
+        nruns = len(ro) - 1
+        h = C.c_void_p()
+        self._check(L.grb_merge_ranges(self.h, ps, pe, ro.ctypes.data_as(_capi.u64p), nruns, int(distance), C.byref(h)))
+        try:
+            m = L.grb_merged_len(h)
+            ms, me, first = np.empty(m, np.uint32), np.empty(m, np.uint32), np.empty(m + 1, np.uint32)
+            rom = np.empty(nruns + 1, np.uint64)
+            self._check(L.grb_merged_copy(h, ms.ctypes.data, me.ctypes.data, first.ctypes.data, rom.ctypes.data_as(_capi.u64p)))
+            res = (rom, ms, me, first)
+            if ops is not None:
+                psc, ksc, _ = _arg(scores, np.float64)
+                pv, kv, _ = _arg(valid, np.uint8)
+                ops_a, ops_p = self._ops(ops)
+                k = len(ops_a)
+                out, ov = np.zeros((m, k), np.float64), np.zeros((m, k), np.uint8)
+                self._check(L.grb_merged_map_f64(self.h, h, psc, pv, ops_p, k, out.ctypes.data, ov.ctypes.data))
+                res = res + (out, ov)
+        finally:
+            L.grb_merged_destroy(h)
+        return res
+
+
 class PreparedMap:
     """A grb_map_joins_f64_batch call with all arguments already marshalled."""
 

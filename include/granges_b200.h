@@ -81,6 +81,7 @@ typedef struct grb_ctx grb_ctx;
 typedef struct grb_index grb_index;
 typedef struct grb_pairs grb_pairs;
 typedef struct grb_ranges grb_ranges;
+typedef struct grb_merged grb_merged;
 
 /* ---- context ----------------------------------------------------------- */
 
@@ -196,6 +197,35 @@ int grb_ranges_copy(const grb_ranges *r, uint32_t *seq_id, uint32_t *starts, uin
 const uint32_t *grb_ranges_dev_starts(const grb_ranges *r);
 const uint32_t *grb_ranges_dev_ends(const grb_ranges *r);
 void grb_ranges_destroy(grb_ranges *r);
+
+/* ---- merging (`granges merge`, feature-density's per-feature merge) ---------- */
+
+/* MergingEmptyIterator / MergingEmptyResultIterator / MergingResultIterator -- src/merging_iterators.rs:39-241,
+ * as driven by Merge::run (src/commands.rs:616-673) and FeatureDensity (src/commands.rs:818-826).
+ * The records are given in file order as `nruns` runs (run r = records [run_offsets[r], run_offsets[r+1]),
+ * a maximal stretch of consecutive records of one seqname -- the iterator never merges across a seqname
+ * change).  A record joins the open range iff distance_or_overlap(open, record) <= distance
+ * (src/traits.rs:89-108: negative = minus the overlap width, 0 = book-ended, positive = gap) and extends its
+ * end to max(end, record.end).  Start-sorted runs with distance >= 0 take a prefix-max scan; any other input
+ * (negative distance, unsorted starts) is walked by the reference's own state machine, one warp per run.
+ * starts / ends may be host or device pointers; run_offsets is a host array of nruns + 1 entries. */
+int grb_merge_ranges(grb_ctx *ctx, const uint32_t *starts, const uint32_t *ends, const uint64_t *run_offsets, int nruns,
+                     int64_t distance, grb_merged **out);
+/* Number of merged ranges. */
+size_t grb_merged_len(const grb_merged *m);
+/* Copy out (any pointer may be NULL): the merged ranges, first[g] = input position of group g's first
+ * record (len + 1 entries, first[len] = number of records; group g = records [first[g], first[g+1])), and
+ * the merged-range offsets of the runs (nruns + 1 entries, host). */
+int grb_merged_copy(const grb_merged *m, uint32_t *starts, uint32_t *ends, uint32_t *first, uint64_t *run_offsets_merged);
+const uint32_t *grb_merged_dev_starts(const grb_merged *m);
+const uint32_t *grb_merged_dev_ends(const grb_merged *m);
+/* The closure of Merge::run for BED5 input (src/commands.rs:650-657): FloatOperation::run over the non-missing
+ * scores of each merged group.  scores / valid are per input record (valid NULL = all Some); out / out_valid
+ * are len x k, row-major.  Sums are the correctly rounded exact sums (within 1e-12 of the reference's
+ * left-to-right f64 sum); min / max / median are bit-exact. */
+int grb_merged_map_f64(grb_ctx *ctx, const grb_merged *m, const double *scores, const uint8_t *valid, const int *ops, int k,
+                       double *out, uint8_t *out_valid);
+void grb_merged_destroy(grb_merged *m);
 
 /* ---- multi-GPU sharding (host-side, no device work) --------------------- */
 

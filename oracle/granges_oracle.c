@@ -576,3 +576,73 @@ int orc_max_threads(void) {
     long n = sysconf(_SC_NPROCESSORS_ONLN);
     return n > 0 ? (int)n : 1;
 }
+
+
+/* --- merging_iterators.rs ------------------------------------------------ */
+
+/* GenericRange::distance_or_overlap -- traits.rs:89-108 (self = a, other = b). */
+static int64_t orc_distance_or_overlap(uint32_t as, uint32_t ae, uint32_t bs, uint32_t be) {
+    if (ae > bs && as < be) return -(int64_t)orc_overlap_width(as, ae, bs, be);
+    if (ae == bs || as == be) return 0;
+    uint32_t d1 = bs > ae ? bs - ae : 0; /* saturating_sub */
+    uint32_t d2 = as > be ? as - be : 0;
+    return (int64_t)(d1 > d2 ? d1 : d2);
+}
+
+/* MergingEmptyResultIterator (merging_iterators.rs:72-136) and MergingResultIterator
+ * (:138-241) restated as one streaming pass over the records of a file, in file order.
+ * seq[i] = seqname id of record i.  scores NULL => the "empty" (BED3) iterator; otherwise
+ * the closure of Merge::run for BED5 (commands.rs:650-657): the non-missing scores of the
+ * accumulated records go through FloatOperation::run(op).  Outputs (each may be NULL) have
+ * room for n entries; returns the number of merged ranges.  out_first[g] = position of the
+ * first record of merged range g. */
+size_t orc_merge(const uint32_t *seq, const uint32_t *starts, const uint32_t *ends, size_t n, int64_t min_distance,
+                 const double *scores, const uint8_t *valid, int op, uint32_t *out_seq, uint32_t *out_start,
+                 uint32_t *out_end, uint64_t *out_first, double *out_val, uint8_t *out_ok) {
+    size_t m = 0;
+    int have_last = 0;
+    uint32_t last_seq = 0, last_start = 0, last_end = 0;
+    size_t first = 0;
+    double *acc = scores ? (double *)malloc((n ? n : 1) * sizeof(double)) : NULL; /* accumulated_data (Some scores only) */
+    size_t nacc = 0;
+    for (size_t i = 0; i <= n; i++) {
+        int flush = 0;
+        if (i < n) {
+            if (have_last) {
+                int on_same_chrom = last_seq == seq[i];
+                if (on_same_chrom && orc_distance_or_overlap(last_start, last_end, starts[i], ends[i]) <= min_distance) {
+                    if (ends[i] > last_end) last_end = ends[i]; /* last_range.end = max(..) */
+                    if (scores && (!valid || valid[i])) acc[nacc++] = scores[i];
+                    continue;
+                }
+                flush = 1;
+            }
+        } else {
+            flush = have_last;
+        }
+        if (flush) {
+            if (out_seq) out_seq[m] = last_seq;
+            if (out_start) out_start[m] = last_start;
+            if (out_end) out_end[m] = last_end;
+            if (out_first) out_first[m] = first;
+            if (scores) {
+                double v = 0.0;
+                int ok = orc_float_op(op, acc, nacc, &v);
+                if (out_val) out_val[m] = ok == 1 ? v : 0.0;
+                if (out_ok) out_ok[m] = ok == 1;
+            }
+            m++;
+            nacc = 0;
+        }
+        if (i < n) {
+            have_last = 1;
+            last_seq = seq[i];
+            last_start = starts[i];
+            last_end = ends[i];
+            first = i;
+            if (scores && (!valid || valid[i])) acc[nacc++] = scores[i];
+        }
+    }
+    free(acc);
+    return m;
+}

@@ -69,6 +69,8 @@ def lib():
         L.orc_filter_overlaps.argtypes = [C.c_void_p, u32p, u32p, C.c_size_t, C.c_int, u8p]
         L.orc_windows.restype = C.c_size_t
         L.orc_windows.argtypes = [u32p, C.c_int, C.c_uint32, C.c_uint32, C.c_int, u32p, u32p, u32p, C.c_size_t]
+        L.orc_merge.restype = C.c_size_t
+        L.orc_merge.argtypes = [u32p, u32p, u32p, C.c_size_t, C.c_int64, f64p, u8p, C.c_int, u32p, u32p, u32p, u64p, f64p, u8p]
         L.orc_max_threads.restype = C.c_int
         _lib = L
     return _lib
@@ -185,6 +187,24 @@ def float_op(op, values):
     out = C.c_double(0)
     ok = lib().orc_float_op(OPS[op] if isinstance(op, str) else op, _p(v, C.c_double), len(v), C.byref(out))
     return out.value if ok == 1 else None
+
+
+def merge(seq, starts, ends, distance=0, scores=None, valid=None, op=None):
+    """Streaming merge of a file's records (merging_iterators.rs): (seq, start, end, first[, value, ok])."""
+    seq, starts, ends = _u32(seq), _u32(starts), _u32(ends)
+    n = len(starts)
+    sc = None if scores is None else np.ascontiguousarray(scores, dtype=np.float64)
+    va = None if valid is None else np.ascontiguousarray(valid, dtype=np.uint8)
+    o_seq, o_s, o_e = np.empty(n, np.uint32), np.empty(n, np.uint32), np.empty(n, np.uint32)
+    o_first, o_val, o_ok = np.empty(n, np.uint64), np.zeros(n, np.float64), np.zeros(n, np.uint8)
+    opc = 0 if op is None else (OPS[op] if isinstance(op, str) else int(op))
+    m = lib().orc_merge(_p(seq, C.c_uint32), _p(starts, C.c_uint32), _p(ends, C.c_uint32), n, int(distance), _p(sc, C.c_double),
+                        _p(va, C.c_uint8), opc, _p(o_seq, C.c_uint32), _p(o_s, C.c_uint32), _p(o_e, C.c_uint32), _p(o_first, C.c_uint64),
+                        _p(o_val, C.c_double), _p(o_ok, C.c_uint8))
+    res = (o_seq[:m], o_s[:m], o_e[:m], o_first[:m])
+    if scores is not None:
+        res = res + (o_val[:m], o_ok[:m])
+    return res
 
 
 def max_threads():
