@@ -19,6 +19,7 @@
 #include <cstring>
 #include <algorithm>
 #include <functional>
+#include <map>
 #include <string>
 #include <string_view>
 #include <thread>
@@ -529,6 +530,268 @@ int cmd_windows(const Args &a) {
     return 0;
 }
 
+// ---- file-order records (merge, feature-density): the merging iterators stream the file as it is ----------
+
+struct Records {
+    std::vector<std::string_view> seqname, name;  // name: 4th column (BED4 / BED5)
+    std::vector<uint32_t> starts, ends;
+    std::vector<double> score;  // BED5
+    std::vector<uint8_t> valid;
+    int ncols = 0;  // of the first record: 3, 4 or 5 (src/io/parsers/detect.rs:39-53 tries BED5, BED4, BED3)
+};
+
+Records parse_records(const Mapped &f, int want_cols /* 0 = detect */) {
+    Records r;
+    const char *p = f.p, *end = f.p + f.n;
+    while (p < end) {
+        const char *line = p;
+        const char *nl = (const char *)memchr(p, '\n', end - p);
+        const char *le = nl ? nl : end;
+        p = le + 1;
+        if (le > line && le[-1] == '\r') le--;
+        if (le == line || *line == '#') continue;
+        const char *col[6];
+        int nc = 0;
+        col[nc++] = line;
+        for (const char *q = line; q < le && nc < 6; q++)
+            if (*q == '\t') col[nc++] = q + 1;
+        int total_cols = nc;
+        if (nc == 6) {
+            total_cols = 6;
+            for (const char *q = col[5]; q < le; q++)
+                if (*q == '\t') total_cols++;
+        }
+        auto col_end = [&](int c) { return c + 1 < nc ? col[c + 1] - 1 : le; };
+        if (nc < 3) die("expected at least 3 tab-separated columns");
+        if (r.ncols == 0) {
+            r.ncols = want_cols ? want_cols : total_cols;
+            if (!want_cols && r.ncols > 5) die("Unsupported genomic ranges file format: BED-like input with more than five columns (the reference's merge stops at todo!())");
+        }
+        if (total_cols < r.ncols) die("a record has fewer columns than the first one");
+        uint64_t s = 0, e = 0;
+        bool bad = col_end(1) == col[1] || col_end(2) == col[2];
+        for (const char *q = col[1]; q < col_end(1); q++) {
+            bad |= *q < '0' || *q > '9';
+            s = s * 10 + (uint64_t)(*q - '0');
+        }
+        for (const char *q = col[2]; q < col_end(2); q++) {
+            bad |= *q < '0' || *q > '9';
+            e = e * 10 + (uint64_t)(*q - '0');
+        }
+        if (bad) die("invalid start / end coordinate");
+        if (e <= s || e > 0x7fffffffull) die("invalid range: end must be > start and fit i32");
+        r.seqname.emplace_back(col[0], col_end(0) - col[0]);
+        r.starts.push_back((uint32_t)s);
+        r.ends.push_back((uint32_t)e);
+        if (r.ncols >= 4) r.name.emplace_back(col[3], col_end(3) - col[3]);
+        if (r.ncols >= 5) {
+            const char *a = col[4], *b = col_end(4);
+            if (b - a == 1 && *a == '.') {
+                r.score.push_back(0.0);
+                r.valid.push_back(0);
+            } else {
+                char tmp[64];
+                size_t len = (size_t)(b - a);
+                if (len == 0 || len >= sizeof(tmp)) die("parsing error: invalid float literal");
+                memcpy(tmp, a, len);
+                tmp[len] = 0;
+                char *ep;
+                double v = strtod(tmp, &ep);
+                if (ep == tmp || *ep) die("parsing error: invalid float literal");
+                r.score.push_back(v);
+                r.valid.push_back(1);
+            }
+        }
+    }
+    return r;
+}
+
+// maximal stretches of consecutive records with the same seqname
+std::vector<uint64_t> seqname_runs(const std::vector<std::string_view> &seqname) {
+    std::vector<uint64_t> ro{0};
+    for (size_t i = 1; i < seqname.size(); i++)
+        if (seqname[i] != seqname[i - 1]) ro.push_back(i);
+    if (!seqname.empty()) ro.push_back(seqname.size());
+    return ro;
+}
+
+// `granges merge` -- Merge::run, src/commands.rs:616-673: BED3 -> merged ranges; BED4 -> names joined with ",";
+// BED5 -> FloatOperation over the merged records' scores.
+int cmd_merge(const std::string &bedfile, long long distance, const std::vector<int> &ops, const Args &a) {
+    Mapped f(bedfile);
+    Records r = parse_records(f, 0);
+    if (r.starts.empty()) die("File '" + bedfile + "' is empty.");
+    if (r.ncols == 5 && ops.size() != 1) die("BED5 input needs exactly one --func (the reference unwraps it: src/commands.rs:656)");
+    grb_ctx *ctx = nullptr;
+    check(nullptr, grb_ctx_create(0, &ctx));
+    std::vector<uint64_t> ro = seqname_runs(r.seqname);
+    grb_merged *mg = nullptr;
+    check(ctx, grb_merge_ranges(ctx, r.starts.data(), r.ends.data(), ro.data(), (int)ro.size() - 1, distance, &mg));
+    const size_t m = grb_merged_len(mg);
+    std::vector<uint32_t> ms(m), me(m), first(m + 1);
+    check(ctx, grb_merged_copy(mg, ms.data(), me.data(), first.data(), nullptr));
+    std::vector<double> val;
+    std::vector<uint8_t> ok;
+    if (r.ncols == 5) {
+        val.resize(m);
+        ok.resize(m);
+        check(ctx, grb_merged_map_f64(ctx, mg, r.score.data(), r.valid.data(), ops.data(), 1, val.data(), ok.data()));
+    }
+    size_t max_row = 64;
+    for (auto &nm : r.seqname) max_row = std::max(max_row, nm.size() + 96);
+    if (r.ncols == 4) {
+        size_t worst = 0;
+        for (size_t g = 0; g < m; g++) {
+            size_t len = 0;
+            for (uint32_t i = first[g]; i < first[g + 1]; i++) len += r.name[i].size() + 1;
+            worst = std::max(worst, len);
+        }
+        max_row += worst;
+    }
+    write_rows(a.has_output ? a.output.c_str() : nullptr, m, max_row, [&](size_t g, char *q) {
+        std::string_view nm = r.seqname[first[g]];
+        memcpy(q, nm.data(), nm.size());
+        q += nm.size();
+        *q++ = '\t';
+        q = grh::format_u32(q, ms[g]);
+        *q++ = '\t';
+        q = grh::format_u32(q, me[g]);
+        if (r.ncols == 4) {
+            *q++ = '\t';
+            for (uint32_t i = first[g]; i < first[g + 1]; i++) {
+                if (i > first[g]) *q++ = ',';
+                memcpy(q, r.name[i].data(), r.name[i].size());
+                q += r.name[i].size();
+            }
+        } else if (r.ncols == 5) {
+            *q++ = '\t';
+            if (ok[g])
+                q = grh::format_f64(q, val[g]);
+            else
+                *q++ = '.';
+        }
+        *q++ = '\n';
+        return q;
+    });
+    grb_merged_destroy(mg);
+    grb_ctx_destroy(ctx);
+    return 0;
+}
+
+// `granges feature-density` (non-exclusive) -- FeatureDensity::feature_density, src/commands.rs:796-858: the BED4
+// records are split by feature name, each feature's ranges are bookend-merged in file order, and every window
+// gets the number of basepairs each feature covers in it (sum of overlap widths over merged = disjoint ranges).
+// Columns are the features in sorted order (the reference iterates a HashMap: its order is unspecified).
+int cmd_feature_density(const std::string &bedfile, bool headers, const Args &a) {
+    if (!a.has_width) die("the following required arguments were not provided: --width <WIDTH>");
+    Genome g = read_genome(a.genome);
+    Mapped f(bedfile);
+    Records r = parse_records(f, 4);
+    const int nseq = (int)g.names.size();
+    std::map<std::string_view, std::vector<uint32_t>> by_feature;  // feature -> record positions, file order
+    for (size_t i = 0; i < r.name.size(); i++) by_feature[r.name[i]].push_back((uint32_t)i);
+    grb_ctx *ctx = nullptr;
+    check(nullptr, grb_ctx_create(0, &ctx));
+    grb_ranges *w = nullptr;
+    check(ctx, grb_windows(ctx, g.lens.data(), nseq, a.width, a.step, a.chop ? 1 : 0, &w));
+    const size_t nw = grb_ranges_len(w);
+    std::vector<uint64_t> woff(nseq + 1);
+    check(ctx, grb_ranges_seq_offsets(w, woff.data()));
+    std::vector<uint32_t> wseq(nw), wst(nw), wen(nw);
+    check(ctx, grb_ranges_copy(w, wseq.data(), wst.data(), wen.data()));
+    const size_t nf = by_feature.size();
+    std::vector<std::vector<double>> cols(nf);
+    std::vector<std::string_view> feature_names;
+    size_t fi = 0;
+    for (auto &kv : by_feature) {
+        feature_names.push_back(kv.first);
+        const std::vector<uint32_t> &pos = kv.second;
+        std::vector<uint32_t> st(pos.size()), en(pos.size());
+        std::vector<std::string_view> sq(pos.size());
+        for (size_t j = 0; j < pos.size(); j++) {
+            st[j] = r.starts[pos[j]];
+            en[j] = r.ends[pos[j]];
+            sq[j] = r.seqname[pos[j]];
+        }
+        std::vector<uint64_t> ro = seqname_runs(sq);
+        grb_merged *mg = nullptr;
+        check(ctx, grb_merge_ranges(ctx, st.data(), en.data(), ro.data(), (int)ro.size() - 1, 0, &mg));
+        const size_t m = grb_merged_len(mg);
+        std::vector<uint32_t> ms(m), me(m), first(m + 1);
+        check(ctx, grb_merged_copy(mg, ms.data(), me.data(), first.data(), nullptr));
+        grb_merged_destroy(mg);
+        // into the genome-keyed container (GRangesEmpty::from_iter_ok): per seqname, in arrival order
+        std::vector<std::vector<uint32_t>> ss(nseq), ee(nseq);
+        for (size_t k = 0; k < m; k++) {
+            auto it = g.id.find(sq[first[k]]);
+            if (it == g.id.end())
+                die("The sequence name '" + std::string(sq[first[k]]) +
+                    "' is not found within the provided ranges container. Check the sequence names for typos or missing entries.");
+            ss[it->second].push_back(ms[k]);
+            ee[it->second].push_back(me[k]);
+        }
+        std::vector<grb_index *> idx(nseq, nullptr);
+        for (int s = 0; s < nseq; s++)
+            if (!ss[s].empty()) check(ctx, grb_index_build(ctx, ss[s].data(), ee[s].data(), nullptr, ss[s].size(), &idx[s]));
+        cols[fi].resize(nw);
+        std::vector<uint8_t> okv(nw);
+        const int op = GRB_OP_OVERLAP_BP;
+        if (nw)
+            check(ctx, grb_map_joins_f64_batch(ctx, idx.data(), woff.data(), nseq, grb_ranges_dev_starts(w), grb_ranges_dev_ends(w), &op, 1,
+                                               cols[fi].data(), okv.data()));
+        for (auto ix : idx) grb_index_destroy(ix);
+        fi++;
+    }
+    FILE *out = a.has_output ? fopen(a.output.c_str(), "wb") : stdout;
+    if (!out) die(a.output + ": " + strerror(errno));
+    if (headers) {
+        fputs("chrom\tstart\tend", out);
+        for (auto &nm : feature_names) {
+            fputc('\t', out);
+            fwrite(nm.data(), 1, nm.size(), out);
+        }
+        fputc('\n', out);
+        fflush(out);
+    }
+    if (out != stdout) fclose(out);
+    size_t max_name = 0;
+    for (auto &nm : g.names) max_name = std::max(max_name, nm.size());
+    // write_rows reopens the file: append after the header
+    struct Appender {
+        static void rows(const char *path, bool append, size_t n, size_t max_row, const std::function<char *(size_t, char *)> &row) {
+            FILE *fo = path ? fopen(path, append ? "ab" : "wb") : stdout;
+            if (!fo) die(std::string(path) + ": " + strerror(errno));
+            std::vector<char> tmp(max_row);
+            for (size_t i = 0; i < n; i++) {
+                char *e = row(i, tmp.data());
+                fwrite(tmp.data(), 1, (size_t)(e - tmp.data()), fo);
+            }
+            if (fo != stdout)
+                fclose(fo);
+            else
+                fflush(stdout);
+        }
+    };
+    Appender::rows(a.has_output ? a.output.c_str() : nullptr, headers, nw, max_name + 40 + 12 * nf, [&](size_t i, char *q) {
+        const std::string &name = g.names[wseq[i]];
+        memcpy(q, name.data(), name.size());
+        q += name.size();
+        *q++ = '\t';
+        q = grh::format_u32(q, wst[i]);
+        *q++ = '\t';
+        q = grh::format_u32(q, wen[i]);
+        for (size_t c = 0; c < nf; c++) {
+            *q++ = '\t';
+            q = grh::format_u32(q, (uint32_t)cols[c][i]);
+        }
+        *q++ = '\n';
+        return q;
+    });
+    grb_ranges_destroy(w);
+    grb_ctx_destroy(ctx);
+    return 0;
+}
+
 // `granges random-bed` (dev command of the reference, src/commands.rs:563-588 + src/test_utilities.rs:60-164): seqname
 // uniform over the genome file's names, length U{1..999}, start uniform, optional BED5 name + score U[0,1).  The
 // generator is a counter-based splitmix64 (the reference's StdRng stream is not reproducible without the crate).
@@ -600,6 +863,8 @@ void usage() {
             "  granges map     -g <genome> -l <left.bed> -r <right.bed5> -f <op[,op..]> [-o <out>] [-s]\n"
             "  granges filter  -g <genome> -l <left.bed> -r <right.bed> [-o <out>] [-s]\n"
             "  granges windows -g <genome> -w <width> [-s <step>] [-c] [-o <out>]\n"
+            "  granges merge   -b <bedfile> [-d <distance>] [-f <op>] [-o <out>]\n"
+            "  granges feature-density -g <genome> -b <bed4> -w <width> [-s <step>] [-c] [-l] [-o <out>]\n"
             "  granges random-bed <genome> -n <num> [-o <out>] [-s] [-c] [--seed <n>]\n"
             "ops: sum, sum-not-empty, min, max, mean, median\n");
 }
@@ -612,8 +877,11 @@ int main(int argc, char **argv) {
         return 2;
     }
     const std::string cmd = argv[1];
-    const bool windows = cmd == "windows";
+    const bool windows = cmd == "windows" || cmd == "feature-density";
     Args a;
+    std::string bedfile;
+    long long distance = 0;
+    bool headers = false, exclusive = false;
     if (cmd == "random-bed") {
         size_t num = 0;
         bool sort = false, scores = false;
@@ -655,6 +923,14 @@ int main(int argc, char **argv) {
         };
         if (f == "-g" || f == "--genome")
             a.genome = need();
+        else if (cmd == "feature-density" && (f == "-l" || f == "--headers"))
+            headers = true;
+        else if (cmd == "feature-density" && (f == "-e" || f == "--exclusive"))
+            exclusive = true;
+        else if (f == "-b" || f == "--bedfile")
+            bedfile = need();
+        else if (cmd == "merge" && (f == "-d" || f == "--distance"))
+            distance = strtoll(need().c_str(), nullptr, 10);
         else if (f == "-l" || f == "--left")
             a.left = need();
         else if (f == "-r" || f == "--right")
@@ -686,7 +962,16 @@ int main(int argc, char **argv) {
         } else
             die("unexpected argument '" + f + "' found");
     }
+    if (cmd == "merge") {
+        if (bedfile.empty()) die("the following required arguments were not provided: --bedfile <BEDFILE>");
+        return cmd_merge(bedfile, distance, a.ops, a);
+    }
     if (a.genome.empty()) die("the following required arguments were not provided: --genome <GENOME>");
+    if (cmd == "feature-density") {
+        if (bedfile.empty()) die("the following required arguments were not provided: --bedfile <BEDFILE>");
+        if (exclusive) die("--exclusive is experimental and untested in the reference (src/commands.rs:779-780); this mirror does not offer it");
+        return cmd_feature_density(bedfile, headers, a);
+    }
     if (cmd == "map") {
         if (a.left.empty() || a.right.empty()) die("the following required arguments were not provided: --left <LEFT> --right <RIGHT>");
         return cmd_map(a);
@@ -695,6 +980,6 @@ int main(int argc, char **argv) {
         if (a.left.empty() || a.right.empty()) die("the following required arguments were not provided: --left <LEFT> --right <RIGHT>");
         return cmd_filter(a);
     }
-    if (windows) return cmd_windows(a);
-    die("unrecognized subcommand '" + cmd + "' (this mirror implements map, filter and windows)");
+    if (cmd == "windows") return cmd_windows(a);
+    die("unrecognized subcommand '" + cmd + "' (this mirror implements map, filter, windows, merge and feature-density)");
 }

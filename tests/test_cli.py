@@ -158,3 +158,109 @@ def test_cli_errors(tmp_path):
     (tmp_path / "e.bed").write_text("")
     r = run("map", "-g", tmp_path / "g.tsv", "-l", tmp_path / "e.bed", "-r", tmp_path / "b.bed", "-f", "sum", check=False)
     assert r.returncode == 1 and "The input file had no rows." in r.stderr
+
+
+# ---- merge / feature-density -------------------------------------------------------------------
+
+def _merge_file(tmp_path, ncols, seed=9, n=4000):
+    rng = np.random.default_rng(seed)
+    names = ["chr1", "chr2", "chr10", "chrX"]
+    rows = []
+    for nm in names:
+        k = int(rng.integers(n // 8, n // 3))
+        st = np.sort(rng.integers(0, 40 * k, k))
+        en = st + rng.integers(1, 90, k)
+        for a, b in zip(st, en):
+            sc = "." if rng.random() < 0.1 else repr(float(np.round(rng.standard_normal() * 10, 2)))
+            rows.append((nm, int(a), int(b), f"f{int(rng.integers(0, 5))}", sc))
+    path = tmp_path / f"in{ncols}.bed"
+    path.write_text("".join("\t".join(map(str, r[:ncols])) + "\n" for r in rows))
+    return path, rows
+
+
+@pytest.mark.parametrize("distance", [0, 30, -5])
+def test_cli_merge_bed3_and_bed4(tmp_path, orc, distance):
+    """BED3 -> merged ranges; BED4 -> the merged records' names joined with "," (src/commands.rs:629-645)."""
+    for ncols in (3, 4):
+        path, rows = _merge_file(tmp_path, ncols)
+        names = sorted({r[0] for r in rows})
+        seq = np.array([names.index(r[0]) for r in rows], np.uint32)
+        s, e = np.array([r[1] for r in rows], np.uint32), np.array([r[2] for r in rows], np.uint32)
+        mseq, ms, me, first = orc.merge(seq, s, e, distance)
+        bounds = list(first) + [len(rows)]
+        want = []
+        for g in range(len(ms)):
+            line = f"{names[mseq[g]]}\t{ms[g]}\t{me[g]}"
+            if ncols == 4:
+                line += "\t" + ",".join(rows[i][3] for i in range(int(bounds[g]), int(bounds[g + 1])))
+            want.append(line)
+        got = run("merge", "--bedfile", path, "--distance", distance).stdout
+        assert got == "\n".join(want) + "\n"
+
+
+@pytest.mark.parametrize("op", ["sum", "mean", "median", "min", "max"])
+def test_cli_merge_bed5(tmp_path, orc, op):
+    """BED5 -> FloatOperation over the merged records' non-missing scores (src/commands.rs:646-662)."""
+    path, rows = _merge_file(tmp_path, 5)
+    names = sorted({r[0] for r in rows})
+    seq = np.array([names.index(r[0]) for r in rows], np.uint32)
+    s, e = np.array([r[1] for r in rows], np.uint32), np.array([r[2] for r in rows], np.uint32)
+    sc = np.array([0.0 if r[4] == "." else float(r[4]) for r in rows])
+    valid = np.array([r[4] != "." for r in rows], np.uint8)
+    mseq, ms, me, first, val, ok = orc.merge(seq, s, e, 0, sc, valid, op)
+    out_path = tmp_path / "merged.bed"
+    run("merge", "-b", path, "-f", op, "-o", out_path)
+    lines = out_path.read_text().splitlines()
+    assert len(lines) == len(ms)
+    for g, line in enumerate(lines):
+        f = line.split("\t")
+        assert f[:3] == [names[mseq[g]], str(ms[g]), str(me[g])]
+        if not ok[g]:
+            assert f[3] == "."
+        elif op in ("sum", "mean"):
+            assert abs(float(f[3]) - val[g]) <= 1e-12 * max(1.0, abs(val[g])) * 50
+        else:
+            assert f[3] == rust_display(float(val[g]))
+    r = run("merge", "-b", path, check=False)
+    assert r.returncode == 1 and "func" in r.stderr
+
+
+def test_cli_feature_density(tmp_path, orc):
+    """Per window and feature: basepairs covered by the feature's bookend-merged ranges (src/commands.rs:796-858)."""
+    rng = np.random.default_rng(21)
+    genome = {"chr1": 50_000, "chr2": 20_000, "chr3": 7_000}
+    (tmp_path / "genome.tsv").write_text("".join(f"{k}\t{v}\n" for k, v in genome.items()))
+    feats = ["CDS", "exon", "five_prime_UTR"]
+    rows = []
+    for nm, L in genome.items():
+        if nm == "chr3":
+            continue
+        k = 400
+        st = np.sort(rng.integers(0, L - 300, k))
+        for a in st:
+            rows.append((nm, int(a), int(a + rng.integers(1, 300)), feats[int(rng.integers(0, 3))]))
+    (tmp_path / "feat.bed").write_text("".join("\t".join(map(str, r)) + "\n" for r in rows))
+    width, step = 1000, 400
+    got = run("feature-density", "-g", tmp_path / "genome.tsv", "-b", tmp_path / "feat.bed", "-w", width, "-s", step, "--headers").stdout
+    lines = got.splitlines()
+    assert lines[0].split("\t") == ["chrom", "start", "end"] + sorted(feats)
+    names = list(genome)
+    wseq, ws, we = orc.windows(list(genome.values()), width, step, False)
+    assert len(lines) - 1 == len(ws)
+    cover = {}
+    for nm, L in genome.items():
+        for ft in feats:
+            c = np.zeros(L + 400, bool)
+            for r in rows:
+                if r[0] == nm and r[3] == ft:
+                    c[r[1]:r[2]] = True
+            cover[(nm, ft)] = np.concatenate([[0], np.cumsum(c)])
+    for i, line in enumerate(lines[1:]):
+        f = line.split("\t")
+        nm = names[wseq[i]]
+        assert f[:3] == [nm, str(ws[i]), str(we[i])]
+        for c, ft in enumerate(sorted(feats)):
+            assert int(f[3 + c]) == cover[(nm, ft)][we[i]] - cover[(nm, ft)][ws[i]]
+    # without --headers: same rows, no header line
+    got2 = run("feature-density", "-g", tmp_path / "genome.tsv", "-b", tmp_path / "feat.bed", "-w", width, "-s", step).stdout
+    assert got2.splitlines() == lines[1:]
