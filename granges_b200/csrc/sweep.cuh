@@ -41,21 +41,35 @@ __device__ __forceinline__ void sweep_tile(const SeqDev *__restrict__ sd, u64 g_
     const bool sweep_sums = sd->sum_mode == GRB_SUM_SWEEP;
     u64 *kbuf = reinterpret_cast<u64 *>(s_buf) + (size_t)gidx * CAP;  // order-preserving integer images of the scores
 
-    for (u64 g = g_lo + gidx; g < g_hi; g += NGROUPS) {
-        const u32 u = ubv[g], p = ppv[g], l = lbv[g];
-        const u32 lstart = ls[g], lend = le[g];
+    // Warp-synchronous walk (see sweep3.cuh): the groups of a warp take every step together, so each vote is one
+    // full-warp instruction instead of one per group mask.
+    const u64 g_warp = g_lo + (threadIdx.x >> 5) * (32 / G);
+    const u32 rounds = g_warp < g_hi ? (u32)((g_hi - g_warp + NGROUPS - 1) / NGROUPS) : 0u;
+    u64 g = g_lo + gidx;
+    for (u32 round = 0; round < rounds; round++, g += NGROUPS) {
+        const bool live = g < g_hi;
+        u32 u = 0, p = 0, l = 0, lstart = 0, lend = 0;
+        if (live) {
+            u = ubv[g];
+            p = ppv[g];
+            l = lbv[g];
+            lstart = ls[g];
+            lend = le[g];
+        }
         u32 nvalid = 0;
         double sum = 0.0, mn = 0.0, mx = 0.0;
         bool have = false;
         u64 bp = 0, wtot = 0;  // overlap bp of all members / of the members with a score
         double wsum = 0.0;     // sum of score * overlap bp
         // ---- members that start inside the left: [p, u), ascending
-        for (u32 j0 = p; j0 < u; j0 += G) {
-            const u32 j = j0 + glane;
+        const u32 fw = u > p ? u - p : 0u;
+        const u32 fw_steps = __reduce_max_sync(GRB_FULL, (fw + G - 1) / G);
+        for (u32 it = 0; it < fw_steps; it++) {
+            const u32 j = p + it * G + glane;
             const bool in = j < u;
             bool v = in && has_scores;
             if (v && has_nulls) v = (vbits[j >> 5] >> (j & 31)) & 1u;
-            const u32 vm = (__ballot_sync(gmask, v) >> gshift) & (G == 32 ? 0xffffffffu : ((1u << G) - 1u));
+            const u32 vm = (__ballot_sync(GRB_FULL, v) >> gshift) & (G == 32 ? 0xffffffffu : ((1u << G) - 1u));
             u32 wid = 0;
             if (WIDTHS && in) {
                 wid = min(lend, ends[j]) - starts[j];
@@ -84,60 +98,59 @@ __device__ __forceinline__ void sweep_tile(const SeqDev *__restrict__ sd, u64 g_
         const u32 need = p - l;
         u32 found = 0;
         long long cb = p ? (long long)((p - 1) & ~(u32)(G - 1)) : -1;
-        while (found < need && cb >= 0) {
-            if (bme[cb >> GRB_BME_SHIFT] > lstart) {
-                const u32 j = (u32)cb + glane;
-                const bool in = j < p;
-                const u32 e = in ? ends[j] : 0u;
-                const bool hit = in && e > lstart;
-                const u32 hm = (__ballot_sync(gmask, hit) >> gshift) & (G == 32 ? 0xffffffffu : ((1u << G) - 1u));
-                bool v = hit && has_scores;
-                if (v && has_nulls) v = (vbits[j >> 5] >> (j & 31)) & 1u;
-                const u32 vm = (__ballot_sync(gmask, v) >> gshift) & (G == 32 ? 0xffffffffu : ((1u << G) - 1u));
-                u32 wid = 0;
-                if (WIDTHS && hit) {
-                    wid = min(lend, e) - lstart;
-                    bp += wid;
-                }
-                if (v) {
-                    const double x = score[j];
-                    sum += x;
-                    if (WIDTHS) {
-                        wsum += x * (double)wid;
-                        wtot += wid;
-                    }
-                    if (isfinite(x)) {
-                        mn = have ? fmin(mn, x) : x;
-                        mx = have ? fmax(mx, x) : x;
-                        have = true;
-                    }
-                    if (o.want_median) {
-                        const u32 slot = nvalid + __popc(vm & lt);
-                        if (slot < CAP) kbuf[slot] = f64_key(x);
-                    }
-                }
-                found += __popc(hm);
-                nvalid += __popc(vm);
-                cb -= G;
-            } else {
-                cb = ((cb >> GRB_BME_SHIFT) << GRB_BME_SHIFT) - G;  // skip the rest of this 64-block
+        while (true) {
+            const bool act = found < need && cb >= 0;
+            if (!__any_sync(GRB_FULL, act)) break;
+            const bool look = act && bme[cb >> GRB_BME_SHIFT] > lstart;
+            const u32 j = (u32)cb + glane;
+            const bool in = look && j < p;
+            const u32 e = in ? ends[j] : 0u;
+            const bool hit = in && e > lstart;
+            const u32 hm = (__ballot_sync(GRB_FULL, hit) >> gshift) & (G == 32 ? 0xffffffffu : ((1u << G) - 1u));
+            bool v = hit && has_scores;
+            if (v && has_nulls) v = (vbits[j >> 5] >> (j & 31)) & 1u;
+            const u32 vm = (__ballot_sync(GRB_FULL, v) >> gshift) & (G == 32 ? 0xffffffffu : ((1u << G) - 1u));
+            u32 wid = 0;
+            if (WIDTHS && hit) {
+                wid = min(lend, e) - lstart;
+                bp += wid;
             }
+            if (v) {
+                const double x = score[j];
+                sum += x;
+                if (WIDTHS) {
+                    wsum += x * (double)wid;
+                    wtot += wid;
+                }
+                if (isfinite(x)) {
+                    mn = have ? fmin(mn, x) : x;
+                    mx = have ? fmax(mx, x) : x;
+                    have = true;
+                }
+                if (o.want_median) {
+                    const u32 slot = nvalid + __popc(vm & lt);
+                    if (slot < CAP) kbuf[slot] = f64_key(x);
+                }
+            }
+            found += __popc(hm);
+            nvalid += __popc(vm);
+            if (act) cb = look ? cb - G : ((cb >> GRB_BME_SHIFT) << GRB_BME_SHIFT) - G;
         }
         // ---- group reductions (fixed shuffle order: deterministic)
 #pragma unroll
         for (int s = G / 2; s; s >>= 1) {
-            sum += __shfl_xor_sync(gmask, sum, s);
-            const double omn = __shfl_xor_sync(gmask, mn, s), omx = __shfl_xor_sync(gmask, mx, s);
-            const bool ohave = __shfl_xor_sync(gmask, (int)have, s);
+            sum += __shfl_xor_sync(GRB_FULL, sum, s);
+            const double omn = __shfl_xor_sync(GRB_FULL, mn, s), omx = __shfl_xor_sync(GRB_FULL, mx, s);
+            const bool ohave = __shfl_xor_sync(GRB_FULL, (int)have, s);
             if (ohave) {
                 mn = have ? fmin(mn, omn) : omn;
                 mx = have ? fmax(mx, omx) : omx;
                 have = true;
             }
             if (WIDTHS) {
-                bp += __shfl_xor_sync(gmask, bp, s);
-                wsum += __shfl_xor_sync(gmask, wsum, s);
-                wtot += __shfl_xor_sync(gmask, wtot, s);
+                bp += __shfl_xor_sync(GRB_FULL, bp, s);
+                wsum += __shfl_xor_sync(GRB_FULL, wsum, s);
+                wtot += __shfl_xor_sync(GRB_FULL, wtot, s);
             }
         }
         // ---- median of up to CAP values: quickselect inside the group.  Elements are ordered by (key, slot); a
@@ -220,7 +233,7 @@ __device__ __forceinline__ void sweep_tile(const SeqDev *__restrict__ sd, u64 g_
                 }
             }
         }
-        if (glane == 0) {
+        if (glane == 0 && live) {
             for (int c = 0; c < o.k; c++) {
                 double r = 0.0;
                 u8 ok = 0;
@@ -280,7 +293,7 @@ __device__ __forceinline__ void sweep_tile(const SeqDev *__restrict__ sd, u64 g_
                 o.heavy_list[slot] = (u32)g;  // the host checks total < 2^32 when a median is requested
             }
         }
-        __syncwarp(gmask);  // the next left reuses kbuf
+        __syncwarp();  // the next left reuses kbuf
     }
 }
 
@@ -327,34 +340,45 @@ template <int G>
 __device__ __forceinline__ void emit_tile(const SeqDev *__restrict__ sd, u64 g_lo, u64 g_hi, const u32 *__restrict__ ls,
                                           const u32 *__restrict__ ubv, const u32 *__restrict__ ppv, const u32 *__restrict__ lbv,
                                           const u64 *__restrict__ offsets, u32 *__restrict__ pos) {
+    // Warp-synchronous like sweep3_run: the 32 / G groups of a warp step together and every vote is one
+    // full-warp instruction (per-group masks make the hardware run each group's copy in turn).
     constexpr int NGROUPS = SW2_TPB / G;
+    constexpr u32 GM = G == 32 ? 0xffffffffu : ((1u << G) - 1u);
     const u32 glane = threadIdx.x & (G - 1), gidx = threadIdx.x / G;
-    const u32 gmask = group_mask<G>();
     const u32 gshift = (threadIdx.x & 31) & ~(G - 1);
     const u32 *__restrict__ ends = sd->ends;
     const u32 *__restrict__ bme = sd->bme;
-    for (u64 g = g_lo + gidx; g < g_hi; g += NGROUPS) {
-        const u32 u = ubv[g], p = ppv[g], l = lbv[g];
-        const u32 lstart = ls[g];
+    const u64 g_warp = g_lo + (threadIdx.x >> 5) * (32 / G);
+    const u32 rounds = g_warp < g_hi ? (u32)((g_hi - g_warp + NGROUPS - 1) / NGROUPS) : 0u;
+    u64 g = g_lo + gidx;
+    for (u32 round = 0; round < rounds; round++, g += NGROUPS) {
+        const bool live = g < g_hi;
+        u32 u = 0, p = 0, l = 0, lstart = 0;
+        u32 *__restrict__ dst = pos;
+        if (live) {
+            u = ubv[g];
+            p = ppv[g];
+            l = lbv[g];
+            lstart = ls[g];
+            dst = pos + offsets[g];
+        }
         const u32 need = p - l;
-        u32 *__restrict__ dst = pos + offsets[g];
         for (u32 j = p + glane; j < u; j += G) dst[need + (j - p)] = j;
         u32 found = 0;
         long long cb = p ? (long long)((p - 1) & ~(u32)(G - 1)) : -1;
-        while (found < need && cb >= 0) {
-            if (bme[cb >> GRB_BME_SHIFT] > lstart) {
-                const u32 j = (u32)cb + glane;
-                const bool hit = j < p && ends[j] > lstart;
-                const u32 hm = (__ballot_sync(gmask, hit) >> gshift) & (G == 32 ? 0xffffffffu : ((1u << G) - 1u));
-                if (hit) {
-                    const u32 above = glane == G - 1 ? 0u : __popc(hm >> (glane + 1));
-                    dst[need - 1 - (found + above)] = j;
-                }
-                found += __popc(hm);
-                cb -= G;
-            } else {
-                cb = ((cb >> GRB_BME_SHIFT) << GRB_BME_SHIFT) - G;
+        while (true) {
+            const bool act = found < need && cb >= 0;
+            if (!__any_sync(GRB_FULL, act)) break;
+            const bool look = act && bme[cb >> GRB_BME_SHIFT] > lstart;
+            const u32 j = (u32)cb + glane;
+            const bool hit = look && j < p && ends[j] > lstart;
+            const u32 hm = (__ballot_sync(GRB_FULL, hit) >> gshift) & GM;
+            if (hit) {
+                const u32 above = glane == G - 1 ? 0u : __popc(hm >> (glane + 1));
+                dst[need - 1 - (found + above)] = j;
             }
+            found += __popc(hm);
+            if (act) cb = look ? cb - G : ((cb >> GRB_BME_SHIFT) << GRB_BME_SHIFT) - G;
         }
     }
 }

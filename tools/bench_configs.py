@@ -211,6 +211,54 @@ def c5(scale):
            pairs_per_s=tot_pairs / tot_ms * 1e3, lefts_per_s=nl / tot_ms * 1e3, index_build_ms=tb * 1e3)
 
 
+def c6(scale):
+    """granges merge: sorted BED5 records, distance 0, sum of the merged scores; device-resident input."""
+    n = int(100_000_000 * scale)
+    per = bench.split_counts(n, 22)
+    g = torch.Generator(device=dev)
+    g.manual_seed(6)
+    ss, ee = [], []
+    for s in range(22):
+        L = HG38[s]
+        st, _ = torch.sort((torch.rand(per[s], generator=g, device=dev, dtype=torch.float64) * (L - 40)).to(torch.int64))
+        ln = torch.randint(1, 40, (per[s],), generator=g, device=dev)
+        ss.append(st.to(torch.int32))
+        ee.append((st + ln).to(torch.int32))
+    st, en = torch.cat(ss), torch.cat(ee)
+    sc = torch.rand(n, generator=g, device=dev, dtype=torch.float64)
+    ro = np.concatenate([[0], np.cumsum(per)]).astype(np.uint64)
+    import ctypes as C
+
+    from granges_b200 import _capi
+
+    L_ = _capi.lib()
+    ops = (C.c_int * 1)(0)
+    res = {}
+
+    def run():
+        h = C.c_void_p()
+        t0 = time.perf_counter()
+        rc = L_.grb_merge_ranges(ctx.h, st.data_ptr(), en.data_ptr(), ro.ctypes.data_as(_capi.u64p), 22, 0, C.byref(h))
+        assert rc == 0, ctx._check(rc)
+        ctx.sync()
+        t1 = time.perf_counter()
+        m = L_.grb_merged_len(h)
+        out = torch.empty(m, dtype=torch.float64, device=dev)
+        ov = torch.empty(m, dtype=torch.uint8, device=dev)
+        rc = L_.grb_merged_map_f64(ctx.h, h, sc.data_ptr(), None, ops, 1, out.data_ptr(), ov.data_ptr())
+        assert rc == 0, ctx._check(rc)
+        ctx.sync()
+        t2 = time.perf_counter()
+        L_.grb_merged_destroy(h)
+        res.update(m=m, merge_ms=(t1 - t0) * 1e3, map_ms=(t2 - t1) * 1e3, total=float(out.sum().item()))
+
+    run()
+    run()
+    report("C6 merge %d sorted BED5 records, distance 0, sum (wall clock of the second run)" % n, merged=res["m"], merge_ms=res["merge_ms"],
+           reduce_ms=res["map_ms"], records_per_s=n / (res["merge_ms"] + res["map_ms"]) * 1e3, score_total=res["total"],
+           score_total_check=float(sc.sum().item()))
+
+
 if __name__ == "__main__":
     argv = sys.argv[1:]
     scale = 1.0
@@ -219,7 +267,7 @@ if __name__ == "__main__":
         scale = float(argv[i + 1])
         del argv[i:i + 2]
     args = argv
-    which = args or ["c1", "c2", "c3", "c4", "c5"]
+    which = args or ["c1", "c2", "c3", "c4", "c5", "c6"]
     for w in which:
         torch.cuda.empty_cache()
-        {"c1": c1, "c2": lambda: c2(scale), "c3": lambda: c3(scale), "c4": lambda: c4(scale), "c5": lambda: c5(scale), "c3ops": lambda: c3ops(scale)}[w]()
+        {"c1": c1, "c2": lambda: c2(scale), "c3": lambda: c3(scale), "c4": lambda: c4(scale), "c5": lambda: c5(scale), "c3ops": lambda: c3ops(scale), "c6": lambda: c6(scale)}[w]()
