@@ -262,7 +262,12 @@ def main():
     # ---- shard plan (identical on every rank; bounds come from the data below)
     from granges_b200 import sharding
 
-    plan = sharding.plan(left_off, nr_per, world)
+    # cost of a seqname = lefts + rights, plus its expected pairs when a reduction has to visit the members
+    # (min / max / median / weighted mean): pairs = NL * NR * (mean left length + mean right length) / seqname length
+    cost_per = [int(c) for c in nr_per]
+    if any(o in ("min", "max", "median", "weighted-mean") for o in ops):
+        cost_per = [int(nr_per[s] + sharding.PAIR_WEIGHT * nl_per[s] * nr_per[s] * 1000.0 / HG38[s]) for s in range(22)]
+    plan = sharding.plan(left_off, cost_per, world)
     mine = sharding.units_of(plan, rank)
 
     # a non-default stream: stream-ordered allocation on the legacy default stream is several times slower

@@ -15,8 +15,15 @@ import numpy as np
 from .api import shard_plan
 
 
+# What one overlap pair costs a member sweep (min / max / median), in units of one left of the prefix-sum path
+# (measured on a B200: 100M x 100M, 4.3e9 pairs -- 35 ms against 0.8 ms).
+PAIR_WEIGHT = 0.15
+
+
 def plan(left_offsets, right_counts, world, ls=None, le=None):
-    """Units (dicts: seq, rank, left_begin, left_end, right_lo, right_hi), ordered by (seq, left_begin)."""
+    """Units (dicts: seq, rank, left_begin, left_end, right_lo, right_hi), ordered by (seq, left_begin).
+    `right_counts[s]` is the cost the seqname's rights add to its lefts: the number of rights for the
+    prefix-sum reductions, plus PAIR_WEIGHT * expected pairs when the members have to be visited."""
     return shard_plan(left_offsets, right_counts, ls, le, world)
 
 
