@@ -179,6 +179,12 @@ struct grb_index {
     // overlap-bp tables, built on first use by grb_index_prepare_bp
     u64 *sum_starts;      // n + 1: sum of the i smallest starts
     u64 *sum_ends;        // n + 1: sum of the i smallest ends
+    // weighted-mean tables, built on first use by grb_index_prepare_wm (exact-sum indexes only)
+    i128 *wsum_a;         // n + 1: exact prefix of score * start (fixed point), start order
+    i128 *wsum_b;         // n + 1: exact prefix of score * end, end order
+    u64 *sum_starts_v;    // n + 1: like sum_starts over the rights that carry a score (only if has_nulls)
+    u64 *sum_ends_v;
+    bool wm_ready, wm_unavailable;
     u32 *fb;              // ceil(n/64): fb[b] <= position of the earliest right that straddles any coordinate
                           // >= starts[64 b]  (how far back a window over the rights must reach)
 };
@@ -195,7 +201,8 @@ struct SeqDev {
     const u32 *lut_a, *lut_b;
     const u32 *rank_a, *fb;
     const double *score_sorted;
-    const u64 *sum_starts, *sum_ends;
+    const u64 *sum_starts, *sum_ends, *sum_starts_v, *sum_ends_v;
+    const i128 *wsum_a, *wsum_b;
     u64 left_begin, left_end;
     double scale;    // 2^e0
     u32 n;
@@ -300,6 +307,9 @@ int grb_scan_u32_to_u32(grb_ctx *ctx, const u32 *in, u32 *out, size_t n, bool wr
 int grb_index_prepare_members(grb_ctx *ctx, grb_index *ix);
 // index.cu: prefix sums of the sorted starts / ends (the closed form of OVERLAP_BP), built on first use.
 int grb_index_prepare_bp(grb_ctx *ctx, grb_index *ix);
+// index.cu: exact prefixes of score * coordinate (the closed form of WEIGHTED_MEAN); sets ix->wm_unavailable when the
+// products do not fit the 128-bit fixed point (or the index has no exact sums) -- the caller then sweeps the members.
+int grb_index_prepare_wm(grb_ctx *ctx, grb_index *ix);
 
 // sort.cu: stable LSD radix sort of (u64 key, u32 value) pairs; skips digits that do not vary and
 // the whole sort when the keys are already non-decreasing.  On return *keys_out / *vals_out point

@@ -253,6 +253,54 @@ __global__ void __launch_bounds__(256) k_fx_blocks(const double *__restrict__ sc
     }
 }
 
+// The same block scan over score * coordinate (exact: the product of a W-bit and a 31-bit integer).
+//   phase 0: blocksum[b];  phase 2: wide[p] = base[b] + local exclusive prefix, p in [b*256, b*256+256), p <= n
+template <int PHASE>
+__global__ void __launch_bounds__(256) k_wfx_blocks(const double *__restrict__ score_a, const u32 *__restrict__ perm,
+                                                    const u32 *__restrict__ coord, size_t n, int e0, i128 *__restrict__ blocksum,
+                                                    const i128 *__restrict__ base, i128 *__restrict__ wide) {
+    __shared__ u64 s_lo[8], s_hi[8];
+    const size_t b = blockIdx.x;
+    const size_t p = (b << GRB_BASE_SHIFT) + threadIdx.x;
+    i128 v = 0;
+    if (p < n) v = to_fx(score_a[perm ? perm[p] : p], e0) * (i128)coord[p];
+    i128 incl = v;
+    const u32 lane = lane_id(), warp = threadIdx.x >> 5;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {
+        u64 tlo = __shfl_up_sync(GRB_FULL, (u64)incl, o);
+        u64 thi = __shfl_up_sync(GRB_FULL, (u64)((u128)incl >> 64), o);
+        if (lane >= o) incl += (i128)(((u128)thi << 64) | tlo);
+    }
+    if (lane == 31) {
+        s_lo[warp] = (u64)incl;
+        s_hi[warp] = (u64)((u128)incl >> 64);
+    }
+    __syncthreads();
+    i128 woff = 0, total = 0;
+#pragma unroll
+    for (int w = 0; w < 8; w++) {
+        i128 t = (i128)(((u128)s_hi[w] << 64) | s_lo[w]);
+        if (w < (int)warp) woff += t;
+        total += t;
+    }
+    i128 excl = woff + incl - v;
+    if (PHASE == 0) {
+        if (threadIdx.x == 0) blocksum[b] = total;
+    } else {
+        if (p <= n) wide[p] = base[b] + excl;
+    }
+}
+
+// coordinate of the rights that carry a score, 0 for the others (start order: perm == nullptr)
+__global__ void k_masked_coords(const u32 *__restrict__ coord, const u32 *__restrict__ vbits_a, const u32 *__restrict__ perm, size_t n,
+                                u32 *__restrict__ out) {
+    size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    const u32 j = perm ? perm[i] : (u32)i;
+    out[i] = ((vbits_a[j >> 5] >> (j & 31)) & 1u) ? coord[i] : 0u;
+}
+
 // Exclusive scan of nb i128 block sums by one CTA (nb = n/256 + 1: small).
 __global__ void __launch_bounds__(1024) k_scan_i128_single(const i128 *__restrict__ in, size_t nb, i128 *__restrict__ out) {
     __shared__ u64 s_lo[1024], s_hi[1024];
@@ -382,6 +430,13 @@ void free_scores(grb_index *ix) {
     grb_dev_free(ix->ctx, ix->base_b);
     grb_dev_free(ix->ctx, ix->rank_a);
     grb_dev_free(ix->ctx, ix->score_sorted);
+    grb_dev_free(ix->ctx, ix->wsum_a);
+    grb_dev_free(ix->ctx, ix->wsum_b);
+    grb_dev_free(ix->ctx, ix->sum_starts_v);
+    grb_dev_free(ix->ctx, ix->sum_ends_v);
+    ix->wsum_a = ix->wsum_b = nullptr;
+    ix->sum_starts_v = ix->sum_ends_v = nullptr;
+    ix->wm_ready = ix->wm_unavailable = false;
     ix->rank_a = nullptr;
     ix->score_sorted = nullptr;
     ix->members_ready = false;
@@ -773,6 +828,53 @@ int grb_index_prepare_bp(grb_ctx *ctx, grb_index *ix) {
     GRB_TRY(dev_alloc(ctx, (void **)&ix->sum_ends, (n + 1) * 8));
     GRB_TRY(grb_scan_u32_to_u64(ctx, ix->starts, ix->sum_starts, n, true));
     GRB_TRY(grb_scan_u32_to_u64(ctx, ix->ends_sorted, ix->sum_ends, n, true));
+    return GRB_OK;
+}
+
+// WEIGHTED_MEAN in closed form needs exact prefixes of score * start (start order) and score * end (end order):
+// sum_r score_r |l & r| = G(l.end) - G(l.start),  G(x) = WE[#{end <= x}] - WS[#{start < x}] + x (PA[#{start < x}] - PB[#{end <= x}]).
+static int build_wprefix(grb_ctx *ctx, grb_index *ix, const u32 *perm, const u32 *coord, i128 **out) {
+    const size_t n = ix->n;
+    const size_t nb = (n >> GRB_BASE_SHIFT) + 1;
+    TempBuf bsum, bbase;
+    GRB_TRY(bsum.alloc(ctx, nb * sizeof(i128)));
+    GRB_TRY(bbase.alloc(ctx, nb * sizeof(i128)));
+    GRB_TRY(dev_alloc(ctx, (void **)out, (n + 1) * sizeof(i128)));
+    k_wfx_blocks<0><<<(unsigned)nb, 256, 0, ctx->stream>>>(ix->score_a, perm, coord, n, ix->e0, bsum.as<i128>(), nullptr, nullptr);
+    GRB_LAUNCHED(ctx);
+    k_scan_i128_single<<<1, 1024, 0, ctx->stream>>>(bsum.as<i128>(), nb, bbase.as<i128>());
+    GRB_LAUNCHED(ctx);
+    k_wfx_blocks<2><<<(unsigned)nb, 256, 0, ctx->stream>>>(ix->score_a, perm, coord, n, ix->e0, nullptr, bbase.as<i128>(), *out);
+    GRB_LAUNCHED(ctx);
+    return GRB_OK;
+}
+
+int grb_index_prepare_wm(grb_ctx *ctx, grb_index *ix) {
+    if (!ix || ix->wm_ready || ix->wm_unavailable || !ix->n || !ix->has_scores) return GRB_OK;
+    const int L = ceil_log2((u64)ix->n + 1);
+    // score (W bits) * coordinate (31 bits) summed over n rights must fit the signed 128-bit fixed point, and the
+    // rounded result a double
+    if (ix->sum_mode == GRB_SUM_SWEEP || ix->width + L + 32 > 126 || ix->e0 + ix->width + L + 33 >= 1023) {
+        ix->wm_unavailable = true;
+        return GRB_OK;
+    }
+    const size_t n = ix->n;
+    GRB_TRY(grb_index_prepare_bp(ctx, ix));
+    GRB_TRY(build_wprefix(ctx, ix, nullptr, ix->starts, &ix->wsum_a));
+    GRB_TRY(build_wprefix(ctx, ix, ix->perm_e, ix->ends_sorted, &ix->wsum_b));
+    if (ix->has_nulls) {
+        TempBuf m;
+        GRB_TRY(m.alloc(ctx, n * 4));
+        GRB_TRY(dev_alloc(ctx, (void **)&ix->sum_starts_v, (n + 1) * 8));
+        GRB_TRY(dev_alloc(ctx, (void **)&ix->sum_ends_v, (n + 1) * 8));
+        k_masked_coords<<<blocks_for(n, 256), 256, 0, ctx->stream>>>(ix->starts, ix->vbits_a, nullptr, n, m.as<u32>());
+        GRB_LAUNCHED(ctx);
+        GRB_TRY(grb_scan_u32_to_u64(ctx, m.as<u32>(), ix->sum_starts_v, n, true));
+        k_masked_coords<<<blocks_for(n, 256), 256, 0, ctx->stream>>>(ix->ends_sorted, ix->vbits_a, ix->perm_e, n, m.as<u32>());
+        GRB_LAUNCHED(ctx);
+        GRB_TRY(grb_scan_u32_to_u64(ctx, m.as<u32>(), ix->sum_ends_v, n, true));
+    }
+    ix->wm_ready = true;
     return GRB_OK;
 }
 

@@ -630,6 +630,61 @@ __global__ void __launch_bounds__(256) k_overlap_bp(const SeqDev *__restrict__ s
         }
 }
 
+// exact 128-bit prefix of the scores at position j (start order: pfx_a / base_a, end order: pfx_b / base_b)
+__device__ __forceinline__ i128 exact_prefix(const u64 *__restrict__ pfx, const i128 *__restrict__ base, int mode, u32 j) {
+    if (mode == GRB_SUM_WIDE) return base[j];
+    const i128 b = base[j >> GRB_BASE_SHIFT];
+    return b + (i128)(i64)(pfx[j] - (u64)(u128)b);
+}
+
+// WEIGHTED_MEAN (examples/weighted_mean.rs:4-31: sum(score * overlap width) / sum(overlap width) over the rights that
+// carry a score, 0.0 if there is none) in closed form, like k_overlap_bp: no member is visited and the weighted sum is
+// exact before it is rounded once.
+__global__ void __launch_bounds__(256) k_weighted_mean(const SeqDev *__restrict__ seqs, int nseq, u64 total, const u32 *__restrict__ ls,
+                                                       const u32 *__restrict__ le, const u32 *__restrict__ ubv,
+                                                       const u32 *__restrict__ ppv, const u32 *__restrict__ lbv,
+                                                       double *__restrict__ out, u8 *__restrict__ out_valid, int k, u32 col_mask) {
+    const u64 g = (u64)blockIdx.x * blockDim.x + threadIdx.x;
+    if (g >= total) return;
+    const SeqDev *__restrict__ sd = &seqs[find_seq_by_left(seqs, nseq, g)];
+    double r = 0.0;
+    if (sd->n && sd->has_scores) {
+        const u32 u = ubv[g], p = ppv[g], l = lbv[g], a = ls[g], b = le[g];
+        u32 lo = l, hi = u;
+        if (hi < lo) hi = lo;  // invalid left (flagged elsewhere)
+        const u32 *__restrict__ es = sd->ends_sorted;
+        while (lo < hi) {
+            const u32 mid = lo + ((hi - lo) >> 1);
+            if (es[mid] <= b)
+                lo = mid + 1;
+            else
+                hi = mid;
+        }
+        const u32 a2 = lo;  // #{end <= l.end}
+        const int mode = sd->sum_mode;
+        const i128 pa_u = exact_prefix(sd->pfx_a, sd->base_a, mode, u), pa_p = exact_prefix(sd->pfx_a, sd->base_a, mode, p);
+        const i128 pb_a2 = exact_prefix(sd->pfx_b, sd->base_b, mode, a2), pb_l = exact_prefix(sd->pfx_b, sd->base_b, mode, l);
+        const i128 g_end = sd->wsum_b[a2] - sd->wsum_a[u] + (i128)b * (pa_u - pb_a2);
+        const i128 g_start = sd->wsum_b[l] - sd->wsum_a[p] + (i128)a * (pa_p - pb_l);
+        const i128 wsum = g_end - g_start;
+        u64 wtot;
+        if (sd->has_nulls) {
+            const u32 vu = sd->vcnt_a[u], vp = sd->vcnt_a[p], va2 = sd->vcnt_b[a2], vl = sd->vcnt_b[l];
+            wtot = (sd->sum_ends_v[a2] - sd->sum_starts_v[u] + (u64)b * (u64)(vu - va2)) -
+                   (sd->sum_ends_v[l] - sd->sum_starts_v[p] + (u64)a * (u64)(vp - vl));
+        } else {
+            wtot = (sd->sum_ends[a2] - sd->sum_starts[u] + (u64)b * (u64)(u - a2)) -
+                   (sd->sum_ends[l] - sd->sum_starts[p] + (u64)a * (u64)(p - l));
+        }
+        if (wtot) r = fx_to_double(wsum, sd->e0) / (double)wtot;
+    }
+    for (int c = 0; c < k; c++)
+        if ((col_mask >> c) & 1u) {
+            out[g * (u64)k + c] = r;
+            out_valid[g * (u64)k + c] = 1;
+        }
+}
+
 // filter_overlaps as a stream compaction: keep flags -> exclusive scan -> scatter of the kept left indices
 // (ascending, i.e. the reference's order-preserving filter, src/granges.rs:1485-1508).
 __global__ void k_keep_to_u32(const u8 *__restrict__ keep, u64 n, u32 *__restrict__ flags) {
@@ -685,6 +740,10 @@ int make_batch(grb_ctx *ctx, const grb_index *const *idx, const u64 *left_offset
             d.fb = ix->fb;
             d.sum_starts = ix->sum_starts;
             d.sum_ends = ix->sum_ends;
+            d.sum_starts_v = ix->sum_starts_v;
+            d.sum_ends_v = ix->sum_ends_v;
+            d.wsum_a = ix->wsum_a;
+            d.wsum_b = ix->wsum_b;
             d.lut_shift = ix->lut_shift;
             d.lut_bmax = ix->lut_bmax;
             d.base_a = ix->base_a;
@@ -768,10 +827,11 @@ int launch_tile(grb_ctx *ctx, const Batch &b, const u32 *ls, const u32 *le, cons
 template <int FAST>
 int launch_pipe(grb_ctx *ctx, const Batch &b, const u32 *ls, const u32 *le, const TileOut &o) {
     if (b.ntiles == 0) return GRB_OK;
-    static bool configured = false;
-    if (!configured) {
+    // the opt-in to > 48 KB of dynamic shared memory is per device: remembered per device, not per process
+    static bool configured[64] = {};
+    if (ctx->device < 0 || ctx->device >= 64 || !configured[ctx->device]) {
         GRB_CUDA(ctx, cudaFuncSetAttribute(k_map_pipe<FAST>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(PipeSmem)));
-        configured = true;
+        if (ctx->device >= 0 && ctx->device < 64) configured[ctx->device] = true;
     }
     const int flags = (ctx->tile_mode ? 1 : 0) | (ctx->pipe_mode == 2 ? 2 : 0) | (ctx->pipe_mode == 3 ? 4 : 0);
     // the kernel keeps its seqnames' descriptors in shared memory: at most PIPE_MAXSEQ per launch
@@ -1065,7 +1125,23 @@ static int map_joins_impl(grb_ctx *ctx, const grb_index *const *idx, const uint6
             return grb_fail(ctx, GRB_ERR_NAN_SCORE, "map_joins: median over NaN scores (the reference panics in partial_cmp().unwrap())");
         if (need_sum && ix->n && ix->sum_mode == GRB_SUM_SWEEP) need_members = true;
     }
-    // OVERLAP_BP has a closed form (k_overlap_bp) unless the weighted mean needs the members' widths anyway
+    // WEIGHTED_MEAN has a closed form (k_weighted_mean) when every index has exact sums with room for score * coordinate
+    u32 wm_cols = 0;
+    if (want_wm && ctx->sweep_mode != 0) {
+        bool ok = true;
+        for (int s = 0; s < nseq && ok; s++) {
+            const grb_index *ix = idx ? idx[s] : nullptr;
+            if (!ix || !ix->n) continue;
+            GRB_TRY(grb_index_prepare_wm(ctx, const_cast<grb_index *>(ix)));
+            ok = ix->wm_ready;
+        }
+        if (ok) {
+            for (int c = 0; c < k; c++)
+                if (ops[c] == GRB_OP_WEIGHTED_MEAN) wm_cols |= 1u << c;
+            want_wm = false;
+        }
+    }
+    // OVERLAP_BP has a closed form (k_overlap_bp) unless a swept weighted mean needs the members' widths anyway
     const bool bp_closed = want_bp && !want_wm && ctx->sweep_mode != 0;
     u32 bp_cols = 0;
     if (bp_closed) {
@@ -1118,7 +1194,7 @@ static int map_joins_impl(grb_ctx *ctx, const grb_index *const *idx, const uint6
     o.k = k;
     o.need_sum = need_sum;
     for (int c = 0; c < k; c++) o.ops[c] = ops[c];
-    if (!need_members && !bp_cols) {
+    if (!need_members && !bp_cols && !wm_cols) {
         GRB_TRY(launch_map<M_MAP>(ctx, b, dls.as<u32>(), dle.as<u32>(), o));
     } else {
         TempBuf ub, lb, pp, heavy;
@@ -1132,6 +1208,11 @@ static int map_joins_impl(grb_ctx *ctx, const grb_index *const *idx, const uint6
         if (bp_cols) {
             k_overlap_bp<<<(unsigned)((b.total + 255) / 256), 256, 0, ctx->stream>>>(b.seqs, b.nseq, b.total, dls.as<u32>(), dle.as<u32>(), o.ub,
                                                                                    o.pp, o.lb, o.out, o.out_valid, k, bp_cols);
+            GRB_LAUNCHED(ctx);
+        }
+        if (wm_cols) {
+            k_weighted_mean<<<(unsigned)((b.total + 255) / 256), 256, 0, ctx->stream>>>(b.seqs, b.nseq, b.total, dls.as<u32>(), dle.as<u32>(),
+                                                                                      o.ub, o.pp, o.lb, o.out, o.out_valid, k, wm_cols);
             GRB_LAUNCHED(ctx);
         }
         if (need_members) {
@@ -1152,10 +1233,10 @@ static int map_joins_impl(grb_ctx *ctx, const grb_index *const *idx, const uint6
                 so.heavy_list = heavy.as<u32>() + 1;
             }
             if (rank_sweep) {
-                static bool configured = false;
-                if (!configured) {
+                static bool configured[64] = {};
+                if (ctx->device < 0 || ctx->device >= 64 || !configured[ctx->device]) {
                     GRB_CUDA(ctx, cudaFuncSetAttribute(k_sweep3, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(Sweep3Smem)));
-                    configured = true;
+                    if (ctx->device >= 0 && ctx->device < 64) configured[ctx->device] = true;
                 }
                 k_sweep3<<<b.ntiles, SW3_TPB, sizeof(Sweep3Smem), ctx->stream>>>(b.seqs, b.tile_begin, b.nseq, dls.as<u32>(), o.ub, o.pp, o.lb, so,
                                                                                 ctx->sweep_mode == 1 ? 1 : 0);

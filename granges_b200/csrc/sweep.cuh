@@ -276,6 +276,7 @@ __device__ __forceinline__ void sweep_tile(const SeqDev *__restrict__ sd, u64 g_
                         r = (double)bp;
                         break;
                     case GRB_OP_WEIGHTED_MEAN:
+                        mine = o.want_wm != 0;  // otherwise k_weighted_mean answers it in closed form
                         ok = 1;
                         r = wtot ? wsum / (double)wtot : 0.0;
                         break;

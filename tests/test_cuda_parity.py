@@ -611,8 +611,8 @@ def test_rank_sweep_batch_with_absent_seqnames(eng, orc):
 @pytest.mark.parametrize("ops", [["overlap-bp"], ["min", "overlap-bp", "mean", "median"], ["overlap-bp", "weighted-mean"]],
                          ids=["bp", "bp+members", "bp+wm"])
 def test_overlap_bp_closed_form(eng, orc, name, ops):
-    """OVERLAP_BP from the prefix sums of the sorted starts / ends (k_overlap_bp, no member visited) is exact;
-    beside a weighted mean it still comes from the member sweep -- same numbers."""
+    """OVERLAP_BP from the prefix sums of the sorted starts / ends (k_overlap_bp, no member visited) is exact,
+    alone, beside member reductions and beside a weighted mean."""
     kw = dict(RANK_SWEEP_CASES[name])
     nl, nr = kw.pop("nl"), kw.pop("nr")
     c = random_case(777 + nr, nl, nr, **kw)
@@ -632,3 +632,43 @@ def test_overlap_bp_closed_form(eng, orc, name, ops):
     for i in range(0, nl, max(1, nl // 200)):
         w = np.minimum(c["re"], c["le"][i]).astype(np.int64) - np.maximum(c["rs"], c["ls"][i]).astype(np.int64)
         assert out[i, col] == w[w > 0].sum()
+
+
+@pytest.mark.parametrize("kind", ["plain", "nulls-int", "long-mixed", "dense-ties", "wide", "sorted-left", "nulls-sorted"])
+def test_weighted_mean_closed_form(orc, monkeypatch, kind):
+    """WEIGHTED_MEAN (examples/weighted_mean.rs:4-31) from exact prefixes of score * coordinate (k_weighted_mean) against
+    the member sweep (GRB_SWEEP_MODE=0) and the oracle; score ranges too wide for the fixed point ("wide") fall back
+    to the sweep on their own."""
+    import granges_b200 as gb
+
+    c = random_case(4100, 4000, 6000, **dict(KINDS[kind], span=KINDS[kind].get("span", 40000)))
+    ops = ["weighted-mean", "overlap-bp", "count", "mean"]
+    res = {}
+    for mode in ("1", "0"):
+        monkeypatch.setenv("GRB_SWEEP_MODE", mode)
+        ctx = gb.Context(0)
+        ix = ctx.index_build(c["rs"], c["re"]).set_scores(c["scores"], c["valid"])
+        res[mode] = ctx.map_joins(ix, c["ls"], c["le"], ops)
+    t = orc.Tree(c["rs"], c["re"])
+    want, wv = orc.map_joins(t, c["scores"], c["valid"], c["ls"], c["le"], ops)
+    amax = np.abs(c["scores"]).max() if len(c["scores"]) else 0.0
+    for mode in res:
+        out, ov = res[mode]
+        assert (ov == wv).all()
+        assert (out[:, 1] == want[:, 1]).all() and (out[:, 2] == want[:, 2]).all()
+        # |weighted mean| <= max |score|; both sides round a sum of products: 1e-12 of that scale
+        assert (np.abs(out[:, 0] - want[:, 0]) <= 1e-12 * amax).all(), mode
+    # brute force of the closed form's exactness on a few lefts: sum(score * width) / sum(width) in exact arithmetic
+    from fractions import Fraction
+
+    valid = np.ones(len(c["rs"]), bool) if c["valid"] is None else c["valid"].astype(bool)
+    if kind not in ("wide", "long-mixed"):  # those score ranges leave no room for score * coordinate: swept, not exact
+        for i in range(0, len(c["ls"]), 400):
+            w = np.minimum(c["re"], c["le"][i]).astype(np.int64) - np.maximum(c["rs"], c["ls"][i]).astype(np.int64)
+            m = (w > 0) & valid
+            if not m.any():
+                assert res["1"][0][i, 0] == 0.0
+                continue
+            num = sum(Fraction(float(s)) * int(x) for s, x in zip(c["scores"][m], w[m]))
+            exact = float(num) / float(int(w[m].sum()))
+            assert res["1"][0][i, 0] == exact
