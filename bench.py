@@ -398,13 +398,9 @@ def main():
         def e2e_step():
             if not nl_mine:
                 return 0.0
-            hs = ctx.index_build_batch([(a.numpy().view(np.uint32), b.numpy().view(np.uint32), c.numpy()) for a, b, c in h_rights])
-            ctx.map_joins_batch(hs, offs, h_ls.numpy().view(np.uint32), h_le.numpy().view(np.uint32), ops, out=h_out.numpy(),
-                                out_valid=h_ov.numpy())
-            chk = float(h_out[0, 0])  # the result is on the host
-            for h in hs:
-                h.close()
-            return chk
+            ctx.map_whole([(a.numpy().view(np.uint32), b.numpy().view(np.uint32), c.numpy()) for a, b, c in h_rights], offs,
+                          h_ls.numpy().view(np.uint32), h_le.numpy().view(np.uint32), ops, out=h_out.numpy(), out_valid=h_ov.numpy())
+            return float(h_out[0, 0])  # the result is on the host
 
         e2e_steps = max(2, min(args.steps, 3))
         e2e_step()
@@ -420,8 +416,8 @@ def main():
         nr_all = int(agg[2].item())
         e2e = {"value": args.lefts / e2e_s, "unit": "left ranges/s", "h2d_bytes_per_step": nr_all * 16 + nl_total * 8,
                "d2h_bytes_per_step": nl_total * k * 9, "ms_per_step": e2e_s * 1e3, "steps": e2e_steps,
-               "includes": "grb_index_build_batch (H2D rights+scores, index builds) + grb_map_joins_f64_batch (H2D lefts, map pass, D2H "
-                           "results), pinned host buffers, per rank for its own units; wall clock, max over ranks"}
+               "includes": "grb_map_joins_whole_f64 = `granges map` in one call: H2D of rights + scores + lefts, index builds, map pass, D2H "
+                           "of the results, pipelined per seqname; pinned host buffers, per rank for its own units; wall clock, max over ranks"}
         del h_rights, h_ls, h_le
 
     if rank != 0:

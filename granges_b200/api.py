@@ -225,6 +225,42 @@ class Context:
                                                       VP(*psc) if any_scores else None, VP(*pva) if any_valid else None, out))
         return [Index(self, C.c_void_p(h)) for h in out]
 
+    def map_whole(self, rights, left_offsets, ls, le, ops, out=None, out_valid=None):
+        """`granges map` in one call for host arrays (grb_map_joins_whole_f64): `rights` as in index_build_batch,
+        lefts concatenated in seqname order.  Uploads, index builds, map kernels and downloads of different seqnames
+        overlap; the results equal index_build_batch + map_joins_batch."""
+        nseq = len(rights)
+        keep, ps, pe, psc, pva, ns = [], [], [], [], [], []
+        any_scores = any(len(r) > 2 and r[2] is not None for r in rights)
+        any_valid = any(len(r) > 3 and r[3] is not None for r in rights)
+        for r in rights:
+            a, ka, _ = _arg(r[0], np.uint32)
+            b, kb, _ = _arg(r[1], np.uint32)
+            c, kc, _ = _arg(r[2] if len(r) > 2 else None, np.float64)
+            d, kd, _ = _arg(r[3] if len(r) > 3 else None, np.uint8)
+            keep += [ka, kb, kc, kd]
+            ps.append(a)
+            pe.append(b)
+            psc.append(c)
+            pva.append(d)
+            ns.append(len(ka))
+        pl, kl, _ = _arg(ls, np.uint32)
+        ple, kle, _ = _arg(le, np.uint32)
+        off = np.ascontiguousarray(left_offsets, dtype=np.uint64)
+        ops_a, ops_p = self._ops(ops)
+        k = len(ops_a)
+        nl = len(kl)
+        if out is None:
+            out = np.empty((nl, k), np.float64)
+        if out_valid is None:
+            out_valid = np.empty((nl, k), np.uint8)
+        po, pv = _arg(out, np.float64)[0], _arg(out_valid, np.uint8)[0]
+        VP = C.c_void_p * nseq
+        self._check(_capi.lib().grb_map_joins_whole_f64(self.h, nseq, VP(*ps), VP(*pe), (C.c_size_t * nseq)(*ns),
+                                                        VP(*psc) if any_scores else None, VP(*pva) if any_valid else None,
+                                                        off.ctypes.data_as(_capi.u64p), pl, ple, ops_p, k, po, pv))
+        return out, out_valid
+
     # -- helpers
     @staticmethod
     def _ops(ops):

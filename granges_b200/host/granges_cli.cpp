@@ -380,7 +380,6 @@ int cmd_map(const Args &a) {
         check(nullptr, ctx_rc);
     }
     const int nseq = (int)g.names.size();
-    std::vector<grb_index *> idx(nseq, nullptr);
     std::vector<uint64_t> off(nseq + 1, 0);
     std::vector<uint32_t> ls, le;
     ls.reserve(nl);
@@ -391,9 +390,14 @@ int cmd_map(const Args &a) {
         le.insert(le.end(), L[s].ends.begin(), L[s].ends.end());
     }
     off[nseq] = ls.size();
+    const int k = (int)a.ops.size();
+    std::vector<double> out(nl * (size_t)k);
+    std::vector<uint8_t> ov(nl * (size_t)k);
     {
-        Phase ph("index build (batch)");
-        // the whole right-hand side at once: uploads and builds of different seqnames overlap
+        Phase ph("index builds + map_joins");
+        // into_coitrees -> left_overlaps -> map_joins in one pipelined call: uploads, index builds, map kernels and
+        // downloads of different seqnames overlap.  A seqname the right file never mentions (n = 0) has no container
+        // (its groups are empty either way).
         std::vector<const uint32_t *> ps(nseq), pe(nseq);
         std::vector<const double *> psc(nseq);
         std::vector<const uint8_t *> pva(nseq);
@@ -405,20 +409,8 @@ int cmd_map(const Args &a) {
             pva[s] = R[s].valid.data();
             pn[s] = R[s].starts.size();
         }
-        check(ctx, grb_index_build_batch(ctx, nseq, ps.data(), pe.data(), pn.data(), psc.data(), pva.data(), idx.data()));
-        // a seqname the right file never mentions has no container (its groups are empty either way)
-        for (int s = 0; s < nseq; s++)
-            if (pn[s] == 0) {
-                grb_index_destroy(idx[s]);
-                idx[s] = nullptr;
-            }
-    }
-    const int k = (int)a.ops.size();
-    std::vector<double> out(nl * (size_t)k);
-    std::vector<uint8_t> ov(nl * (size_t)k);
-    {
-        Phase ph("map_joins");
-        check(ctx, grb_map_joins_f64_batch(ctx, idx.data(), off.data(), nseq, ls.data(), le.data(), a.ops.data(), k, out.data(), ov.data()));
+        check(ctx, grb_map_joins_whole_f64(ctx, nseq, ps.data(), pe.data(), pn.data(), psc.data(), pva.data(), off.data(), ls.data(), le.data(),
+                                           a.ops.data(), k, out.data(), ov.data()));
     }
     Phase phw("write");
     size_t max_name = 0;
@@ -442,7 +434,6 @@ int cmd_map(const Args &a) {
         *q++ = '\n';
         return q;
     });
-    for (auto ix : idx) grb_index_destroy(ix);
     grb_ctx_destroy(ctx);
     return 0;
 }

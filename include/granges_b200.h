@@ -183,6 +183,16 @@ int grb_map_joins_f64_batch(grb_ctx *ctx, const grb_index *const *idx, const uin
                             const uint32_t *ls, const uint32_t *le, const int *ops, int k, double *out,
                             uint8_t *out_valid);
 
+/* `granges map` in one call for host-resident inputs -- src/commands.rs:477-547 (into_coitrees -> map_data ->
+ * left_overlaps -> map_joins): grb_index_build_batch + grb_map_joins_f64_batch, pipelined per seqname so that the
+ * results of the first seqnames travel back while the rights of the later ones are still being uploaded and indexed.
+ * Same results as the two calls; the indexes are internal and gone on return.  r_scores / r_valid as in
+ * grb_index_build_batch; r_n[s] == 0 means the right file never mentions the seqname. */
+int grb_map_joins_whole_f64(grb_ctx *ctx, int nseq, const uint32_t *const *r_starts, const uint32_t *const *r_ends,
+                            const size_t *r_n, const double *const *r_scores, const uint8_t *const *r_valid,
+                            const uint64_t *left_offsets, const uint32_t *ls, const uint32_t *le, const int *ops, int k,
+                            double *out, uint8_t *out_valid);
+
 /* ---- windows ----------------------------------------------------------- */
 
 /* GRangesEmpty::from_windows -- src/granges.rs:634-666, generated on the device.  step 0 means

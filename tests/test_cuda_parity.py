@@ -672,3 +672,35 @@ def test_weighted_mean_closed_form(orc, monkeypatch, kind):
             num = sum(Fraction(float(s)) * int(x) for s, x in zip(c["scores"][m], w[m]))
             exact = float(num) / float(int(w[m].sum()))
             assert res["1"][0][i, 0] == exact
+
+
+@pytest.mark.parametrize("ops", [["mean"], ["min", "mean", "median", "count"]], ids=["mean", "mixed"])
+def test_map_whole_equals_two_calls(eng, orc, ops):
+    """grb_map_joins_whole_f64 (`granges map` in one call, pipelined per seqname) returns exactly what
+    grb_index_build_batch + grb_map_joins_f64_batch return -- seqnames without rights, without lefts, None scores."""
+    specs = [(60_000, 50_000, 3_000_000, 0.0), (1500, 0, 10_000, 0.0), (0, 500, 10_000, 0.0), (45_000, 70_000, 5_000_000, 0.2),
+             (700, 900, 40_000, 0.0), (30_000, 20_000, 900_000, 0.0), (5, 3, 100, 0.0), (20_000, 25_000, 1_000_000, 0.0),
+             (20_000, 25_000, 1_000_000, 0.0), (9_000, 12_000, 400_000, 0.5)]
+    cases = [random_case(1200 + i, nl, nr, span=span, maxlen=900, sorted_left=True, null_frac=nf) for i, (nl, nr, span, nf) in enumerate(specs)]
+    off = np.concatenate([[0], np.cumsum([len(c["ls"]) for c in cases])]).astype(np.uint64)
+    ls = np.concatenate([c["ls"] for c in cases])
+    le = np.concatenate([c["le"] for c in cases])
+    rights = [(c["rs"], c["re"], c["scores"], c["valid"] if c["valid"] is not None else np.ones(len(c["rs"]), np.uint8)) for c in cases]
+    got, gv = eng.ctx.map_whole(rights, off, ls, le, ops)
+    idxs = eng.ctx.index_build_batch(rights)
+    want, wv = eng.ctx.map_joins_batch(idxs, off, ls, le, ops)
+    assert (gv == wv).all()
+    m = wv == 1
+    assert (got[m] == want[m]).all()
+    # and the oracle on one seqname
+    c = cases[3]
+    sl = slice(int(off[3]), int(off[4]))
+    t = orc.Tree(c["rs"], c["re"])
+    o_want, o_wv = orc.map_joins(t, c["scores"], c["valid"], c["ls"], c["le"], ops)
+    assert (gv[sl] == o_wv).all()
+    for col, op in enumerate(ops):
+        mm = o_wv[:, col] == 1
+        if op == "mean":
+            assert np.allclose(got[sl][mm, col], o_want[mm, col], rtol=1e-12, atol=0)
+        else:
+            assert (got[sl][mm, col] == o_want[mm, col]).all()
