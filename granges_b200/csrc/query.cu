@@ -597,11 +597,11 @@ __global__ void k_pairs_widths(const u32 *__restrict__ pos, const u64 *__restric
 
 // OVERLAP_BP (sum of LeftGroupedJoin::overlap_widths, join.rs:158-163) in closed form from ub / pp / lb and the
 // prefix sums of the sorted starts / ends (index.cu: grb_index_prepare_bp): one more bounded search per left.
-__global__ void __launch_bounds__(256) k_overlap_bp(const SeqDev *__restrict__ seqs, int nseq, u64 total, const u32 *__restrict__ ls,
+__global__ void __launch_bounds__(256) k_overlap_bp(const SeqDev *__restrict__ seqs, int nseq, u64 first, u64 total, const u32 *__restrict__ ls,
                                                     const u32 *__restrict__ le, const u32 *__restrict__ ubv,
                                                     const u32 *__restrict__ ppv, const u32 *__restrict__ lbv,
                                                     double *__restrict__ out, u8 *__restrict__ out_valid, int k, u32 col_mask) {
-    const u64 g = (u64)blockIdx.x * blockDim.x + threadIdx.x;
+    const u64 g = first + (u64)blockIdx.x * blockDim.x + threadIdx.x;  // a batch may start anywhere in the left arrays
     if (g >= total) return;
     const SeqDev *__restrict__ sd = &seqs[find_seq_by_left(seqs, nseq, g)];
     u64 bp = 0;
@@ -640,11 +640,11 @@ __device__ __forceinline__ i128 exact_prefix(const u64 *__restrict__ pfx, const 
 // WEIGHTED_MEAN (examples/weighted_mean.rs:4-31: sum(score * overlap width) / sum(overlap width) over the rights that
 // carry a score, 0.0 if there is none) in closed form, like k_overlap_bp: no member is visited and the weighted sum is
 // exact before it is rounded once.
-__global__ void __launch_bounds__(256) k_weighted_mean(const SeqDev *__restrict__ seqs, int nseq, u64 total, const u32 *__restrict__ ls,
+__global__ void __launch_bounds__(256) k_weighted_mean(const SeqDev *__restrict__ seqs, int nseq, u64 first, u64 total, const u32 *__restrict__ ls,
                                                        const u32 *__restrict__ le, const u32 *__restrict__ ubv,
                                                        const u32 *__restrict__ ppv, const u32 *__restrict__ lbv,
                                                        double *__restrict__ out, u8 *__restrict__ out_valid, int k, u32 col_mask) {
-    const u64 g = (u64)blockIdx.x * blockDim.x + threadIdx.x;
+    const u64 g = first + (u64)blockIdx.x * blockDim.x + threadIdx.x;  // a batch may start anywhere in the left arrays
     if (g >= total) return;
     const SeqDev *__restrict__ sd = &seqs[find_seq_by_left(seqs, nseq, g)];
     double r = 0.0;
@@ -1175,7 +1175,7 @@ static int map_joins_impl(grb_ctx *ctx, const grb_index *const *idx, const uint6
     }
     Batch b;
     GRB_TRY(make_batch(ctx, idx, left_offsets, nseq, &b));
-    if (b.total == 0) return GRB_OK;
+    if (b.total == 0 || b.ntiles == 0) return GRB_OK;  // (a batch that starts past 0 may hold no lefts at all)
     if (!ls || !le || !out || !out_valid) return grb_fail(ctx, GRB_ERR_INVALID_ARG, "map_joins: NULL buffer");
     if (allow_chunks && nseq >= 2 && b.total >= (1u << 22) && !grb_is_device_ptr(ls) && !grb_is_device_ptr(le) &&
         !grb_is_device_ptr(out) && !grb_is_device_ptr(out_valid))
@@ -1206,12 +1206,14 @@ static int map_joins_impl(grb_ctx *ctx, const grb_index *const *idx, const uint6
         o.pp = pp.as<u32>();
         GRB_TRY(launch_map<M_MAP | M_UBLB>(ctx, b, dls.as<u32>(), dle.as<u32>(), o));
         if (bp_cols) {
-            k_overlap_bp<<<(unsigned)((b.total + 255) / 256), 256, 0, ctx->stream>>>(b.seqs, b.nseq, b.total, dls.as<u32>(), dle.as<u32>(), o.ub,
+            k_overlap_bp<<<(unsigned)((b.total - left_offsets[0] + 255) / 256), 256, 0, ctx->stream>>>(b.seqs, b.nseq, left_offsets[0], b.total,
+                                                                                                     dls.as<u32>(), dle.as<u32>(), o.ub,
                                                                                    o.pp, o.lb, o.out, o.out_valid, k, bp_cols);
             GRB_LAUNCHED(ctx);
         }
         if (wm_cols) {
-            k_weighted_mean<<<(unsigned)((b.total + 255) / 256), 256, 0, ctx->stream>>>(b.seqs, b.nseq, b.total, dls.as<u32>(), dle.as<u32>(),
+            k_weighted_mean<<<(unsigned)((b.total - left_offsets[0] + 255) / 256), 256, 0, ctx->stream>>>(b.seqs, b.nseq, left_offsets[0], b.total,
+                                                                                                        dls.as<u32>(), dle.as<u32>(),
                                                                                       o.ub, o.pp, o.lb, o.out, o.out_valid, k, wm_cols);
             GRB_LAUNCHED(ctx);
         }

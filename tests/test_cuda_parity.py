@@ -459,7 +459,7 @@ def test_host_buffers_chunked_pipeline(eng):
     ls, le = np.concatenate(lss), np.concatenate(les)
     assert len(ls) >= 1 << 22
     dls, dle = torch.from_numpy(ls.view(np.int32)).cuda(), torch.from_numpy(le.view(np.int32)).cuda()
-    for ops in (["mean"], ["max", "mean", "count"]):
+    for ops in (["mean"], ["max", "mean", "count"], ["overlap-bp", "weighted-mean", "median"]):
         host_out, host_v = ctx.map_joins_batch(idxs, off, ls, le, ops)            # chunked host path
         dev_out, dev_v = ctx.map_joins_batch(idxs, off, dls, dle, ops)            # device path
         ctx.sync()
@@ -674,11 +674,11 @@ def test_weighted_mean_closed_form(orc, monkeypatch, kind):
             assert res["1"][0][i, 0] == exact
 
 
-@pytest.mark.parametrize("ops", [["mean"], ["min", "mean", "median", "count"]], ids=["mean", "mixed"])
+@pytest.mark.parametrize("ops", [["mean"], ["min", "mean", "median", "count"], ["weighted-mean", "overlap-bp"]], ids=["mean", "mixed", "widths"])
 def test_map_whole_equals_two_calls(eng, orc, ops):
     """grb_map_joins_whole_f64 (`granges map` in one call, pipelined per seqname) returns exactly what
     grb_index_build_batch + grb_map_joins_f64_batch return -- seqnames without rights, without lefts, None scores."""
-    specs = [(60_000, 50_000, 3_000_000, 0.0), (1500, 0, 10_000, 0.0), (0, 500, 10_000, 0.0), (45_000, 70_000, 5_000_000, 0.2),
+    specs = [(60_000, 50_000, 3_000_000, 0.0), (1500, 0, 10_000, 0.0), (0, 500_000, 10_000_000, 0.0), (45_000, 70_000, 5_000_000, 0.2),
              (700, 900, 40_000, 0.0), (30_000, 20_000, 900_000, 0.0), (5, 3, 100, 0.0), (20_000, 25_000, 1_000_000, 0.0),
              (20_000, 25_000, 1_000_000, 0.0), (9_000, 12_000, 400_000, 0.5)]
     cases = [random_case(1200 + i, nl, nr, span=span, maxlen=900, sorted_left=True, null_frac=nf) for i, (nl, nr, span, nf) in enumerate(specs)]
@@ -700,7 +700,7 @@ def test_map_whole_equals_two_calls(eng, orc, ops):
     assert (gv[sl] == o_wv).all()
     for col, op in enumerate(ops):
         mm = o_wv[:, col] == 1
-        if op == "mean":
+        if op in ("mean", "weighted-mean"):
             assert np.allclose(got[sl][mm, col], o_want[mm, col], rtol=1e-12, atol=0)
         else:
             assert (got[sl][mm, col] == o_want[mm, col]).all()
