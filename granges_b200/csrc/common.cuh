@@ -176,6 +176,14 @@ struct grb_index {
     u32 *rank_a;          // n + pad, start order: rank of the right's score among the valid scores, ordered by
                           // (score, position) -- all different; GRB_RANK_NONE when the score is None
     double *score_sorted; // n_valid: the scores in rank order
+    // MIN / MAX tables, built on first use by grb_index_prepare_minmax (ranks as in rank_a)
+    bool minmax_ready;
+    u32 *stab_min;        // 2n + 1: smallest rank among the rights with start < x < end, indexed by #{start < x} + #{end <= x}
+    int *stab_max;        // 2n + 1: largest such rank, -1 if none
+    u32 *sp_min;          // (sp_levels) x sp_nb: sparse table of the per-32-block rank minima in start order
+    int *sp_max;
+    u32 sp_nb;
+    int sp_levels;
     // overlap-bp tables, built on first use by grb_index_prepare_bp
     u64 *sum_starts;      // n + 1: sum of the i smallest starts
     u64 *sum_ends;        // n + 1: sum of the i smallest ends
@@ -201,6 +209,9 @@ struct SeqDev {
     const u32 *lut_a, *lut_b;
     const u32 *rank_a, *fb;
     const double *score_sorted;
+    const u32 *stab_min, *sp_min;
+    const int *stab_max, *sp_max;
+    u32 sp_nb;
     const u64 *sum_starts, *sum_ends, *sum_starts_v, *sum_ends_v;
     const i128 *wsum_a, *wsum_b;
     u64 left_begin, left_end;
@@ -305,6 +316,8 @@ int grb_scan_u32_to_u32(grb_ctx *ctx, const u32 *in, u32 *out, size_t n, bool wr
 
 // index.cu: build the member-sweep tables of an index (rank_a, score_sorted, fb) if they are not there yet.
 int grb_index_prepare_members(grb_ctx *ctx, grb_index *ix);
+// index.cu: the stabbing-minimum / -maximum tables and the block sparse tables that answer MIN / MAX without a sweep.
+int grb_index_prepare_minmax(grb_ctx *ctx, grb_index *ix);
 // index.cu: prefix sums of the sorted starts / ends (the closed form of OVERLAP_BP), built on first use.
 int grb_index_prepare_bp(grb_ctx *ctx, grb_index *ix);
 // index.cu: exact prefixes of score * coordinate (the closed form of WEIGHTED_MEAN); sets ix->wm_unavailable when the

@@ -412,6 +412,105 @@ __global__ void k_first_back(const u32 *__restrict__ starts, const u32 *__restri
     fb[b] = r;
 }
 
+// ---- MIN / MAX without a sweep ------------------------------------------------------------
+// A left's group is [pp, ub) in start order (range minimum: block sparse table) plus the rights that straddle
+// l.start (start < x < end, x = l.start).  As x grows the straddler set changes at "open" events (coordinate
+// start + 1) and "close" events (coordinate end); after all events with coordinate <= x there have been
+// pp(x) = #{start < x} opens and lb(x) = #{end <= x} closes, so the set -- hence its smallest / largest rank --
+// is a function of t = pp + lb alone.  Right r is in the set for t in [P_open + 1, P_close + 1) (P = 0-based
+// position of its event in the merged order, closes first at equal coordinates).  stab_min / stab_max are
+// filled by an offline range-chmin: each range drops its rank into two overlapping power-of-two cells of a
+// dual sparse table, which is then pushed down level by level.
+
+__global__ void k_block_rank_minmax(const u32 *__restrict__ rank_a, size_t n, u32 *__restrict__ bmin, int *__restrict__ bmax) {
+    const size_t b = ((size_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+    const size_t nb = (n + 31) >> 5;
+    if (b >= nb) return;
+    const size_t i = (b << 5) + lane_id();
+    const u32 r = i < n ? rank_a[i] : GRB_RANK_NONE;
+    const u32 mn = __reduce_min_sync(GRB_FULL, r);
+    const int mx = __reduce_max_sync(GRB_FULL, (int)r);
+    if (lane_id() == 0) {
+        bmin[b] = mn;
+        bmax[b] = mx;
+    }
+}
+
+__global__ void k_sparse_level(const u32 *__restrict__ pmin, const int *__restrict__ pmax, u32 nb, u32 half, u32 *__restrict__ omin,
+                               int *__restrict__ omax) {
+    const u32 i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= nb) return;
+    const u32 j = i + half < nb ? i + half : i;
+    omin[i] = min(pmin[i], pmin[j]);
+    omax[i] = max(pmax[i], pmax[j]);
+}
+
+// per right (by end-order position j): its life [lo, hi) in event time, and the longest life
+__global__ void k_stab_ranges(const u32 *__restrict__ starts, const u32 *__restrict__ ends_sorted, const u32 *__restrict__ perm_e,
+                              u32 n, u32 *__restrict__ lo_out, u32 *__restrict__ hi_out, u32 *max_len) {
+    const u32 j = blockIdx.x * blockDim.x + threadIdx.x;
+    u32 len = 0;
+    if (j < n) {
+        const u32 i = perm_e[j];
+        const u32 oc = starts[i] + 1, cc = ends_sorted[j];
+        // P_open = i + #{end <= open coordinate};  P_close = j + #{start + 1 < close coordinate} = j + #{start < cc - 1}
+        u32 a = 0, b = n;
+        while (a < b) {
+            const u32 m = a + ((b - a) >> 1);
+            if (ends_sorted[m] <= oc)
+                a = m + 1;
+            else
+                b = m;
+        }
+        const u32 p_open = i + a;
+        a = 0, b = n;
+        while (a < b) {
+            const u32 m = a + ((b - a) >> 1);
+            if (starts[m] + 1 < cc)
+                a = m + 1;
+            else
+                b = m;
+        }
+        const u32 p_close = j + a;
+        const u32 lo = p_open + 1, hi = p_close + 1;
+        lo_out[j] = lo;
+        hi_out[j] = hi > lo ? hi : lo;
+        len = hi > lo ? hi - lo : 0;
+    }
+    len = warp_max(len);
+    if (lane_id() == 0 && len) atomicMax(max_len, len);
+}
+
+__global__ void k_stab_drop(const u32 *__restrict__ rank_a, const u32 *__restrict__ perm_e, const u32 *__restrict__ lo_in,
+                            const u32 *__restrict__ hi_in, u32 n, size_t T, u32 *__restrict__ tmin, int *__restrict__ tmax) {
+    const u32 j = blockIdx.x * blockDim.x + threadIdx.x;
+    if (j >= n) return;
+    const u32 r = rank_a[perm_e[j]];
+    const u32 lo = lo_in[j], hi = hi_in[j];
+    if (r == GRB_RANK_NONE || hi <= lo) return;
+    const int k = 31 - __clz(hi - lo);
+    const size_t base = (size_t)k * T;
+    atomicMin(&tmin[base + lo], r);
+    atomicMin(&tmin[base + hi - (1u << k)], r);
+    atomicMax(&tmax[base + lo], (int)r);
+    atomicMax(&tmax[base + hi - (1u << k)], (int)r);
+}
+
+// level k -> level k - 1: a cell [s, s + 2^k) is the union of [s, s + half) and [s + half, s + 2^k)
+__global__ void k_stab_push(const u32 *__restrict__ umin, const int *__restrict__ umax, size_t T, u32 half, u32 *__restrict__ dmin,
+                            int *__restrict__ dmax) {
+    const size_t t = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (t >= T) return;
+    u32 mn = min(dmin[t], umin[t]);
+    int mx = max(dmax[t], umax[t]);
+    if (t >= half) {
+        mn = min(mn, umin[t - half]);
+        mx = max(mx, umax[t - half]);
+    }
+    dmin[t] = mn;
+    dmax[t] = mx;
+}
+
 inline unsigned blocks_for(size_t n, int tpb) { return (unsigned)((n + tpb - 1) / tpb); }
 
 int dev_alloc(grb_ctx *ctx, void **p, size_t bytes) {
@@ -430,6 +529,13 @@ void free_scores(grb_index *ix) {
     grb_dev_free(ix->ctx, ix->base_b);
     grb_dev_free(ix->ctx, ix->rank_a);
     grb_dev_free(ix->ctx, ix->score_sorted);
+    grb_dev_free(ix->ctx, ix->stab_min);
+    grb_dev_free(ix->ctx, ix->stab_max);
+    grb_dev_free(ix->ctx, ix->sp_min);
+    grb_dev_free(ix->ctx, ix->sp_max);
+    ix->stab_min = ix->sp_min = nullptr;
+    ix->stab_max = ix->sp_max = nullptr;
+    ix->minmax_ready = false;
     grb_dev_free(ix->ctx, ix->wsum_a);
     grb_dev_free(ix->ctx, ix->wsum_b);
     grb_dev_free(ix->ctx, ix->sum_starts_v);
@@ -815,6 +921,65 @@ int grb_index_prepare_members(grb_ctx *ctx, grb_index *ix) {
         GRB_LAUNCHED(ctx);
     }
     ix->members_ready = true;
+    return GRB_OK;
+}
+
+int grb_index_prepare_minmax(grb_ctx *ctx, grb_index *ix) {
+    if (!ix || ix->minmax_ready || !ix->n || !ix->has_scores) return GRB_OK;
+    GRB_TRY(grb_index_prepare_members(ctx, ix));
+    const size_t n = ix->n;
+    // ---- range minimum / maximum over rank_a: per-32-block values and their sparse table
+    const u32 nb = (u32)((n + 31) >> 5);
+    int levels = 1;
+    while ((1u << levels) <= nb) levels++;
+    ix->sp_nb = nb;
+    ix->sp_levels = levels;
+    GRB_TRY(dev_alloc(ctx, (void **)&ix->sp_min, (size_t)levels * nb * 4));
+    GRB_TRY(dev_alloc(ctx, (void **)&ix->sp_max, (size_t)levels * nb * 4));
+    k_block_rank_minmax<<<blocks_for((size_t)nb * 32, 256), 256, 0, ctx->stream>>>(ix->rank_a, n, ix->sp_min, ix->sp_max);
+    GRB_LAUNCHED(ctx);
+    for (int k = 1; k < levels; k++) {
+        k_sparse_level<<<blocks_for(nb, 256), 256, 0, ctx->stream>>>(ix->sp_min + (size_t)(k - 1) * nb, ix->sp_max + (size_t)(k - 1) * nb, nb,
+                                                                    1u << (k - 1), ix->sp_min + (size_t)k * nb, ix->sp_max + (size_t)k * nb);
+        GRB_LAUNCHED(ctx);
+    }
+    // ---- stabbing minimum / maximum over event time t in [0, 2n]
+    const size_t T = 2 * n + 1;
+    TempBuf lo, hi, mx;
+    GRB_TRY(lo.alloc(ctx, n * 4));
+    GRB_TRY(hi.alloc(ctx, n * 4));
+    GRB_TRY(mx.alloc(ctx, 4));
+    GRB_CUDA(ctx, cudaMemsetAsync(mx.p, 0, 4, ctx->stream));
+    k_stab_ranges<<<blocks_for(n, 256), 256, 0, ctx->stream>>>(ix->starts, ix->ends_sorted, ix->perm_e, (u32)n, lo.as<u32>(), hi.as<u32>(),
+                                                              mx.as<u32>());
+    GRB_LAUNCHED(ctx);
+    u32 max_len = 0;
+    GRB_CUDA(ctx, cudaMemcpyAsync(&max_len, mx.p, 4, cudaMemcpyDeviceToHost, ctx->stream));
+    GRB_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+    int K = 0;
+    while ((2u << K) <= max_len && K < 31) K++;  // floor(log2(max_len)), 0 when no right straddles anything
+    GRB_TRY(dev_alloc(ctx, (void **)&ix->stab_min, T * 4));
+    GRB_TRY(dev_alloc(ctx, (void **)&ix->stab_max, T * 4));
+    {
+        // levels 1..K are scratch; level 0 is the table itself
+        TempBuf tmin, tmax;
+        GRB_TRY(tmin.alloc(ctx, (size_t)(K + 1) * T * 4));
+        GRB_TRY(tmax.alloc(ctx, (size_t)(K + 1) * T * 4));
+        GRB_CUDA(ctx, cudaMemsetAsync(tmin.p, 0xff, (size_t)(K + 1) * T * 4, ctx->stream));  // GRB_RANK_NONE
+        GRB_CUDA(ctx, cudaMemsetAsync(tmax.p, 0xff, (size_t)(K + 1) * T * 4, ctx->stream));  // -1
+        k_stab_drop<<<blocks_for(n, 256), 256, 0, ctx->stream>>>(ix->rank_a, ix->perm_e, lo.as<u32>(), hi.as<u32>(), (u32)n, T, tmin.as<u32>(),
+                                                                tmax.as<int>());
+        GRB_LAUNCHED(ctx);
+        for (int k = K; k >= 1; k--) {
+            k_stab_push<<<blocks_for(T, 256), 256, 0, ctx->stream>>>(tmin.as<u32>() + (size_t)k * T, tmax.as<int>() + (size_t)k * T, T, 1u << (k - 1),
+                                                                    tmin.as<u32>() + (size_t)(k - 1) * T, tmax.as<int>() + (size_t)(k - 1) * T);
+            GRB_LAUNCHED(ctx);
+        }
+        GRB_CUDA(ctx, cudaMemcpyAsync(ix->stab_min, tmin.p, T * 4, cudaMemcpyDeviceToDevice, ctx->stream));
+        GRB_CUDA(ctx, cudaMemcpyAsync(ix->stab_max, tmax.p, T * 4, cudaMemcpyDeviceToDevice, ctx->stream));
+        GRB_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+    }
+    ix->minmax_ready = true;
     return GRB_OK;
 }
 

@@ -630,6 +630,63 @@ __global__ void __launch_bounds__(256) k_overlap_bp(const SeqDev *__restrict__ s
         }
 }
 
+// MIN / MAX without a sweep (index.cu: grb_index_prepare_minmax): the straddlers of l.start from the stabbing tables at
+// t = pp + lb, the members that start inside the left from the block sparse table over [pp, ub) -- at most 62 ranks are
+// read one by one (the partial blocks at both ends), everything in between is two table cells.
+__global__ void __launch_bounds__(256) k_minmax(const SeqDev *__restrict__ seqs, int nseq, u64 first, u64 total,
+                                                const u32 *__restrict__ ubv, const u32 *__restrict__ ppv, const u32 *__restrict__ lbv,
+                                                double *__restrict__ out, u8 *__restrict__ out_valid, int k, u32 min_cols, u32 max_cols) {
+    const u64 g = first + (u64)blockIdx.x * blockDim.x + threadIdx.x;
+    if (g >= total) return;
+    const SeqDev *__restrict__ sd = &seqs[find_seq_by_left(seqs, nseq, g)];
+    u32 mn = GRB_RANK_NONE;
+    int mx = -1;
+    if (sd->n && sd->has_scores) {
+        const u32 u = ubv[g], p = ppv[g], l = lbv[g];
+        const u32 t = p + l;
+        mn = sd->stab_min[t];
+        mx = sd->stab_max[t];
+        if (u > p) {
+            const u32 *__restrict__ rk = sd->rank_a;
+            const u32 fa = p >> 5, la = (u - 1) >> 5;
+            if (la - fa <= 1) {
+                for (u32 j = p; j < u; j++) {
+                    const u32 r = rk[j];
+                    mn = min(mn, r);
+                    mx = max(mx, (int)r);
+                }
+            } else {
+                for (u32 j = p; j < ((fa + 1) << 5); j++) {
+                    const u32 r = rk[j];
+                    mn = min(mn, r);
+                    mx = max(mx, (int)r);
+                }
+                for (u32 j = la << 5; j < u; j++) {
+                    const u32 r = rk[j];
+                    mn = min(mn, r);
+                    mx = max(mx, (int)r);
+                }
+                const u32 b0 = fa + 1, b1 = la;  // whole blocks [b0, b1)
+                const int kk = 31 - __clz(b1 - b0);
+                const size_t base = (size_t)kk * sd->sp_nb;
+                mn = min(mn, min(sd->sp_min[base + b0], sd->sp_min[base + b1 - (1u << kk)]));
+                mx = max(mx, max(sd->sp_max[base + b0], sd->sp_max[base + b1 - (1u << kk)]));
+            }
+        }
+    }
+    const double vmin = mn != GRB_RANK_NONE ? sd->score_sorted[mn] : 0.0;
+    const double vmax = mx >= 0 ? sd->score_sorted[mx] : 0.0;
+    for (int c = 0; c < k; c++) {
+        if ((min_cols >> c) & 1u) {
+            out[g * (u64)k + c] = vmin;
+            out_valid[g * (u64)k + c] = mn != GRB_RANK_NONE;
+        } else if ((max_cols >> c) & 1u) {
+            out[g * (u64)k + c] = vmax;
+            out_valid[g * (u64)k + c] = mx >= 0;
+        }
+    }
+}
+
 // exact 128-bit prefix of the scores at position j (start order: pfx_a / base_a, end order: pfx_b / base_b)
 __device__ __forceinline__ i128 exact_prefix(const u64 *__restrict__ pfx, const i128 *__restrict__ base, int mode, u32 j) {
     if (mode == GRB_SUM_WIDE) return base[j];
@@ -738,6 +795,11 @@ int make_batch(grb_ctx *ctx, const grb_index *const *idx, const u64 *left_offset
             d.rank_a = ix->rank_a;
             d.score_sorted = ix->score_sorted;
             d.fb = ix->fb;
+            d.stab_min = ix->stab_min;
+            d.stab_max = ix->stab_max;
+            d.sp_min = ix->sp_min;
+            d.sp_max = ix->sp_max;
+            d.sp_nb = ix->sp_nb;
             d.sum_starts = ix->sum_starts;
             d.sum_ends = ix->sum_ends;
             d.sum_starts_v = ix->sum_starts_v;
@@ -1173,6 +1235,21 @@ static int map_joins_impl(grb_ctx *ctx, const grb_index *const *idx, const uint6
         const grb_index *ix = idx ? idx[s] : nullptr;
         if (ix && ix->n && !ix->members_ready) GRB_TRY(grb_index_prepare_members(ctx, const_cast<grb_index *>(ix)));
     }
+    // MIN / MAX without a median beside them need no sweep at all: stabbing tables + range minimum (k_minmax)
+    u32 min_cols = 0, max_cols = 0;
+    {
+        const char *mm = getenv("GRB_MINMAX_MODE");  // debug: 0 = sweep the members for MIN / MAX too
+        if (rank_sweep && !want_median && ctx->sweep_mode == 1 && !(mm && atoi(mm) == 0)) {
+            for (int c = 0; c < k; c++) {
+                if (ops[c] == GRB_OP_MIN) min_cols |= 1u << c;
+                if (ops[c] == GRB_OP_MAX) max_cols |= 1u << c;
+            }
+            for (int s = 0; s < nseq; s++) {
+                const grb_index *ix = idx ? idx[s] : nullptr;
+                if (ix && ix->n && !ix->minmax_ready) GRB_TRY(grb_index_prepare_minmax(ctx, const_cast<grb_index *>(ix)));
+            }
+        }
+    }
     Batch b;
     GRB_TRY(make_batch(ctx, idx, left_offsets, nseq, &b));
     if (b.total == 0 || b.ntiles == 0) return GRB_OK;  // (a batch that starts past 0 may hold no lefts at all)
@@ -1217,7 +1294,11 @@ static int map_joins_impl(grb_ctx *ctx, const grb_index *const *idx, const uint6
                                                                                       o.ub, o.pp, o.lb, o.out, o.out_valid, k, wm_cols);
             GRB_LAUNCHED(ctx);
         }
-        if (need_members) {
+        if (min_cols | max_cols) {
+            k_minmax<<<(unsigned)((b.total - left_offsets[0] + 255) / 256), 256, 0, ctx->stream>>>(b.seqs, b.nseq, left_offsets[0], b.total, o.ub, o.pp,
+                                                                                                 o.lb, o.out, o.out_valid, k, min_cols, max_cols);
+            GRB_LAUNCHED(ctx);
+        } else if (need_members) {
             SweepOut so;
             memset(&so, 0, sizeof(so));
             so.out = o.out;

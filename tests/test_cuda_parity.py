@@ -704,3 +704,57 @@ def test_map_whole_equals_two_calls(eng, orc, ops):
             assert np.allclose(got[sl][mm, col], o_want[mm, col], rtol=1e-12, atol=0)
         else:
             assert (got[sl][mm, col] == o_want[mm, col]).all()
+
+
+@pytest.mark.parametrize("name", list(RANK_SWEEP_CASES))
+def test_minmax_without_a_sweep(orc, monkeypatch, name):
+    """MIN / MAX with no median beside them come from the stabbing tables + block sparse table (k_minmax): the same
+    bits as the member sweep (GRB_MINMAX_MODE=0) and the oracle -- long rights, dense groups spanning many blocks,
+    None scores, ties, unsorted lefts, length-1 rights."""
+    import granges_b200 as gb
+
+    kw = dict(RANK_SWEEP_CASES[name])
+    nl, nr = kw.pop("nl"), kw.pop("nr")
+    c = random_case(5151 + nr, nl, nr, **kw)
+    # sprinkle length-1 rights (their open and close events share a coordinate) and exact book-ends
+    c["re"][::17] = c["rs"][::17] + 1
+    ops = ["max", "mean", "min", "count"]
+    res = {}
+    for mode in ("1", "0"):
+        monkeypatch.setenv("GRB_MINMAX_MODE", mode)
+        ctx = gb.Context(0)
+        ix = ctx.index_build(c["rs"], c["re"]).set_scores(c["scores"], c["valid"])
+        n0 = ctx.launch_count
+        res[mode] = ctx.map_joins(ix, c["ls"], c["le"], ops)
+        res[mode + "b"] = ctx.map_joins(ix, c["ls"], c["le"], ["min"])  # tables are reused
+    t = orc.Tree(c["rs"], c["re"])
+    want, wv = orc.map_joins(t, c["scores"], c["valid"], c["ls"], c["le"], ops)
+    abs_sums = orc.map_joins(t, np.abs(c["scores"]), c["valid"], c["ls"], c["le"], ["sum"])[0][:, 0]
+    for mode in ("1", "0"):
+        out, ov = res[mode]
+        assert_map_equal(out, ov, want, wv, ops, abs_sums)
+        ob, vb = res[mode + "b"]
+        assert (vb[:, 0] == wv[:, 2]).all()
+        m = wv[:, 2] == 1
+        assert (ob[m, 0] == want[m, 2]).all()
+
+
+def test_minmax_batch_with_absent_seqnames(eng, orc):
+    cases = [random_case(950 + i, nl, nr, span=50000, maxlen=800, sorted_left=True, null_frac=nf)
+             for i, (nl, nr, nf) in enumerate([(3000, 4000, 0.0), (1500, 0, 0.0), (0, 500, 0.0), (2100, 2600, 0.3), (700, 900, 0.0)])]
+    ops = ["max", "min"]
+    idxs = [None if i == 1 else eng.build(c["rs"], c["re"], None, c["scores"], c["valid"]) for i, c in enumerate(cases)]
+    off = np.concatenate([[0], np.cumsum([len(c["ls"]) for c in cases])]).astype(np.uint64)
+    ls = np.concatenate([c["ls"] for c in cases])
+    le = np.concatenate([c["le"] for c in cases])
+    out, ov = eng.ctx.map_joins_batch(idxs, off, ls, le, ops)
+    for i, c in enumerate(cases):
+        sl = slice(int(off[i]), int(off[i + 1]))
+        if i == 1:
+            assert (ov[sl] == 0).all()
+            continue
+        t = orc.Tree(c["rs"], c["re"])
+        want, wv = orc.map_joins(t, c["scores"], c["valid"], c["ls"], c["le"], ops)
+        assert (ov[sl] == wv).all()
+        m = wv == 1
+        assert (out[sl][m] == want[m]).all()
