@@ -21,5 +21,8 @@ done
 unset GRANGES_THREADS
 tm "granges filter" $G filter -g $D/hg38.tsv -l $D/left.bed -r $D/right.bed -o $D/filt.tsv
 tm "granges windows 1kb/500bp" $G windows -g $D/hg38.tsv -w 1000 -s 500 -o $D/win.bed
-wc -l $D/out.tsv $D/filt.tsv $D/win.bed; head -2 $D/out.tsv
+tm "granges merge (BED5, --func mean, $N sorted rows)" $G merge -b $D/right.bed -f mean -o $D/merged.bed
+awk 'BEGIN{OFS="\t"} NR<=2000000{print $1,$2,$3,"f" (NR%5)}' $D/right.bed > $D/feat.bed
+tm "granges feature-density (2M BED4 rows, 5 features, 100 kb windows)" $G feature-density -g $D/hg38.tsv -b $D/feat.bed -w 100000 -l -o $D/fd.tsv
+wc -l $D/out.tsv $D/filt.tsv $D/win.bed $D/merged.bed $D/fd.tsv; head -2 $D/out.tsv; head -2 $D/merged.bed; head -2 $D/fd.tsv
 rm -rf $D

@@ -8,4 +8,6 @@ ncu --metrics gpu__time_duration.sum --clock-control none -c 2000 --csv --log-fi
 ncu --metrics gpu__time_duration.sum --clock-control none -c 2000 --csv --log-file gpurun_out/launches_c3_r1s3.csv python tools/bench_configs.py c3 > gpurun_out/ncu_lc3_r1s3.log 2>&1
 ncu --set full --clock-control none --import-source on -k regex:k_map_pipe -c 1 -o gpurun_out/prof_pipe_r1s3 -f python bench.py --steps 1 --warmup 3 --no-cpu --no-e2e > gpurun_out/ncu_p_r1s3.log 2>&1
 ncu --set full --clock-control none --import-source on -k regex:k_sweep3 -c 1 -o gpurun_out/prof_sweep3_r1s3 -f python tools/bench_configs.py c3 > gpurun_out/ncu_s3_r1s3.log 2>&1
+bash tools/bench_cli.sh 20000000 > gpurun_out/cli_r1s3.txt 2>&1; tail -25 gpurun_out/cli_r1s3.txt
+python tools/e2e_phases.py > gpurun_out/e2e_phases_r1s3.txt 2>&1
 ls -la gpurun_out/*.ncu-rep | tail -3
