@@ -9,7 +9,7 @@ import ctypes as C
 import os
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "libgranges_b200.so")
+LIB_PATH = os.environ.get("GRB_LIB_PATH") or os.path.join(_HERE, "libgranges_b200.so")  # the override is for A/B builds of the same ABI
 
 u32p = C.POINTER(C.c_uint32)
 u64p = C.POINTER(C.c_uint64)

@@ -305,7 +305,7 @@ __device__ __forceinline__ void sweep3_run(const SeqDev *__restrict__ sd, u64 c_
 }
 
 // One CTA per tile of 1024 lefts (the tiling of k_tile).
-__global__ void __launch_bounds__(SW3_TPB, 3) k_sweep3(const SeqDev *__restrict__ seqs, const u32 *__restrict__ tile_begin, int nseq,
+__global__ void __launch_bounds__(SW3_TPB, 4) k_sweep3(const SeqDev *__restrict__ seqs, const u32 *__restrict__ tile_begin, int nseq,
                                                     const u32 *__restrict__ ls, const u32 *__restrict__ ubv,
                                                     const u32 *__restrict__ ppv, const u32 *__restrict__ lbv, const SweepOut o,
                                                     int stage_mode) {
