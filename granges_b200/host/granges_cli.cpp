@@ -531,9 +531,9 @@ struct Records {
     int ncols = 0;  // of the first record: 3, 4 or 5 (src/io/parsers/detect.rs:39-53 tries BED5, BED4, BED3)
 };
 
-Records parse_records(const Mapped &f, int want_cols /* 0 = detect */) {
+// one chunk of the file (cut at line boundaries); ncols = 0: take it from the first record
+Records parse_records_chunk(const char *p, const char *end, int want_cols /* 0 = detect */) {
     Records r;
-    const char *p = f.p, *end = f.p + f.n;
     while (p < end) {
         const char *line = p;
         const char *nl = (const char *)memchr(p, '\n', end - p);
@@ -597,6 +597,65 @@ Records parse_records(const Mapped &f, int want_cols /* 0 = detect */) {
     return r;
 }
 
+// The file is cut into chunks at line boundaries, the chunks are parsed on all host threads and stitched back in file
+// order; the column count is that of the first record (src/io/parsers/detect.rs:39-53).
+Records parse_records(const Mapped &f, int want_cols /* 0 = detect */) {
+    const char *p = f.p, *end = f.p + f.n;
+    if (want_cols == 0) {
+        // detect on the first record alone
+        const char *q = p;
+        while (q < end) {
+            const char *nl = (const char *)memchr(q, '\n', end - q);
+            const char *le = nl ? nl : end;
+            if (le > q && *q != '#' && !(le - q == 1 && *q == '\r')) {
+                Records one = parse_records_chunk(q, le, 0);
+                want_cols = one.ncols;
+                break;
+            }
+            q = le + 1;
+        }
+        if (want_cols == 0) return Records();
+    }
+    const int nchunks = f.n < (1u << 20) ? 1 : n_threads() * 4;
+    std::vector<const char *> cut((size_t)nchunks + 1);
+    cut[0] = p;
+    cut[nchunks] = end;
+    for (int c = 1; c < nchunks; c++) {
+        const char *q = p + f.n / nchunks * c;
+        const char *nl = (const char *)memchr(q, '\n', end - q);
+        cut[c] = nl ? nl + 1 : end;
+        if (cut[c] < cut[c - 1]) cut[c] = cut[c - 1];
+    }
+    std::vector<Records> part((size_t)nchunks);
+    parallel_for(nchunks, [&](int c) { part[c] = parse_records_chunk(cut[c], cut[c + 1], want_cols); });
+    if (nchunks == 1) {
+        part[0].ncols = want_cols;
+        return std::move(part[0]);
+    }
+    Records r;
+    r.ncols = want_cols;
+    size_t total = 0;
+    for (auto &q : part) total += q.starts.size();
+    r.seqname.reserve(total);
+    r.starts.reserve(total);
+    r.ends.reserve(total);
+    if (want_cols >= 4) r.name.reserve(total);
+    if (want_cols >= 5) {
+        r.score.reserve(total);
+        r.valid.reserve(total);
+    }
+    for (auto &q : part) {
+        r.seqname.insert(r.seqname.end(), q.seqname.begin(), q.seqname.end());
+        r.name.insert(r.name.end(), q.name.begin(), q.name.end());
+        r.starts.insert(r.starts.end(), q.starts.begin(), q.starts.end());
+        r.ends.insert(r.ends.end(), q.ends.begin(), q.ends.end());
+        r.score.insert(r.score.end(), q.score.begin(), q.score.end());
+        r.valid.insert(r.valid.end(), q.valid.begin(), q.valid.end());
+        q = Records();
+    }
+    return r;
+}
+
 // maximal stretches of consecutive records with the same seqname
 std::vector<uint64_t> seqname_runs(const std::vector<std::string_view> &seqname) {
     std::vector<uint64_t> ro{0};
@@ -610,11 +669,14 @@ std::vector<uint64_t> seqname_runs(const std::vector<std::string_view> &seqname)
 // BED5 -> FloatOperation over the merged records' scores.
 int cmd_merge(const std::string &bedfile, long long distance, const std::vector<int> &ops, const Args &a) {
     Mapped f(bedfile);
+    grb_ctx *ctx = nullptr;
+    int ctx_rc = GRB_OK;
+    std::thread init([&] { ctx_rc = grb_ctx_create(0, &ctx); });  // CUDA start-up runs beside the parsing
     Records r = parse_records(f, 0);
+    init.join();
     if (r.starts.empty()) die("File '" + bedfile + "' is empty.");
     if (r.ncols == 5 && ops.size() != 1) die("BED5 input needs exactly one --func (the reference unwraps it: src/commands.rs:656)");
-    grb_ctx *ctx = nullptr;
-    check(nullptr, grb_ctx_create(0, &ctx));
+    check(nullptr, ctx_rc);
     std::vector<uint64_t> ro = seqname_runs(r.seqname);
     grb_merged *mg = nullptr;
     check(ctx, grb_merge_ranges(ctx, r.starts.data(), r.ends.data(), ro.data(), (int)ro.size() - 1, distance, &mg));
@@ -677,12 +739,15 @@ int cmd_feature_density(const std::string &bedfile, bool headers, const Args &a)
     if (!a.has_width) die("the following required arguments were not provided: --width <WIDTH>");
     Genome g = read_genome(a.genome);
     Mapped f(bedfile);
+    grb_ctx *ctx = nullptr;
+    int ctx_rc = GRB_OK;
+    std::thread init([&] { ctx_rc = grb_ctx_create(0, &ctx); });  // CUDA start-up runs beside the parsing
     Records r = parse_records(f, 4);
     const int nseq = (int)g.names.size();
     std::map<std::string_view, std::vector<uint32_t>> by_feature;  // feature -> record positions, file order
     for (size_t i = 0; i < r.name.size(); i++) by_feature[r.name[i]].push_back((uint32_t)i);
-    grb_ctx *ctx = nullptr;
-    check(nullptr, grb_ctx_create(0, &ctx));
+    init.join();
+    check(nullptr, ctx_rc);
     grb_ranges *w = nullptr;
     check(ctx, grb_windows(ctx, g.lens.data(), nseq, a.width, a.step, a.chop ? 1 : 0, &w));
     const size_t nw = grb_ranges_len(w);
