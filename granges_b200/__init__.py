@@ -6,6 +6,8 @@ is its Python face.  Importing it requires the built library -- there is no CPU 
 from . import _capi
 from .api import OPS, Context, GRangesError, Index, PreparedMap, Windows, shard_plan
 
+from . import granges  # noqa: E402  (the reference's container names over the C ABI)
+
 _capi.lib()  # fail loudly at import time if the CUDA library is missing
 
 __all__ = ["Context", "Index", "Windows", "PreparedMap", "GRangesError", "OPS", "shard_plan"]
