@@ -1328,8 +1328,12 @@ static int map_joins_impl(grb_ctx *ctx, const grb_index *const *idx, const uint6
             }
             GRB_LAUNCHED(ctx);
             if (want_median) {
-                k_median_heavy<<<ctx->sm_count * 4, SW_TPB, 0, ctx->stream>>>(b.seqs, b.nseq, dls.as<u32>(), o.ub, o.lb, so.heavy_list,
-                                                                              so.heavy_count, so);
+                if (rank_sweep)
+                    k_median_heavy3<<<ctx->sm_count * 6, MH3_TPB, 0, ctx->stream>>>(b.seqs, b.nseq, dls.as<u32>(), o.ub, o.pp, o.lb,
+                                                                                    so.heavy_list, so.heavy_count, so);
+                else
+                    k_median_heavy<<<ctx->sm_count * 4, SW_TPB, 0, ctx->stream>>>(b.seqs, b.nseq, dls.as<u32>(), o.ub, o.lb, so.heavy_list,
+                                                                                  so.heavy_count, so);
                 GRB_LAUNCHED(ctx);
             }
         }

@@ -419,3 +419,154 @@ __global__ void __launch_bounds__(SW3_TPB, 4) k_sweep3(const SeqDev *__restrict_
         c_lo = c_hi;
     }
 }
+
+
+// Median of the groups too large for the in-group networks of k_sweep3 (more than 16 ranks per lane): one CTA per such
+// left.  The straddlers' positions are found once (backward walk with block-max-end skipping) and kept in shared
+// memory; then an MSB-first radix select over the 32-bit ranks, 10 bits per pass, reads the members -- the run
+// [pp, ub) and the cached straddlers -- once per pass, and one more pass finds the upper middle of an even group.
+// (k_median_heavy, the score-based version, needs 8 passes per middle element and re-walks the candidates each time.)
+constexpr int MH3_TPB = 256;
+constexpr u32 MH3_STRAD = 6144;  // straddler positions kept in shared memory; beyond that the walk is repeated per pass
+constexpr u32 MH3_BINS = 1024;
+
+template <typename F>
+__device__ __forceinline__ void mh3_for_straddlers(const u32 *__restrict__ ends, const u32 *__restrict__ bme, u32 p, u32 need, u32 lstart,
+                                                   F &&visit) {
+    // CTA-wide backward walk: 256 positions per step, whole 64-blocks skipped through their block-max-end
+    u32 found = 0;
+    long long top = p;  // positions [top - 256, top) are examined next
+    while (found < need && top > 0) {
+        const long long j = top - 1 - threadIdx.x;
+        bool hit = false;
+        if (j >= 0 && bme[j >> GRB_BME_SHIFT] > lstart) hit = ends[j] > lstart;
+        if (hit) visit((u32)j);
+        found += __syncthreads_count(hit);
+        top -= MH3_TPB;
+    }
+}
+
+__global__ void __launch_bounds__(MH3_TPB) k_median_heavy3(const SeqDev *__restrict__ seqs, int nseq, const u32 *__restrict__ ls,
+                                                           const u32 *__restrict__ ubv, const u32 *__restrict__ ppv,
+                                                           const u32 *__restrict__ lbv, const u32 *__restrict__ heavy_list,
+                                                           const u32 *__restrict__ heavy_count, const SweepOut o) {
+    __shared__ u32 s_strad[MH3_STRAD];
+    __shared__ u32 hist[MH3_BINS];
+    __shared__ u32 s_n, s_prefix, s_k, s_total, s_red[MH3_TPB / 32];
+    const u32 nheavy = *heavy_count;
+    const u32 tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    for (u32 h = blockIdx.x; h < nheavy; h += gridDim.x) {
+        const u64 g = heavy_list[h];
+        const SeqDev *__restrict__ sd = &seqs[find_seq_by_left(seqs, nseq, g)];
+        const u32 u = ubv[g], p = ppv[g], l = lbv[g], lstart = ls[g];
+        const u32 need = p - l;
+        const u32 *__restrict__ ends = sd->ends;
+        const u32 *__restrict__ bme = sd->bme;
+        const u32 *__restrict__ rank = sd->rank_a;
+        if (tid == 0) s_n = 0;
+        __syncthreads();
+        // ---- the straddlers, once
+        mh3_for_straddlers(ends, bme, p, need, lstart, [&](u32 j) {
+            const u32 slot = atomicAdd(&s_n, 1u);
+            if (slot < MH3_STRAD) s_strad[slot] = j;
+        });
+        __syncthreads();
+        const bool cached = s_n <= MH3_STRAD;
+        const u32 nstrad = cached ? s_n : 0;
+        // visit every member's rank: [p, u) and the straddlers (from the cache, or by walking again)
+        auto for_members = [&](auto &&f) {
+            for (u32 j = p + tid; j < u; j += MH3_TPB) f(rank[j]);
+            if (cached) {
+                for (u32 q = tid; q < nstrad; q += MH3_TPB) f(rank[s_strad[q]]);
+            } else {
+                mh3_for_straddlers(ends, bme, p, need, lstart, [&](u32 j) { f(rank[j]); });
+            }
+        };
+        // ---- radix select, most significant digit first
+        int bits = 1;
+        while (bits < 32 && (sd->n >> bits)) bits++;  // ranks are below n
+        const int passes = (bits + 9) / 10;
+        if (tid == 0) {
+            s_prefix = 0;
+            s_k = 0;
+        }
+        u32 m = 0;  // members that carry a score
+        for (int pass = 0; pass < passes; pass++) {
+            const int shift = 10 * (passes - 1 - pass);
+            for (u32 i = tid; i < MH3_BINS; i += MH3_TPB) hist[i] = 0;
+            __syncthreads();
+            const u32 prefix = s_prefix;
+            for_members([&](u32 r) {
+                if (r == GRB_RANK_NONE) return;
+                if (pass == 0 || (r >> (shift + 10)) == (prefix >> (shift + 10))) atomicAdd(&hist[(r >> shift) & (MH3_BINS - 1)], 1u);
+            });
+            __syncthreads();
+            // one warp finds the digit: 32 bins per lane, then a scan of the lane totals
+            if (warp == 0) {
+                u32 mine = 0;
+                for (u32 i = 0; i < 32; i++) mine += hist[lane * 32 + i];
+                u32 incl = mine;
+#pragma unroll
+                for (int d = 1; d < 32; d <<= 1) {
+                    const u32 t = __shfl_up_sync(GRB_FULL, incl, d);
+                    if (lane >= (u32)d) incl += t;
+                }
+                const u32 total = __shfl_sync(GRB_FULL, incl, 31);
+                if (pass == 0) {
+                    if (lane == 0) {
+                        s_total = total;
+                        s_k = total ? (total - 1) >> 1 : 0;  // lower middle
+                    }
+                }
+                __syncwarp();
+                const u32 kk = pass == 0 ? (total ? (total - 1) >> 1 : 0) : s_k;
+                const u32 excl = incl - mine;
+                const bool here = total && kk >= excl && kk < incl;
+                if (here) {
+                    u32 c = excl;
+                    u32 digit = lane * 32;
+                    for (u32 i = 0; i < 32; i++) {
+                        const u32 hv = hist[lane * 32 + i];
+                        if (kk < c + hv) {
+                            digit = lane * 32 + i;
+                            break;
+                        }
+                        c += hv;
+                    }
+                    s_k = kk - c;
+                    s_prefix = prefix | (digit << shift);
+                }
+            }
+            __syncthreads();
+            if (pass == 0) m = s_total;
+        }
+        const u32 med_lo = s_prefix;
+        u32 med_hi = med_lo;
+        if (m && !(m & 1)) {
+            // even: the upper middle is the smallest rank above the lower middle
+            u32 best = GRB_RANK_NONE;
+            for_members([&](u32 r) {
+                if (r != GRB_RANK_NONE && r > med_lo) best = min(best, r);
+            });
+            best = warp_min(best);
+            if (lane == 0) s_red[warp] = best;
+            __syncthreads();
+            best = GRB_RANK_NONE;
+            for (int w = 0; w < MH3_TPB / 32; w++) best = min(best, s_red[w]);
+            med_hi = best;
+        }
+        if (tid == 0) {
+            double r = 0.0;
+            if (m) {
+                const double a = sd->score_sorted[med_lo];
+                r = med_hi != med_lo ? (a + sd->score_sorted[med_hi]) / 2.0 : a;
+            }
+            for (int c = 0; c < o.k; c++) {
+                if (o.ops[c] != GRB_OP_MEDIAN) continue;
+                o.out[g * (u64)o.k + c] = r;
+                o.out_valid[g * (u64)o.k + c] = m ? 1 : 0;
+            }
+        }
+        __syncthreads();
+    }
+}

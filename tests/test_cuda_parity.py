@@ -545,6 +545,7 @@ RANK_SWEEP_CASES = {
     "mid-dense": dict(nl=4000, nr=12000, span=60000, maxlen=500, sorted_left=True),
     "dense": dict(nl=2500, nr=40000, span=20000, maxlen=400, sorted_left=True),
     "very-dense": dict(nl=1200, nr=60000, span=6000, maxlen=900, sorted_left=True, null_frac=0.1),
+    "ultra-dense": dict(nl=300, nr=100000, span=4000, maxlen=1500, sorted_left=True, null_frac=0.05, score_kind="int"),
     "mixed-sign": dict(nl=3000, nr=3000, span=30000, maxlen=700, sorted_left=True, score_kind="mixed"),
 }
 

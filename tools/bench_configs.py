@@ -166,6 +166,45 @@ def c4(scale):
            pairs=pairs, max_group=int(cnt.max().item()), pairs_per_s=pairs / ms * 1e3, index_build_ms=tb * 1e3)
 
 
+def c4ops(scale):
+    """C4's right set (500M clustered BED5) under the member reductions: skewed groups (hundreds to tens of thousands of
+    members per window) through k_minmax, k_sweep3 with whole-warp groups and the radix-select path for the heaviest."""
+    nr = int(500_000_000 * scale)
+    nr_per = bench.split_counts(nr, 22)
+    idxs = []
+    for s in range(22):
+        rs, re, sc = clustered_rights(s, nr_per[s], 15)
+        idxs.append(ctx.index_build(rs, re).set_scores(sc))
+        del rs, re, sc
+    w = ctx.windows_dev(HG38, 1000, 500, False)
+    off = w.seq_offsets()
+    n = len(w)
+    ps, pe = w.dev_ptrs()
+    import ctypes as C
+
+    from granges_b200 import _capi
+
+    for ops_names in (["min", "max"], ["median"], ["overlap-bp"], ["weighted-mean"]):
+        k = len(ops_names)
+        out = torch.empty((n, k), dtype=torch.float64, device=dev)
+        ov = torch.empty((n, k), dtype=torch.uint8, device=dev)
+        ops = (C.c_int * k)(*[gb.OPS[o] for o in ops_names])
+        handles = (C.c_void_p * 22)(*[ix.h for ix in idxs])
+
+        def run():
+            rc = _capi.lib().grb_map_joins_f64_batch(ctx.h, handles, off.ctypes.data_as(_capi.u64p), 22, ps, pe, ops, k, out.data_ptr(),
+                                                     ov.data_ptr())
+            assert rc == 0, ctx._check(rc)
+
+        t0 = time.perf_counter()
+        run()
+        ctx.sync()
+        first = (time.perf_counter() - t0) * 1e3
+        ms, _ = timed(run, reps=2, warm=0)
+        report("C4 rights (%d clustered) x %d windows, %s" % (nr, n, ",".join(ops_names)), ms=ms, first_call_ms_incl_tables=first,
+               lefts_per_s=n / ms * 1e3, checksum=float(out[ov.bool()].sum().item()))
+
+
 def c5(scale):
     nl, nr = int(50_000_000 * scale), int(200_000_000 * scale)
     nl_per, nr_per = bench.split_counts(nl, 22), bench.split_counts(nr, 22)
@@ -270,4 +309,4 @@ if __name__ == "__main__":
     which = args or ["c1", "c2", "c3", "c4", "c5", "c6"]
     for w in which:
         torch.cuda.empty_cache()
-        {"c1": c1, "c2": lambda: c2(scale), "c3": lambda: c3(scale), "c4": lambda: c4(scale), "c5": lambda: c5(scale), "c3ops": lambda: c3ops(scale), "c6": lambda: c6(scale)}[w]()
+        {"c1": c1, "c2": lambda: c2(scale), "c3": lambda: c3(scale), "c4": lambda: c4(scale), "c5": lambda: c5(scale), "c3ops": lambda: c3ops(scale), "c6": lambda: c6(scale), "c4ops": lambda: c4ops(scale)}[w]()
