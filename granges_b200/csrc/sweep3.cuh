@@ -175,8 +175,12 @@ __device__ __forceinline__ void sweep3_run(const SeqDev *__restrict__ sd, u64 c_
         u32 nvalid = 0;
         u32 rmin = GRB_RANK_NONE;  // unsigned min ignores NONE
         int rmax = -1;             // signed max ignores NONE (ranks are below 2^31)
+        // A group that cannot fit the in-group median buffer (its size is known before any member is read) is left
+        // entirely to k_median_heavy3, a whole CTA per left: one warp walking thousands of members would hold up
+        // its CTA, and the ranks it collected would be thrown away.
+        const bool pre_heavy = want_median && u > l && u - l > CAP;
         // ---- members that start inside the left: [p, u), ascending
-        const u32 fw = u > p ? u - p : 0u;
+        const u32 fw = (u > p && !pre_heavy) ? u - p : 0u;
         const u32 fw_steps = __reduce_max_sync(FULL, (fw + G - 1) / G);
         for (u32 it = 0; it < fw_steps; it++) {
             const u32 j = p + it * G + glane;
@@ -198,7 +202,7 @@ __device__ __forceinline__ void sweep3_run(const SeqDev *__restrict__ sd, u64 c_
         }
         if (!has_nulls) nvalid = fw;
         // ---- straddlers: below p, end > l.start; exactly p - l of them
-        const u32 need = p - l;
+        const u32 need = pre_heavy ? 0u : p - l;
         u32 found = 0;
         int cb = p ? (int)((p - 1) & ~(u32)(G - 1)) : -1;
         while (true) {
@@ -232,10 +236,10 @@ __device__ __forceinline__ void sweep3_run(const SeqDev *__restrict__ sd, u64 c_
             rmax = max(rmax, __shfl_xor_sync(FULL, rmax, s));
         }
         // ---- median: sorting network over the (all different) ranks; its size is the warp's largest group
-        bool heavy = false;
+        bool heavy = pre_heavy;
         u32 med_lo = 0, med_hi = 0;
         if (want_median) {
-            heavy = nvalid > CAP;
+            heavy = pre_heavy || nvalid > CAP;  // (nvalid <= the group size, so the second test never adds anything)
             const u32 m = heavy ? 0u : nvalid;
             const u32 mx = __reduce_max_sync(FULL, m);
             __syncwarp();
@@ -264,11 +268,11 @@ __device__ __forceinline__ void sweep3_run(const SeqDev *__restrict__ sd, u64 c_
             u32 r1 = 0, r2 = 0;
             bool ok = false, mine = false;
             if (my_op == GRB_OP_MIN) {
-                mine = true;
+                mine = !heavy;
                 ok = rmin != GRB_RANK_NONE;
                 r1 = r2 = rmin;
             } else if (my_op == GRB_OP_MAX) {
-                mine = true;
+                mine = !heavy;
                 ok = rmax >= 0;
                 r1 = r2 = (u32)rmax;
             } else if (my_op == GRB_OP_MEDIAN) {
@@ -453,6 +457,7 @@ __global__ void __launch_bounds__(MH3_TPB) k_median_heavy3(const SeqDev *__restr
     __shared__ u32 s_strad[MH3_STRAD];
     __shared__ u32 hist[MH3_BINS];
     __shared__ u32 s_n, s_prefix, s_k, s_total, s_red[MH3_TPB / 32];
+    __shared__ int s_redmax[MH3_TPB / 32];
     const u32 nheavy = *heavy_count;
     const u32 tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     for (u32 h = blockIdx.x; h < nheavy; h += gridDim.x) {
@@ -491,6 +496,8 @@ __global__ void __launch_bounds__(MH3_TPB) k_median_heavy3(const SeqDev *__restr
             s_k = 0;
         }
         u32 m = 0;  // members that carry a score
+        u32 t_min = GRB_RANK_NONE;
+        int t_max = -1;
         for (int pass = 0; pass < passes; pass++) {
             const int shift = 10 * (passes - 1 - pass);
             for (u32 i = tid; i < MH3_BINS; i += MH3_TPB) hist[i] = 0;
@@ -498,6 +505,10 @@ __global__ void __launch_bounds__(MH3_TPB) k_median_heavy3(const SeqDev *__restr
             const u32 prefix = s_prefix;
             for_members([&](u32 r) {
                 if (r == GRB_RANK_NONE) return;
+                if (pass == 0) {
+                    t_min = min(t_min, r);
+                    t_max = max(t_max, (int)r);
+                }
                 if (pass == 0 || (r >> (shift + 10)) == (prefix >> (shift + 10))) atomicAdd(&hist[(r >> shift) & (MH3_BINS - 1)], 1u);
             });
             __syncthreads();
@@ -540,6 +551,22 @@ __global__ void __launch_bounds__(MH3_TPB) k_median_heavy3(const SeqDev *__restr
             __syncthreads();
             if (pass == 0) m = s_total;
         }
+        // smallest / largest rank of the group (k_sweep3 left this group's MIN / MAX columns to this kernel too)
+        t_min = warp_min(t_min);
+        t_max = __reduce_max_sync(GRB_FULL, t_max);
+        __syncthreads();
+        if (lane == 0) {
+            s_red[warp] = t_min;
+            s_redmax[warp] = t_max;
+        }
+        __syncthreads();
+        t_min = GRB_RANK_NONE;
+        t_max = -1;
+        for (int w = 0; w < MH3_TPB / 32; w++) {
+            t_min = min(t_min, s_red[w]);
+            t_max = max(t_max, s_redmax[w]);
+        }
+        __syncthreads();
         const u32 med_lo = s_prefix;
         u32 med_hi = med_lo;
         if (m && !(m & 1)) {
@@ -562,8 +589,16 @@ __global__ void __launch_bounds__(MH3_TPB) k_median_heavy3(const SeqDev *__restr
                 r = med_hi != med_lo ? (a + sd->score_sorted[med_hi]) / 2.0 : a;
             }
             for (int c = 0; c < o.k; c++) {
-                if (o.ops[c] != GRB_OP_MEDIAN) continue;
-                o.out[g * (u64)o.k + c] = r;
+                double v;
+                if (o.ops[c] == GRB_OP_MEDIAN)
+                    v = r;
+                else if (o.ops[c] == GRB_OP_MIN)
+                    v = m ? sd->score_sorted[t_min] : 0.0;
+                else if (o.ops[c] == GRB_OP_MAX)
+                    v = m ? sd->score_sorted[t_max] : 0.0;
+                else
+                    continue;
+                o.out[g * (u64)o.k + c] = v;
                 o.out_valid[g * (u64)o.k + c] = m ? 1 : 0;
             }
         }
