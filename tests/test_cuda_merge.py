@@ -114,3 +114,14 @@ def test_merge_large_property(eng):
     assert (ms == st[first[:-1]]).all()
     assert (np.maximum.reduceat(en, first[:-1].astype(np.int64)) == me).all()
     assert (out[:, 0] == np.diff(first.astype(np.int64))).all() and int(out[:, 0].sum()) == n
+
+
+def test_merge_at_the_coordinate_limits(eng, orc):
+    top = 2**31 - 1
+    s = np.array([0, 10, top - 50, top - 40, top - 5], np.uint32)
+    e = np.array([5, top - 45, top - 45, top - 10, top], np.uint32)
+    seq = np.zeros(5, np.uint32)
+    for d in (0, 5, 2**31, -1, -(2**31)):
+        want = orc.merge(seq, s, e, d)
+        rom, ms, me, first = eng.ctx.merge(s, e, None, d)
+        assert (ms == want[1]).all() and (me == want[2]).all() and (first[:-1] == want[3]).all(), d

@@ -759,3 +759,51 @@ def test_minmax_batch_with_absent_seqnames(eng, orc):
         assert (ov[sl] == wv).all()
         m = wv == 1
         assert (out[sl][m] == want[m]).all()
+
+
+def test_closed_forms_at_the_coordinate_limits(eng, orc):
+    """Coordinates up to 2^31 - 1 (the reference's i32 limit), lefts entirely before / after every right, single-range
+    inputs: MIN / MAX (k_minmax), MEDIAN, OVERLAP_BP, WEIGHTED_MEAN, SUM, COUNT against the oracle."""
+    top = 2**31 - 1
+    rs = np.array([0, 5, top - 900, top - 500, top - 2, 1_000_000_000, 1_000_000_000, 1_000_000_010], np.uint32)
+    re = np.array([top, 6, top - 100, top, top, 1_000_000_500, 1_000_000_001, top], np.uint32)
+    sc = np.array([0.5, -2.25, 3.0, 1e6, -1e-3, 7.0, 7.0, 0.125])
+    ls = np.array([0, 0, 6, top - 1, top - 600, 999_999_999, 1_000_000_000, 1_000_000_001, 2, top - 1000], np.uint32)
+    le = np.array([1, top, 7, top, top - 400, 1_000_000_001, 1_000_000_001, 1_000_000_002, 5, top], np.uint32)
+    ops = ["min", "max", "overlap-bp", "weighted-mean", "sum", "count"]
+    for valid in (None, np.array([1, 1, 0, 1, 1, 0, 1, 1], np.uint8)):
+        ix = eng.build(rs, re, None, sc, valid)
+        t = orc.Tree(rs, re)
+        want, wv = orc.map_joins(t, sc, valid, ls, le, ops)
+        out, ov = eng.map_joins(ix, ls, le, ops)
+        assert (ov == wv).all()
+        for col, op in enumerate(ops):
+            m = wv[:, col] == 1
+            if op in ("weighted-mean", "sum"):
+                assert np.allclose(out[m, col], want[m, col], rtol=1e-12, atol=0), op
+            else:
+                assert (out[m, col] == want[m, col]).all(), op
+        want, wv = orc.map_joins(t, sc, valid, ls, le, ["median", "min"])
+        out, ov = eng.map_joins(ix, ls, le, ["median", "min"])
+        assert (ov == wv).all() and (out[wv == 1] == want[wv == 1]).all()
+    # one right, lefts on every side of it
+    ix = eng.build([100], [200], None, [4.5], None)
+    out, ov = eng.map_joins(ix, [0, 100, 150, 199, 200, 50], [100, 101, 160, 300, 300, 250], ["min", "overlap-bp", "weighted-mean", "median"])
+    assert ov.tolist() == [[0, 1, 1, 0], [1, 1, 1, 1], [1, 1, 1, 1], [1, 1, 1, 1], [0, 1, 1, 0], [1, 1, 1, 1]]
+    assert out[:, 1].tolist() == [0, 1, 10, 1, 0, 100]
+    assert out[[1, 2, 3, 5], 0].tolist() == [4.5] * 4 and out[[1, 2, 3, 5], 2].tolist() == [4.5] * 4
+
+
+def test_map_whole_degenerate_shapes(eng, orc):
+    """One seqname; a genome where no seqname has lefts; rights without scores for a count."""
+    c = random_case(31, 5000, 4000, span=200_000, maxlen=700, sorted_left=True)
+    got, gv = eng.ctx.map_whole([(c["rs"], c["re"], c["scores"])], [0, len(c["ls"])], c["ls"], c["le"], ["mean", "max"])
+    t = orc.Tree(c["rs"], c["re"])
+    want, wv = orc.map_joins(t, c["scores"], None, c["ls"], c["le"], ["mean", "max"])
+    assert (gv == wv).all()
+    assert np.allclose(got[:, 0][wv[:, 0] == 1], want[:, 0][wv[:, 0] == 1], rtol=1e-12, atol=0)
+    assert (got[:, 1][wv[:, 1] == 1] == want[:, 1][wv[:, 1] == 1]).all()
+    out, ov = eng.ctx.map_whole([(c["rs"], c["re"], c["scores"])] * 3, [0, 0, 0, 0], np.zeros(0, np.uint32), np.zeros(0, np.uint32), ["mean"])
+    assert out.shape == (0, 1)
+    got, gv = eng.ctx.map_whole([(c["rs"], c["re"])], [0, len(c["ls"])], c["ls"], c["le"], ["count"])
+    assert (got[:, 0] == orc.map_joins(t, None, None, c["ls"], c["le"], ["count"])[0][:, 0]).all()
