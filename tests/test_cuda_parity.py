@@ -727,7 +727,9 @@ def test_minmax_without_a_sweep(orc, monkeypatch, name):
         ix = ctx.index_build(c["rs"], c["re"]).set_scores(c["scores"], c["valid"])
         n0 = ctx.launch_count
         res[mode] = ctx.map_joins(ix, c["ls"], c["le"], ops)
-        res[mode + "b"] = ctx.map_joins(ix, c["ls"], c["le"], ["min"])  # tables are reused
+        n1 = ctx.launch_count
+        res[mode + "b"] = ctx.map_joins(ix, c["ls"], c["le"], ["min"])  # tables are reused: far fewer launches than the first call
+        assert ctx.launch_count - n1 < n1 - n0
     t = orc.Tree(c["rs"], c["re"])
     want, wv = orc.map_joins(t, c["scores"], c["valid"], c["ls"], c["le"], ops)
     abs_sums = orc.map_joins(t, np.abs(c["scores"]), c["valid"], c["ls"], c["le"], ["sum"])[0][:, 0]
