@@ -82,9 +82,15 @@ __device__ __forceinline__ void mbar_arrive(u64 *bar) {
 
 constexpr int PIPE_MULTI = 100;  // FAST value: several prefix-sum reductions (sum / sum-not-empty / mean / count) per left
 
+constexpr int PIPE_UBLB = 102;   // FAST value: PIPE_MULTI for the columns the prefix sums answer (others are left alone) + the three
+                                 // counts ub = #{start < l.end}, pp = #{start < l.start}, lb = #{end <= l.start} written out for the
+                                 // member sweep / the closed forms that follow
+
 struct PipeOps {
     int k;
     int ops[GRB_MAX_OPS];
+    u32 *ub, *pp, *lb;  // PIPE_UBLB
+    int need_pfx;       // PIPE_UBLB: some column needs the score prefixes
 };
 
 // flags: bit 0 = stage with TMA; bit 1 = debug, consumers skip the arithmetic (pipeline-only timing)
@@ -93,6 +99,7 @@ __global__ void __launch_bounds__(PIPE_THREADS, 1) k_map_pipe(const SeqDev *__re
                                                               const u32 *__restrict__ ls, const u32 *__restrict__ le,
                                                               double *__restrict__ out, u8 *__restrict__ out_valid, int flags,
                                                               u32 *__restrict__ ctx_flags, const PipeOps mops) {
+    const bool want_prefixes = FAST != GRB_OP_COUNT && (FAST != PIPE_UBLB || mops.need_pfx != 0);
     extern __shared__ __align__(128) unsigned char smem_raw[];
     PipeSmem &S = *reinterpret_cast<PipeSmem *>(smem_raw);
     const u32 tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
@@ -186,7 +193,7 @@ __global__ void __launch_bounds__(PIPE_THREADS, 1) k_map_pipe(const SeqDev *__re
             // bound[1] == 0xffffffff: the surveyor found invalid lefts in this tile (no index is that long)
             const bool staged = use_tma && ti.bound[1] != 0xffffffffu && alen <= PIPE_WIN && blen <= PIPE_WIN && lalen <= PIPE_LUT &&
                                 lblen <= PIPE_LUT;
-            const bool want_pfx = FAST != GRB_OP_COUNT;
+            const bool want_pfx = want_prefixes;
             // lane l issues copy l: 0 lut_a, 1 lut_b, 2 starts, 3 ends_sorted, 4 pfx_a, 5 pfx_b
             const void *src = nullptr;
             void *dst = nullptr;
@@ -270,7 +277,8 @@ __global__ void __launch_bounds__(PIPE_THREADS, 1) k_map_pipe(const SeqDev *__re
                 const bool tile_bad = mx_w >= 0x7fffffffu || mx_e > 0x7fffffffu;
                 if (tile_bad && lane == 0) atomicOr(ctx_flags, 1u);
                 const u32 qq = lane & 3;
-                const u32 v = qq == 0 ? mn_e : qq == 1 ? mx_e : qq == 2 ? mn_s : mx_s;
+                // (PIPE_UBLB also searches the starts for l.start: the low end of that window comes from min l.start)
+                const u32 v = qq == 0 ? (FAST == PIPE_UBLB ? mn_s : mn_e) : qq == 1 ? mx_e : qq == 2 ? mn_s : mx_s;
                 const u32 x = v + (qq >> 1);  // l.end for the starts table, l.start + 1 for the ends table
                 bin_new = min(x >> q.sh, q.bmax);
                 bound_new = ((qq < 2) ? q.lut_a : q.lut_b)[bin_new + (qq & 1)];
@@ -329,8 +337,10 @@ __global__ void __launch_bounds__(PIPE_THREADS, 1) k_map_pipe(const SeqDev *__re
             // the surveyor, which also keeps its tile off the staged path.)
             const u32 a0 = d.a0, b0 = d.b0, la0 = d.la0, lb0 = d.lb0;
             const SeqDev *__restrict__ sd = &seqs[d.seq];  // only dereferenced on the rare paths
-            u32 ub[PIPE_LPT], lbk[PIPE_LPT];  // absolute positions
+            u32 ub[PIPE_LPT], lbk[PIPE_LPT], ppk[PIPE_LPT];  // absolute positions
             u64 pa[PIPE_LPT], pb[PIPE_LPT];
+#pragma unroll
+            for (int k = 0; k < PIPE_LPT; k++) ppk[k] = 0;
             if (d.staged) {
                 const u32 *__restrict__ KA = S.ka[sw];
                 const u32 *__restrict__ KB = S.kb[sw];
@@ -358,12 +368,27 @@ __global__ void __launch_bounds__(PIPE_THREADS, 1) k_map_pipe(const SeqDev *__re
                     pA[k] = okv[k] ? qa + cA[k] : 0u;
                     pB[k] = okv[k] ? qb + cB[k] : 0u;
                 }
+                if (FAST == PIPE_UBLB) {
+                    // third search: #{start < l.start}, same scheme on the starts window
+#pragma unroll
+                    for (int k = 0; k < PIPE_LPT; k++) {
+                        const u32 xp = okv[k] ? a[k] : 0u;
+                        u32 pP = okv[k] ? S.la[sw][min(a[k] >> sh, bmax) - la0] - a0 : 0u;
+                        const u32 qp = pP & ~3u;
+                        const uint4 p0v = *reinterpret_cast<const uint4 *>(KA + qp), p1v = *reinterpret_cast<const uint4 *>(KA + qp + 4);
+                        const u32 cP = (p0v.x < xp) + (p0v.y < xp) + (p0v.z < xp) + (p0v.w < xp) + (p1v.x < xp) + (p1v.y < xp) + (p1v.z < xp) +
+                                       (p1v.w < xp);
+                        pP = okv[k] ? qp + cP : 0u;
+                        if (cP == 8) pP = scan_lower_bound(KA, pP, a[k]);
+                        ppk[k] = a0 + pP;
+                    }
+                }
 #pragma unroll
                 for (int k = 0; k < PIPE_LPT; k++) {
                     if (cA[k] == 8) pA[k] = scan_lower_bound(KA, pA[k], b[k]);      // rare: a crowded bin
                     if (cB[k] == 8) pB[k] = scan_lower_bound(KB, pB[k], a[k] + 1);
-                    pa[k] = FAST != GRB_OP_COUNT ? S.pa[sw][pA[k]] : 0ull;
-                    pb[k] = FAST != GRB_OP_COUNT ? S.pb[sw][pB[k]] : 0ull;
+                    pa[k] = want_prefixes ? S.pa[sw][pA[k]] : 0ull;
+                    pb[k] = want_prefixes ? S.pb[sw][pB[k]] : 0ull;
                     ub[k] = a0 + pA[k];
                     lbk[k] = b0 + pB[k];
                 }
@@ -378,10 +403,11 @@ __global__ void __launch_bounds__(PIPE_THREADS, 1) k_map_pipe(const SeqDev *__re
                     const u32 xa = b[k], xb = a[k] + 1;
                     ub[k] = scan_lower_bound(q.starts, q.lut_a[min(xa >> sh, bmax)], xa);
                     lbk[k] = scan_lower_bound(q.ends_sorted, q.lut_b[min(xb >> sh, bmax)], xb);
-                    if (FAST != GRB_OP_COUNT) {
+                    if (want_prefixes) {
                         pa[k] = q.pfx_a[ub[k]];
                         pb[k] = q.pfx_b[lbk[k]];
                     }
+                    if (FAST == PIPE_UBLB) ppk[k] = scan_lower_bound(q.starts, q.lut_a[min(a[k] >> sh, bmax)], a[k]);
                 }
             }
             // ---- everything this warp needs from the two ring slots is in registers now: hand them back
@@ -393,14 +419,31 @@ __global__ void __launch_bounds__(PIPE_THREADS, 1) k_map_pipe(const SeqDev *__re
                 mbar_arrive(&S.emptyL[sl]);
             }
             // ---- reductions
-            if (FAST == PIPE_MULTI) {
+            if (FAST == PIPE_UBLB) {
+                if (PIPE_LPT == 2 && okv[0] && okv[1]) {
+                    *reinterpret_cast<uint2 *>(mops.ub + g0) = make_uint2(ub[0], ub[1 % PIPE_LPT]);
+                    *reinterpret_cast<uint2 *>(mops.pp + g0) = make_uint2(ppk[0], ppk[1 % PIPE_LPT]);
+                    *reinterpret_cast<uint2 *>(mops.lb + g0) = make_uint2(lbk[0], lbk[1 % PIPE_LPT]);
+                } else {
+#pragma unroll
+                    for (int k = 0; k < PIPE_LPT; k++)
+                        if (okv[k]) {
+                            mops.ub[g0 + k] = ub[k];
+                            mops.pp[g0 + k] = ppk[k];
+                            mops.lb[g0 + k] = lbk[k];
+                        }
+                }
+            }
+            if (FAST == PIPE_MULTI || FAST == PIPE_UBLB) {
                 // several reductions from the same (count, exact sum): row-major out[left][column]
 #pragma unroll
                 for (int k = 0; k < PIPE_LPT; k++) {
                     if (!okv[k]) continue;
                     const u32 c = ub[k] - lbk[k];
-                    double sum;
-                    if (c < fast_cmax) {
+                    double sum = 0.0;
+                    if (!want_prefixes) {
+                        // no column needs a sum
+                    } else if (c < fast_cmax) {
                         sum = (double)(i64)(pa[k] - pb[k]) * scale;
                     } else {
                         const i128 ba128 = sd->base_a[ub[k] >> GRB_BASE_SHIFT], bb128 = sd->base_b[lbk[k] >> GRB_BASE_SHIFT];
@@ -413,6 +456,8 @@ __global__ void __launch_bounds__(PIPE_THREADS, 1) k_map_pipe(const SeqDev *__re
                     u8 *pv = out_valid + (g0 + k) * (u64)mops.k;
                     for (int col = 0; col < mops.k; col++) {
                         const int op = mops.ops[col];
+                        if (FAST == PIPE_UBLB && op != GRB_OP_COUNT && op != GRB_OP_MEAN && op != GRB_OP_SUM && op != GRB_OP_SUM_NOT_EMPTY)
+                            continue;  // a member reduction / closed form: the kernels that follow own this column
                         const double rr = op == GRB_OP_COUNT ? (double)c : op == GRB_OP_MEAN ? mean : sum;
                         const u8 vv = (op == GRB_OP_SUM || op == GRB_OP_COUNT) ? (u8)1 : (u8)(c != 0);
                         __stcs(po + col, rr);

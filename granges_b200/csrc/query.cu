@@ -906,6 +906,10 @@ int launch_pipe(grb_ctx *ctx, const Batch &b, const u32 *ls, const u32 *le, cons
         PipeOps mops;
         mops.k = o.k;
         for (int c = 0; c < GRB_MAX_OPS; c++) mops.ops[c] = c < o.k ? o.ops[c] : 0;
+        mops.ub = o.ub;
+        mops.pp = o.pp;
+        mops.lb = o.lb;
+        mops.need_pfx = o.need_sum;
         k_map_pipe<FAST><<<grid, PIPE_THREADS, sizeof(PipeSmem), ctx->stream>>>(b.seqs + s0, s1 - s0, t0, t1 - t0, ls, le, o.out, o.out_valid,
                                                                               flags, o.flags, mops);
         GRB_LAUNCHED(ctx);
@@ -916,6 +920,15 @@ int launch_pipe(grb_ctx *ctx, const Batch &b, const u32 *ls, const u32 *le, cons
 // MAP launch: the single-reduction fast kernels when the batch is uniform, else the general one.
 template <int MODE>
 int launch_map(grb_ctx *ctx, const Batch &b, const u32 *ls, const u32 *le, const TileOut &o) {
+    const char *up = getenv("GRB_UBLB_PIPE");  // debug: 1 = the pipeline for every (ub, pp, lb) pass, 0 = never
+    const bool ublb_pipe = up ? atoi(up) != 0 : o.need_sum != 0;
+    if (MODE == (M_MAP | M_UBLB) && ctx->pipe_mode == 1 && ublb_pipe && (b.uniform || !o.need_sum) && b.ntiles >= 4u * (u32)ctx->sm_count) {
+        // The counts for the member sweep / the closed forms, with the columns the prefix sums answer, in the pipeline
+        // (sums need a uniform batch: scores, no None, compact prefixes).  Measured at 100M x 100M: with sums beside the
+        // members (config C3) the pipeline saves 0.8 ms; for counts alone the tile kernel is as fast (3.1 vs 3.3 ms for
+        // `min`), so it keeps those.
+        return launch_pipe<PIPE_UBLB>(ctx, b, ls, le, o);
+    }
     if (MODE == M_MAP && b.uniform && o.k > 1 && ctx->pipe_mode) {
         // several reductions, all answered by the prefix sums: still one pass of the pipelined kernel
         bool algebraic = true;

@@ -809,3 +809,46 @@ def test_map_whole_degenerate_shapes(eng, orc):
     assert out.shape == (0, 1)
     got, gv = eng.ctx.map_whole([(c["rs"], c["re"])], [0, len(c["ls"])], c["ls"], c["le"], ["count"])
     assert (got[:, 0] == orc.map_joins(t, None, None, c["ls"], c["le"], ["count"])[0][:, 0]).all()
+
+
+@pytest.mark.parametrize("variant", ["sums", "no-sums-with-nulls", "median"])
+def test_counts_through_the_pipeline(orc, monkeypatch, variant):
+    """The (ub, pp, lb) pass in front of the member sweep / closed forms runs in the persistent pipeline when there are
+    many tiles (k_map_pipe<UBLB>): bit-identical to the one-tile-per-CTA kernel (GRB_PIPE_MODE=0) and to the oracle --
+    ragged seqname boundaries, an absent seqname, None scores (counts only), crowded bins, unsorted lefts."""
+    import granges_b200 as gb
+
+    nf = 0.3 if variant == "no-sums-with-nulls" else 0.0
+    specs = [(330_000, 200_000, 9_000_000, True), (1, 5, 100, True), (2_500, 0, 1000, True), (250_000, 400_000, 6_000_000, True),
+             (80_000, 3_000, 60_000_000, True), (30_000, 30_000, 600_000, False), (1025, 5000, 60, True)]
+    cases = [random_case(800 + i, nl, nr, span=span, maxlen=999, sorted_left=srt, null_frac=nf) for i, (nl, nr, span, srt) in enumerate(specs)]
+    off = np.concatenate([[0], np.cumsum([len(c["ls"]) for c in cases])]).astype(np.uint64)
+    assert off[-1] >= 620_000
+    ls = np.concatenate([c["ls"] for c in cases])
+    le = np.concatenate([c["le"] for c in cases])
+    ops = {"sums": ["min", "count", "mean", "max", "sum", "weighted-mean"], "no-sums-with-nulls": ["max", "overlap-bp", "count", "min"],
+           "median": ["median", "mean", "overlap-bp"]}[variant]
+    res = {}
+    monkeypatch.setenv("GRB_UBLB_PIPE", "1")  # also where the default keeps the tile kernel (no sums)
+    for mode in ("1", "0"):
+        monkeypatch.setenv("GRB_PIPE_MODE", mode)
+        ctx = gb.Context(0)
+        idxs = [None if i == 2 else ctx.index_build(c["rs"], c["re"]).set_scores(c["scores"], c["valid"]) for i, c in enumerate(cases)]
+        res[mode] = ctx.map_joins_batch(idxs, off, ls, le, ops)
+    assert (res["1"][1] == res["0"][1]).all()
+    m = res["1"][1] == 1
+    assert (res["1"][0][m] == res["0"][0][m]).all()
+    for i in (0, 3, 5, 6):
+        c = cases[i]
+        sl = slice(int(off[i]), int(off[i + 1]))
+        pick = np.arange(0, len(c["ls"]), 37)
+        t = orc.Tree(c["rs"], c["re"])
+        want, wv = orc.map_joins(t, c["scores"], c["valid"], c["ls"][pick], c["le"][pick], ops)
+        got, gv = res["1"][0][sl][pick], res["1"][1][sl][pick]
+        assert (gv == wv).all()
+        for col, op in enumerate(ops):
+            mm = wv[:, col] == 1
+            if op in ("mean", "sum", "weighted-mean"):
+                assert np.allclose(got[mm, col], want[mm, col], rtol=1e-12, atol=0), op
+            else:
+                assert (got[mm, col] == want[mm, col]).all(), op
