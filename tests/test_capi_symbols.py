@@ -94,3 +94,33 @@ def test_shard_plan_covers_everything(built):
             cost[p["rank"]] += (p["left_end"] - p["left_begin"]) * (nls[s] + nr[s]) / nls[s]
         if nranks > 1:
             assert cost.max() <= 1.25 * cost.sum() / nranks
+
+
+def test_pair_aware_shard_cost_balances_member_sweeps(built):
+    """bench.py --ops min,...,median adds PAIR_WEIGHT x expected pairs to a seqname's cost (sharding.PAIR_WEIGHT): with
+    equal counts per seqname the short chromosomes hold several times the pairs of the long ones, and the plan must
+    balance lefts + weighted pairs, not lefts + rights."""
+    import bench
+    from granges_b200 import sharding
+
+    n = 100_000_000
+    per = bench.split_counts(n, 22)
+    off = np.concatenate([[0], np.cumsum(per)]).astype(np.uint64)
+    pairs = [per[s] * per[s] * 1000.0 / bench.HG38[s] for s in range(22)]
+    cost = [int(per[s] + sharding.PAIR_WEIGHT * pairs[s]) for s in range(22)]
+    for world in (2, 4, 8):
+        plan = sharding.plan(off, cost, world)
+        work = np.zeros(world)
+        for u in plan:
+            s = u["seq"]
+            frac = (u["left_end"] - u["left_begin"]) / per[s]
+            work[u["rank"]] += frac * (per[s] + per[s] + sharding.PAIR_WEIGHT * pairs[s])
+        assert work.max() <= 1.02 * work.mean(), (world, work)
+        # the lefts + rights plan of the same job is off by tens of percent on that measure
+        plain = sharding.plan(off, per, world)
+        w2 = np.zeros(world)
+        for u in plain:
+            s = u["seq"]
+            frac = (u["left_end"] - u["left_begin"]) / per[s]
+            w2[u["rank"]] += frac * (per[s] + per[s] + sharding.PAIR_WEIGHT * pairs[s])
+        assert w2.max() > 1.2 * w2.mean()
