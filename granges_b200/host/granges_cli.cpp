@@ -12,6 +12,7 @@
 #include <unistd.h>
 
 #include <time.h>
+#include <zlib.h>
 
 #include <cerrno>
 #include <cstdio>
@@ -50,9 +51,14 @@ struct Phase {
     exit(1);
 }
 
+// gzip input is detected by its magic bytes, like the reference's reader (src/io/parsers/tsv.rs:27-45), and inflated
+// into memory (all members of a multi-member / bgzip file).
+std::vector<char> *inflate_all(const unsigned char *src, size_t n, const std::string &path);
+
 struct Mapped {
     const char *p = nullptr;
     size_t n = 0;
+    std::vector<char> *inflated = nullptr;
     explicit Mapped(const std::string &path) {
         int fd = open(path.c_str(), O_RDONLY);
         if (fd < 0) die(path + ": " + strerror(errno));
@@ -63,12 +69,54 @@ struct Mapped {
             void *m = mmap(nullptr, n, PROT_READ, MAP_PRIVATE, fd, 0);
             if (m == MAP_FAILED) die(path + ": mmap failed");
             p = (const char *)m;
-            if (n >= 2 && (unsigned char)p[0] == 0x1f && (unsigned char)p[1] == 0x8b)
-                die(path + ": gzip-compressed input is not supported by this mirror (decompress it first)");
+            if (n >= 2 && (unsigned char)p[0] == 0x1f && (unsigned char)p[1] == 0x8b) {
+                inflated = inflate_all((const unsigned char *)p, n, path);
+                munmap(m, n);
+                p = inflated->data();
+                n = inflated->size();
+            }
         }
         close(fd);
     }
+    Mapped(const Mapped &) = delete;
+    Mapped &operator=(const Mapped &) = delete;
+    ~Mapped() { delete inflated; }  // (a plain mapping lives until the process exits)
 };
+
+std::vector<char> *inflate_all(const unsigned char *src, size_t n, const std::string &path) {
+    auto *out = new std::vector<char>();
+    out->reserve(n * 4);
+    z_stream zs;
+    memset(&zs, 0, sizeof(zs));
+    if (inflateInit2(&zs, 16 + MAX_WBITS) != Z_OK) die(path + ": cannot initialise zlib");
+    std::vector<unsigned char> buf(1 << 20);
+    size_t pos = 0;
+    int rc = Z_OK;
+    while (pos < n) {
+        const size_t chunk = std::min(n - pos, (size_t)1 << 30);
+        zs.next_in = const_cast<unsigned char *>(src + pos);
+        zs.avail_in = (uInt)chunk;
+        while (zs.avail_in > 0) {
+            zs.next_out = buf.data();
+            zs.avail_out = (uInt)buf.size();
+            rc = inflate(&zs, Z_NO_FLUSH);
+            if (rc != Z_OK && rc != Z_STREAM_END) {
+                inflateEnd(&zs);
+                die(path + ": corrupt gzip stream");
+            }
+            out->insert(out->end(), (const char *)buf.data(), (const char *)buf.data() + (buf.size() - zs.avail_out));
+            if (rc == Z_STREAM_END) {
+                if (zs.avail_in == 0) break;
+                if (inflateReset(&zs) != Z_OK) die(path + ": corrupt gzip stream");  // the next member
+            }
+        }
+        pos += chunk - zs.avail_in;
+        if (rc == Z_STREAM_END && pos < n && inflateReset(&zs) != Z_OK) die(path + ": corrupt gzip stream");  // a member ended on the chunk boundary
+    }
+    inflateEnd(&zs);
+    if (rc != Z_STREAM_END) die(path + ": truncated gzip stream");
+    return out;
+}
 
 struct Genome {
     std::vector<std::string> names;

@@ -264,3 +264,26 @@ def test_cli_feature_density(tmp_path, orc):
     # without --headers: same rows, no header line
     got2 = run("feature-density", "-g", tmp_path / "genome.tsv", "-b", tmp_path / "feat.bed", "-w", width, "-s", step).stdout
     assert got2.splitlines() == lines[1:]
+
+
+def test_cli_gzip_input(tmp_path, orc):
+    """gzip input is detected by its magic bytes (src/io/parsers/tsv.rs:27-45), also multi-member (bgzip-style) files:
+    the output equals that of the plain files."""
+    import gzip
+
+    make_files(tmp_path, seed=12)
+    plain = run("map", "-g", tmp_path / "genome.tsv", "-l", tmp_path / "left.bed", "-r", tmp_path / "right.bed", "-f", "mean,median,max").stdout
+    with open(tmp_path / "left.bed", "rb") as f, gzip.open(tmp_path / "left.bed.gz", "wb") as g:
+        g.write(f.read())
+    data = (tmp_path / "right.bed").read_bytes()
+    cut = data.index(b"\n", len(data) // 2) + 1
+    with open(tmp_path / "right.bed.gz", "wb") as g:  # two gzip members back to back
+        g.write(gzip.compress(data[:cut]))
+        g.write(gzip.compress(data[cut:]))
+    got = run("map", "-g", tmp_path / "genome.tsv", "-l", tmp_path / "left.bed.gz", "-r", tmp_path / "right.bed.gz", "-f", "mean,median,max").stdout
+    assert got == plain and len(plain) > 1000
+    merged_plain = run("merge", "-b", tmp_path / "right.bed", "-f", "sum").stdout
+    assert run("merge", "-b", tmp_path / "right.bed.gz", "-f", "sum").stdout == merged_plain
+    (tmp_path / "bad.bed.gz").write_bytes(gzip.compress(data)[:200])
+    r = run("filter", "-g", tmp_path / "genome.tsv", "-l", tmp_path / "bad.bed.gz", "-r", tmp_path / "right.bed", check=False)
+    assert r.returncode == 1 and "gzip" in r.stderr
