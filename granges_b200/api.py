@@ -70,6 +70,33 @@ def _arg(a, dtype):
     return arr.ctypes.data, arr, False
 
 
+def _out_arg(a, dtype, shape=None):
+    """Pointer of a caller-provided OUTPUT buffer.  Never copies: the buffer must already be contiguous, writeable,
+    of the exact dtype (and shape, when given) -- a silently made temporary would receive the results instead of the
+    caller's array.  -> (pointer, the buffer itself as keep-alive)."""
+    if _is_torch(a):
+        import torch
+
+        want = {np.uint32: (torch.uint32, torch.int32), np.uint64: (torch.uint64, torch.int64), np.float64: (torch.float64,),
+                np.uint8: (torch.uint8, torch.bool)}[dtype]
+        if a.dtype not in want:
+            raise TypeError(f"output tensor dtype {a.dtype} does not match {dtype.__name__}")
+        if not a.is_contiguous():
+            raise ValueError("output tensor must be contiguous")
+        if shape is not None and tuple(a.shape) != tuple(shape):
+            raise ValueError(f"output tensor has shape {tuple(a.shape)}, expected {tuple(shape)}")
+        return a.data_ptr(), a
+    if not isinstance(a, np.ndarray):
+        raise TypeError("output buffer must be a numpy array or a torch tensor")
+    if a.dtype != np.dtype(dtype):
+        raise TypeError(f"output array dtype {a.dtype} does not match {np.dtype(dtype)}")
+    if not a.flags.c_contiguous or not a.flags.writeable:
+        raise ValueError("output array must be C-contiguous and writeable")
+    if shape is not None and tuple(a.shape) != tuple(shape):
+        raise ValueError(f"output array has shape {a.shape}, expected {tuple(shape)}")
+    return a.ctypes.data, a
+
+
 class Index:
     """One seqname's right-hand index (replaces COITrees<M>, src/ranges/coitrees.rs:25-84)."""
 
@@ -254,7 +281,7 @@ class Context:
             out = np.empty((nl, k), np.float64)
         if out_valid is None:
             out_valid = np.empty((nl, k), np.uint8)
-        po, pv = _arg(out, np.float64)[0], _arg(out_valid, np.uint8)[0]
+        po, pv = _out_arg(out, np.float64, (nl, k))[0], _out_arg(out_valid, np.uint8, (nl, k))[0]
         VP = C.c_void_p * nseq
         self._check(_capi.lib().grb_map_joins_whole_f64(self.h, nseq, VP(*ps), VP(*pe), (C.c_size_t * nseq)(*ns),
                                                         VP(*psc) if any_scores else None, VP(*pva) if any_valid else None,
@@ -342,7 +369,7 @@ class Context:
         if out is None:
             po, out = self._out(dev, (len(kl),), np.uint32, kl)
         else:
-            po = _arg(out, np.uint32)[0]
+            po = _out_arg(out, np.uint32, (len(kl),))[0]
         self._check(_capi.lib().grb_count_overlaps_batch(self.h, self._handles(indexes), off.ctypes.data_as(_capi.u64p), len(indexes),
                                                          pl, pe, po))
         return out
@@ -354,7 +381,7 @@ class Context:
         if out is None:
             po, out = self._out(dev, (len(kl),), np.uint8, kl)
         else:
-            po = _arg(out, np.uint8)[0]
+            po = _out_arg(out, np.uint8, (len(kl),))[0]
         nk = C.c_uint64(0)
         self._check(_capi.lib().grb_filter_overlaps_batch(self.h, self._handles(indexes), off.ctypes.data_as(_capi.u64p), len(indexes),
                                                           pl, pe, int(bool(anti)), po, C.byref(nk)))
@@ -371,26 +398,31 @@ class Context:
                                                            pl, pe, int(bool(anti)), po, C.byref(nk)))
         return out[: nk.value]
 
-    def map_joins_batch(self, indexes, left_offsets, ls, le, ops, out=None, out_valid=None):
+    def map_joins_batch(self, indexes, left_offsets, ls, le, ops, out=None, out_valid=None, valid_bits=False):
+        """valid_bits=True: the validity comes back as a u32 bit array (bit i * k + c), grb_map_joins_f64_batch_bits."""
         pl, kl, dev = _arg(ls, np.uint32)
         pe, ke, _ = _arg(le, np.uint32)
         off = np.ascontiguousarray(left_offsets, dtype=np.uint64)
         ops_a, ops_p = self._ops(ops)
         k = len(ops_a)
+        nl = len(kl)
+        vshape, vdt = (((nl * k + 31) // 32,), np.uint32) if valid_bits else ((nl, k), np.uint8)
         if out is None:
-            po, out = self._out(dev, (len(kl), k), np.float64, kl)
-            pv, out_valid = self._out(dev, (len(kl), k), np.uint8, kl)
+            po, out = self._out(dev, (nl, k), np.float64, kl)
         else:
-            po = _arg(out, np.float64)[0]
-            pv = _arg(out_valid, np.uint8)[0]
-        self._check(_capi.lib().grb_map_joins_f64_batch(self.h, self._handles(indexes), off.ctypes.data_as(_capi.u64p), len(indexes),
-                                                        pl, pe, ops_p, k, po, pv))
+            po = _out_arg(out, np.float64, (nl, k))[0]
+        if out_valid is None:
+            pv, out_valid = self._out(dev, vshape, vdt, kl)
+        else:
+            pv = _out_arg(out_valid, vdt, vshape)[0]
+        fn = _capi.lib().grb_map_joins_f64_batch_bits if valid_bits else _capi.lib().grb_map_joins_f64_batch
+        self._check(fn(self.h, self._handles(indexes), off.ctypes.data_as(_capi.u64p), len(indexes), pl, pe, ops_p, k, po, pv))
         return out, out_valid
 
-    def prepare_map(self, indexes, left_offsets, ls, le, ops, out, out_valid):
-        """Bind every argument of grb_map_joins_f64_batch once; calling the returned object repeats the
+    def prepare_map(self, indexes, left_offsets, ls, le, ops, out, out_valid, valid_bits=False):
+        """Bind every argument of grb_map_joins_f64_batch[_bits] once; calling the returned object repeats the
         query with no per-call Python work beyond the foreign call (for tight loops over a fixed batch)."""
-        return PreparedMap(self, indexes, left_offsets, ls, le, ops, out, out_valid)
+        return PreparedMap(self, indexes, left_offsets, ls, le, ops, out, out_valid, valid_bits)
 
     # -- windows
     def windows_dev(self, seqlens, width, step=None, chop=False):
@@ -442,7 +474,7 @@ class Context:
 class PreparedMap:
     """A grb_map_joins_f64_batch call with all arguments already marshalled."""
 
-    def __init__(self, ctx, indexes, left_offsets, ls, le, ops, out, out_valid):
+    def __init__(self, ctx, indexes, left_offsets, ls, le, ops, out, out_valid, valid_bits=False):
         self.ctx = ctx
         self._keep = (indexes, ls, le, out, out_valid)  # keep the buffers alive
         self._handles = Context._handles(indexes)
@@ -451,9 +483,9 @@ class PreparedMap:
         k = len(self._ops)
         pl, _, _ = _arg(ls, np.uint32)
         pe, _, _ = _arg(le, np.uint32)
-        po = _arg(out, np.float64)[0]
-        pv = _arg(out_valid, np.uint8)[0]
-        self._fn = _capi.lib().grb_map_joins_f64_batch
+        po = _out_arg(out, np.float64)[0]
+        pv = _out_arg(out_valid, np.uint32 if valid_bits else np.uint8)[0]
+        self._fn = _capi.lib().grb_map_joins_f64_batch_bits if valid_bits else _capi.lib().grb_map_joins_f64_batch
         self._args = (ctx.h, self._handles, self._off.ctypes.data_as(_capi.u64p), len(indexes), pl, pe, ops_p, k, po, pv)
 
     def __call__(self):

@@ -8,6 +8,7 @@
 #include "granges_b200.h"
 
 typedef uint8_t u8;
+typedef uint16_t u16;
 typedef uint32_t u32;
 typedef uint64_t u64;
 typedef int64_t i64;
@@ -33,6 +34,9 @@ struct grb_ctx {
     void *zeros;    // 1 KB of zeros (tables) + 1 KB of 0xff (sentinel keys): what an absent seqname / empty index reads
     int pipe_mode;  // 1 = persistent warp-specialised pipeline for single-reduction maps (default), 0 = k_tile only (debug)
     int tile_mode;  // 1 = TMA-staged smem windows (default), 0 = global binary search only (debug)
+    int ublb_pipe;  // GRB_UBLB_PIPE: 1 / 0 = the (ub, pp, lb) pass always / never in the pipelined kernel; -1 (default) = beside sums
+    int minmax_mode; // GRB_MINMAX_MODE: 0 = MIN / MAX sweep the members even without a median beside them (debug)
+    int whole_chunks, whole_workers;  // GRB_WHOLE_CHUNKS / GRB_WHOLE_WORKERS (defaults 8 / 4)
     int sweep_mode; // 1 = staged rank sweep k_sweep3 for MIN / MAX / MEDIAN (default), 2 = k_sweep3 without staging, 0 = k_sweep2 only (debug)
     char err[512];
 };
@@ -134,7 +138,13 @@ inline void grb_dev_free(grb_ctx *ctx, void *p) {
 // ---- index ----------------------------------------------------------------
 
 // How SUM / MEAN are answered for one index.
-enum { GRB_SUM_SWEEP = 0, GRB_SUM_COMPACT = 1, GRB_SUM_WIDE = 2 };
+//   SWEEP    the members are summed one by one (subnormal scores, or a dynamic range beyond 126 bits)
+//   COMPACT  W + 8 <= 62: prefixes mod 2^64 per right + one exact i128 base per 256 rights
+//   WIDE     one exact i128 prefix per right (W too large for WIDE96)
+//   WIDE96   W + 8 <= 94: prefixes mod 2^96 per right as two planes (u64 low, u32 high) + the per-256 bases
+// Non-finite scores do not change the mode: they count as 0 in the fixed point and are tallied by the nf_* prefix
+// counters, from which the IEEE result of the left-to-right sum (NaN / +inf / -inf) follows by rule.
+enum { GRB_SUM_SWEEP = 0, GRB_SUM_COMPACT = 1, GRB_SUM_WIDE = 2, GRB_SUM_WIDE96 = 3 };
 
 #define GRB_BASE_SHIFT 8  // compact mode: one exact i128 base per 256 rights beside the 64-bit wrapped prefixes
 #define GRB_BME_SHIFT 6   // block-max-end granularity: 64 rights
@@ -162,6 +172,12 @@ struct grb_index {
     int width;    // bits of the largest |score| in fixed point (W)
     u64 *pfx_a;   // compact: n+1 prefixes mod 2^64 (start order)
     u64 *pfx_b;   // compact: n+1 prefixes mod 2^64 (end order)
+    u32 *pfh_a;   // wide96: bits 64..95 of the prefixes (start order); pfx_a holds bits 0..63
+    u32 *pfh_b;
+    uint4 *nf_a;  // only if has_nonfinite: n+1 prefix counts (x = +inf, y = -inf, z = NaN) in start order
+    uint4 *nf_b;  // ... in end order
+    u16 *vc16_a;  // only if has_nulls: vcnt_a & 0xffff (what the pipelined kernel stages)
+    u16 *vc16_b;
     i128 *base_a; // compact: (n>>8)+1 exact block bases;  wide: n+1 exact prefixes
     i128 *base_b;
     // coordinate-bin lookup tables: lut[b] = #keys < (b << lut_shift), b in [0, lut_bmax + 1]
@@ -169,6 +185,8 @@ struct grb_index {
     u32 lut_bmax;
     u32 *lut_a;   // over starts
     u32 *lut_b;   // over ends_sorted
+    u16 *lut16_a;  // lut_a & 0xffff: within one staged window (< 65536 keys) the low halves are enough
+    u16 *lut16_b;
     // member-sweep tables (MIN / MAX / MEDIAN), built on first use by grb_index_prepare_members
     bool has_nonfinite;
     bool members_ready;
@@ -205,8 +223,12 @@ struct SeqDev {
     const double *score_a;
     const u32 *vbits_a, *vcnt_a, *vcnt_b;
     const u64 *pfx_a, *pfx_b;
+    const u32 *pfh_a, *pfh_b;
+    const uint4 *nf_a, *nf_b;
+    const u16 *vc16_a, *vc16_b;
     const i128 *base_a, *base_b;
     const u32 *lut_a, *lut_b;
+    const u16 *lut16_a, *lut16_b;
     const u32 *rank_a, *fb;
     const double *score_sorted;
     const u32 *stab_min, *sp_min;
@@ -259,31 +281,41 @@ __device__ __forceinline__ i128 to_fx(double x, int e0) {
     return (b >> 63) ? -(i128)v : (i128)v;
 }
 
-// fixed point -> nearest f64 (round half to even): the correctly rounded exact sum.
+// fixed point -> nearest f64 (round half to even): the correctly rounded exact sum.  Values beyond 63 bits are
+// shifted down to 62 significant bits with a sticky bit, so the one rounding of the integer -> f64 conversion is
+// the rounding of the exact value.
 __device__ __forceinline__ double fx_to_double(i128 v, int e0) {
     if (v == 0) return 0.0;
-    bool neg = v < 0;
-    u128 m = neg ? (u128)(-v) : (u128)v;
-    u64 hi = (u64)(m >> 64), lo = (u64)m;
-    int nbits = hi ? 128 - __clzll((long long)hi) : 64 - __clzll((long long)lo);
+    const bool neg = v < 0;
+    const u128 m = neg ? (u128)(-v) : (u128)v;
+    const u64 hi = (u64)(m >> 64), lo = (u64)m;
+    const int nbits = hi ? 128 - __clzll((long long)hi) : 64 - __clzll((long long)lo);
     int sh = 0;
-    u64 q;
-    if (nbits <= 53) {
-        q = lo;
-    } else {
-        sh = nbits - 53;
+    u64 q = lo;
+    if (nbits > 63) {
+        sh = nbits - 62;
         q = (u64)(m >> sh);
-        u128 rem = m & (((u128)1 << sh) - 1);
-        u128 half = (u128)1 << (sh - 1);
-        if (rem > half || (rem == half && (q & 1))) q++;
+        if ((m & (((u128)1 << sh) - 1)) != 0) q |= 1;
     }
-    double r = (double)q;  // exact: q <= 2^53
+    double r = (double)(i64)q;
     // scale by 2^(sh+e0) in two exact steps (each factor is a normal power of two)
-    int e = sh + e0;
-    int e1 = e / 2, e2 = e - e1;
+    const int e = sh + e0;
+    const int e1 = e / 2, e2 = e - e1;
     r *= __longlong_as_double((long long)(u64)(1023 + e1) << 52);
     r *= __longlong_as_double((long long)(u64)(1023 + e2) << 52);
     return neg ? -r : r;
+}
+
+// the 96-bit two-plane prefix (hi:lo) as a sign-extended i128
+__device__ __forceinline__ i128 sext96(u32 hi, u64 lo) { return (i128)(((u128)(u64)(i64)(int)hi << 64) | (u128)lo); }
+
+// IEEE outcome of a left-to-right f64 sum that met np +inf, nn -inf and nan NaN scores: NaN beats everything,
+// +inf and -inf together give NaN, one kind of infinity wins over any finite part.
+__device__ __forceinline__ double nf_rule(double finite_sum, u32 np, u32 nn, u32 nan) {
+    if (nan || (np && nn)) return __longlong_as_double(0x7ff8000000000000ll);
+    if (np) return __longlong_as_double(0x7ff0000000000000ll);
+    if (nn) return __longlong_as_double((long long)0xfff0000000000000ull);
+    return finite_sum;
 }
 
 // order-preserving integer image of an f64 (and back): -inf < ... < -0.0 < +0.0 < ... < +inf

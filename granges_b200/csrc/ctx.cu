@@ -94,6 +94,15 @@ int grb_ctx_create(int device, grb_ctx **out) {
     ctx->sweep_mode = 1;
     const char *sm = getenv("GRB_SWEEP_MODE");
     if (sm) ctx->sweep_mode = atoi(sm);
+    // the remaining tuning knobs are read once, here, not on every call
+    const char *up = getenv("GRB_UBLB_PIPE");
+    ctx->ublb_pipe = up ? (atoi(up) != 0) : -1;
+    const char *mm = getenv("GRB_MINMAX_MODE");
+    ctx->minmax_mode = mm ? atoi(mm) : 1;
+    const char *wc = getenv("GRB_WHOLE_CHUNKS");
+    ctx->whole_chunks = wc && atoi(wc) > 0 ? atoi(wc) : 8;
+    const char *ww = getenv("GRB_WHOLE_WORKERS");
+    ctx->whole_workers = ww && atoi(ww) > 0 ? atoi(ww) : 4;
     int ndev = 0;
     cudaError_t e = cudaGetDeviceCount(&ndev);
     if (e != cudaSuccess || device < 0 || device >= ndev) {

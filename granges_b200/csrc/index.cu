@@ -101,11 +101,12 @@ __global__ void k_block_max_end(const u32 *__restrict__ ends, size_t n, u32 *__r
 }
 
 // lut[b] = #keys < (b << shift) for b in [0, bmax]; entries bmax+1 .. bmax+PAD = n.
-__global__ void k_build_lut(const u32 *__restrict__ keys, u32 n, int shift, u32 bmax, u32 *__restrict__ lut) {
+__global__ void k_build_lut(const u32 *__restrict__ keys, u32 n, int shift, u32 bmax, u32 *__restrict__ lut, u16 *__restrict__ lut16) {
     u32 b = blockIdx.x * blockDim.x + threadIdx.x;
     if (b > bmax + PAD) return;
     if (b > bmax) {
         lut[b] = n;
+        lut16[b] = (u16)n;
         return;
     }
     u64 x = (u64)b << shift;
@@ -118,6 +119,7 @@ __global__ void k_build_lut(const u32 *__restrict__ keys, u32 n, int shift, u32 
             hi = mid;
     }
     lut[b] = lo;
+    lut16[b] = (u16)lo;
 }
 
 // ---- scores ------------------------------------------------------------------
@@ -212,11 +214,12 @@ __global__ void k_permute_u32(const u32 *__restrict__ src, const u32 *__restrict
 //   phase 0: blocksum[b] = sum of the block's elements
 //   phase 1 (compact): pfx[p] = low 64 bits of base[b] + local exclusive prefix
 //   phase 2 (wide):    wide[p] = base[b] + local exclusive prefix (i128)
+//   phase 3 (wide96):  pfx[p] / pfh[p] = bits 0..63 / 64..95 of base[b] + local exclusive prefix
 template <int PHASE>
 __global__ void __launch_bounds__(256) k_fx_blocks(const double *__restrict__ score_a, const u32 *__restrict__ perm,
                                                    size_t n, int e0, i128 *__restrict__ blocksum,
                                                    const i128 *__restrict__ base, u64 *__restrict__ pfx,
-                                                   i128 *__restrict__ wide) {
+                                                   i128 *__restrict__ wide, u32 *__restrict__ pfh) {
     __shared__ u64 s_lo[8], s_hi[8];
     const size_t b = blockIdx.x;
     const size_t p = (b << GRB_BASE_SHIFT) + threadIdx.x;
@@ -248,9 +251,38 @@ __global__ void __launch_bounds__(256) k_fx_blocks(const double *__restrict__ sc
         if (threadIdx.x == 0) blocksum[b] = total;
     } else if (PHASE == 1) {
         if (p <= n) pfx[p] = (u64)(u128)(base[b] + excl);
+    } else if (PHASE == 3) {
+        if (p <= n) {
+            const u128 t = (u128)(base[b] + excl);
+            pfx[p] = (u64)t;
+            pfh[p] = (u32)(t >> 64);
+        }
     } else {
         if (p <= n) wide[p] = base[b] + excl;
     }
+}
+
+// low halves of a u32 array (what the pipelined kernel stages for the valid-score counts)
+__global__ void k_narrow_u16(const u32 *__restrict__ in, size_t n, u16 *__restrict__ out) {
+    size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n) out[i] = (u16)in[i];
+}
+
+// which = 0 / 1 / 2: flag the +inf / -inf / NaN scores (position i of the start order, or of the end order through perm)
+__global__ void k_nf_flags(const double *__restrict__ score_a, const u32 *__restrict__ vbits_a, const u32 *__restrict__ perm, size_t n,
+                           int which, u32 *__restrict__ flags) {
+    size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    const u32 j = perm ? perm[i] : (u32)i;
+    const bool ok = vbits_a ? ((vbits_a[j >> 5] >> (j & 31)) & 1u) : true;
+    const u64 b = (u64)__double_as_longlong(score_a[j]);
+    const bool nonfinite = ((b >> 52) & 0x7ff) == 0x7ff, nan = nonfinite && (b & ((1ull << 52) - 1)) != 0;
+    const int cls = !ok || !nonfinite ? -1 : nan ? 2 : (b >> 63) ? 1 : 0;
+    flags[i] = cls == which ? 1u : 0u;
+}
+__global__ void k_nf_pack(const u32 *__restrict__ a, const u32 *__restrict__ b, const u32 *__restrict__ c, size_t n, uint4 *__restrict__ out) {
+    size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n) out[i] = make_uint4(a[i], b[i], c[i], 0u);
 }
 
 // The same block scan over score * coordinate (exact: the product of a W-bit and a 31-bit integer).
@@ -525,6 +557,15 @@ void free_scores(grb_index *ix) {
     grb_dev_free(ix->ctx, ix->vcnt_b);
     grb_dev_free(ix->ctx, ix->pfx_a);
     grb_dev_free(ix->ctx, ix->pfx_b);
+    grb_dev_free(ix->ctx, ix->pfh_a);
+    grb_dev_free(ix->ctx, ix->pfh_b);
+    grb_dev_free(ix->ctx, ix->nf_a);
+    grb_dev_free(ix->ctx, ix->nf_b);
+    grb_dev_free(ix->ctx, ix->vc16_a);
+    grb_dev_free(ix->ctx, ix->vc16_b);
+    ix->pfh_a = ix->pfh_b = nullptr;
+    ix->nf_a = ix->nf_b = nullptr;
+    ix->vc16_a = ix->vc16_b = nullptr;
     grb_dev_free(ix->ctx, ix->base_a);
     grb_dev_free(ix->ctx, ix->base_b);
     grb_dev_free(ix->ctx, ix->rank_a);
@@ -556,19 +597,24 @@ void free_scores(grb_index *ix) {
     ix->sum_mode = GRB_SUM_SWEEP;
 }
 
-int build_prefix(grb_ctx *ctx, grb_index *ix, const u32 *perm, u64 **pfx_out, i128 **base_out) {
+int build_prefix(grb_ctx *ctx, grb_index *ix, const u32 *perm, u64 **pfx_out, u32 **pfh_out, i128 **base_out) {
     const size_t n = ix->n;
     const size_t nb = (n >> GRB_BASE_SHIFT) + 1;
     TempBuf bsum;
     GRB_TRY(bsum.alloc(ctx, nb * sizeof(i128)));
-    k_fx_blocks<0><<<(unsigned)nb, 256, 0, ctx->stream>>>(ix->score_a, perm, n, ix->e0, bsum.as<i128>(), nullptr, nullptr, nullptr);
+    k_fx_blocks<0><<<(unsigned)nb, 256, 0, ctx->stream>>>(ix->score_a, perm, n, ix->e0, bsum.as<i128>(), nullptr, nullptr, nullptr, nullptr);
     GRB_LAUNCHED(ctx);
-    if (ix->sum_mode == GRB_SUM_COMPACT) {
+    if (ix->sum_mode == GRB_SUM_COMPACT || ix->sum_mode == GRB_SUM_WIDE96) {
         GRB_TRY(dev_alloc(ctx, (void **)base_out, nb * sizeof(i128)));
         GRB_TRY(dev_alloc(ctx, (void **)pfx_out, (n + 1 + PAD) * sizeof(u64)));  // padded: bulk copies round up to 16 B
         k_scan_i128_single<<<1, 1024, 0, ctx->stream>>>(bsum.as<i128>(), nb, *base_out);
         GRB_LAUNCHED(ctx);
-        k_fx_blocks<1><<<(unsigned)nb, 256, 0, ctx->stream>>>(ix->score_a, perm, n, ix->e0, nullptr, *base_out, *pfx_out, nullptr);
+        if (ix->sum_mode == GRB_SUM_COMPACT) {
+            k_fx_blocks<1><<<(unsigned)nb, 256, 0, ctx->stream>>>(ix->score_a, perm, n, ix->e0, nullptr, *base_out, *pfx_out, nullptr, nullptr);
+        } else {
+            GRB_TRY(dev_alloc(ctx, (void **)pfh_out, (n + 1 + PAD) * sizeof(u32)));
+            k_fx_blocks<3><<<(unsigned)nb, 256, 0, ctx->stream>>>(ix->score_a, perm, n, ix->e0, nullptr, *base_out, *pfx_out, nullptr, *pfh_out);
+        }
         GRB_LAUNCHED(ctx);
     } else {
         TempBuf bbase;
@@ -576,9 +622,29 @@ int build_prefix(grb_ctx *ctx, grb_index *ix, const u32 *perm, u64 **pfx_out, i1
         GRB_TRY(dev_alloc(ctx, (void **)base_out, (n + 1) * sizeof(i128)));
         k_scan_i128_single<<<1, 1024, 0, ctx->stream>>>(bsum.as<i128>(), nb, bbase.as<i128>());
         GRB_LAUNCHED(ctx);
-        k_fx_blocks<2><<<(unsigned)nb, 256, 0, ctx->stream>>>(ix->score_a, perm, n, ix->e0, nullptr, bbase.as<i128>(), nullptr, *base_out);
+        k_fx_blocks<2><<<(unsigned)nb, 256, 0, ctx->stream>>>(ix->score_a, perm, n, ix->e0, nullptr, bbase.as<i128>(), nullptr, *base_out, nullptr);
         GRB_LAUNCHED(ctx);
     }
+    return GRB_OK;
+}
+
+// prefix counts of the +inf / -inf / NaN scores in one order (perm == nullptr: start order)
+int build_nf(grb_ctx *ctx, grb_index *ix, const u32 *perm, uint4 **out) {
+    const size_t n = ix->n;
+    TempBuf fl, c0, c1, c2;
+    GRB_TRY(fl.alloc(ctx, n * 4));
+    GRB_TRY(c0.alloc(ctx, (n + 1) * 4));
+    GRB_TRY(c1.alloc(ctx, (n + 1) * 4));
+    GRB_TRY(c2.alloc(ctx, (n + 1) * 4));
+    TempBuf *cs[3] = {&c0, &c1, &c2};
+    for (int which = 0; which < 3; which++) {
+        k_nf_flags<<<blocks_for(n, 256), 256, 0, ctx->stream>>>(ix->score_a, ix->has_nulls ? ix->vbits_a : nullptr, perm, n, which, fl.as<u32>());
+        GRB_LAUNCHED(ctx);
+        GRB_TRY(grb_scan_u32_to_u32(ctx, fl.as<u32>(), cs[which]->as<u32>(), n, true));
+    }
+    GRB_TRY(dev_alloc(ctx, (void **)out, (n + 1) * sizeof(uint4)));
+    k_nf_pack<<<blocks_for(n + 1, 256), 256, 0, ctx->stream>>>(c0.as<u32>(), c1.as<u32>(), c2.as<u32>(), n + 1, *out);
+    GRB_LAUNCHED(ctx);
     return GRB_OK;
 }
 
@@ -688,9 +754,11 @@ int grb_index_build(grb_ctx *ctx, const uint32_t *starts, const uint32_t *ends, 
             size_t entries = (size_t)ix->lut_bmax + 1 + PAD;
             if ((rc = dev_alloc(ctx, (void **)&ix->lut_a, entries * 4))) break;
             if ((rc = dev_alloc(ctx, (void **)&ix->lut_b, entries * 4))) break;
-            k_build_lut<<<blocks_for(entries, 256), 256, 0, ctx->stream>>>(ix->starts, (u32)n, shift, ix->lut_bmax, ix->lut_a);
+            if ((rc = dev_alloc(ctx, (void **)&ix->lut16_a, entries * 2))) break;
+            if ((rc = dev_alloc(ctx, (void **)&ix->lut16_b, entries * 2))) break;
+            k_build_lut<<<blocks_for(entries, 256), 256, 0, ctx->stream>>>(ix->starts, (u32)n, shift, ix->lut_bmax, ix->lut_a, ix->lut16_a);
             ctx->launches++;
-            k_build_lut<<<blocks_for(entries, 256), 256, 0, ctx->stream>>>(ix->ends_sorted, (u32)n, shift, ix->lut_bmax, ix->lut_b);
+            k_build_lut<<<blocks_for(entries, 256), 256, 0, ctx->stream>>>(ix->ends_sorted, (u32)n, shift, ix->lut_bmax, ix->lut_b, ix->lut16_b);
             ctx->launches++;
         }
         if (n) {
@@ -724,6 +792,8 @@ void grb_index_destroy(grb_index *ix) {
     grb_dev_free(ix->ctx, ix->perm_e);
     grb_dev_free(ix->ctx, ix->lut_a);
     grb_dev_free(ix->ctx, ix->lut_b);
+    grb_dev_free(ix->ctx, ix->lut16_a);
+    grb_dev_free(ix->ctx, ix->lut16_b);
     grb_dev_free(ix->ctx, ix->fb);
     grb_dev_free(ix->ctx, ix->sum_starts);
     grb_dev_free(ix->ctx, ix->sum_ends);
@@ -783,6 +853,12 @@ int grb_index_set_scores(grb_index *ix, const double *by_data_idx, const uint8_t
         GRB_LAUNCHED(ctx);
         GRB_TRY(grb_scan_u32_to_u32(ctx, vflag_a.as<u32>(), ix->vcnt_a, n, true));
         GRB_TRY(grb_scan_u32_to_u32(ctx, vflag_b.as<u32>(), ix->vcnt_b, n, true));
+        GRB_TRY(dev_alloc(ctx, (void **)&ix->vc16_a, (n + 1 + PAD) * 2));
+        GRB_TRY(dev_alloc(ctx, (void **)&ix->vc16_b, (n + 1 + PAD) * 2));
+        k_narrow_u16<<<blocks_for(n + 1, 256), 256, 0, ctx->stream>>>(ix->vcnt_a, n + 1, ix->vc16_a);
+        GRB_LAUNCHED(ctx);
+        k_narrow_u16<<<blocks_for(n + 1, 256), 256, 0, ctx->stream>>>(ix->vcnt_b, n + 1, ix->vc16_b);
+        GRB_LAUNCHED(ctx);
     } else if (ix->vbits_a) {
         grb_dev_free(ix->ctx, ix->vbits_a);
         ix->vbits_a = nullptr;
@@ -790,8 +866,9 @@ int grb_index_set_scores(grb_index *ix, const double *by_data_idx, const uint8_t
     // choose how SUM / MEAN are answered
     ix->sum_mode = GRB_SUM_SWEEP;
     ix->e0 = 0;
-    const char *force = getenv("GRB_SUM_MODE");  // debug: 0 sweep, 1 compact, 2 wide (only if representable)
-    if (!st.has_nonfinite && !st.has_subnormal) {
+    const char *force = getenv("GRB_SUM_MODE");  // debug: 0 sweep, 2 wide, 3 wide96 (only if representable)
+    // (non-finite scores count as 0 in the fixed point; the nf_* counters below carry them)
+    if (!st.has_subnormal) {
         int W = 1, e0 = 0, emax = 0;
         if (st.n_nonzero) {
             e0 = st.min_lsb_exp;
@@ -803,17 +880,22 @@ int grb_index_set_scores(grb_index *ix, const double *by_data_idx, const uint8_t
         if (representable) {
             ix->e0 = e0;
             ix->width = W;
-            ix->sum_mode = (W + GRB_BASE_SHIFT <= 62) ? GRB_SUM_COMPACT : GRB_SUM_WIDE;
+            ix->sum_mode = (W + GRB_BASE_SHIFT <= 62) ? GRB_SUM_COMPACT : (W + GRB_BASE_SHIFT <= 94) ? GRB_SUM_WIDE96 : GRB_SUM_WIDE;
             if (force) {
                 int f = atoi(force);
                 if (f == GRB_SUM_SWEEP) ix->sum_mode = GRB_SUM_SWEEP;
                 if (f == GRB_SUM_WIDE) ix->sum_mode = GRB_SUM_WIDE;
+                if (f == GRB_SUM_WIDE96 && W + GRB_BASE_SHIFT <= 94) ix->sum_mode = GRB_SUM_WIDE96;
             }
         }
     }
     if (ix->sum_mode != GRB_SUM_SWEEP) {
-        GRB_TRY(build_prefix(ctx, ix, nullptr, &ix->pfx_a, &ix->base_a));
-        GRB_TRY(build_prefix(ctx, ix, ix->perm_e, &ix->pfx_b, &ix->base_b));
+        GRB_TRY(build_prefix(ctx, ix, nullptr, &ix->pfx_a, &ix->pfh_a, &ix->base_a));
+        GRB_TRY(build_prefix(ctx, ix, ix->perm_e, &ix->pfx_b, &ix->pfh_b, &ix->base_b));
+        if (ix->has_nonfinite && n) {
+            GRB_TRY(build_nf(ctx, ix, nullptr, &ix->nf_a));
+            GRB_TRY(build_nf(ctx, ix, ix->perm_e, &ix->nf_b));
+        }
     }
     GRB_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
     return GRB_OK;
@@ -1019,7 +1101,7 @@ int grb_index_prepare_wm(grb_ctx *ctx, grb_index *ix) {
     const int L = ceil_log2((u64)ix->n + 1);
     // score (W bits) * coordinate (31 bits) summed over n rights must fit the signed 128-bit fixed point, and the
     // rounded result a double
-    if (ix->sum_mode == GRB_SUM_SWEEP || ix->width + L + 32 > 126 || ix->e0 + ix->width + L + 33 >= 1023) {
+    if (ix->sum_mode == GRB_SUM_SWEEP || ix->has_nonfinite || ix->width + L + 32 > 126 || ix->e0 + ix->width + L + 33 >= 1023) {
         ix->wm_unavailable = true;
         return GRB_OK;
     }

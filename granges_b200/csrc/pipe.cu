@@ -1,0 +1,652 @@
+// pipe.cu -- the pipelined prefix-sum map kernel (headline path: `granges map --func mean`).
+//
+// Replaces, per left range, COITrees::query + the gather of JoinDataLeftEmpty::map + FloatOperation::run for the
+// reductions a prefix sum answers (src/ranges/coitrees.rs:48-57, src/join.rs:343-361, src/commands.rs:524-542,
+// src/data/operations.rs:60-70,87-95):  count = ub - lb,  sum = PA[ub] - PB[lb]  with
+//     ub = #{r.start < l.end}     lb = #{r.end <= l.start}.
+//
+// A persistent, warp-specialised TMA pipeline so that no warp ever waits on a dependent chain of global loads.
+// One CTA per SM, tiles blockIdx.x, blockIdx.x + gridDim.x, ...; per tile (1024 consecutive lefts of one seqname):
+//
+//   warp 0  lefts loader   A: TMA the lefts (ls, le) of tile j into the lefts ring, as far ahead as
+//                             the ring allows                                                 -> fullL
+//   warps 1, 3, 4, 5  surveyors (tile j goes to surveyor j mod 4)
+//                          B: min / max of the tile's lefts out of shared memory -> coordinate bins
+//                             -> four bin-table entries by plain loads                        -> statsL
+//   warp 2  window loader  C: TMA the slices the tile can touch -- starts, ends_sorted, the low halves of both
+//                             bin tables, both prefix arrays (and, per variant, the high planes of 96-bit
+//                             prefixes and the low halves of the valid-score counts) -- into the window ring,
+//                             one bulk copy per lane, one mbarrier                            -> fullW
+//   warps 6.. consumers:      wait fullW, resolve ub / lb of 2 lefts per thread out of shared
+//                             memory, exact sums from the staged prefixes, write results,
+//                             release the slots                                               -> emptyW, emptyL
+//
+// Variants (template VAR, chosen per run of seqnames by what their indexes hold):
+//   PIPE_VAR_NULLS  some scores are None (BED "."): the mean divides by the number of members that carry a score,
+//                   vcnt_a[ub] - vcnt_b[lb]; only the low 16 bits of those counts are staged (groups below 65536).
+//   PIPE_VAR_WIDE   the scores need more than 54 bits of fixed point (decimal fractions over a few decades):
+//                   prefixes mod 2^96 in two planes, u64 low + u32 high.
+// Non-finite scores (+-inf, NaN) need no variant: the seqname carries prefix counters nf_a / nf_b that are read from
+// global memory for its lefts, and the IEEE outcome of the reference's left-to-right sum follows by rule.
+//
+// Tiles whose windows do not fit the ring slots (sparse lefts over dense rights, unsorted lefts) are resolved by
+// per-left global searches inside the consumers; results are identical.
+#include "tilelib.cuh"
+
+namespace {
+
+constexpr int PIPE_NCG = 16;    // consumer warps
+constexpr int PIPE_LPT = TILE / (PIPE_NCG * 32);  // lefts per consumer thread: slots cw * 64 + k * 32 + lane
+static_assert(PIPE_LPT == 2, "consumer layout");
+constexpr int PIPE_NSURV = 4;  // surveyor warps (tile j goes to surveyor j % PIPE_NSURV)
+constexpr int PIPE_THREADS = (PIPE_NCG + 2 + PIPE_NSURV) * 32;
+constexpr int PIPE_LSTAGES = 8;
+constexpr u32 PIPE_WIN = 1280;  // keys (and prefixes) per staged window
+constexpr u32 PIPE_LUT = 640;   // bin-table entries per staged slice
+constexpr int PIPE_MAXSEQ = 32; // seqnames per launch (their descriptors live in shared memory)
+
+struct PipeSeq {
+    const u32 *starts, *ends_sorted, *lut_a, *lut_b;
+    const u16 *lut16_a, *lut16_b, *vc16_a, *vc16_b;
+    const u64 *pfx_a, *pfx_b;
+    const u32 *pfh_a, *pfh_b;
+    const uint4 *nf_a, *nf_b;
+    u64 left_begin, left_end;
+    double scale;
+    u32 tile_begin, bmax, fast_cmax;
+    int sh;
+};
+
+struct PipeTile {      // one per lefts-ring slot
+    u64 g_first;       // global index of the tile's slot 0                (loader)
+    u32 vlo, vhi;      // valid slots of the tile: [vlo, vhi)              (loader)
+    int seq;           //                                                  (loader)
+    u32 bin[4];        // bins of min l.end, max l.end, min l.start+1, max l.start+1   (surveyor)
+    u32 bound[4];      // lut_a[bin0], lut_a[bin1 + 1], lut_b[bin2], lut_b[bin3 + 1]     (surveyor)
+};
+
+struct PipeDesc {      // one per window-ring slot (loader -> consumers)
+    u64 g_first;
+    u32 vlo, vhi;
+    u32 a0, b0, la0, lb0;
+    u32 staged;        // 1: windows staged in the slot; 0: search in global memory (windows too large, or invalid lefts)
+    int seq;
+};
+
+template <int VAR>
+struct PipeSmemT {
+    static constexpr int WST = (VAR & PIPE_VAR_WIDE) ? 3 : 4;  // window-ring depth: what fits beside the extra planes
+    static constexpr u32 NH = (VAR & PIPE_VAR_WIDE) ? PIPE_WIN + 8 : 4;
+    static constexpr u32 NV = (VAR & PIPE_VAR_NULLS) ? PIPE_WIN + 8 : 8;
+    alignas(16) u32 ls[PIPE_LSTAGES][TILE];
+    alignas(16) u32 le[PIPE_LSTAGES][TILE];
+    alignas(16) u64 pa[WST][PIPE_WIN + 8];
+    alignas(16) u64 pb[WST][PIPE_WIN + 8];
+    alignas(16) u32 ka[WST][PIPE_WIN + 8];
+    alignas(16) u32 kb[WST][PIPE_WIN + 8];
+    alignas(16) u32 pah[WST][NH];
+    alignas(16) u32 pbh[WST][NH];
+    alignas(16) u16 la[WST][PIPE_LUT + 8];
+    alignas(16) u16 lb[WST][PIPE_LUT + 8];
+    alignas(16) u16 va[WST][NV];
+    alignas(16) u16 vb[WST][NV];
+    PipeSeq seq[PIPE_MAXSEQ];
+    PipeTile tile[PIPE_LSTAGES];
+    PipeDesc desc[WST];
+    alignas(8) u64 fullL[PIPE_LSTAGES];
+    alignas(8) u64 emptyL[PIPE_LSTAGES];
+    alignas(8) u64 statsL[PIPE_LSTAGES];
+    alignas(8) u64 fullW[WST];
+    alignas(8) u64 emptyW[WST];
+};
+static_assert(sizeof(PipeSmemT<0>) <= 232448 && sizeof(PipeSmemT<1>) <= 232448 && sizeof(PipeSmemT<2>) <= 232448 &&
+                  sizeof(PipeSmemT<3>) <= 232448,
+              "the rings must fit the 227 KB of shared memory a CTA can opt in to");
+
+__device__ __forceinline__ void mbar_arrive(u64 *bar) {
+    asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_addr(bar)) : "memory");
+}
+
+struct PipeOps {
+    int k;
+    int ops[GRB_MAX_OPS];
+    u32 *ub, *pp, *lb;  // PIPE_UBLB
+    int need_pfx;       // PIPE_UBLB / PIPE_MULTI: some column needs the score prefixes
+    u32 *valid_bits;    // single-reduction kernels: validity as bits (bit g of word g / 32) instead of bytes
+};
+
+// #(keys < x) among the 8 keys of the two aligned quads at q
+__device__ __forceinline__ u32 count8_below(const u32 *__restrict__ K, u32 q, u32 x) {
+    const uint4 v0 = *reinterpret_cast<const uint4 *>(K + q), v1 = *reinterpret_cast<const uint4 *>(K + q + 4);
+    return (v0.x < x) + (v0.y < x) + (v0.z < x) + (v0.w < x) + (v1.x < x) + (v1.y < x) + (v1.z < x) + (v1.w < x);
+}
+
+// flags: bit 0 = stage with TMA; bit 1 = debug, consumers skip the arithmetic (pipeline-only timing); bit 2 = debug, no stores
+template <int FAST, int VAR>
+__global__ void __launch_bounds__(PIPE_THREADS, 1) k_map_pipe(const SeqDev *__restrict__ seqs, int nseq, u32 tile_base, u32 ntiles,
+                                                              const u32 *__restrict__ ls, const u32 *__restrict__ le,
+                                                              double *__restrict__ out, u8 *__restrict__ out_valid, int flags,
+                                                              u32 *__restrict__ ctx_flags, const PipeOps mops) {
+    using Smem = PipeSmemT<VAR>;
+    constexpr int WST = Smem::WST;
+    constexpr bool NULLS = (VAR & PIPE_VAR_NULLS) != 0, WIDE = (VAR & PIPE_VAR_WIDE) != 0;
+    const bool want_prefixes = FAST != GRB_OP_COUNT && ((FAST != PIPE_UBLB && FAST != PIPE_MULTI) || mops.need_pfx != 0);
+    extern __shared__ __align__(128) unsigned char smem_raw[];
+    Smem &S = *reinterpret_cast<Smem *>(smem_raw);
+    const u32 tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const bool use_tma = flags & 1;
+    if (tid == 0) {
+        for (int i = 0; i < PIPE_LSTAGES; i++) {
+            mbar_init(&S.fullL[i], 1);
+            mbar_init(&S.emptyL[i], PIPE_NCG);
+            mbar_init(&S.statsL[i], 1);
+        }
+        for (int i = 0; i < WST; i++) {
+            mbar_init(&S.fullW[i], 1);
+            mbar_init(&S.emptyW[i], PIPE_NCG);
+        }
+    }
+    if ((int)tid < nseq) {
+        const SeqDev *sd = &seqs[tid];
+        PipeSeq &q = S.seq[tid];
+        q.starts = sd->starts;
+        q.ends_sorted = sd->ends_sorted;
+        q.lut_a = sd->lut_a;
+        q.lut_b = sd->lut_b;
+        q.lut16_a = sd->lut16_a;
+        q.lut16_b = sd->lut16_b;
+        q.vc16_a = sd->vc16_a;
+        q.vc16_b = sd->vc16_b;
+        q.pfx_a = sd->pfx_a;
+        q.pfx_b = sd->pfx_b;
+        q.pfh_a = sd->pfh_a;
+        q.pfh_b = sd->pfh_b;
+        q.nf_a = sd->nf_a;
+        q.nf_b = sd->nf_b;
+        q.left_begin = sd->left_begin;
+        q.left_end = sd->left_end;
+        q.scale = sd->scale;
+        q.tile_begin = sd->tile_begin;
+        q.bmax = sd->lut_bmax;
+        q.fast_cmax = sd->fast_cmax;
+        q.sh = sd->lut_shift;
+    }
+    __syncthreads();
+    const u32 nmine = blockIdx.x < ntiles ? (ntiles - blockIdx.x + gridDim.x - 1) / gridDim.x : 0;
+
+    if (warp == 0) {
+        // ================= lefts loader (A) =================
+        const u64 pol = l2_evict_first_policy();
+        const bool vec_in = ((((uintptr_t)ls) | ((uintptr_t)le)) & 15) == 0;
+        int sq = 0;  // tiles only move forward, so does the seqname
+        for (u32 j = 0; j < nmine; j++) {
+            const u32 sl = j % PIPE_LSTAGES;
+            const u32 t = tile_base + blockIdx.x + j * gridDim.x;
+            while (sq + 1 < nseq && S.seq[sq + 1].tile_begin <= t) sq++;
+            const PipeSeq &q = S.seq[sq];
+            const u64 g_first = ((q.left_begin >> TILE_SHIFT) + (t - q.tile_begin)) << TILE_SHIFT;
+            const u64 lo_g = q.left_begin > g_first ? q.left_begin : g_first;
+            const u64 hi_g = q.left_end < g_first + TILE ? q.left_end : g_first + TILE;
+            const bool whole = vec_in && lo_g == g_first && hi_g == g_first + TILE;
+            mbar_wait(&S.emptyL[sl], ((j / PIPE_LSTAGES) & 1) ^ 1);
+            if (lane == 0) {
+                PipeTile &ti = S.tile[sl];
+                ti.g_first = g_first;
+                ti.vlo = (u32)(lo_g - g_first);
+                ti.vhi = (u32)(hi_g - g_first);
+                ti.seq = sq;
+            }
+            if (whole && use_tma) {
+                if (lane == 0) mbar_arrive_expect_tx(&S.fullL[sl], 2 * TILE * 4);
+                __syncwarp();
+                if (lane < 2) tma_load_1d_hint(lane ? S.le[sl] : S.ls[sl], (lane ? le : ls) + g_first, TILE * 4, &S.fullL[sl], pol);
+            } else {
+                // ragged tile (seqname boundary, end of the arrays, unaligned pointers): plain copies
+                for (u32 i = lane; i < TILE; i += 32) {
+                    const u64 g = g_first + i;
+                    const bool ok = g >= lo_g && g < hi_g;
+                    S.ls[sl][i] = ok ? ls[g] : 0u;
+                    S.le[sl][i] = ok ? le[g] : 0u;
+                }
+                __syncwarp();
+                if (lane == 0) mbar_arrive(&S.fullL[sl]);
+            }
+            __syncwarp();
+        }
+        return;
+    }
+
+    if (warp == 2) {
+        // ================= window loader (C) =================
+        const u64 pol = l2_evict_first_policy();
+        for (u32 j = 0; j < nmine; j++) {
+            const u32 sw = j % WST, sl = j % PIPE_LSTAGES;
+            mbar_wait(&S.statsL[sl], (j / PIPE_LSTAGES) & 1);
+            mbar_wait(&S.emptyW[sw], ((j / WST) & 1) ^ 1);
+            const PipeTile &ti = S.tile[sl];
+            const PipeSeq &q = S.seq[ti.seq];
+            // slices start on multiples of 8 entries: 16-byte aligned sources for the 2-byte planes too
+            const u32 a0 = ti.bound[0] & ~7u, b0 = ti.bound[2] & ~7u, la0 = ti.bin[0] & ~7u, lb0 = ti.bin[2] & ~7u;
+            // + 8: a search reads the two aligned quads around its answer, i.e. up to 7 keys past it
+            const u32 alen = ti.bound[1] - a0 + 8, blen = ti.bound[3] - b0 + 8;
+            const u32 lalen = ti.bin[1] + 1 - la0, lblen = ti.bin[3] + 1 - lb0;
+            // bound[1] == 0xffffffff: the surveyor found invalid lefts in this tile (no index is that long)
+            const bool staged = use_tma && ti.bound[1] != 0xffffffffu && alen <= PIPE_WIN && blen <= PIPE_WIN && lalen <= PIPE_LUT &&
+                                lblen <= PIPE_LUT;
+            const bool want_pfx = want_prefixes;
+            // lane l issues copy l
+            const void *src = nullptr;
+            void *dst = nullptr;
+            u32 bytes = 0;
+            switch (lane) {
+                case 0: src = q.lut16_a + la0; dst = S.la[sw]; bytes = lalen * 2; break;
+                case 1: src = q.lut16_b + lb0; dst = S.lb[sw]; bytes = lblen * 2; break;
+                case 2: src = q.starts + a0; dst = S.ka[sw]; bytes = alen * 4; break;
+                case 3: src = q.ends_sorted + b0; dst = S.kb[sw]; bytes = blen * 4; break;
+                case 4: src = q.pfx_a + a0; dst = S.pa[sw]; bytes = want_pfx ? alen * 8 : 0; break;
+                case 5: src = q.pfx_b + b0; dst = S.pb[sw]; bytes = want_pfx ? blen * 8 : 0; break;
+                case 6: if (WIDE) { src = q.pfh_a + a0; dst = S.pah[sw]; bytes = want_pfx ? alen * 4 : 0; } break;
+                case 7: if (WIDE) { src = q.pfh_b + b0; dst = S.pbh[sw]; bytes = want_pfx ? blen * 4 : 0; } break;
+                case 8: if (NULLS) { src = q.vc16_a + a0; dst = S.va[sw]; bytes = alen * 2; } break;
+                case 9: if (NULLS) { src = q.vc16_b + b0; dst = S.vb[sw]; bytes = blen * 2; } break;
+                default: break;
+            }
+            bytes = (bytes + 15) & ~15u;
+            const u32 total_bytes = warp_sum(bytes);
+            if (lane == 0) {
+                PipeDesc &d = S.desc[sw];
+                d.g_first = ti.g_first;
+                d.vlo = ti.vlo;
+                d.vhi = ti.vhi;
+                d.seq = ti.seq;
+                d.a0 = a0;
+                d.b0 = b0;
+                d.la0 = la0;
+                d.lb0 = lb0;
+                d.staged = staged ? 1u : 0u;
+                if (staged)
+                    mbar_arrive_expect_tx(&S.fullW[sw], total_bytes);
+                else
+                    mbar_arrive(&S.fullW[sw]);
+            }
+            __syncwarp();
+            if (staged && bytes) tma_load_1d_hint(dst, src, bytes, &S.fullW[sw], pol);
+            __syncwarp();
+        }
+        return;
+    }
+
+    if (warp == 1 || (warp >= 3 && warp < 2 + PIPE_NSURV)) {
+        // ================= surveyors =================
+        const u32 sid = warp == 1 ? 0u : warp - 2;
+        for (u32 j = sid; j < nmine; j += PIPE_NSURV) {
+            const u32 sl = j % PIPE_LSTAGES;
+            mbar_wait(&S.fullL[sl], (j / PIPE_LSTAGES) & 1);
+            const PipeTile &ti = S.tile[sl];
+            const u32 vlo = ti.vlo, vhi = ti.vhi;
+            const PipeSeq &q = S.seq[ti.seq];
+            u32 mn_s = 0xffffffffu, mx_s = 0, mn_e = 0xffffffffu, mx_e = 0;
+            // widest (end - start - 1) mod 2^32: it reaches 2^31-1 iff some left has end <= start (ends <= 2^31-1)
+            u32 mx_w = 0;
+            if (vlo == 0 && vhi == TILE) {
+                const uint4 *vs = reinterpret_cast<const uint4 *>(S.ls[sl]);
+                const uint4 *ve = reinterpret_cast<const uint4 *>(S.le[sl]);
+#pragma unroll
+                for (int r = 0; r < TILE / 128; r++) {
+                    const uint4 x = vs[r * 32 + lane], y = ve[r * 32 + lane];
+                    mx_w = max(mx_w, max(max(y.x - x.x - 1, y.y - x.y - 1), max(y.z - x.z - 1, y.w - x.w - 1)));
+                    mn_s = min(mn_s, min(min(x.x, x.y), min(x.z, x.w)));
+                    mx_s = max(mx_s, max(max(x.x, x.y), max(x.z, x.w)));
+                    mn_e = min(mn_e, min(min(y.x, y.y), min(y.z, y.w)));
+                    mx_e = max(mx_e, max(max(y.x, y.y), max(y.z, y.w)));
+                }
+            } else {
+                for (u32 i = vlo + lane; i < vhi; i += 32) {
+                    const u32 x = S.ls[sl][i], y = S.le[sl][i];
+                    mx_w = max(mx_w, y - x - 1);
+                    mn_s = min(mn_s, x);
+                    mx_s = max(mx_s, x);
+                    mn_e = min(mn_e, y);
+                    mx_e = max(mx_e, y);
+                }
+            }
+            mn_e = warp_min(mn_e);
+            mx_e = warp_max(mx_e);
+            mn_s = warp_min(mn_s);
+            mx_s = warp_max(mx_s);
+            // invalid lefts cannot exist in the reference (it panics: ranges/mod.rs:30, coitrees.rs:53-54): make the call fail
+            mx_w = warp_max(mx_w);
+            const bool tile_bad = mx_w >= 0x7fffffffu || mx_e > 0x7fffffffu;
+            if (tile_bad && lane == 0) atomicOr(ctx_flags, 1u);
+            const u32 qq = lane & 3;
+            // (PIPE_UBLB also searches the starts for l.start: the low end of that window comes from min l.start)
+            const u32 v = qq == 0 ? (FAST == PIPE_UBLB ? mn_s : mn_e) : qq == 1 ? mx_e : qq == 2 ? mn_s : mx_s;
+            const u32 x = v + (qq >> 1);  // l.end for the starts table, l.start + 1 for the ends table
+            const u32 bin_new = min(x >> q.sh, q.bmax);
+            u32 bound_new = ((qq < 2) ? q.lut_a : q.lut_b)[bin_new + (qq & 1)];
+            // a tile with invalid lefts must not be staged (their bins may fall outside the slices): an impossible
+            // upper bound tells the window loader, and the consumers' global path skips those lefts
+            if (tile_bad && qq == 1) bound_new = 0xffffffffu;
+            if (lane < 4) {
+                S.tile[sl].bin[lane] = bin_new;
+                S.tile[sl].bound[lane] = bound_new;
+            }
+            __syncwarp();
+            if (lane == 0) mbar_arrive(&S.statsL[sl]);
+        }
+        return;
+    }
+
+    // ================= consumers =================
+    const u32 cw = warp - 2 - PIPE_NSURV;
+    const u32 i0 = cw * 64 + lane;  // this thread's slots inside a tile: i0 and i0 + 32 (stores of a warp are contiguous)
+    const bool skip = flags & 2;
+    const bool nostore = flags & 4;  // debug: do the arithmetic, keep the stores out (timing experiments)
+    for (u32 j = 0; j < nmine; j++) {
+        const u32 sw = j % WST, sl = j % PIPE_LSTAGES;
+        mbar_wait(&S.fullW[sw], (j / WST) & 1);
+        if (skip) {
+            __syncwarp();
+            if (lane == 0) {
+                mbar_arrive(&S.emptyW[sw]);
+                mbar_arrive(&S.emptyL[sl]);
+            }
+            continue;
+        }
+        const PipeDesc &d = S.desc[sw];
+        const PipeSeq &q = S.seq[d.seq];
+        const u32 vlo = d.vlo, vhi = d.vhi;
+        const int sh = q.sh;
+        const u32 bmax = q.bmax, fast_cmax = q.fast_cmax;
+        const double scale = q.scale;
+        const uint4 *__restrict__ nf_a = q.nf_a, *__restrict__ nf_b = q.nf_b;
+        u32 a[PIPE_LPT], b[PIPE_LPT];
+        bool okv[PIPE_LPT];
+#pragma unroll
+        for (int k = 0; k < PIPE_LPT; k++) {
+            a[k] = S.ls[sl][i0 + 32 * k];
+            b[k] = S.le[sl][i0 + 32 * k];
+            okv[k] = i0 + 32 * k >= vlo && i0 + 32 * k < vhi;
+        }
+        // (A left with end <= start or end > 2^31-1 -- impossible in the reference, which panics -- was flagged by
+        // the surveyor, which also keeps its tile off the staged path.)
+        const u32 a0 = d.a0, b0 = d.b0, la0 = d.la0, lb0 = d.lb0;
+        const SeqDev *__restrict__ sd = &seqs[d.seq];  // only dereferenced on the rare paths
+        u32 ub[PIPE_LPT], lbk[PIPE_LPT], ppk[PIPE_LPT];  // absolute positions
+        u64 pa[PIPE_LPT], pb[PIPE_LPT];
+        u32 pha[PIPE_LPT], phb[PIPE_LPT];  // WIDE: bits 64..95 of the prefixes
+        u32 nv16[PIPE_LPT];                // NULLS: (valid-score count of the group) mod 2^16
+#pragma unroll
+        for (int k = 0; k < PIPE_LPT; k++) ppk[k] = pha[k] = phb[k] = nv16[k] = 0;
+        if (d.staged) {
+            const u32 *__restrict__ KA = S.ka[sw];
+            const u32 *__restrict__ KB = S.kb[sw];
+            const u32 a16 = a0 & 0xffffu, b16 = b0 & 0xffffu;
+            u32 pA[PIPE_LPT], pB[PIPE_LPT], cA[PIPE_LPT], cB[PIPE_LPT];
+            // bin -> first position of the bin relative to the staged slice (a window holds < 65536 keys, so the low
+            // halves of the table entries are enough); invalid slots scan with x = 0
+#pragma unroll
+            for (int k = 0; k < PIPE_LPT; k++) {
+                const u32 ba = min(b[k] >> sh, bmax), bb = min((a[k] + 1) >> sh, bmax);
+                pA[k] = okv[k] ? ((u32)S.la[sw][ba - la0] - a16) & 0xffffu : 0u;
+                pB[k] = okv[k] ? ((u32)S.lb[sw][bb - lb0] - b16) & 0xffffu : 0u;
+            }
+            // one unconditional round per search: the 8 keys of the two aligned quads around the bin's first
+            // position, two 128-bit loads.  Keys before that position are < x by construction, so the answer
+            // is (quad base) + #(keys < x) unless all 8 are smaller (a crowded bin: finish with the scan).
+#pragma unroll
+            for (int k = 0; k < PIPE_LPT; k++) {
+                const u32 xa = okv[k] ? b[k] : 0u, xb = okv[k] ? a[k] + 1 : 0u;
+                const u32 qa = pA[k] & ~3u, qb = pB[k] & ~3u;
+                cA[k] = count8_below(KA, qa, xa);
+                cB[k] = count8_below(KB, qb, xb);
+                pA[k] = okv[k] ? qa + cA[k] : 0u;
+                pB[k] = okv[k] ? qb + cB[k] : 0u;
+            }
+            if (FAST == PIPE_UBLB) {
+                // third search: #{start < l.start}, same scheme on the starts window
+#pragma unroll
+                for (int k = 0; k < PIPE_LPT; k++) {
+                    const u32 xp = okv[k] ? a[k] : 0u;
+                    u32 pP = okv[k] ? ((u32)S.la[sw][min(a[k] >> sh, bmax) - la0] - a16) & 0xffffu : 0u;
+                    const u32 qp = pP & ~3u;
+                    const u32 cP = count8_below(KA, qp, xp);
+                    pP = okv[k] ? qp + cP : 0u;
+                    if (cP == 8) pP = scan_lower_bound(KA, pP, a[k]);
+                    ppk[k] = a0 + pP;
+                }
+            }
+#pragma unroll
+            for (int k = 0; k < PIPE_LPT; k++) {
+                if (cA[k] == 8) pA[k] = scan_lower_bound(KA, pA[k], b[k]);      // rare: a crowded bin
+                if (cB[k] == 8) pB[k] = scan_lower_bound(KB, pB[k], a[k] + 1);
+                pa[k] = want_prefixes ? S.pa[sw][pA[k]] : 0ull;
+                pb[k] = want_prefixes ? S.pb[sw][pB[k]] : 0ull;
+                if (WIDE && want_prefixes) {
+                    pha[k] = S.pah[sw][pA[k]];
+                    phb[k] = S.pbh[sw][pB[k]];
+                }
+                if (NULLS) nv16[k] = ((u32)S.va[sw][pA[k]] - (u32)S.vb[sw][pB[k]]) & 0xffffu;
+                ub[k] = a0 + pA[k];
+                lbk[k] = b0 + pB[k];
+            }
+        } else {
+            // the tile's windows do not fit the ring slot: per-left searches in global memory
+#pragma unroll
+            for (int k = 0; k < PIPE_LPT; k++) {
+                ub[k] = lbk[k] = 0;
+                pa[k] = pb[k] = 0;
+                if (!okv[k]) continue;
+                if (b[k] <= a[k] || b[k] > 0x7fffffffu) continue;  // invalid left (flagged by the surveyor): an empty group
+                const u32 xa = b[k], xb = a[k] + 1;
+                ub[k] = scan_lower_bound(q.starts, q.lut_a[min(xa >> sh, bmax)], xa);
+                lbk[k] = scan_lower_bound(q.ends_sorted, q.lut_b[min(xb >> sh, bmax)], xb);
+                if (want_prefixes) {
+                    pa[k] = q.pfx_a[ub[k]];
+                    pb[k] = q.pfx_b[lbk[k]];
+                    if (WIDE) {
+                        pha[k] = q.pfh_a[ub[k]];
+                        phb[k] = q.pfh_b[lbk[k]];
+                    }
+                }
+                if (NULLS) nv16[k] = ((u32)q.vc16_a[ub[k]] - (u32)q.vc16_b[lbk[k]]) & 0xffffu;
+                if (FAST == PIPE_UBLB) ppk[k] = scan_lower_bound(q.starts, q.lut_a[min(a[k] >> sh, bmax)], a[k]);
+            }
+        }
+        // ---- everything this warp needs from the two ring slots is in registers now: hand them back
+        // before the arithmetic and the stores, so the loaders can refill them meanwhile
+        const u64 g0 = d.g_first + i0;
+        __syncwarp();
+        if (lane == 0) {
+            mbar_arrive(&S.emptyW[sw]);
+            mbar_arrive(&S.emptyL[sl]);
+        }
+        // ---- count, number of members that carry a score, exact sum
+        u32 cnt[PIPE_LPT], nval[PIPE_LPT];
+        double sum[PIPE_LPT];
+#pragma unroll
+        for (int k = 0; k < PIPE_LPT; k++) {
+            const u32 c = ub[k] - lbk[k];
+            cnt[k] = c;
+            nval[k] = c;
+            if (NULLS) nval[k] = c < 65536u ? nv16[k] : (okv[k] ? sd->vcnt_a[ub[k]] - sd->vcnt_b[lbk[k]] : 0u);
+            sum[k] = 0.0;
+            if (!want_prefixes) continue;
+            if (!WIDE) {
+                if (c < fast_cmax) {
+                    sum[k] = (double)(i64)(pa[k] - pb[k]) * scale;
+                } else {
+                    const i128 ba128 = sd->base_a[ub[k] >> GRB_BASE_SHIFT], bb128 = sd->base_b[lbk[k] >> GRB_BASE_SHIFT];
+                    const i128 PA = ba128 + (i128)(i64)(pa[k] - (u64)(u128)ba128);
+                    const i128 PB = bb128 + (i128)(i64)(pb[k] - (u64)(u128)bb128);
+                    sum[k] = fx_to_double(PA - PB, sd->e0);
+                }
+            } else {
+                if (c < fast_cmax) {
+                    const u64 lo = pa[k] - pb[k];
+                    const u32 hi = pha[k] - phb[k] - (pa[k] < pb[k] ? 1u : 0u);
+                    const i64 lo_s = (i64)lo;
+                    // most sums of modest groups fit 63 bits even in the wide format: one conversion instead of the 128-bit path
+                    if (hi == (u32)(lo_s >> 63))
+                        sum[k] = (double)lo_s * scale;
+                    else
+                        sum[k] = fx_to_double(sext96(hi, lo), sd->e0);
+                } else {
+                    const u128 m96 = (((u128)1) << 96) - 1;
+                    const i128 ba128 = sd->base_a[ub[k] >> GRB_BASE_SHIFT], bb128 = sd->base_b[lbk[k] >> GRB_BASE_SHIFT];
+                    const u128 da = ((((u128)pha[k] << 64) | pa[k]) - (u128)ba128) & m96;
+                    const u128 db = ((((u128)phb[k] << 64) | pb[k]) - (u128)bb128) & m96;
+                    const i128 PA = ba128 + sext96((u32)(da >> 64), (u64)da);
+                    const i128 PB = bb128 + sext96((u32)(db >> 64), (u64)db);
+                    sum[k] = fx_to_double(PA - PB, sd->e0);
+                }
+            }
+            if (nf_a != nullptr && okv[k]) {
+                const uint4 na = nf_a[ub[k]], nb = nf_b[lbk[k]];
+                sum[k] = nf_rule(sum[k], na.x - nb.x, na.y - nb.y, na.z - nb.z);
+            }
+        }
+        // ---- outputs
+        if (FAST == PIPE_UBLB) {
+#pragma unroll
+            for (int k = 0; k < PIPE_LPT; k++)
+                if (okv[k]) {
+                    mops.ub[g0 + 32 * k] = ub[k];
+                    mops.pp[g0 + 32 * k] = ppk[k];
+                    mops.lb[g0 + 32 * k] = lbk[k];
+                }
+        }
+        if (FAST == PIPE_MULTI || FAST == PIPE_UBLB) {
+            // several reductions from the same (count, exact sum): row-major out[left][column]
+#pragma unroll
+            for (int k = 0; k < PIPE_LPT; k++) {
+                if (!okv[k]) continue;
+                const double mean = nval[k] ? sum[k] / (double)nval[k] : 0.0;
+                double *po = out + (g0 + 32 * k) * (u64)mops.k;
+                u8 *pv = out_valid + (g0 + 32 * k) * (u64)mops.k;
+                for (int col = 0; col < mops.k; col++) {
+                    const int op = mops.ops[col];
+                    if (FAST == PIPE_UBLB && op != GRB_OP_COUNT && op != GRB_OP_MEAN && op != GRB_OP_SUM && op != GRB_OP_SUM_NOT_EMPTY)
+                        continue;  // a member reduction / closed form: the kernels that follow own this column
+                    const double rr = op == GRB_OP_COUNT ? (double)cnt[k] : op == GRB_OP_MEAN ? mean : sum[k];
+                    const u8 vv = (op == GRB_OP_SUM || op == GRB_OP_COUNT) ? (u8)1 : (u8)(nval[k] != 0);
+                    __stcs(po + col, rr);
+                    pv[col] = vv;
+                }
+            }
+            continue;
+        }
+        double r[PIPE_LPT];
+        bool v[PIPE_LPT];
+#pragma unroll
+        for (int k = 0; k < PIPE_LPT; k++) {
+            if (FAST == GRB_OP_COUNT) {
+                r[k] = (double)cnt[k];
+                v[k] = true;
+            } else if (FAST == GRB_OP_SUM) {
+                r[k] = sum[k];
+                v[k] = true;
+            } else if (FAST == GRB_OP_SUM_NOT_EMPTY) {
+                r[k] = sum[k];
+                v[k] = nval[k] != 0;
+            } else {
+                v[k] = nval[k] != 0;
+                r[k] = v[k] ? sum[k] / (double)nval[k] : 0.0;
+            }
+        }
+        if (nostore && r[0] != 1.2345e300) continue;
+#pragma unroll
+        for (int k = 0; k < PIPE_LPT; k++) {
+            // a warp's 32 results are contiguous: 256-byte streaming stores (the results are not read back here)
+            if (okv[k]) __stcs(out + g0 + 32 * k, r[k]);
+            if (mops.valid_bits == nullptr) {
+                if (okv[k]) out_valid[g0 + 32 * k] = v[k] ? (u8)1 : (u8)0;
+            } else {
+                const u32 live = __ballot_sync(GRB_FULL, okv[k]);
+                const u32 bits = __ballot_sync(GRB_FULL, okv[k] && v[k]);
+                if (lane == 0 && live) {
+                    u32 *w = mops.valid_bits + ((d.g_first + cw * 64 + 32 * k) >> 5);  // tiles start on multiples of 1024 lefts
+                    if (live == GRB_FULL) {
+                        __stcs(w, bits);
+                    } else {
+                        // a seqname boundary inside the word: the neighbouring tile owns the other bits
+                        atomicAnd(w, ~live);
+                        atomicOr(w, bits);
+                    }
+                }
+            }
+        }
+    }
+}
+
+template <int FAST, int VAR>
+int launch_var(grb_ctx *ctx, const Batch &b, int s0, int s1, const u32 *ls, const u32 *le, const TileOut &o, u32 *valid_bits) {
+    using Smem = PipeSmemT<VAR>;
+    // the opt-in to > 48 KB of dynamic shared memory is per device: remembered per device, not per process
+    static bool configured[64] = {};
+    if (ctx->device < 0 || ctx->device >= 64 || !configured[ctx->device]) {
+        GRB_CUDA(ctx, cudaFuncSetAttribute(k_map_pipe<FAST, VAR>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(Smem)));
+        if (ctx->device >= 0 && ctx->device < 64) configured[ctx->device] = true;
+    }
+    const int flags = (ctx->tile_mode ? 1 : 0) | (ctx->pipe_mode == 2 ? 2 : 0) | (ctx->pipe_mode == 3 ? 4 : 0);
+    const u32 t0 = b.host_tile_begin[s0], t1 = b.host_tile_begin[s1];
+    if (t1 == t0) return GRB_OK;
+    u32 grid = (u32)ctx->sm_count;
+    if (grid > t1 - t0) grid = t1 - t0;
+    PipeOps mops;
+    mops.k = o.k;
+    for (int c = 0; c < GRB_MAX_OPS; c++) mops.ops[c] = c < o.k ? o.ops[c] : 0;
+    mops.ub = o.ub;
+    mops.pp = o.pp;
+    mops.lb = o.lb;
+    mops.need_pfx = o.need_sum;
+    mops.valid_bits = valid_bits;
+    k_map_pipe<FAST, VAR><<<grid, PIPE_THREADS, sizeof(Smem), ctx->stream>>>(b.seqs + s0, s1 - s0, t0, t1 - t0, ls, le, o.out, o.out_valid, flags,
+                                                                          o.flags, mops);
+    GRB_LAUNCHED(ctx);
+    return GRB_OK;
+}
+
+template <int FAST>
+int launch_fast(grb_ctx *ctx, const Batch &b, int s0, int s1, int var, const u32 *ls, const u32 *le, const TileOut &o, u32 *valid_bits) {
+    switch (var) {
+        case 0: return launch_var<FAST, 0>(ctx, b, s0, s1, ls, le, o, valid_bits);
+        case 1: return launch_var<FAST, 1>(ctx, b, s0, s1, ls, le, o, valid_bits);
+        case 2: return launch_var<FAST, 2>(ctx, b, s0, s1, ls, le, o, valid_bits);
+        default: return launch_var<FAST, 3>(ctx, b, s0, s1, ls, le, o, valid_bits);
+    }
+}
+
+}  // namespace
+
+int grb_launch_pipe(grb_ctx *ctx, const Batch &b, const u32 *ls, const u32 *le, const TileOut &o, int fast, u32 *valid_bits) {
+    if (b.ntiles == 0) return GRB_OK;
+    // Runs of consecutive seqnames that need the same variant (absent / empty seqnames fit any), at most PIPE_MAXSEQ
+    // per launch: the kernel keeps its seqnames' descriptors in shared memory.
+    int s0 = 0;
+    while (s0 < b.nseq) {
+        int var = -1, s1 = s0;
+        while (s1 < b.nseq && s1 - s0 < PIPE_MAXSEQ) {
+            const int v = b.var[s1];
+            if (v >= 0 && var >= 0 && v != var) break;
+            if (v >= 0) var = v;
+            s1++;
+        }
+        if (var < 0) var = 0;
+        // counts alone need no score planes at all
+        if (fast == GRB_OP_COUNT || ((fast == PIPE_UBLB || fast == PIPE_MULTI) && !o.need_sum)) var = 0;
+        int rc;
+        switch (fast) {
+            case GRB_OP_MEAN: rc = launch_fast<GRB_OP_MEAN>(ctx, b, s0, s1, var, ls, le, o, valid_bits); break;
+            case GRB_OP_SUM: rc = launch_fast<GRB_OP_SUM>(ctx, b, s0, s1, var, ls, le, o, valid_bits); break;
+            case GRB_OP_SUM_NOT_EMPTY: rc = launch_fast<GRB_OP_SUM_NOT_EMPTY>(ctx, b, s0, s1, var, ls, le, o, valid_bits); break;
+            case GRB_OP_COUNT: rc = launch_var<GRB_OP_COUNT, 0>(ctx, b, s0, s1, ls, le, o, valid_bits); break;
+            case PIPE_MULTI: rc = launch_fast<PIPE_MULTI>(ctx, b, s0, s1, var, ls, le, o, nullptr); break;
+            case PIPE_UBLB: rc = launch_fast<PIPE_UBLB>(ctx, b, s0, s1, var, ls, le, o, nullptr); break;
+            default: return grb_fail(ctx, GRB_ERR_INVALID_ARG, "pipe: unknown reduction %d", fast);
+        }
+        if (rc != GRB_OK) return rc;
+        s0 = s1;
+    }
+    return GRB_OK;
+}

@@ -23,147 +23,20 @@
 
 #include <vector>
 
-#include "common.cuh"
+#include "tilelib.cuh"
 
 namespace {
 
-constexpr int TILE_TPB = 256;
-constexpr int TILE_LPT = 4;
-constexpr int TILE = TILE_TPB * TILE_LPT;
-constexpr int TILE_SHIFT = 10;
-static_assert(TILE == 1 << TILE_SHIFT, "tile size");
-constexpr u32 WIN_CAP = 2048;  // keys per staged window (2 x 8 KB of shared memory)
-constexpr u32 LUT_CAP = 1024;  // bin-table entries per staged slice (2 x 4 KB)
-
-enum { M_COUNTS = 1, M_KEEP = 2, M_UBLB = 4, M_MAP = 8 };
-
-struct TileOut {
-    u32 *counts;
-    u8 *keep;
-    unsigned long long *n_kept;
-    int anti;
-    u32 *ub, *lb, *pp;  // M_UBLB: #{start < l.end}, #{end <= l.start}, #{start < l.start}
-    double *out;
-    u8 *out_valid;
-    int k;
-    int need_sum;
-    int ops[GRB_MAX_OPS];
-    u32 *flags;  // context flag word (bit 0: invalid left range seen)
-};
-
-// ---- PTX: mbarrier + TMA 1-D bulk copy ---------------------------------------
-
-__device__ __forceinline__ u32 smem_addr(const void *p) { return (u32)__cvta_generic_to_shared(p); }
-
-__device__ __forceinline__ void mbar_init(u64 *bar, u32 count) {
-    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_addr(bar)), "r"(count) : "memory");
-    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
-}
-__device__ __forceinline__ void mbar_arrive_expect_tx(u64 *bar, u32 bytes) {
-    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_addr(bar)), "r"(bytes) : "memory");
-}
-__device__ __forceinline__ void tma_load_1d(void *dst, const void *src, u32 bytes, u64 *bar) {
-    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(smem_addr(dst)),
-                 "l"(src), "r"(bytes), "r"(smem_addr(bar))
-                 : "memory");
-}
-// Same copy with an L2 evict-first policy: for data that is read once per pass (it should not push the
-// prefix bases / descriptors / other CTAs' overlapping slices out of L2).
-__device__ __forceinline__ u64 l2_evict_first_policy() {
-    u64 pol;
-    asm volatile("createpolicy.fractional.L2::evict_first.b64 %0, 1.0;" : "=l"(pol));
-    return pol;
-}
-__device__ __forceinline__ void tma_load_1d_hint(void *dst, const void *src, u32 bytes, u64 *bar, u64 policy) {
-    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes.L2::cache_hint [%0], [%1], %2, [%3], %4;" ::"r"(
-                     smem_addr(dst)),
-                 "l"(src), "r"(bytes), "r"(smem_addr(bar)), "l"(policy)
-                 : "memory");
-}
-__device__ __forceinline__ bool mbar_try_wait(u64 *bar, u32 parity) {
-    u32 ok;
-    asm volatile(
-        "{\n"
-        ".reg .pred P1;\n"
-        "mbarrier.try_wait.parity.shared::cta.b64 P1, [%1], %2;\n"
-        "selp.u32 %0, 1, 0, P1;\n"
-        "}\n"
-        : "=r"(ok)
-        : "r"(smem_addr(bar)), "r"(parity)
-        : "memory");
-    return ok != 0;
-}
-// Poll, and sleep between polls: a waiting warp should not eat the issue slots the working warps need.
-__device__ __forceinline__ void mbar_wait(u64 *bar, u32 parity) {
-    if (mbar_try_wait(bar, parity)) return;
-    while (!mbar_try_wait(bar, parity)) __nanosleep(64);
-}
-
-// ---- searches -------------------------------------------------------------------
-
-// #keys < x in the answer interval [lo, hi] of a sorted array (shared or global).
-__device__ __forceinline__ u32 bounded_lower_bound(const u32 *__restrict__ keys, u32 lo, u32 hi, u32 x) {
-    while (lo < hi) {
-        u32 mid = (lo + hi) >> 1;
-        if (keys[mid] < x)
-            lo = mid + 1;
-        else
-            hi = mid;
+// exact 128-bit prefix of the scores at position j (start order: pfx_a / pfh_a / base_a, end order: pfx_b / pfh_b / base_b)
+__device__ __forceinline__ i128 exact_prefix(const u64 *__restrict__ pfx, const u32 *__restrict__ pfh, const i128 *__restrict__ base, int mode,
+                                             u32 j) {
+    if (mode == GRB_SUM_WIDE) return base[j];
+    const i128 b = base[j >> GRB_BASE_SHIFT];
+    if (mode == GRB_SUM_WIDE96) {
+        const u128 d = ((((u128)pfh[j] << 64) | pfx[j]) - (u128)b) & ((((u128)1) << 96) - 1);
+        return b + sext96((u32)(d >> 64), (u64)d);
     }
-    return lo;
-}
-
-
-// #keys < x, scanning forward from a bin's first position `lo` (<= answer) four keys at a time.
-// No upper bound is needed: `keys` is sorted and every key at or after the end of the searched
-// slice is >= x (real keys of later bins, then the 0xffffffff sentinels that pad every key
-// array), so the predicates are a run of trues followed by falses and the scan always stops.
-// Bins hold ~4-8 keys; the four loads of a round are independent.
-__device__ __forceinline__ u32 scan_lower_bound(const u32 *__restrict__ keys, u32 lo, u32 x) {
-    while (true) {
-        const u32 c = (keys[lo] < x ? 1u : 0u) + (keys[lo + 1] < x ? 1u : 0u) + (keys[lo + 2] < x ? 1u : 0u) +
-                      (keys[lo + 3] < x ? 1u : 0u);
-        if (c < 4) return lo + c;
-        lo += 4;
-    }
-}
-
-__device__ __forceinline__ int find_seq_by_tile(const u32 *__restrict__ tile_begin, int nseq, u32 t) {
-    int lo = 0, hi = nseq;
-    while (hi - lo > 1) {
-        int mid = (lo + hi) >> 1;
-        if (tile_begin[mid] <= t)
-            lo = mid;
-        else
-            hi = mid;
-    }
-    return lo;
-}
-
-__device__ __forceinline__ int find_seq_by_left(const SeqDev *__restrict__ seqs, int nseq, u64 g) {
-    int lo = 0, hi = nseq;
-    while (hi - lo > 1) {
-        int mid = (lo + hi) >> 1;
-        if (seqs[mid].left_begin <= g)
-            lo = mid;
-        else
-            hi = mid;
-    }
-    return lo;
-}
-
-// Exact sum of the group [lb, ub) from the compact prefixes.  Small groups (the usual case): the
-// sum fits 63 bits, so the difference of the prefixes mod 2^64 IS the sum; otherwise rebuild the
-// two exact 128-bit prefixes from the per-256 bases.  Either way one rounding to f64.
-__device__ __forceinline__ double compact_group_sum(const u64 *__restrict__ pfx_a, const u64 *__restrict__ pfx_b,
-                                                    const i128 *__restrict__ base_a, const i128 *__restrict__ base_b, u32 ub,
-                                                    u32 lb, u32 fast_cmax, double scale, int e0) {
-    const u64 pa = pfx_a[ub], pb = pfx_b[lb];
-    if (ub - lb < fast_cmax) return (double)(i64)(pa - pb) * scale;
-    const i128 ba = base_a[ub >> GRB_BASE_SHIFT], bb = base_b[lb >> GRB_BASE_SHIFT];
-    const i128 PA = ba + (i128)(i64)(pa - (u64)(u128)ba);
-    const i128 PB = bb + (i128)(i64)(pb - (u64)(u128)bb);
-    return fx_to_double(PA - PB, e0);
+    return b + (i128)(i64)(pfx[j] - (u64)(u128)b);
 }
 
 // ---- the tile kernel --------------------------------------------------------------
@@ -419,11 +292,14 @@ __global__ void __launch_bounds__(TILE_TPB) k_tile(const SeqDev *__restrict__ se
             if (has_nulls) nvalid = sd->vcnt_a[ub[k]] - sd->vcnt_b[lb[k]];
             if (!has_scores) nvalid = 0;
             double sum = 0.0;
-            if (o.need_sum) {
-                if (mode == GRB_SUM_COMPACT)
-                    sum = compact_group_sum(sd->pfx_a, sd->pfx_b, sd->base_a, sd->base_b, ub[k], lb[k], sd->fast_cmax, sd->scale, sd->e0);
-                else if (mode == GRB_SUM_WIDE)
-                    sum = fx_to_double(sd->base_a[ub[k]] - sd->base_b[lb[k]], sd->e0);
+            if (o.need_sum && mode != GRB_SUM_SWEEP && has_scores) {
+                sum = fx_to_double(exact_prefix(sd->pfx_a, sd->pfh_a, sd->base_a, mode, ub[k]) -
+                                       exact_prefix(sd->pfx_b, sd->pfh_b, sd->base_b, mode, lb[k]),
+                                   sd->e0);
+                if (sd->nf_a) {
+                    const uint4 na = sd->nf_a[ub[k]], nb = sd->nf_b[lb[k]];
+                    sum = nf_rule(sum, na.x - nb.x, na.y - nb.y, na.z - nb.z);
+                }
             }
             for (int c = 0; c < o.k; c++) {
                 const int op = o.ops[c];
@@ -468,8 +344,6 @@ __global__ void __launch_bounds__(TILE_TPB) k_tile(const SeqDev *__restrict__ se
         }
     }
 }
-
-#include "map_pipe.cuh"
 
 // ---- the sweep kernels ----------------------------------------------------------------
 
@@ -687,13 +561,6 @@ __global__ void __launch_bounds__(256) k_minmax(const SeqDev *__restrict__ seqs,
     }
 }
 
-// exact 128-bit prefix of the scores at position j (start order: pfx_a / base_a, end order: pfx_b / base_b)
-__device__ __forceinline__ i128 exact_prefix(const u64 *__restrict__ pfx, const i128 *__restrict__ base, int mode, u32 j) {
-    if (mode == GRB_SUM_WIDE) return base[j];
-    const i128 b = base[j >> GRB_BASE_SHIFT];
-    return b + (i128)(i64)(pfx[j] - (u64)(u128)b);
-}
-
 // WEIGHTED_MEAN (examples/weighted_mean.rs:4-31: sum(score * overlap width) / sum(overlap width) over the rights that
 // carry a score, 0.0 if there is none) in closed form, like k_overlap_bp: no member is visited and the weighted sum is
 // exact before it is rounded once.
@@ -719,8 +586,8 @@ __global__ void __launch_bounds__(256) k_weighted_mean(const SeqDev *__restrict_
         }
         const u32 a2 = lo;  // #{end <= l.end}
         const int mode = sd->sum_mode;
-        const i128 pa_u = exact_prefix(sd->pfx_a, sd->base_a, mode, u), pa_p = exact_prefix(sd->pfx_a, sd->base_a, mode, p);
-        const i128 pb_a2 = exact_prefix(sd->pfx_b, sd->base_b, mode, a2), pb_l = exact_prefix(sd->pfx_b, sd->base_b, mode, l);
+        const i128 pa_u = exact_prefix(sd->pfx_a, sd->pfh_a, sd->base_a, mode, u), pa_p = exact_prefix(sd->pfx_a, sd->pfh_a, sd->base_a, mode, p);
+        const i128 pb_a2 = exact_prefix(sd->pfx_b, sd->pfh_b, sd->base_b, mode, a2), pb_l = exact_prefix(sd->pfx_b, sd->pfh_b, sd->base_b, mode, l);
         const i128 g_end = sd->wsum_b[a2] - sd->wsum_a[u] + (i128)b * (pa_u - pb_a2);
         const i128 g_start = sd->wsum_b[l] - sd->wsum_a[p] + (i128)a * (pa_p - pb_l);
         const i128 wsum = g_end - g_start;
@@ -755,22 +622,14 @@ __global__ void k_scatter_kept(const u8 *__restrict__ keep, const u64 *__restric
 
 // ---- host orchestration -------------------------------------------------------------------
 
-struct Batch {
-    const SeqDev *seqs = nullptr;
-    const u32 *tile_begin = nullptr;
-    u32 ntiles = 0;
-    u64 total = 0;
-    int nseq = 0;
-    bool uniform = true;  // every present seqname: scores, no None, compact prefixes
-    std::vector<u32> host_tile_begin;  // nseq + 1
-};
-
 int make_batch(grb_ctx *ctx, const grb_index *const *idx, const u64 *left_offsets, int nseq, Batch *b) {
     if (nseq <= 0) return grb_fail(ctx, GRB_ERR_INVALID_ARG, "batch: nseq must be >= 1");
     std::vector<SeqDev> h((size_t)nseq);
     std::vector<u32> tb((size_t)nseq + 1);
     u64 tiles = 0;
+    b->pipeable = true;
     b->uniform = true;
+    b->var.assign((size_t)nseq, -1);
     const u32 *zeros = (const u32 *)ctx->zeros;
     for (int s = 0; s < nseq; s++) {
         if (left_offsets[s + 1] < left_offsets[s]) return grb_fail(ctx, GRB_ERR_INVALID_ARG, "batch: left_offsets must be non-decreasing");
@@ -790,8 +649,16 @@ int make_batch(grb_ctx *ctx, const grb_index *const *idx, const u64 *left_offset
             d.vcnt_b = ix->vcnt_b;
             d.pfx_a = ix->pfx_a;
             d.pfx_b = ix->pfx_b;
+            d.pfh_a = ix->pfh_a;
+            d.pfh_b = ix->pfh_b;
+            d.nf_a = ix->nf_a;
+            d.nf_b = ix->nf_b;
+            d.vc16_a = ix->vc16_a;
+            d.vc16_b = ix->vc16_b;
             d.lut_a = ix->lut_a;
             d.lut_b = ix->lut_b;
+            d.lut16_a = ix->lut16_a;
+            d.lut16_b = ix->lut16_b;
             d.rank_a = ix->rank_a;
             d.score_sorted = ix->score_sorted;
             d.fb = ix->fb;
@@ -817,14 +684,21 @@ int make_batch(grb_ctx *ctx, const grb_index *const *idx, const u64 *left_offset
             d.has_nulls = ix->has_nulls;
             d.has_scores = ix->has_scores;
             d.fast_cmax = 0;
-            if (d.sum_mode == GRB_SUM_COMPACT) {
-                int room = 63 - ix->width;  // a group of fewer than 2^room members sums to < 2^63
+            if (d.sum_mode == GRB_SUM_COMPACT || d.sum_mode == GRB_SUM_WIDE96) {
+                // a group of fewer than 2^room members sums to < 2^63 (2^95): the wrapped prefixes suffice
+                int room = (d.sum_mode == GRB_SUM_COMPACT ? 63 : 95) - ix->width;
                 d.fast_cmax = room >= 31 ? 0x7fffffffu : (1u << room);
             }
-            if (!(ix->has_scores && !ix->has_nulls && ix->sum_mode == GRB_SUM_COMPACT)) b->uniform = false;
+            if (!(ix->has_scores && !ix->has_nulls && !ix->has_nonfinite && ix->sum_mode == GRB_SUM_COMPACT)) b->uniform = false;
+            if (ix->has_scores && (ix->sum_mode == GRB_SUM_COMPACT || ix->sum_mode == GRB_SUM_WIDE96))
+                b->var[s] = (ix->has_nulls ? PIPE_VAR_NULLS : 0) | (ix->sum_mode == GRB_SUM_WIDE96 ? PIPE_VAR_WIDE : 0);
+            else
+                b->pipeable = false;  // no scores / full 128-bit prefixes / member sums: the tile kernel (and the sweep)
         } else {
             // absent seqname / empty index: every group is empty; all tables read as zeros
             d.lut_a = d.lut_b = zeros;
+            d.lut16_a = d.lut16_b = d.vc16_a = d.vc16_b = (const u16 *)zeros;
+            d.pfh_a = d.pfh_b = zeros;
             d.starts = d.ends = d.ends_sorted = zeros + 256;  // sentinel keys: every forward scan stops at once
             d.pfx_a = d.pfx_b = (const u64 *)zeros;
             d.base_a = d.base_b = (const i128 *)zeros;
@@ -878,6 +752,19 @@ int make_batch(grb_ctx *ctx, const grb_index *const *idx, const u64 *left_offset
     return GRB_OK;
 }
 
+// Which pipelined kernel answers a plain map call (no member reduction, no closed form): the op code of a single
+// reduction, PIPE_MULTI for several, -1 when the batch or the reductions need the tile kernel.
+int map_pipe_fast(const Batch &b, const TileOut &o) {
+    bool need_scores = false;
+    for (int c = 0; c < o.k; c++) {
+        const int op = o.ops[c];
+        if (op != GRB_OP_SUM && op != GRB_OP_SUM_NOT_EMPTY && op != GRB_OP_MEAN && op != GRB_OP_COUNT) return -1;
+        need_scores |= op != GRB_OP_COUNT;
+    }
+    if (need_scores && !b.pipeable) return -1;
+    return o.k == 1 ? o.ops[0] : PIPE_MULTI;
+}
+
 template <int MODE, int FAST>
 int launch_tile(grb_ctx *ctx, const Batch &b, const u32 *ls, const u32 *le, const TileOut &o) {
     if (b.ntiles == 0) return GRB_OK;
@@ -886,70 +773,18 @@ int launch_tile(grb_ctx *ctx, const Batch &b, const u32 *ls, const u32 *le, cons
     return GRB_OK;
 }
 
-template <int FAST>
-int launch_pipe(grb_ctx *ctx, const Batch &b, const u32 *ls, const u32 *le, const TileOut &o) {
-    if (b.ntiles == 0) return GRB_OK;
-    // the opt-in to > 48 KB of dynamic shared memory is per device: remembered per device, not per process
-    static bool configured[64] = {};
-    if (ctx->device < 0 || ctx->device >= 64 || !configured[ctx->device]) {
-        GRB_CUDA(ctx, cudaFuncSetAttribute(k_map_pipe<FAST>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(PipeSmem)));
-        if (ctx->device >= 0 && ctx->device < 64) configured[ctx->device] = true;
-    }
-    const int flags = (ctx->tile_mode ? 1 : 0) | (ctx->pipe_mode == 2 ? 2 : 0) | (ctx->pipe_mode == 3 ? 4 : 0);
-    // the kernel keeps its seqnames' descriptors in shared memory: at most PIPE_MAXSEQ per launch
-    for (int s0 = 0; s0 < b.nseq; s0 += PIPE_MAXSEQ) {
-        const int s1 = s0 + PIPE_MAXSEQ < b.nseq ? s0 + PIPE_MAXSEQ : b.nseq;
-        const u32 t0 = b.host_tile_begin[s0], t1 = b.host_tile_begin[s1];
-        if (t1 == t0) continue;
-        u32 grid = (u32)ctx->sm_count;
-        if (grid > t1 - t0) grid = t1 - t0;
-        PipeOps mops;
-        mops.k = o.k;
-        for (int c = 0; c < GRB_MAX_OPS; c++) mops.ops[c] = c < o.k ? o.ops[c] : 0;
-        mops.ub = o.ub;
-        mops.pp = o.pp;
-        mops.lb = o.lb;
-        mops.need_pfx = o.need_sum;
-        k_map_pipe<FAST><<<grid, PIPE_THREADS, sizeof(PipeSmem), ctx->stream>>>(b.seqs + s0, s1 - s0, t0, t1 - t0, ls, le, o.out, o.out_valid,
-                                                                              flags, o.flags, mops);
-        GRB_LAUNCHED(ctx);
-    }
-    return GRB_OK;
-}
-
-// MAP launch: the single-reduction fast kernels when the batch is uniform, else the general one.
+// MAP launch: the pipelined kernel when the prefix sums of every seqname can be staged, else the tile kernels.
+// valid_bits (single-reduction pipelined launches only; the caller checked): validity as bits instead of bytes.
 template <int MODE>
-int launch_map(grb_ctx *ctx, const Batch &b, const u32 *ls, const u32 *le, const TileOut &o) {
-    const char *up = getenv("GRB_UBLB_PIPE");  // debug: 1 = the pipeline for every (ub, pp, lb) pass, 0 = never
-    const bool ublb_pipe = up ? atoi(up) != 0 : o.need_sum != 0;
-    if (MODE == (M_MAP | M_UBLB) && ctx->pipe_mode == 1 && ublb_pipe && (b.uniform || !o.need_sum) && b.ntiles >= 4u * (u32)ctx->sm_count) {
-        // The counts for the member sweep / the closed forms, with the columns the prefix sums answer, in the pipeline
-        // (sums need a uniform batch: scores, no None, compact prefixes).  Measured at 100M x 100M: with sums beside the
-        // members (config C3) the pipeline saves 0.8 ms; for counts alone the tile kernel is as fast (3.1 vs 3.3 ms for
-        // `min`), so it keeps those.
-        return launch_pipe<PIPE_UBLB>(ctx, b, ls, le, o);
+int launch_map(grb_ctx *ctx, const Batch &b, const u32 *ls, const u32 *le, const TileOut &o, u32 *valid_bits = nullptr) {
+    const bool ublb_pipe = ctx->ublb_pipe < 0 ? o.need_sum != 0 : ctx->ublb_pipe != 0;
+    if (MODE == (M_MAP | M_UBLB) && ctx->pipe_mode == 1 && ublb_pipe && (b.pipeable || !o.need_sum) && b.ntiles >= 4u * (u32)ctx->sm_count) {
+        // The counts for the member sweep / the closed forms, with the columns the prefix sums answer, in the pipeline.
+        // Measured at 100M x 100M: with sums beside the members (config C3) the pipeline saves 0.8 ms; for counts alone
+        // the tile kernel is as fast (3.1 vs 3.3 ms for `min`), so it keeps those.
+        return grb_launch_pipe(ctx, b, ls, le, o, PIPE_UBLB, nullptr);
     }
-    if (MODE == M_MAP && b.uniform && o.k > 1 && ctx->pipe_mode) {
-        // several reductions, all answered by the prefix sums: still one pass of the pipelined kernel
-        bool algebraic = true;
-        for (int c = 0; c < o.k; c++)
-            algebraic &= o.ops[c] == GRB_OP_SUM || o.ops[c] == GRB_OP_SUM_NOT_EMPTY || o.ops[c] == GRB_OP_MEAN || o.ops[c] == GRB_OP_COUNT;
-        if (algebraic) return launch_pipe<PIPE_MULTI>(ctx, b, ls, le, o);
-    }
-    if (MODE == M_MAP && b.uniform && o.k == 1 && ctx->pipe_mode) {
-        switch (o.ops[0]) {
-            case GRB_OP_MEAN:
-                return launch_pipe<GRB_OP_MEAN>(ctx, b, ls, le, o);
-            case GRB_OP_SUM:
-                return launch_pipe<GRB_OP_SUM>(ctx, b, ls, le, o);
-            case GRB_OP_SUM_NOT_EMPTY:
-                return launch_pipe<GRB_OP_SUM_NOT_EMPTY>(ctx, b, ls, le, o);
-            case GRB_OP_COUNT:
-                return launch_pipe<GRB_OP_COUNT>(ctx, b, ls, le, o);
-            default:
-                break;
-        }
-    }
+    if (MODE == M_MAP && ctx->pipe_mode && map_pipe_fast(b, o) >= 0) return grb_launch_pipe(ctx, b, ls, le, o, map_pipe_fast(b, o), valid_bits);
     if (MODE == M_MAP && b.uniform && o.k == 1) {
         switch (o.ops[0]) {
             case GRB_OP_MEAN:
@@ -1088,7 +923,8 @@ int grb_filter_overlaps(grb_ctx *ctx, const grb_index *idx, const uint32_t *ls, 
 }
 
 static int map_joins_impl(grb_ctx *ctx, const grb_index *const *idx, const uint64_t *left_offsets, int nseq, const uint32_t *ls,
-                          const uint32_t *le, const int *ops, int k, double *out, uint8_t *out_valid, bool allow_chunks);
+                          const uint32_t *le, const int *ops, int k, double *out, uint8_t *out_valid, bool allow_chunks,
+                          uint32_t *valid_bits = nullptr);
 
 // Host buffers, many seqnames: run the seqnames in chunks so that the upload of the next chunk's lefts, the kernels
 // of the current one and the download of the previous chunk's results overlap (PCIe is full duplex).
@@ -1159,8 +995,26 @@ int grb_map_joins_f64_batch(grb_ctx *ctx, const grb_index *const *idx, const uin
     return map_joins_impl(ctx, idx, left_offsets, nseq, ls, le, ops, k, out, out_valid, true);
 }
 
+int grb_map_joins_f64_batch_bits(grb_ctx *ctx, const grb_index *const *idx, const uint64_t *left_offsets, int nseq,
+                                 const uint32_t *ls, const uint32_t *le, const int *ops, int k, double *out,
+                                 uint32_t *out_valid_bits) {
+    if (!ctx) return GRB_ERR_INVALID_ARG;
+    if (!out_valid_bits) return grb_fail(ctx, GRB_ERR_INVALID_ARG, "map_joins_bits: NULL validity buffer");
+    if (left_offsets && nseq > 0 && left_offsets[0] != 0)
+        return grb_fail(ctx, GRB_ERR_INVALID_ARG, "map_joins_bits: left_offsets[0] must be 0 (the validity words are addressed from row 0)");
+    return map_joins_impl(ctx, idx, left_offsets, nseq, ls, le, ops, k, out, nullptr, false, out_valid_bits);
+}
+
+// validity bytes -> bits: word w covers flattened entries [32 w, 32 w + 32) of the nl x k byte array
+__global__ void k_pack_bits(const u8 *__restrict__ bytes, u64 n, u32 *__restrict__ bits) {
+    const u64 i = (u64)blockIdx.x * blockDim.x + threadIdx.x;
+    const u32 m = __ballot_sync(GRB_FULL, i < n && bytes[i] != 0);
+    if (lane_id() == 0 && (i & ~31ull) < n) bits[i >> 5] = m;
+}
+
 static int map_joins_impl(grb_ctx *ctx, const grb_index *const *idx, const uint64_t *left_offsets, int nseq, const uint32_t *ls,
-                          const uint32_t *le, const int *ops, int k, double *out, uint8_t *out_valid, bool allow_chunks) {
+                          const uint32_t *le, const int *ops, int k, double *out, uint8_t *out_valid, bool allow_chunks,
+                          uint32_t *valid_bits) {
     GRB_TRY(enter(ctx));
     if (!left_offsets || !ops) return grb_fail(ctx, GRB_ERR_INVALID_ARG, "map_joins: NULL left_offsets / ops");
     if (k < 1 || k > GRB_MAX_OPS) return grb_fail(ctx, GRB_ERR_INVALID_ARG, "map_joins: k must be in [1, %d]", GRB_MAX_OPS);
@@ -1251,8 +1105,7 @@ static int map_joins_impl(grb_ctx *ctx, const grb_index *const *idx, const uint6
     // MIN / MAX without a median beside them need no sweep at all: stabbing tables + range minimum (k_minmax)
     u32 min_cols = 0, max_cols = 0;
     {
-        const char *mm = getenv("GRB_MINMAX_MODE");  // debug: 0 = sweep the members for MIN / MAX too
-        if (rank_sweep && !want_median && ctx->sweep_mode == 1 && !(mm && atoi(mm) == 0)) {
+        if (rank_sweep && !want_median && ctx->sweep_mode == 1 && ctx->minmax_mode != 0) {
             for (int c = 0; c < k; c++) {
                 if (ops[c] == GRB_OP_MIN) min_cols |= 1u << c;
                 if (ops[c] == GRB_OP_MAX) max_cols |= 1u << c;
@@ -1266,26 +1119,38 @@ static int map_joins_impl(grb_ctx *ctx, const grb_index *const *idx, const uint6
     Batch b;
     GRB_TRY(make_batch(ctx, idx, left_offsets, nseq, &b));
     if (b.total == 0 || b.ntiles == 0) return GRB_OK;  // (a batch that starts past 0 may hold no lefts at all)
-    if (!ls || !le || !out || !out_valid) return grb_fail(ctx, GRB_ERR_INVALID_ARG, "map_joins: NULL buffer");
+    if (!ls || !le || !out || (!out_valid && !valid_bits)) return grb_fail(ctx, GRB_ERR_INVALID_ARG, "map_joins: NULL buffer");
     if (allow_chunks && nseq >= 2 && b.total >= (1u << 22) && !grb_is_device_ptr(ls) && !grb_is_device_ptr(le) &&
         !grb_is_device_ptr(out) && !grb_is_device_ptr(out_valid))
         return map_joins_host_chunked(ctx, idx, left_offsets, nseq, ls, le, ops, k, out, out_valid);
     InBuf dls, dle;
-    OutBuf dout, dval;
+    OutBuf dout, dval, dbits;
+    TempBuf val_tmp;
     GRB_TRY(dls.stage(ctx, ls, b.total * 4));
     GRB_TRY(dle.stage(ctx, le, b.total * 4));
     GRB_TRY(dout.stage(ctx, out, b.total * (u64)k * 8));
-    GRB_TRY(dval.stage(ctx, out_valid, b.total * (u64)k));
     TileOut o;
     memset(&o, 0, sizeof(o));
     o.flags = ctx->dev_flags;
     o.out = dout.as<double>();
-    o.out_valid = dval.as<u8>();
     o.k = k;
     o.need_sum = need_sum;
     for (int c = 0; c < k; c++) o.ops[c] = ops[c];
+    // validity as bits: written by the pipelined kernel itself for a single prefix-sum reduction, else packed from bytes
+    bool bits_direct = false;
+    if (valid_bits) {
+        GRB_TRY(dbits.stage(ctx, valid_bits, ((b.total * (u64)k + 31) / 32) * 4));
+        bits_direct = k == 1 && !need_members && !bp_cols && !wm_cols && ctx->pipe_mode == 1 && map_pipe_fast(b, o) >= 0;
+        if (!bits_direct) {
+            GRB_TRY(val_tmp.alloc(ctx, b.total * (u64)k));
+            o.out_valid = val_tmp.as<u8>();
+        }
+    } else {
+        GRB_TRY(dval.stage(ctx, out_valid, b.total * (u64)k));
+        o.out_valid = dval.as<u8>();
+    }
     if (!need_members && !bp_cols && !wm_cols) {
-        GRB_TRY(launch_map<M_MAP>(ctx, b, dls.as<u32>(), dle.as<u32>(), o));
+        GRB_TRY(launch_map<M_MAP>(ctx, b, dls.as<u32>(), dle.as<u32>(), o, bits_direct ? dbits.as<u32>() : nullptr));
     } else {
         TempBuf ub, lb, pp, heavy;
         GRB_TRY(ub.alloc(ctx, b.total * 4));
@@ -1351,9 +1216,15 @@ static int map_joins_impl(grb_ctx *ctx, const grb_index *const *idx, const uint6
             }
         }
     }
+    if (valid_bits && !bits_direct) {
+        const u64 nflat = b.total * (u64)k;
+        k_pack_bits<<<(unsigned)((nflat + 255) / 256), 256, 0, ctx->stream>>>(val_tmp.as<u8>(), nflat, dbits.as<u32>());
+        GRB_LAUNCHED(ctx);
+    }
     GRB_TRY(dout.finish(ctx));
     GRB_TRY(dval.finish(ctx));
-    if (dout.host || dval.host) return grb_check_flags(ctx);
+    GRB_TRY(dbits.finish(ctx));
+    if (dout.host || dval.host || dbits.host) return grb_check_flags(ctx);
     return GRB_OK;
 }
 

@@ -38,8 +38,7 @@ extern "C" int grb_map_joins_whole_f64(grb_ctx *ctx, int nseq, const uint32_t *c
     {
         u64 vol_total = 0;
         for (int s = 0; s < nseq; s++) vol_total += (left_offsets[s + 1] - left_offsets[s]) * (8 + 9ull * k) + (u64)r_n[s] * 16;
-        const char *ce = getenv("GRB_WHOLE_CHUNKS");  // tuning knob
-        const u64 nch = ce && atoi(ce) > 0 ? (u64)atoi(ce) : 8;
+        const u64 nch = (u64)ctx->whole_chunks;  // GRB_WHOLE_CHUNKS
         const u64 target = vol_total / nch + 1;
         u64 acc = 0;
         for (int s = 0; s < nseq; s++) {
@@ -60,8 +59,7 @@ extern "C" int grb_map_joins_whole_f64(grb_ctx *ctx, int nseq, const uint32_t *c
     std::mutex mu;
     std::condition_variable cv;
     std::atomic<int> failed{0};
-    const char *we = getenv("GRB_WHOLE_WORKERS");  // tuning knob
-    const int wmax = we && atoi(we) > 0 ? atoi(we) : 4;
+    const int wmax = ctx->whole_workers;  // GRB_WHOLE_WORKERS
     const int nworkers = nseq < wmax ? nseq : wmax;
     std::vector<grb_ctx> clones((size_t)nworkers);
     std::vector<int> rcs((size_t)nworkers, GRB_OK);

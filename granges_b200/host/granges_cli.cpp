@@ -740,6 +740,7 @@ int cmd_merge(const std::string &bedfile, long long distance, const std::vector<
     }
     size_t max_row = 64;
     for (auto &nm : r.seqname) max_row = std::max(max_row, nm.size() + 96);
+    if (r.ncols == 5) max_row += 420;  // grh::format_f64: positional notation, up to ~330 characters (1e-300, 1e300)
     if (r.ncols == 4) {
         size_t worst = 0;
         for (size_t g = 0; g < m; g++) {

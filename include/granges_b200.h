@@ -183,6 +183,15 @@ int grb_map_joins_f64_batch(grb_ctx *ctx, const grb_index *const *idx, const uin
                             const uint32_t *ls, const uint32_t *le, const int *ops, int k, double *out,
                             uint8_t *out_valid);
 
+/* The same call with the validity as BITS: bit (i * k + c) of out_valid_bits (word (i * k + c) / 32, u32 words,
+ * ceil(nl * k / 32) of them) is 1 for DatumType::Float64, 0 for DatumType::NoValue -- the NL * K / 8 bytes SURVEY 8(d)
+ * budgets for the valid flags instead of NL * K.  A single prefix-sum reduction (sum / sum-not-empty / mean / count)
+ * writes the bits from the kernel itself; other calls pack them on the device.  left_offsets[0] must be 0.  Bits past
+ * nl * k in the last word are unspecified. */
+int grb_map_joins_f64_batch_bits(grb_ctx *ctx, const grb_index *const *idx, const uint64_t *left_offsets, int nseq,
+                                 const uint32_t *ls, const uint32_t *le, const int *ops, int k, double *out,
+                                 uint32_t *out_valid_bits);
+
 /* `granges map` in one call for host-resident inputs -- src/commands.rs:477-547 (into_coitrees -> map_data ->
  * left_overlaps -> map_joins): grb_index_build_batch + grb_map_joins_f64_batch, pipelined per seqname so that the
  * results of the first seqnames travel back while the rights of the later ones are still being uploaded and indexed.

@@ -33,6 +33,17 @@ def random_case(seed, nl, nr, span=2000, maxlen=60, null_frac=0.0, score_kind="u
         sc = rng.standard_normal(nr) * 10.0 ** rng.integers(-3, 4, nr)
     elif score_kind == "wide":  # dynamic range too wide for the exact fixed-point path
         sc = rng.standard_normal(nr) * 10.0 ** rng.integers(-30, 30, nr)
+    elif score_kind == "decimal":  # what BED files hold: decimal fractions over a few decades (about 70 bits of fixed point)
+        sc = np.round(0.001 + rng.random(nr) * 456.788, 3)
+    elif score_kind == "wide96":  # 53-bit fractions over 31 binary decades: 84 bits, groups beyond 2^11 members leave the fast path
+        sc = rng.random(nr) * 2.0 ** (-rng.integers(0, 31, nr))
+    elif score_kind == "signed-decimal":  # mixed signs: cancellation
+        sc = np.round((rng.random(nr) - 0.5) * 2000.0, 2)
+    elif score_kind == "nan":
+        sc = np.round(rng.random(nr) * 10, 2)
+        if nr:
+            sc[rng.integers(0, nr, max(1, nr // 50))] = np.nan
+            sc[rng.integers(0, nr, max(1, nr // 50))] = np.inf
     elif score_kind == "nonfinite":
         sc = rng.random(nr)
         if nr:

@@ -225,6 +225,18 @@ def test_cli_merge_bed5(tmp_path, orc, op):
     assert r.returncode == 1 and "func" in r.stderr
 
 
+def test_cli_merge_bed5_extreme_scores(tmp_path):
+    """Scores of very small / very large magnitude print as hundreds of characters in Rust's positional notation
+    (f64::to_string never uses an exponent): the row buffer must hold them."""
+    path = tmp_path / "x.bed"
+    path.write_text("chr1\t0\t10\ta\t1e-100\nchr1\t5\t20\tb\t1e-100\nchr1\t100\t200\tc\t1e300\nchr2\t7\t9\td\t-2.5e-300\n")
+    for op, want in (("sum", [2e-100, 1e300, -2.5e-300]), ("max", [1e-100, 1e300, -2.5e-300])):
+        lines = run("merge", "-b", path, "-f", op).stdout.splitlines()
+        assert [ln.split("\t")[:3] for ln in lines] == [["chr1", "0", "20"], ["chr1", "100", "200"], ["chr2", "7", "9"]]
+        assert [ln.split("\t")[3] for ln in lines] == [rust_display(v) for v in want]
+        assert len(lines[1].split("\t")[3]) == 301 and len(lines[2].split("\t")[3]) > 300
+
+
 def test_cli_feature_density(tmp_path, orc):
     """Per window and feature: basepairs covered by the feature's bookend-merged ranges (src/commands.rs:796-858)."""
     rng = np.random.default_rng(21)

@@ -6,11 +6,11 @@ import numpy as np
 import pytest
 
 from tests import golden_checks as gc
+from tests.mapchecks import SUM_TOL, assert_map_equal, finite_abs
 from tests.randcases import ALL_OPS, random_case
 
 pytestmark = pytest.mark.gpu
 
-SUM_TOL = 1e-12
 
 
 @pytest.fixture(scope="module")
@@ -32,21 +32,6 @@ def test_golden(eng, goldens, check):
     check(eng, goldens)
 
 
-def assert_map_equal(out, ov, want, wv, ops, abs_sums):
-    assert (np.asarray(ov) == wv).all(), "validity (NoValue) mismatch"
-    for c, op in enumerate(ops):
-        m = wv[:, c] == 1
-        if op in ("sum", "sum-not-empty", "mean", "weighted-mean"):
-            tol = SUM_TOL * np.maximum(abs_sums[m], 0) + 0.0
-            if op == "mean":
-                pass  # |mean error| <= |sum error| / n <= tol
-            err = np.abs(out[m, c] - want[m, c])
-            bad = err > tol
-            assert not bad.any(), (op, out[m, c][bad][:5], want[m, c][bad][:5])
-        else:
-            assert (out[m, c] == want[m, c]).all(), op
-
-
 def run_case(eng, orc, c, ops=ALL_OPS, idx=None):
     t = orc.Tree(c["rs"], c["re"], idx)
     ix = eng.build(c["rs"], c["re"], idx, c["scores"], c["valid"])
@@ -59,9 +44,10 @@ def run_case(eng, orc, c, ops=ALL_OPS, idx=None):
     assert (eng.filter(ix, c["ls"], c["le"], anti=True) == (want_counts == 0)).all()
     # reductions
     want, wv = orc.map_joins(t, c["scores"], c["valid"], c["ls"], c["le"], ops)
-    abs_sums = orc.map_joins(t, np.abs(c["scores"]), c["valid"], c["ls"], c["le"], ["sum"])[0][:, 0]
+    abs_sums = orc.map_joins(t, finite_abs(c["scores"]), c["valid"], c["ls"], c["le"], ["sum"])[0][:, 0]
+    nvalid = orc.map_joins(t, np.ones(len(c["rs"])), c["valid"], c["ls"], c["le"], ["sum"])[0][:, 0]
     out, ov = eng.map_joins(ix, c["ls"], c["le"], ops)
-    assert_map_equal(out, ov, want, wv, ops, abs_sums)
+    assert_map_equal(out, ov, want, wv, ops, abs_sums, nvalid)
     return ix, t
 
 
@@ -73,6 +59,8 @@ KINDS = {
     "dense-ties": dict(maxlen=3, span=50),
     "wide": dict(score_kind="wide"),
     "nonfinite": dict(score_kind="nonfinite"),
+    "decimal": dict(score_kind="decimal"),
+    "signed-decimal-nulls": dict(score_kind="signed-decimal", null_frac=0.2),
     "sorted-left": dict(sorted_left=True, span=20000),
     "nulls-sorted": dict(null_frac=0.5, sorted_left=True, span=5000),
 }
