@@ -257,6 +257,7 @@ def main():
     ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--ops", default="mean")
+    ap.add_argument("--valid-bytes", action="store_true", help="validity as one byte per result (grb_map_joins_f64_batch) instead of one bit")
     args = ap.parse_args()
     if args.impl == "reference":
         reference_arm(args)
@@ -345,9 +346,10 @@ def main():
     nl_mine = int(offs[-1])
     offs = np.array(offs, dtype=np.uint64)
     out = torch.empty((nl_mine, k), dtype=torch.float64, device=dev)
-    ov = torch.empty((nl_mine, k), dtype=torch.uint8, device=dev)
+    bits = not args.valid_bytes
+    ov = torch.empty(((nl_mine * k + 31) // 32,), dtype=torch.int32, device=dev) if bits else torch.empty((nl_mine, k), dtype=torch.uint8, device=dev)
 
-    call = ctx.prepare_map(idxs, offs, ls, le, ops, out, ov) if nl_mine else None
+    call = ctx.prepare_map(idxs, offs, ls, le, ops, out, ov, valid_bits=bits) if nl_mine else None
 
     def step():
         if call is not None:
@@ -402,7 +404,12 @@ def main():
     chk_slice = None
     if world == 1 and rank == 0:
         a, b = int(left_off[chk_seq]), int(left_off[chk_seq + 1])
-        chk_slice = (out[a:b].cpu().numpy(), ov[a:b].cpu().numpy())
+        if bits:
+            w0, w1 = (a * k) // 32, (b * k + 31) // 32
+            flat = np.unpackbits(ov[w0:w1].cpu().numpy().view(np.uint8), bitorder="little")[a * k - w0 * 32: b * k - w0 * 32]
+            chk_slice = (out[a:b].cpu().numpy(), flat.reshape(b - a, k))
+        else:
+            chk_slice = (out[a:b].cpu().numpy(), ov[a:b].cpu().numpy())
 
     # ---- e2e: host (pinned) buffers through the C ABI, copies inside the timed region; every rank does its own
     # units from its own host buffers, wall clock between barriers, max over ranks

@@ -262,6 +262,13 @@ __global__ void __launch_bounds__(256) k_fx_blocks(const double *__restrict__ sc
     }
 }
 
+// out[i] = i: the valid-score counts of an index without None scores (only built beside non-finite scores, whose
+// seqnames run in the NULLS variant of the pipelined kernel)
+__global__ void k_iota_u32(size_t n, u32 *__restrict__ a, u32 *__restrict__ b) {
+    size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n) a[i] = b[i] = (u32)i;
+}
+
 // low halves of a u32 array (what the pipelined kernel stages for the valid-score counts)
 __global__ void k_narrow_u16(const u32 *__restrict__ in, size_t n, u16 *__restrict__ out) {
     size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
@@ -853,13 +860,21 @@ int grb_index_set_scores(grb_index *ix, const double *by_data_idx, const uint8_t
         GRB_LAUNCHED(ctx);
         GRB_TRY(grb_scan_u32_to_u32(ctx, vflag_a.as<u32>(), ix->vcnt_a, n, true));
         GRB_TRY(grb_scan_u32_to_u32(ctx, vflag_b.as<u32>(), ix->vcnt_b, n, true));
+    } else if (ix->has_nonfinite) {
+        GRB_TRY(dev_alloc(ctx, (void **)&ix->vcnt_a, (n + 1) * 4));
+        GRB_TRY(dev_alloc(ctx, (void **)&ix->vcnt_b, (n + 1) * 4));
+        k_iota_u32<<<blocks_for(n + 1, 256), 256, 0, ctx->stream>>>(n + 1, ix->vcnt_a, ix->vcnt_b);
+        GRB_LAUNCHED(ctx);
+    }
+    if (ix->has_nulls || ix->has_nonfinite) {
         GRB_TRY(dev_alloc(ctx, (void **)&ix->vc16_a, (n + 1 + PAD) * 2));
         GRB_TRY(dev_alloc(ctx, (void **)&ix->vc16_b, (n + 1 + PAD) * 2));
         k_narrow_u16<<<blocks_for(n + 1, 256), 256, 0, ctx->stream>>>(ix->vcnt_a, n + 1, ix->vc16_a);
         GRB_LAUNCHED(ctx);
         k_narrow_u16<<<blocks_for(n + 1, 256), 256, 0, ctx->stream>>>(ix->vcnt_b, n + 1, ix->vc16_b);
         GRB_LAUNCHED(ctx);
-    } else if (ix->vbits_a) {
+    }
+    if (!ix->has_nulls && ix->vbits_a) {
         grb_dev_free(ix->ctx, ix->vbits_a);
         ix->vbits_a = nullptr;
     }

@@ -691,7 +691,7 @@ int make_batch(grb_ctx *ctx, const grb_index *const *idx, const u64 *left_offset
             }
             if (!(ix->has_scores && !ix->has_nulls && !ix->has_nonfinite && ix->sum_mode == GRB_SUM_COMPACT)) b->uniform = false;
             if (ix->has_scores && (ix->sum_mode == GRB_SUM_COMPACT || ix->sum_mode == GRB_SUM_WIDE96))
-                b->var[s] = (ix->has_nulls ? PIPE_VAR_NULLS : 0) | (ix->sum_mode == GRB_SUM_WIDE96 ? PIPE_VAR_WIDE : 0);
+                b->var[s] = ((ix->has_nulls || ix->has_nonfinite) ? PIPE_VAR_NULLS : 0) | (ix->sum_mode == GRB_SUM_WIDE96 ? PIPE_VAR_WIDE : 0);
             else
                 b->pipeable = false;  // no scores / full 128-bit prefixes / member sums: the tile kernel (and the sweep)
         } else {
