@@ -74,6 +74,287 @@ def split_counts(total, nseq):
     return [q + (1 if s < r else 0) for s in range(nseq)]
 
 
+def clustered_rights(seq, n, seed, dev):
+    """Config C4's right set: 80 % of the ranges in 5 % of the 1 Mb bins (log-normal bin weights, sigma 1.5),
+    the rest uniform; len U{1..999}, scores U[0,1); sorted.  torch's generator: device-specific streams, so the CPU
+    checks copy the arrays back instead of regenerating them."""
+    L = HG38[seq]
+    g = torch.Generator(device=dev)
+    g.manual_seed(seed * 1000 + seq)
+    nb = (L + 999_999) // 1_000_000
+    hot = torch.randperm(nb, generator=g, device=dev)[: max(1, nb // 20)]
+    w = torch.exp(1.5 * torch.randn(len(hot), generator=g, device=dev))
+    nh = int(n * 0.8)
+    which = hot[torch.multinomial(w, nh, replacement=True, generator=g)]
+    ln = torch.randint(1, 1000, (n,), generator=g, device=dev)
+    st_hot = which * 1_000_000 + torch.randint(0, 1_000_000, (nh,), generator=g, device=dev)
+    st_uni = (torch.rand(n - nh, generator=g, device=dev, dtype=torch.float64) * L).to(torch.int64)
+    st = torch.cat([st_hot, st_uni])
+    st = torch.minimum(st, torch.tensor(L, device=dev) - ln)
+    st = torch.clamp(st, min=0)
+    key, _ = torch.sort(st * 4294967296 + (st + ln))
+    sc = torch.rand(n, generator=g, device=dev, dtype=torch.float64)
+    return (key >> 32).to(torch.int32), (key & 0xFFFFFFFF).to(torch.int32), sc
+
+
+def gtf_like_lefts(seq, n, g, dev):
+    """Config C5's lefts: len ~ log-normal(median 2 kb, sigma 1.0) clipped to [50, 2e6], starts uniform; sorted."""
+    L = HG38[seq]
+    ln = torch.exp(np.log(2000.0) + torch.randn(n, generator=g, device=dev, dtype=torch.float64)).clamp(50, 2e6).to(torch.int64)
+    st = (torch.rand(n, generator=g, device=dev, dtype=torch.float64) * (L - ln).to(torch.float64)).to(torch.int64)
+    key, _ = torch.sort(st * 4294967296 + (st + ln))
+    return (key >> 32).to(torch.int32), (key & 0xFFFFFFFF).to(torch.int32)
+
+
+def reads_like_rights(seq, n, g, dev):
+    """Config C5's rights: len U{75..151}, starts uniform; sorted."""
+    L = HG38[seq]
+    rl = torch.randint(75, 152, (n,), generator=g, device=dev)
+    rst = (torch.rand(n, generator=g, device=dev, dtype=torch.float64) * (L - 151)).to(torch.int64)
+    key, _ = torch.sort(rst * 4294967296 + (rst + rl))
+    return (key >> 32).to(torch.int32), (key & 0xFFFFFFFF).to(torch.int32)
+
+
+def variant_scores(kind, seq, n, dev):
+    """Scores (and validity) of the input classes the reference takes at one speed: `nulls` = 1 % BED "." scores,
+    `wide` = decimal fractions over five decades (about 70 bits of fixed point: the 96-bit prefix planes),
+    `nonfinite` = one +inf per seqname (prefix counters + the IEEE rule).  Same on CPU and CUDA."""
+    i = torch.arange(n, dtype=torch.int64, device=dev)
+    base = i * 4 + (14 * 1000003 + seq * 7919) * 1_000_000_007
+    sc = _lsr(_mix(base + 2), 11).to(torch.float64) * (2.0 ** -53)
+    valid = None
+    if kind == "nulls":
+        valid = ((_mix(base + 3) & M63) % 100 != 0).to(torch.uint8)
+    elif kind == "wide":
+        sc = torch.round((0.001 + sc * 456.788) * 1000.0) / 1000.0
+    elif kind == "nonfinite":
+        sc = sc.clone()
+        sc[n // 2] = float("inf")
+    return sc, valid
+
+
+def event_ms(fn, steps, warmup):
+    """Mean CUDA-event time of fn() on the current stream."""
+    for _ in range(warmup):
+        fn()
+    torch.cuda.synchronize()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for _ in range(steps):
+        fn()
+    e1.record()
+    torch.cuda.synchronize()
+    return e0.elapsed_time(e1) / steps
+
+
+def map_matches_oracle(got, gv, want, wv, ops):
+    """The parity rule of the tests: validity equal; min / max / median / count bit-exact; sum / mean within 1e-12
+    relative; non-finite results equal in kind."""
+    if not (gv == wv).all():
+        return False
+    for c, op in enumerate(ops):
+        m = wv[:, c] == 1
+        g, w = got[m, c], want[m, c]
+        if op in ("sum", "mean", "sum-not-empty"):
+            fin = np.isfinite(w)
+            if not ((np.isnan(g) == np.isnan(w)).all() and (g[np.isinf(w)] == w[np.isinf(w)]).all()):
+                return False
+            if fin.any() and float(np.max(np.abs(g[fin] - w[fin]) / np.maximum(np.abs(w[fin]), 1e-300))) > 1e-12:
+                return False
+        elif not (g == w).all():
+            return False
+    return True
+
+
+CHECK_SEQ, CHECK_LEFTS = 20, 200_000  # oracle spot checks: the first 200k lefts of chr21 against all of chr21's rights
+
+
+def run_variants(ctx, idxs, offs, ls, le, nl_per, nr_per, dev, base_ms, steps, warmup):
+    """The headline job (map mean, 100M x 100M) on the input classes that used to leave the pipelined kernel, plus
+    shuffled lefts: ms per pass, ratio to the sorted / all-Some pass, oracle spot check.  Leaves the indexes with their
+    original scores."""
+    from oracle import oracle as orc
+
+    s = CHECK_SEQ
+    rs_h, re_h, _ = (t.numpy() for t in gen_ranges(s, nr_per[s], 14, "cpu", True))
+    tree = orc.Tree(rs_h.astype(np.uint32), re_h.astype(np.uint32))
+    a = int(offs[s])
+    nchk = min(CHECK_LEFTS, nl_per[s])
+    k = 1
+    out = torch.empty((len(ls), k), dtype=torch.float64, device=dev)
+    ov = torch.empty((len(ls), k), dtype=torch.uint8, device=dev)
+    res = {}
+
+    def check(ls_d, le_d, rows, sc_h, va_h):
+        hl = ls_d[rows].cpu().numpy().astype(np.uint32)
+        he = le_d[rows].cpu().numpy().astype(np.uint32)
+        want, wv = orc.map_joins(tree, sc_h, va_h, hl, he, ["mean"], nthreads=orc.max_threads())
+        return map_matches_oracle(out[rows].cpu().numpy(), ov[rows].cpu().numpy(), want, wv, ["mean"])
+
+    for kind in ("nulls", "wide", "nonfinite"):
+        for q, ix in enumerate(idxs):
+            sc, va = variant_scores(kind, q, nr_per[q], dev)
+            ix.set_scores(sc, va)
+        call = ctx.prepare_map(idxs, offs, ls, le, ["mean"], out, ov)
+        ms = event_ms(call, steps, warmup)
+        sc_h, va_h = variant_scores(kind, s, nr_per[s], "cpu")
+        ok = check(ls, le, slice(a, a + nchk), sc_h.numpy(), None if va_h is None else va_h.numpy())
+        res[kind] = {"ms": ms, "x_sorted_all_some": ms / base_ms, "parity_ok": bool(ok)}
+    # original scores back, then shuffled lefts (any left order is legal: src/granges.rs:935-984)
+    for q, ix in enumerate(idxs):
+        ix.set_scores(gen_ranges(q, nr_per[q], 14, dev, True)[2])
+    perm = torch.cat([int(offs[q]) + torch.randperm(nl_per[q], device=dev) for q in range(len(idxs))])
+    ls_s, le_s = ls[perm].contiguous(), le[perm].contiguous()
+    call = ctx.prepare_map(idxs, offs, ls_s, le_s, ["mean"], out, ov)
+    first_ms = event_ms(call, 1, 0)  # device buffers, AUTO order: the first call takes the lefts as they are and learns from it
+    ms = event_ms(call, max(2, steps // 2), 1)
+    sc_h = gen_ranges(s, nr_per[s], 14, "cpu", True)[2].numpy()
+    ok = check(ls_s, le_s, slice(a, a + nchk), sc_h, None)
+    res["shuffled_lefts"] = {"ms": ms, "x_sorted_all_some": ms / base_ms, "parity_ok": bool(ok), "first_call_ms": first_ms,
+                             "how": "lefts bucketed by coordinate on the device, rows written back (bucket.cu); order learned from the first call"}
+    return res
+
+
+def run_c3(ctx, idxs, offs, ls, le, nl_per, nr_per, dev, peak):
+    """BASELINE config C3 on one GPU: map --func min,max,mean,sum,median over the headline's indexes."""
+    from oracle import oracle as orc
+
+    ops = ["min", "max", "mean", "sum", "median"]
+    n = len(ls)
+    out = torch.empty((n, 5), dtype=torch.float64, device=dev)
+    ov = torch.empty((n, 5), dtype=torch.uint8, device=dev)
+    call = ctx.prepare_map(idxs, offs, ls, le, ops, out, ov)
+    ms = event_ms(call, 3, 1)
+    s = CHECK_SEQ
+    rs_h, re_h, sc_h = (t.numpy() for t in gen_ranges(s, nr_per[s], 14, "cpu", True))
+    a, nchk = int(offs[s]), min(CHECK_LEFTS, nl_per[s])
+    hl, he = ls[a:a + nchk].cpu().numpy().astype(np.uint32), le[a:a + nchk].cpu().numpy().astype(np.uint32)
+    want, wv = orc.map_joins(orc.Tree(rs_h.astype(np.uint32), re_h.astype(np.uint32)), sc_h, None, hl, he, ops, nthreads=orc.max_threads())
+    ok = map_matches_oracle(out[a:a + nchk].cpu().numpy(), ov[a:a + nchk].cpu().numpy(), want, wv, ops)
+    nr = sum(nr_per)
+    alg = n * 8 + nr * 16 + n * 5 * 8 + n * 5 / 8
+    return {"workload": f"map min,max,mean,sum,median {n} x {nr} uniform", "ms": ms, "lefts_per_s": n / ms * 1e3,
+            "roofline_frac": alg / (ms * 1e-3) / 1e9 / peak, "algorithmic_bytes": alg, "parity_ok": bool(ok)}
+
+
+def run_configs(ctx, dev, peak, scale=1.0):
+    """BASELINE configs C2, C4, C5 at their stated sizes on one GPU (own data): ms, fraction of the HBM roofline on SURVEY
+    8(d)'s algorithmic bytes, and an oracle spot check on one seqname."""
+    import ctypes as C
+
+    from granges_b200 import _capi
+    from oracle import oracle as orc
+
+    L_ = _capi.lib()
+    res = {}
+    # ---- C2: granges filter, 10M x 10M uniform BED3
+    n = int(10_000_000 * scale)
+    per = split_counts(n, 22)
+    idxs, ls, le, chk = [], [], [], None
+    for s in range(22):
+        a, b = gen_ranges(s, per[s], 13, dev, False)
+        rs, re = gen_ranges(s, per[s], 14, dev, False)
+        idxs.append(ctx.index_build(rs, re))
+        ls.append(a)
+        le.append(b)
+        if s == CHECK_SEQ:
+            chk = (rs.cpu().numpy().astype(np.uint32), re.cpu().numpy().astype(np.uint32), a.cpu().numpy().astype(np.uint32),
+                   b.cpu().numpy().astype(np.uint32))
+    off = np.concatenate([[0], np.cumsum(per)]).astype(np.uint64)
+    ls, le = torch.cat(ls), torch.cat(le)
+    keep = torch.empty(n, dtype=torch.uint8, device=dev)
+    ms = event_ms(lambda: ctx.filter_overlaps_batch(idxs, off, ls, le, out=keep), 10, 3)
+    a0 = int(off[CHECK_SEQ])
+    want = orc.filter_overlaps(orc.Tree(chk[0], chk[1]), chk[2], chk[3])
+    ok = bool((keep[a0:a0 + per[CHECK_SEQ]].cpu().numpy() == want).all())
+    alg = n * 8 + n * 8 + n
+    res["C2"] = {"workload": f"filter {n} x {n} uniform BED3", "ms": ms, "lefts_per_s": n / ms * 1e3, "roofline_frac": alg / (ms * 1e-3) / 1e9 / peak,
+                 "algorithmic_bytes": alg, "parity_ok": ok}
+    for ix in idxs:
+        ix.close()
+    del idxs, ls, le, keep
+    # ---- C4: windows (1 kb / 500 bp) over hg38 x 500M clustered BED5, map mean
+    nr = int(500_000_000 * scale)
+    nr_per = split_counts(nr, 22)
+    idxs, chk, t_build = [], None, 0.0
+    for s in range(22):
+        rs, re, sc = clustered_rights(s, nr_per[s], 15, dev)
+        torch.cuda.synchronize()
+        t0 = time.perf_counter()
+        idxs.append(ctx.index_build(rs, re).set_scores(sc))
+        ctx.sync()
+        t_build += time.perf_counter() - t0
+        if s == CHECK_SEQ:
+            chk = (rs.cpu().numpy().astype(np.uint32), re.cpu().numpy().astype(np.uint32), sc.cpu().numpy())
+        del rs, re, sc
+    w = ctx.windows_dev(HG38, 1000, 500, False)
+    off = w.seq_offsets()
+    nw = len(w)
+    ps, pe = w.dev_ptrs()
+    out = torch.empty((nw, 1), dtype=torch.float64, device=dev)
+    ov = torch.empty((nw, 1), dtype=torch.uint8, device=dev)
+    ops1 = (C.c_int * 1)(4)
+    handles = (C.c_void_p * 22)(*[ix.h for ix in idxs])
+
+    def run():
+        rc = L_.grb_map_joins_f64_batch(ctx.h, handles, off.ctypes.data_as(_capi.u64p), 22, ps, pe, ops1, 1, out.data_ptr(), ov.data_ptr())
+        assert rc == 0, rc
+
+    ms = event_ms(run, 10, 3)
+    a0, a1 = int(off[CHECK_SEQ]), int(off[CHECK_SEQ + 1])
+    ws = (np.arange(a1 - a0, dtype=np.uint64) * 500).astype(np.uint32)
+    we = np.minimum(ws.astype(np.uint64) + 1000, HG38[CHECK_SEQ]).astype(np.uint32)
+    want, wv = orc.map_joins(orc.Tree(chk[0], chk[1]), chk[2], None, ws, we, ["mean", "count"], nthreads=orc.max_threads())
+    ok = map_matches_oracle(out[a0:a1].cpu().numpy(), ov[a0:a1].cpu().numpy(), want[:, :1], wv[:, :1], ["mean"])
+    alg = nr * 16 + nw * 8.125
+    res["C4"] = {"workload": f"windows 1 kb / 500 bp ({nw}) x {nr} clustered BED5, map mean", "ms": ms, "lefts_per_s": nw / ms * 1e3,
+                 "roofline_frac": alg / (ms * 1e-3) / 1e9 / peak, "algorithmic_bytes": alg, "parity_ok": bool(ok), "index_build_ms": t_build * 1e3,
+                 "max_group_checked": int(want[:, 1].max())}
+    for ix in idxs:
+        ix.close()
+    w.close()
+    del idxs, out, ov
+    # ---- C5: left_overlaps with full pair materialisation, 50M GTF-like x 200M reads-like, seqname by seqname
+    nl, nr = int(50_000_000 * scale), int(200_000_000 * scale)
+    nl_per, nr_per = split_counts(nl, 22), split_counts(nr, 22)
+    g = torch.Generator(device=dev)
+    g.manual_seed(5)
+    tot_pairs, tot_ms, ok = 0, 0.0, True
+    for s in range(22):
+        ls, le = gtf_like_lefts(s, nl_per[s], g, dev)
+        rs, re = reads_like_rights(s, nr_per[s], g, dev)
+        ix = ctx.index_build(rs, re)
+        offd = torch.empty(nl_per[s] + 1, dtype=torch.int64, device=dev)
+        for rep in range(2):  # the second run reuses the pool's memory: steady state
+            ph = C.c_void_p()
+            torch.cuda.synchronize()
+            t0 = time.perf_counter()
+            rc = L_.grb_left_overlaps(ctx.h, ix.h, ls.data_ptr(), le.data_ptr(), nl_per[s], offd.data_ptr(), C.byref(ph))
+            assert rc == 0, rc
+            ctx.sync()
+            dt = (time.perf_counter() - t0) * 1e3
+            npairs = L_.grb_pairs_len(ph)
+            L_.grb_pairs_destroy(ph)
+        tot_ms += dt
+        tot_pairs += npairs
+        if s == 0:
+            # spot check: the first 100k lefts of chr1 against all of chr1's rights, offsets and pair indices bit for bit
+            nchk = min(100_000, nl_per[s])
+            hl, he = ls[:nchk].cpu().numpy().astype(np.uint32), le[:nchk].cpu().numpy().astype(np.uint32)
+            tree = orc.Tree(rs.cpu().numpy().astype(np.uint32), re.cpu().numpy().astype(np.uint32))
+            woff, widx, _, _ = orc.left_overlaps(tree, hl, he)
+            goff, gidx, _, _ = ctx.left_overlaps(ix, ls[:nchk].contiguous(), le[:nchk].contiguous())
+            ok = bool((goff == woff).all() and (gidx == widx).all())
+            del tree
+        ix.close()
+        del ls, le, rs, re, offd
+    alg = nl * 8 + nr * 12 + (nl + 22) * 8 + tot_pairs * 4
+    res["C5"] = {"workload": f"left_overlaps pairs {nl} GTF-like x {nr} reads-like (per seqname, wall clock incl. the pair-count read-back)",
+                 "ms": tot_ms, "pairs": tot_pairs, "pairs_per_s": tot_pairs / tot_ms * 1e3, "roofline_frac": alg / (tot_ms * 1e-3) / 1e9 / peak,
+                 "algorithmic_bytes": alg, "parity_ok": ok}
+    return res
+
+
 class ClockSampler:
     """SM clock and throttle reasons sampled DURING the timed region (NVML, every ~5 ms, own thread)."""
     REASONS = {0x8: "hw_slowdown", 0x40: "hw_thermal_slowdown", 0x20: "sw_thermal_slowdown", 0x4: "sw_power_cap"}
@@ -256,8 +537,11 @@ def main():
     ap.add_argument("--rights", type=int, default=100_000_000)
     ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
     ap.add_argument("--no-e2e", action="store_true")
+    ap.add_argument("--no-configs", action="store_true", help="skip the `variants` and `configs` legs (N = 1 only)")
     ap.add_argument("--ops", default="mean")
-    ap.add_argument("--valid-bytes", action="store_true", help="validity as one byte per result (grb_map_joins_f64_batch) instead of one bit")
+    ap.add_argument("--valid-bits", action="store_true", help="validity as one bit per result (grb_map_joins_f64_batch_bits); measured slower "
+                                                              "than bytes on this kernel (profiles/r2/ab_pipe_kernel.txt), so bytes are the default")
+    ap.add_argument("--valid-bytes", action="store_true", help="(default) validity as one byte per result")
     args = ap.parse_args()
     if args.impl == "reference":
         reference_arm(args)
@@ -346,7 +630,7 @@ def main():
     nl_mine = int(offs[-1])
     offs = np.array(offs, dtype=np.uint64)
     out = torch.empty((nl_mine, k), dtype=torch.float64, device=dev)
-    bits = not args.valid_bytes
+    bits = args.valid_bits
     ov = torch.empty(((nl_mine * k + 31) // 32,), dtype=torch.int32, device=dev) if bits else torch.empty((nl_mine, k), dtype=torch.uint8, device=dev)
 
     call = ctx.prepare_map(idxs, offs, ls, le, ops, out, ov, valid_bits=bits) if nl_mine else None
@@ -411,6 +695,19 @@ def main():
         else:
             chk_slice = (out[a:b].cpu().numpy(), ov[a:b].cpu().numpy())
 
+    peaks_path = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(peaks_path):
+        peak, peak_src = float(json.load(open(peaks_path))["hbm_gbs"]), "measured (MEASURED_PEAKS.json hbm_gbs)"
+    else:
+        peak, peak_src = 6650.0, "fallback (B200_PROFILING.md)"
+
+    # ---- the other input classes of the headline job, and config C3, on the same indexes (N = 1)
+    variants = configs = None
+    if world == 1 and not args.no_configs and ops == ["mean"] and nl_mine:
+        call = None
+        variants = run_variants(ctx, idxs, offs, ls, le, nl_per, nr_per, dev, float(np.mean(per_step)), args.steps, args.warmup)
+        configs = {"C3": run_c3(ctx, idxs, offs, ls, le, nl_per, nr_per, dev, peak)}
+
     # ---- e2e: host (pinned) buffers through the C ABI, copies inside the timed region; every rank does its own
     # units from its own host buffers, wall clock between barriers, max over ranks
     e2e = None
@@ -472,11 +769,6 @@ def main():
         line["config"]["ops"] = ops
 
     # ---- roofline of the dominant kernel (k_tile<MAP>: the only kernel of a map_mean step)
-    peaks_path = os.path.join(ROOT, "MEASURED_PEAKS.json")
-    if os.path.exists(peaks_path):
-        peak, peak_src = float(json.load(open(peaks_path))["hbm_gbs"]), "measured (MEASURED_PEAKS.json hbm_gbs)"
-    else:
-        peak, peak_src = 6650.0, "fallback (B200_PROFILING.md)"
     nr_tot = int(agg[2].item())
     alg_bytes = nl_total * 8 + nr_tot * 16 + nl_total * k * 8 + nl_total * k / 8  # B_map
     kernel_ms = float(np.mean(per_step))  # rank 0's launch duration (one k_tile launch per step when ops = mean)
@@ -495,6 +787,12 @@ def main():
             pass
 
     line["e2e"] = e2e
+    if variants is not None:
+        line["variants"] = variants
+    if configs is not None:
+        torch.cuda.empty_cache()
+        configs.update(run_configs(ctx, dev, peak))
+        line["configs"] = configs
 
     # ---- cpu baseline: the oracle on a bounded sample (one seqname), 1 thread like the reference
     if world == 1 and not args.no_cpu:

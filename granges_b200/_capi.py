@@ -31,6 +31,7 @@ SIGNATURES = {
     "grb_ctx_set_stream": (C.c_int, [vp, vp]),
     "grb_ctx_use_own_stream": (C.c_int, [vp]),
     "grb_ctx_sync": (C.c_int, [vp]),
+    "grb_ctx_set_left_order": (C.c_int, [vp, C.c_int]),
     "grb_ctx_destroy": (None, [vp]),
     "grb_last_error": (C.c_char_p, [vp]),
     "grb_ctx_launch_count": (C.c_uint64, [vp]),

@@ -184,6 +184,15 @@ class Context:
             raise GRangesError(rc, f"cannot create a context on CUDA device {device} (no CPU fallback exists)")
         self.h = h
         self.device = int(device)
+        if stream is None:
+            # Device tensors handed to this context are produced on torch's current stream: run there too, so that the
+            # library's kernels are ordered after the producer and before the consumer of every tensor (the context's own
+            # non-blocking stream would race with both).  Callers who manage streams themselves pass one explicitly.
+            import sys
+
+            torch = sys.modules.get("torch")
+            if torch is not None and torch.cuda.is_available():
+                stream = torch.cuda.current_stream(self.device)
         if stream is not None:
             self.set_stream(stream)
 
@@ -199,6 +208,11 @@ class Context:
             return
         ptr = int(getattr(stream, "cuda_stream", stream))
         self._check(_capi.lib().grb_ctx_set_stream(self.h, C.c_void_p(ptr)))
+
+    def set_left_order(self, order):
+        """"auto" (default) | "sorted" (never bucket) | "unsorted" (always bucket): grb_ctx_set_left_order."""
+        code = {"auto": 0, "sorted": 1, "unsorted": 2}[order] if isinstance(order, str) else int(order)
+        self._check(_capi.lib().grb_ctx_set_left_order(self.h, code))
 
     def sync(self):
         self._check(_capi.lib().grb_ctx_sync(self.h))

@@ -37,6 +37,13 @@ struct grb_ctx {
     int ublb_pipe;  // GRB_UBLB_PIPE: 1 / 0 = the (ub, pp, lb) pass always / never in the pipelined kernel; -1 (default) = beside sums
     int minmax_mode; // GRB_MINMAX_MODE: 0 = MIN / MAX sweep the members even without a median beside them (debug)
     int whole_chunks, whole_workers;  // GRB_WHOLE_CHUNKS / GRB_WHOLE_WORKERS (defaults 8 / 4)
+    int left_order; // grb_left_order: how the order of the lefts is decided (grb_ctx_set_left_order)
+    u32 *stats_host; // mapped pinned words the kernels report to without any stream operation: [0] adjacent inversions seen by the
+    u32 *stats_dev;  // last bucket pass, [16 + b] tiles CTA b of the last pipelined launch could not stage; device alias
+    const void *hist_ls;  // AUTO on device buffers: the lefts of the previous call, and what it did with them
+    u64 hist_first, hist_total;
+    u32 hist_tiles;
+    int hist_bucketed;
     int sweep_mode; // 1 = staged rank sweep k_sweep3 for MIN / MAX / MEDIAN (default), 2 = k_sweep3 without staging, 0 = k_sweep2 only (debug)
     char err[512];
 };
@@ -355,6 +362,12 @@ int grb_index_prepare_bp(grb_ctx *ctx, grb_index *ix);
 // index.cu: exact prefixes of score * coordinate (the closed form of WEIGHTED_MEAN); sets ix->wm_unavailable when the
 // products do not fit the 128-bit fixed point (or the index has no exact sums) -- the caller then sweeps the members.
 int grb_index_prepare_wm(grb_ctx *ctx, grb_index *ix);
+
+// bucket.cu: left ranges in any order -- coordinate buckets, results written back through `rank`
+int grb_left_disorder(grb_ctx *ctx, const u32 *ls, u64 first, u64 total, int *per_1024);
+int grb_bucket_lefts(grb_ctx *ctx, const u64 *left_offsets, const u64 *extent, int nseq, const u32 *ls, const u32 *le, u32 *ls_b, u32 *le_b,
+                     u32 *rank, u32 *inversions_dev);
+int grb_unbucket_results(grb_ctx *ctx, u64 first, u64 total, int k, const double *out_b, const u8 *val_b, const u32 *rank, double *out, u8 *val);
 
 // sort.cu: stable LSD radix sort of (u64 key, u32 value) pairs; skips digits that do not vary and
 // the whole sort when the keys are already non-decreasing.  On return *keys_out / *vals_out point

@@ -133,7 +133,26 @@ int grb_ctx_create(int device, grb_ctx **out) {
         free(ctx);
         return GRB_ERR_OOM;
     }
+    // mapped pinned words: kernels report to the host without any stream operation (see grb_ctx::stats_host)
+    if (cudaHostAlloc((void **)&ctx->stats_host, 1024 * 4, cudaHostAllocMapped) != cudaSuccess ||
+        cudaHostGetDevicePointer((void **)&ctx->stats_dev, ctx->stats_host, 0) != cudaSuccess) {
+        cudaGetLastError();
+        ctx->stats_host = ctx->stats_dev = nullptr;  // order detection on device buffers is simply off
+    } else {
+        memset(ctx->stats_host, 0, 1024 * 4);
+    }
+    const char *lo = getenv("GRB_LEFT_ORDER");
+    ctx->left_order = lo ? atoi(lo) : GRB_LEFT_ORDER_AUTO;
     *out = ctx;
+    return GRB_OK;
+}
+
+int grb_ctx_set_left_order(grb_ctx *ctx, int order) {
+    if (!ctx) return GRB_ERR_INVALID_ARG;
+    if (order != GRB_LEFT_ORDER_AUTO && order != GRB_LEFT_ORDER_SORTED && order != GRB_LEFT_ORDER_UNSORTED)
+        return grb_fail(ctx, GRB_ERR_INVALID_ARG, "set_left_order: unknown order %d", order);
+    ctx->left_order = order;
+    ctx->hist_ls = nullptr;
     return GRB_OK;
 }
 
@@ -163,6 +182,7 @@ void grb_ctx_destroy(grb_ctx *ctx) {
     cudaFree(ctx->zeros);
     cudaFree(ctx->dev_flags);
     cudaFree(ctx->batch_dev);
+    if (ctx->stats_host) cudaFreeHost(ctx->stats_host);
     free(ctx->batch_host);
     free(ctx);
 }

@@ -70,7 +70,7 @@ struct PipeSeq {
     const uint4 *nf_a, *nf_b;
     u64 left_begin, left_end;
     double scale;
-    u32 tile_begin, bmax, fast_cmax;
+    u32 tile_begin, bmax, fast_cmax, n;
     int sh;
 };
 
@@ -80,6 +80,7 @@ struct PipeTile {      // one per lefts-ring slot
     int seq;           //                                                  (loader)
     u32 bin[4];        // bins of min l.end, max l.end, min l.start+1, max l.start+1   (surveyor)
     u32 bound[4];      // lut_a[bin0], lut_a[bin1 + 1], lut_b[bin2], lut_b[bin3 + 1]     (surveyor)
+    u32 nf;            // NULLS variants: 1 = some group of the tile may hold a non-finite score (surveyor)
 };
 
 struct PipeDesc {      // one per window-ring slot (loader -> consumers)
@@ -87,6 +88,7 @@ struct PipeDesc {      // one per window-ring slot (loader -> consumers)
     u32 vlo, vhi;
     u32 a0, b0, la0, lb0;
     u32 staged;        // 1: windows staged in the slot; 0: search in global memory (windows too large, or invalid lefts)
+    u32 nf;            // copied from the tile
     int seq;
 };
 
@@ -163,6 +165,7 @@ struct PipeOps {
     u32 *ub, *pp, *lb;  // PIPE_UBLB
     int need_pfx;       // PIPE_UBLB / PIPE_MULTI: some column needs the score prefixes
     u32 *valid_bits;    // single-reduction kernels: validity as bits (bit g of word g / 32) instead of bytes
+    u32 *stats;         // see TileOut::stats
 };
 
 // #(keys < x) among the 8 keys of the two aligned quads at q
@@ -219,6 +222,7 @@ __global__ void __launch_bounds__(PIPE_THREADS, 1) k_map_pipe(const SeqDev *__re
         q.tile_begin = sd->tile_begin;
         q.bmax = sd->lut_bmax;
         q.fast_cmax = sd->fast_cmax;
+        q.n = sd->n;
         q.sh = sd->lut_shift;
     }
     __syncthreads();
@@ -269,6 +273,7 @@ __global__ void __launch_bounds__(PIPE_THREADS, 1) k_map_pipe(const SeqDev *__re
     if (warp == 2) {
         // ================= window loader (C) =================
         const u64 pol = l2_evict_first_policy();
+        u32 unstaged = 0;
         for (u32 j = 0; j < nmine; j++) {
             const u32 sw = j % WST, sl = j % PIPE_LSTAGES;
             pipe_wait<64>(&S.statsL[sl], (j / PIPE_LSTAGES) & 1);
@@ -320,6 +325,7 @@ __global__ void __launch_bounds__(PIPE_THREADS, 1) k_map_pipe(const SeqDev *__re
                 d.la0 = la0;
                 d.lb0 = lb0;
                 d.staged = staged ? 1u : 0u;
+                d.nf = ti.nf;
                 if (staged)
                     mbar_arrive_expect_tx(&S.fullW[sw], total_bytes);
                 else
@@ -327,8 +333,11 @@ __global__ void __launch_bounds__(PIPE_THREADS, 1) k_map_pipe(const SeqDev *__re
             }
             __syncwarp();
             if (staged && bytes) tma_load_1d_hint(dst, src, bytes, &S.fullW[sw], pol);
+            unstaged += staged ? 0u : 1u;
             __syncwarp();
         }
+        // feedback for the caller's order detection: a plain store to a mapped host word, nothing on the stream
+        if (lane == 0 && mops.stats != nullptr && blockIdx.x < 1000) mops.stats[16 + blockIdx.x] = unstaged;
         return;
     }
 
@@ -387,6 +396,19 @@ __global__ void __launch_bounds__(PIPE_THREADS, 1) k_map_pipe(const SeqDev *__re
                 S.tile[sl].bin[lane] = bin_new;
                 S.tile[sl].bound[lane] = bound_new;
             }
+            if (NULLS) {
+                // Non-finite scores are rare: every ub of the tile lies in [bound0, bound1] and every lb in [bound2, bound3], so
+                // if the non-finite prefix counters agree at those four positions no group of the tile holds one, and the
+                // consumers skip their per-left counter loads (a second round trip here, where there is slack, not there).
+                u32 nf = 0;
+                if (q.nf_a != nullptr) {
+                    const u32 pos = min(bound_new, q.n);  // (an impossible bound marks a tile with invalid lefts)
+                    const uint4 c4 = qq < 2 ? q.nf_a[pos] : q.nf_b[pos];
+                    const u32 x0 = __shfl_sync(GRB_FULL, c4.x, 0), y0 = __shfl_sync(GRB_FULL, c4.y, 0), z0 = __shfl_sync(GRB_FULL, c4.z, 0);
+                    nf = __any_sync(GRB_FULL, lane < 4 && (c4.x != x0 || c4.y != y0 || c4.z != z0)) || tile_bad ? 1u : 0u;
+                }
+                if (lane == 0) S.tile[sl].nf = nf;
+            }
             __syncwarp();
             if (lane == 0) mbar_arrive(&S.statsL[sl]);
         }
@@ -417,6 +439,7 @@ __global__ void __launch_bounds__(PIPE_THREADS, 1) k_map_pipe(const SeqDev *__re
         const u32 bmax = q.bmax, fast_cmax = q.fast_cmax;
         const double scale = q.scale;
         const uint4 *__restrict__ nf_a = q.nf_a, *__restrict__ nf_b = q.nf_b;
+        const bool tile_nf = NULLS && nf_a != nullptr && d.nf != 0;
         u32 a[PIPE_LPT], b[PIPE_LPT];
         bool okv[PIPE_LPT];
         {
@@ -613,7 +636,7 @@ __global__ void __launch_bounds__(PIPE_THREADS, 1) k_map_pipe(const SeqDev *__re
                     sum[k] = fx_to_double(PA - PB, sd->e0);
                 }
             }
-            if (NULLS && nf_a != nullptr && okv[k]) {
+            if (NULLS && tile_nf && okv[k]) {
                 const uint4 na = nf_a[ub[k]], nb = nf_b[lbk[k]];
                 sum[k] = nf_rule(sum[k], na.x - nb.x, na.y - nb.y, na.z - nb.z);
             }
@@ -726,6 +749,7 @@ int launch_var(grb_ctx *ctx, const Batch &b, int s0, int s1, const u32 *ls, cons
     mops.lb = o.lb;
     mops.need_pfx = o.need_sum;
     mops.valid_bits = valid_bits;
+    mops.stats = o.stats;
     k_map_pipe<FAST, VAR><<<grid, PIPE_THREADS, sizeof(Smem), ctx->stream>>>(b.seqs + s0, s1 - s0, t0, t1 - t0, ls, le, o.out, o.out_valid, flags,
                                                                           o.flags, mops);
     GRB_LAUNCHED(ctx);

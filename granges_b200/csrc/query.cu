@@ -924,7 +924,7 @@ int grb_filter_overlaps(grb_ctx *ctx, const grb_index *idx, const uint32_t *ls, 
 
 static int map_joins_impl(grb_ctx *ctx, const grb_index *const *idx, const uint64_t *left_offsets, int nseq, const uint32_t *ls,
                           const uint32_t *le, const int *ops, int k, double *out, uint8_t *out_valid, bool allow_chunks,
-                          uint32_t *valid_bits = nullptr);
+                          uint32_t *valid_bits = nullptr, bool no_bucket = false);
 
 // Host buffers, many seqnames: run the seqnames in chunks so that the upload of the next chunk's lefts, the kernels
 // of the current one and the download of the previous chunk's results overlap (PCIe is full duplex).
@@ -1012,9 +1012,46 @@ __global__ void k_pack_bits(const u8 *__restrict__ bytes, u64 n, u32 *__restrict
     if (lane_id() == 0 && (i & ~31ull) < n) bits[i >> 5] = m;
 }
 
+// Should the lefts of this call go through the coordinate buckets (bucket.cu)?  See grb_left_order in the header.
+static int decide_bucketing(grb_ctx *ctx, const u32 *ls, u64 first, u64 total, u32 ntiles, bool *bucket, bool *report) {
+    *bucket = *report = false;
+    const u64 n = total - first;
+    if (n < (1u << 16) || n >= 0xffffffffull) return GRB_OK;  // small calls: the searches are cheap either way
+    if (ctx->left_order == GRB_LEFT_ORDER_SORTED) return GRB_OK;
+    if (ctx->left_order == GRB_LEFT_ORDER_UNSORTED) {
+        *bucket = true;
+        return GRB_OK;
+    }
+    if (!grb_is_device_ptr(ls)) {
+        int d = 0;
+        GRB_TRY(grb_left_disorder(ctx, ls, first, total, &d));
+        *bucket = d > 100;  // more than ~10 % of the sampled neighbours out of order
+        return GRB_OK;
+    }
+    if (!ctx->stats_host) return GRB_OK;
+    // device buffers: what did the previous call learn about this very buffer?
+    if (ctx->hist_ls == (const void *)ls && ctx->hist_first == first && ctx->hist_total == total) {
+        if (ctx->hist_bucketed) {
+            *bucket = (u64)ctx->stats_host[0] * 1024 / n > 100;  // adjacent inversions seen by the last bucket pass
+        } else {
+            u64 unstaged = 0;
+            for (int b = 0; b < 1000; b++) unstaged += ctx->stats_host[16 + b];
+            *bucket = unstaged * 8 > ctx->hist_tiles;  // more than an eighth of the tiles fell off the staged path
+        }
+    }
+    ctx->hist_ls = ls;
+    ctx->hist_first = first;
+    ctx->hist_total = total;
+    ctx->hist_tiles = ntiles;
+    ctx->hist_bucketed = *bucket;
+    memset(ctx->stats_host, 0, 1024 * 4);
+    *report = true;
+    return GRB_OK;
+}
+
 static int map_joins_impl(grb_ctx *ctx, const grb_index *const *idx, const uint64_t *left_offsets, int nseq, const uint32_t *ls,
                           const uint32_t *le, const int *ops, int k, double *out, uint8_t *out_valid, bool allow_chunks,
-                          uint32_t *valid_bits) {
+                          uint32_t *valid_bits, bool no_bucket) {
     GRB_TRY(enter(ctx));
     if (!left_offsets || !ops) return grb_fail(ctx, GRB_ERR_INVALID_ARG, "map_joins: NULL left_offsets / ops");
     if (k < 1 || k > GRB_MAX_OPS) return grb_fail(ctx, GRB_ERR_INVALID_ARG, "map_joins: k must be in [1, %d]", GRB_MAX_OPS);
@@ -1120,6 +1157,55 @@ static int map_joins_impl(grb_ctx *ctx, const grb_index *const *idx, const uint6
     GRB_TRY(make_batch(ctx, idx, left_offsets, nseq, &b));
     if (b.total == 0 || b.ntiles == 0) return GRB_OK;  // (a batch that starts past 0 may hold no lefts at all)
     if (!ls || !le || !out || (!out_valid && !valid_bits)) return grb_fail(ctx, GRB_ERR_INVALID_ARG, "map_joins: NULL buffer");
+    bool bucket = false, report = false;
+    if (!no_bucket) GRB_TRY(decide_bucketing(ctx, ls, left_offsets[0], b.total, b.ntiles, &bucket, &report));
+    if (bucket) {
+        // lefts in coordinate buckets -> the same call on the bucketed copies -> rows back to where their lefts came from
+        const u64 first = left_offsets[0], n = b.total - first;
+        InBuf dls, dle;
+        OutBuf dout, dval, dbits;
+        TempBuf ls_b, le_b, rank, out_b, val_b, val_tmp, inv;
+        GRB_TRY(dls.stage(ctx, ls + first, n * 4));
+        GRB_TRY(dle.stage(ctx, le + first, n * 4));
+        GRB_TRY(ls_b.alloc(ctx, b.total * 4));
+        GRB_TRY(le_b.alloc(ctx, b.total * 4));
+        GRB_TRY(rank.alloc(ctx, b.total * 4));
+        GRB_TRY(out_b.alloc(ctx, b.total * (u64)k * 8));
+        GRB_TRY(val_b.alloc(ctx, b.total * (u64)k));
+        GRB_TRY(inv.alloc(ctx, 4));
+        std::vector<u64> extent((size_t)nseq);
+        for (int s = 0; s < nseq; s++) {
+            const grb_index *ix = idx ? idx[s] : nullptr;
+            extent[s] = ix && ix->n ? ((u64)ix->lut_bmax << ix->lut_shift) : 0;
+        }
+        // (the staged copies start at the batch's first left: shift the pointers back so that absolute positions index them)
+        GRB_TRY(grb_bucket_lefts(ctx, left_offsets, extent.data(), nseq, dls.as<u32>() - first, dle.as<u32>() - first, ls_b.as<u32>(), le_b.as<u32>(),
+                                 rank.as<u32>(), inv.as<u32>()));
+        if (report) GRB_CUDA(ctx, cudaMemcpyAsync(ctx->stats_host, inv.p, 4, cudaMemcpyDeviceToHost, ctx->stream));
+        GRB_TRY(map_joins_impl(ctx, idx, left_offsets, nseq, ls_b.as<u32>(), le_b.as<u32>(), ops, k, out_b.as<double>(), val_b.as<u8>(), false, nullptr,
+                               true));
+        GRB_TRY(dout.stage(ctx, out + first * (u64)k, n * (u64)k * 8));
+        u8 *vdst;
+        if (valid_bits) {
+            GRB_TRY(dbits.stage(ctx, valid_bits, ((b.total * (u64)k + 31) / 32) * 4));
+            GRB_TRY(val_tmp.alloc(ctx, b.total * (u64)k));
+            vdst = val_tmp.as<u8>();
+        } else {
+            GRB_TRY(dval.stage(ctx, out_valid + first * (u64)k, n * (u64)k));
+            vdst = dval.as<u8>() - first * (u64)k;
+        }
+        GRB_TRY(grb_unbucket_results(ctx, first, b.total, k, out_b.as<double>(), val_b.as<u8>(), rank.as<u32>(), dout.as<double>() - first * (u64)k, vdst));
+        if (valid_bits) {
+            const u64 nflat = b.total * (u64)k;
+            k_pack_bits<<<(unsigned)((nflat + 255) / 256), 256, 0, ctx->stream>>>(val_tmp.as<u8>(), nflat, dbits.as<u32>());
+            GRB_LAUNCHED(ctx);
+        }
+        GRB_TRY(dout.finish(ctx));
+        GRB_TRY(dval.finish(ctx));
+        GRB_TRY(dbits.finish(ctx));
+        if (dout.host || dval.host || dbits.host) return grb_check_flags(ctx);
+        return GRB_OK;
+    }
     if (allow_chunks && nseq >= 2 && b.total >= (1u << 22) && !grb_is_device_ptr(ls) && !grb_is_device_ptr(le) &&
         !grb_is_device_ptr(out) && !grb_is_device_ptr(out_valid))
         return map_joins_host_chunked(ctx, idx, left_offsets, nseq, ls, le, ops, k, out, out_valid);
@@ -1132,6 +1218,7 @@ static int map_joins_impl(grb_ctx *ctx, const grb_index *const *idx, const uint6
     TileOut o;
     memset(&o, 0, sizeof(o));
     o.flags = ctx->dev_flags;
+    o.stats = report ? ctx->stats_dev : nullptr;
     o.out = dout.as<double>();
     o.k = k;
     o.need_sum = need_sum;

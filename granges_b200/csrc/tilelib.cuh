@@ -17,6 +17,7 @@ struct TileOut {
     int need_sum;
     int ops[GRB_MAX_OPS];
     u32 *flags;  // context flag word (bit 0: invalid left range seen)
+    u32 *stats;  // pipelined kernel: stats[16 + blockIdx.x] = tiles this CTA could not stage (mapped host words; may be NULL)
 };
 
 // ---- host side: one batch = the seqnames of one call, concatenated in GenomeMap order -------------------

@@ -32,6 +32,18 @@ extern "C" int grb_map_joins_whole_f64(grb_ctx *ctx, int nseq, const uint32_t *c
         if (left_offsets[s + 1] < left_offsets[s]) return grb_fail(ctx, GRB_ERR_INVALID_ARG, "map_joins_whole: left_offsets must be non-decreasing");
     if (total == 0) return GRB_OK;
     GRB_CUDA(ctx, cudaStreamSynchronize(ctx->stream));  // earlier work on the caller's stream precedes the workers'
+    // The lefts are on the host: sample their order here, once, and tell the per-chunk calls (which only see device copies)
+    const int saved_order = ctx->left_order;
+    if (saved_order == GRB_LEFT_ORDER_AUTO) {
+        int disorder = 0;
+        GRB_TRY(grb_left_disorder(ctx, ls, 0, total, &disorder));
+        ctx->left_order = disorder > 100 ? GRB_LEFT_ORDER_UNSORTED : GRB_LEFT_ORDER_SORTED;
+    }
+    struct RestoreOrder {
+        grb_ctx *c;
+        int v;
+        ~RestoreOrder() { c->left_order = v; }
+    } restore_order{ctx, saved_order};
 
     // ---- chunks of whole seqnames, about an eighth of the transfer volume each
     std::vector<int> cuts{0};

@@ -220,3 +220,71 @@ def test_output_buffers_are_never_copied(ctx):
         ctx.map_joins_batch([ix], off, c["ls"], c["le"], ["mean"], out=np.empty((100, 2))[:, :1], out_valid=gv)
     with pytest.raises((TypeError, ValueError)):
         ctx.map_joins_batch([ix], off, c["ls"], c["le"], ["mean"], out=np.empty((99, 1)), out_valid=gv)
+
+
+def test_unsorted_lefts_go_through_buckets(ctx, orc):
+    """Lefts in any order give the reference's rows (src/granges.rs:935-984 walks the left container as it is).  Large
+    unsorted calls are bucketed by coordinate on the device and their rows written back: host buffers are sampled on
+    the host (AUTO), and the option forces either path -- all three must agree with the oracle and with each other."""
+    import granges_b200 as gb
+
+    c = random_case(801, 150_000, 120_000, span=3_000_000, maxlen=400, null_frac=0.05)
+    nl = len(c["ls"])
+    ix = ctx.index_build(c["rs"], c["re"]).set_scores(c["scores"], c["valid"])
+    off = np.array([0, nl], np.uint64)
+    for ops in (["mean"], ["sum", "count", "mean"], ["min", "median", "mean"]):
+        want, wv, abs_sums, nvalid = oracle_refs(orc, c, ops)
+        res = {}
+        ctx.set_left_order("sorted")
+        ctx.map_joins_batch([ix], off, c["ls"], c["le"], ops)  # (builds the member tables these reductions need, once)
+        for order in ("auto", "sorted", "unsorted"):
+            ctx.set_left_order(order)
+            n0 = ctx.launch_count
+            res[order] = ctx.map_joins_batch([ix], off, c["ls"], c["le"], ops) + (ctx.launch_count - n0,)
+            assert_map_equal(res[order][0], res[order][1], want, wv, ops, abs_sums, nvalid)
+        ctx.set_left_order("auto")
+        assert res["auto"][2] == res["unsorted"][2] > res["sorted"][2]  # AUTO sampled the host buffer and bucketed
+        for order in ("sorted", "unsorted"):
+            assert (res[order][1] == res["auto"][1]).all() and same_bits(res[order][0][wv == 1], res["auto"][0][wv == 1])
+    # sorted host lefts are left alone: AUTO launches what SORTED launches
+    o = np.lexsort((c["le"], c["ls"]))
+    counts = {}
+    for order in ("sorted", "auto"):
+        ctx.set_left_order(order)
+        n0 = ctx.launch_count
+        ctx.map_joins_batch([ix], off, c["ls"][o], c["le"][o], ["mean"])
+        counts[order] = ctx.launch_count - n0
+    ctx.set_left_order("auto")
+    assert counts["auto"] == counts["sorted"]
+
+
+def test_unsorted_device_lefts_are_learned(ctx, orc):
+    """Device buffers in AUTO mode put nothing extra on the stream: the pipelined kernel reports the tiles it could not
+    stage, and the next call on the same buffer takes the buckets.  Several seqnames, one absent, batch starting past 0."""
+    import torch
+
+    parts, idxs, off = [], [], [0]
+    for s, nl in enumerate([70_000, 0, 90_000, 40_000]):
+        c = random_case(810 + s, nl, 60_000, span=2_000_000, maxlen=300)
+        parts.append(c)
+        idxs.append(ctx.index_build(c["rs"], c["re"]).set_scores(c["scores"]) if s != 3 else None)
+        off.append(off[-1] + nl)
+    ls = torch.from_numpy(np.concatenate([c["ls"] for c in parts]).astype(np.int32)).cuda()
+    le = torch.from_numpy(np.concatenate([c["le"] for c in parts]).astype(np.int32)).cuda()
+    off = np.array(off, np.uint64)
+    launches, outs = [], []
+    for rep in range(3):
+        n0 = ctx.launch_count
+        out, ov = ctx.map_joins_batch(idxs, off, ls, le, ["mean"])
+        ctx.sync()
+        launches.append(ctx.launch_count - n0)
+        outs.append((out.cpu().numpy(), ov.cpu().numpy()))
+    assert launches[1] > launches[0] and launches[2] == launches[1]  # learned after the first call, and stays
+    for out, ov in outs:
+        for s, c in enumerate(parts):
+            sl = slice(int(off[s]), int(off[s + 1]))
+            if idxs[s] is None:
+                assert not ov[sl].any()
+                continue
+            want, wv, abs_sums, nvalid = oracle_refs(orc, c, ["mean"])
+            assert_map_equal(out[sl], ov[sl], want, wv, ["mean"], abs_sums, nvalid)
