@@ -374,3 +374,6 @@ int grb_unbucket_results(grb_ctx *ctx, u64 first, u64 total, int k, const double
 // at whichever of the two buffers holds the result.
 int grb_sort_pairs(grb_ctx *ctx, u64 *keys, u32 *vals, u64 *keys_alt, u32 *vals_alt, size_t n, u64 **keys_out,
                    u32 **vals_out, bool *was_sorted);
+// sort.cu: stable argsort of u32 keys (read only): keys_sorted[i] = keys[perm[i]], equal keys in position order.
+// tmp_keys / tmp_vals: scratch of n entries each.
+int grb_argsort_u32(grb_ctx *ctx, const u32 *keys, u32 *keys_sorted, u32 *perm, u32 *tmp_keys, u32 *tmp_vals, size_t n);

@@ -55,8 +55,7 @@ __global__ void k_idx_keys(const u64 *__restrict__ data_idx, size_t n, u64 *__re
 
 __global__ void k_unpack_start_order(const u64 *__restrict__ keys, const u32 *__restrict__ perm,
                                      const u64 *__restrict__ data_idx, size_t n, u32 *__restrict__ starts,
-                                     u32 *__restrict__ ends, u32 *__restrict__ didx, u64 *__restrict__ keys2,
-                                     u32 *__restrict__ vals2) {
+                                     u32 *__restrict__ ends, u32 *__restrict__ didx) {
     size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= n + PAD) return;
     if (i >= n) {
@@ -69,21 +68,9 @@ __global__ void k_unpack_start_order(const u64 *__restrict__ keys, const u32 *__
     starts[i] = (u32)(k >> 32);
     ends[i] = (u32)k;
     didx[i] = data_idx ? (u32)data_idx[p] : p;
-    keys2[i] = (u64)(u32)k;
-    vals2[i] = (u32)i;
 }
 
-__global__ void k_unpack_end_order(const u64 *__restrict__ keys2, const u32 *__restrict__ vals2, size_t n,
-                                   u32 *__restrict__ ends_sorted, u32 *__restrict__ perm_e) {
-    size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
-    if (i >= n + PAD) return;
-    if (i >= n) {
-        ends_sorted[i] = 0xffffffffu;
-        return;
-    }
-    ends_sorted[i] = (u32)keys2[i];
-    perm_e[i] = vals2[i];
-}
+__global__ void k_pad_keys(u32 *__restrict__ tail) { tail[threadIdx.x] = 0xffffffffu; }
 
 __global__ void k_block_max_end(const u32 *__restrict__ ends, size_t n, u32 *__restrict__ bme) {
     // one warp per block of 64 rights
@@ -101,25 +88,18 @@ __global__ void k_block_max_end(const u32 *__restrict__ ends, size_t n, u32 *__r
 }
 
 // lut[b] = #keys < (b << shift) for b in [0, bmax]; entries bmax+1 .. bmax+PAD = n.
+// Position i is the answer for every bin b with bin(keys[i-1]) < b <= bin(keys[i]) (keys sorted; bin(keys[-1]) = -1,
+// and the n-th "key" closes the table): each thread fills the bins between its key and its predecessor's -- coalesced
+// reads, no searching.  The table has about n / 2 bins, so the fills are short on average.
 __global__ void k_build_lut(const u32 *__restrict__ keys, u32 n, int shift, u32 bmax, u32 *__restrict__ lut, u16 *__restrict__ lut16) {
-    u32 b = blockIdx.x * blockDim.x + threadIdx.x;
-    if (b > bmax + PAD) return;
-    if (b > bmax) {
-        lut[b] = n;
-        lut16[b] = (u16)n;
-        return;
+    const u32 i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i > n) return;
+    const long long prev = i == 0 ? -1ll : (long long)min(keys[i - 1] >> shift, bmax);
+    const long long cur = i == n ? (long long)bmax + PAD : (long long)min(keys[i] >> shift, bmax);
+    for (long long b = prev + 1; b <= cur; b++) {
+        lut[b] = i;
+        lut16[b] = (u16)i;
     }
-    u64 x = (u64)b << shift;
-    u32 lo = 0, hi = n;
-    while (lo < hi) {
-        u32 mid = lo + ((hi - lo) >> 1);
-        if ((u64)keys[mid] < x)
-            lo = mid + 1;
-        else
-            hi = mid;
-    }
-    lut[b] = lo;
-    lut16[b] = (u16)lo;
 }
 
 // ---- scores ------------------------------------------------------------------
@@ -188,19 +168,36 @@ __global__ void k_gather_scores(const u32 *__restrict__ didx, size_t n, const do
         oor |= __shfl_xor_sync(GRB_FULL, oor, s);
         nz |= __shfl_xor_sync(GRB_FULL, nz, s);
     }
+    // block reduce, then one set of atomics per block
+    __shared__ int s_lsb[8], s_top[8];
+    __shared__ u32 s_flags[8], s_null[8];
+    const u32 w = threadIdx.x >> 5;
     if (lane_id() == 0) {
-        // plain reads first: after the first few warps almost nobody needs the atomic any more
+        s_lsb[w] = lsb;
+        s_top[w] = top;
+        s_flags[w] = nonfinite | (nan << 1) | (sub << 2) | (oor << 3) | (nz << 4);
+        s_null[w] = nnull;
+    }
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        u32 fl = 0;
+        for (u32 k = 0; k < (blockDim.x >> 5); k++) {
+            lsb = min(lsb, s_lsb[k]);
+            top = max(top, s_top[k]);
+            fl |= s_flags[k];
+            if (k) nnull += s_null[k];
+        }
         volatile ScoreStats *vs = st;
-        if (nz) {
+        if (fl & 16u) {
             if (lsb < vs->min_lsb_exp) atomicMin(&st->min_lsb_exp, lsb);
             if (top > vs->max_exp) atomicMax(&st->max_exp, top);
             if (!vs->n_nonzero) atomicOr(&st->n_nonzero, 1u);
         }
         if (nnull) atomicAdd(&st->n_null, nnull);
-        if (nonfinite && !vs->has_nonfinite) atomicOr(&st->has_nonfinite, 1u);
-        if (nan && !vs->has_nan) atomicOr(&st->has_nan, 1u);
-        if (sub && !vs->has_subnormal) atomicOr(&st->has_subnormal, 1u);
-        if (oor && !vs->idx_out_of_range) atomicOr(&st->idx_out_of_range, 1u);
+        if ((fl & 1u) && !vs->has_nonfinite) atomicOr(&st->has_nonfinite, 1u);
+        if ((fl & 2u) && !vs->has_nan) atomicOr(&st->has_nan, 1u);
+        if ((fl & 4u) && !vs->has_subnormal) atomicOr(&st->has_subnormal, 1u);
+        if ((fl & 8u) && !vs->idx_out_of_range) atomicOr(&st->idx_out_of_range, 1u);
     }
 }
 
@@ -342,28 +339,43 @@ __global__ void k_masked_coords(const u32 *__restrict__ coord, const u32 *__rest
 
 // Exclusive scan of nb i128 block sums by one CTA (nb = n/256 + 1: small).
 __global__ void __launch_bounds__(1024) k_scan_i128_single(const i128 *__restrict__ in, size_t nb, i128 *__restrict__ out) {
-    __shared__ u64 s_lo[1024], s_hi[1024];
+    __shared__ u64 s_lo[32], s_hi[32];
     const size_t per = (nb + 1023) / 1024;
     const size_t lo = (size_t)threadIdx.x * per;
     const size_t hi = lo + per < nb ? lo + per : nb;
     i128 t = 0;
     for (size_t i = lo; i < hi; i++) t += in[i];
-    s_lo[threadIdx.x] = (u64)t;
-    s_hi[threadIdx.x] = (u64)((u128)t >> 64);
-    __syncthreads();
-    if (threadIdx.x == 0) {
-        i128 run = 0;
-        for (int k = 0; k < 1024; k++) {
-            i128 c = (i128)(((u128)s_hi[k] << 64) | s_lo[k]);
-            s_lo[k] = (u64)run;
-            s_hi[k] = (u64)((u128)run >> 64);
-            run += c;
-        }
+    // inclusive scan of the 1024 thread sums: warp shuffles, then the 32 warp totals by warp 0
+    const u32 lane = lane_id(), warp = threadIdx.x >> 5;
+    i128 incl = t;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {
+        const u64 tlo = __shfl_up_sync(GRB_FULL, (u64)incl, o);
+        const u64 thi = __shfl_up_sync(GRB_FULL, (u64)((u128)incl >> 64), o);
+        if (lane >= (u32)o) incl += (i128)(((u128)thi << 64) | tlo);
+    }
+    if (lane == 31) {
+        s_lo[warp] = (u64)incl;
+        s_hi[warp] = (u64)((u128)incl >> 64);
     }
     __syncthreads();
-    i128 run = (i128)(((u128)s_hi[threadIdx.x] << 64) | s_lo[threadIdx.x]);
+    if (warp == 0) {
+        i128 w = (i128)(((u128)s_hi[lane] << 64) | s_lo[lane]);
+        i128 wi = w;
+#pragma unroll
+        for (int o = 1; o < 32; o <<= 1) {
+            const u64 tlo = __shfl_up_sync(GRB_FULL, (u64)wi, o);
+            const u64 thi = __shfl_up_sync(GRB_FULL, (u64)((u128)wi >> 64), o);
+            if (lane >= (u32)o) wi += (i128)(((u128)thi << 64) | tlo);
+        }
+        const i128 wex = wi - w;  // exclusive prefix of the warp totals
+        s_lo[lane] = (u64)wex;
+        s_hi[lane] = (u64)((u128)wex >> 64);
+    }
+    __syncthreads();
+    i128 run = (i128)(((u128)s_hi[warp] << 64) | s_lo[warp]) + incl - t;
     for (size_t i = lo; i < hi; i++) {
-        i128 c = in[i];
+        const i128 c = in[i];
         out[i] = run;
         run += c;
     }
@@ -734,23 +746,21 @@ int grb_index_build(grb_ctx *ctx, const uint32_t *starts, const uint32_t *ends, 
             rc = grb_fail(ctx, GRB_ERR_UNSUPPORTED, "index_build: data index >= 2^32-1");
             break;
         }
-        // the other ping-pong pair is free now: reuse it for the end-order sort
+        // the other ping-pong pair is free now: scratch of the end-order sort
         u64 *k2 = (ks == k0.as<u64>()) ? k1.as<u64>() : k0.as<u64>();
         u32 *v2 = (vs == v0.as<u32>()) ? v1.as<u32>() : v0.as<u32>();
         k_unpack_start_order<<<blocks_for(n + PAD, 256), 256, 0, ctx->stream>>>(ks, vs, d_idx.as<u64>(), n, ix->starts, ix->ends,
-                                                                               ix->didx, k2, v2);
+                                                                               ix->didx);
         ctx->launches++;
-        // end order: sort (end, position) -- the start-order buffers double as scratch
-        u64 *ke;
-        u32 *ve;
-        if ((rc = grb_sort_pairs(ctx, k2, v2, ks, vs, n, &ke, &ve, nullptr))) break;
-        k_unpack_end_order<<<blocks_for(n + PAD, 256), 256, 0, ctx->stream>>>(ke, ve, n, ix->ends_sorted, ix->perm_e);
+        // end order: a stable argsort of the ends as u32 keys, whose last pass lands in ends_sorted / perm_e
+        if ((rc = grb_argsort_u32(ctx, ix->ends, ix->ends_sorted, ix->perm_e, (u32 *)k2, v2, n))) break;
+        k_pad_keys<<<1, PAD, 0, ctx->stream>>>(ix->ends_sorted + n);
         ctx->launches++;
         {
             // coordinate bins of ~2-4 rights each (so one round of four compares usually ends a search);
             // the largest end bounds every key
             u32 maxend = 0;
-            if (n) cudaMemcpyAsync(&maxend, ke + (n - 1), 4, cudaMemcpyDeviceToHost, ctx->stream);  // low half of the last u64 key
+            if (n) cudaMemcpyAsync(&maxend, ix->ends_sorted + (n - 1), 4, cudaMemcpyDeviceToHost, ctx->stream);
             cudaStreamSynchronize(ctx->stream);
             int shift = 0;
             const char *ld = getenv("GRB_LUT_DIV");  // tuning knob: average rights per bin (default 2)
@@ -763,9 +773,9 @@ int grb_index_build(grb_ctx *ctx, const uint32_t *starts, const uint32_t *ends, 
             if ((rc = dev_alloc(ctx, (void **)&ix->lut_b, entries * 4))) break;
             if ((rc = dev_alloc(ctx, (void **)&ix->lut16_a, entries * 2))) break;
             if ((rc = dev_alloc(ctx, (void **)&ix->lut16_b, entries * 2))) break;
-            k_build_lut<<<blocks_for(entries, 256), 256, 0, ctx->stream>>>(ix->starts, (u32)n, shift, ix->lut_bmax, ix->lut_a, ix->lut16_a);
+            k_build_lut<<<blocks_for(n + 1, 256), 256, 0, ctx->stream>>>(ix->starts, (u32)n, shift, ix->lut_bmax, ix->lut_a, ix->lut16_a);
             ctx->launches++;
-            k_build_lut<<<blocks_for(entries, 256), 256, 0, ctx->stream>>>(ix->ends_sorted, (u32)n, shift, ix->lut_bmax, ix->lut_b, ix->lut16_b);
+            k_build_lut<<<blocks_for(n + 1, 256), 256, 0, ctx->stream>>>(ix->ends_sorted, (u32)n, shift, ix->lut_bmax, ix->lut_b, ix->lut16_b);
             ctx->launches++;
         }
         if (n) {
