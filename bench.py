@@ -597,7 +597,7 @@ def main():
     torch.cuda.set_stream(stream)
     ctx = gb.Context(local_rank, stream=stream)
     # ---- synthetic data, generated on the device, only what this rank's units touch
-    idxs, offs, ls_parts, le_parts, host_parts = [], [0], [], [], []
+    idxs, offs, ls_parts, le_parts = [], [0], [], []
     n_right_mine = 0
     t_build = 0.0
     for p in mine:
@@ -621,8 +621,6 @@ def main():
         offs.append(offs[-1] + (b - a))
         ls_parts.append(ls_s)
         le_parts.append(le_s)
-        if not args.no_e2e:
-            host_parts.append((rs.cpu(), re.cpu(), sc.cpu()))
         del rs, re, sc
     ls = torch.cat(ls_parts) if ls_parts else torch.zeros(0, dtype=torch.int32, device=dev)
     le = torch.cat(le_parts) if le_parts else torch.zeros(0, dtype=torch.int32, device=dev)
@@ -708,45 +706,65 @@ def main():
         variants = run_variants(ctx, idxs, offs, ls, le, nl_per, nr_per, dev, float(np.mean(per_step)), args.steps, args.warmup)
         configs = {"C3": run_c3(ctx, idxs, offs, ls, le, nl_per, nr_per, dev, peak)}
 
-    # ---- e2e: host (pinned) buffers through the C ABI, copies inside the timed region; every rank does its own
-    # units from its own host buffers, wall clock between barriers, max over ranks
+    # ---- e2e: the whole job from HOST buffers through ONE call of the C ABI -- grb_map_joins_whole_f64 at N = 1,
+    # grb_map_joins_whole_f64_mgpu over the N GPUs of the box at N > 1 (one process: rank 0 makes the call from the host
+    # arrays of the WHOLE job, the gather into one output array is inside the timed region; the other ranks free their
+    # GPU memory and wait).  Measured for page-locked and for pageable host buffers.
     e2e = None
     if not args.no_e2e:
-        h_ls, h_le = ls.cpu().pin_memory(), le.cpu().pin_memory()
-        h_rights = [(a.pin_memory(), b.pin_memory(), c.pin_memory()) for a, b, c in host_parts]
-        h_out = torch.empty((nl_mine, k), dtype=torch.float64).pin_memory()
-        h_ov = torch.empty((nl_mine, k), dtype=torch.uint8).pin_memory()
         call = None
         for ix in idxs:
             ix.close()
         idxs.clear()
-        del out, ov
+        del out, ov, ls, le
         torch.cuda.empty_cache()
-
-        def e2e_step():
-            if not nl_mine:
-                return 0.0
-            ctx.map_whole([(a.numpy().view(np.uint32), b.numpy().view(np.uint32), c.numpy()) for a, b, c in h_rights], offs,
-                          h_ls.numpy().view(np.uint32), h_le.numpy().view(np.uint32), ops, out=h_out.numpy(), out_valid=h_ov.numpy())
-            return float(h_out[0, 0])  # the result is on the host
-
-        e2e_steps = max(2, min(args.steps, 5))
-        e2e_step()
         barrier()
-        t0 = time.perf_counter()
-        for _ in range(e2e_steps):
-            e2e_step()
-        torch.cuda.synchronize()
-        te = torch.tensor([time.perf_counter() - t0], dtype=torch.float64, device=dev)
-        if dist is not None:
-            dist.all_reduce(te, op=dist.ReduceOp.MAX)
-        e2e_s = float(te.item()) / e2e_steps
-        nr_all = int(agg[2].item())
-        e2e = {"value": args.lefts / e2e_s, "unit": "left ranges/s", "h2d_bytes_per_step": nr_all * 16 + nl_total * 8,
-               "d2h_bytes_per_step": nl_total * k * 9, "ms_per_step": e2e_s * 1e3, "steps": e2e_steps,
-               "includes": "grb_map_joins_whole_f64 = `granges map` in one call: H2D of rights + scores + lefts, index builds, map pass, D2H "
-                           "of the results, pipelined per seqname; pinned host buffers, per rank for its own units; wall clock, max over ranks"}
-        del h_rights, h_ls, h_le
+        if rank == 0:
+            host = []
+            for s in range(22):
+                rs, re, sc = gen_ranges(s, nr_per[s], 14, dev, True)
+                a, b = gen_ranges(s, nl_per[s], 13, dev, False)
+                host.append(tuple(t.cpu().numpy() for t in (rs, re, sc, a, b)))
+                del rs, re, sc, a, b
+            torch.cuda.empty_cache()
+            p_ls = np.concatenate([h[3] for h in host]).view(np.uint32)
+            p_le = np.concatenate([h[4] for h in host]).view(np.uint32)
+            p_rights = [(h[0].view(np.uint32), h[1].view(np.uint32), h[2]) for h in host]
+            p_out, p_ov = np.empty((args.lefts, k), np.float64), np.empty((args.lefts, k), np.uint8)
+            pin = lambda x: torch.from_numpy(x).pin_memory().numpy()
+            h_ls, h_le = pin(p_ls), pin(p_le)
+            h_rights = [tuple(pin(x) for x in r) for r in p_rights]
+            h_out, h_ov = pin(p_out), pin(p_ov)
+            devices = list(range(world))
+
+            def e2e_step(rights, l_s, l_e, o, v):
+                if world == 1:
+                    ctx.map_whole(rights, left_off, l_s, l_e, ops, out=o, out_valid=v)
+                else:
+                    gb.map_whole_mgpu(devices, rights, left_off, l_s, l_e, ops, out=o, out_valid=v)
+                return float(o[0, 0])  # the result is on the host
+
+            def timed(args_):
+                e2e_step(*args_)
+                n = max(2, min(args.steps, 5))
+                t0 = time.perf_counter()
+                for _ in range(n):
+                    e2e_step(*args_)
+                return (time.perf_counter() - t0) / n, n
+
+            e2e_s, e2e_steps = timed((h_rights, h_ls, h_le, h_out, h_ov))
+            pg_s, _ = timed((p_rights, p_ls, p_le, p_out, p_ov))
+            same = bool((p_ov == h_ov).all() and (p_out[p_ov == 1] == h_out[h_ov == 1]).all())
+            e2e = {"value": args.lefts / e2e_s, "unit": "left ranges/s", "h2d_bytes_per_step": args.rights * 16 + args.lefts * 8,
+                   "d2h_bytes_per_step": args.lefts * k * 9, "ms_per_step": e2e_s * 1e3, "steps": e2e_steps,
+                   "pageable": {"value": args.lefts / pg_s, "ms_per_step": pg_s * 1e3, "equals_pinned": same,
+                                "how": "the same call on ordinary (pageable) numpy arrays: the library stages them through its own page-locked rings"},
+                   "includes": ("grb_map_joins_whole_f64" if world == 1 else f"grb_map_joins_whole_f64_mgpu over {world} GPUs (one process, one host "
+                                "thread + context per GPU, contiguous runs of seqnames, every GPU writes its rows of the one output array)") +
+                               " = `granges map` in one call: H2D of rights + scores + lefts, index builds, map pass, D2H of the results, pipelined "
+                               "per seqname; page-locked host buffers; wall clock of the calling process"}
+            del h_rights, h_ls, h_le, p_rights, p_ls, p_le, host
+        barrier()
 
     if rank != 0:
         if dist is not None:

@@ -4,10 +4,10 @@ The product is the C-ABI shared library `libgranges_b200.so` (include/granges_b2
 is its Python face.  Importing it requires the built library -- there is no CPU fallback.
 """
 from . import _capi
-from .api import OPS, Context, GRangesError, Index, PreparedMap, Windows, shard_plan
+from .api import OPS, Context, GRangesError, Index, PreparedMap, Windows, map_whole_mgpu, shard_plan
 
 from . import granges  # noqa: E402  (the reference's container names over the C ABI)
 
 _capi.lib()  # fail loudly at import time if the CUDA library is missing
 
-__all__ = ["Context", "Index", "Windows", "PreparedMap", "GRangesError", "OPS", "shard_plan"]
+__all__ = ["Context", "Index", "Windows", "PreparedMap", "GRangesError", "OPS", "shard_plan", "map_whole_mgpu"]

@@ -59,6 +59,8 @@ SIGNATURES = {
     "grb_map_joins_f64_batch_bits": (C.c_int, [vp, C.POINTER(vp), u64p, C.c_int, vp, vp, i32p, C.c_int, vp, vp]),
     "grb_map_joins_whole_f64": (C.c_int, [vp, C.c_int, C.POINTER(vp), C.POINTER(vp), C.POINTER(C.c_size_t), C.POINTER(vp), C.POINTER(vp),
                                            u64p, vp, vp, i32p, C.c_int, vp, vp]),
+    "grb_map_joins_whole_f64_mgpu": (C.c_int, [i32p, C.c_int, C.c_int, C.POINTER(vp), C.POINTER(vp), C.POINTER(C.c_size_t), C.POINTER(vp),
+                                                C.POINTER(vp), u64p, vp, vp, i32p, C.c_int, vp, vp, C.c_char_p, C.c_size_t]),
     "grb_windows": (C.c_int, [vp, vp, C.c_int, C.c_uint32, C.c_uint32, C.c_int, C.POINTER(vp)]),
     "grb_ranges_len": (C.c_size_t, [vp]),
     "grb_ranges_seq_offsets": (C.c_int, [vp, u64p]),

@@ -485,6 +485,46 @@ class Context:
         return res
 
 
+def map_whole_mgpu(devices, rights, left_offsets, ls, le, ops, out=None, out_valid=None):
+    """`granges map` for host arrays on several GPUs of this box in one call (grb_map_joins_whole_f64_mgpu): whole seqnames are
+    dealt to the GPUs in contiguous runs, every GPU writes its rows of `out` / `out_valid`.  Arguments as Context.map_whole."""
+    nseq = len(rights)
+    keep, ps, pe, psc, pva, ns = [], [], [], [], [], []
+    any_scores = any(len(r) > 2 and r[2] is not None for r in rights)
+    any_valid = any(len(r) > 3 and r[3] is not None for r in rights)
+    for r in rights:
+        a, ka, _ = _arg(r[0], np.uint32)
+        b, kb, _ = _arg(r[1], np.uint32)
+        c, kc, _ = _arg(r[2] if len(r) > 2 else None, np.float64)
+        d, kd, _ = _arg(r[3] if len(r) > 3 else None, np.uint8)
+        keep += [ka, kb, kc, kd]
+        ps.append(a)
+        pe.append(b)
+        psc.append(c)
+        pva.append(d)
+        ns.append(len(ka))
+    pl, kl, _ = _arg(ls, np.uint32)
+    ple, kle, _ = _arg(le, np.uint32)
+    off = np.ascontiguousarray(left_offsets, dtype=np.uint64)
+    ops_a, ops_p = Context._ops(ops)
+    k = len(ops_a)
+    nl = len(kl)
+    if out is None:
+        out = np.empty((nl, k), np.float64)
+    if out_valid is None:
+        out_valid = np.empty((nl, k), np.uint8)
+    po, pv = _out_arg(out, np.float64, (nl, k))[0], _out_arg(out_valid, np.uint8, (nl, k))[0]
+    devs = np.ascontiguousarray(devices, dtype=np.int32)
+    VP = C.c_void_p * nseq
+    err = C.create_string_buffer(512)
+    rc = _capi.lib().grb_map_joins_whole_f64_mgpu(devs.ctypes.data_as(_capi.i32p), len(devs), nseq, VP(*ps), VP(*pe), (C.c_size_t * nseq)(*ns),
+                                                  VP(*psc) if any_scores else None, VP(*pva) if any_valid else None,
+                                                  off.ctypes.data_as(_capi.u64p), pl, ple, ops_p, k, po, pv, err, 512)
+    if rc != 0:
+        raise GRangesError(rc, err.value.decode())
+    return out, out_valid
+
+
 class PreparedMap:
     """A grb_map_joins_f64_batch call with all arguments already marshalled."""
 

@@ -131,6 +131,15 @@ struct OutBuf {
 };
 
 bool grb_is_device_ptr(const void *p);
+// Is p ordinary pageable host memory (a Rust Vec, a malloc'ed buffer, a numpy array) -- neither device memory nor
+// page-locked?  cudaMemcpyAsync on such memory is staged by the driver in small synchronous pieces.
+bool grb_is_pageable_ptr(const void *p);
+// Host <-> device copies on `stream` that go through the library's own ring of page-locked staging buffers when the host
+// side is pageable and the copy is large: the calling thread copies chunk c + 1 into the ring while the DMA engine moves
+// chunk c.  Page-locked host memory takes the plain asynchronous copy.  grb_d2h_staged returns when the data is in `dst`
+// (pageable) or when the copy is enqueued (page-locked).
+int grb_h2d_staged(grb_ctx *ctx, cudaStream_t stream, void *dst_dev, const void *src_host, size_t bytes);
+int grb_d2h_staged(grb_ctx *ctx, cudaStream_t stream, void *dst_host, const void *src_dev, size_t bytes);
 // Read-and-clear the device flag word after a synchronisation; turns a flagged invalid left range into
 // GRB_ERR_INVALID_RANGE (the reference cannot even construct such a range: src/ranges/mod.rs:30, coitrees.rs:53-54).
 int grb_check_flags(grb_ctx *ctx);

@@ -2,6 +2,9 @@
 #include <stdarg.h>
 #include <stdlib.h>
 
+#include <mutex>
+#include <vector>
+
 #include "common.cuh"
 
 int grb_fail(grb_ctx *ctx, int code, const char *fmt, ...) {
@@ -24,6 +27,135 @@ bool grb_is_device_ptr(const void *p) {
     return a.type == cudaMemoryTypeDevice || a.type == cudaMemoryTypeManaged;
 }
 
+bool grb_is_pageable_ptr(const void *p) {
+    cudaPointerAttributes a;
+    cudaError_t e = cudaPointerGetAttributes(&a, p);
+    if (e != cudaSuccess) {
+        cudaGetLastError();
+        return true;
+    }
+    return a.type == cudaMemoryTypeUnregistered;
+}
+
+// ---- page-locked staging rings -------------------------------------------------------------------------------------
+// One ring = 4 page-locked buffers of 8 MB with an event each.  Rings are pooled process-wide (allocating page-locked
+// memory costs milliseconds) and borrowed for the duration of one copy; each host thread that copies borrows its own.
+namespace {
+
+constexpr size_t RING_CHUNK = 8u << 20;
+constexpr int RING_SLOTS = 4;
+constexpr size_t STAGE_MIN = 1u << 20;  // smaller copies: the driver's own staging is fine
+
+struct PinRing {
+    void *buf[RING_SLOTS];
+    cudaEvent_t ev[RING_SLOTS];
+    int dev;
+};
+
+std::mutex g_ring_mu;
+std::vector<PinRing *> g_ring_pool[64];  // per device: an event can only be recorded on a stream of the device it was created on
+
+PinRing *ring_borrow() {
+    int dev = 0;
+    if (cudaGetDevice(&dev) != cudaSuccess || dev < 0 || dev >= 64) return nullptr;
+    {
+        std::lock_guard<std::mutex> lk(g_ring_mu);
+        if (!g_ring_pool[dev].empty()) {
+            PinRing *r = g_ring_pool[dev].back();
+            g_ring_pool[dev].pop_back();
+            return r;
+        }
+    }
+    PinRing *r = new PinRing();
+    r->dev = dev;
+    for (int i = 0; i < RING_SLOTS; i++) {
+        r->buf[i] = nullptr;
+        r->ev[i] = nullptr;
+    }
+    for (int i = 0; i < RING_SLOTS; i++) {
+        if (cudaHostAlloc(&r->buf[i], RING_CHUNK, cudaHostAllocPortable) != cudaSuccess ||
+            cudaEventCreateWithFlags(&r->ev[i], cudaEventDisableTiming) != cudaSuccess) {
+            cudaGetLastError();
+            for (int j = 0; j < RING_SLOTS; j++) {
+                if (r->buf[j]) cudaFreeHost(r->buf[j]);
+                if (r->ev[j]) cudaEventDestroy(r->ev[j]);
+            }
+            delete r;
+            return nullptr;
+        }
+    }
+    return r;
+}
+
+void ring_return(PinRing *r) {
+    std::lock_guard<std::mutex> lk(g_ring_mu);
+    g_ring_pool[r->dev].push_back(r);
+}
+
+}  // namespace
+
+int grb_h2d_staged(grb_ctx *ctx, cudaStream_t stream, void *dst_dev, const void *src_host, size_t bytes) {
+    if (bytes == 0) return GRB_OK;
+    PinRing *r = (bytes >= STAGE_MIN && grb_is_pageable_ptr(src_host)) ? ring_borrow() : nullptr;
+    if (!r) {
+        GRB_CUDA(ctx, cudaMemcpyAsync(dst_dev, src_host, bytes, cudaMemcpyHostToDevice, stream));
+        return GRB_OK;
+    }
+    // (events belong to the device that is current when they are recorded: the ring's are recorded on `stream`'s device)
+    cudaError_t e = cudaSuccess;
+    int used = 0;
+    for (size_t off = 0; off < bytes && e == cudaSuccess; off += RING_CHUNK, used++) {
+        const int i = used % RING_SLOTS;
+        const size_t len = bytes - off < RING_CHUNK ? bytes - off : RING_CHUNK;
+        if (used >= RING_SLOTS) e = cudaEventSynchronize(r->ev[i]);  // the DMA out of this slot has finished
+        if (e != cudaSuccess) break;
+        memcpy(r->buf[i], (const char *)src_host + off, len);
+        e = cudaMemcpyAsync((char *)dst_dev + off, r->buf[i], len, cudaMemcpyHostToDevice, stream);
+        if (e == cudaSuccess) e = cudaEventRecord(r->ev[i], stream);
+    }
+    // the ring goes back to the pool only when the engine is done with it
+    for (int i = 0; i < RING_SLOTS && i < used; i++) {
+        cudaError_t e2 = cudaEventSynchronize(r->ev[i]);
+        if (e == cudaSuccess) e = e2;
+    }
+    ring_return(r);
+    if (e != cudaSuccess) return grb_fail(ctx, GRB_ERR_CUDA, "staged host-to-device copy: %s", cudaGetErrorString(e));
+    return GRB_OK;
+}
+
+int grb_d2h_staged(grb_ctx *ctx, cudaStream_t stream, void *dst_host, const void *src_dev, size_t bytes) {
+    if (bytes == 0) return GRB_OK;
+    PinRing *r = (bytes >= STAGE_MIN && grb_is_pageable_ptr(dst_host)) ? ring_borrow() : nullptr;
+    if (!r) {
+        GRB_CUDA(ctx, cudaMemcpyAsync(dst_host, src_dev, bytes, cudaMemcpyDeviceToHost, stream));
+        return GRB_OK;
+    }
+    cudaError_t e = cudaSuccess;
+    const size_t nchunks = (bytes + RING_CHUNK - 1) / RING_CHUNK;
+    auto drain = [&](size_t c) {  // chunk c: wait for its DMA, copy it out of the ring
+        const int i = (int)(c % RING_SLOTS);
+        const size_t off = c * RING_CHUNK, len = bytes - off < RING_CHUNK ? bytes - off : RING_CHUNK;
+        cudaError_t e2 = cudaEventSynchronize(r->ev[i]);
+        if (e2 == cudaSuccess) memcpy((char *)dst_host + off, r->buf[i], len);
+        return e2;
+    };
+    for (size_t c = 0; c < nchunks && e == cudaSuccess; c++) {
+        const int i = (int)(c % RING_SLOTS);
+        const size_t off = c * RING_CHUNK, len = bytes - off < RING_CHUNK ? bytes - off : RING_CHUNK;
+        if (c >= RING_SLOTS) e = drain(c - RING_SLOTS);  // frees slot i
+        if (e != cudaSuccess) break;
+        e = cudaMemcpyAsync(r->buf[i], (const char *)src_dev + off, len, cudaMemcpyDeviceToHost, stream);
+        if (e == cudaSuccess) e = cudaEventRecord(r->ev[i], stream);
+    }
+    for (size_t c = nchunks > RING_SLOTS ? nchunks - RING_SLOTS : 0; c < nchunks; c++) {
+        cudaError_t e2 = drain(c);
+        if (e == cudaSuccess) e = e2;
+    }
+    ring_return(r);
+    if (e != cudaSuccess) return grb_fail(ctx, GRB_ERR_CUDA, "staged device-to-host copy: %s", cudaGetErrorString(e));
+    return GRB_OK;
+}
+
 int InBuf::stage(grb_ctx *ctx, const void *src, size_t bytes) {
     if (bytes == 0 || src == nullptr) {
         d = src;
@@ -34,7 +166,7 @@ int InBuf::stage(grb_ctx *ctx, const void *src, size_t bytes) {
         return GRB_OK;
     }
     GRB_TRY(tmp.alloc(ctx, bytes));
-    GRB_CUDA(ctx, cudaMemcpyAsync(tmp.p, src, bytes, cudaMemcpyHostToDevice, ctx->stream));
+    GRB_TRY(grb_h2d_staged(ctx, ctx->stream, tmp.p, src, bytes));
     d = tmp.p;
     return GRB_OK;
 }
@@ -57,7 +189,7 @@ int OutBuf::stage(grb_ctx *ctx, void *dst, size_t nbytes) {
 }
 
 int OutBuf::finish(grb_ctx *ctx) {
-    if (host && bytes) GRB_CUDA(ctx, cudaMemcpyAsync(host, d, bytes, cudaMemcpyDeviceToHost, ctx->stream));
+    if (host && bytes) GRB_TRY(grb_d2h_staged(ctx, ctx->stream, host, d, bytes));
     return GRB_OK;
 }
 

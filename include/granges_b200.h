@@ -21,7 +21,9 @@
  *     (src/iterators.rs:43-76) so one launch covers the whole genome.
  *   - ls/le/out/... pointers may be HOST pointers (pageable or pinned) or
  *     DEVICE pointers of the context's device; the library detects which
- *     (cudaPointerGetAttributes) and stages host buffers itself.  With host
+ *     (cudaPointerGetAttributes) and stages host buffers itself: large
+ *     pageable buffers (a Rust Vec, a numpy array) travel through the
+ *     library's own ring of page-locked staging buffers.  With host
  *     buffers a call returns after its results are in the caller's buffers;
  *     with device buffers it returns after enqueueing on the context's stream.
  *   - A grb_ctx is bound to one CUDA device and one stream and is not
@@ -211,6 +213,18 @@ int grb_map_joins_whole_f64(grb_ctx *ctx, int nseq, const uint32_t *const *r_sta
                             const size_t *r_n, const double *const *r_scores, const uint8_t *const *r_valid,
                             const uint64_t *left_offsets, const uint32_t *ls, const uint32_t *le, const int *ops, int k,
                             double *out, uint8_t *out_valid);
+
+/* The same call on several GPUs of one box, in one process.  Overlaps never cross seqnames (src/granges.rs:958-962), so
+ * the seqnames are cut into `ndev` contiguous runs of near-equal transfer volume; one host thread and one context per GPU
+ * (created on first use, kept for later calls) runs grb_map_joins_whole_f64 on its run, and every run writes its own
+ * rows of the caller's out / out_valid -- the host-side concatenation in the reference's row order (seqnames in GenomeMap
+ * order, then left insertion order: src/iterators.rs:43-76).  No data moves between the GPUs.  Bit-identical to the
+ * single-GPU call.  Host buffers only (pageable or page-locked).  The message of a failure is copied to err (may be NULL). */
+int grb_map_joins_whole_f64_mgpu(const int *devices, int ndev, int nseq, const uint32_t *const *r_starts,
+                                 const uint32_t *const *r_ends, const size_t *r_n, const double *const *r_scores,
+                                 const uint8_t *const *r_valid, const uint64_t *left_offsets, const uint32_t *ls,
+                                 const uint32_t *le, const int *ops, int k, double *out, uint8_t *out_valid, char *err,
+                                 size_t err_len);
 
 /* ---- windows ----------------------------------------------------------- */
 

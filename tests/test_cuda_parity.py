@@ -695,6 +695,47 @@ def test_map_whole_equals_two_calls(eng, orc, ops):
             assert (got[sl][mm, col] == o_want[mm, col]).all()
 
 
+def test_map_whole_mgpu_and_pageable_staging(eng, orc):
+    """grb_map_joins_whole_f64_mgpu (one process, one host thread + context per GPU, contiguous runs of seqnames, every
+    GPU writing its rows of the caller's arrays) returns the single-GPU call's bits on every GPU count the box offers;
+    so do pageable host buffers large enough for the page-locked staging rings and page-locked ones."""
+    import torch
+
+    import granges_b200 as gb
+
+    specs = [(400_000, 300_000, 30_000_000, 0.0), (0, 1000, 10_000, 0.0), (350_000, 500_000, 40_000_000, 0.1), (1200, 0, 10_000, 0.0),
+             (300_000, 280_000, 20_000_000, 0.0), (5, 3, 100, 0.0), (280_000, 300_000, 25_000_000, 0.0)]
+    cases = [random_case(1300 + i, nl, nr, span=span, maxlen=900, sorted_left=True, null_frac=nf) for i, (nl, nr, span, nf) in enumerate(specs)]
+    off = np.concatenate([[0], np.cumsum([len(c["ls"]) for c in cases])]).astype(np.uint64)
+    ls = np.concatenate([c["ls"] for c in cases])
+    le = np.concatenate([c["le"] for c in cases])
+    rights = [(c["rs"], c["re"], c["scores"], c["valid"] if c["valid"] is not None else np.ones(len(c["rs"]), np.uint8)) for c in cases]
+    ops = ["mean", "count"]
+    want, wv = eng.ctx.map_whole(rights, off, ls, le, ops)  # pageable numpy arrays: staged through the rings
+    # the oracle on one seqname
+    c = cases[2]
+    sl = slice(int(off[2]), int(off[3]))
+    o_want, o_wv = orc.map_joins(orc.Tree(c["rs"], c["re"]), c["scores"], c["valid"], c["ls"], c["le"], ops, nthreads=4)
+    assert (wv[sl] == o_wv).all() and (want[sl][:, 1] == o_want[:, 1]).all()
+    m = o_wv[:, 0] == 1
+    assert np.allclose(want[sl][m, 0], o_want[m, 0], rtol=1e-12, atol=0)
+    # page-locked buffers take the plain asynchronous copies
+    pin = lambda a: torch.from_numpy(np.ascontiguousarray(a)).pin_memory().numpy()
+    p_rights = [tuple(pin(x) for x in r) for r in rights]
+    out_p, ov_p = pin(np.zeros_like(want)), pin(np.zeros_like(wv))
+    eng.ctx.map_whole(p_rights, off, pin(ls), pin(le), ops, out=out_p, out_valid=ov_p)
+    assert (ov_p == wv).all() and (out_p[wv == 1] == want[wv == 1]).all()
+    # every GPU count
+    ndev = torch.cuda.device_count()
+    for n in sorted({1, min(2, ndev), ndev}):
+        got, gv = gb.map_whole_mgpu(list(range(n)), rights, off, ls, le, ops)
+        assert (gv == wv).all() and (got[wv == 1] == want[wv == 1]).all(), n
+    got, gv = gb.map_whole_mgpu([0], p_rights, off, pin(ls), pin(le), ops, out=out_p, out_valid=ov_p)
+    assert (gv == wv).all() and (got[wv == 1] == want[wv == 1]).all()
+    with pytest.raises(gb.GRangesError):
+        gb.map_whole_mgpu([ndev + 3], rights, off, ls, le, ops)
+
+
 @pytest.mark.parametrize("name", list(RANK_SWEEP_CASES))
 def test_minmax_without_a_sweep(orc, monkeypatch, name):
     """MIN / MAX with no median beside them come from the stabbing tables + block sparse table (k_minmax): the same
