@@ -569,6 +569,9 @@ def main():
             warm = torch.zeros(1, device=dev)
             dist.all_reduce(warm)
             torch.cuda.synchronize()
+            # a host-only group: ranks that wait while rank 0 drives every GPU from one process must not wait inside an NCCL
+            # kernel (it would share their GPU's time slices with rank 0's work there)
+            cpu_group = dist.new_group(backend="gloo")
         finally:
             sys.stdout.flush()
             os.dup2(saved_stdout, 1)
@@ -719,6 +722,13 @@ def main():
         del out, ov, ls, le
         torch.cuda.empty_cache()
         barrier()
+
+        def host_barrier():
+            torch.cuda.synchronize()
+            if dist is not None:
+                dist.barrier(group=cpu_group)
+
+        host_barrier()
         if rank == 0:
             host = []
             for s in range(22):
@@ -764,7 +774,7 @@ def main():
                                " = `granges map` in one call: H2D of rights + scores + lefts, index builds, map pass, D2H of the results, pipelined "
                                "per seqname; page-locked host buffers; wall clock of the calling process"}
             del h_rights, h_ls, h_le, p_rights, p_ls, p_le, host
-        barrier()
+        host_barrier()
 
     if rank != 0:
         if dist is not None:

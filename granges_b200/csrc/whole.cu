@@ -24,7 +24,13 @@
 
 #include "common.cuh"
 
+#include <chrono>
+
 namespace {
+
+double now_ms() {
+    return std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now().time_since_epoch()).count();
+}
 
 struct Job {
     int kind;  // 0: upload + index seqname s;  1: download rows [a, b) once event `after` has fired;  -1: stop
@@ -49,6 +55,8 @@ extern "C" int grb_map_joins_whole_f64(grb_ctx *ctx, int nseq, const uint32_t *c
     for (int s = 0; s < nseq; s++)
         if (left_offsets[s + 1] < left_offsets[s]) return grb_fail(ctx, GRB_ERR_INVALID_ARG, "map_joins_whole: left_offsets must be non-decreasing");
     if (total == first) return GRB_OK;
+    const bool timing = getenv("GRB_TIMING") != nullptr;  // debug: per-job wall times on stderr
+    const double t_call = now_ms();
     GRB_CUDA(ctx, cudaStreamSynchronize(ctx->stream));  // earlier work on the caller's stream precedes the workers'
     // The lefts are on the host: sample their order here, once, and tell the per-chunk calls (which only see device copies)
     const int saved_order = ctx->left_order;
@@ -132,6 +140,7 @@ extern "C" int grb_map_joins_whole_f64(grb_ctx *ctx, int nseq, const uint32_t *c
                 jobs.pop_front();
             }
             int rc = GRB_OK;
+            const double t_job = now_ms();
             if (j.kind == 0) {
                 const int s = j.s;
                 if (!failed.load()) {
@@ -158,6 +167,9 @@ extern "C" int grb_map_joins_whole_f64(grb_ctx *ctx, int nseq, const uint32_t *c
                 rc = grb_d2h_staged(c, c->stream, out + j.a * (u64)k, d_out.as<double>() + j.a * (u64)k, (j.b - j.a) * (u64)k * 8);
                 if (rc == GRB_OK) rc = grb_d2h_staged(c, c->stream, out_valid + j.a * (u64)k, d_val.as<u8>() + j.a * (u64)k, (j.b - j.a) * (u64)k);
             }
+            if (timing)
+                fprintf(stderr, "[whole dev %d] worker %d %s seq %d: %.2f .. %.2f ms\n", ctx->device, w, j.kind == 0 ? "upload+index" : "download", j.s,
+                        t_job - t_call, now_ms() - t_call);
             if (rc != GRB_OK) {
                 rcs[w] = rc;
                 failed.store(1);
@@ -189,6 +201,7 @@ extern "C" int grb_map_joins_whole_f64(grb_ctx *ctx, int nseq, const uint32_t *c
         rc = grb_map_joins_f64_batch(ctx, idx.data() + s0, left_offsets + s0, s1 - s0, d_ls.as<u32>(), d_le.as<u32>(), ops, k, d_out.as<double>(),
                                      d_val.as<u8>());
         cudaEventRecord(done[c], ctx->stream);
+        if (timing) fprintf(stderr, "[whole dev %d] map chunk %d (seq %d..%d) enqueued at %.2f ms\n", ctx->device, c, s0, s1, now_ms() - t_call);
         if (rc == GRB_OK) {
             std::lock_guard<std::mutex> lk(mu);
             // downloads go to the FRONT of the queue: the next free worker starts them, so results travel back while the
@@ -223,6 +236,7 @@ extern "C" int grb_map_joins_whole_f64(grb_ctx *ctx, int nseq, const uint32_t *c
             idx[s]->ctx = ctx;
             grb_index_destroy(idx[s]);
         }
+    if (timing) fprintf(stderr, "[whole dev %d] done at %.2f ms\n", ctx->device, now_ms() - t_call);
     if (rc != GRB_OK) return rc;
     if (e3 != cudaSuccess) return grb_fail(ctx, GRB_ERR_CUDA, "map_joins_whole: %s", cudaGetErrorString(e3));
     return grb_check_flags(ctx);
