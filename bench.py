@@ -7,10 +7,13 @@ U{1..999}, starts uniform, scores U[0,1), equal share per seqname), both sides s
 
   value      left ranges/s of one map pass (left_overlaps + map_joins(mean), index already built,
              everything resident in HBM), CUDA events on the launching stream, max over ranks
-  e2e        the same metric through the C ABI with HOST (pinned) buffers: grb_index_build_batch (H2D of
-             the rights and scores + 22 index builds) then grb_map_joins_f64_batch (H2D of the lefts,
-             map pass, D2H of the results), all inside the timed region
-  roofline   the dominant kernel (k_tile<MAP>) against the measured HBM peak
+  e2e        the same metric through ONE call of the C ABI from HOST buffers: grb_map_joins_whole_f64 (N = 1) or
+             grb_map_joins_whole_f64_mgpu (N > 1, one process driving the N GPUs): H2D of rights, scores and
+             lefts, index builds, map pass, D2H of the results into one output array, all inside the timed
+             region; page-locked buffers for the headline figure, pageable ones beside it
+  variants   the headline job on the other input classes (None scores, decimal scores, a non-finite score,
+             shuffled lefts) with an oracle spot check each;  configs: BASELINE configs C2-C5 likewise
+  roofline   the dominant kernel (k_map_pipe<MEAN>: the only kernel of a map_mean step) against the measured HBM peak
   cpu_baseline / --impl reference
              the CPU oracle (coitrees-restated, oracle/granges_oracle.c) on a bounded sample
              (one whole seqname) -- the reference is Rust and cannot be built in this image
@@ -488,6 +491,9 @@ def reference_arm(args):
         "vs_baseline": None, "dtype": "f64", "data": "synthetic",
         "config": workload_config(args),
         "cpu_baseline": {"value": value, "unit": "left ranges/s", "cores": threads, "kind": "port",
+                         "sample_lefts": n_sample, "sample_rights": sum(nr_per[q] for q in seqs), "sample_seqnames": len(seqs),
+                         "extrapolated": "rate measured on the sample (whole seqnames whose pairs/left match the job's mean), quoted as the job's rate; "
+                                         "all host threads, although the reference itself is single-threaded",
                          "sample": f"{len(seqs)} whole seqnames ({','.join('chr%d' % (q + 1) for q in seqs)}; {n_sample} lefts x "
                                    f"{sum(nr_per[q] for q in seqs)} rights, ~{mean_ppl:.1f} pairs/left) per step: tree build + "
                                    f"left_overlaps + map_joins, seqnames concurrent, {threads} threads in all "
@@ -667,8 +673,12 @@ def main():
     total_ms = t_all0.elapsed_time(t_all1)
     per_step = [a.elapsed_time(b) for a, b in evs]
     tmax = torch.tensor([total_ms], dtype=torch.float64, device=dev)
+    per_rank_ms = [total_ms / args.steps]
     if dist is not None:
         dist.all_reduce(tmax, op=dist.ReduceOp.MAX)
+        gathered = [torch.zeros(1, dtype=torch.float64, device=dev) for _ in range(world)]
+        dist.all_gather(gathered, torch.tensor([total_ms / args.steps], dtype=torch.float64, device=dev))
+        per_rank_ms = [float(g.item()) for g in gathered]
     total_ms_max = float(tmax.item())
     ms_per_step = total_ms_max / args.steps
 
@@ -790,16 +800,16 @@ def main():
         "pairs_per_s": pairs_total / (ms_per_step * 1e-3), "overlap_pairs": pairs_total, "lefts_processed": nl_total,
         "index_build_ms_rank0": t_build * 1e3, "gpu_launches": int(launches), "clocks": clocks,
         "step_ms_rank0": {"min": min(per_step), "median": float(np.median(per_step)), "max": max(per_step)},
-        "units_rank0": len(mine), "cpus_bound_rank0": numa,
+        "units_rank0": len(mine), "cpus_bound_rank0": numa, "step_ms_per_rank": per_rank_ms,
     }
     if ops != ["mean"]:
         line["metric"] = "map_%s left ranges/s" % "_".join(ops)
         line["config"]["ops"] = ops
 
-    # ---- roofline of the dominant kernel (k_tile<MAP>: the only kernel of a map_mean step)
+    # ---- roofline of the dominant kernel (k_map_pipe<MEAN>: the only kernel of a map_mean step)
     nr_tot = int(agg[2].item())
     alg_bytes = nl_total * 8 + nr_tot * 16 + nl_total * k * 8 + nl_total * k / 8  # B_map
-    kernel_ms = float(np.mean(per_step))  # rank 0's launch duration (one k_tile launch per step when ops = mean)
+    kernel_ms = float(np.mean(per_step))  # rank 0's launch duration (one k_map_pipe launch per step when ops = mean)
     alg_rank0 = nl_mine * 8 + n_right_mine * 16 + nl_mine * k * 8 + nl_mine * k / 8
     achieved = alg_rank0 / (kernel_ms * 1e-3) / 1e9
     line["roofline"] = {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
@@ -836,6 +846,7 @@ def main():
         line["parity_check"] = {"seqname": f"chr{chk_seq + 1}", "lefts": int(len(want)), "validity_equal": okv, "max_rel_err": rel,
                                 "tolerance": 1e-12, "ok": bool(okv and rel <= 1e-12)}
         line["cpu_baseline"] = {"value": n_sample / r["total_s"], "unit": "left ranges/s", "cores": 1, "kind": "port",
+                                "sample_lefts": n_sample, "sample_rights": sum(nr_per[q] for q in seqs), "sample_seqnames": len(seqs),
                                 "sample": f"{len(seqs)} whole seqnames ({','.join('chr%d' % (q + 1) for q in seqs)}; {n_sample} lefts x "
                                           f"{sum(nr_per[q] for q in seqs)} rights, ~{mean_ppl:.1f} pairs/left): tree build "
                                           f"{r['build_s']:.2f} s + left_overlaps + map_joins {r['map_s']:.2f} s, single thread "

@@ -101,8 +101,9 @@ class Index:
     """One seqname's right-hand index (replaces COITrees<M>, src/ranges/coitrees.rs:25-84)."""
 
     def __init__(self, ctx, handle):
-        self.ctx = ctx
+        self.ctx = ctx  # (keeps the context alive: a handle must never outlive its context)
         self.h = handle
+        ctx._children.add(self)
 
     def __len__(self):
         return _capi.lib().grb_index_len(self.h)
@@ -142,6 +143,7 @@ class Windows:
 
     def __init__(self, ctx, handle, nseq):
         self.ctx, self.h, self.nseq = ctx, handle, nseq
+        ctx._children.add(self)
 
     def __len__(self):
         return _capi.lib().grb_ranges_len(self.h)
@@ -184,6 +186,9 @@ class Context:
             raise GRangesError(rc, f"cannot create a context on CUDA device {device} (no CPU fallback exists)")
         self.h = h
         self.device = int(device)
+        import weakref
+
+        self._children = weakref.WeakSet()  # indexes / windows created here: closed before the context goes
         if stream is None:
             # Device tensors handed to this context are produced on torch's current stream: run there too, so that the
             # library's kernels are ordered after the producer and before the consumer of every tensor (the context's own
@@ -227,6 +232,8 @@ class Context:
 
     def close(self):
         if self.h:
+            for ch in list(self._children):
+                ch.close()
             _capi.lib().grb_ctx_destroy(self.h)
             self.h = None
 

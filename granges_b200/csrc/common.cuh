@@ -74,6 +74,14 @@ int grb_fail(grb_ctx *ctx, int code, const char *fmt, ...);
                             cudaGetErrorString(_e));                                          \
     } while (0)
 
+// The same inside a `do { ... } while (0)` body that reports through a local `rc` and `break`.
+#define GRB_LAUNCHED_BREAK(ctx, rc)                                                                   \
+    (ctx)->launches++;                                                                                \
+    if (cudaError_t _e = cudaGetLastError(); _e != cudaSuccess) {                                     \
+        rc = grb_fail((ctx), GRB_ERR_CUDA, "%s:%d: kernel launch: %s", __FILE__, __LINE__, cudaGetErrorString(_e)); \
+        break;                                                                                        \
+    }
+
 // Stream-ordered temporary device buffer (pool keeps the memory cached, no sync on free).
 struct TempBuf {
     grb_ctx *ctx = nullptr;

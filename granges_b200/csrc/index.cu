@@ -715,7 +715,7 @@ int grb_index_build(grb_ctx *ctx, const uint32_t *starts, const uint32_t *ends, 
         if (n && data_idx) {
             // ties on (start, end) must come out in data-index order: pre-order the input by data index
             k_idx_keys<<<blocks_for(n, 256), 256, 0, ctx->stream>>>(d_idx.as<u64>(), n, k0.as<u64>(), v0.as<u32>(), fl.as<BuildFlags>());
-            ctx->launches++;
+            GRB_LAUNCHED_BREAK(ctx, rc)
             bool sorted0;
             if ((rc = grb_sort_pairs(ctx, k0.as<u64>(), v0.as<u32>(), k1.as<u64>(), v1.as<u32>(), n, &ks, &vs, &sorted0))) break;
             if (!sorted0) {
@@ -727,7 +727,7 @@ int grb_index_build(grb_ctx *ctx, const uint32_t *starts, const uint32_t *ends, 
         if (n) {
             k_make_keys<<<blocks_for(n, 256), 256, 0, ctx->stream>>>(d_starts.as<u32>(), d_ends.as<u32>(), order, n, k0.as<u64>(),
                                                                     v0.as<u32>(), fl.as<BuildFlags>());
-            ctx->launches++;
+            GRB_LAUNCHED_BREAK(ctx, rc)
         }
         if ((rc = grb_sort_pairs(ctx, k0.as<u64>(), v0.as<u32>(), k1.as<u64>(), v1.as<u32>(), n, &ks, &vs, nullptr))) break;
         BuildFlags hf;
@@ -751,11 +751,11 @@ int grb_index_build(grb_ctx *ctx, const uint32_t *starts, const uint32_t *ends, 
         u32 *v2 = (vs == v0.as<u32>()) ? v1.as<u32>() : v0.as<u32>();
         k_unpack_start_order<<<blocks_for(n + PAD, 256), 256, 0, ctx->stream>>>(ks, vs, d_idx.as<u64>(), n, ix->starts, ix->ends,
                                                                                ix->didx);
-        ctx->launches++;
+        GRB_LAUNCHED_BREAK(ctx, rc)
         // end order: a stable argsort of the ends as u32 keys, whose last pass lands in ends_sorted / perm_e
         if ((rc = grb_argsort_u32(ctx, ix->ends, ix->ends_sorted, ix->perm_e, (u32 *)k2, v2, n))) break;
         k_pad_keys<<<1, PAD, 0, ctx->stream>>>(ix->ends_sorted + n);
-        ctx->launches++;
+        GRB_LAUNCHED_BREAK(ctx, rc)
         {
             // coordinate bins of ~2-4 rights each (so one round of four compares usually ends a search);
             // the largest end bounds every key
@@ -774,14 +774,14 @@ int grb_index_build(grb_ctx *ctx, const uint32_t *starts, const uint32_t *ends, 
             if ((rc = dev_alloc(ctx, (void **)&ix->lut16_a, entries * 2))) break;
             if ((rc = dev_alloc(ctx, (void **)&ix->lut16_b, entries * 2))) break;
             k_build_lut<<<blocks_for(n + 1, 256), 256, 0, ctx->stream>>>(ix->starts, (u32)n, shift, ix->lut_bmax, ix->lut_a, ix->lut16_a);
-            ctx->launches++;
+            GRB_LAUNCHED_BREAK(ctx, rc)
             k_build_lut<<<blocks_for(n + 1, 256), 256, 0, ctx->stream>>>(ix->ends_sorted, (u32)n, shift, ix->lut_bmax, ix->lut_b, ix->lut16_b);
-            ctx->launches++;
+            GRB_LAUNCHED_BREAK(ctx, rc)
         }
         if (n) {
             size_t nbw = (n + 63) >> GRB_BME_SHIFT;
             k_block_max_end<<<blocks_for(nbw * 32, 256), 256, 0, ctx->stream>>>(ix->ends, n, ix->bme);
-            ctx->launches++;
+            GRB_LAUNCHED_BREAK(ctx, rc)
         }
         cudaError_t e = cudaStreamSynchronize(ctx->stream);
         if (e != cudaSuccess) {

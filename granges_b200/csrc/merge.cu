@@ -315,7 +315,7 @@ int grb_merge_ranges(grb_ctx *ctx, const uint32_t *starts, const uint32_t *ends,
         cudaMemsetAsync(fl.p, 0, sizeof(MergeFlags), ctx->stream);
         k_merge_keys<<<blocks_for(n, 256), 256, 0, ctx->stream>>>(d_s.as<u32>(), d_e.as<u32>(), ro.as<u64>(), nruns, n, keys.as<u64>(),
                                                                  fl.as<MergeFlags>());
-        ctx->launches++;
+        GRB_LAUNCHED_BREAK(ctx, rc)
         MergeFlags hf;
         cudaMemcpyAsync(&hf, fl.p, sizeof(hf), cudaMemcpyDeviceToHost, ctx->stream);
         if (cudaStreamSynchronize(ctx->stream) != cudaSuccess) {
@@ -332,12 +332,12 @@ int grb_merge_ranges(grb_ctx *ctx, const uint32_t *starts, const uint32_t *ends,
             TempBuf bmax;
             if ((rc = bmax.alloc(ctx, nb * 8))) break;
             k_block_max<<<(unsigned)nb, MG_TPB, 0, ctx->stream>>>(keys.as<u64>(), n, bmax.as<u64>());
-            ctx->launches++;
+            GRB_LAUNCHED_BREAK(ctx, rc)
             k_prefix_max64_single<<<1, 1024, 0, ctx->stream>>>(bmax.as<u64>(), nb);
-            ctx->launches++;
+            GRB_LAUNCHED_BREAK(ctx, rc)
             k_merge_flags_sorted<<<(unsigned)nb, MG_TPB, 0, ctx->stream>>>(d_s.as<u32>(), keys.as<u64>(), bmax.as<u64>(), n, (long long)distance,
                                                                           flags.as<u32>(), iend.as<u32>());
-            ctx->launches++;
+            GRB_LAUNCHED_BREAK(ctx, rc)
             if (cudaStreamSynchronize(ctx->stream) != cudaSuccess) {  // bmax goes out of scope
                 rc = grb_fail(ctx, GRB_ERR_CUDA, "merge: %s", cudaGetErrorString(cudaGetLastError()));
                 break;
@@ -345,16 +345,16 @@ int grb_merge_ranges(grb_ctx *ctx, const uint32_t *starts, const uint32_t *ends,
         } else {
             k_merge_flags_sequential<<<(unsigned)nruns, 32, 0, ctx->stream>>>(d_s.as<u32>(), d_e.as<u32>(), ro.as<u64>(), nruns,
                                                                              (long long)distance, flags.as<u32>(), iend.as<u32>());
-            ctx->launches++;
+            GRB_LAUNCHED_BREAK(ctx, rc)
         }
         if ((rc = grb_scan_u32_to_u64(ctx, flags.as<u32>(), pos.as<u64>(), n, true))) break;
         // merged ranges in all, and per run
         TempBuf rom;
         if ((rc = rom.alloc(ctx, ((size_t)nruns + 1) * 8))) break;
         k_gather_u64<<<blocks_for((u64)nruns + 1, 128), 128, 0, ctx->stream>>>(pos.as<u64>(), ro.as<u64>(), nruns + 1, rom.as<u64>());
-        ctx->launches++;
-        cudaMemcpyAsync(mg->run_offsets_m, rom.p, ((size_t)nruns + 1) * 8, cudaMemcpyDeviceToHost, ctx->stream);
-        if (cudaStreamSynchronize(ctx->stream) != cudaSuccess) {
+        GRB_LAUNCHED_BREAK(ctx, rc)
+        if (cudaMemcpyAsync(mg->run_offsets_m, rom.p, ((size_t)nruns + 1) * 8, cudaMemcpyDeviceToHost, ctx->stream) != cudaSuccess ||
+            cudaStreamSynchronize(ctx->stream) != cudaSuccess) {
             rc = grb_fail(ctx, GRB_ERR_CUDA, "merge: %s", cudaGetErrorString(cudaGetLastError()));
             break;
         }
@@ -367,7 +367,7 @@ int grb_merge_ranges(grb_ctx *ctx, const uint32_t *starts, const uint32_t *ends,
         }
         k_merge_emit<<<blocks_for(n, 256), 256, 0, ctx->stream>>>(d_s.as<u32>(), flags.as<u32>(), iend.as<u32>(), pos.as<u64>(), n, m,
                                                                  mg->starts, mg->ends, mg->first);
-        ctx->launches++;
+        GRB_LAUNCHED_BREAK(ctx, rc)
         cudaError_t e = cudaStreamSynchronize(ctx->stream);
         if (e != cudaSuccess) {
             rc = grb_fail(ctx, GRB_ERR_CUDA, "merge: %s", cudaGetErrorString(e));
@@ -432,9 +432,10 @@ int grb_merged_map_f64(grb_ctx *ctx, const grb_merged *mg, const double *scores,
         if (rc == GRB_OK) {
             k_shift_copy<<<blocks_for(m, 256), 256, 0, ctx->stream>>>(mg->first, m, le.as<u32>());
             ctx->launches++;
+            if (cudaError_t e = cudaGetLastError(); e != cudaSuccess) rc = grb_fail(ctx, GRB_ERR_CUDA, "merged_map: kernel launch: %s", cudaGetErrorString(e));
             const uint64_t off[2] = {0, m};
             const grb_index *cp = pix;
-            rc = grb_map_joins_f64_batch(ctx, &cp, off, 1, mg->first, le.as<u32>(), ops, k, out, out_valid);
+            if (rc == GRB_OK) rc = grb_map_joins_f64_batch(ctx, &cp, off, 1, mg->first, le.as<u32>(), ops, k, out, out_valid);
             if (rc == GRB_OK && cudaStreamSynchronize(ctx->stream) != cudaSuccess)
                 rc = grb_fail(ctx, GRB_ERR_CUDA, "merged_map: %s", cudaGetErrorString(cudaGetLastError()));
         }

@@ -1376,7 +1376,7 @@ int grb_left_overlaps(grb_ctx *ctx, const grb_index *idx, const uint32_t *ls, co
         }
         if (np) {
             k_emit2<<<b.ntiles, SW2_TPB, 0, ctx->stream>>>(b.seqs, b.tile_begin, 1, p->ls, o.ub, o.pp, o.lb, p->offsets, p->pos);
-            ctx->launches++;
+            GRB_LAUNCHED_BREAK(ctx, rc)
         }
         e = cudaMemcpyAsync(offsets, p->offsets, (nl + 1) * 8, cudaMemcpyDefault, ctx->stream);
         if (e == cudaSuccess) e = cudaStreamSynchronize(ctx->stream);

@@ -141,6 +141,7 @@ extern "C" int grb_map_joins_whole_f64(grb_ctx *ctx, int nseq, const uint32_t *c
             }
             int rc = GRB_OK;
             const double t_job = now_ms();
+            double t_up = 0, t_ix = 0;
             if (j.kind == 0) {
                 const int s = j.s;
                 if (!failed.load()) {
@@ -149,8 +150,13 @@ extern "C" int grb_map_joins_whole_f64(grb_ctx *ctx, int nseq, const uint32_t *c
                         rc = grb_h2d_staged(c, c->stream, d_ls.as<u32>() + a, ls + a, (b - a) * 4);
                         if (rc == GRB_OK) rc = grb_h2d_staged(c, c->stream, d_le.as<u32>() + a, le + a, (b - a) * 4);
                     }
+                    if (timing) {
+                        cudaStreamSynchronize(c->stream);
+                        t_up = now_ms();
+                    }
                     if (rc == GRB_OK && r_n[s]) {
                         rc = grb_index_build(c, r_starts[s], r_ends[s], nullptr, r_n[s], &idx[s]);
+                        t_ix = now_ms();
                         if (rc == GRB_OK && r_scores && r_scores[s])
                             rc = grb_index_set_scores(idx[s], r_scores[s], (r_valid && r_valid[s]) ? r_valid[s] : nullptr, r_n[s]);
                         if (rc == GRB_OK) idx[s]->ctx = ctx;  // the clone goes away; the index is used on the caller's context
@@ -168,8 +174,9 @@ extern "C" int grb_map_joins_whole_f64(grb_ctx *ctx, int nseq, const uint32_t *c
                 if (rc == GRB_OK) rc = grb_d2h_staged(c, c->stream, out_valid + j.a * (u64)k, d_val.as<u8>() + j.a * (u64)k, (j.b - j.a) * (u64)k);
             }
             if (timing)
-                fprintf(stderr, "[whole dev %d] worker %d %s seq %d: %.2f .. %.2f ms\n", ctx->device, w, j.kind == 0 ? "upload+index" : "download", j.s,
-                        t_job - t_call, now_ms() - t_call);
+                fprintf(stderr, "[whole dev %d] worker %d %s seq %d: %.2f .. %.2f ms (lefts up %.2f, index built %.2f)\n", ctx->device, w,
+                        j.kind == 0 ? "upload+index" : "download", j.s, t_job - t_call, now_ms() - t_call, t_up ? t_up - t_call : 0.0,
+                        t_ix ? t_ix - t_call : 0.0);
             if (rc != GRB_OK) {
                 rcs[w] = rc;
                 failed.store(1);

@@ -96,7 +96,7 @@ int grb_windows(grb_ctx *ctx, const uint32_t *seqlens, int nseq, uint32_t width,
         cudaMemcpyAsync(d.p, ws.data(), sizeof(WinSeq) * (nseq + 1), cudaMemcpyHostToDevice, ctx->stream);
         u64 blocks = (total + 255) / 256;
         k_windows<<<(unsigned)blocks, 256, 0, ctx->stream>>>(d.as<WinSeq>(), nseq, total, width, (u32)st, r->seq_id, r->starts, r->ends);
-        ctx->launches++;
+        GRB_LAUNCHED_BREAK(ctx, rc)
         cudaError_t e = cudaGetLastError();
         if (e != cudaSuccess) rc = grb_fail(ctx, GRB_ERR_CUDA, "windows: %s", cudaGetErrorString(e));
     } while (0);

@@ -28,6 +28,19 @@
  *     with device buffers it returns after enqueueing on the context's stream.
  *   - A grb_ctx is bound to one CUDA device and one stream and is not
  *     thread-safe (one context per GPU per thread).
+ *   - Lifetimes: handles hold plain back-pointers.  A context must outlive
+ *     every handle created on it (indexes, pairs, ranges, merged sets:
+ *     destroy them first), and an index must outlive the grb_pairs made from
+ *     it (grb_pairs_copy / grb_pairs_overlap_widths read the index).
+ *   - Invalid left ranges (end <= start, end > 2^31-1: the reference cannot
+ *     even construct them, src/ranges/mod.rs:30) are answered as empty groups
+ *     and flagged on the device.  Calls with HOST buffers check the flag
+ *     before they return (GRB_ERR_INVALID_RANGE); calls with DEVICE buffers
+ *     only enqueue work, so the error surfaces at the next call that
+ *     synchronises -- grb_ctx_sync, or any call with host buffers.
+ *   - Work is ordered on the context's stream only: device buffers produced
+ *     on another stream need that stream synchronised (or the context bound
+ *     to it with grb_ctx_set_stream) before they are passed in.
  *   - Coordinates are 0-based half-open u32 with end > start and
  *     end <= 2^31-1 (the reference converts to i32 and panics beyond that,
  *     src/ranges/coitrees.rs:53-54,173-178).
@@ -264,8 +277,11 @@ const uint32_t *grb_merged_dev_starts(const grb_merged *m);
 const uint32_t *grb_merged_dev_ends(const grb_merged *m);
 /* The closure of Merge::run for BED5 input (src/commands.rs:650-657): FloatOperation::run over the non-missing
  * scores of each merged group.  scores / valid are per input record (valid NULL = all Some); out / out_valid
- * are len x k, row-major.  Sums are the correctly rounded exact sums (within 1e-12 of the reference's
- * left-to-right f64 sum); min / max / median are bit-exact. */
+ * are len x k, row-major.  Sums are the correctly rounded EXACT sums: a deliberate deviation from the
+ * reference's left-to-right f64 fold, whose own rounding error (<= n * 2^-53 * sum|x|) is the only difference -- e.g.
+ * 1e16 + 1 - 1e16 is 1 here and 0 there.  Indexes whose scores cannot be held in the fixed point (subnormals, more
+ * than 126 bits of dynamic range: grb_index_exact_sums == 0) sum the members in index order instead, with that same
+ * error bound.  min / max / median are bit-exact. */
 int grb_merged_map_f64(grb_ctx *ctx, const grb_merged *m, const double *scores, const uint8_t *valid, const int *ops, int k,
                        double *out, uint8_t *out_valid);
 void grb_merged_destroy(grb_merged *m);
