@@ -57,6 +57,11 @@ SIGNATURES = {
     "grb_filter_overlaps_select": (C.c_int, [vp, C.POINTER(vp), u64p, C.c_int, vp, vp, C.c_int, vp, u64p]),
     "grb_map_joins_f64_batch": (C.c_int, [vp, C.POINTER(vp), u64p, C.c_int, vp, vp, i32p, C.c_int, vp, vp]),
     "grb_map_joins_f64_batch_bits": (C.c_int, [vp, C.POINTER(vp), u64p, C.c_int, vp, vp, i32p, C.c_int, vp, vp]),
+    "grb_map_joins_reduce_batch": (C.c_int, [vp, C.POINTER(vp), u64p, C.c_int, vp, vp, vp, C.c_int, vp, vp]),
+    "grb_collapse_f64": (C.c_int, [vp, vp, vp, vp, C.c_size_t, C.POINTER(vp)]),
+    "grb_text_bytes": (C.c_size_t, [vp]),
+    "grb_text_copy": (C.c_int, [vp, vp, vp]),
+    "grb_text_destroy": (None, [vp]),
     "grb_map_joins_whole_f64": (C.c_int, [vp, C.c_int, C.POINTER(vp), C.POINTER(vp), C.POINTER(C.c_size_t), C.POINTER(vp), C.POINTER(vp),
                                            u64p, vp, vp, i32p, C.c_int, vp, vp]),
     "grb_map_joins_whole_f64_mgpu": (C.c_int, [i32p, C.c_int, C.c_int, C.POINTER(vp), C.POINTER(vp), C.POINTER(C.c_size_t), C.POINTER(vp),

@@ -25,7 +25,15 @@ OPS = {
     "count": 6,
     "overlap-bp": 7,
     "weighted-mean": 8,
+    "weighted-sum": 9,
 }
+
+# grb_reducer parts (include/granges_b200.h)
+RED_VALUE = {"score": 0, "one": 1}
+RED_WEIGHT = {"one": 0, "overlap-width": 1}
+RED_FOLD = {"sum": 0, "min": 1, "max": 2}
+RED_DIVIDE = {"none": 0, "by-weights": 1}
+RED_EMPTY = {"zero": 0, "novalue": 1}
 
 STATUS = {
     0: "GRB_OK",
@@ -439,6 +447,39 @@ class Context:
         fn = _capi.lib().grb_map_joins_f64_batch_bits if valid_bits else _capi.lib().grb_map_joins_f64_batch
         self._check(fn(self.h, self._handles(indexes), off.ctypes.data_as(_capi.u64p), len(indexes), pl, pe, ops_p, k, po, pv))
         return out, out_valid
+
+    def map_joins_reduce(self, indexes, left_offsets, ls, le, reducers):
+        """Composable reducers (grb_map_joins_reduce_batch): `reducers` = [(value, weight, fold, divide, empty), ...] with the
+        names of RED_VALUE / RED_WEIGHT / RED_FOLD / RED_DIVIDE / RED_EMPTY, one per output column."""
+        pl, kl, dev = _arg(ls, np.uint32)
+        pe, ke, _ = _arg(le, np.uint32)
+        off = np.ascontiguousarray(left_offsets, dtype=np.uint64)
+        k = len(reducers)
+        red = np.ascontiguousarray([[RED_VALUE[v], RED_WEIGHT[w], RED_FOLD[f], RED_DIVIDE[d], RED_EMPTY[e]] for v, w, f, d, e in reducers],
+                                   dtype=np.int32)
+        po, out = self._out(dev, (len(kl), k), np.float64, kl)
+        pv, ov = self._out(dev, (len(kl), k), np.uint8, kl)
+        self._check(_capi.lib().grb_map_joins_reduce_batch(self.h, self._handles(indexes), off.ctypes.data_as(_capi.u64p), len(indexes), pl, pe,
+                                                           red.ctypes.data, k, po, pv))
+        return out, ov
+
+    def collapse(self, index, ls, le):
+        """FloatOperation::Collapse in sort_ranges order (grb_collapse_f64): one string per left."""
+        L = _capi.lib()
+        pl, kl, _ = _arg(ls, np.uint32)
+        pe, ke, _ = _arg(le, np.uint32)
+        nl = len(kl)
+        h = C.c_void_p()
+        self._check(L.grb_collapse_f64(self.h, index.h if index is not None else None, pl, pe, nl, C.byref(h)))
+        try:
+            nb = L.grb_text_bytes(h)
+            off = np.zeros(nl + 1, np.uint64)
+            buf = np.zeros(max(nb, 1), np.uint8)
+            self._check(L.grb_text_copy(h, off.ctypes.data, buf.ctypes.data))
+        finally:
+            L.grb_text_destroy(h)
+        raw = buf.tobytes()
+        return [raw[int(off[i]):int(off[i + 1])].decode() for i in range(nl)]
 
     def prepare_map(self, indexes, left_offsets, ls, le, ops, out, out_valid, valid_bits=False):
         """Bind every argument of grb_map_joins_f64_batch[_bits] once; calling the returned object repeats the

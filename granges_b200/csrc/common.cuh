@@ -241,6 +241,17 @@ struct grb_index {
 
 #define GRB_RANK_NONE 0xffffffffu
 
+// CSR form of a left grouped join (grb_left_overlaps)
+struct grb_pairs {
+    grb_ctx *ctx;
+    const grb_index *idx;
+    u64 nl, np;
+    u32 *ls, *le;   // device copies of the lefts
+    u64 *offsets;   // device, nl + 1
+    u32 *pos;       // device, np positions in the index's start order
+};
+
+
 // Per-seqname view handed to the kernels (one entry per seqname of a batch).
 struct SeqDev {
     const u32 *starts, *ends, *ends_sorted, *didx, *bme;

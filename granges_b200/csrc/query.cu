@@ -567,11 +567,12 @@ __global__ void __launch_bounds__(256) k_minmax(const SeqDev *__restrict__ seqs,
 __global__ void __launch_bounds__(256) k_weighted_mean(const SeqDev *__restrict__ seqs, int nseq, u64 first, u64 total, const u32 *__restrict__ ls,
                                                        const u32 *__restrict__ le, const u32 *__restrict__ ubv,
                                                        const u32 *__restrict__ ppv, const u32 *__restrict__ lbv,
-                                                       double *__restrict__ out, u8 *__restrict__ out_valid, int k, u32 col_mask) {
+                                                       double *__restrict__ out, u8 *__restrict__ out_valid, int k, u32 col_mask,
+                                                       u32 sum_mask /* columns that want the weighted SUM (the numerator) */) {
     const u64 g = first + (u64)blockIdx.x * blockDim.x + threadIdx.x;  // a batch may start anywhere in the left arrays
     if (g >= total) return;
     const SeqDev *__restrict__ sd = &seqs[find_seq_by_left(seqs, nseq, g)];
-    double r = 0.0;
+    double r = 0.0, rsum = 0.0;
     if (sd->n && sd->has_scores) {
         const u32 u = ubv[g], p = ppv[g], l = lbv[g], a = ls[g], b = le[g];
         u32 lo = l, hi = u;
@@ -600,11 +601,12 @@ __global__ void __launch_bounds__(256) k_weighted_mean(const SeqDev *__restrict_
             wtot = (sd->sum_ends[a2] - sd->sum_starts[u] + (u64)b * (u64)(u - a2)) -
                    (sd->sum_ends[l] - sd->sum_starts[p] + (u64)a * (u64)(p - l));
         }
-        if (wtot) r = fx_to_double(wsum, sd->e0) / (double)wtot;
+        rsum = fx_to_double(wsum, sd->e0);
+        if (wtot) r = rsum / (double)wtot;
     }
     for (int c = 0; c < k; c++)
-        if ((col_mask >> c) & 1u) {
-            out[g * (u64)k + c] = r;
+        if (((col_mask | sum_mask) >> c) & 1u) {
+            out[g * (u64)k + c] = ((sum_mask >> c) & 1u) ? rsum : r;
             out_valid[g * (u64)k + c] = 1;
         }
 }
@@ -810,14 +812,6 @@ int enter(grb_ctx *ctx) {
 
 }  // namespace
 
-struct grb_pairs {
-    grb_ctx *ctx;
-    const grb_index *idx;
-    u64 nl, np;
-    u32 *ls, *le;   // device copies of the lefts
-    u64 *offsets;   // device, nl + 1
-    u32 *pos;       // device, np positions in the index's start order
-};
 
 extern "C" {
 
@@ -1076,6 +1070,7 @@ static int map_joins_impl(grb_ctx *ctx, const grb_index *const *idx, const uint6
                 need_members = want_bp = true;
                 break;
             case GRB_OP_WEIGHTED_MEAN:
+            case GRB_OP_WEIGHTED_SUM:
                 need_scores = need_members = want_bp = want_wm = true;
                 break;
             default:
@@ -1092,7 +1087,7 @@ static int map_joins_impl(grb_ctx *ctx, const grb_index *const *idx, const uint6
         if (need_sum && ix->n && ix->sum_mode == GRB_SUM_SWEEP) need_members = true;
     }
     // WEIGHTED_MEAN has a closed form (k_weighted_mean) when every index has exact sums with room for score * coordinate
-    u32 wm_cols = 0;
+    u32 wm_cols = 0, ws_cols = 0;
     if (want_wm && ctx->sweep_mode != 0) {
         bool ok = true;
         for (int s = 0; s < nseq && ok; s++) {
@@ -1103,7 +1098,10 @@ static int map_joins_impl(grb_ctx *ctx, const grb_index *const *idx, const uint6
         }
         if (ok) {
             for (int c = 0; c < k; c++)
-                if (ops[c] == GRB_OP_WEIGHTED_MEAN) wm_cols |= 1u << c;
+                if (ops[c] == GRB_OP_WEIGHTED_MEAN)
+                    wm_cols |= 1u << c;
+                else if (ops[c] == GRB_OP_WEIGHTED_SUM)
+                    ws_cols |= 1u << c;
             want_wm = false;
         }
     }
@@ -1227,7 +1225,7 @@ static int map_joins_impl(grb_ctx *ctx, const grb_index *const *idx, const uint6
     bool bits_direct = false;
     if (valid_bits) {
         GRB_TRY(dbits.stage(ctx, valid_bits, ((b.total * (u64)k + 31) / 32) * 4));
-        bits_direct = k == 1 && !need_members && !bp_cols && !wm_cols && ctx->pipe_mode == 1 && map_pipe_fast(b, o) >= 0;
+        bits_direct = k == 1 && !need_members && !bp_cols && !wm_cols && !ws_cols && ctx->pipe_mode == 1 && map_pipe_fast(b, o) >= 0;
         if (!bits_direct) {
             GRB_TRY(val_tmp.alloc(ctx, b.total * (u64)k));
             o.out_valid = val_tmp.as<u8>();
@@ -1236,7 +1234,7 @@ static int map_joins_impl(grb_ctx *ctx, const grb_index *const *idx, const uint6
         GRB_TRY(dval.stage(ctx, out_valid, b.total * (u64)k));
         o.out_valid = dval.as<u8>();
     }
-    if (!need_members && !bp_cols && !wm_cols) {
+    if (!need_members && !bp_cols && !wm_cols && !ws_cols) {
         GRB_TRY(launch_map<M_MAP>(ctx, b, dls.as<u32>(), dle.as<u32>(), o, bits_direct ? dbits.as<u32>() : nullptr));
     } else {
         TempBuf ub, lb, pp, heavy;
@@ -1253,10 +1251,10 @@ static int map_joins_impl(grb_ctx *ctx, const grb_index *const *idx, const uint6
                                                                                    o.pp, o.lb, o.out, o.out_valid, k, bp_cols);
             GRB_LAUNCHED(ctx);
         }
-        if (wm_cols) {
+        if (wm_cols | ws_cols) {
             k_weighted_mean<<<(unsigned)((b.total - left_offsets[0] + 255) / 256), 256, 0, ctx->stream>>>(b.seqs, b.nseq, left_offsets[0], b.total,
                                                                                                         dls.as<u32>(), dle.as<u32>(),
-                                                                                      o.ub, o.pp, o.lb, o.out, o.out_valid, k, wm_cols);
+                                                                                      o.ub, o.pp, o.lb, o.out, o.out_valid, k, wm_cols, ws_cols);
             GRB_LAUNCHED(ctx);
         }
         if (min_cols | max_cols) {

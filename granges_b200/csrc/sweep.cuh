@@ -280,6 +280,11 @@ __device__ __forceinline__ void sweep_tile(const SeqDev *__restrict__ sd, u64 g_
                         ok = 1;
                         r = wtot ? wsum / (double)wtot : 0.0;
                         break;
+                    case GRB_OP_WEIGHTED_SUM:
+                        mine = o.want_wm != 0;
+                        ok = 1;
+                        r = wsum;
+                        break;
                     default:
                         mine = false;
                         break;

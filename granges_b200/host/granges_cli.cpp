@@ -381,6 +381,8 @@ void check(grb_ctx *ctx, int rc) {
     if (rc != GRB_OK) die(ctx ? grb_last_error(ctx) : "cannot create a CUDA context (granges_b200 has no CPU fallback)");
 }
 
+constexpr int OP_COLLAPSE = 1000;  // FloatOperation::Collapse: not a grb_op (its result is text)
+
 int parse_op(const std::string &s) {
     // clap ValueEnum names of FloatOperation (src/data/operations.rs:35-51), kebab-case
     if (s == "sum") return GRB_OP_SUM;
@@ -389,7 +391,7 @@ int parse_op(const std::string &s) {
     if (s == "max") return GRB_OP_MAX;
     if (s == "mean") return GRB_OP_MEAN;
     if (s == "median") return GRB_OP_MEDIAN;
-    if (s == "collapse") die("collapse is not offered: its output depends on the reference's unspecified visit order");
+    if (s == "collapse") return OP_COLLAPSE;  // text column: grb_collapse_f64, order defined as sort_ranges order
     die("invalid value '" + s + "' for '--func <FUNC>'");
 }
 
@@ -399,6 +401,7 @@ struct Args {
     std::vector<int> ops;
     uint32_t width = 0, step = 0;
     bool has_width = false;
+    int gpus = 1;  // --gpus N (an extension of this mirror): spread `map` over the first N GPUs of the box
 };
 
 int cmd_map(const Args &a) {
@@ -439,31 +442,77 @@ int cmd_map(const Args &a) {
     }
     off[nseq] = ls.size();
     const int k = (int)a.ops.size();
-    std::vector<double> out(nl * (size_t)k);
-    std::vector<uint8_t> ov(nl * (size_t)k);
-    {
+    // numeric reductions go through one fused call; Collapse columns are text and come from the materialised pairs
+    std::vector<int> nops, col_num(k, -1);
+    bool any_collapse = false;
+    for (int c = 0; c < k; c++) {
+        if (a.ops[c] == OP_COLLAPSE) {
+            any_collapse = true;
+        } else {
+            col_num[c] = (int)nops.size();
+            nops.push_back(a.ops[c]);
+        }
+    }
+    const int kn = (int)nops.size();
+    std::vector<double> out(nl * (size_t)kn);
+    std::vector<uint8_t> ov(nl * (size_t)kn);
+    std::vector<const uint32_t *> ps(nseq), pe(nseq);
+    std::vector<const double *> psc(nseq);
+    std::vector<const uint8_t *> pva(nseq);
+    std::vector<size_t> pn(nseq);
+    for (int s = 0; s < nseq; s++) {
+        ps[s] = R[s].starts.data();
+        pe[s] = R[s].ends.data();
+        psc[s] = R[s].score.data();
+        pva[s] = R[s].valid.data();
+        pn[s] = R[s].starts.size();
+    }
+    if (kn) {
         Phase ph("index builds + map_joins");
         // into_coitrees -> left_overlaps -> map_joins in one pipelined call: uploads, index builds, map kernels and
         // downloads of different seqnames overlap.  A seqname the right file never mentions (n = 0) has no container
         // (its groups are empty either way).
-        std::vector<const uint32_t *> ps(nseq), pe(nseq);
-        std::vector<const double *> psc(nseq);
-        std::vector<const uint8_t *> pva(nseq);
-        std::vector<size_t> pn(nseq);
-        for (int s = 0; s < nseq; s++) {
-            ps[s] = R[s].starts.data();
-            pe[s] = R[s].ends.data();
-            psc[s] = R[s].score.data();
-            pva[s] = R[s].valid.data();
-            pn[s] = R[s].starts.size();
+        if (a.gpus > 1) {
+            std::vector<int> devs(a.gpus);
+            for (int d = 0; d < a.gpus; d++) devs[d] = d;
+            char err[512];
+            if (grb_map_joins_whole_f64_mgpu(devs.data(), a.gpus, nseq, ps.data(), pe.data(), pn.data(), psc.data(), pva.data(), off.data(), ls.data(),
+                                             le.data(), nops.data(), kn, out.data(), ov.data(), err, sizeof(err)) != GRB_OK)
+                die(err);
+        } else {
+            check(ctx, grb_map_joins_whole_f64(ctx, nseq, ps.data(), pe.data(), pn.data(), psc.data(), pva.data(), off.data(), ls.data(), le.data(),
+                                               nops.data(), kn, out.data(), ov.data()));
         }
-        check(ctx, grb_map_joins_whole_f64(ctx, nseq, ps.data(), pe.data(), pn.data(), psc.data(), pva.data(), off.data(), ls.data(), le.data(),
-                                           a.ops.data(), k, out.data(), ov.data()));
+    }
+    std::vector<uint64_t> ctext_off;  // Collapse: row i is ctext[ctext_off[i] .. ctext_off[i + 1])
+    std::string ctext;
+    size_t max_collapse = 0;
+    if (any_collapse) {
+        Phase ph("collapse");
+        ctext_off.assign(nl + 1, 0);
+        for (int s = 0; s < nseq; s++) {
+            const size_t n_s = (size_t)(off[s + 1] - off[s]);
+            grb_index *ix = nullptr;
+            if (pn[s]) {
+                check(ctx, grb_index_build(ctx, ps[s], pe[s], nullptr, pn[s], &ix));
+                check(ctx, grb_index_set_scores(ix, psc[s], pva[s], pn[s]));
+            }
+            grb_text *t = nullptr;
+            check(ctx, grb_collapse_f64(ctx, ix, ls.data() + off[s], le.data() + off[s], n_s, &t));
+            std::vector<uint64_t> to(n_s + 1);
+            const size_t base = ctext.size();
+            ctext.resize(base + grb_text_bytes(t));
+            check(ctx, grb_text_copy(t, to.data(), ctext.data() + base));
+            for (size_t i = 0; i <= n_s; i++) ctext_off[off[s] + i] = base + to[i];
+            for (size_t i = 0; i < n_s; i++) max_collapse = std::max(max_collapse, (size_t)(to[i + 1] - to[i]));
+            grb_text_destroy(t);
+            grb_index_destroy(ix);
+        }
     }
     Phase phw("write");
     size_t max_name = 0;
     for (auto &nm : g.names) max_name = std::max(max_name, nm.size());
-    write_rows(a.has_output ? a.output.c_str() : nullptr, nl, max_name + 64 + (size_t)k * 420, [&](size_t i, char *q) {
+    write_rows(a.has_output ? a.output.c_str() : nullptr, nl, max_name + 64 + (size_t)k * (420 + max_collapse), [&](size_t i, char *q) {
         const int sq = (int)(std::upper_bound(off.begin(), off.end(), (uint64_t)i) - off.begin()) - 1;
         const std::string &name = g.names[sq];
         memcpy(q, name.data(), name.size());
@@ -474,8 +523,12 @@ int cmd_map(const Args &a) {
         q = grh::format_u32(q, le[i]);
         for (int c = 0; c < k; c++) {
             *q++ = '\t';
-            if (ov[i * k + c])
-                q = grh::format_f64(q, out[i * k + c]);
+            if (col_num[c] < 0) {
+                const size_t len = (size_t)(ctext_off[i + 1] - ctext_off[i]);
+                memcpy(q, ctext.data() + ctext_off[i], len);
+                q += len;
+            } else if (ov[i * kn + col_num[c]])
+                q = grh::format_f64(q, out[i * kn + col_num[c]]);
             else
                 *q++ = '.';
         }
@@ -724,6 +777,7 @@ int cmd_merge(const std::string &bedfile, long long distance, const std::vector<
     init.join();
     if (r.starts.empty()) die("File '" + bedfile + "' is empty.");
     if (r.ncols == 5 && ops.size() != 1) die("BED5 input needs exactly one --func (the reference unwraps it: src/commands.rs:656)");
+    if (r.ncols == 5 && ops[0] == OP_COLLAPSE) die("merge --func collapse is not offered by this mirror (map --func collapse is)");
     check(nullptr, ctx_rc);
     std::vector<uint64_t> ro = seqname_runs(r.seqname);
     grb_merged *mg = nullptr;
@@ -965,7 +1019,7 @@ int cmd_random_bed(const Args &a, size_t num, bool sort, bool scores, uint64_t s
 void usage() {
     fprintf(stderr,
             "granges (B200 mirror of the overlap-join commands)\n"
-            "  granges map     -g <genome> -l <left.bed> -r <right.bed5> -f <op[,op..]> [-o <out>] [-s]\n"
+            "  granges map     -g <genome> -l <left.bed> -r <right.bed5> -f <op[,op..]> [-o <out>] [-s] [--gpus N]\n"
             "  granges filter  -g <genome> -l <left.bed> -r <right.bed> [-o <out>] [-s]\n"
             "  granges windows -g <genome> -w <width> [-s <step>] [-c] [-o <out>]\n"
             "  granges merge   -b <bedfile> [-d <distance>] [-f <op>] [-o <out>]\n"
@@ -1061,6 +1115,10 @@ int main(int argc, char **argv) {
             a.chop = true;
         else if (!windows && (f == "-s" || f == "--skip-missing"))
             a.skip_missing = true;
+        else if (cmd == "map" && f == "--gpus") {
+            a.gpus = (int)strtol(need().c_str(), nullptr, 10);
+            if (a.gpus < 1 || a.gpus > 64) die("invalid value for '--gpus <N>'");
+        }
         else if (f == "-h" || f == "--help") {
             usage();
             return 0;

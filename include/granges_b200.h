@@ -74,8 +74,8 @@ typedef enum grb_status {
 } grb_status;
 
 /* FloatOperation (src/data/operations.rs:35-51) plus the two join-metadata
- * reductions closures commonly use (src/join.rs:153-163).  Collapse is not
- * offered: its output depends on the unspecified visit order (src/join.rs:97). */
+ * reductions closures commonly use (src/join.rs:153-163).  Collapse yields text, not a
+ * number: see grb_collapse_f64 below. */
 typedef enum grb_op {
     GRB_OP_SUM = 0,           /* empty -> 0.0            operations.rs:60-63 */
     GRB_OP_SUM_NOT_EMPTY = 1, /* empty -> NoValue        operations.rs:64-70 */
@@ -87,7 +87,8 @@ typedef enum grb_op {
     GRB_OP_OVERLAP_BP = 7,    /* sum of overlap_widths, join.rs:158-163, commands.rs:839-843 */
     GRB_OP_WEIGHTED_MEAN = 8, /* sum(score * overlap_width) / sum(overlap_width) over the non-missing scores, 0.0 if none:
                                  the closure of examples/weighted_mean.rs:4-31 (join.rs:158-163 overlap_widths) */
-    GRB_OP__COUNT = 9
+    GRB_OP_WEIGHTED_SUM = 9,  /* sum(score * overlap_width) over the non-missing scores, 0.0 if none (the numerator above) */
+    GRB_OP__COUNT = 10
 } grb_op;
 
 #define GRB_MAX_OPS 16
@@ -207,6 +208,44 @@ int grb_filter_overlaps_select(grb_ctx *ctx, const grb_index *const *idx, const 
 int grb_map_joins_f64_batch(grb_ctx *ctx, const grb_index *const *idx, const uint64_t *left_offsets, int nseq,
                             const uint32_t *ls, const uint32_t *le, const int *ops, int k, double *out,
                             uint8_t *out_valid);
+
+/* Composable reducers: the closures users write over a join -- examples/weighted_mean.rs:4-31,
+ * src/commands.rs:839-843 -- are folds of  value(right) * weight(left, right)  over the overlapping rights.  Instead of
+ * one enum value per closure a reducer is described by its parts, and every column of one call may have its own:
+ *   value   SCORE: the right's score, rights whose score is None are skipped (src/commands.rs:526-531)
+ *           ONE:   1 per overlapping right, scored or not
+ *   weight  ONE, or OVERLAP_WIDTH = LeftGroupedJoin::overlap_widths (src/join.rs:158-163)
+ *   fold    SUM, MIN, MAX (MIN / MAX see finite values only, like FloatOperation::Min / Max; they take weight ONE)
+ *   divide  NONE, or BY_WEIGHTS: divide the sum by the summed weights of the rights that contributed (a mean)
+ *   empty   what a left without contributing rights gets: ZERO (0.0, a value) or NOVALUE (DatumType::NoValue)
+ * e.g. {SCORE, OVERLAP_WIDTH, SUM, BY_WEIGHTS, ZERO} is the weighted mean of examples/weighted_mean.rs,
+ * {ONE, OVERLAP_WIDTH, SUM, NONE, ZERO} the covered basepairs of feature-density, {SCORE, ONE, SUM, BY_WEIGHTS, NOVALUE}
+ * FloatOperation::Mean.  Every supported combination is answered without visiting the members (prefix sums, closed forms,
+ * stabbing tables); a combination with no such form returns GRB_ERR_UNSUPPORTED. */
+typedef enum grb_red_value { GRB_VALUE_SCORE = 0, GRB_VALUE_ONE = 1 } grb_red_value;
+typedef enum grb_red_weight { GRB_WEIGHT_ONE = 0, GRB_WEIGHT_OVERLAP_WIDTH = 1 } grb_red_weight;
+typedef enum grb_red_fold { GRB_FOLD_SUM = 0, GRB_FOLD_MIN = 1, GRB_FOLD_MAX = 2 } grb_red_fold;
+typedef enum grb_red_divide { GRB_DIVIDE_NONE = 0, GRB_DIVIDE_BY_WEIGHTS = 1 } grb_red_divide;
+typedef enum grb_red_empty { GRB_EMPTY_ZERO = 0, GRB_EMPTY_NOVALUE = 1 } grb_red_empty;
+typedef struct grb_reducer {
+    int value, weight, fold, divide, empty;
+} grb_reducer;
+int grb_map_joins_reduce_batch(grb_ctx *ctx, const grb_index *const *idx, const uint64_t *left_offsets, int nseq,
+                               const uint32_t *ls, const uint32_t *le, const grb_reducer *reducers, int k, double *out,
+                               uint8_t *out_valid);
+
+/* FloatOperation::Collapse (src/data/operations.rs:99-106): the non-missing scores of every group as text, joined by
+ * ",", each printed like Rust's f64::to_string (shortest round-trip digits, positional).  The reference concatenates in
+ * the tree's visit order, which it leaves unspecified (src/join.rs:97); here the order is DEFINED as
+ * LeftGroupedJoin::sort_ranges order -- (start, end, data index), src/join.rs:121-128 -- so the output is reproducible.
+ * A left without scored overlaps gets the empty string (DatumType::String("")).  Row i is bytes
+ * [offsets[i], offsets[i+1]) of the text; one seqname per call (idx NULL: every row empty). */
+typedef struct grb_text grb_text;
+int grb_collapse_f64(grb_ctx *ctx, const grb_index *idx, const uint32_t *ls, const uint32_t *le, size_t nl, grb_text **out);
+size_t grb_text_bytes(const grb_text *t);
+/* offsets: nl + 1 entries; bytes: grb_text_bytes(t) characters, no terminator.  Host buffers. */
+int grb_text_copy(const grb_text *t, uint64_t *offsets, char *bytes);
+void grb_text_destroy(grb_text *t);
 
 /* The same call with the validity as BITS: bit (i * k + c) of out_valid_bits (word (i * k + c) / 32, u32 words,
  * ceil(nl * k / 32) of them) is 1 for DatumType::Float64, 0 for DatumType::NoValue -- the NL * K / 8 bytes SURVEY 8(d)

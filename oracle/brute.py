@@ -88,7 +88,7 @@ def map_joins(ls, le, rs, re, scores, valid, ops, idx=None):
         for o, op in enumerate(ops):
             if op == "count":
                 out[i, o], ov[i, o] = len(g), 1
-            elif op == "weighted-mean":
+            elif op in ("weighted-mean", "weighted-sum"):
                 num = den = 0.0
                 for d in g:
                     if valid is None or valid[d]:
@@ -96,7 +96,7 @@ def map_joins(ls, le, rs, re, scores, valid, ops, idx=None):
                         w = float(max(0, min(le[i], re[j]) - max(ls[i], rs[j])))
                         num += scores[d] * w
                         den += w
-                out[i, o], ov[i, o] = (num / den if den > 0 else 0.0), 1
+                out[i, o], ov[i, o] = (num if op == "weighted-sum" else (num / den if den > 0 else 0.0)), 1
             elif op == "overlap-bp":
                 bp = 0
                 for d in g:

@@ -60,6 +60,7 @@ enum {
     ORC_OP_COUNT = 6,      /* LeftGroupedJoin::num_overlaps, join.rs:153 */
     ORC_OP_OVERLAP_BP = 7, /* sum of overlap_widths, join.rs:158-163, commands.rs:839-843 */
     ORC_OP_WEIGHTED_MEAN = 8, /* examples/weighted_mean.rs:4-31: sum(score*width)/sum(width) over Some scores, else 0.0 */
+    ORC_OP_WEIGHTED_SUM = 9,  /* the numerator of the same closure: score_sum (examples/weighted_mean.rs:17-21) */
 };
 
 /* One node = coitrees::IntervalNode<usize, usize> restated: closed interval
@@ -476,6 +477,9 @@ static void *map_worker(void *arg) {
                     ok = 1;
                 } else if (jb->ops[o] == ORC_OP_WEIGHTED_MEAN) {
                     r = total_width > 0.0 ? score_sum / total_width : 0.0; /* examples/weighted_mean.rs:26-30 */
+                    ok = 1;
+                } else if (jb->ops[o] == ORC_OP_WEIGHTED_SUM) {
+                    r = score_sum;
                     ok = 1;
                 } else {
                     ok = orc_float_op(jb->ops[o], vals, nv, &r);

@@ -14,7 +14,7 @@ import numpy as np
 _HERE = os.path.dirname(os.path.abspath(__file__))
 _LIB_PATH = os.path.join(_HERE, "liboracle.so")
 
-OP_SUM, OP_SUM_NOT_EMPTY, OP_MIN, OP_MAX, OP_MEAN, OP_MEDIAN, OP_COUNT, OP_OVERLAP_BP, OP_WEIGHTED_MEAN = range(9)
+OP_SUM, OP_SUM_NOT_EMPTY, OP_MIN, OP_MAX, OP_MEAN, OP_MEDIAN, OP_COUNT, OP_OVERLAP_BP, OP_WEIGHTED_MEAN, OP_WEIGHTED_SUM = range(10)
 OPS = {
     "sum": OP_SUM,
     "sum-not-empty": OP_SUM_NOT_EMPTY,
@@ -25,6 +25,7 @@ OPS = {
     "count": OP_COUNT,
     "overlap-bp": OP_OVERLAP_BP,
     "weighted-mean": OP_WEIGHTED_MEAN,
+    "weighted-sum": OP_WEIGHTED_SUM,
 }
 
 

@@ -12,12 +12,14 @@ def assert_map_equal(out, ov, want, wv, ops, abs_sums, nvalid=None):
     assert (np.asarray(ov) == wv).all(), "validity (NoValue) mismatch"
     for c, op in enumerate(ops):
         m = wv[:, c] == 1
-        if op in ("sum", "sum-not-empty", "mean", "weighted-mean"):
+        if op in ("sum", "sum-not-empty", "mean", "weighted-mean", "weighted-sum"):
             o, w = out[m, c], want[m, c]
             fin = np.isfinite(w)
             assert (np.isnan(o) == np.isnan(w)).all(), (op, "NaN results differ")
             assert (o[np.isinf(w)] == w[np.isinf(w)]).all(), (op, "infinite results differ")
             tol = SUM_TOL * np.maximum(abs_sums[m], 0) + 0.0
+            if op == "weighted-sum":
+                tol = tol * 1e3 + SUM_TOL * np.abs(w)  # every term carries an overlap width (< maxlen of the test cases)
             if op == "mean" and nvalid is not None:
                 tol = tol / np.maximum(nvalid[m], 1)
             err = np.abs(o[fin] - w[fin])

@@ -57,4 +57,4 @@ def random_case(seed, nl, nr, span=2000, maxlen=60, null_frac=0.0, score_kind="u
     return dict(ls=ls, le=le, rs=rs, re=re, scores=sc, valid=valid)
 
 
-ALL_OPS = ["sum", "sum-not-empty", "min", "max", "mean", "median", "count", "overlap-bp", "weighted-mean"]
+ALL_OPS = ["sum", "sum-not-empty", "min", "max", "mean", "median", "count", "overlap-bp", "weighted-mean", "weighted-sum"]

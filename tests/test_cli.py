@@ -108,6 +108,39 @@ def test_map_matches_oracle_text(tmp_path, orc):
                     assert ops[c] in ("mean", "sum", "sum-not-empty") and abs(float(a) - float(b)) <= 1e-12 * abs(float(b)), (g, w)
 
 
+def test_map_collapse_and_gpus(tmp_path, orc):
+    """`map --func max,collapse,mean`: the Collapse column is text -- the group's non-missing scores in sort_ranges order
+    (src/join.rs:121-128; the reference leaves the order open), joined by "," -- beside numeric columns; `--gpus N` (the
+    in-process multi-GPU call) prints the same bytes as one GPU."""
+    import torch
+
+    genome, left, right, lorder, rorder, _ = make_files(tmp_path, seed=12)
+    base = ["map", "--genome", tmp_path / "genome.tsv", "--left", tmp_path / "left.bed", "--right", tmp_path / "right.bed", "--func", "max,collapse,mean"]
+    got = run(*base).stdout
+    want = []
+    for name in genome:
+        if name not in left:
+            continue
+        ls, le = (a[lorder[name]] for a in left[name])
+        rs, re, sc, valid = (a[rorder[name]] for a in right[name])
+        t = orc.Tree(rs, re) if len(rs) else None
+        o, ov = orc.map_joins(t, sc if t is not None else None, valid.astype(np.uint8) if t is not None else None, ls, le, ["max", "mean"])
+        off, idx, _, _ = orc.left_overlaps(t, ls, le)
+        for i in range(len(ls)):
+            members = [int(d) for d in idx[int(off[i]):int(off[i + 1])] if valid[int(d)]]
+            cols = [rust_display(float(o[i, 0])) if ov[i, 0] else ".", ",".join(rust_display(float(sc[d])) for d in members),
+                    rust_display(float(o[i, 1])) if ov[i, 1] else "."]
+            want.append("\t".join([name, str(ls[i]), str(le[i])] + cols))
+    rows = got.splitlines()
+    assert len(rows) == len(want)
+    for g, w in zip(rows, want):
+        gf, wf = g.split("\t"), w.split("\t")
+        assert gf[:5] == wf[:5], (g, w)
+        assert gf[5] == wf[5] or abs(float(gf[5]) - float(wf[5])) <= 1e-12 * abs(float(wf[5]))
+    for n in sorted({1, torch.cuda.device_count()}):
+        assert run(*base, "--gpus", n).stdout == got
+
+
 def test_map_bedtools_doc_example(tmp_path, goldens):
     g = goldens["bedtools_map_example"]
     (tmp_path / "g.tsv").write_text("chr1\t1000\n")

@@ -288,3 +288,49 @@ def test_unsorted_device_lefts_are_learned(ctx, orc):
                 continue
             want, wv, abs_sums, nvalid = oracle_refs(orc, c, ["mean"])
             assert_map_equal(out[sl], ov[sl], want, wv, ["mean"], abs_sums, nvalid)
+
+
+def test_composable_reducers(ctx, orc):
+    """grb_map_joins_reduce_batch: a reducer described by its parts (value, weight, fold, divide, empty) gives what the
+    closure it stands for gives -- FloatOperation::run (src/data/operations.rs:53-109), the weighted mean of
+    examples/weighted_mean.rs:4-31, the covered basepairs of src/commands.rs:839-843 -- and unsupported combinations fail."""
+    import granges_b200 as gb
+
+    c = random_case(901, 4000, 5000, span=90_000, maxlen=700, sorted_left=True, null_frac=0.15, score_kind="signed-decimal")
+    ix = ctx.index_build(c["rs"], c["re"]).set_scores(c["scores"], c["valid"])
+    off = np.array([0, len(c["ls"])], np.uint64)
+    table = [(("score", "one", "sum", "none", "zero"), "sum"), (("score", "one", "sum", "none", "novalue"), "sum-not-empty"),
+             (("score", "one", "sum", "by-weights", "novalue"), "mean"), (("one", "one", "sum", "none", "zero"), "count"),
+             (("one", "overlap-width", "sum", "none", "zero"), "overlap-bp"), (("score", "overlap-width", "sum", "by-weights", "zero"), "weighted-mean"),
+             (("score", "overlap-width", "sum", "none", "zero"), "weighted-sum"), (("score", "one", "min", "none", "novalue"), "min"),
+             (("score", "one", "max", "none", "novalue"), "max")]
+    ops = [op for _, op in table]
+    out, ov = ctx.map_joins_reduce([ix], off, c["ls"], c["le"], [r for r, _ in table])
+    want, wv, abs_sums, nvalid = oracle_refs(orc, c, ops)
+    assert_map_equal(out, ov, want, wv, ops, abs_sums, nvalid)
+    # the same numbers as the enum spelling, bit for bit
+    o2, v2 = ctx.map_joins_batch([ix], off, c["ls"], c["le"], ops)
+    assert (v2 == ov).all() and same_bits(o2[ov == 1], out[ov == 1])
+    for bad in [("score", "overlap-width", "min", "none", "novalue"), ("one", "one", "sum", "by-weights", "zero"), ("score", "one", "min", "none", "zero")]:
+        with pytest.raises(gb.GRangesError) as ei:
+            ctx.map_joins_reduce([ix], off, c["ls"], c["le"], [bad])
+        assert ei.value.code == -8
+
+
+def test_collapse_in_sort_ranges_order(ctx, orc):
+    """FloatOperation::Collapse (src/data/operations.rs:99-106) with the order the reference leaves open pinned to
+    LeftGroupedJoin::sort_ranges (src/join.rs:121-128): per left, the non-missing scores of its group in (start, end, index)
+    order, printed like f64::to_string and joined by ","; "" for a left without scored overlaps."""
+    from tests.test_host_format import rust_display
+
+    for seed, kw in ((31, dict(null_frac=0.3, score_kind="decimal")), (32, dict(score_kind="nonfinite")), (33, dict(score_kind="mixed", maxlen=3, span=40))):
+        c = random_case(seed, 700, 900, **kw)
+        ix = ctx.index_build(c["rs"], c["re"]).set_scores(c["scores"], c["valid"])
+        rows = ctx.collapse(ix, c["ls"], c["le"])
+        off, idx, _, _ = orc.left_overlaps(orc.Tree(c["rs"], c["re"]), c["ls"], c["le"])
+        assert len(rows) == len(c["ls"])
+        for i, row in enumerate(rows):
+            members = [int(d) for d in idx[int(off[i]):int(off[i + 1])] if c["valid"] is None or c["valid"][int(d)]]
+            assert row == ",".join(rust_display(float(c["scores"][d])) for d in members), i
+    assert ctx.collapse(None, c["ls"][:5], c["le"][:5]) == [""] * 5
+    assert ctx.collapse(ix, np.zeros(0, np.uint32), np.zeros(0, np.uint32)) == []

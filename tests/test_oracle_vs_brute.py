@@ -36,9 +36,9 @@ def test_tree_vs_brute(nl, nr, kw):
     assert (ov == bov).all()
     for o, op in enumerate(ALL_OPS):
         m = bov[:, o] == 1
-        if op in ("sum", "sum-not-empty", "mean", "weighted-mean"):
+        if op in ("sum", "sum-not-empty", "mean", "weighted-mean", "weighted-sum"):
             # visit order differs between tree and brute force: tolerance relative to sum |x|
-            assert np.allclose(out[m, o], bout[m, o], rtol=1e-12, atol=1e-9 * (np.abs(c["scores"]).max() if nr else 1))
+            assert np.allclose(out[m, o], bout[m, o], rtol=1e-12, atol=1e-9 * (np.abs(c["scores"]).max() if nr else 1) * (1e3 if op == "weighted-sum" else 1))
         else:
             assert (out[m, o] == bout[m, o]).all(), op
 
