@@ -169,9 +169,37 @@ struct PipeOps {
 };
 
 // #(keys < x) among the 8 keys of the two aligned quads at q
+#ifndef PIPE_COUNT_PTX
+#define PIPE_COUNT_PTX 0  // A/B switch: compare + predicated add per key in PTX (2 instructions; nvcc's own code takes 3: compare, add, un-add)
+#endif
+#ifndef PIPE_MERGE_RARE
+#define PIPE_MERGE_RARE 0  // A/B switch: one branch for "some search of this thread met a crowded bin" instead of one per search
+#endif
+__device__ __forceinline__ u32 count4_below(const uint4 v, u32 x) {
+#if PIPE_COUNT_PTX
+    u32 c;
+    asm("{\n"
+        ".reg .pred p0, p1, p2, p3;\n"
+        "setp.lt.u32 p0, %1, %5;\n"
+        "setp.lt.u32 p1, %2, %5;\n"
+        "setp.lt.u32 p2, %3, %5;\n"
+        "setp.lt.u32 p3, %4, %5;\n"
+        "mov.u32 %0, 0;\n"
+        "@p0 add.u32 %0, %0, 1;\n"
+        "@p1 add.u32 %0, %0, 1;\n"
+        "@p2 add.u32 %0, %0, 1;\n"
+        "@p3 add.u32 %0, %0, 1;\n"
+        "}\n"
+        : "=r"(c)
+        : "r"(v.x), "r"(v.y), "r"(v.z), "r"(v.w), "r"(x));
+    return c;
+#else
+    return (v.x < x) + (v.y < x) + (v.z < x) + (v.w < x);
+#endif
+}
 __device__ __forceinline__ u32 count8_below(const u32 *__restrict__ K, u32 q, u32 x) {
     const uint4 v0 = *reinterpret_cast<const uint4 *>(K + q), v1 = *reinterpret_cast<const uint4 *>(K + q + 4);
-    return (v0.x < x) + (v0.y < x) + (v0.z < x) + (v0.w < x) + (v1.x < x) + (v1.y < x) + (v1.z < x) + (v1.w < x);
+    return count4_below(v0, x) + count4_below(v1, x);
 }
 
 // flags: bit 0 = stage with TMA; bit 1 = debug, consumers skip the arithmetic (pipeline-only timing); bit 2 = debug, no stores
@@ -499,10 +527,21 @@ __global__ void __launch_bounds__(PIPE_THREADS, 1) k_map_pipe(const SeqDev *__re
                     ppk[k] = a0 + pP;
                 }
             }
+#if PIPE_MERGE_RARE
+            if (((cA[0] | cB[0] | cA[1] | cB[1]) & 8u) != 0) {  // rare: some search met a crowded bin, the scan goes on
+#pragma unroll
+                for (int k = 0; k < PIPE_LPT; k++) {
+                    if (cA[k] == 8) pA[k] = scan_lower_bound(KA, pA[k], b[k]);
+                    if (cB[k] == 8) pB[k] = scan_lower_bound(KB, pB[k], a[k] + 1);
+                }
+            }
+#endif
 #pragma unroll
             for (int k = 0; k < PIPE_LPT; k++) {
+#if !PIPE_MERGE_RARE
                 if (cA[k] == 8) pA[k] = scan_lower_bound(KA, pA[k], b[k]);      // rare: a crowded bin
                 if (cB[k] == 8) pB[k] = scan_lower_bound(KB, pB[k], a[k] + 1);
+#endif
                 pa[k] = want_prefixes ? S.pa[sw][pA[k]] : 0ull;
                 pb[k] = want_prefixes ? S.pb[sw][pB[k]] : 0ull;
                 if (WIDE && want_prefixes) {
