@@ -358,6 +358,84 @@ def run_configs(ctx, dev, peak, scale=1.0):
     return res
 
 
+def run_c4_sharded(ctx, dev, rank, world, dist, peak, scale=1.0):
+    """BASELINE config C4 (windows 1 kb / 500 bp over hg38 x 500M clustered BED5, map mean) over the ranks of this run:
+    the windows are cut into contiguous (seqname, coordinate) units of equal cost, every rank indexes only the rights its
+    units can touch and answers its windows; no data moves between ranks.  Device-timed, max over ranks."""
+    nr = int(500_000_000 * scale)
+    nr_per = split_counts(nr, 22)
+    CH = 2048  # planning granularity: chunks of 2048 windows (1.024 Mbp)
+    nw = [(HG38[s] + 499) // 500 for s in range(22)]
+    rights, chunk_cost, chunk_seq, chunk_w0 = {}, [], [], []
+    for s in range(22):
+        rs, re, sc = clustered_rights(s, nr_per[s], 15, dev)
+        rights[s] = (rs, re, sc)
+        edges_w = torch.arange(0, nw[s] + CH, CH, device=dev).clamp(max=nw[s])
+        cum = torch.searchsorted(rs.to(torch.int64), edges_w * 500)
+        # Cost of a chunk: two searches per window, each a bin-table lookup plus a scan through the bin -- bins are sized for
+        # the seqname's MEAN density (about 2 rights), so a window in a region k times denser scans k times further:
+        # windows * (1 + occupancy / 8) with occupancy = rights in the chunk / bins in the chunk, bin width = 2 L / n.
+        wins = (edges_w[1:] - edges_w[:-1]).to(torch.float64)
+        cost = wins + (cum[1:] - cum[:-1]).to(torch.float64) * (HG38[s] / (2000.0 * max(nr_per[s], 1)))
+        chunk_cost.append(cost.cpu().numpy())
+        chunk_seq += [s] * len(cost)
+        chunk_w0 += [int(x) for x in edges_w[:-1].cpu().numpy()]
+    cost = np.concatenate(chunk_cost)
+    cum = np.concatenate([[0.0], np.cumsum(cost)])
+    owner = np.minimum((cum[:-1] + cost / 2) / cum[-1] * world, world - 1).astype(np.int64)  # contiguous runs of chunks
+    mine = np.nonzero(owner == rank)[0]
+    idxs, offs, ls_parts, le_parts, n_right_mine = [], [0], [], [], 0
+    if len(mine):
+        # runs of my chunks inside one seqname = units
+        seqs = np.array(chunk_seq)[mine]
+        for s in sorted(set(int(q) for q in seqs)):
+            cs = mine[seqs == s]
+            w0 = chunk_w0[int(cs[0])]
+            w1 = min(chunk_w0[int(cs[-1])] + CH, nw[s])
+            L = HG38[s]
+            ws = torch.arange(w0, w1, dtype=torch.int64, device=dev) * 500
+            we = torch.clamp(ws + 1000, max=L)
+            lo, hi = int(ws[0].item()), int(we[-1].item())
+            rs, re, sc = rights[s]
+            m = (rs < hi) & (re > lo)
+            idxs.append(ctx.index_build(rs[m].contiguous(), re[m].contiguous()).set_scores(sc[m].contiguous()))
+            n_right_mine += int(m.sum().item())
+            ls_parts.append(ws.to(torch.int32))
+            le_parts.append(we.to(torch.int32))
+            offs.append(offs[-1] + (w1 - w0))
+    del rights
+    torch.cuda.empty_cache()
+    n_mine = offs[-1]
+    ms_mine = 0.0
+    if n_mine:
+        ls, le = torch.cat(ls_parts), torch.cat(le_parts)
+        out = torch.empty((n_mine, 1), dtype=torch.float64, device=dev)
+        ov = torch.empty((n_mine, 1), dtype=torch.uint8, device=dev)
+        call = ctx.prepare_map(idxs, np.array(offs, np.uint64), ls, le, ["mean"], out, ov)
+        torch.cuda.synchronize()
+    if dist is not None:
+        dist.barrier()
+    if n_mine:
+        ms_mine = event_ms(call, 10, 3)
+    t = torch.tensor([ms_mine], dtype=torch.float64, device=dev)
+    per_rank = [ms_mine]
+    if dist is not None:
+        gathered = [torch.zeros(1, dtype=torch.float64, device=dev) for _ in range(world)]
+        dist.all_gather(gathered, t)
+        per_rank = [float(g.item()) for g in gathered]
+    agg = torch.tensor([n_mine, n_right_mine], dtype=torch.int64, device=dev)
+    if dist is not None:
+        dist.all_reduce(agg)
+    for ix in idxs:
+        ix.close()
+    ms = max(per_rank)
+    nw_tot = int(agg[0].item())
+    alg = nr * 16 + nw_tot * 8.125
+    return {"workload": f"windows 1 kb / 500 bp ({nw_tot}) x {nr} clustered BED5, map mean, sharded by (seqname, coordinate) over {world} GPUs",
+            "ms": ms, "lefts_per_s": nw_tot / ms * 1e3, "roofline_frac": alg / (ms * 1e-3) / 1e9 / peak / world, "algorithmic_bytes": alg,
+            "ms_per_rank": per_rank, "rights_indexed_all_ranks": int(agg[1].item())}
+
+
 class ClockSampler:
     """SM clock and throttle reasons sampled DURING the timed region (NVML, every ~5 ms, own thread)."""
     REASONS = {0x8: "hw_slowdown", 0x40: "hw_thermal_slowdown", 0x20: "sw_thermal_slowdown", 0x4: "sw_power_cap"}
@@ -786,6 +864,10 @@ def main():
             del h_rights, h_ls, h_le, p_rights, p_ls, p_le, host
         host_barrier()
 
+    c4_sharded = None
+    if world > 1 and not args.no_configs and ops == ["mean"]:
+        c4_sharded = run_c4_sharded(ctx, dev, rank, world, dist, peak)
+
     if rank != 0:
         if dist is not None:
             dist.barrier()
@@ -831,6 +913,8 @@ def main():
         torch.cuda.empty_cache()
         configs.update(run_configs(ctx, dev, peak))
         line["configs"] = configs
+    if c4_sharded is not None:
+        line["configs"] = {"C4": c4_sharded}
 
     # ---- cpu baseline: the oracle on a bounded sample (one seqname), 1 thread like the reference
     if world == 1 and not args.no_cpu:
