@@ -676,8 +676,10 @@ def main():
     cost_per = [int(c) for c in nr_per]
     if any(o in ("min", "max", "median", "weighted-mean") for o in ops):
         cost_per = [int(nr_per[s] + sharding.PAIR_WEIGHT * nl_per[s] * nr_per[s] * 1000.0 / HG38[s]) for s in range(22)]
-    plan = sharding.plan(left_off, cost_per, world)
-    mine = sharding.units_of(plan, rank)
+    # (development knob: time the share rank R of a W-rank run would get, on one GPU, without launching W processes)
+    plan_world, plan_rank = int(os.environ.get("GRB_BENCH_AS_WORLD", world)), int(os.environ.get("GRB_BENCH_AS_RANK", rank))
+    plan = sharding.plan(left_off, cost_per, plan_world)
+    mine = sharding.units_of(plan, plan_rank)
 
     # a non-default stream: stream-ordered allocation on the legacy default stream is several times slower
     stream = torch.cuda.Stream(device=dev)
@@ -698,6 +700,10 @@ def main():
             lo, hi = sharding.unit_bounds(ls_s, le_s)
             m = sharding.unit_right_mask(rs, re, lo, hi)
             rs, re, sc = rs[m].contiguous(), re[m].contiguous(), sc[m].contiguous()
+            # re-base the unit to its own origin: overlaps only depend on coordinate differences, and the index sizes its
+            # coordinate bins for [0, max end) -- a unit from the far end of a chromosome would get bins several rights wide
+            base = sharding.unit_origin(rs, lo)
+            rs, re, ls_s, le_s = rs - base, re - base, ls_s - base, le_s - base
         torch.cuda.synchronize()
         t0 = time.perf_counter()
         ix = ctx.index_build(rs, re).set_scores(sc)

@@ -5,12 +5,14 @@
 // coordinate (sorted BED files, from_windows): a tile of 1024 such lefts touches a slice of the index that fits shared
 // memory.  Shuffled lefts break that -- every left becomes a chain of dependent global loads, 20x slower.
 //
-// So unsorted lefts are first dropped into coordinate buckets of ~64 lefts per seqname (a counting sort: histogram with
-// global atomics, one scan over the bucket counts, scatter through per-bucket cursors).  Order inside a bucket does not
-// matter: a tile of bucketed lefts spans 1024 + 64 lefts' worth of coordinates, so its windows fit, and every result is
-// written back to the row its left came from (`rank`).  Blocks walk the lefts in array order, i.e. seqname by seqname,
-// and one seqname's share of every array involved fits the L2, so the atomics and the scattered 4- and 8-byte writes
-// are absorbed there: DRAM sees each array about once.
+// So unsorted lefts are first dropped into coordinate buckets of ~64 lefts per seqname, in two levels of 256-way
+// partitions that only use shared-memory atomics: level A sends the lefts of every tile of 4096 to the seqname's 256
+// coarse buckets (per-tile histograms -> one scan -> scatter), level B splits every coarse bucket (a few thousand lefts,
+// contiguous by then, L2-resident) into its 256 fine buckets with one CTA.  Order inside a bucket does not matter: a
+// tile of bucketed lefts spans 1024 + 64 lefts' worth of coordinates, so its windows fit the pipeline's ring slots.
+// Level B also records where every original row went (`pos`), and the results are gathered back through it: sequential
+// writes, gathers out of a region the L2 holds.  (A first version with global atomics per left -- histogram and cursor
+// bumps -- spent 5.4 ms of an 8.2 ms pass at 100M lefts on 40 G atomics/s: profiles/r2/unsorted_lefts.txt.)
 #include <vector>
 
 #include "common.cuh"
@@ -19,19 +21,27 @@ namespace {
 
 struct BucketSeq {
     u64 left_begin, left_end;
-    u32 bucket_base;  // first bucket of this seqname in the global bucket array
-    u32 nb;           // buckets of this seqname
-    int shift;        // bucket = min(l.start >> shift, nb - 1)
+    u32 tile_begin;   // first tile of this seqname (tiles of BK_TILE lefts, never across seqnames)
+    u32 ntiles;
+    u32 hist_base;    // first entry of this seqname in the (digit-major) histogram: 256 * tile_begin
+    u32 nb;           // fine buckets of this seqname (<= 65536)
+    int shift;        // fine bucket f = min(l.start >> shift, nb - 1); coarse digit = f >> 8, fine digit = f & 255
 };
 
 constexpr int BK_TPB = 256;
-constexpr int BK_MAXSEQ = 1024;
+#ifndef BK_ITEMS
+#define BK_ITEMS 16  // lefts per thread of a level-A tile (4096-left tiles; 16384-left tiles measured slower: 9.8 vs 9.1 ms)
+#endif
+#ifndef BK_FINE_TPB
+#define BK_FINE_TPB 1024  // threads of a level-B CTA: fewer, larger CTAs keep the buckets being split inside the L2
+#endif
+constexpr int BK_TILE = BK_TPB * BK_ITEMS;
 
-__device__ __forceinline__ int bucket_seq_of(const BucketSeq *__restrict__ seqs, int nseq, u64 g) {
+__device__ __forceinline__ int seq_of_tile(const BucketSeq *__restrict__ seqs, int nseq, u32 t) {
     int lo = 0, hi = nseq;
     while (hi - lo > 1) {
         const int mid = (lo + hi) >> 1;
-        if (seqs[mid].left_begin <= g)
+        if (seqs[mid].tile_begin <= t)
             lo = mid;
         else
             hi = mid;
@@ -39,43 +49,111 @@ __device__ __forceinline__ int bucket_seq_of(const BucketSeq *__restrict__ seqs,
     return lo;
 }
 
-// counts[bucket]++, and (for free) the number of adjacent inversions: how unsorted the lefts really are
-__global__ void __launch_bounds__(BK_TPB) k_bucket_hist(const u32 *__restrict__ ls, const BucketSeq *__restrict__ seqs, int nseq, u64 first, u64 total,
-                                                        u32 *__restrict__ counts, u32 *__restrict__ inversions) {
-    const u64 g = first + (u64)blockIdx.x * BK_TPB + threadIdx.x;
-    bool inv = false;
-    if (g < total) {
-        const BucketSeq q = seqs[bucket_seq_of(seqs, nseq, g)];
-        const u32 x = ls[g];
-        const u32 b = min(x >> q.shift, q.nb - 1u);
-        atomicAdd(&counts[q.bucket_base + b], 1u);
-        inv = g + 1 < q.left_end && ls[g + 1] < x;
+// Level A, pass 1: per tile, how many lefts fall into each of the seqname's 256 coarse buckets (shared-memory atomics
+// only); and, for free, the number of adjacent inversions: how unsorted the lefts really are.
+__global__ void __launch_bounds__(BK_TPB) k_coarse_hist(const u32 *__restrict__ ls, const BucketSeq *__restrict__ seqs, int nseq,
+                                                        u32 *__restrict__ hist, u32 *__restrict__ inversions) {
+    __shared__ u32 h[256];
+    __shared__ u32 s_inv;
+    h[threadIdx.x] = 0;
+    if (threadIdx.x == 0) s_inv = 0;
+    __syncthreads();
+    const BucketSeq q = seqs[seq_of_tile(seqs, nseq, blockIdx.x)];
+    const u32 tis = blockIdx.x - q.tile_begin;
+    const u64 base = q.left_begin + (u64)tis * BK_TILE;
+    u32 inv = 0;
+#pragma unroll 8
+    for (int i = 0; i < BK_ITEMS; i++) {
+        const u64 g = base + (u64)i * BK_TPB + threadIdx.x;
+        if (g < q.left_end) {
+            const u32 x = ls[g];
+            atomicAdd(&h[min(x >> q.shift, q.nb - 1u) >> 8], 1u);
+            inv += (g + 1 < q.left_end && ls[g + 1] < x) ? 1u : 0u;
+        }
     }
-    const u32 m = __ballot_sync(GRB_FULL, inv);
-    if (lane_id() == 0 && m) atomicAdd(inversions, (u32)__popc(m));
+    inv = warp_sum(inv);
+    if (lane_id() == 0 && inv) atomicAdd(&s_inv, inv);
+    __syncthreads();
+    hist[q.hist_base + threadIdx.x * q.ntiles + tis] = h[threadIdx.x];
+    if (threadIdx.x == 0 && s_inv) atomicAdd(inversions, s_inv);
 }
 
-__global__ void __launch_bounds__(BK_TPB) k_bucket_scatter(const u32 *__restrict__ ls, const u32 *__restrict__ le, const BucketSeq *__restrict__ seqs,
-                                                           int nseq, u64 first, u64 total, u32 *__restrict__ cursor, u32 *__restrict__ ls_b,
-                                                           u32 *__restrict__ le_b, u32 *__restrict__ rank) {
-    const u64 g = first + (u64)blockIdx.x * BK_TPB + threadIdx.x;
-    if (g >= total) return;
-    const BucketSeq q = seqs[bucket_seq_of(seqs, nseq, g)];
-    const u32 x = ls[g];
-    const u32 b = min(x >> q.shift, q.nb - 1u);
-    const u64 p = first + atomicAdd(&cursor[q.bucket_base + b], 1u);  // cursor: exclusive scan of the counts, relative to `first`
-    ls_b[p] = x;
-    le_b[p] = le[g];
-    rank[p] = (u32)(g - first);
+// Level A, pass 2: the lefts of a tile go to their coarse buckets; offs = exclusive scan of hist (positions relative to
+// the batch's first left).  Order inside a bucket is whatever the shared-memory atomics give: it does not matter.
+__global__ void __launch_bounds__(BK_TPB) k_coarse_scatter(const u32 *__restrict__ ls, const u32 *__restrict__ le, const BucketSeq *__restrict__ seqs,
+                                                           int nseq, u64 first, const u32 *__restrict__ offs, u32 *__restrict__ ls_a,
+                                                           u32 *__restrict__ le_a, u32 *__restrict__ rank_a) {
+    __shared__ u32 cur[256];
+    const BucketSeq q = seqs[seq_of_tile(seqs, nseq, blockIdx.x)];
+    const u32 tis = blockIdx.x - q.tile_begin;
+    cur[threadIdx.x] = offs[q.hist_base + threadIdx.x * q.ntiles + tis];
+    __syncthreads();
+    const u64 base = q.left_begin + (u64)tis * BK_TILE;
+#pragma unroll 8
+    for (int i = 0; i < BK_ITEMS; i++) {
+        const u64 g = base + (u64)i * BK_TPB + threadIdx.x;
+        if (g < q.left_end) {
+            const u32 x = ls[g];
+            const u32 p = atomicAdd(&cur[min(x >> q.shift, q.nb - 1u) >> 8], 1u);
+            ls_a[p] = x;
+            le_a[p] = le[g];
+            rank_a[p] = (u32)(g - first);
+        }
+    }
 }
 
-// row i of the bucketed results goes back to the row its left came from
+// Level B: one CTA per coarse bucket (its lefts are contiguous after level A: a few thousand, L2-resident) splits it into
+// its 256 fine buckets -- count, scan, scatter, all in shared memory -- and records where every original row went.
+__global__ void __launch_bounds__(BK_FINE_TPB) k_fine_partition(const u32 *__restrict__ ls_a, const u32 *__restrict__ le_a, const u32 *__restrict__ rank_a,
+                                                           const BucketSeq *__restrict__ seqs, u64 first, const u32 *__restrict__ offs,
+                                                           u32 *__restrict__ ls_b, u32 *__restrict__ le_b, u32 *__restrict__ pos) {
+    __shared__ u32 cnt[256];
+    __shared__ u32 wsum[8];
+    const BucketSeq q = seqs[blockIdx.x >> 8];
+    const u32 nthr = blockDim.x;
+    const u32 c = blockIdx.x & 255u;
+    if (q.ntiles == 0) return;
+    const u32 b0 = offs[q.hist_base + c * q.ntiles], b1 = offs[q.hist_base + (c + 1) * q.ntiles];  // (the scan has one entry past the end)
+    if (b1 <= b0) return;
+    if (threadIdx.x < 256) cnt[threadIdx.x] = 0;
+    __syncthreads();
+    for (u32 i = b0 + threadIdx.x; i < b1; i += nthr) atomicAdd(&cnt[min(ls_a[i] >> q.shift, q.nb - 1u) & 255u], 1u);
+    __syncthreads();
+    // exclusive scan of the 256 counts (the first 8 warps)
+    u32 v = 0, incl = 0;
+    if (threadIdx.x < 256) {
+        v = cnt[threadIdx.x];
+        incl = v;
+#pragma unroll
+        for (int o = 1; o < 32; o <<= 1) {
+            const u32 t = __shfl_up_sync(GRB_FULL, incl, o);
+            if (lane_id() >= (u32)o) incl += t;
+        }
+        if (lane_id() == 31) wsum[threadIdx.x >> 5] = incl;
+    }
+    __syncthreads();
+    if (threadIdx.x < 256) {
+        u32 woff = 0;
+        for (u32 w = 0; w < (threadIdx.x >> 5); w++) woff += wsum[w];
+        cnt[threadIdx.x] = b0 + woff + incl - v;
+    }
+    __syncthreads();
+    for (u32 i = b0 + threadIdx.x; i < b1; i += nthr) {
+        const u32 x = ls_a[i];
+        const u32 p = atomicAdd(&cnt[min(x >> q.shift, q.nb - 1u) & 255u], 1u);
+        ls_b[first + p] = x;
+        le_b[first + p] = le_a[i];
+        pos[rank_a[i]] = p;
+    }
+}
+
+// row r of the results = row pos[r] of the bucketed results: sequential writes, gathers out of a region the L2 holds
 template <int K>
-__global__ void __launch_bounds__(BK_TPB) k_unbucket(const double *__restrict__ out_b, const u8 *__restrict__ val_b, const u32 *__restrict__ rank, u64 first,
+__global__ void __launch_bounds__(BK_TPB) k_unbucket(const double *__restrict__ out_b, const u8 *__restrict__ val_b, const u32 *__restrict__ pos, u64 first,
                                                      u64 total, int k, double *__restrict__ out, u8 *__restrict__ val) {
-    const u64 i = first + (u64)blockIdx.x * BK_TPB + threadIdx.x;
-    if (i >= total) return;
-    const u64 r = first + rank[i];
+    const u64 r = first + (u64)blockIdx.x * BK_TPB + threadIdx.x;
+    if (r >= total) return;
+    const u64 i = first + pos[r - first];
     if (K == 1) {
         out[r] = out_b[i];
         val[r] = val_b[i];
@@ -125,63 +203,73 @@ int grb_left_disorder(grb_ctx *ctx, const u32 *ls, u64 first, u64 total, int *pe
     return GRB_OK;
 }
 
-// Drop the lefts [left_offsets[0], left_offsets[nseq]) of a batch into coordinate buckets.  extent[s] = a coordinate at or
-// beyond which seqname s holds no right (lefts past it share the last bucket).  ls_b / le_b are indexed like ls / le
-// (absolute positions, so tiles stay aligned), and so is rank: rank[p] = original row (relative to the batch's first left) of the left now at p.  inversions_dev (may be NULL)
-// receives the number of adjacent inversions seen -- the caller's feedback on whether bucketing was needed at all.
+// Drop the lefts [left_offsets[0], left_offsets[nseq]) of a batch into coordinate buckets of ~64 lefts.  extent[s] = a
+// coordinate at or beyond which seqname s holds no right (lefts past it share the last bucket).  ls_b / le_b are indexed
+// like ls / le (absolute positions, so tiles stay aligned); pos[r] = where row r (relative to the batch's first left) went
+// (relative likewise).  inversions_dev (may be NULL) receives the number of adjacent inversions seen -- the caller's
+// feedback on whether bucketing was needed at all.
 int grb_bucket_lefts(grb_ctx *ctx, const u64 *left_offsets, const u64 *extent, int nseq, const u32 *ls, const u32 *le, u32 *ls_b, u32 *le_b,
-                     u32 *rank, u32 *inversions_dev) {
-    if (nseq > BK_MAXSEQ * 64) return grb_fail(ctx, GRB_ERR_UNSUPPORTED, "bucket: too many seqnames in one call");
+                     u32 *pos, u32 *inversions_dev) {
     const u64 first = left_offsets[0], total = left_offsets[nseq];
-    if (total - first >= 0xffffffffull) return grb_fail(ctx, GRB_ERR_UNSUPPORTED, "bucket: more than 2^32-1 lefts in one call");
+    const u64 n = total - first;
+    if (n >= 0xffffffffull) return grb_fail(ctx, GRB_ERR_UNSUPPORTED, "bucket: more than 2^32-1 lefts in one call");
+    if ((u64)nseq * 256 >= 0x7fffffffull) return grb_fail(ctx, GRB_ERR_UNSUPPORTED, "bucket: too many seqnames in one call");
     std::vector<BucketSeq> h((size_t)nseq);
-    u64 nbuckets = 0;
+    u64 tiles = 0;
     for (int s = 0; s < nseq; s++) {
         BucketSeq q;
         q.left_begin = left_offsets[s];
         q.left_end = left_offsets[s + 1];
         const u64 nl = q.left_end - q.left_begin;
         u64 want = nl / 64 + 1;  // ~64 lefts per bucket: a tile of 1024 bucketed lefts spans 1024 + 64 lefts' worth of coordinates
-        if (want > (1u << 22)) want = 1u << 22;
+        if (want > 65536) want = 65536;
         const u64 ext = extent[s] ? extent[s] : 1;
         int shift = 0;
         while (shift < 31 && (ext >> shift) + 1 > want) shift++;
         q.shift = shift;
         q.nb = (u32)((ext >> shift) + 1);
-        q.bucket_base = (u32)nbuckets;
-        nbuckets += q.nb;
+        q.tile_begin = (u32)tiles;
+        q.ntiles = (u32)((nl + BK_TILE - 1) / BK_TILE);
+        q.hist_base = (u32)(tiles * 256);
+        tiles += q.ntiles;
         h[s] = q;
     }
-    if (nbuckets >= 0x7fffffffull) return grb_fail(ctx, GRB_ERR_UNSUPPORTED, "bucket: too many buckets");
-    TempBuf d_seqs, counts, cursor, inv_tmp;
+    if (tiles * 256 >= 0x7fffffffull) return grb_fail(ctx, GRB_ERR_UNSUPPORTED, "bucket: too many lefts in one call");
+    if (tiles == 0) return GRB_OK;
+    const size_t nh = (size_t)tiles * 256;
+    TempBuf d_seqs, hist, offs, inv_tmp, ls_a, le_a, rank_a;
     GRB_TRY(d_seqs.alloc(ctx, sizeof(BucketSeq) * nseq));
-    GRB_TRY(counts.alloc(ctx, nbuckets * 4));
-    GRB_TRY(cursor.alloc(ctx, nbuckets * 4));
+    GRB_TRY(hist.alloc(ctx, nh * 4));
+    GRB_TRY(offs.alloc(ctx, (nh + 1) * 4));
+    GRB_TRY(ls_a.alloc(ctx, n * 4));
+    GRB_TRY(le_a.alloc(ctx, n * 4));
+    GRB_TRY(rank_a.alloc(ctx, n * 4));
     if (!inversions_dev) {
         GRB_TRY(inv_tmp.alloc(ctx, 4));
         inversions_dev = inv_tmp.as<u32>();
     }
     // (pageable source: the copy is staged before the call returns, so the vector may go out of scope)
     GRB_CUDA(ctx, cudaMemcpyAsync(d_seqs.p, h.data(), sizeof(BucketSeq) * nseq, cudaMemcpyHostToDevice, ctx->stream));
-    GRB_CUDA(ctx, cudaMemsetAsync(counts.p, 0, nbuckets * 4, ctx->stream));
     GRB_CUDA(ctx, cudaMemsetAsync(inversions_dev, 0, 4, ctx->stream));
-    const unsigned blocks = (unsigned)((total - first + BK_TPB - 1) / BK_TPB);
-    if (blocks == 0) return GRB_OK;
-    k_bucket_hist<<<blocks, BK_TPB, 0, ctx->stream>>>(ls, d_seqs.as<BucketSeq>(), nseq, first, total, counts.as<u32>(), inversions_dev);
+    k_coarse_hist<<<(unsigned)tiles, BK_TPB, 0, ctx->stream>>>(ls, d_seqs.as<BucketSeq>(), nseq, hist.as<u32>(), inversions_dev);
     GRB_LAUNCHED(ctx);
-    GRB_TRY(grb_scan_u32_to_u32(ctx, counts.as<u32>(), cursor.as<u32>(), nbuckets, false));
-    k_bucket_scatter<<<blocks, BK_TPB, 0, ctx->stream>>>(ls, le, d_seqs.as<BucketSeq>(), nseq, first, total, cursor.as<u32>(), ls_b, le_b, rank);
+    GRB_TRY(grb_scan_u32_to_u32(ctx, hist.as<u32>(), offs.as<u32>(), nh, true));
+    k_coarse_scatter<<<(unsigned)tiles, BK_TPB, 0, ctx->stream>>>(ls, le, d_seqs.as<BucketSeq>(), nseq, first, offs.as<u32>(), ls_a.as<u32>(),
+                                                                 le_a.as<u32>(), rank_a.as<u32>());
+    GRB_LAUNCHED(ctx);
+    k_fine_partition<<<(unsigned)nseq * 256u, BK_FINE_TPB, 0, ctx->stream>>>(ls_a.as<u32>(), le_a.as<u32>(), rank_a.as<u32>(), d_seqs.as<BucketSeq>(), first,
+                                                                       offs.as<u32>(), ls_b, le_b, pos);
     GRB_LAUNCHED(ctx);
     return GRB_OK;
 }
 
-int grb_unbucket_results(grb_ctx *ctx, u64 first, u64 total, int k, const double *out_b, const u8 *val_b, const u32 *rank, double *out, u8 *val) {
+int grb_unbucket_results(grb_ctx *ctx, u64 first, u64 total, int k, const double *out_b, const u8 *val_b, const u32 *pos, double *out, u8 *val) {
     const unsigned blocks = (unsigned)((total - first + BK_TPB - 1) / BK_TPB);
     if (blocks == 0) return GRB_OK;
     if (k == 1)
-        k_unbucket<1><<<blocks, BK_TPB, 0, ctx->stream>>>(out_b, val_b, rank, first, total, k, out, val);
+        k_unbucket<1><<<blocks, BK_TPB, 0, ctx->stream>>>(out_b, val_b, pos, first, total, k, out, val);
     else
-        k_unbucket<0><<<blocks, BK_TPB, 0, ctx->stream>>>(out_b, val_b, rank, first, total, k, out, val);
+        k_unbucket<0><<<blocks, BK_TPB, 0, ctx->stream>>>(out_b, val_b, pos, first, total, k, out, val);
     GRB_LAUNCHED(ctx);
     return GRB_OK;
 }

@@ -394,8 +394,8 @@ int grb_index_prepare_wm(grb_ctx *ctx, grb_index *ix);
 // bucket.cu: left ranges in any order -- coordinate buckets, results written back through `rank`
 int grb_left_disorder(grb_ctx *ctx, const u32 *ls, u64 first, u64 total, int *per_1024);
 int grb_bucket_lefts(grb_ctx *ctx, const u64 *left_offsets, const u64 *extent, int nseq, const u32 *ls, const u32 *le, u32 *ls_b, u32 *le_b,
-                     u32 *rank, u32 *inversions_dev);
-int grb_unbucket_results(grb_ctx *ctx, u64 first, u64 total, int k, const double *out_b, const u8 *val_b, const u32 *rank, double *out, u8 *val);
+                     u32 *pos, u32 *inversions_dev);
+int grb_unbucket_results(grb_ctx *ctx, u64 first, u64 total, int k, const double *out_b, const u8 *val_b, const u32 *pos, double *out, u8 *val);
 
 // sort.cu: stable LSD radix sort of (u64 key, u32 value) pairs; skips digits that do not vary and
 // the whole sort when the keys are already non-decreasing.  On return *keys_out / *vals_out point

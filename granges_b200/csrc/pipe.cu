@@ -283,12 +283,23 @@ __global__ void __launch_bounds__(PIPE_THREADS, 1) k_map_pipe(const SeqDev *__re
                 __syncwarp();
                 if (lane < 2) tma_load_1d_hint(lane ? S.le[sl] : S.ls[sl], (lane ? le : ls) + g_first, TILE * 4, &S.fullL[sl], pol);
             } else {
-                // ragged tile (seqname boundary, end of the arrays, unaligned pointers): plain copies
-                for (u32 i = lane; i < TILE; i += 32) {
-                    const u64 g = g_first + i;
-                    const bool ok = g >= lo_g && g < hi_g;
-                    S.ls[sl][i] = ok ? ls[g] : 0u;
-                    S.le[sl][i] = ok ? le[g] : 0u;
+                // ragged tile (seqname boundary, end of the arrays, unaligned pointers): plain copies, 16 loads of each
+                // array in flight per lane (one at a time costs a memory round trip per element: ~30 us per ragged tile)
+#pragma unroll 1
+                for (u32 i0 = 0; i0 < TILE; i0 += 32 * 16) {
+                    u32 xs[16], xe[16];
+#pragma unroll
+                    for (int r = 0; r < 16; r++) {
+                        const u64 g = g_first + i0 + r * 32 + lane;
+                        const bool ok = g >= lo_g && g < hi_g;
+                        xs[r] = ok ? ls[g] : 0u;
+                        xe[r] = ok ? le[g] : 0u;
+                    }
+#pragma unroll
+                    for (int r = 0; r < 16; r++) {
+                        S.ls[sl][i0 + r * 32 + lane] = xs[r];
+                        S.le[sl][i0 + r * 32 + lane] = xe[r];
+                    }
                 }
                 __syncwarp();
                 if (lane == 0) mbar_arrive(&S.fullL[sl]);

@@ -41,6 +41,14 @@ def unit_right_mask(rs, re, lo, hi):
     return (rs < hi) & (re > lo)
 
 
+def unit_origin(rs_unit, lo):
+    """Coordinate to subtract from a unit's lefts and (already filtered) rights: the smallest coordinate it holds, rounded
+    down to a multiple of 1024.  Overlap tests, counts, widths and sums only see coordinate differences, so results do
+    not change; the index sizes its coordinate bins for [0, max end), so a re-based unit keeps ~2 rights per bin."""
+    first = int(rs_unit.min()) if len(rs_unit) else int(lo)
+    return (min(first, int(lo)) // 1024) * 1024
+
+
 def concat_in_order(units, parts):
     """parts[i] = result rows of units[i] (any rank); returns them in the reference's row order."""
     order = sorted(range(len(units)), key=lambda i: (units[i]["seq"], units[i]["left_begin"]))
