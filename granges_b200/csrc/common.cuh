@@ -38,12 +38,18 @@ struct grb_ctx {
     int minmax_mode; // GRB_MINMAX_MODE: 0 = MIN / MAX sweep the members even without a median beside them (debug)
     int whole_chunks, whole_workers;  // GRB_WHOLE_CHUNKS / GRB_WHOLE_WORKERS (defaults 8 / 4)
     int left_order; // grb_left_order: how the order of the lefts is decided (grb_ctx_set_left_order)
-    u32 *stats_host; // mapped pinned words the kernels report to without any stream operation: [0] adjacent inversions seen by the
-    u32 *stats_dev;  // last bucket pass, [16 + b] tiles CTA b of the last pipelined launch could not stage; device alias
-    const void *hist_ls;  // AUTO on device buffers: the lefts of the previous call, and what it did with them
+    // Mapped pinned words the kernels report to without any stream operation (device alias: stats_dev).  Every report carries
+    // the generation number of the call that asked for it, written last, so the host never mistakes an older report for news:
+    //   [0] adjacent inversions seen by a bucket pass, [2] its generation;
+    //   [16 + b] tiles CTA b of a pipelined launch could not stage, [1] that launch's generation (written by CTA 0).
+    u32 *stats_host;
+    u32 *stats_dev;
+    const void *hist_ls;  // AUTO on device buffers: the lefts of the previous call ...
     u64 hist_first, hist_total;
     u32 hist_tiles;
-    int hist_bucketed;
+    int hist_bucketed;    // ... the verdict in force for them (kept until a newer report says otherwise) ...
+    u32 hist_gen0;        // ... and the first generation that belongs to them
+    u32 gen;              // generation counter of the reporting calls
     int sweep_mode; // 1 = staged rank sweep k_sweep3 for MIN / MAX / MEDIAN (default), 2 = k_sweep3 without staging, 0 = k_sweep2 only (debug)
     char err[512];
 };

@@ -30,17 +30,104 @@ constexpr u32 PAD = 16;  // sentinel entries after the last key (bulk copies rou
 struct BuildFlags {
     u32 invalid_range;
     u32 idx_too_big;
+    u32 max_end;    // largest end seen (k_make_keys)
+    u32 heavy_bin;  // the counting sort of the ends met a coordinate bin too crowded for its fix-up pass
 };
 
-__global__ void k_make_keys(const u32 *__restrict__ starts, const u32 *__restrict__ ends, const u32 *__restrict__ order,
-                            size_t n, u64 *__restrict__ keys, u32 *__restrict__ vals, BuildFlags *flags) {
-    size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+constexpr u32 BIN_FIX_MAX = 128;  // ends per coordinate bin the fix-up pass of the counting sort orders by insertion
+
+__global__ void __launch_bounds__(256) k_make_keys(const u32 *__restrict__ starts, const u32 *__restrict__ ends, const u32 *__restrict__ order,
+                                                   size_t n, u64 *__restrict__ keys, u32 *__restrict__ vals, BuildFlags *flags) {
+    // grid-stride: a few blocks per SM, so that the largest end costs one atomic per block (every warp of a start-sorted
+    // input raises the running maximum: per-warp atomics on the one word serialise -- 74 us of a 4.5M-range build)
+    __shared__ u32 s_max[8];
+    u32 mx = 0;
+    bool bad = false;
+    for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (size_t)gridDim.x * blockDim.x) {
+        const u32 src = order ? order[i] : (u32)i;
+        const u32 s = starts[src], e = ends[src];
+        bad |= e <= s || e > 0x7fffffffu;
+        keys[i] = ((u64)s << 32) | e;
+        vals[i] = src;
+        mx = max(mx, e);
+    }
+    mx = warp_max(mx);
+    if (__any_sync(GRB_FULL, bad) && lane_id() == 0) flags->invalid_range = 1;
+    if (lane_id() == 0) s_max[threadIdx.x >> 5] = mx;
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        for (int w = 1; w < 8; w++) mx = max(mx, s_max[w]);
+        atomicMax(&flags->max_end, mx);
+    }
+}
+
+// ---- end order by a counting sort over the coordinate bins of the lookup table ---------------------------------------
+// The table needs lut_b[b] = #ends < (b << shift) anyway: that IS the exclusive scan of the per-bin counts, and it also
+// tells every end where its bin starts in end order.  So: count per bin (atomics; for start-sorted input neighbouring
+// threads hit neighbouring bins, which the L2 coalesces), scan, scatter through per-bin cursors, then order every bin
+// -- ~2 ends on average -- by (end, position): exactly what a stable radix sort of (end, position) gives, in 4 light
+// passes instead of 4 x (histogram + scan + scatter).  A bin beyond BIN_FIX_MAX ends (thousands of identical ends) raises a
+// flag and the radix sort redoes the order.
+__global__ void k_bin_count(const u32 *__restrict__ ends, u32 n, int shift, u32 bmax, u32 *__restrict__ cnt) {
+    const u32 i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n) atomicAdd(&cnt[min(ends[i] >> shift, bmax)], 1u);
+}
+__global__ void k_bin_scatter(const u32 *__restrict__ ends, u32 n, int shift, u32 bmax, const u32 *__restrict__ lut, u32 *__restrict__ cur,
+                              u32 *__restrict__ ends_sorted, u32 *__restrict__ perm_e) {
+    const u32 i = blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= n) return;
-    u32 src = order ? order[i] : (u32)i;
-    u32 s = starts[src], e = ends[src];
-    if (e <= s || e > 0x7fffffffu) flags->invalid_range = 1;
-    keys[i] = ((u64)s << 32) | e;
-    vals[i] = src;
+    const u32 e = ends[i];
+    const u32 b = min(e >> shift, bmax);
+    const u32 p = lut[b] + atomicAdd(&cur[b], 1u);
+    ends_sorted[p] = e;
+    perm_e[p] = i;
+}
+__global__ void k_bin_fixup(const u32 *__restrict__ lut, u32 bmax, u32 *__restrict__ ends_sorted, u32 *__restrict__ perm_e, BuildFlags *flags) {
+    const u32 b = blockIdx.x * blockDim.x + threadIdx.x;
+    if (b > bmax) return;
+    const u32 lo = lut[b], hi = lut[b + 1];
+    const u32 c = hi - lo;
+    if (c < 2) return;
+    if (c > BIN_FIX_MAX) {
+        flags->heavy_bin = 1;
+        return;
+    }
+    if (c <= 4) {
+        // the usual bin: all loads at once, a 4-element sorting network on (end, position) keys, stores
+        u64 k[4];
+#pragma unroll
+        for (int i = 0; i < 4; i++) k[i] = (u32)i < c ? ((u64)ends_sorted[lo + i] << 32) | perm_e[lo + i] : ~0ull;
+#define GRB_CSWAP(a, b)               \
+    {                                 \
+        const u64 x = k[a], y = k[b]; \
+        k[a] = x < y ? x : y;         \
+        k[b] = x < y ? y : x;         \
+    }
+        GRB_CSWAP(0, 1) GRB_CSWAP(2, 3) GRB_CSWAP(0, 2) GRB_CSWAP(1, 3) GRB_CSWAP(1, 2)
+#undef GRB_CSWAP
+#pragma unroll
+        for (int i = 0; i < 4; i++)
+            if ((u32)i < c) {
+                ends_sorted[lo + i] = (u32)(k[i] >> 32);
+                perm_e[lo + i] = (u32)k[i];
+            }
+        return;
+    }
+    for (u32 i = lo + 1; i < hi; i++) {  // insertion sort by (end, position)
+        const u32 e = ends_sorted[i], q = perm_e[i];
+        u32 j = i;
+        while (j > lo && (ends_sorted[j - 1] > e || (ends_sorted[j - 1] == e && perm_e[j - 1] > q))) {
+            ends_sorted[j] = ends_sorted[j - 1];
+            perm_e[j] = perm_e[j - 1];
+            j--;
+        }
+        ends_sorted[j] = e;
+        perm_e[j] = q;
+    }
+}
+__global__ void k_fill_u32(u32 *__restrict__ p, u32 n, u32 v) {
+    const u32 i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n) p[i] = v;
 }
 
 __global__ void k_idx_keys(const u64 *__restrict__ data_idx, size_t n, u64 *__restrict__ keys, u32 *__restrict__ vals,
@@ -725,8 +812,9 @@ int grb_index_build(grb_ctx *ctx, const uint32_t *starts, const uint32_t *ends, 
             }
         }
         if (n) {
-            k_make_keys<<<blocks_for(n, 256), 256, 0, ctx->stream>>>(d_starts.as<u32>(), d_ends.as<u32>(), order, n, k0.as<u64>(),
-                                                                    v0.as<u32>(), fl.as<BuildFlags>());
+            const unsigned mk_blocks = blocks_for(n, 256) < (unsigned)ctx->sm_count * 8u ? blocks_for(n, 256) : (unsigned)ctx->sm_count * 8u;
+            k_make_keys<<<mk_blocks, 256, 0, ctx->stream>>>(d_starts.as<u32>(), d_ends.as<u32>(), order, n, k0.as<u64>(), v0.as<u32>(),
+                                                           fl.as<BuildFlags>());
             GRB_LAUNCHED_BREAK(ctx, rc)
         }
         if ((rc = grb_sort_pairs(ctx, k0.as<u64>(), v0.as<u32>(), k1.as<u64>(), v1.as<u32>(), n, &ks, &vs, nullptr))) break;
@@ -746,36 +834,48 @@ int grb_index_build(grb_ctx *ctx, const uint32_t *starts, const uint32_t *ends, 
             rc = grb_fail(ctx, GRB_ERR_UNSUPPORTED, "index_build: data index >= 2^32-1");
             break;
         }
-        // the other ping-pong pair is free now: scratch of the end-order sort
-        u64 *k2 = (ks == k0.as<u64>()) ? k1.as<u64>() : k0.as<u64>();
-        u32 *v2 = (vs == v0.as<u32>()) ? v1.as<u32>() : v0.as<u32>();
         k_unpack_start_order<<<blocks_for(n + PAD, 256), 256, 0, ctx->stream>>>(ks, vs, d_idx.as<u64>(), n, ix->starts, ix->ends,
                                                                                ix->didx);
         GRB_LAUNCHED_BREAK(ctx, rc)
-        // end order: a stable argsort of the ends as u32 keys, whose last pass lands in ends_sorted / perm_e
-        if ((rc = grb_argsort_u32(ctx, ix->ends, ix->ends_sorted, ix->perm_e, (u32 *)k2, v2, n))) break;
-        k_pad_keys<<<1, PAD, 0, ctx->stream>>>(ix->ends_sorted + n);
-        GRB_LAUNCHED_BREAK(ctx, rc)
         {
-            // coordinate bins of ~2-4 rights each (so one round of four compares usually ends a search);
-            // the largest end bounds every key
-            u32 maxend = 0;
-            if (n) cudaMemcpyAsync(&maxend, ix->ends_sorted + (n - 1), 4, cudaMemcpyDeviceToHost, ctx->stream);
-            cudaStreamSynchronize(ctx->stream);
+            // coordinate bins of ~2 rights each (so one round of compares usually ends a search); the largest end bounds every key
+            const u32 maxend = hf.max_end;
             int shift = 0;
             const char *ld = getenv("GRB_LUT_DIV");  // tuning knob: average rights per bin (default 2)
             const u64 lut_div = ld && atoi(ld) > 0 ? (u64)atoi(ld) : 2;
             while (shift < 31 && ((u64)maxend >> shift) > (u64)n / lut_div + 1) shift++;
             ix->lut_shift = shift;
             ix->lut_bmax = (maxend >> shift) + 1;
-            size_t entries = (size_t)ix->lut_bmax + 1 + PAD;
+            const u32 bmax = ix->lut_bmax;
+            size_t entries = (size_t)bmax + 1 + PAD;
             if ((rc = dev_alloc(ctx, (void **)&ix->lut_a, entries * 4))) break;
             if ((rc = dev_alloc(ctx, (void **)&ix->lut_b, entries * 4))) break;
             if ((rc = dev_alloc(ctx, (void **)&ix->lut16_a, entries * 2))) break;
             if ((rc = dev_alloc(ctx, (void **)&ix->lut16_b, entries * 2))) break;
-            k_build_lut<<<blocks_for(n + 1, 256), 256, 0, ctx->stream>>>(ix->starts, (u32)n, shift, ix->lut_bmax, ix->lut_a, ix->lut16_a);
+            k_build_lut<<<blocks_for(n + 1, 256), 256, 0, ctx->stream>>>(ix->starts, (u32)n, shift, bmax, ix->lut_a, ix->lut16_a);
             GRB_LAUNCHED_BREAK(ctx, rc)
-            k_build_lut<<<blocks_for(n + 1, 256), 256, 0, ctx->stream>>>(ix->ends_sorted, (u32)n, shift, ix->lut_bmax, ix->lut_b, ix->lut16_b);
+            // end order + the ends' table in one go: counting sort over the bins (see k_bin_count)
+            TempBuf cnt;
+            if ((rc = cnt.alloc(ctx, ((size_t)bmax + 1) * 4))) break;
+            cudaMemsetAsync(cnt.p, 0, ((size_t)bmax + 1) * 4, ctx->stream);
+            if (n) {
+                k_bin_count<<<blocks_for(n, 256), 256, 0, ctx->stream>>>(ix->ends, (u32)n, shift, bmax, cnt.as<u32>());
+                GRB_LAUNCHED_BREAK(ctx, rc)
+            }
+            if ((rc = grb_scan_u32_to_u32(ctx, cnt.as<u32>(), ix->lut_b, (size_t)bmax + 1, true))) break;  // lut_b[bmax + 1] = n
+            k_fill_u32<<<1, PAD, 0, ctx->stream>>>(ix->lut_b + bmax + 2, PAD - 1, (u32)n);
+            GRB_LAUNCHED_BREAK(ctx, rc)
+            k_narrow_u16<<<blocks_for(entries, 256), 256, 0, ctx->stream>>>(ix->lut_b, entries, ix->lut16_b);
+            GRB_LAUNCHED_BREAK(ctx, rc)
+            if (n) {
+                cudaMemsetAsync(cnt.p, 0, ((size_t)bmax + 1) * 4, ctx->stream);
+                k_bin_scatter<<<blocks_for(n, 256), 256, 0, ctx->stream>>>(ix->ends, (u32)n, shift, bmax, ix->lut_b, cnt.as<u32>(), ix->ends_sorted,
+                                                                          ix->perm_e);
+                GRB_LAUNCHED_BREAK(ctx, rc)
+                k_bin_fixup<<<blocks_for((size_t)bmax + 1, 256), 256, 0, ctx->stream>>>(ix->lut_b, bmax, ix->ends_sorted, ix->perm_e, fl.as<BuildFlags>());
+                GRB_LAUNCHED_BREAK(ctx, rc)
+            }
+            k_pad_keys<<<1, PAD, 0, ctx->stream>>>(ix->ends_sorted + n);
             GRB_LAUNCHED_BREAK(ctx, rc)
         }
         if (n) {
@@ -783,10 +883,23 @@ int grb_index_build(grb_ctx *ctx, const uint32_t *starts, const uint32_t *ends, 
             k_block_max_end<<<blocks_for(nbw * 32, 256), 256, 0, ctx->stream>>>(ix->ends, n, ix->bme);
             GRB_LAUNCHED_BREAK(ctx, rc)
         }
+        cudaMemcpyAsync(&hf, fl.p, sizeof(hf), cudaMemcpyDeviceToHost, ctx->stream);
         cudaError_t e = cudaStreamSynchronize(ctx->stream);
         if (e != cudaSuccess) {
             rc = grb_fail(ctx, GRB_ERR_CUDA, "index_build: %s", cudaGetErrorString(e));
             break;
+        }
+        if (hf.heavy_bin) {
+            // a coordinate bin with hundreds of ends (e.g. thousands of rights ending on one base): the stable radix sort
+            // gives the same (end, position) order
+            u64 *k2 = (ks == k0.as<u64>()) ? k1.as<u64>() : k0.as<u64>();
+            u32 *v2 = (vs == v0.as<u32>()) ? v1.as<u32>() : v0.as<u32>();
+            if ((rc = grb_argsort_u32(ctx, ix->ends, ix->ends_sorted, ix->perm_e, (u32 *)k2, v2, n))) break;
+            e = cudaStreamSynchronize(ctx->stream);
+            if (e != cudaSuccess) {
+                rc = grb_fail(ctx, GRB_ERR_CUDA, "index_build: %s", cudaGetErrorString(e));
+                break;
+            }
         }
     } while (0);
     if (rc != GRB_OK) {

@@ -166,6 +166,7 @@ struct PipeOps {
     int need_pfx;       // PIPE_UBLB / PIPE_MULTI: some column needs the score prefixes
     u32 *valid_bits;    // single-reduction kernels: validity as bits (bit g of word g / 32) instead of bytes
     u32 *stats;         // see TileOut::stats
+    u32 stats_gen;
 };
 
 // #(keys < x) among the 8 keys of the two aligned quads at q
@@ -376,7 +377,13 @@ __global__ void __launch_bounds__(PIPE_THREADS, 1) k_map_pipe(const SeqDev *__re
             __syncwarp();
         }
         // feedback for the caller's order detection: a plain store to a mapped host word, nothing on the stream
-        if (lane == 0 && mops.stats != nullptr && blockIdx.x < 1000) mops.stats[16 + blockIdx.x] = unstaged;
+        if (lane == 0 && mops.stats != nullptr && blockIdx.x < 1000) {
+            mops.stats[16 + blockIdx.x] = unstaged;
+            if (blockIdx.x == 0) {
+                __threadfence_system();
+                mops.stats[1] = mops.stats_gen;
+            }
+        }
         return;
     }
 
@@ -800,6 +807,7 @@ int launch_var(grb_ctx *ctx, const Batch &b, int s0, int s1, const u32 *ls, cons
     mops.need_pfx = o.need_sum;
     mops.valid_bits = valid_bits;
     mops.stats = o.stats;
+    mops.stats_gen = o.stats_gen;
     k_map_pipe<FAST, VAR><<<grid, PIPE_THREADS, sizeof(Smem), ctx->stream>>>(b.seqs + s0, s1 - s0, t0, t1 - t0, ls, le, o.out, o.out_valid, flags,
                                                                           o.flags, mops);
     GRB_LAUNCHED(ctx);

@@ -999,6 +999,8 @@ int grb_map_joins_f64_batch_bits(grb_ctx *ctx, const grb_index *const *idx, cons
     return map_joins_impl(ctx, idx, left_offsets, nseq, ls, le, ops, k, out, nullptr, false, out_valid_bits);
 }
 
+__global__ void k_store_u32(u32 *p, u32 v) { *p = v; }
+
 // validity bytes -> bits: word w covers flattened entries [32 w, 32 w + 32) of the nl x k byte array
 __global__ void k_pack_bits(const u8 *__restrict__ bytes, u64 n, u32 *__restrict__ bits) {
     const u64 i = (u64)blockIdx.x * blockDim.x + threadIdx.x;
@@ -1023,22 +1025,30 @@ static int decide_bucketing(grb_ctx *ctx, const u32 *ls, u64 first, u64 total, u
         return GRB_OK;
     }
     if (!ctx->stats_host) return GRB_OK;
-    // device buffers: what did the previous call learn about this very buffer?
+    // Device buffers: what have earlier calls on this very buffer reported?  Reports arrive when their kernels finish, which may
+    // be several (asynchronous) calls later, so the verdict in force is kept until a report that belongs to this buffer -- its
+    // generation is not older than the buffer's first call -- says otherwise.
+    volatile u32 *st = ctx->stats_host;
     if (ctx->hist_ls == (const void *)ls && ctx->hist_first == first && ctx->hist_total == total) {
-        if (ctx->hist_bucketed) {
-            *bucket = (u64)ctx->stats_host[0] * 1024 / n > 100;  // adjacent inversions seen by the last bucket pass
-        } else {
+        const u32 gen_bucket = st[2], gen_plain = st[1];
+        const bool have_bucket = (u32)(gen_bucket - ctx->hist_gen0) < 0x40000000u, have_plain = (u32)(gen_plain - ctx->hist_gen0) < 0x40000000u;
+        if (have_bucket && (!have_plain || (u32)(gen_bucket - gen_plain) < 0x40000000u)) {
+            ctx->hist_bucketed = (u64)st[0] * 1024 / n > 100;  // adjacent inversions seen by the newest bucket pass
+        } else if (have_plain) {
             u64 unstaged = 0;
-            for (int b = 0; b < 1000; b++) unstaged += ctx->stats_host[16 + b];
-            *bucket = unstaged * 8 > ctx->hist_tiles;  // more than an eighth of the tiles fell off the staged path
+            for (int b = 0; b < 1000; b++) unstaged += st[16 + b];
+            ctx->hist_bucketed = unstaged * 8 > ctx->hist_tiles;  // more than an eighth of the tiles fell off the staged path
         }
+    } else {
+        ctx->hist_ls = ls;
+        ctx->hist_first = first;
+        ctx->hist_total = total;
+        ctx->hist_bucketed = 0;
+        ctx->hist_gen0 = ctx->gen + 1;
     }
-    ctx->hist_ls = ls;
-    ctx->hist_first = first;
-    ctx->hist_total = total;
     ctx->hist_tiles = ntiles;
-    ctx->hist_bucketed = *bucket;
-    memset(ctx->stats_host, 0, 1024 * 4);
+    ctx->gen++;
+    *bucket = ctx->hist_bucketed != 0;
     *report = true;
     return GRB_OK;
 }
@@ -1179,7 +1189,13 @@ static int map_joins_impl(grb_ctx *ctx, const grb_index *const *idx, const uint6
         // (the staged copies start at the batch's first left: shift the pointers back so that absolute positions index them)
         GRB_TRY(grb_bucket_lefts(ctx, left_offsets, extent.data(), nseq, dls.as<u32>() - first, dle.as<u32>() - first, ls_b.as<u32>(), le_b.as<u32>(),
                                  rank.as<u32>(), inv.as<u32>()));
-        if (report) GRB_CUDA(ctx, cudaMemcpyAsync(ctx->stats_host, inv.p, 4, cudaMemcpyDeviceToHost, ctx->stream));
+        if (report) {
+            // inversions, then -- in stream order, so it lands second -- the generation of this report
+            GRB_CUDA(ctx, cudaMemcpyAsync(ctx->stats_host, inv.p, 4, cudaMemcpyDeviceToHost, ctx->stream));
+            GRB_CUDA(ctx, cudaMemsetAsync(inv.p, 0, 4, ctx->stream));
+            k_store_u32<<<1, 1, 0, ctx->stream>>>(ctx->stats_dev + 2, ctx->gen);
+            GRB_LAUNCHED(ctx);
+        }
         GRB_TRY(map_joins_impl(ctx, idx, left_offsets, nseq, ls_b.as<u32>(), le_b.as<u32>(), ops, k, out_b.as<double>(), val_b.as<u8>(), false, nullptr,
                                true));
         GRB_TRY(dout.stage(ctx, out + first * (u64)k, n * (u64)k * 8));
@@ -1217,6 +1233,7 @@ static int map_joins_impl(grb_ctx *ctx, const grb_index *const *idx, const uint6
     memset(&o, 0, sizeof(o));
     o.flags = ctx->dev_flags;
     o.stats = report ? ctx->stats_dev : nullptr;
+    o.stats_gen = ctx->gen;
     o.out = dout.as<double>();
     o.k = k;
     o.need_sum = need_sum;

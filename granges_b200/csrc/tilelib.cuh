@@ -18,6 +18,7 @@ struct TileOut {
     int ops[GRB_MAX_OPS];
     u32 *flags;  // context flag word (bit 0: invalid left range seen)
     u32 *stats;  // pipelined kernel: stats[16 + blockIdx.x] = tiles this CTA could not stage (mapped host words; may be NULL)
+    u32 stats_gen;  // ... and stats[1] = this number, by CTA 0, after its count
 };
 
 // ---- host side: one batch = the seqnames of one call, concatenated in GenomeMap order -------------------

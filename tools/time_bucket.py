@@ -25,3 +25,11 @@ for rep in range(3):
     ctx.map_joins_batch(idxs, off, ls, le, ["mean"], out=out, out_valid=ov)
     ctx.sync(); torch.cuda.synchronize()
     print("unsorted", rep, "ms", round((time.perf_counter() - t0) * 1e3, 3), flush=True)
+ctx.set_left_order("auto")
+call = ctx.prepare_map(idxs, off, ls, le, ["mean"], out, ov)
+for rep in range(4):
+    n0 = ctx.launch_count
+    torch.cuda.synchronize(); t0 = time.perf_counter()
+    call()
+    ctx.sync(); torch.cuda.synchronize()
+    print("auto (prepared)", rep, "ms", round((time.perf_counter() - t0) * 1e3, 3), "launches", ctx.launch_count - n0, flush=True)
