@@ -1,14 +1,16 @@
+# Round-2 evidence run (one B200): everything below lands in gpurun_out/ and is summarised into profiles/r2/ afterwards.
+# Every ncu capture comes after the same command has exited 0 without ncu; numbers printed under ncu are never bench values.
 set -x
-python -m pytest tests -m gpu -x -q > gpurun_out/pytest_r1_final.log 2>&1; echo "pytest rc=$?" >> gpurun_out/pytest_r1_final.log; tail -3 gpurun_out/pytest_r1_final.log
-python bench.py --impl reference --steps 3 --warmup 1 > gpurun_out/bench_r1s3_ref.json 2> gpurun_out/bench_r1s3_ref.err; tail -c 600 gpurun_out/bench_r1s3_ref.json
-python bench.py > gpurun_out/bench_r1s3_n1.json 2> gpurun_out/bench_r1s3_n1.err; python tools/benchline.py n1 < gpurun_out/bench_r1s3_n1.json
-python tools/bench_configs.py > gpurun_out/configs_r1s3.jsonl 2> gpurun_out/configs_r1s3.err; cat gpurun_out/configs_r1s3.jsonl; tail -3 gpurun_out/configs_r1s3.err
-python tools/bench_configs.py c3ops > gpurun_out/c3ops_r1s3.jsonl 2>/dev/null; cat gpurun_out/c3ops_r1s3.jsonl
-python tools/bench_configs.py c4ops > gpurun_out/c4ops_r1s3.jsonl 2>/dev/null; cat gpurun_out/c4ops_r1s3.jsonl
-ncu --metrics gpu__time_duration.sum --clock-control none -c 2000 --csv --log-file gpurun_out/launches_r1s3.csv python bench.py --steps 3 --warmup 3 --no-cpu --no-e2e > gpurun_out/ncu_l_r1s3.log 2>&1
-ncu --metrics gpu__time_duration.sum --clock-control none -k regex:"k_tile|k_sweep|k_median|k_minmax|k_overlap|k_weighted|k_map_pipe" -c 400 --csv --log-file gpurun_out/launches_c3_r1s3.csv python tools/bench_configs.py c3ops > gpurun_out/ncu_lc3_r1s3.log 2>&1
-ncu --set full --clock-control none --import-source on -k regex:k_map_pipe -c 1 -o gpurun_out/prof_pipe_r1s3 -f python bench.py --steps 1 --warmup 3 --no-cpu --no-e2e > gpurun_out/ncu_p_r1s3.log 2>&1
-ncu --set full --clock-control none --import-source on -k regex:k_sweep3 -c 1 -o gpurun_out/prof_sweep3_r1s3 -f python tools/bench_configs.py c3 > gpurun_out/ncu_s3_r1s3.log 2>&1
-bash tools/bench_cli.sh 20000000 > gpurun_out/cli_r1s3.txt 2>&1; tail -25 gpurun_out/cli_r1s3.txt
-python tools/e2e_phases.py > gpurun_out/e2e_phases_r1s3.txt 2>&1
+mkdir -p gpurun_out
+python -m pytest tests -m gpu -x -q > gpurun_out/pytest_r2.log 2>&1; echo "pytest rc=$?" >> gpurun_out/pytest_r2.log; tail -3 gpurun_out/pytest_r2.log
+python bench.py --impl reference --steps 3 --warmup 1 > gpurun_out/bench_r2_ref.json 2> gpurun_out/bench_r2_ref.err; tail -c 400 gpurun_out/bench_r2_ref.json
+python bench.py --steps 20 --warmup 5 > gpurun_out/bench_r2_n1.json 2> gpurun_out/bench_r2_n1.err; tail -c 300 gpurun_out/bench_r2_n1.json
+# launch list of the timed map passes and the index builds: our kernels only (-k regex:k_), so the list is not cut off inside torch's generator
+ncu --metrics gpu__time_duration.sum --clock-control none -k regex:k_ --csv --log-file gpurun_out/launches_r2.csv python bench.py --steps 3 --warmup 3 --no-cpu --no-e2e --no-configs > gpurun_out/ncu_l_r2.log 2>&1
+# full captures: the headline kernel, and the None / wide variants (bench variants leg launches them after the headline passes)
+ncu --set full --clock-control none --import-source on -k regex:k_map_pipe -s 3 -c 1 -o gpurun_out/prof_pipe_r2 -f python bench.py --steps 1 --warmup 3 --no-cpu --no-e2e --no-configs > gpurun_out/ncu_p_r2.log 2>&1
+ncu --metrics gpu__time_duration.sum,dram__bytes_read.sum,dram__bytes_write.sum,smsp__inst_executed.sum --clock-control none -k regex:"k_map_pipe|k_coarse|k_fine|k_unbucket" -s 8 -c 24 --csv --log-file gpurun_out/variants_kernels_r2.csv python bench.py --steps 2 --warmup 1 --no-cpu --no-e2e > gpurun_out/ncu_v_r2.log 2>&1
+ncu --metrics gpu__time_duration.sum --clock-control none -k regex:k_ --csv --log-file gpurun_out/build_launches_r2.csv python tools/time_build.py 100000000 1 > gpurun_out/ncu_b_r2.log 2>&1
+python tools/time_build.py > gpurun_out/build_times_r2.txt 2>&1; tail -6 gpurun_out/build_times_r2.txt
+python tools/time_bucket.py > gpurun_out/unsorted_times_r2.txt 2>&1; tail -8 gpurun_out/unsorted_times_r2.txt
 ls -la gpurun_out/*.ncu-rep | tail -3
