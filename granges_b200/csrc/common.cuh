@@ -50,6 +50,7 @@ struct grb_ctx {
     int hist_bucketed;    // ... the verdict in force for them (kept until a newer report says otherwise) ...
     u32 hist_gen0;        // ... and the first generation that belongs to them
     u32 gen;              // generation counter of the reporting calls
+    int wave_ratio; // GRB_WAVE_RATIO: medians of a run of lefts come from per-run wavelet trees when lefts * ratio >= slice rights (default 8, 0 = never)
     int sweep_mode; // 1 = staged rank sweep k_sweep3 for MIN / MAX / MEDIAN (default), 2 = k_sweep3 without staging, 0 = k_sweep2 only (debug)
     char err[512];
 };
@@ -270,7 +271,7 @@ struct SeqDev {
     const i128 *base_a, *base_b;
     const u32 *lut_a, *lut_b;
     const u16 *lut16_a, *lut16_b;
-    const u32 *rank_a, *fb;
+    const u32 *rank_a, *fb, *perm_e;
     const double *score_sorted;
     const u32 *stab_min, *sp_min;
     const int *stab_max, *sp_max;

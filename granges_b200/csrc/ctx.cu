@@ -226,6 +226,8 @@ int grb_ctx_create(int device, grb_ctx **out) {
     ctx->sweep_mode = 1;
     const char *sm = getenv("GRB_SWEEP_MODE");
     if (sm) ctx->sweep_mode = atoi(sm);
+    ctx->wave_ratio = 8;
+    if (const char *wr = getenv("GRB_WAVE_RATIO")) ctx->wave_ratio = atoi(wr);
     // the remaining tuning knobs are read once, here, not on every call
     const char *up = getenv("GRB_UBLB_PIPE");
     ctx->ublb_pipe = up ? (atoi(up) != 0) : -1;

@@ -782,7 +782,7 @@ int grb_index_build(grb_ctx *ctx, const uint32_t *starts, const uint32_t *ends, 
         if ((rc = dev_alloc(ctx, (void **)&ix->ends, (n + PAD) * 4))) break;
         if ((rc = dev_alloc(ctx, (void **)&ix->ends_sorted, (n + PAD) * 4))) break;
         if ((rc = dev_alloc(ctx, (void **)&ix->didx, n * 4))) break;
-        if ((rc = dev_alloc(ctx, (void **)&ix->perm_e, n * 4))) break;
+        if ((rc = dev_alloc(ctx, (void **)&ix->perm_e, (n + PAD) * 4))) break;  // padded: k_sweep3 bulk-copies 16-byte multiples
         if ((rc = dev_alloc(ctx, (void **)&ix->bme, (((n + 63) >> GRB_BME_SHIFT) + PAD) * 4))) break;
         InBuf d_starts, d_ends, d_idx;
         if ((rc = d_starts.stage(ctx, starts, n * 4))) break;

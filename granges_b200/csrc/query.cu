@@ -357,6 +357,7 @@ struct SweepOut {
     int want_median, want_bp, want_wm;  // want_wm implies want_bp (the overlap widths are needed)
     u32 *heavy_list;
     u32 *heavy_count;
+    int wave_ratio;  // k_sweep3: a run of lefts answers its medians from per-run wavelet trees when lefts * wave_ratio >= rights of its slice (0: never)
 };
 
 __device__ __forceinline__ bool score_valid(const SeqDev *sd, u32 j) {
@@ -662,6 +663,7 @@ int make_batch(grb_ctx *ctx, const grb_index *const *idx, const u64 *left_offset
             d.lut16_a = ix->lut16_a;
             d.lut16_b = ix->lut16_b;
             d.rank_a = ix->rank_a;
+            d.perm_e = ix->perm_e;
             d.score_sorted = ix->score_sorted;
             d.fb = ix->fb;
             d.stab_min = ix->stab_min;
@@ -1288,6 +1290,7 @@ static int map_joins_impl(grb_ctx *ctx, const grb_index *const *idx, const uint6
             so.want_median = want_median;
             so.want_bp = want_bp;
             so.want_wm = want_wm;
+            so.wave_ratio = ctx->wave_ratio;
             if (want_median) {
                 if (b.total >= 0xffffffffull) return grb_fail(ctx, GRB_ERR_UNSUPPORTED, "map_joins: median over more than 2^32-1 lefts per call");
                 GRB_TRY(heavy.alloc(ctx, (b.total + 1) * 4));

@@ -18,14 +18,54 @@ constexpr u32 SW3_WCAP = 4096;      // rights per staged slice
 constexpr u32 SW3_KBUF = 4096;      // rank slots per CTA for the medians: 32 groups x 128, 16 x 256 or 8 x 512
 constexpr u32 SW3_MIN_RUN = 32;     // runs shorter than this are not halved any further
 
+// ---- wavelet runs: the median as an order statistic of a prefix difference -------------------------------------
+// A run of lefts whose slice of rights S = start-order positions [wlo, whi) fits WV_CAP builds, once for the run,
+//   * the dense local ranks of S (bitonic sort of the 32-bit score ranks in registers / shuffles / shared memory,
+//     then one binary search per right): keys 0 .. W-1, all different, sorted[] maps a key back to the score rank;
+//   * two levelwise wavelet trees over permutations of those keys: A = S in start order, B = S as
+//     C ++ end-order range [min lb, max lb) ++ R, C = the rights of S that end at or before every left start of the
+//     run, R = those that end after all of them (neither can separate two lefts of the run, so any order will do).
+// A left's members are then the first ub - wlo elements of A minus the first |C| + lb - min lb elements of B (the
+// counting identity of DESIGN.md section 3 inside the slice: everything below wlo ends before every left starts), and
+// its k-th smallest member is one descent: per level one rank query in each tree (the keys are dense, so node
+// boundaries are arithmetic), whatever the group's size.  MIN / MAX beside a median are the descents k = 0 and m - 1.
+// Cost per run: ~45 warp-instructions per right of the slice + ~8 per left and descent, against ~270 per left for the
+// member sweep at 43 members per left (growing like m log^2 m): taken when the run has at least W / wave_ratio lefts.
+constexpr u32 WV_CAP = 2048;           // rights per wavelet slice
+constexpr int WV_LMAX = 11;            // levels: keys below 2^11
+constexpr u32 WV_ROW = WV_CAP / 32 + 1;  // words per level (+1: a query may ask for the position one past the end)
+
+struct WaveSmem {
+    union {
+        alignas(16) u32 rank[WV_CAP];            // staged score ranks (None -> 0x80000000 | local position) ...
+        u32 bits[2][WV_LMAX][WV_ROW];            // ... then the level bitmaps of A and B (set bit = key bit is one)
+    };
+    union {
+        alignas(16) u32 ends[WV_CAP];            // staged ends ...
+        u16 seq1[2][WV_CAP];                     // ... then the second halves of the two ping-pong sequences
+    };
+    union {
+        alignas(16) u32 perm[WV_CAP + 8];        // staged perm_e[min lb .. max lb) ...
+        u16 cum[2][WV_LMAX][WV_ROW + 1];         // ... then zeros before each word of a level
+    };
+    alignas(16) u32 sorted[WV_CAP];              // the slice's ranks in ascending order: key -> score rank
+    u16 seq0[2][WV_CAP];                         // A and B at the current level (start: local rank of each position)
+    u32 cnt[2];                                  // cursors of the C / R fill
+};
+
 struct Sweep3Smem {
-    alignas(16) u32 ends[SW3_WCAP];
-    alignas(16) u32 rank[SW3_WCAP];
-    alignas(16) u32 bme[SW3_WCAP / 64 + 8];
-    u32 kbuf[SW3_KBUF];
+    union {
+        struct {
+            alignas(16) u32 ends[SW3_WCAP];
+            alignas(16) u32 rank[SW3_WCAP];
+            alignas(16) u32 bme[SW3_WCAP / 64 + 8];
+            u32 kbuf[SW3_KBUF];
+        };
+        WaveSmem w;
+    };
     alignas(8) u64 bar;
-    u32 red[3][SW3_TPB / 32];
-    u32 bcast[4];
+    u32 red[7][SW3_TPB / 32];
+    u32 bcast[8];
 };
 
 // Median of m <= G * R different 32-bit keys held in kbuf[0, m) by a group of G lanes: a bitonic sorting network
@@ -308,6 +348,256 @@ __device__ __forceinline__ void sweep3_run(const SeqDev *__restrict__ sd, u64 c_
     }
 }
 
+// ---- wavelet runs: device code ---------------------------------------------------------------------------------
+
+// Bitonic sort of P = 256 * nblk keys (nblk a power of two <= 8) in shared memory, ascending.  Warp w owns the block of 256
+// consecutive keys [256 w, 256 w + 256): element 8 * lane + r sits in register r of `lane`, so partner distances below 8
+// are register pairs, 8 .. 128 one shuffle per register, and only the distances >= 256 (6 of the 66 steps at P = 2048) go
+// through shared memory.
+__device__ __forceinline__ void wv_ce_regs(u32 (&v)[8], const int j, const u32 ebase, const u32 k) {
+#pragma unroll
+    for (int r = 0; r < 8; r++) {
+        const int q = r ^ j;
+        if (q > r) {
+            const bool asc = k < 8 ? ((u32)r & k) == 0 : (ebase & k) == 0;
+            const u32 a = v[r], b = v[q];
+            const u32 lo = min(a, b), hi = max(a, b);
+            v[r] = asc ? lo : hi;
+            v[q] = asc ? hi : lo;
+        }
+    }
+}
+__device__ __forceinline__ void wv_ce_lanes(u32 (&v)[8], const int j, const u32 ebase, const u32 k, const u32 lane) {
+    const int lm = j >> 3;
+    const bool keep_min = ((ebase & k) == 0) == ((lane & (u32)lm) == 0);
+#pragma unroll
+    for (int r = 0; r < 8; r++) {
+        const u32 w = __shfl_xor_sync(GRB_FULL, v[r], lm);
+        v[r] = keep_min ? min(v[r], w) : max(v[r], w);
+    }
+}
+__device__ __forceinline__ void wv_sort(u32 *keys, const u32 P) {
+    const u32 tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const u32 nblk = P >> 8;
+    const u32 ebase = warp * 256 + lane * 8;
+    u32 v[8];
+    if (warp < nblk) {
+        const uint4 a = *reinterpret_cast<const uint4 *>(keys + ebase), b = *reinterpret_cast<const uint4 *>(keys + ebase + 4);
+        v[0] = a.x, v[1] = a.y, v[2] = a.z, v[3] = a.w, v[4] = b.x, v[5] = b.y, v[6] = b.z, v[7] = b.w;
+#pragma unroll
+        for (int k = 2; k <= 256; k <<= 1) {
+#pragma unroll
+            for (int j = k >> 1; j >= 1; j >>= 1) {
+                if (j >= 8)
+                    wv_ce_lanes(v, j, ebase, (u32)k, lane);
+                else
+                    wv_ce_regs(v, j, ebase, (u32)k);
+            }
+        }
+        *reinterpret_cast<uint4 *>(keys + ebase) = make_uint4(v[0], v[1], v[2], v[3]);
+        *reinterpret_cast<uint4 *>(keys + ebase + 4) = make_uint4(v[4], v[5], v[6], v[7]);
+    }
+    for (u32 k = 512; k <= P; k <<= 1) {
+        for (u32 j = k >> 1; j >= 256; j >>= 1) {
+            __syncthreads();
+            for (u32 t = tid; t < (P >> 1); t += SW3_TPB) {
+                const u32 i = ((t & ~(j - 1)) << 1) | (t & (j - 1));
+                const u32 a = keys[i], b = keys[i | j];
+                const bool asc = (i & k) == 0;
+                if ((a > b) == asc) {
+                    keys[i] = b;
+                    keys[i | j] = a;
+                }
+            }
+        }
+        __syncthreads();
+        if (warp < nblk) {
+            const uint4 a = *reinterpret_cast<const uint4 *>(keys + ebase), b = *reinterpret_cast<const uint4 *>(keys + ebase + 4);
+            v[0] = a.x, v[1] = a.y, v[2] = a.z, v[3] = a.w, v[4] = b.x, v[5] = b.y, v[6] = b.z, v[7] = b.w;
+#pragma unroll
+            for (int j = 128; j >= 1; j >>= 1) {
+                if (j >= 8)
+                    wv_ce_lanes(v, j, ebase, k, lane);
+                else
+                    wv_ce_regs(v, j, ebase, k);
+            }
+            *reinterpret_cast<uint4 *>(keys + ebase) = make_uint4(v[0], v[1], v[2], v[3]);
+            *reinterpret_cast<uint4 *>(keys + ebase + 4) = make_uint4(v[4], v[5], v[6], v[7]);
+        }
+    }
+    __syncthreads();
+}
+
+// k-th smallest key (0-based) of: the first x elements of A minus the first y elements of B.
+__device__ __forceinline__ u32 wv_kth(const WaveSmem &w, const int L, const u32 x, const u32 y, u32 k) {
+    u32 p = 0, xa = x, xb = y;
+    for (int l = 0; l < L; l++) {
+        const int sh = L - 1 - l;
+        const u32 s = p << (sh + 1), z0 = p << sh;
+        const u32 pa = s + xa, pb = s + xb;
+        const u32 wa = w.bits[0][l][pa >> 5], wb = w.bits[1][l][pb >> 5];
+        const u32 za = (u32)w.cum[0][l][pa >> 5] + __popc(~wa & ((1u << (pa & 31)) - 1u)) - z0;
+        const u32 zb = (u32)w.cum[1][l][pb >> 5] + __popc(~wb & ((1u << (pb & 31)) - 1u)) - z0;
+        const u32 dz = za - zb;
+        const bool one = k >= dz;
+        k -= one ? dz : 0u;
+        p = 2 * p + (one ? 1u : 0u);
+        xa = one ? xa - za : za;
+        xb = one ? xb - zb : zb;
+    }
+    return p;
+}
+
+struct WaveRun {
+    u32 wlo, W;        // slice [wlo, wlo + W) in start order
+    u32 lbmin, lbmax;  // end-order range of the run
+    u32 qlo;           // first staged entry of perm_e (lbmin rounded down to 4)
+    u32 lsmin, lsmax;  // smallest / largest left start of the run
+};
+
+// The slice (rank, ends, perm) is in shared memory; builds the trees and answers the run's lefts.
+__device__ __forceinline__ void wave_run(const SeqDev *__restrict__ sd, WaveSmem &w, const WaveRun q, u64 c_lo, u64 c_hi,
+                                         const u32 *__restrict__ ubv, const u32 *__restrict__ lbv, const SweepOut &o, u64 ops_packed) {
+    const u32 tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const u32 W = q.W;
+    u32 P = 256;
+    while (P < W) P <<= 1;
+    int L = 1;
+    while ((1u << L) < W) L++;
+    const u32 nC = q.lbmin - q.wlo, nM = q.lbmax - q.lbmin;
+    // ---- keys: None scores sort last, each on its own
+    for (u32 i = tid; i < P; i += SW3_TPB) {
+        u32 r = 0xffffffffu;
+        if (i < W) {
+            r = w.rank[i];
+            if (r == GRB_RANK_NONE) r = 0x80000000u | i;
+            w.rank[i] = r;
+        }
+        w.sorted[i] = r;
+    }
+    if (tid < 2) w.cnt[tid] = 0;
+    __syncthreads();
+    wv_sort(w.sorted, P);
+    // ---- local rank of every position = where its key sits in the sorted slice: A's first sequence
+    for (u32 i = tid; i < W; i += SW3_TPB) {
+        const u32 r = w.rank[i];
+        u32 lo = 0;
+        for (u32 step = P >> 1; step; step >>= 1)
+            if (w.sorted[lo + step - 1] < r) lo += step;
+        w.seq0[0][i] = (u16)lo;
+    }
+    __syncthreads();
+    // ---- B's first sequence: C ++ end-order range ++ R
+    for (u32 i = tid; i < W; i += SW3_TPB) {
+        const u32 e = w.ends[i];
+        if (e <= q.lsmin) {
+            const u32 slot = atomicAdd(&w.cnt[0], 1u);
+            if (slot < nC) w.seq0[1][slot] = w.seq0[0][i];
+        } else if (e > q.lsmax) {
+            const u32 d = nC + nM + atomicAdd(&w.cnt[1], 1u);
+            if (d < W) w.seq0[1][d] = w.seq0[0][i];
+        }
+    }
+    for (u32 i = tid; i < nM; i += SW3_TPB) {
+        const u32 j = w.perm[i + (q.lbmin - q.qlo)] - q.wlo;
+        if (j < W && nC + i < W) w.seq0[1][nC + i] = w.seq0[0][j];
+    }
+    __syncthreads();
+    // ---- the levels
+    const u32 nch = (W + 31) >> 5;
+    for (int l = 0; l < L; l++) {
+        const int sh = L - 1 - l;
+        // bitmaps + zeros per word (the sequences ping-pong between seq0 and seq1)
+        for (u32 c = warp; c < 2 * nch; c += SW3_TPB / 32) {
+            const u32 t = c >= nch ? 1u : 0u, cc = c - t * nch;
+            const u16 *cur = (l & 1) ? w.seq1[t] : w.seq0[t];
+            const u32 i = cc * 32 + lane;
+            const bool one = i < W ? ((cur[i] >> sh) & 1u) != 0 : true;
+            const u32 word = __ballot_sync(GRB_FULL, one);
+            if (lane == 0) {
+                w.bits[t][l][cc] = word;
+                w.cum[t][l][cc] = (u16)(32 - __popc(word));
+            }
+        }
+        __syncthreads();
+        // exclusive scan of the zeros per word (entries 0 .. nch): warp 0 for A, warp 1 for B, three entries per lane
+        if (warp < 2) {
+            u16 *row = w.cum[warp][l];
+            u32 z[3], sum = 0;
+#pragma unroll
+            for (int e = 0; e < 3; e++) {
+                const u32 c = lane * 3 + e;
+                z[e] = c < nch ? row[c] : 0u;
+                sum += z[e];
+            }
+            u32 incl = sum;
+#pragma unroll
+            for (int d = 1; d < 32; d <<= 1) {
+                const u32 t = __shfl_up_sync(GRB_FULL, incl, d);
+                if (lane >= (u32)d) incl += t;
+            }
+            u32 run = incl - sum;
+#pragma unroll
+            for (int e = 0; e < 3; e++) {
+                const u32 c = lane * 3 + e;
+                if (c <= nch) row[c] = (u16)run;
+                run += z[e];
+            }
+        }
+        __syncthreads();
+        if (l == L - 1) break;
+        // stable partition inside every node: zeros to the front of the node, ones behind them
+        for (u32 c = warp; c < 2 * nch; c += SW3_TPB / 32) {
+            const u32 t = c >= nch ? 1u : 0u, cc = c - t * nch;
+            const u16 *cur = (l & 1) ? w.seq1[t] : w.seq0[t];
+            u16 *nxt = (l & 1) ? w.seq0[t] : w.seq1[t];
+            const u32 i = cc * 32 + lane;
+            if (i < W) {
+                const u32 key = cur[i];
+                const u32 word = w.bits[t][l][cc];
+                const u32 zb = (u32)w.cum[t][l][cc] + __popc(~word & ((1u << lane) - 1u));  // zeros before i on this level
+                const u32 node = key >> (sh + 1), s = node << (sh + 1), z0 = node << sh;
+                const u32 zin = zb - z0;                                                      // zeros of the node before i
+                const u32 dest = (word >> lane) & 1u ? s + (1u << sh) + (i - s - zin) : s + zin;
+                if (dest < W) nxt[dest] = (u16)key;  // (always, for the permutations valid lefts produce)
+            }
+        }
+        __syncthreads();
+    }
+    // ---- the lefts: one thread each
+    const bool has_nulls = sd->has_nulls != 0;
+    const double *__restrict__ sorted_scores = sd->score_sorted;
+    const int k = o.k;
+    bool want_min = false, want_max = false;
+    for (int c = 0; c < k; c++) {
+        const int op = (int)((ops_packed >> (4 * c)) & 15u);
+        want_min |= op == GRB_OP_MIN;
+        want_max |= op == GRB_OP_MAX;
+    }
+    for (u64 g = c_lo + tid; g < c_hi; g += SW3_TPB) {
+        const u32 u = ubv[g], l = lbv[g];
+        u32 m = 0;
+        if (u > l && u >= q.wlo && u - q.wlo <= W && l >= q.lbmin && l <= q.lbmax) m = has_nulls ? sd->vcnt_a[u] - sd->vcnt_b[l] : u - l;
+        const u32 x = u - q.wlo, y = nC + (l - q.lbmin);
+        double v_min = 0.0, v_max = 0.0, v_med = 0.0;
+        if (m) {
+            if (want_min) v_min = sorted_scores[w.sorted[wv_kth(w, L, x, y, 0u)]];
+            if (want_max) v_max = sorted_scores[w.sorted[wv_kth(w, L, x, y, m - 1u)]];
+            if (o.want_median) {
+                v_med = sorted_scores[w.sorted[wv_kth(w, L, x, y, (m - 1u) >> 1)]];
+                if (!(m & 1u)) v_med = (v_med + sorted_scores[w.sorted[wv_kth(w, L, x, y, m >> 1)]]) / 2.0;
+            }
+        }
+        for (int c = 0; c < k; c++) {
+            const int op = (int)((ops_packed >> (4 * c)) & 15u);
+            if (op == GRB_OP_MIN || op == GRB_OP_MAX || op == GRB_OP_MEDIAN) {
+                o.out[g * (u64)k + c] = op == GRB_OP_MIN ? v_min : op == GRB_OP_MAX ? v_max : v_med;
+                o.out_valid[g * (u64)k + c] = m ? 1 : 0;
+            }
+        }
+    }
+}
+
 // One CTA per tile of 1024 lefts (the tiling of k_tile).
 __global__ void __launch_bounds__(SW3_TPB, 4) k_sweep3(const SeqDev *__restrict__ seqs, const u32 *__restrict__ tile_begin, int nseq,
                                                     const u32 *__restrict__ ls, const u32 *__restrict__ ubv,
@@ -346,35 +636,60 @@ __global__ void __launch_bounds__(SW3_TPB, 4) k_sweep3(const SeqDev *__restrict_
     while (c_lo < g_hi) {
         const u64 c_hi = c_lo + run < g_hi ? c_lo + run : g_hi;
         // the slice of rights this run of lefts can touch, and its members per left
-        u32 pmin = 0xffffffffu, umax = 0, mem = 0;
+        u32 pmin = 0xffffffffu, umax = 0, mem = 0, lbmin = 0xffffffffu, lbmax = 0, lsmin = 0xffffffffu, lsmax = 0;
         for (u64 g = c_lo + tid; g < c_hi; g += SW3_TPB) {
-            const u32 u = ubv[g], p = ppv[g];
+            const u32 u = ubv[g], p = ppv[g], l = lbv[g], x = ls[g];
             pmin = min(pmin, p);
             umax = max(umax, max(u, p));  // p > u only for an invalid left (flagged by k_tile); stay inside the slice
-            mem += u - lbv[g];
+            mem += u - l;
+            lbmin = min(lbmin, l);
+            lbmax = max(lbmax, l);
+            lsmin = min(lsmin, x);
+            lsmax = max(lsmax, x);
         }
         pmin = warp_min(pmin);
         umax = warp_max(umax);
         mem = warp_sum(mem);
+        lbmin = warp_min(lbmin);
+        lbmax = warp_max(lbmax);
+        lsmin = warp_min(lsmin);
+        lsmax = warp_max(lsmax);
         if (lane == 0) {
             S.red[0][warp] = pmin;
             S.red[1][warp] = umax;
             S.red[2][warp] = mem;
+            S.red[3][warp] = lbmin;
+            S.red[4][warp] = lbmax;
+            S.red[5][warp] = lsmin;
+            S.red[6][warp] = lsmax;
         }
         __syncthreads();
         if (warp == 0) {
-            u32 a = lane < SW3_TPB / 32 ? S.red[0][lane] : 0xffffffffu;
-            u32 b = lane < SW3_TPB / 32 ? S.red[1][lane] : 0u;
-            u32 c = lane < SW3_TPB / 32 ? S.red[2][lane] : 0u;
+            const bool in = lane < SW3_TPB / 32;
+            u32 a = in ? S.red[0][lane] : 0xffffffffu;
+            u32 b = in ? S.red[1][lane] : 0u;
+            u32 c = in ? S.red[2][lane] : 0u;
+            u32 d = in ? S.red[3][lane] : 0xffffffffu;
+            u32 e = in ? S.red[4][lane] : 0u;
+            u32 f = in ? S.red[5][lane] : 0xffffffffu;
+            u32 h = in ? S.red[6][lane] : 0u;
             a = warp_min(a);
             b = warp_max(b);
             c = warp_sum(c);
+            d = warp_min(d);
+            e = warp_max(e);
+            f = warp_min(f);
+            h = warp_max(h);
             if (lane == 0) {
                 u32 wlo = a ? sd->fb[(a - 1) >> GRB_BME_SHIFT] : 0u;
                 wlo &= ~255u;  // bulk copies need 16-byte aligned sources, also for the block-max-end slice
                 S.bcast[0] = wlo;
                 S.bcast[1] = b;
                 S.bcast[2] = c;
+                S.bcast[3] = d;
+                S.bcast[4] = e;
+                S.bcast[5] = f;
+                S.bcast[6] = h;
             }
         }
         __syncthreads();
@@ -384,6 +699,33 @@ __global__ void __launch_bounds__(SW3_TPB, 4) k_sweep3(const SeqDev *__restrict_
         const u64 avg_den = c_hi - c_lo;
         const int gsel = (u64)S.bcast[2] > 150ull * avg_den ? 32 : (u64)S.bcast[2] > 64ull * avg_den ? 16 : 8;
         const u32 W = whi > wlo ? whi - wlo : 0u;
+        // a wavelet run: the slice fits WV_CAP, the run is long enough to pay for the trees, and the end-order range is
+        // consistent with the slice (it always is for valid lefts; an invalid one is flagged by k_tile and answered anyhow)
+        WaveRun wq;
+        wq.wlo = wlo, wq.W = W, wq.lbmin = S.bcast[3], wq.lbmax = S.bcast[4], wq.qlo = S.bcast[3] & ~3u, wq.lsmin = S.bcast[5], wq.lsmax = S.bcast[6];
+        const bool wave = stage_mode && o.wave_ratio > 0 && o.want_median && W && W <= WV_CAP && (c_hi - c_lo) * (u64)o.wave_ratio >= W &&
+                          wq.lbmin >= wlo && wq.lbmax >= wq.lbmin && wq.lbmax - wlo <= W;
+        if (wave) {
+            if (tid == 0) {
+                const u32 bytes = ((W + 3) & ~3u) * 4;
+                const u32 pbytes = ((wq.lbmax - wq.qlo + 3) & ~3u) * 4;
+                mbar_arrive_expect_tx(&S.bar, 2 * bytes + pbytes);
+                tma_load_1d(S.w.ends, sd->ends + wlo, bytes, &S.bar);
+                tma_load_1d(S.w.rank, sd->rank_a + wlo, bytes, &S.bar);
+                if (pbytes) tma_load_1d(S.w.perm, sd->perm_e + wq.qlo, pbytes, &S.bar);
+            }
+            mbar_wait(&S.bar, phase);
+            phase ^= 1;
+            wave_run(sd, S.w, wq, c_lo, c_hi, ubv, lbv, o, ops_packed);
+            __syncthreads();  // the slice and S.bcast are rewritten by the next run
+            c_lo = c_hi;
+            continue;
+        }
+        if (stage_mode && o.wave_ratio > 0 && o.want_median && W > WV_CAP && (c_hi - c_lo) * (u64)o.wave_ratio >= W && c_hi - c_lo > SW3_MIN_RUN) {
+            run = (c_hi - c_lo + 1) >> 1;  // dense lefts over a slice too wide for the trees: halve the run, not the method
+            __syncthreads();
+            continue;
+        }
         const bool fits = stage_mode && W <= SW3_WCAP;
         if (!fits && stage_mode && c_hi - c_lo > SW3_MIN_RUN) {
             run = (c_hi - c_lo + 1) >> 1;
