@@ -37,19 +37,19 @@ constexpr u32 WV_ROW = WV_CAP / 32 + 1;  // words per level (+1: a query may ask
 
 struct WaveSmem {
     union {
-        alignas(16) u32 rank[WV_CAP];            // staged score ranks (None -> 0x80000000 | local position) ...
-        u32 bits[2][WV_LMAX][WV_ROW];            // ... then the level bitmaps of A and B (set bit = key bit is one)
-    };
+        struct {
+            alignas(16) u32 rank[WV_CAP];        // staged score ranks (None -> 0x80000000 | local position)
+            alignas(16) u32 perm[WV_CAP + 8];    // staged perm_e[min lb .. max lb)
+        };
+        uint2 tree[2][WV_LMAX][WV_ROW];          // then, per tree / level / 32 positions: x = bitmap (set bit = key bit is one),
+    };                                           // y = zeros of the level before the word
     union {
         alignas(16) u32 ends[WV_CAP];            // staged ends ...
         u16 seq1[2][WV_CAP];                     // ... then the second halves of the two ping-pong sequences
     };
-    union {
-        alignas(16) u32 perm[WV_CAP + 8];        // staged perm_e[min lb .. max lb) ...
-        u16 cum[2][WV_LMAX][WV_ROW + 1];         // ... then zeros before each word of a level
-    };
     alignas(16) u32 sorted[WV_CAP];              // the slice's ranks in ascending order: key -> score rank
     u16 seq0[2][WV_CAP];                         // A and B at the current level (start: local rank of each position)
+    u32 wtot[2][SW3_TPB / 32];                   // zeros per warp of the level being built
     u32 cnt[2];                                  // cursors of the C / R fill
 };
 
@@ -428,24 +428,26 @@ __device__ __forceinline__ void wv_sort(u32 *keys, const u32 P) {
     __syncthreads();
 }
 
-// k-th smallest key (0-based) of: the first x elements of A minus the first y elements of B.
+// k-th smallest key (0-based) of: the first x elements of A minus the first y elements of B.  Per level: the node starts
+// at position s of both level sequences (dense keys), s / 2 zeros precede it, and one word + one count per tree give the
+// zeros among the node's first xa (xb) elements.
 __device__ __forceinline__ u32 wv_kth(const WaveSmem &w, const int L, const u32 x, const u32 y, u32 k) {
-    u32 p = 0, xa = x, xb = y;
-    for (int l = 0; l < L; l++) {
-        const int sh = L - 1 - l;
-        const u32 s = p << (sh + 1), z0 = p << sh;
+    u32 s = 0, xa = x, xb = y;
+    const uint2 *ta = w.tree[0][0], *tb = w.tree[1][0];
+    for (u32 half = 1u << (L - 1); half; half >>= 1, ta += WV_ROW, tb += WV_ROW) {
         const u32 pa = s + xa, pb = s + xb;
-        const u32 wa = w.bits[0][l][pa >> 5], wb = w.bits[1][l][pb >> 5];
-        const u32 za = (u32)w.cum[0][l][pa >> 5] + __popc(~wa & ((1u << (pa & 31)) - 1u)) - z0;
-        const u32 zb = (u32)w.cum[1][l][pb >> 5] + __popc(~wb & ((1u << (pb & 31)) - 1u)) - z0;
+        const uint2 qa = ta[pa >> 5], qb = tb[pb >> 5];
+        const u32 z0 = s >> 1;
+        const u32 za = qa.y + __popc(~qa.x & ((1u << (pa & 31)) - 1u)) - z0;
+        const u32 zb = qb.y + __popc(~qb.x & ((1u << (pb & 31)) - 1u)) - z0;
         const u32 dz = za - zb;
         const bool one = k >= dz;
         k -= one ? dz : 0u;
-        p = 2 * p + (one ? 1u : 0u);
+        s += one ? half : 0u;
         xa = one ? xa - za : za;
         xb = one ? xb - zb : zb;
     }
-    return p;
+    return s;
 }
 
 struct WaveRun {
@@ -503,63 +505,59 @@ __device__ __forceinline__ void wave_run(const SeqDev *__restrict__ sd, WaveSmem
         if (j < W && nC + i < W) w.seq0[1][nC + i] = w.seq0[0][j];
     }
     __syncthreads();
-    // ---- the levels
+    // ---- the levels.  Warp w owns the chunks (32 positions) [w cpw, (w + 1) cpw) of both level sequences: it keeps their keys
+    // and bitmaps in registers, publishes its zero count, and after one barrier knows the zeros before each of its chunks:
+    // the words' counts are written and the keys move to their places in the next level (inside every node the zeros first,
+    // then the ones, both in order).  Two barriers per level.
     const u32 nch = (W + 31) >> 5;
+    const u32 cpw = (nch + SW3_TPB / 32 - 1) / (SW3_TPB / 32);  // <= 8
+    const u32 ltmask = (1u << lane) - 1u;
     for (int l = 0; l < L; l++) {
         const int sh = L - 1 - l;
-        // bitmaps + zeros per word (the sequences ping-pong between seq0 and seq1)
-        for (u32 c = warp; c < 2 * nch; c += SW3_TPB / 32) {
-            const u32 t = c >= nch ? 1u : 0u, cc = c - t * nch;
+        u32 word[2][8];
+#pragma unroll
+        for (int t = 0; t < 2; t++) {
             const u16 *cur = (l & 1) ? w.seq1[t] : w.seq0[t];
-            const u32 i = cc * 32 + lane;
-            const bool one = i < W ? ((cur[i] >> sh) & 1u) != 0 : true;
-            const u32 word = __ballot_sync(GRB_FULL, one);
-            if (lane == 0) {
-                w.bits[t][l][cc] = word;
-                w.cum[t][l][cc] = (u16)(32 - __popc(word));
+            u32 zsum = 0;
+#pragma unroll
+            for (int e = 0; e < 8; e++) {
+                const u32 i = (warp * cpw + e) * 32 + lane;
+                const u32 key = (u32)e < cpw && i < W ? cur[i] : 0xffffu;  // beyond the end: ones, never counted
+                word[t][e] = __ballot_sync(GRB_FULL, (key >> sh) & 1u);
+                zsum += 32 - __popc(word[t][e]);
             }
+            if (lane == 0) w.wtot[t][warp] = zsum;
         }
         __syncthreads();
-        // exclusive scan of the zeros per word (entries 0 .. nch): warp 0 for A, warp 1 for B, three entries per lane
-        if (warp < 2) {
-            u16 *row = w.cum[warp][l];
-            u32 z[3], sum = 0;
 #pragma unroll
-            for (int e = 0; e < 3; e++) {
-                const u32 c = lane * 3 + e;
-                z[e] = c < nch ? row[c] : 0u;
-                sum += z[e];
-            }
-            u32 incl = sum;
-#pragma unroll
-            for (int d = 1; d < 32; d <<= 1) {
-                const u32 t = __shfl_up_sync(GRB_FULL, incl, d);
-                if (lane >= (u32)d) incl += t;
-            }
-            u32 run = incl - sum;
-#pragma unroll
-            for (int e = 0; e < 3; e++) {
-                const u32 c = lane * 3 + e;
-                if (c <= nch) row[c] = (u16)run;
-                run += z[e];
-            }
-        }
-        __syncthreads();
-        if (l == L - 1) break;
-        // stable partition inside every node: zeros to the front of the node, ones behind them
-        for (u32 c = warp; c < 2 * nch; c += SW3_TPB / 32) {
-            const u32 t = c >= nch ? 1u : 0u, cc = c - t * nch;
+        for (int t = 0; t < 2; t++) {
             const u16 *cur = (l & 1) ? w.seq1[t] : w.seq0[t];
             u16 *nxt = (l & 1) ? w.seq0[t] : w.seq1[t];
-            const u32 i = cc * 32 + lane;
-            if (i < W) {
-                const u32 key = cur[i];
-                const u32 word = w.bits[t][l][cc];
-                const u32 zb = (u32)w.cum[t][l][cc] + __popc(~word & ((1u << lane) - 1u));  // zeros before i on this level
-                const u32 node = key >> (sh + 1), s = node << (sh + 1), z0 = node << sh;
-                const u32 zin = zb - z0;                                                      // zeros of the node before i
-                const u32 dest = (word >> lane) & 1u ? s + (1u << sh) + (i - s - zin) : s + zin;
-                if (dest < W) nxt[dest] = (u16)key;  // (always, for the permutations valid lefts produce)
+            uint2 *row = w.tree[t][l];
+            u32 zrun = 0;  // zeros of the level before this warp's first chunk
+#pragma unroll
+            for (int v = 0; v < SW3_TPB / 32; v++) zrun += (u32)v < warp ? w.wtot[t][v] : 0u;
+#pragma unroll
+            for (int e = 0; e < 8; e++) {
+                const u32 c = warp * cpw + e;
+                if ((u32)e < cpw && c < nch) {
+                    const u32 wd = word[t][e];
+                    const u32 zc = 32 - __popc(wd);
+                    if (lane == 0) {
+                        row[c] = make_uint2(wd, zrun);
+                        if (c == nch - 1) row[nch] = make_uint2(0xffffffffu, zrun + zc);  // a query may ask for position W
+                    }
+                    const u32 i = c * 32 + lane;
+                    if (sh && i < W) {
+                        const u32 key = cur[i];
+                        const u32 zb = zrun + __popc(~wd & ltmask);            // zeros before i on this level
+                        const u32 s = (key >> (sh + 1)) << (sh + 1);           // the node of this key starts here
+                        const u32 zin = zb - (s >> 1);                         // zeros of the node before i
+                        const u32 dest = (wd >> lane) & 1u ? s + (1u << sh) + (i - s - zin) : s + zin;
+                        if (dest < W) nxt[dest] = (u16)key;  // (always, for the permutations valid lefts produce)
+                    }
+                    zrun += zc;
+                }
             }
         }
         __syncthreads();
@@ -682,7 +680,8 @@ __global__ void __launch_bounds__(SW3_TPB, 4) k_sweep3(const SeqDev *__restrict_
             h = warp_max(h);
             if (lane == 0) {
                 u32 wlo = a ? sd->fb[(a - 1) >> GRB_BME_SHIFT] : 0u;
-                wlo &= ~255u;  // bulk copies need 16-byte aligned sources, also for the block-max-end slice
+                S.bcast[7] = wlo & ~3u;  // wavelet runs: bulk copies need 16-byte aligned sources
+                wlo &= ~255u;            // member sweep: also for the block-max-end slice
                 S.bcast[0] = wlo;
                 S.bcast[1] = b;
                 S.bcast[2] = c;
@@ -702,16 +701,19 @@ __global__ void __launch_bounds__(SW3_TPB, 4) k_sweep3(const SeqDev *__restrict_
         // a wavelet run: the slice fits WV_CAP, the run is long enough to pay for the trees, and the end-order range is
         // consistent with the slice (it always is for valid lefts; an invalid one is flagged by k_tile and answered anyhow)
         WaveRun wq;
-        wq.wlo = wlo, wq.W = W, wq.lbmin = S.bcast[3], wq.lbmax = S.bcast[4], wq.qlo = S.bcast[3] & ~3u, wq.lsmin = S.bcast[5], wq.lsmax = S.bcast[6];
-        const bool wave = stage_mode && o.wave_ratio > 0 && o.want_median && W && W <= WV_CAP && (c_hi - c_lo) * (u64)o.wave_ratio >= W &&
-                          wq.lbmin >= wlo && wq.lbmax >= wq.lbmin && wq.lbmax - wlo <= W;
+        wq.wlo = S.bcast[7], wq.W = whi > wq.wlo ? whi - wq.wlo : 0u;
+        wq.lbmin = S.bcast[3], wq.lbmax = S.bcast[4], wq.qlo = S.bcast[3] & ~3u, wq.lsmin = S.bcast[5], wq.lsmax = S.bcast[6];
+        const bool wave_on = stage_mode && o.wave_ratio > 0 && o.want_median;
+        const bool wave_dense = (c_hi - c_lo) * (u64)o.wave_ratio >= wq.W;
+        const bool wave = wave_on && wave_dense && wq.W && wq.W <= WV_CAP && wq.lbmin >= wq.wlo && wq.lbmax >= wq.lbmin &&
+                          wq.lbmax - wq.wlo <= wq.W;
         if (wave) {
             if (tid == 0) {
-                const u32 bytes = ((W + 3) & ~3u) * 4;
+                const u32 bytes = ((wq.W + 3) & ~3u) * 4;
                 const u32 pbytes = ((wq.lbmax - wq.qlo + 3) & ~3u) * 4;
                 mbar_arrive_expect_tx(&S.bar, 2 * bytes + pbytes);
-                tma_load_1d(S.w.ends, sd->ends + wlo, bytes, &S.bar);
-                tma_load_1d(S.w.rank, sd->rank_a + wlo, bytes, &S.bar);
+                tma_load_1d(S.w.ends, sd->ends + wq.wlo, bytes, &S.bar);
+                tma_load_1d(S.w.rank, sd->rank_a + wq.wlo, bytes, &S.bar);
                 if (pbytes) tma_load_1d(S.w.perm, sd->perm_e + wq.qlo, pbytes, &S.bar);
             }
             mbar_wait(&S.bar, phase);
@@ -721,7 +723,7 @@ __global__ void __launch_bounds__(SW3_TPB, 4) k_sweep3(const SeqDev *__restrict_
             c_lo = c_hi;
             continue;
         }
-        if (stage_mode && o.wave_ratio > 0 && o.want_median && W > WV_CAP && (c_hi - c_lo) * (u64)o.wave_ratio >= W && c_hi - c_lo > SW3_MIN_RUN) {
+        if (wave_on && wave_dense && wq.W > WV_CAP && c_hi - c_lo > SW3_MIN_RUN) {
             run = (c_hi - c_lo + 1) >> 1;  // dense lefts over a slice too wide for the trees: halve the run, not the method
             __syncthreads();
             continue;
