@@ -778,6 +778,24 @@ def main():
         dist.all_reduce(agg)
     pairs_total, nl_total = int(agg[0].item()), int(agg[1].item())
 
+    # ---- index build once more on the warm memory pool (index_build_ms_rank0 above is the first build of the process: it
+    # pays for the pool's growth): the same units, one by one with a synchronisation each, and closed again
+    t_build_warm = 0.0
+    if world == 1 and not args.no_configs:
+        for p in mine:
+            s = p["seq"]
+            if (p["left_begin"] - int(left_off[s]), p["left_end"] - int(left_off[s])) != (0, nl_per[s]):
+                t_build_warm = None  # (coordinate slices: not re-derived here)
+                break
+            rs, re, sc = gen_ranges(s, nr_per[s], 14, dev, True)
+            torch.cuda.synchronize()
+            t0 = time.perf_counter()
+            ixw = ctx.index_build(rs, re).set_scores(sc)
+            ctx.sync()
+            t_build_warm += time.perf_counter() - t0
+            ixw.close()
+            del rs, re, sc
+
     # keep one seqname's device-timed results for the parity check against the oracle below
     chk_seq = pick_sample_seqs(nl_per, nr_per)[0][0]
     chk_slice = None
@@ -886,7 +904,8 @@ def main():
         "warmup": args.warmup, "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "strong", "vs_baseline": None,
         "dtype": "f64", "data": "synthetic", "config": workload_config(args),
         "pairs_per_s": pairs_total / (ms_per_step * 1e-3), "overlap_pairs": pairs_total, "lefts_processed": nl_total,
-        "index_build_ms_rank0": t_build * 1e3, "gpu_launches": int(launches), "clocks": clocks,
+        "index_build_ms_rank0": t_build * 1e3, "index_build_warm_ms_rank0": (t_build_warm * 1e3 if t_build_warm else None),
+        "gpu_launches": int(launches), "clocks": clocks,
         "step_ms_rank0": {"min": min(per_step), "median": float(np.median(per_step)), "max": max(per_step)},
         "units_rank0": len(mine), "cpus_bound_rank0": numa, "step_ms_per_rank": per_rank_ms,
     }
