@@ -32,6 +32,7 @@ struct grb_ctx {
     size_t batch_bytes, batch_cap;
     u32 *dev_flags; // device word: bit 0 = a left range with end <= start or end > 2^31-1 was seen by a kernel
     void *zeros;    // 1 KB of zeros (tables) + 1 KB of 0xff (sentinel keys): what an absent seqname / empty index reads
+    int pipe_assign; // GRB_PIPE_ASSIGN (A/B): 1 = runs of consecutive tiles per CTA instead of round-robin single tiles
     int pipe_mode;  // 1 = persistent warp-specialised pipeline for single-reduction maps (default), 0 = k_tile only (debug)
     int tile_mode;  // 1 = TMA-staged smem windows (default), 0 = global binary search only (debug)
     int ublb_pipe;  // GRB_UBLB_PIPE: 1 / 0 = the (ub, pp, lb) pass always / never in the pipelined kernel; -1 (default) = beside sums

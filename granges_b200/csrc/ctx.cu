@@ -223,6 +223,8 @@ int grb_ctx_create(int device, grb_ctx **out) {
     ctx->pipe_mode = 1;
     const char *pm = getenv("GRB_PIPE_MODE");
     if (pm) ctx->pipe_mode = atoi(pm);
+    ctx->pipe_assign = 0;
+    if (const char *pa = getenv("GRB_PIPE_ASSIGN")) ctx->pipe_assign = atoi(pa);
     ctx->sweep_mode = 1;
     const char *sm = getenv("GRB_SWEEP_MODE");
     if (sm) ctx->sweep_mode = atoi(sm);

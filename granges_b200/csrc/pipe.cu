@@ -57,10 +57,19 @@ constexpr int PIPE_LPT = TILE / (PIPE_NCG * 32);  // consecutive lefts per consu
 static_assert(PIPE_LPT == 2, "consumer layout");
 constexpr int PIPE_NSURV = 4;  // surveyor warps (tile j goes to surveyor j % PIPE_NSURV)
 constexpr int PIPE_THREADS = (PIPE_NCG + 2 + PIPE_NSURV) * 32;
-constexpr int PIPE_LSTAGES = 8;
+#ifndef PIPE_LSTAGES_N
+#define PIPE_LSTAGES_N 8   // A/B switch: lefts-ring depth
+#endif
+#ifndef PIPE_WST_N
+#define PIPE_WST_N 4       // A/B switch: window-ring depth of the variants without extra planes
+#endif
+constexpr int PIPE_LSTAGES = PIPE_LSTAGES_N;
 constexpr u32 PIPE_WIN = 1280;  // keys (and prefixes) per staged window
 constexpr u32 PIPE_LUT = 640;   // bin-table entries per staged slice
 constexpr int PIPE_MAXSEQ = 32; // seqnames per launch (their descriptors live in shared memory)
+#ifndef PIPE_RUN
+#define PIPE_RUN 4u             // A/B switch (GRB_PIPE_ASSIGN=1): consecutive tiles per CTA visit
+#endif
 
 struct PipeSeq {
     const u32 *starts, *ends_sorted, *lut_a, *lut_b;
@@ -92,9 +101,21 @@ struct PipeDesc {      // one per window-ring slot (loader -> consumers)
     int seq;
 };
 
+#ifndef PIPE_CONS_PACK
+#define PIPE_CONS_PACK 0  // A/B switch: the consumers read their per-tile parameters as three 16-byte words written by the window loader
+#endif
+struct alignas(16) PipeCons {  // one per window-ring slot: everything a consumer needs to know about the tile
+    u32 a0, b0, la0, lb0;
+    u64 g_first;
+    u32 vlo_vhi;   // vlo | vhi << 16
+    u32 flags;     // bit 0 staged, bit 1 nf, bits 8..12 lut shift, bits 16.. seqname slot
+    double scale;
+    u32 bmax, fast_cmax;
+};
+
 template <int VAR>
 struct PipeSmemT {
-    static constexpr int WST = (VAR & PIPE_VAR_WIDE) ? 3 : 4;  // window-ring depth: what fits beside the extra planes
+    static constexpr int WST = (VAR & PIPE_VAR_WIDE) ? (PIPE_LSTAGES_N > 8 ? 2 : 3) : PIPE_WST_N;  // window-ring depth: what fits beside the extra planes
     static constexpr u32 NH = (VAR & PIPE_VAR_WIDE) ? PIPE_WIN + 8 : 4;
     static constexpr u32 NV = (VAR & PIPE_VAR_NULLS) ? PIPE_WIN + 8 : 8;
     alignas(16) u32 ls[PIPE_LSTAGES][TILE];
@@ -113,6 +134,7 @@ struct PipeSmemT {
     PipeSeq seq[PIPE_MAXSEQ];
     PipeTile tile[PIPE_LSTAGES];
     PipeDesc desc[WST];
+    PipeCons cons[WST];
     alignas(8) u64 fullL[PIPE_LSTAGES];
     alignas(8) u64 emptyL[PIPE_LSTAGES];
     alignas(8) u64 statsL[PIPE_LSTAGES];
@@ -255,7 +277,19 @@ __global__ void __launch_bounds__(PIPE_THREADS, 1) k_map_pipe(const SeqDev *__re
         q.sh = sd->lut_shift;
     }
     __syncthreads();
-    const u32 nmine = blockIdx.x < ntiles ? (ntiles - blockIdx.x + gridDim.x - 1) / gridDim.x : 0;
+    // tile assignment: round-robin (tile blockIdx.x + j gridDim.x), or -- flags bit 3, A/B switch GRB_PIPE_ASSIGN=1 -- runs of
+    // PIPE_RUN consecutive tiles dealt round-robin (run r of CTA b = run r gridDim.x + b)
+    const bool blocked = (flags & 8) != 0;
+    u32 nmine = blockIdx.x < ntiles ? (ntiles - blockIdx.x + gridDim.x - 1) / gridDim.x : 0;
+    if (blocked) {
+        const u32 nruns = (ntiles + PIPE_RUN - 1) / PIPE_RUN;
+        const u32 myruns = blockIdx.x < nruns ? (nruns - blockIdx.x + gridDim.x - 1) / gridDim.x : 0;
+        nmine = myruns * PIPE_RUN;
+        if (myruns) {
+            const u32 last = (blockIdx.x + (myruns - 1) * gridDim.x) * PIPE_RUN;  // first tile of my last run
+            if (last + PIPE_RUN > ntiles) nmine -= last + PIPE_RUN - ntiles;
+        }
+    }
 
     if (warp == 0) {
         // ================= lefts loader (A) =================
@@ -264,7 +298,7 @@ __global__ void __launch_bounds__(PIPE_THREADS, 1) k_map_pipe(const SeqDev *__re
         int sq = 0;  // tiles only move forward, so does the seqname
         for (u32 j = 0; j < nmine; j++) {
             const u32 sl = j % PIPE_LSTAGES;
-            const u32 t = tile_base + blockIdx.x + j * gridDim.x;
+            const u32 t = tile_base + (blocked ? (blockIdx.x + (j / PIPE_RUN) * gridDim.x) * PIPE_RUN + j % PIPE_RUN : blockIdx.x + j * gridDim.x);
             while (sq + 1 < nseq && S.seq[sq + 1].tile_begin <= t) sq++;
             const PipeSeq &q = S.seq[sq];
             const u64 g_first = ((q.left_begin >> TILE_SHIFT) + (t - q.tile_begin)) << TILE_SHIFT;
@@ -366,6 +400,15 @@ __global__ void __launch_bounds__(PIPE_THREADS, 1) k_map_pipe(const SeqDev *__re
                 d.lb0 = lb0;
                 d.staged = staged ? 1u : 0u;
                 d.nf = ti.nf;
+#if PIPE_CONS_PACK
+                PipeCons &pc = S.cons[sw];
+                pc.a0 = a0, pc.b0 = b0, pc.la0 = la0, pc.lb0 = lb0;
+                pc.g_first = ti.g_first;
+                pc.vlo_vhi = ti.vlo | (ti.vhi << 16);
+                pc.flags = (staged ? 1u : 0u) | (ti.nf ? 2u : 0u) | ((u32)q.sh << 8) | ((u32)ti.seq << 16);
+                pc.scale = q.scale;
+                pc.bmax = q.bmax, pc.fast_cmax = q.fast_cmax;
+#endif
                 if (staged)
                     mbar_arrive_expect_tx(&S.fullW[sw], total_bytes);
                 else
@@ -478,12 +521,32 @@ __global__ void __launch_bounds__(PIPE_THREADS, 1) k_map_pipe(const SeqDev *__re
             }
             continue;
         }
+#if PIPE_CONS_PACK
+        const uint4 c0 = *reinterpret_cast<const uint4 *>(&S.cons[sw]);
+        const uint4 c1 = *(reinterpret_cast<const uint4 *>(&S.cons[sw]) + 1);
+        const uint4 c2 = *(reinterpret_cast<const uint4 *>(&S.cons[sw]) + 2);
+        struct {
+            u64 g_first;
+            u32 staged, nf;
+            int seq;
+        } d;
+        d.g_first = ((u64)c1.y << 32) | c1.x;
+        d.staged = c1.w & 1u;
+        d.nf = (c1.w >> 1) & 1u;
+        d.seq = (int)(c1.w >> 16);
+        const PipeSeq &q = S.seq[d.seq];  // (only the rare paths and the NULLS variants read it)
+        const u32 vlo = c1.z & 0xffffu, vhi = c1.z >> 16;
+        const int sh = (int)((c1.w >> 8) & 31u);
+        const u32 bmax = c2.z, fast_cmax = c2.w;
+        const double scale = __hiloint2double((int)c2.y, (int)c2.x);
+#else
         const PipeDesc &d = S.desc[sw];
         const PipeSeq &q = S.seq[d.seq];
         const u32 vlo = d.vlo, vhi = d.vhi;
         const int sh = q.sh;
         const u32 bmax = q.bmax, fast_cmax = q.fast_cmax;
         const double scale = q.scale;
+#endif
         const uint4 *__restrict__ nf_a = q.nf_a, *__restrict__ nf_b = q.nf_b;
         const bool tile_nf = NULLS && nf_a != nullptr && d.nf != 0;
         u32 a[PIPE_LPT], b[PIPE_LPT];
@@ -498,7 +561,11 @@ __global__ void __launch_bounds__(PIPE_THREADS, 1) k_map_pipe(const SeqDev *__re
         for (int k = 0; k < PIPE_LPT; k++) okv[k] = i0 + k >= vlo && i0 + k < vhi;
         // (A left with end <= start or end > 2^31-1 -- impossible in the reference, which panics -- was flagged by
         // the surveyor, which also keeps its tile off the staged path.)
+#if PIPE_CONS_PACK
+        const u32 a0 = c0.x, b0 = c0.y, la0 = c0.z, lb0 = c0.w;
+#else
         const u32 a0 = d.a0, b0 = d.b0, la0 = d.la0, lb0 = d.lb0;
+#endif
         const SeqDev *__restrict__ sd = &seqs[d.seq];  // only dereferenced on the rare paths
         u32 ub[PIPE_LPT], lbk[PIPE_LPT], ppk[PIPE_LPT];  // absolute positions
         u64 pa[PIPE_LPT], pb[PIPE_LPT];
@@ -793,7 +860,7 @@ int launch_var(grb_ctx *ctx, const Batch &b, int s0, int s1, const u32 *ls, cons
         GRB_CUDA(ctx, cudaFuncSetAttribute(k_map_pipe<FAST, VAR>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(Smem)));
         if (ctx->device >= 0 && ctx->device < 64) configured[ctx->device] = true;
     }
-    const int flags = (ctx->tile_mode ? 1 : 0) | (ctx->pipe_mode == 2 ? 2 : 0) | (ctx->pipe_mode == 3 ? 4 : 0);
+    const int flags = (ctx->tile_mode ? 1 : 0) | (ctx->pipe_mode == 2 ? 2 : 0) | (ctx->pipe_mode == 3 ? 4 : 0) | (ctx->pipe_assign ? 8 : 0);
     const u32 t0 = b.host_tile_begin[s0], t1 = b.host_tile_begin[s1];
     if (t1 == t0) return GRB_OK;
     u32 grid = (u32)ctx->sm_count;
