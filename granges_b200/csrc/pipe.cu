@@ -67,8 +67,11 @@ constexpr int PIPE_LSTAGES = PIPE_LSTAGES_N;
 constexpr u32 PIPE_WIN = 1280;  // keys (and prefixes) per staged window
 constexpr u32 PIPE_LUT = 640;   // bin-table entries per staged slice
 constexpr int PIPE_MAXSEQ = 32; // seqnames per launch (their descriptors live in shared memory)
+#ifndef PIPE_ASSIGN_AB
+#define PIPE_ASSIGN_AB 0        // A/B build: GRB_PIPE_ASSIGN=1 deals runs of PIPE_RUN consecutive tiles to the CTAs instead of single tiles
+#endif
 #ifndef PIPE_RUN
-#define PIPE_RUN 4u             // A/B switch (GRB_PIPE_ASSIGN=1): consecutive tiles per CTA visit
+#define PIPE_RUN 4u
 #endif
 
 struct PipeSeq {
@@ -134,7 +137,9 @@ struct PipeSmemT {
     PipeSeq seq[PIPE_MAXSEQ];
     PipeTile tile[PIPE_LSTAGES];
     PipeDesc desc[WST];
+#if PIPE_CONS_PACK
     PipeCons cons[WST];
+#endif
     alignas(8) u64 fullL[PIPE_LSTAGES];
     alignas(8) u64 emptyL[PIPE_LSTAGES];
     alignas(8) u64 statsL[PIPE_LSTAGES];
@@ -277,8 +282,9 @@ __global__ void __launch_bounds__(PIPE_THREADS, 1) k_map_pipe(const SeqDev *__re
         q.sh = sd->lut_shift;
     }
     __syncthreads();
+#if PIPE_ASSIGN_AB
     // tile assignment: round-robin (tile blockIdx.x + j gridDim.x), or -- flags bit 3, A/B switch GRB_PIPE_ASSIGN=1 -- runs of
-    // PIPE_RUN consecutive tiles dealt round-robin (run r of CTA b = run r gridDim.x + b)
+    // PIPE_RUN consecutive tiles dealt round-robin (run r of CTA b = run r gridDim.x + b).  Measured: no gain (profiles/r2/ab_pipe_kernel.txt).
     const bool blocked = (flags & 8) != 0;
     u32 nmine = blockIdx.x < ntiles ? (ntiles - blockIdx.x + gridDim.x - 1) / gridDim.x : 0;
     if (blocked) {
@@ -290,6 +296,9 @@ __global__ void __launch_bounds__(PIPE_THREADS, 1) k_map_pipe(const SeqDev *__re
             if (last + PIPE_RUN > ntiles) nmine -= last + PIPE_RUN - ntiles;
         }
     }
+#else
+    const u32 nmine = blockIdx.x < ntiles ? (ntiles - blockIdx.x + gridDim.x - 1) / gridDim.x : 0;
+#endif
 
     if (warp == 0) {
         // ================= lefts loader (A) =================
@@ -298,7 +307,11 @@ __global__ void __launch_bounds__(PIPE_THREADS, 1) k_map_pipe(const SeqDev *__re
         int sq = 0;  // tiles only move forward, so does the seqname
         for (u32 j = 0; j < nmine; j++) {
             const u32 sl = j % PIPE_LSTAGES;
+#if PIPE_ASSIGN_AB
             const u32 t = tile_base + (blocked ? (blockIdx.x + (j / PIPE_RUN) * gridDim.x) * PIPE_RUN + j % PIPE_RUN : blockIdx.x + j * gridDim.x);
+#else
+            const u32 t = tile_base + blockIdx.x + j * gridDim.x;
+#endif
             while (sq + 1 < nseq && S.seq[sq + 1].tile_begin <= t) sq++;
             const PipeSeq &q = S.seq[sq];
             const u64 g_first = ((q.left_begin >> TILE_SHIFT) + (t - q.tile_begin)) << TILE_SHIFT;
