@@ -51,6 +51,7 @@ struct grb_ctx {
     int hist_bucketed;    // ... the verdict in force for them (kept until a newer report says otherwise) ...
     u32 hist_gen0;        // ... and the first generation that belongs to them
     u32 gen;              // generation counter of the reporting calls
+    int planar_rows; // GRB_PLANAR_ROWS (default 1): beside k_sweep3 the prefix-sum columns travel through a side array and the sweep writes whole rows
     int wave_ratio; // GRB_WAVE_RATIO: medians of a run of lefts come from per-run wavelet trees when lefts * ratio >= slice rights (default 8, 0 = never)
     int sweep_mode; // 1 = staged rank sweep k_sweep3 for MIN / MAX / MEDIAN (default), 2 = k_sweep3 without staging, 0 = k_sweep2 only (debug)
     char err[512];

@@ -229,6 +229,8 @@ int grb_ctx_create(int device, grb_ctx **out) {
     const char *sm = getenv("GRB_SWEEP_MODE");
     if (sm) ctx->sweep_mode = atoi(sm);
     ctx->wave_ratio = 8;
+    ctx->planar_rows = 1;
+    if (const char *pr = getenv("GRB_PLANAR_ROWS")) ctx->planar_rows = atoi(pr);
     if (const char *wr = getenv("GRB_WAVE_RATIO")) ctx->wave_ratio = atoi(wr);
     // the remaining tuning knobs are read once, here, not on every call
     const char *up = getenv("GRB_UBLB_PIPE");

@@ -194,6 +194,7 @@ struct PipeOps {
     u32 *valid_bits;    // single-reduction kernels: validity as bits (bit g of word g / 32) instead of bytes
     u32 *stats;         // see TileOut::stats
     u32 stats_gen;
+    uint4 *planar;      // see TileOut::planar
 };
 
 // #(keys < x) among the 8 keys of the two aligned quads at q
@@ -788,6 +789,16 @@ __global__ void __launch_bounds__(PIPE_THREADS, 1) k_map_pipe(const SeqDev *__re
                     mops.lb[g0 + k] = lbk[k];
                 }
         }
+        if (FAST == PIPE_UBLB && mops.planar != nullptr) {
+            // the member sweep that follows writes the rows: hand it (sum, count, scored members), one 16-byte store per left
+#pragma unroll
+            for (int k = 0; k < PIPE_LPT; k++)
+                if (okv[k]) {
+                    const u64 sb = (u64)__double_as_longlong(sum[k]);
+                    __stcs(mops.planar + g0 + k, make_uint4((u32)sb, (u32)(sb >> 32), cnt[k], nval[k]));
+                }
+            continue;
+        }
         if (FAST == PIPE_MULTI || FAST == PIPE_UBLB) {
             // several reductions from the same (count, exact sum): row-major out[left][column]
 #pragma unroll
@@ -888,6 +899,7 @@ int launch_var(grb_ctx *ctx, const Batch &b, int s0, int s1, const u32 *ls, cons
     mops.valid_bits = valid_bits;
     mops.stats = o.stats;
     mops.stats_gen = o.stats_gen;
+    mops.planar = o.planar;
     k_map_pipe<FAST, VAR><<<grid, PIPE_THREADS, sizeof(Smem), ctx->stream>>>(b.seqs + s0, s1 - s0, t0, t1 - t0, ls, le, o.out, o.out_valid, flags,
                                                                           o.flags, mops);
     GRB_LAUNCHED(ctx);

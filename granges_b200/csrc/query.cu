@@ -357,6 +357,7 @@ struct SweepOut {
     int want_median, want_bp, want_wm;  // want_wm implies want_bp (the overlap widths are needed)
     u32 *heavy_list;
     u32 *heavy_count;
+    const uint4 *planar;  // k_sweep3: (sum, count, scored members) per left from the pipelined pass: the prefix-sum columns are written here, with the rows
     int wave_ratio;  // k_sweep3: a run of lefts answers its medians from per-run wavelet trees when lefts * wave_ratio >= rights of its slice (0: never)
 };
 
@@ -1263,6 +1264,18 @@ static int map_joins_impl(grb_ctx *ctx, const grb_index *const *idx, const uint6
         o.ub = ub.as<u32>();
         o.lb = lb.as<u32>();
         o.pp = pp.as<u32>();
+        // k_sweep3 follows and some columns come from the prefix sums: the pipelined pass leaves (sum, count, scored members)
+        // per left in a side array and the sweep writes whole rows -- otherwise both kernels read-modify-write the partial
+        // sectors of a row-major `out` (at config C3: 4.5 GB of extra DRAM reads in each of them)
+        TempBuf planar;
+        const bool ublb_in_pipe = ctx->pipe_mode == 1 && (ctx->ublb_pipe < 0 ? need_sum != 0 : ctx->ublb_pipe != 0) && (b.pipeable || !need_sum) &&
+                                  b.ntiles >= 4u * (u32)ctx->sm_count;
+        bool has_pipe_col = false;
+        for (int c = 0; c < k; c++) has_pipe_col |= ops[c] == GRB_OP_COUNT || ops[c] == GRB_OP_SUM || ops[c] == GRB_OP_SUM_NOT_EMPTY || ops[c] == GRB_OP_MEAN;
+        if (rank_sweep && want_median && ublb_in_pipe && has_pipe_col && !bp_cols && !wm_cols && !ws_cols && ctx->planar_rows) {
+            GRB_TRY(planar.alloc(ctx, b.total * 16));
+            o.planar = planar.as<uint4>();
+        }
         GRB_TRY(launch_map<M_MAP | M_UBLB>(ctx, b, dls.as<u32>(), dle.as<u32>(), o));
         if (bp_cols) {
             k_overlap_bp<<<(unsigned)((b.total - left_offsets[0] + 255) / 256), 256, 0, ctx->stream>>>(b.seqs, b.nseq, left_offsets[0], b.total,
@@ -1291,6 +1304,7 @@ static int map_joins_impl(grb_ctx *ctx, const grb_index *const *idx, const uint6
             so.want_bp = want_bp;
             so.want_wm = want_wm;
             so.wave_ratio = ctx->wave_ratio;
+            so.planar = o.planar;
             if (want_median) {
                 if (b.total >= 0xffffffffull) return grb_fail(ctx, GRB_ERR_UNSUPPORTED, "map_joins: median over more than 2^32-1 lefts per call");
                 GRB_TRY(heavy.alloc(ctx, (b.total + 1) * 4));

@@ -68,6 +68,20 @@ struct Sweep3Smem {
     u32 bcast[8];
 };
 
+// A prefix-sum column (count / sum / sum-not-empty / mean) from what the pipelined pass left per left: exactly its own
+// arithmetic (pipe.cu, PIPE_MULTI epilogue), so the column is the same whoever writes it.
+__device__ __forceinline__ bool sw3_is_pipe_op(int op) {
+    return op == GRB_OP_COUNT || op == GRB_OP_SUM || op == GRB_OP_SUM_NOT_EMPTY || op == GRB_OP_MEAN;
+}
+__device__ __forceinline__ double sw3_pipe_col(int op, const uint4 pl, u8 &valid) {
+    const double sum = __hiloint2double((int)pl.y, (int)pl.x);
+    const u32 cnt = pl.z, nval = pl.w;
+    valid = (op == GRB_OP_SUM || op == GRB_OP_COUNT) ? (u8)1 : (u8)(nval != 0);
+    if (op == GRB_OP_COUNT) return (double)cnt;
+    if (op == GRB_OP_MEAN) return nval ? sum / (double)nval : 0.0;
+    return sum;
+}
+
 // Median of m <= G * R different 32-bit keys held in kbuf[0, m) by a group of G lanes: a bitonic sorting network
 // over R registers per lane (element position = lane * R + register: small partner distances stay inside a
 // lane, the large ones are one shuffle per register), padded with low / high sentinels so that the middle pair
@@ -191,6 +205,8 @@ __device__ __forceinline__ void sweep3_run(const SeqDev *__restrict__ sd, u64 c_
     double pend_v1 = 0.0, pend_v2 = 0.0;
     bool pend_ok = false, pend_two = false;
 
+    const bool pipe_lane = o.planar != nullptr && my_op >= 0 && sw3_is_pipe_op(my_op);
+    uint4 pl = make_uint4(0, 0, 0, 0);
     u64 g = c_lo + gidx;
     u32 u = 0, p = 0, l = 0, lstart = 0;
     if (g < c_hi) {
@@ -198,6 +214,7 @@ __device__ __forceinline__ void sweep3_run(const SeqDev *__restrict__ sd, u64 c_
         p = ppv[g];
         l = lbv[g];
         lstart = ls[g];
+        if (pipe_lane) pl = o.planar[g];
     }
     const u64 g_warp = c_lo + (threadIdx.x >> 5) * (32 / G);
     const u32 rounds = g_warp < c_hi ? (u32)((c_hi - g_warp + NGROUPS - 1) / NGROUPS) : 0u;
@@ -206,11 +223,13 @@ __device__ __forceinline__ void sweep3_run(const SeqDev *__restrict__ sd, u64 c_
         // parameters of the next left of this group
         const u64 gn = g + NGROUPS;
         u32 nu = 0, np = 0, nl = 0, nls = 0;
+        uint4 npl = make_uint4(0, 0, 0, 0);
         if (gn < c_hi) {
             nu = ubv[gn];
             np = ppv[gn];
             nl = lbv[gn];
             nls = ls[gn];
+            if (pipe_lane) npl = o.planar[gn];
         }
         u32 nvalid = 0;
         u32 rmin = GRB_RANK_NONE;  // unsigned min ignores NONE
@@ -331,6 +350,12 @@ __device__ __forceinline__ void sweep3_run(const SeqDev *__restrict__ sd, u64 c_
                 }
             }
         }
+        if (pipe_lane && live) {
+            u8 vv;
+            o.out[g * (u64)k + glane] = sw3_pipe_col(my_op, pl, vv);
+            o.out_valid[g * (u64)k + glane] = vv;
+        }
+        pl = npl;
         if (heavy && live && glane == 0) {
             const u32 slot = atomicAdd(o.heavy_count, 1u);
             o.heavy_list[slot] = (u32)g;  // the host checks total < 2^32 when a median is requested
@@ -586,11 +611,17 @@ __device__ __forceinline__ void wave_run(const SeqDev *__restrict__ sd, WaveSmem
                 if (!(m & 1u)) v_med = (v_med + sorted_scores[w.sorted[wv_kth(w, L, x, y, m >> 1)]]) / 2.0;
             }
         }
+        uint4 pl = make_uint4(0, 0, 0, 0);
+        if (o.planar != nullptr) pl = o.planar[g];
         for (int c = 0; c < k; c++) {
             const int op = (int)((ops_packed >> (4 * c)) & 15u);
             if (op == GRB_OP_MIN || op == GRB_OP_MAX || op == GRB_OP_MEDIAN) {
                 o.out[g * (u64)k + c] = op == GRB_OP_MIN ? v_min : op == GRB_OP_MAX ? v_max : v_med;
                 o.out_valid[g * (u64)k + c] = m ? 1 : 0;
+            } else if (o.planar != nullptr && sw3_is_pipe_op(op)) {
+                u8 vv;
+                o.out[g * (u64)k + c] = sw3_pipe_col(op, pl, vv);
+                o.out_valid[g * (u64)k + c] = vv;
             }
         }
     }
@@ -620,6 +651,10 @@ __global__ void __launch_bounds__(SW3_TPB, 4) k_sweep3(const SeqDev *__restrict_
                 if (op == GRB_OP_MIN || op == GRB_OP_MAX || op == GRB_OP_MEDIAN) {
                     o.out[g * (u64)o.k + c] = 0.0;
                     o.out_valid[g * (u64)o.k + c] = 0;
+                } else if (o.planar != nullptr && sw3_is_pipe_op(op)) {
+                    u8 vv;
+                    o.out[g * (u64)o.k + c] = sw3_pipe_col(op, o.planar[g], vv);
+                    o.out_valid[g * (u64)o.k + c] = vv;
                 }
             }
         return;

@@ -19,6 +19,8 @@ struct TileOut {
     u32 *flags;  // context flag word (bit 0: invalid left range seen)
     u32 *stats;  // pipelined kernel: stats[16 + blockIdx.x] = tiles this CTA could not stage (mapped host words; may be NULL)
     u32 stats_gen;  // ... and stats[1] = this number, by CTA 0, after its count
+    uint4 *planar;  // PIPE_UBLB beside k_sweep3: {sum lo, sum hi, count, scored members} per left here instead of the prefix-sum
+                    // columns in `out` -- the sweep writes whole rows, nobody read-modify-writes partial sectors (may be NULL)
 };
 
 // ---- host side: one batch = the seqnames of one call, concatenated in GenomeMap order -------------------
