@@ -357,17 +357,31 @@ __device__ __forceinline__ void emit_tile(const SeqDev *__restrict__ sd, u64 g_l
     const u64 g_warp = g_lo + (threadIdx.x >> 5) * (32 / G);
     const u32 rounds = g_warp < g_hi ? (u32)((g_hi - g_warp + NGROUPS - 1) / NGROUPS) : 0u;
     u64 g = g_lo + gidx;
+    // the next left's parameters are loaded while this one is written: one warp per left and ~1 KB of pairs per left make the
+    // kernel a chain of dependent round trips otherwise (3.8 TB/s of writes at config C5)
+    u32 nu = 0, np = 0, nl = 0, nls = 0;
+    u64 noff = 0;
+    if (g < g_hi) {
+        nu = ubv[g];
+        np = ppv[g];
+        nl = lbv[g];
+        nls = ls[g];
+        noff = offsets[g];
+    }
     for (u32 round = 0; round < rounds; round++, g += NGROUPS) {
         const bool live = g < g_hi;
-        u32 u = 0, p = 0, l = 0, lstart = 0;
-        u32 *__restrict__ dst = pos;
-        if (live) {
-            u = ubv[g];
-            p = ppv[g];
-            l = lbv[g];
-            lstart = ls[g];
-            dst = pos + offsets[g];
+        const u32 u = nu, p = np, l = nl, lstart = nls;
+        u32 *__restrict__ dst = pos + noff;
+        nu = np = nl = nls = 0;
+        noff = 0;
+        if (g + NGROUPS < g_hi) {
+            nu = ubv[g + NGROUPS];
+            np = ppv[g + NGROUPS];
+            nl = lbv[g + NGROUPS];
+            nls = ls[g + NGROUPS];
+            noff = offsets[g + NGROUPS];
         }
+        (void)live;
         const u32 need = p - l;
         for (u32 j = p + glane; j < u; j += G) dst[need + (j - p)] = j;
         u32 found = 0;
