@@ -383,15 +383,30 @@ __device__ __forceinline__ void emit_tile(const SeqDev *__restrict__ sd, u64 g_l
         }
         (void)live;
         const u32 need = p - l;
-        for (u32 j = p + glane; j < u; j += G) dst[need + (j - p)] = j;
+        // [p, u) as an iota: a scalar head up to the next 16-byte boundary, 16-byte stores, a scalar tail
+        {
+            u32 *__restrict__ q = dst + need;
+            const u32 cnt = u > p ? u - p : 0u;
+            const u32 head = min(cnt, (4u - (u32)(((uintptr_t)q >> 2) & 3u)) & 3u);
+            if (glane < head) q[glane] = p + glane;
+            const u32 nvec = (cnt - head) >> 2;
+            for (u32 v = glane; v < nvec; v += G) {
+                const u32 j = p + head + 4u * v;
+                *reinterpret_cast<uint4 *>(q + head + 4u * v) = make_uint4(j, j + 1, j + 2, j + 3);
+            }
+            const u32 t0 = head + 4u * nvec;
+            if (t0 + glane < cnt) q[t0 + glane] = p + t0 + glane;
+        }
         u32 found = 0;
         long long cb = p ? (long long)((p - 1) & ~(u32)(G - 1)) : -1;
         while (true) {
             const bool act = found < need && cb >= 0;
             if (!__any_sync(GRB_FULL, act)) break;
-            const bool look = act && bme[cb >> GRB_BME_SHIFT] > lstart;
+            // (the end is loaded beside the block maximum, not after it: one round trip per step instead of two)
             const u32 j = (u32)cb + glane;
-            const bool hit = look && j < p && ends[j] > lstart;
+            const u32 e = act && j < p ? ends[j] : 0u;
+            const bool look = act && bme[cb >> GRB_BME_SHIFT] > lstart;
+            const bool hit = look && e > lstart;
             const u32 hm = (__ballot_sync(GRB_FULL, hit) >> gshift) & GM;
             if (hit) {
                 const u32 above = glane == G - 1 ? 0u : __popc(hm >> (glane + 1));
@@ -413,8 +428,19 @@ __global__ void __launch_bounds__(SW2_TPB) k_emit2(const SeqDev *__restrict__ se
     const u64 g_lo = sd->left_begin > g_first ? sd->left_begin : g_first;
     const u64 g_hi = sd->left_end < g_first + TILE ? sd->left_end : g_first + TILE;
     const u64 pairs = offsets[g_hi] - offsets[g_lo];
-    if (pairs > 64ull * (g_hi - g_lo))
+    // lanes per left.  The kernel is bound by its instructions per left (~190 per warp round whatever the group width), and a
+    // lane writes 16 bytes per store: narrow groups share a round between more lefts (config C5, ~300 pairs per left:
+    // 15.1 ms with a warp per left, EMIT_T16 / EMIT_T32 = average pairs per left from which 16 / 32 lanes take over)
+#ifndef EMIT_T16
+#define EMIT_T16 128ull
+#endif
+#ifndef EMIT_T32
+#define EMIT_T32 1024ull
+#endif
+    if (pairs > EMIT_T32 * (g_hi - g_lo))
         emit_tile<32>(sd, g_lo, g_hi, ls, ubv, ppv, lbv, offsets, pos);
+    else if (pairs > EMIT_T16 * (g_hi - g_lo))
+        emit_tile<16>(sd, g_lo, g_hi, ls, ubv, ppv, lbv, offsets, pos);
     else
         emit_tile<8>(sd, g_lo, g_hi, ls, ubv, ppv, lbv, offsets, pos);
 }
