@@ -305,20 +305,26 @@ int grb_merge_ranges(grb_ctx *ctx, const uint32_t *starts, const uint32_t *ends,
         // run offsets always come from the host
         TempBuf ro;
         if ((rc = ro.alloc(ctx, ((size_t)nruns + 1) * 8))) break;
-        cudaMemcpyAsync(ro.p, run_offsets, ((size_t)nruns + 1) * 8, cudaMemcpyHostToDevice, ctx->stream);
+        if (cudaMemcpyAsync(ro.p, run_offsets, ((size_t)nruns + 1) * 8, cudaMemcpyHostToDevice, ctx->stream) != cudaSuccess) {
+            rc = grb_fail(ctx, GRB_ERR_CUDA, "merge: %s", cudaGetErrorString(cudaGetLastError()));
+            break;
+        }
         TempBuf keys, flags, iend, pos, fl;
         if ((rc = keys.alloc(ctx, n * 8))) break;
         if ((rc = flags.alloc(ctx, n * 4))) break;
         if ((rc = iend.alloc(ctx, n * 4))) break;
         if ((rc = pos.alloc(ctx, (n + 1) * 8))) break;
         if ((rc = fl.alloc(ctx, sizeof(MergeFlags)))) break;
-        cudaMemsetAsync(fl.p, 0, sizeof(MergeFlags), ctx->stream);
+        if (cudaMemsetAsync(fl.p, 0, sizeof(MergeFlags), ctx->stream) != cudaSuccess) {
+            rc = grb_fail(ctx, GRB_ERR_CUDA, "merge: %s", cudaGetErrorString(cudaGetLastError()));
+            break;
+        }
         k_merge_keys<<<blocks_for(n, 256), 256, 0, ctx->stream>>>(d_s.as<u32>(), d_e.as<u32>(), ro.as<u64>(), nruns, n, keys.as<u64>(),
                                                                  fl.as<MergeFlags>());
         GRB_LAUNCHED_BREAK(ctx, rc)
         MergeFlags hf;
-        cudaMemcpyAsync(&hf, fl.p, sizeof(hf), cudaMemcpyDeviceToHost, ctx->stream);
-        if (cudaStreamSynchronize(ctx->stream) != cudaSuccess) {
+        if (cudaMemcpyAsync(&hf, fl.p, sizeof(hf), cudaMemcpyDeviceToHost, ctx->stream) != cudaSuccess ||
+            cudaStreamSynchronize(ctx->stream) != cudaSuccess) {
             rc = grb_fail(ctx, GRB_ERR_CUDA, "merge: %s", cudaGetErrorString(cudaGetLastError()));
             break;
         }

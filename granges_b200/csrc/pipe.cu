@@ -104,18 +104,6 @@ struct PipeDesc {      // one per window-ring slot (loader -> consumers)
     int seq;
 };
 
-#ifndef PIPE_CONS_PACK
-#define PIPE_CONS_PACK 0  // A/B switch: the consumers read their per-tile parameters as three 16-byte words written by the window loader
-#endif
-struct alignas(16) PipeCons {  // one per window-ring slot: everything a consumer needs to know about the tile
-    u32 a0, b0, la0, lb0;
-    u64 g_first;
-    u32 vlo_vhi;   // vlo | vhi << 16
-    u32 flags;     // bit 0 staged, bit 1 nf, bits 8..12 lut shift, bits 16.. seqname slot
-    double scale;
-    u32 bmax, fast_cmax;
-};
-
 template <int VAR>
 struct PipeSmemT {
     static constexpr int WST = (VAR & PIPE_VAR_WIDE) ? (PIPE_LSTAGES_N > 8 ? 2 : 3) : PIPE_WST_N;  // window-ring depth: what fits beside the extra planes
@@ -137,9 +125,6 @@ struct PipeSmemT {
     PipeSeq seq[PIPE_MAXSEQ];
     PipeTile tile[PIPE_LSTAGES];
     PipeDesc desc[WST];
-#if PIPE_CONS_PACK
-    PipeCons cons[WST];
-#endif
     alignas(8) u64 fullL[PIPE_LSTAGES];
     alignas(8) u64 emptyL[PIPE_LSTAGES];
     alignas(8) u64 statsL[PIPE_LSTAGES];
@@ -414,15 +399,6 @@ __global__ void __launch_bounds__(PIPE_THREADS, 1) k_map_pipe(const SeqDev *__re
                 d.lb0 = lb0;
                 d.staged = staged ? 1u : 0u;
                 d.nf = ti.nf;
-#if PIPE_CONS_PACK
-                PipeCons &pc = S.cons[sw];
-                pc.a0 = a0, pc.b0 = b0, pc.la0 = la0, pc.lb0 = lb0;
-                pc.g_first = ti.g_first;
-                pc.vlo_vhi = ti.vlo | (ti.vhi << 16);
-                pc.flags = (staged ? 1u : 0u) | (ti.nf ? 2u : 0u) | ((u32)q.sh << 8) | ((u32)ti.seq << 16);
-                pc.scale = q.scale;
-                pc.bmax = q.bmax, pc.fast_cmax = q.fast_cmax;
-#endif
                 if (staged)
                     mbar_arrive_expect_tx(&S.fullW[sw], total_bytes);
                 else
@@ -535,32 +511,12 @@ __global__ void __launch_bounds__(PIPE_THREADS, 1) k_map_pipe(const SeqDev *__re
             }
             continue;
         }
-#if PIPE_CONS_PACK
-        const uint4 c0 = *reinterpret_cast<const uint4 *>(&S.cons[sw]);
-        const uint4 c1 = *(reinterpret_cast<const uint4 *>(&S.cons[sw]) + 1);
-        const uint4 c2 = *(reinterpret_cast<const uint4 *>(&S.cons[sw]) + 2);
-        struct {
-            u64 g_first;
-            u32 staged, nf;
-            int seq;
-        } d;
-        d.g_first = ((u64)c1.y << 32) | c1.x;
-        d.staged = c1.w & 1u;
-        d.nf = (c1.w >> 1) & 1u;
-        d.seq = (int)(c1.w >> 16);
-        const PipeSeq &q = S.seq[d.seq];  // (only the rare paths and the NULLS variants read it)
-        const u32 vlo = c1.z & 0xffffu, vhi = c1.z >> 16;
-        const int sh = (int)((c1.w >> 8) & 31u);
-        const u32 bmax = c2.z, fast_cmax = c2.w;
-        const double scale = __hiloint2double((int)c2.y, (int)c2.x);
-#else
         const PipeDesc &d = S.desc[sw];
         const PipeSeq &q = S.seq[d.seq];
         const u32 vlo = d.vlo, vhi = d.vhi;
         const int sh = q.sh;
         const u32 bmax = q.bmax, fast_cmax = q.fast_cmax;
         const double scale = q.scale;
-#endif
         const uint4 *__restrict__ nf_a = q.nf_a, *__restrict__ nf_b = q.nf_b;
         const bool tile_nf = NULLS && nf_a != nullptr && d.nf != 0;
         u32 a[PIPE_LPT], b[PIPE_LPT];
@@ -575,11 +531,7 @@ __global__ void __launch_bounds__(PIPE_THREADS, 1) k_map_pipe(const SeqDev *__re
         for (int k = 0; k < PIPE_LPT; k++) okv[k] = i0 + k >= vlo && i0 + k < vhi;
         // (A left with end <= start or end > 2^31-1 -- impossible in the reference, which panics -- was flagged by
         // the surveyor, which also keeps its tile off the staged path.)
-#if PIPE_CONS_PACK
-        const u32 a0 = c0.x, b0 = c0.y, la0 = c0.z, lb0 = c0.w;
-#else
         const u32 a0 = d.a0, b0 = d.b0, la0 = d.la0, lb0 = d.lb0;
-#endif
         const SeqDev *__restrict__ sd = &seqs[d.seq];  // only dereferenced on the rare paths
         u32 ub[PIPE_LPT], lbk[PIPE_LPT], ppk[PIPE_LPT];  // absolute positions
         u64 pa[PIPE_LPT], pb[PIPE_LPT];
