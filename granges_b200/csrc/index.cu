@@ -245,16 +245,10 @@ __global__ void k_gather_scores(const u32 *__restrict__ didx, size_t n, const do
     }
     // warp reduce stats
     u32 nnull = __popc(__ballot_sync(GRB_FULL, in && !ok));
-#pragma unroll
-    for (int s = 16; s; s >>= 1) {
-        lsb = min(lsb, __shfl_xor_sync(GRB_FULL, lsb, s));
-        top = max(top, __shfl_xor_sync(GRB_FULL, top, s));
-        nonfinite |= __shfl_xor_sync(GRB_FULL, nonfinite, s);
-        nan |= __shfl_xor_sync(GRB_FULL, nan, s);
-        sub |= __shfl_xor_sync(GRB_FULL, sub, s);
-        oor |= __shfl_xor_sync(GRB_FULL, oor, s);
-        nz |= __shfl_xor_sync(GRB_FULL, nz, s);
-    }
+    // (REDUX: three instructions per warp instead of seven shuffle trees)
+    lsb = __reduce_min_sync(GRB_FULL, lsb);
+    top = __reduce_max_sync(GRB_FULL, top);
+    const u32 wflags = __reduce_or_sync(GRB_FULL, nonfinite | (nan << 1) | (sub << 2) | (oor << 3) | (nz << 4));
     // block reduce, then one set of atomics per block
     __shared__ int s_lsb[8], s_top[8];
     __shared__ u32 s_flags[8], s_null[8];
@@ -262,7 +256,7 @@ __global__ void k_gather_scores(const u32 *__restrict__ didx, size_t n, const do
     if (lane_id() == 0) {
         s_lsb[w] = lsb;
         s_top[w] = top;
-        s_flags[w] = nonfinite | (nan << 1) | (sub << 2) | (oor << 3) | (nz << 4);
+        s_flags[w] = wflags;
         s_null[w] = nnull;
     }
     __syncthreads();
@@ -299,13 +293,28 @@ __global__ void k_permute_u32(const u32 *__restrict__ src, const u32 *__restrict
 //   phase 1 (compact): pfx[p] = low 64 bits of base[b] + local exclusive prefix
 //   phase 2 (wide):    wide[p] = base[b] + local exclusive prefix (i128)
 //   phase 3 (wide96):  pfx[p] / pfh[p] = bits 0..63 / 64..95 of base[b] + local exclusive prefix
+// Both orders in one launch: blocks [0, nb) take the start order (side a, no permutation), blocks [nb, 2 nb) the end
+// order (side b, through perm_e) -- half the launches of a build's prefix passes, each twice as large.
+struct FxSide {
+    const u32 *perm;
+    i128 *blocksum;
+    const i128 *base;
+    u64 *pfx;
+    i128 *wide;
+    u32 *pfh;
+};
 template <int PHASE>
-__global__ void __launch_bounds__(256) k_fx_blocks(const double *__restrict__ score_a, const u32 *__restrict__ perm,
-                                                   size_t n, int e0, i128 *__restrict__ blocksum,
-                                                   const i128 *__restrict__ base, u64 *__restrict__ pfx,
-                                                   i128 *__restrict__ wide, u32 *__restrict__ pfh) {
+__global__ void __launch_bounds__(256) k_fx_blocks(const double *__restrict__ score_a, size_t n, int e0, size_t nb, const FxSide sa,
+                                                   const FxSide sb) {
     __shared__ u64 s_lo[8], s_hi[8];
-    const size_t b = blockIdx.x;
+    const bool second = blockIdx.x >= nb;
+    const size_t b = second ? blockIdx.x - nb : blockIdx.x;
+    const u32 *__restrict__ perm = second ? sb.perm : sa.perm;
+    i128 *__restrict__ blocksum = second ? sb.blocksum : sa.blocksum;
+    const i128 *__restrict__ base = second ? sb.base : sa.base;
+    u64 *__restrict__ pfx = second ? sb.pfx : sa.pfx;
+    i128 *__restrict__ wide = second ? sb.wide : sa.wide;
+    u32 *__restrict__ pfh = second ? sb.pfh : sa.pfh;
     const size_t p = (b << GRB_BASE_SHIFT) + threadIdx.x;
     i128 v = 0;
     if (p < n) v = to_fx(score_a[perm ? perm[p] : p], e0);
@@ -425,7 +434,11 @@ __global__ void k_masked_coords(const u32 *__restrict__ coord, const u32 *__rest
 }
 
 // Exclusive scan of nb i128 block sums by one CTA (nb = n/256 + 1: small).
-__global__ void __launch_bounds__(1024) k_scan_i128_single(const i128 *__restrict__ in, size_t nb, i128 *__restrict__ out) {
+__global__ void __launch_bounds__(1024) k_scan_i128_single(const i128 *__restrict__ in0, size_t nb, i128 *__restrict__ out0,
+                                                           const i128 *__restrict__ in1, i128 *__restrict__ out1) {
+    // (CTA 0 scans in0 -> out0; a second CTA, if launched, in1 -> out1)
+    const i128 *__restrict__ in = blockIdx.x ? in1 : in0;
+    i128 *__restrict__ out = blockIdx.x ? out1 : out0;
     __shared__ u64 s_lo[32], s_hi[32];
     const size_t per = (nb + 1023) / 1024;
     const size_t lo = (size_t)threadIdx.x * per;
@@ -703,32 +716,46 @@ void free_scores(grb_index *ix) {
     ix->sum_mode = GRB_SUM_SWEEP;
 }
 
-int build_prefix(grb_ctx *ctx, grb_index *ix, const u32 *perm, u64 **pfx_out, u32 **pfh_out, i128 **base_out) {
+int build_prefix_both(grb_ctx *ctx, grb_index *ix) {
     const size_t n = ix->n;
     const size_t nb = (n >> GRB_BASE_SHIFT) + 1;
-    TempBuf bsum;
-    GRB_TRY(bsum.alloc(ctx, nb * sizeof(i128)));
-    k_fx_blocks<0><<<(unsigned)nb, 256, 0, ctx->stream>>>(ix->score_a, perm, n, ix->e0, bsum.as<i128>(), nullptr, nullptr, nullptr, nullptr);
+    TempBuf bsum, bbase;
+    GRB_TRY(bsum.alloc(ctx, 2 * nb * sizeof(i128)));
+    FxSide a, b;
+    memset(&a, 0, sizeof(a));
+    memset(&b, 0, sizeof(b));
+    b.perm = ix->perm_e;
+    a.blocksum = bsum.as<i128>();
+    b.blocksum = bsum.as<i128>() + nb;
+    k_fx_blocks<0><<<(unsigned)(2 * nb), 256, 0, ctx->stream>>>(ix->score_a, n, ix->e0, nb, a, b);
     GRB_LAUNCHED(ctx);
     if (ix->sum_mode == GRB_SUM_COMPACT || ix->sum_mode == GRB_SUM_WIDE96) {
-        GRB_TRY(dev_alloc(ctx, (void **)base_out, nb * sizeof(i128)));
-        GRB_TRY(dev_alloc(ctx, (void **)pfx_out, (n + 1 + PAD) * sizeof(u64)));  // padded: bulk copies round up to 16 B
-        k_scan_i128_single<<<1, 1024, 0, ctx->stream>>>(bsum.as<i128>(), nb, *base_out);
+        GRB_TRY(dev_alloc(ctx, (void **)&ix->base_a, nb * sizeof(i128)));
+        GRB_TRY(dev_alloc(ctx, (void **)&ix->base_b, nb * sizeof(i128)));
+        GRB_TRY(dev_alloc(ctx, (void **)&ix->pfx_a, (n + 1 + PAD) * sizeof(u64)));  // padded: bulk copies round up to 16 B
+        GRB_TRY(dev_alloc(ctx, (void **)&ix->pfx_b, (n + 1 + PAD) * sizeof(u64)));
+        k_scan_i128_single<<<2, 1024, 0, ctx->stream>>>(a.blocksum, nb, ix->base_a, b.blocksum, ix->base_b);
         GRB_LAUNCHED(ctx);
+        a.base = ix->base_a, b.base = ix->base_b;
+        a.pfx = ix->pfx_a, b.pfx = ix->pfx_b;
         if (ix->sum_mode == GRB_SUM_COMPACT) {
-            k_fx_blocks<1><<<(unsigned)nb, 256, 0, ctx->stream>>>(ix->score_a, perm, n, ix->e0, nullptr, *base_out, *pfx_out, nullptr, nullptr);
+            k_fx_blocks<1><<<(unsigned)(2 * nb), 256, 0, ctx->stream>>>(ix->score_a, n, ix->e0, nb, a, b);
         } else {
-            GRB_TRY(dev_alloc(ctx, (void **)pfh_out, (n + 1 + PAD) * sizeof(u32)));
-            k_fx_blocks<3><<<(unsigned)nb, 256, 0, ctx->stream>>>(ix->score_a, perm, n, ix->e0, nullptr, *base_out, *pfx_out, nullptr, *pfh_out);
+            GRB_TRY(dev_alloc(ctx, (void **)&ix->pfh_a, (n + 1 + PAD) * sizeof(u32)));
+            GRB_TRY(dev_alloc(ctx, (void **)&ix->pfh_b, (n + 1 + PAD) * sizeof(u32)));
+            a.pfh = ix->pfh_a, b.pfh = ix->pfh_b;
+            k_fx_blocks<3><<<(unsigned)(2 * nb), 256, 0, ctx->stream>>>(ix->score_a, n, ix->e0, nb, a, b);
         }
         GRB_LAUNCHED(ctx);
     } else {
-        TempBuf bbase;
-        GRB_TRY(bbase.alloc(ctx, nb * sizeof(i128)));
-        GRB_TRY(dev_alloc(ctx, (void **)base_out, (n + 1) * sizeof(i128)));
-        k_scan_i128_single<<<1, 1024, 0, ctx->stream>>>(bsum.as<i128>(), nb, bbase.as<i128>());
+        GRB_TRY(bbase.alloc(ctx, 2 * nb * sizeof(i128)));
+        GRB_TRY(dev_alloc(ctx, (void **)&ix->base_a, (n + 1) * sizeof(i128)));
+        GRB_TRY(dev_alloc(ctx, (void **)&ix->base_b, (n + 1) * sizeof(i128)));
+        k_scan_i128_single<<<2, 1024, 0, ctx->stream>>>(a.blocksum, nb, bbase.as<i128>(), b.blocksum, bbase.as<i128>() + nb);
         GRB_LAUNCHED(ctx);
-        k_fx_blocks<2><<<(unsigned)nb, 256, 0, ctx->stream>>>(ix->score_a, perm, n, ix->e0, nullptr, bbase.as<i128>(), nullptr, *base_out, nullptr);
+        a.base = bbase.as<i128>(), b.base = bbase.as<i128>() + nb;
+        a.wide = ix->base_a, b.wide = ix->base_b;
+        k_fx_blocks<2><<<(unsigned)(2 * nb), 256, 0, ctx->stream>>>(ix->score_a, n, ix->e0, nb, a, b);
         GRB_LAUNCHED(ctx);
     }
     return GRB_OK;
@@ -1028,8 +1055,7 @@ int grb_index_set_scores(grb_index *ix, const double *by_data_idx, const uint8_t
         }
     }
     if (ix->sum_mode != GRB_SUM_SWEEP) {
-        GRB_TRY(build_prefix(ctx, ix, nullptr, &ix->pfx_a, &ix->pfh_a, &ix->base_a));
-        GRB_TRY(build_prefix(ctx, ix, ix->perm_e, &ix->pfx_b, &ix->pfh_b, &ix->base_b));
+        GRB_TRY(build_prefix_both(ctx, ix));
         if (ix->has_nonfinite && n) {
             GRB_TRY(build_nf(ctx, ix, nullptr, &ix->nf_a));
             GRB_TRY(build_nf(ctx, ix, ix->perm_e, &ix->nf_b));
@@ -1227,7 +1253,7 @@ static int build_wprefix(grb_ctx *ctx, grb_index *ix, const u32 *perm, const u32
     GRB_TRY(dev_alloc(ctx, (void **)out, (n + 1) * sizeof(i128)));
     k_wfx_blocks<0><<<(unsigned)nb, 256, 0, ctx->stream>>>(ix->score_a, perm, coord, n, ix->e0, bsum.as<i128>(), nullptr, nullptr);
     GRB_LAUNCHED(ctx);
-    k_scan_i128_single<<<1, 1024, 0, ctx->stream>>>(bsum.as<i128>(), nb, bbase.as<i128>());
+    k_scan_i128_single<<<1, 1024, 0, ctx->stream>>>(bsum.as<i128>(), nb, bbase.as<i128>(), nullptr, nullptr);
     GRB_LAUNCHED(ctx);
     k_wfx_blocks<2><<<(unsigned)nb, 256, 0, ctx->stream>>>(ix->score_a, perm, coord, n, ix->e0, nullptr, bbase.as<i128>(), *out);
     GRB_LAUNCHED(ctx);
