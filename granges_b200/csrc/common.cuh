@@ -45,6 +45,7 @@ struct grb_ctx {
     //   [16 + b] tiles CTA b of a pipelined launch could not stage, [1] that launch's generation (written by CTA 0).
     u32 *stats_host;
     u32 *stats_dev;
+    int ctl_slot;   // which 256-byte slot of the control area (words 1024.. of the mapped block) grb_read_small uses: 0, or 1 + worker for clones
     const void *hist_ls;  // AUTO on device buffers: the lefts of the previous call ...
     u64 hist_first, hist_total;
     u32 hist_tiles;
@@ -157,6 +158,10 @@ bool grb_is_pageable_ptr(const void *p);
 // (pageable) or when the copy is enqueued (page-locked).
 int grb_h2d_staged(grb_ctx *ctx, cudaStream_t stream, void *dst_dev, const void *src_host, size_t bytes);
 int grb_d2h_staged(grb_ctx *ctx, cudaStream_t stream, void *dst_host, const void *src_dev, size_t bytes);
+// A few words of device memory -> host, now: a one-warp kernel stores them into the context's mapped page-locked block and the
+// stream is synchronised.  Not a cudaMemcpy: a small device-to-host copy queues behind every bulk download that is in flight
+// on the copy engine (results of earlier seqnames travelling back), and the index build that waits for it stalls for milliseconds.
+int grb_read_small(grb_ctx *ctx, void *dst_host, const void *src_dev, size_t bytes);
 // Read-and-clear the device flag word after a synchronisation; turns a flagged invalid left range into
 // GRB_ERR_INVALID_RANGE (the reference cannot even construct such a range: src/ranges/mod.rs:30, coitrees.rs:53-54).
 int grb_check_flags(grb_ctx *ctx);

@@ -193,6 +193,25 @@ int OutBuf::finish(grb_ctx *ctx) {
     return GRB_OK;
 }
 
+__global__ void k_copy_words(u32 *__restrict__ dst, const u32 *__restrict__ src, u32 nwords) {
+    for (u32 i = threadIdx.x; i < nwords; i += blockDim.x) dst[i] = src[i];
+    __threadfence_system();
+}
+
+int grb_read_small(grb_ctx *ctx, void *dst_host, const void *src_dev, size_t bytes) {
+    if (bytes > 256 || !ctx->stats_host || ctx->ctl_slot < 0 || ctx->ctl_slot > 15) {
+        GRB_CUDA(ctx, cudaMemcpyAsync(dst_host, src_dev, bytes, cudaMemcpyDeviceToHost, ctx->stream));
+        GRB_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+        return GRB_OK;
+    }
+    const size_t off = 1024 + 64 * (size_t)ctx->ctl_slot;
+    k_copy_words<<<1, 64, 0, ctx->stream>>>(ctx->stats_dev + off, (const u32 *)src_dev, (u32)((bytes + 3) / 4));
+    GRB_LAUNCHED(ctx);
+    GRB_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+    memcpy(dst_host, ctx->stats_host + off, bytes);
+    return GRB_OK;
+}
+
 int grb_check_flags(grb_ctx *ctx) {
     u32 f = 0;
     GRB_CUDA(ctx, cudaMemcpyAsync(&f, ctx->dev_flags, 4, cudaMemcpyDeviceToHost, ctx->stream));
@@ -272,12 +291,12 @@ int grb_ctx_create(int device, grb_ctx **out) {
         return GRB_ERR_OOM;
     }
     // mapped pinned words: kernels report to the host without any stream operation (see grb_ctx::stats_host)
-    if (cudaHostAlloc((void **)&ctx->stats_host, 1024 * 4, cudaHostAllocMapped) != cudaSuccess ||
+    if (cudaHostAlloc((void **)&ctx->stats_host, 2048 * 4, cudaHostAllocMapped) != cudaSuccess ||
         cudaHostGetDevicePointer((void **)&ctx->stats_dev, ctx->stats_host, 0) != cudaSuccess) {
         cudaGetLastError();
         ctx->stats_host = ctx->stats_dev = nullptr;  // order detection on device buffers is simply off
     } else {
-        memset(ctx->stats_host, 0, 1024 * 4);
+        memset(ctx->stats_host, 0, 2048 * 4);
     }
     const char *lo = getenv("GRB_LEFT_ORDER");
     ctx->left_order = lo ? atoi(lo) : GRB_LEFT_ORDER_AUTO;

@@ -846,11 +846,7 @@ int grb_index_build(grb_ctx *ctx, const uint32_t *starts, const uint32_t *ends, 
         }
         if ((rc = grb_sort_pairs(ctx, k0.as<u64>(), v0.as<u32>(), k1.as<u64>(), v1.as<u32>(), n, &ks, &vs, nullptr))) break;
         BuildFlags hf;
-        cudaMemcpyAsync(&hf, fl.p, sizeof(hf), cudaMemcpyDeviceToHost, ctx->stream);
-        if (cudaStreamSynchronize(ctx->stream) != cudaSuccess) {
-            rc = grb_fail(ctx, GRB_ERR_CUDA, "index_build: %s", cudaGetErrorString(cudaGetLastError()));
-            break;
-        }
+        if ((rc = grb_read_small(ctx, &hf, fl.p, sizeof(hf)))) break;
         if (hf.invalid_range) {
             rc = grb_fail(ctx, GRB_ERR_INVALID_RANGE,
                           "index_build: a range has end <= start or end > 2^31-1 (the reference panics: "
@@ -910,19 +906,14 @@ int grb_index_build(grb_ctx *ctx, const uint32_t *starts, const uint32_t *ends, 
             k_block_max_end<<<blocks_for(nbw * 32, 256), 256, 0, ctx->stream>>>(ix->ends, n, ix->bme);
             GRB_LAUNCHED_BREAK(ctx, rc)
         }
-        cudaMemcpyAsync(&hf, fl.p, sizeof(hf), cudaMemcpyDeviceToHost, ctx->stream);
-        cudaError_t e = cudaStreamSynchronize(ctx->stream);
-        if (e != cudaSuccess) {
-            rc = grb_fail(ctx, GRB_ERR_CUDA, "index_build: %s", cudaGetErrorString(e));
-            break;
-        }
+        if ((rc = grb_read_small(ctx, &hf, fl.p, sizeof(hf)))) break;
         if (hf.heavy_bin) {
             // a coordinate bin with hundreds of ends (e.g. thousands of rights ending on one base): the stable radix sort
             // gives the same (end, position) order
             u64 *k2 = (ks == k0.as<u64>()) ? k1.as<u64>() : k0.as<u64>();
             u32 *v2 = (vs == v0.as<u32>()) ? v1.as<u32>() : v0.as<u32>();
             if ((rc = grb_argsort_u32(ctx, ix->ends, ix->ends_sorted, ix->perm_e, (u32 *)k2, v2, n))) break;
-            e = cudaStreamSynchronize(ctx->stream);
+            const cudaError_t e = cudaStreamSynchronize(ctx->stream);
             if (e != cudaSuccess) {
                 rc = grb_fail(ctx, GRB_ERR_CUDA, "index_build: %s", cudaGetErrorString(e));
                 break;
@@ -991,8 +982,7 @@ int grb_index_set_scores(grb_index *ix, const double *by_data_idx, const uint8_t
         GRB_LAUNCHED(ctx);
     }
     ScoreStats st;
-    GRB_CUDA(ctx, cudaMemcpyAsync(&st, stb.p, sizeof(st), cudaMemcpyDeviceToHost, ctx->stream));
-    GRB_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+    GRB_TRY(grb_read_small(ctx, &st, stb.p, sizeof(st)));
     if (st.idx_out_of_range) {
         free_scores(ix);
         return grb_fail(ctx, GRB_ERR_INDEX_RANGE, "set_scores: a right range's data index is >= n_data (%zu)", n_data);
@@ -1082,6 +1072,7 @@ int grb_index_build_batch(grb_ctx *ctx, int nseq, const uint32_t *const *starts,
     std::vector<int> rcs((size_t)nworkers, GRB_OK);
     for (int w = 0; w < nworkers; w++) {
         clones[w] = *ctx;  // shares the device, the pool and the zero / flag words
+        clones[w].ctl_slot = w + 1;
         clones[w].batch_dev = nullptr;
         clones[w].batch_host = nullptr;
         clones[w].batch_bytes = clones[w].batch_cap = 0;

@@ -171,8 +171,7 @@ int sort_into(grb_ctx *ctx, const K *in_keys, const u32 *vals_in, K *dst_k, u32 
     k_key_stats<K><<<grid, 256, 0, ctx->stream>>>(in_keys, n, stb.as<KeyStats>());
     GRB_LAUNCHED(ctx);
     KeyStats st;
-    GRB_CUDA(ctx, cudaMemcpyAsync(&st, stb.p, sizeof(st), cudaMemcpyDeviceToHost, ctx->stream));
-    GRB_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+    GRB_TRY(grb_read_small(ctx, &st, stb.p, sizeof(st)));
     const u64 varying = st.or_all ^ st.and_all;
     int shifts[8], npass = 0;
     if (st.unsorted)

@@ -115,6 +115,7 @@ extern "C" int grb_map_joins_whole_f64(grb_ctx *ctx, int nseq, const uint32_t *c
     std::vector<int> rcs((size_t)nworkers, GRB_OK);
     for (int w = 0; w < nworkers; w++) {
         clones[w] = *ctx;  // shares the device, the pool and the zero / flag words
+        clones[w].ctl_slot = w + 1;
         clones[w].batch_dev = nullptr;
         clones[w].batch_host = nullptr;
         clones[w].batch_bytes = clones[w].batch_cap = 0;
