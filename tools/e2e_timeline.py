@@ -25,3 +25,8 @@ for _ in range(3):
     torch.cuda.synchronize(); t0 = time.perf_counter(); run(); torch.cuda.synchronize(); print("ms", (time.perf_counter() - t0) * 1e3, flush=True)
 os.environ["GRB_TIMING"] = "1"
 run()
+# raw link rate of this process, for reference: 1 GiB page-locked -> device, three times
+x = torch.empty(1 << 30, dtype=torch.uint8).pin_memory(); y = torch.empty(1 << 30, dtype=torch.uint8, device=dev)
+for _ in range(3):
+    torch.cuda.synchronize(); t0 = time.perf_counter(); y.copy_(x, non_blocking=True); torch.cuda.synchronize()
+    print("raw H2D GB/s", round((1 << 30) / (time.perf_counter() - t0) / 1e9, 1), flush=True)
