@@ -166,10 +166,21 @@ extern "C" int grb_map_joins_whole_f64(grb_ctx *ctx, int nseq, const uint32_t *c
                         t_up = now_ms();
                     }
                     if (rc == GRB_OK && r_n[s]) {
-                        rc = grb_index_build(c, r_starts[s], r_ends[s], nullptr, r_n[s], &idx[s]);
+                        // the scores start travelling before the index build: its kernels and its host round trips then run
+                        // beside a copy that is already queued, and the link does not idle while this worker waits for them
+                        TempBuf d_sc, d_va;
+                        const bool have_sc = r_scores && r_scores[s];
+                        const bool have_va = have_sc && r_valid && r_valid[s];
+                        if (have_sc) {
+                            rc = d_sc.alloc(c, r_n[s] * 8);
+                            if (rc == GRB_OK) rc = grb_h2d_staged(c, c->stream, d_sc.p, r_scores[s], r_n[s] * 8);
+                            if (rc == GRB_OK && have_va) rc = d_va.alloc(c, r_n[s]);
+                            if (rc == GRB_OK && have_va) rc = grb_h2d_staged(c, c->stream, d_va.p, r_valid[s], r_n[s]);
+                        }
+                        if (rc == GRB_OK) rc = grb_index_build(c, r_starts[s], r_ends[s], nullptr, r_n[s], &idx[s]);
                         t_ix = now_ms();
-                        if (rc == GRB_OK && r_scores && r_scores[s])
-                            rc = grb_index_set_scores(idx[s], r_scores[s], (r_valid && r_valid[s]) ? r_valid[s] : nullptr, r_n[s]);
+                        if (rc == GRB_OK && have_sc)
+                            rc = grb_index_set_scores(idx[s], d_sc.as<double>(), have_va ? d_va.as<u8>() : nullptr, r_n[s]);
                         if (rc == GRB_OK) idx[s]->ctx = ctx;  // the clone goes away; the index is used on the caller's context
                     }
                     if (rc == GRB_OK && cudaStreamSynchronize(c->stream) != cudaSuccess) rc = grb_fail(c, GRB_ERR_CUDA, "map_joins_whole: upload failed");
