@@ -796,6 +796,20 @@ def main():
             ixw.close()
             del rs, re, sc
 
+    # ... and all of them through grb_index_build_batch (four host threads with private streams), second of two passes
+    t_build_batch = None
+    if world == 1 and not args.no_configs and t_build_warm:
+        rights_all = [gen_ranges(p["seq"], nr_per[p["seq"]], 14, dev, True) for p in mine]
+        for rep in range(2):
+            torch.cuda.synchronize()
+            t0 = time.perf_counter()
+            ixs = ctx.index_build_batch(rights_all)
+            ctx.sync()
+            t_build_batch = time.perf_counter() - t0
+            for ixw in ixs:
+                ixw.close()
+        del rights_all, ixs
+
     # keep one seqname's device-timed results for the parity check against the oracle below
     chk_seq = pick_sample_seqs(nl_per, nr_per)[0][0]
     chk_slice = None
@@ -905,6 +919,7 @@ def main():
         "dtype": "f64", "data": "synthetic", "config": workload_config(args),
         "pairs_per_s": pairs_total / (ms_per_step * 1e-3), "overlap_pairs": pairs_total, "lefts_processed": nl_total,
         "index_build_ms_rank0": t_build * 1e3, "index_build_warm_ms_rank0": (t_build_warm * 1e3 if t_build_warm else None),
+        "index_build_batch_ms_rank0": (t_build_batch * 1e3 if t_build_batch else None),
         "gpu_launches": int(launches), "clocks": clocks,
         "step_ms_rank0": {"min": min(per_step), "median": float(np.median(per_step)), "max": max(per_step)},
         "units_rank0": len(mine), "cpus_bound_rank0": numa, "step_ms_per_rank": per_rank_ms,
