@@ -673,7 +673,10 @@ def main():
 
     # cost of a seqname = lefts + rights, plus its expected pairs when a reduction has to visit the members
     # (min / max / median / weighted mean): pairs = NL * NR * (mean left length + mean right length) / seqname length
-    cost_per = [int(c) for c in nr_per]
+    # (prefix-sum path: a tile of 1024 lefts also stages the rights its windows reach back over -- ~1000 bp worth, i.e.
+    # 1000 * rights / seqname length per tile: 2 % of a tile's rights on chr1, 10 % on chr21 -- measured as the spread of the
+    # per-rank step times at N = 8 with the plain lefts + rights cost)
+    cost_per = [int(nr_per[s] + (nl_per[s] / 1024.0) * 1000.0 * nr_per[s] / HG38[s]) for s in range(22)]
     if any(o in ("min", "max", "median", "weighted-mean") for o in ops):
         cost_per = [int(nr_per[s] + sharding.PAIR_WEIGHT * nl_per[s] * nr_per[s] * 1000.0 / HG38[s]) for s in range(22)]
     # (development knob: time the share rank R of a W-rank run would get, on one GPU, without launching W processes)
