@@ -677,8 +677,13 @@ def main():
     # 1000 * rights / seqname length per tile: 2 % of a tile's rights on chr1, 10 % on chr21 -- measured as the spread of the
     # per-rank step times at N = 8 with the plain lefts + rights cost)
     cost_per = [int(nr_per[s] + (nl_per[s] / 1024.0) * 1000.0 * nr_per[s] / HG38[s]) for s in range(22)]
-    if any(o in ("min", "max", "median", "weighted-mean") for o in ops):
-        cost_per = [int(nr_per[s] + sharding.PAIR_WEIGHT * nl_per[s] * nr_per[s] * 1000.0 / HG38[s]) for s in range(22)]
+    # (round 1 added PAIR_WEIGHT * expected pairs for min / max / median: the member sweep's cost grew with the group sizes.  The
+    # wavelet runs, the stabbing tables and the closed forms of round 2 cost the same per left whatever the coverage, so dense
+    # lefts over dense rights -- this job -- are planned like the prefix-sum path; the weight remains for sparse lefts, where
+    # the sweep still answers: GRB_BENCH_PAIR_WEIGHT)
+    pair_weight = float(os.environ.get("GRB_BENCH_PAIR_WEIGHT", "0"))
+    if pair_weight > 0 and any(o in ("min", "max", "median", "weighted-mean") for o in ops):
+        cost_per = [int(cost_per[s] + pair_weight * nl_per[s] * nr_per[s] * 1000.0 / HG38[s]) for s in range(22)]
     # (development knob: time the share rank R of a W-rank run would get, on one GPU, without launching W processes)
     plan_world, plan_rank = int(os.environ.get("GRB_BENCH_AS_WORLD", world)), int(os.environ.get("GRB_BENCH_AS_RANK", rank))
     plan = sharding.plan(left_off, cost_per, plan_world)
