@@ -357,31 +357,52 @@ __device__ __forceinline__ void emit_tile(const SeqDev *__restrict__ sd, u64 g_l
     const u64 g_warp = g_lo + (threadIdx.x >> 5) * (32 / G);
     const u32 rounds = g_warp < g_hi ? (u32)((g_hi - g_warp + NGROUPS - 1) / NGROUPS) : 0u;
     u64 g = g_lo + gidx;
-    // the next left's parameters are loaded while this one is written: one warp per left and ~1 KB of pairs per left make the
-    // kernel a chain of dependent round trips otherwise (3.8 TB/s of writes at config C5)
-    u32 nu = 0, np = 0, nl = 0, nls = 0;
-    u64 noff = 0;
-    if (g < g_hi) {
-        nu = ubv[g];
-        np = ppv[g];
-        nl = lbv[g];
-        nls = ls[g];
-        noff = offsets[g];
-    }
-    for (u32 round = 0; round < rounds; round++, g += NGROUPS) {
-        const bool live = g < g_hi;
-        const u32 u = nu, p = np, l = nl, lstart = nls;
-        u32 *__restrict__ dst = pos + noff;
-        nu = np = nl = nls = 0;
-        noff = 0;
-        if (g + NGROUPS < g_hi) {
-            nu = ubv[g + NGROUPS];
-            np = ppv[g + NGROUPS];
-            nl = lbv[g + NGROUPS];
-            nls = ls[g + NGROUPS];
-            noff = offsets[g + NGROUPS];
+    // Software pipeline, two lefts deep: while left i is written, the parameters of left i + 2 and the first straddler step of
+    // left i + 1 (its block maximum and G ends, addressed by parameters that arrived a round ago) are in flight.  One left per
+    // group and ~1 KB of pairs per left make the kernel a chain of dependent round trips otherwise: 43 % of its stall samples
+    // sat on the load of the ends (config C5).
+    auto first_step = [&](u32 p, u32 l, u32 &e0, u32 &bm0) {
+        e0 = bm0 = 0;
+        if (p > l && p) {
+            const u32 cb = (p - 1) & ~(u32)(G - 1);
+            const u32 j = cb + glane;
+            if (j < p) e0 = ends[j];
+            bm0 = bme[cb >> GRB_BME_SHIFT];
         }
-        (void)live;
+    };
+    u32 cu = 0, cp = 0, cl = 0, cls = 0, nu = 0, np = 0, nl = 0, nls = 0;
+    u64 coff = 0, noff = 0;
+    if (g < g_hi) {
+        cu = ubv[g];
+        cp = ppv[g];
+        cl = lbv[g];
+        cls = ls[g];
+        coff = offsets[g];
+    }
+    if (g + NGROUPS < g_hi) {
+        nu = ubv[g + NGROUPS];
+        np = ppv[g + NGROUPS];
+        nl = lbv[g + NGROUPS];
+        nls = ls[g + NGROUPS];
+        noff = offsets[g + NGROUPS];
+    }
+    u32 e0, bm0;
+    first_step(cp, cl, e0, bm0);
+    for (u32 round = 0; round < rounds; round++, g += NGROUPS) {
+        const u32 u = cu, p = cp, l = cl, lstart = cls;
+        u32 *__restrict__ dst = pos + coff;
+        // in flight during this round: parameters two lefts ahead, first straddler step one left ahead
+        u32 mu = 0, mp = 0, ml = 0, mls = 0;
+        u64 moff = 0;
+        if (g + 2 * NGROUPS < g_hi) {
+            mu = ubv[g + 2 * NGROUPS];
+            mp = ppv[g + 2 * NGROUPS];
+            ml = lbv[g + 2 * NGROUPS];
+            mls = ls[g + 2 * NGROUPS];
+            moff = offsets[g + 2 * NGROUPS];
+        }
+        u32 ne0, nbm0;
+        first_step(np, nl, ne0, nbm0);
         const u32 need = p - l;
         // [p, u) as an iota: a scalar head up to the next 16-byte boundary, 16-byte stores, a scalar tail
         {
@@ -399,14 +420,22 @@ __device__ __forceinline__ void emit_tile(const SeqDev *__restrict__ sd, u64 g_l
         }
         u32 found = 0;
         long long cb = p ? (long long)((p - 1) & ~(u32)(G - 1)) : -1;
+        bool first = true;
         while (true) {
             const bool act = found < need && cb >= 0;
             if (!__any_sync(GRB_FULL, act)) break;
-            // (the end is loaded beside the block maximum, not after it: one round trip per step instead of two)
             const u32 j = (u32)cb + glane;
-            const u32 e = act && j < p ? ends[j] : 0u;
-            const bool look = act && bme[cb >> GRB_BME_SHIFT] > lstart;
-            const bool hit = look && e > lstart;
+            u32 e, bm;
+            if (first) {  // (warp-uniform: every group of the warp is in its first step)
+                e = e0;
+                bm = bm0;
+                first = false;
+            } else {
+                e = act && j < p ? ends[j] : 0u;
+                bm = act ? bme[cb >> GRB_BME_SHIFT] : 0u;
+            }
+            const bool look = act && bm > lstart;
+            const bool hit = look && j < p && e > lstart;
             const u32 hm = (__ballot_sync(GRB_FULL, hit) >> gshift) & GM;
             if (hit) {
                 const u32 above = glane == G - 1 ? 0u : __popc(hm >> (glane + 1));
@@ -415,6 +444,9 @@ __device__ __forceinline__ void emit_tile(const SeqDev *__restrict__ sd, u64 g_l
             found += __popc(hm);
             if (act) cb = look ? cb - G : ((cb >> GRB_BME_SHIFT) << GRB_BME_SHIFT) - G;
         }
+        cu = nu, cp = np, cl = nl, cls = nls, coff = noff;
+        nu = mu, np = mp, nl = ml, nls = mls, noff = moff;
+        e0 = ne0, bm0 = nbm0;
     }
 }
 
