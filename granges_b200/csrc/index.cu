@@ -303,55 +303,91 @@ struct FxSide {
     i128 *wide;
     u32 *pfh;
 };
+// One WARP per block of 256 rights: lane l holds elements 8 l .. 8 l + 7 (64 contiguous bytes of scores and of prefixes per
+// lane), scans them in registers and joins one 128-bit warp scan -- an eighth of the shuffles of one element per thread.
 template <int PHASE>
 __global__ void __launch_bounds__(256) k_fx_blocks(const double *__restrict__ score_a, size_t n, int e0, size_t nb, const FxSide sa,
                                                    const FxSide sb) {
-    __shared__ u64 s_lo[8], s_hi[8];
-    const bool second = blockIdx.x >= nb;
-    const size_t b = second ? blockIdx.x - nb : blockIdx.x;
+    const size_t wid = (size_t)blockIdx.x * 8 + (threadIdx.x >> 5);  // warps [0, nb): side a, [nb, 2 nb): side b
+    if (wid >= 2 * nb) return;
+    const bool second = wid >= nb;
+    const size_t b = second ? wid - nb : wid;
     const u32 *__restrict__ perm = second ? sb.perm : sa.perm;
     i128 *__restrict__ blocksum = second ? sb.blocksum : sa.blocksum;
     const i128 *__restrict__ base = second ? sb.base : sa.base;
     u64 *__restrict__ pfx = second ? sb.pfx : sa.pfx;
     i128 *__restrict__ wide = second ? sb.wide : sa.wide;
     u32 *__restrict__ pfh = second ? sb.pfh : sa.pfh;
-    const size_t p = (b << GRB_BASE_SHIFT) + threadIdx.x;
-    i128 v = 0;
-    if (p < n) v = to_fx(score_a[perm ? perm[p] : p], e0);
-    // warp inclusive scan of i128 through its two halves
-    i128 incl = v;
-    const u32 lane = lane_id(), warp = threadIdx.x >> 5;
+    const u32 lane = lane_id();
+    const size_t p0 = (b << GRB_BASE_SHIFT) + (size_t)lane * 8;
+    // the lane's eight values, then their inclusive scan in place
+    i128 v[8];
+    if (p0 + 8 <= n) {
+        double x[8];
+        if (perm) {
+            const uint4 q0 = *reinterpret_cast<const uint4 *>(perm + p0), q1 = *reinterpret_cast<const uint4 *>(perm + p0 + 4);
+            const u32 idx[8] = {q0.x, q0.y, q0.z, q0.w, q1.x, q1.y, q1.z, q1.w};
+#pragma unroll
+            for (int r = 0; r < 8; r++) x[r] = score_a[idx[r]];
+        } else {
+#pragma unroll
+            for (int r = 0; r < 4; r++) {
+                const double2 d = *reinterpret_cast<const double2 *>(score_a + p0 + 2 * r);
+                x[2 * r] = d.x;
+                x[2 * r + 1] = d.y;
+            }
+        }
+#pragma unroll
+        for (int r = 0; r < 8; r++) v[r] = to_fx(x[r], e0);
+    } else {
+#pragma unroll
+        for (int r = 0; r < 8; r++) {
+            const size_t p = p0 + r;
+            v[r] = p < n ? to_fx(score_a[perm ? perm[p] : p], e0) : (i128)0;
+        }
+    }
+    i128 ex[8];  // exclusive prefixes inside the lane
+    i128 tot = 0;
+#pragma unroll
+    for (int r = 0; r < 8; r++) {
+        ex[r] = tot;
+        tot += v[r];
+    }
+    // warp inclusive scan of the lane totals through their two halves
+    i128 incl = tot;
 #pragma unroll
     for (int o = 1; o < 32; o <<= 1) {
-        u64 tlo = __shfl_up_sync(GRB_FULL, (u64)incl, o);
-        u64 thi = __shfl_up_sync(GRB_FULL, (u64)((u128)incl >> 64), o);
-        if (lane >= o) incl += (i128)(((u128)thi << 64) | tlo);
+        const u64 tlo = __shfl_up_sync(GRB_FULL, (u64)incl, o);
+        const u64 thi = __shfl_up_sync(GRB_FULL, (u64)((u128)incl >> 64), o);
+        if (lane >= (u32)o) incl += (i128)(((u128)thi << 64) | tlo);
     }
-    if (lane == 31) {
-        s_lo[warp] = (u64)incl;
-        s_hi[warp] = (u64)((u128)incl >> 64);
-    }
-    __syncthreads();
-    i128 woff = 0, total = 0;
-#pragma unroll
-    for (int w = 0; w < 8; w++) {
-        i128 t = (i128)(((u128)s_hi[w] << 64) | s_lo[w]);
-        if (w < (int)warp) woff += t;
-        total += t;
-    }
-    i128 excl = woff + incl - v;
     if (PHASE == 0) {
-        if (threadIdx.x == 0) blocksum[b] = total;
-    } else if (PHASE == 1) {
-        if (p <= n) pfx[p] = (u64)(u128)(base[b] + excl);
-    } else if (PHASE == 3) {
-        if (p <= n) {
-            const u128 t = (u128)(base[b] + excl);
-            pfx[p] = (u64)t;
-            pfh[p] = (u32)(t >> 64);
+        if (lane == 31) blocksum[b] = incl;
+        return;
+    }
+    const i128 off = base[b] + (incl - tot);
+    if (PHASE == 1) {
+        if (p0 + 8 <= n + 1) {
+#pragma unroll
+            for (int r = 0; r < 4; r++)
+                *reinterpret_cast<ulonglong2 *>(pfx + p0 + 2 * r) = make_ulonglong2((u64)(u128)(off + ex[2 * r]), (u64)(u128)(off + ex[2 * r + 1]));
+        } else {
+#pragma unroll
+            for (int r = 0; r < 8; r++)
+                if (p0 + r <= n) pfx[p0 + r] = (u64)(u128)(off + ex[r]);
         }
+    } else if (PHASE == 3) {
+#pragma unroll
+        for (int r = 0; r < 8; r++)
+            if (p0 + r <= n) {
+                const u128 t = (u128)(off + ex[r]);
+                pfx[p0 + r] = (u64)t;
+                pfh[p0 + r] = (u32)(t >> 64);
+            }
     } else {
-        if (p <= n) wide[p] = base[b] + excl;
+#pragma unroll
+        for (int r = 0; r < 8; r++)
+            if (p0 + r <= n) wide[p0 + r] = off + ex[r];
     }
 }
 
@@ -727,7 +763,7 @@ int build_prefix_both(grb_ctx *ctx, grb_index *ix) {
     b.perm = ix->perm_e;
     a.blocksum = bsum.as<i128>();
     b.blocksum = bsum.as<i128>() + nb;
-    k_fx_blocks<0><<<(unsigned)(2 * nb), 256, 0, ctx->stream>>>(ix->score_a, n, ix->e0, nb, a, b);
+    k_fx_blocks<0><<<(unsigned)((2 * nb + 7) / 8), 256, 0, ctx->stream>>>(ix->score_a, n, ix->e0, nb, a, b);
     GRB_LAUNCHED(ctx);
     if (ix->sum_mode == GRB_SUM_COMPACT || ix->sum_mode == GRB_SUM_WIDE96) {
         GRB_TRY(dev_alloc(ctx, (void **)&ix->base_a, nb * sizeof(i128)));
@@ -739,12 +775,12 @@ int build_prefix_both(grb_ctx *ctx, grb_index *ix) {
         a.base = ix->base_a, b.base = ix->base_b;
         a.pfx = ix->pfx_a, b.pfx = ix->pfx_b;
         if (ix->sum_mode == GRB_SUM_COMPACT) {
-            k_fx_blocks<1><<<(unsigned)(2 * nb), 256, 0, ctx->stream>>>(ix->score_a, n, ix->e0, nb, a, b);
+            k_fx_blocks<1><<<(unsigned)((2 * nb + 7) / 8), 256, 0, ctx->stream>>>(ix->score_a, n, ix->e0, nb, a, b);
         } else {
             GRB_TRY(dev_alloc(ctx, (void **)&ix->pfh_a, (n + 1 + PAD) * sizeof(u32)));
             GRB_TRY(dev_alloc(ctx, (void **)&ix->pfh_b, (n + 1 + PAD) * sizeof(u32)));
             a.pfh = ix->pfh_a, b.pfh = ix->pfh_b;
-            k_fx_blocks<3><<<(unsigned)(2 * nb), 256, 0, ctx->stream>>>(ix->score_a, n, ix->e0, nb, a, b);
+            k_fx_blocks<3><<<(unsigned)((2 * nb + 7) / 8), 256, 0, ctx->stream>>>(ix->score_a, n, ix->e0, nb, a, b);
         }
         GRB_LAUNCHED(ctx);
     } else {
@@ -755,7 +791,7 @@ int build_prefix_both(grb_ctx *ctx, grb_index *ix) {
         GRB_LAUNCHED(ctx);
         a.base = bbase.as<i128>(), b.base = bbase.as<i128>() + nb;
         a.wide = ix->base_a, b.wide = ix->base_b;
-        k_fx_blocks<2><<<(unsigned)(2 * nb), 256, 0, ctx->stream>>>(ix->score_a, n, ix->e0, nb, a, b);
+        k_fx_blocks<2><<<(unsigned)((2 * nb + 7) / 8), 256, 0, ctx->stream>>>(ix->score_a, n, ix->e0, nb, a, b);
         GRB_LAUNCHED(ctx);
     }
     return GRB_OK;
