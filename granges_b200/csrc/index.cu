@@ -202,53 +202,66 @@ struct ScoreStats {
     u32 n_nonzero;
 };
 
-__global__ void k_gather_scores(const u32 *__restrict__ didx, size_t n, const double *__restrict__ scores,
-                                const u8 *__restrict__ valid, u64 n_data, double *__restrict__ score_a,
-                                u32 *__restrict__ vbits_a, u32 *__restrict__ vflag_a, ScoreStats *st) {
-    size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
-    bool in = i < n;
-    bool ok = false;
-    double x = 0.0;
+// Four elements per thread (element (4 blockIdx + k) 256 + threadIdx: a warp still owns 32 consecutive positions per k, i.e. one
+// validity word): the index loads, then the score gathers, of all four are in flight together.
+__global__ void __launch_bounds__(256) k_gather_scores(const u32 *__restrict__ didx, size_t n, const double *__restrict__ scores,
+                                                       const u8 *__restrict__ valid, u64 n_data, double *__restrict__ score_a,
+                                                       u32 *__restrict__ vbits_a, u32 *__restrict__ vflag_a, ScoreStats *st) {
     int lsb = 1 << 30, top = -(1 << 30);
-    u32 nonfinite = 0, nan = 0, sub = 0, oor = 0, nz = 0;
-    if (in) {
-        u32 d = didx[i];
-        if ((u64)d >= n_data) {
-            oor = 1;
-        } else {
-            ok = valid ? valid[d] != 0 : true;
-            if (ok) x = scores[d];
-        }
-        score_a[i] = x;
-        if (ok) {
-            u64 b = (u64)__double_as_longlong(x);
-            int ex = (int)((b >> 52) & 0x7ff);
-            u64 frac = b & ((1ull << 52) - 1);
-            if (ex == 0x7ff) {
-                nonfinite = 1;
-                if (frac) nan = 1;
-            } else if (ex == 0) {
-                if (frac) sub = 1;
+    u32 flags = 0, nnull = 0;
+    size_t idx[4];
+    u32 d[4];
+    bool in[4], ok[4];
+    double x[4];
+#pragma unroll
+    for (int k = 0; k < 4; k++) {
+        idx[k] = ((size_t)blockIdx.x * 4 + k) * 256 + threadIdx.x;
+        in[k] = idx[k] < n;
+        d[k] = in[k] ? didx[idx[k]] : 0u;
+    }
+#pragma unroll
+    for (int k = 0; k < 4; k++) {
+        ok[k] = false;
+        x[k] = 0.0;
+        if (in[k]) {
+            if ((u64)d[k] >= n_data) {
+                flags |= 8u;
             } else {
-                u64 m = frac | (1ull << 52);
-                int tz = __ffsll((long long)m) - 1;
-                lsb = ex - 1075 + tz;
-                top = ex - 1023;
-                nz = 1;
+                ok[k] = valid ? valid[d[k]] != 0 : true;
+                if (ok[k]) x[k] = scores[d[k]];
             }
         }
     }
-    u32 okmask = __ballot_sync(GRB_FULL, ok);
-    if (in) {
-        if (vbits_a && lane_id() == 0) vbits_a[i >> 5] = okmask;
-        if (vflag_a) vflag_a[i] = ok ? 1u : 0u;
+#pragma unroll
+    for (int k = 0; k < 4; k++) {
+        if (in[k]) score_a[idx[k]] = x[k];
+        if (ok[k]) {
+            const u64 b = (u64)__double_as_longlong(x[k]);
+            const int ex = (int)((b >> 52) & 0x7ff);
+            const u64 frac = b & ((1ull << 52) - 1);
+            if (ex == 0x7ff) {
+                flags |= frac ? 3u : 1u;  // non-finite (and NaN)
+            } else if (ex == 0) {
+                if (frac) flags |= 4u;    // subnormal
+            } else {
+                const u64 m = frac | (1ull << 52);
+                const int tz = __ffsll((long long)m) - 1;
+                lsb = min(lsb, ex - 1075 + tz);
+                top = max(top, ex - 1023);
+                flags |= 16u;
+            }
+        }
+        const u32 okmask = __ballot_sync(GRB_FULL, ok[k]);
+        if (in[k]) {
+            if (vbits_a && lane_id() == 0) vbits_a[idx[k] >> 5] = okmask;
+            if (vflag_a) vflag_a[idx[k]] = ok[k] ? 1u : 0u;
+        }
+        nnull += __popc(__ballot_sync(GRB_FULL, in[k] && !ok[k]));
     }
-    // warp reduce stats
-    u32 nnull = __popc(__ballot_sync(GRB_FULL, in && !ok));
-    // (REDUX: three instructions per warp instead of seven shuffle trees)
+    // warp reduce stats (REDUX: three instructions per warp instead of seven shuffle trees)
     lsb = __reduce_min_sync(GRB_FULL, lsb);
     top = __reduce_max_sync(GRB_FULL, top);
-    const u32 wflags = __reduce_or_sync(GRB_FULL, nonfinite | (nan << 1) | (sub << 2) | (oor << 3) | (nz << 4));
+    const u32 wflags = __reduce_or_sync(GRB_FULL, flags);
     // block reduce, then one set of atomics per block
     __shared__ int s_lsb[8], s_top[8];
     __shared__ u32 s_flags[8], s_null[8];
@@ -1012,7 +1025,7 @@ int grb_index_set_scores(grb_index *ix, const double *by_data_idx, const uint8_t
         GRB_TRY(vflag_a.alloc(ctx, n * 4));
     }
     if (n) {
-        k_gather_scores<<<blocks_for(n, 256), 256, 0, ctx->stream>>>(ix->didx, n, d_scores.as<double>(), d_valid.as<u8>(), n_data,
+        k_gather_scores<<<blocks_for(n, 1024), 256, 0, ctx->stream>>>(ix->didx, n, d_scores.as<double>(), d_valid.as<u8>(), n_data,
                                                                     ix->score_a, ix->vbits_a, valid ? vflag_a.as<u32>() : nullptr,
                                                                     stb.as<ScoreStats>());
         GRB_LAUNCHED(ctx);
