@@ -1,5 +1,8 @@
-// sweep3.cuh -- staged member sweep: MIN / MAX / MEDIAN over score *ranks*.  Included by query.cu.
+// sweep3.cuh -- MIN / MAX / MEDIAN over score *ranks* (src/data/operations.rs:17-32,71-98): per run of lefts either wavelet
+// trees over the staged slice (the median as an order statistic of a prefix difference: "wavelet runs" below, round 2) or the
+// staged member sweep (round 1; sparse lefts over dense rights, unsorted lefts).  Included by query.cu.
 //
+// The member sweep:
 // Same group structure as sweep.cuh (k_tile<M_UBLB> has resolved ub, pp, lb per left; the members are
 // [pp, ub) plus pp - lb straddlers below pp), but
 //   * a CTA stages the slice of `ends`, `rank_a` and `bme` its lefts can touch into shared memory with
@@ -8,7 +11,7 @@
 //     how far back a straddler can sit, and ends at the largest ub.  A run of lefts whose slice does not
 //     fit is halved until it does; below 32 lefts the groups walk global memory instead (same code);
 //   * the members' scores are replaced by their ranks (32-bit, all different): MIN / MAX are integer
-//     min / max, the median is a quickselect over 32-bit keys, and only the answers are translated back
+//     min / max, the median is a sorting network over 32-bit keys, and only the answers are translated back
 //     through score_sorted[] -- by loads that are issued one left ahead of the stores that need them.
 // Used when every index of the batch has its member tables, there are at most 8 reductions and no non-finite score (MIN / MAX skip
 // those: src/data/operations.rs:71-86); k_sweep2 keeps the overlap-width reductions and the rest.
