@@ -1101,7 +1101,9 @@ int grb_index_build_batch(grb_ctx *ctx, int nseq, const uint32_t *const *starts,
     for (int s = 0; s < nseq; s++) out[s] = nullptr;
     if (nseq == 0) return GRB_OK;
     GRB_CUDA(ctx, cudaStreamSynchronize(ctx->stream));  // earlier work on the caller's stream precedes the workers'
-    const int nworkers = nseq < 4 ? nseq : 4;
+    int wmax = 4;  // GRB_BUILD_WORKERS: host threads (private streams) of a batched build
+    if (const char *bw = getenv("GRB_BUILD_WORKERS")) wmax = atoi(bw) > 0 && atoi(bw) <= 15 ? atoi(bw) : 4;
+    const int nworkers = nseq < wmax ? nseq : wmax;
     std::vector<grb_ctx> clones((size_t)nworkers);
     std::vector<int> rcs((size_t)nworkers, GRB_OK);
     for (int w = 0; w < nworkers; w++) {
